@@ -1,0 +1,182 @@
+"""Synthetic inputs for the BASELINE.json configs and for the reference's
+self-contained multigroup regression tests (the known-answer tests that pin the
+path without a nuclear-data download).
+
+Each builder returns ``(Model, library, source_box, only_fissionable)``; the numbers are the
+literal inputs of the cited reference files.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .mgxs import MGXSLibrary, XSdata
+from .model import Filter, Mesh, Model, Tally
+
+
+# ----------------------------------------------------------------------------
+# tests/regression_tests/mg_*/test.py : 2-group slab library
+# ----------------------------------------------------------------------------
+def slab_2g_library(order=1, names=("mat_1",)):
+    """create_library() of tests/regression_tests/mg_legendre/test.py:12-41
+    (order=1) and mg_max_order/test.py:12-41 (order=2)."""
+    lib = MGXSLibrary([0.0, 0.625, 20.0e6])
+    nu = [2.50, 2.50]
+    fiss = np.array([0.002817, 0.097])
+    capture = [0.008708, 0.02518]
+    absorption = np.add(capture, fiss)
+    if order == 1:
+        scatter = np.array([[[0.31980, 0.06694], [0.004555, -0.0003972]],
+                            [[0.00000, 0.00000], [0.424100, 0.05439000]]])
+    else:
+        scatter = np.array([[[0.31980, 0.06694, 0.003], [0.004555, -0.0003972, 0.00002]],
+                            [[0.00000, 0.00000, 0.000], [0.424100, 0.05439000, 0.0025]]])
+    total = [0.33588, 0.54628]
+    chi = [1., 0.]
+    for name in names:
+        x = XSdata(name, 2)
+        x.order = order
+        x.set_nu_fission(np.multiply(nu, fiss))
+        x.set_absorption(absorption)
+        x.set_scatter_matrix(scatter)
+        x.set_total(total)
+        x.set_chi(chi)
+        lib.add_xsdata(x)
+    return lib
+
+
+def slab_mg(num_regions=1, mat_names=None):
+    """openmc.examples.slab_mg, openmc/examples.py:557-656: 1-D slab, reflective
+    at x=0, vacuum at x=929.45, uniform box source over the first region."""
+    if mat_names is None:
+        mat_names = ["mat_" + str(i + 1) for i in range(num_regions)]
+    m = Model()
+    mats = []
+    for i, name in enumerate(mat_names):
+        mats.append(m.material(id=i + 1, name=name, macroscopic="mat_" + str(i + 1),
+                               units="macro", density=1.0))
+    rad_outer = 929.45
+    rads = np.linspace(0., rad_outer, len(mats) + 1, endpoint=True)[1:]
+    surfs = [m.surface("x-plane", [0.0], "reflective")]
+    for r, rad in enumerate(rads):
+        surfs.append(m.surface("x-plane", [float(rad)],
+                               "vacuum" if r == len(rads) - 1 else "transmission"))
+    for c in range(len(surfs) - 1):
+        m.cell(region=f"{surfs[c].id} -{surfs[c + 1].id}", fill=mats[c], universe=0)
+    m.settings["legendre_to_tabular"] = False      # tabular_legendre = {'enable': False}
+    INF = 1000.
+    box = [0., -INF, -INF, float(rads[0]), INF, INF]
+    return m, box, False
+
+
+# ----------------------------------------------------------------------------
+# C5G7 7-group data used by examples/pincell_multigroup and mg_temperature_multi
+# ----------------------------------------------------------------------------
+C5G7_EDGES = [1e-5, 0.0635, 10.0, 1.0e2, 1.0e3, 0.5e6, 1.0e6, 20.0e6]
+_UO2_SCATTER = [
+    [0.1275370, 0.0423780, 0.0000094, 0.0000000, 0.0000000, 0.0000000, 0.0000000],
+    [0.0000000, 0.3244560, 0.0016314, 0.0000000, 0.0000000, 0.0000000, 0.0000000],
+    [0.0000000, 0.0000000, 0.4509400, 0.0026792, 0.0000000, 0.0000000, 0.0000000],
+    [0.0000000, 0.0000000, 0.0000000, 0.4525650, 0.0055664, 0.0000000, 0.0000000],
+    [0.0000000, 0.0000000, 0.0000000, 0.0001253, 0.2714010, 0.0102550, 0.0000000],
+    [0.0000000, 0.0000000, 0.0000000, 0.0000000, 0.0012968, 0.2658020, 0.0168090],
+    [0.0000000, 0.0000000, 0.0000000, 0.0000000, 0.0000000, 0.0085458, 0.2730800]]
+_H2O_SCATTER = [
+    [0.0444777, 0.1134000, 0.0007235, 0.0000037, 0.0000001, 0.0000000, 0.0000000],
+    [0.0000000, 0.2823340, 0.1299400, 0.0006234, 0.0000480, 0.0000074, 0.0000010],
+    [0.0000000, 0.0000000, 0.3452560, 0.2245700, 0.0169990, 0.0026443, 0.0005034],
+    [0.0000000, 0.0000000, 0.0000000, 0.0910284, 0.4155100, 0.0637320, 0.0121390],
+    [0.0000000, 0.0000000, 0.0000000, 0.0000714, 0.1391380, 0.5118200, 0.0612290],
+    [0.0000000, 0.0000000, 0.0000000, 0.0000000, 0.0022157, 0.6999130, 0.5373200],
+    [0.0000000, 0.0000000, 0.0000000, 0.0000000, 0.0000000, 0.1324400, 2.4807000]]
+_UO2_TOTAL = [0.1779492, 0.3298048, 0.4803882, 0.5543674, 0.3118013, 0.3951678, 0.5644058]
+_UO2_ABS = [8.0248E-03, 3.7174E-03, 2.6769E-02, 9.6236E-02, 3.0020E-02, 1.1126E-01, 2.8278E-01]
+_UO2_FIS = [7.21206E-03, 8.19301E-04, 6.45320E-03, 1.85648E-02, 1.78084E-02, 8.30348E-02, 2.16004E-01]
+_UO2_NUFIS = [2.005998E-02, 2.027303E-03, 1.570599E-02, 4.518301E-02, 4.334208E-02, 2.020901E-01, 5.257105E-01]
+_UO2_CHI = [5.8791E-01, 4.1176E-01, 3.3906E-04, 1.1761E-07, 0.0000E+00, 0.0000E+00, 0.0000E+00]
+_H2O_TOTAL = [0.15920605, 0.412969593, 0.59030986, 0.58435, 0.718, 1.2544497, 2.650379]
+_H2O_ABS = [6.0105E-04, 1.5793E-05, 3.3716E-04, 1.9406E-03, 5.7416E-03, 1.5001E-02, 3.7239E-02]
+
+
+def _roll(sm):
+    # np.rollaxis(np.array([sm]), 0, 3): [1][G][G'] -> [G][G'][1]
+    return np.rollaxis(np.array([sm]), 0, 3)
+
+
+def c5g7_library(two_temperatures=False):
+    """tests/regression_tests/mg_temperature_multi/test.py:10-70 (two_temperatures)
+    and examples/pincell_multigroup/build_xml.py:14-69 (single temperature)."""
+    lib = MGXSLibrary(C5G7_EDGES)
+    temps = [294.0, 600.0] if two_temperatures else [294.0]
+    uo2 = XSdata("UO2", 7, temperatures=temps)
+    uo2.order = 0
+    for T in temps:
+        uo2.set_total(_UO2_TOTAL, temperature=T)
+        uo2.set_absorption(_UO2_ABS, temperature=T)
+        uo2.set_scatter_matrix(_roll(_UO2_SCATTER), temperature=T)
+        uo2.set_fission(_UO2_FIS, temperature=T)
+        uo2.set_nu_fission(_UO2_NUFIS, temperature=T)
+        chi = list(_UO2_CHI)
+        if T == 600.0:
+            chi[0], chi[1] = chi[1], chi[0]           # "Altered C5G7 data (permuted Chi)"
+        uo2.set_chi(chi, temperature=T)
+    h2o = XSdata("LWTR", 7)
+    h2o.order = 0
+    h2o.set_total(_H2O_TOTAL)
+    h2o.set_absorption(_H2O_ABS)
+    h2o.set_scatter_matrix(_roll(_H2O_SCATTER))
+    lib.add_xsdata(uo2)
+    lib.add_xsdata(h2o)
+    return lib
+
+
+def _pincell_geometry(m: Model, fuel_mat, water_mat, pitch=1.26, r_fuel=0.54, r_inner=None,
+                      inner_T=None, outer_T=None):
+    """fuel pin in a reflective square box (RectangularPrism): surfaces in the
+    order openmc.model.RectangularPrism creates them (min_x, max_x, min_y, max_y)."""
+    ids = {}
+    if r_inner is not None:
+        ids["ir"] = m.surface("z-cylinder", [0.0, 0.0, r_inner]).id
+    ids["or"] = m.surface("z-cylinder", [0.0, 0.0, r_fuel]).id
+    ids["x0"] = m.surface("x-plane", [-pitch / 2], "reflective").id
+    ids["x1"] = m.surface("x-plane", [pitch / 2], "reflective").id
+    ids["y0"] = m.surface("y-plane", [-pitch / 2], "reflective").id
+    ids["y1"] = m.surface("y-plane", [pitch / 2], "reflective").id
+    box = f"{ids['x0']} -{ids['x1']} {ids['y0']} -{ids['y1']}"
+    if r_inner is not None:
+        m.cell(region=f"-{ids['ir']}", fill=fuel_mat, temperature=inner_T)
+        m.cell(region=f"{ids['ir']} -{ids['or']}", fill=fuel_mat, temperature=outer_T)
+    else:
+        m.cell(region=f"-{ids['or']}", fill=fuel_mat)
+    m.cell(region=f"{ids['or']} {box}", fill=water_mat)
+    return ids
+
+
+def mg_temperature_multi():
+    """tests/regression_tests/mg_temperature_multi/test.py:80-160."""
+    m = Model()
+    uo2 = m.material(name="UO2 fuel", macroscopic="UO2", units="macro", density=1.0)
+    water = m.material(name="Water", macroscopic="LWTR", units="macro", density=1.0)
+    pitch = 1.26
+    _pincell_geometry(m, uo2, water, pitch, 0.54, r_inner=0.25, inner_T=600.0, outer_T=294.0)
+    # tallies: the second `filters =` assignment wins -> one cell filter each
+    m.filters = [Filter(1, "cell", [m.cells[0].id]), Filter(2, "cell", [m.cells[1].id])]
+    m.tallies = [Tally(1, [1], ["flux"]), Tally(2, [2], ["flux"])]
+    box = [-pitch / 2, -pitch / 2, -1, pitch / 2, pitch / 2, 1]
+    return m, c5g7_library(True), box, True
+
+
+def pincell_multigroup(mesh_dim=100, energy_bins=500):
+    """Config C1: examples/pincell_multigroup/build_xml.py:14-149 (7-group C5G7
+    UO2/LWTR pin, reflective box, 100x100 mesh {flux, fission, nu-fission} and a
+    500-bin log energy flux spectrum)."""
+    m = Model()
+    uo2 = m.material(name="UO2 fuel", macroscopic="UO2", units="macro", density=1.0)
+    water = m.material(name="Water", macroscopic="LWTR", units="macro", density=1.0)
+    pitch = 1.26
+    _pincell_geometry(m, uo2, water, pitch, 0.54)
+    m.meshes = [Mesh(1, [mesh_dim, mesh_dim], [-pitch / 2, -pitch / 2], [pitch / 2, pitch / 2])]
+    edges = np.logspace(np.log10(1e-5), np.log10(20.0e6), energy_bins + 1)
+    m.filters = [Filter(1, "mesh", 1), Filter(2, "energy", list(edges))]
+    m.tallies = [Tally(1, [1], ["flux", "fission", "nu-fission"]), Tally(2, [2], ["flux"])]
+    box = [-pitch / 2, -pitch / 2, -1, pitch / 2, pitch / 2, 1]
+    return m, c5g7_library(False), box, True

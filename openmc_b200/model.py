@@ -1,0 +1,570 @@
+"""Host-side model description and flattener.
+
+In the real integration libopenmc's own loaders (``read_model_xml``,
+``finalize_geometry``, ``finalize_cross_sections``) build ``model::`` / ``data::``
+and a flattener copies them into the POD arrays of ``omcgpu_model``
+(INTEGRATION.md).  The XML/HDF5 front end is out of scope here, so
+this module provides the small amount of host logic that produces the *same
+flattened arrays* from a Python description: surfaces, CSG regions, cells,
+universes, rectangular lattices, materials and tallies.  The derived quantities
+follow the reference's load-time code:
+
+* region tokenisation / De Morgan / simple-cell stripping   src/cell.cpp:556-682
+* lattice universe ordering (rows listed top to bottom)     src/lattice.cpp:214-231
+* cell sqrt(kT) defaults                                    src/geometry_aux.cpp (assign_temperatures)
+* density normalisation                                     src/material.cpp:417-467
+* tally strides                                             src/tallies/tally.cpp:503-516
+"""
+from __future__ import annotations
+
+import math
+import re
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _abi as abi
+
+K_BOLTZMANN = 8.617333262e-5       # include/openmc/constants.h:102
+N_AVOGADRO = 0.602214076
+MASS_NEUTRON = 1.00866491595
+TEMPERATURE_DEFAULT = 293.6         # src/settings.cpp:141
+
+_SURF_KINDS = {
+    "x-plane": (abi.OMCGPU_SURF_XPLANE, 1), "y-plane": (abi.OMCGPU_SURF_YPLANE, 1),
+    "z-plane": (abi.OMCGPU_SURF_ZPLANE, 1), "plane": (abi.OMCGPU_SURF_PLANE, 4),
+    "x-cylinder": (abi.OMCGPU_SURF_XCYLINDER, 3), "y-cylinder": (abi.OMCGPU_SURF_YCYLINDER, 3),
+    "z-cylinder": (abi.OMCGPU_SURF_ZCYLINDER, 3), "sphere": (abi.OMCGPU_SURF_SPHERE, 4),
+}
+_BCS = {"transmission": abi.OMCGPU_BC_NONE, "vacuum": abi.OMCGPU_BC_VACUUM,
+        "reflective": abi.OMCGPU_BC_REFLECTIVE}
+_SCORES = {"flux": abi.OMCGPU_SCORE_FLUX, "total": abi.OMCGPU_SCORE_TOTAL,
+           "absorption": abi.OMCGPU_SCORE_ABSORPTION, "fission": abi.OMCGPU_SCORE_FISSION,
+           "nu-fission": abi.OMCGPU_SCORE_NU_FISSION, "scatter": abi.OMCGPU_SCORE_SCATTER}
+
+OP_LP, OP_RP = abi.OMCGPU_OP_LEFT_PAREN, abi.OMCGPU_OP_RIGHT_PAREN
+OP_COMP, OP_INT, OP_UNION = (abi.OMCGPU_OP_COMPLEMENT, abi.OMCGPU_OP_INTERSECTION,
+                             abi.OMCGPU_OP_UNION)
+
+
+@dataclass
+class Surface:
+    id: int
+    kind: str
+    coeffs: Sequence[float]
+    boundary: str = "transmission"
+
+
+@dataclass
+class Material:
+    id: int
+    name: str = ""
+    # [(nuclide or macroscopic name, atom fraction (>0) or weight fraction (<0))]
+    components: list = field(default_factory=list)
+    density: Optional[float] = None
+    units: str = "atom/b-cm"           # 'macro', 'sum', 'g/cm3', 'atom/b-cm'
+    macroscopic: Optional[str] = None  # <macroscopic name=.../>
+    temperature: Optional[float] = None
+
+
+@dataclass
+class Cell:
+    id: int
+    region: str = ""                   # OpenMC region syntax with surface ids
+    fill: object = None                # Material | Universe id | RectLattice | None (void)
+    universe: int = 0
+    temperature: Optional[float] = None
+    translation: Sequence[float] = (0.0, 0.0, 0.0)
+    fill_type: str = "material"        # 'material' | 'universe' | 'lattice'
+
+
+@dataclass
+class RectLattice:
+    id: int
+    pitch: Sequence[float]
+    lower_left: Sequence[float]
+    universes: object                  # [ny][nx] or [nz][ny][nx], rows listed top (max y) first
+    outer: Optional[int] = None
+
+
+@dataclass
+class Mesh:
+    id: int
+    dimension: Sequence[int]
+    lower_left: Sequence[float]
+    upper_right: Sequence[float]
+
+
+@dataclass
+class Filter:
+    id: int
+    type: str                          # 'mesh' 'energy' 'cell' 'material' 'universe'
+    bins: object                       # mesh id | energy edges | list of ids
+
+
+@dataclass
+class Tally:
+    id: int
+    filters: list                      # filter ids
+    scores: list                       # names
+
+
+# ----------------------------------------------------------------------------
+# region parsing
+# ----------------------------------------------------------------------------
+def _tokenize(spec: str):
+    toks = []
+    i = 0
+    while i < len(spec):
+        ch = spec[i]
+        if ch == "(":
+            toks.append(OP_LP); i += 1
+        elif ch == ")":
+            toks.append(OP_RP); i += 1
+        elif ch == "|":
+            toks.append(OP_UNION); i += 1
+        elif ch == "~":
+            toks.append(OP_COMP); i += 1
+        elif ch in "+-" or ch.isdigit():
+            j = i + 1
+            while j < len(spec) and spec[j].isdigit():
+                j += 1
+            toks.append(int(spec[i:j])); i = j
+        elif ch.isspace():
+            i += 1
+        else:
+            raise ValueError(f"Region specification contains invalid character, {ch!r}")
+    # insert implicit intersections (src/cell.cpp:600-612)
+    i = 0
+    while i < len(toks) - 1:
+        left = toks[i] < OP_UNION or toks[i] == OP_RP
+        right = toks[i + 1] < OP_UNION or toks[i + 1] in (OP_LP, OP_COMP)
+        if left and right:
+            toks.insert(i + 1, OP_INT)
+        i += 1
+    return toks
+
+
+def _parse_region(toks):
+    """Recursive descent over the infix tokens -> nested tuple tree.
+
+    ('s', id) | ('and', [..]) | ('or', [..]); complements are pushed down with
+    De Morgan's laws (src/cell.cpp:614-640, apply_demorgan :684-698)."""
+    pos = 0
+
+    def negate(node):
+        if node[0] == "s":
+            return ("s", -node[1])
+        return ("or" if node[0] == "and" else "and", [negate(c) for c in node[1]])
+
+    def primary():
+        nonlocal pos
+        t = toks[pos]
+        if t == OP_COMP:
+            pos += 1
+            return negate(primary())
+        if t == OP_LP:
+            pos += 1
+            node = union()
+            assert toks[pos] == OP_RP, "unbalanced parentheses"
+            pos += 1
+            return node
+        pos += 1
+        return ("s", t)
+
+    def inter():
+        nonlocal pos
+        items = [primary()]
+        while pos < len(toks) and toks[pos] == OP_INT:
+            pos += 1
+            items.append(primary())
+        return items[0] if len(items) == 1 else ("and", items)
+
+    def union():
+        nonlocal pos
+        items = [inter()]
+        while pos < len(toks) and toks[pos] == OP_UNION:
+            pos += 1
+            items.append(inter())
+        return items[0] if len(items) == 1 else ("or", items)
+
+    tree = union()
+    assert pos == len(toks), "trailing tokens in region"
+    return tree
+
+
+def _emit(node, parent=None):
+    """Tree -> infix tokens, parenthesised so that intersections bind tighter than
+    unions (the effect of Region::add_precedence, src/cell.cpp:769-800)."""
+    if node[0] == "s":
+        return [node[1]]
+    op = OP_INT if node[0] == "and" else OP_UNION
+    out = []
+    for k, c in enumerate(node[1]):
+        if k:
+            out.append(op)
+        sub = _emit(c, node[0])
+        if c[0] != "s" and c[0] != node[0]:
+            sub = [OP_LP] + sub + [OP_RP]
+        out += sub
+    return out
+
+
+def region_tokens(spec: str, surface_index: dict):
+    """Returns (tokens, simple) with surface ids replaced by +-(index+1)."""
+    if not spec or not spec.strip():
+        return [], True
+    tree = _parse_region(_tokenize(spec))
+
+    def flatten(node):
+        if node[0] == "s":
+            return node
+        kids = []
+        for c in node[1]:
+            c = flatten(c)
+            if c[0] == node[0]:
+                kids += c[1]
+            else:
+                kids.append(c)
+        return (node[0], kids)
+
+    tree = flatten(tree)
+    toks = _emit(tree)
+    simple = OP_UNION not in toks
+    if simple:
+        toks = [t for t in toks if t < OP_UNION]
+    out = []
+    for t in toks:
+        if t < OP_UNION:
+            idx = surface_index[abs(t)] + 1
+            out.append(idx if t > 0 else -idx)
+        else:
+            out.append(t)
+    return out, simple
+
+
+# ----------------------------------------------------------------------------
+# the model
+# ----------------------------------------------------------------------------
+class Model:
+    """Geometry + materials + tallies; ``flatten`` produces omcgpu_model fields."""
+
+    def __init__(self):
+        self.surfaces: list[Surface] = []
+        self.cells: list[Cell] = []
+        self.lattices: list[RectLattice] = []
+        self.materials: list[Material] = []
+        self.meshes: list[Mesh] = []
+        self.filters: list[Filter] = []
+        self.tallies: list[Tally] = []
+        self.settings = dict(run_CE=0, survival_biasing=0, weight_cutoff=0.25, weight_survive=1.0,
+                             energy_cutoff=0.0, max_particle_events=1000000,
+                             create_delayed_neutrons=1, free_gas_threshold=400.0,
+                             n_log_bins=8000, legendre_to_tabular=True,
+                             legendre_to_tabular_points=None, max_order=None,
+                             temperature_tolerance=10.0)
+
+    # -- convenience constructors ------------------------------------------------
+    def surface(self, kind, coeffs, boundary="transmission", id=None):
+        s = Surface(id if id is not None else len(self.surfaces) + 1, kind, list(coeffs), boundary)
+        self.surfaces.append(s)
+        return s
+
+    def material(self, **kw):
+        kw.setdefault("id", len(self.materials) + 1)
+        m = Material(**kw)
+        self.materials.append(m)
+        return m
+
+    def cell(self, **kw):
+        kw.setdefault("id", len(self.cells) + 1)
+        c = Cell(**kw)
+        if isinstance(c.fill, RectLattice):
+            c.fill_type = "lattice"
+        elif isinstance(c.fill, int):
+            c.fill_type = "universe"
+        else:
+            c.fill_type = "material"
+        self.cells.append(c)
+        return c
+
+    def lattice(self, **kw):
+        kw.setdefault("id", len(self.lattices) + 1)
+        l = RectLattice(**kw)
+        self.lattices.append(l)
+        return l
+
+    # -- flattening --------------------------------------------------------------
+    def flatten_geometry(self) -> dict:
+        v = {}
+        s_index = {s.id: i for i, s in enumerate(self.surfaces)}
+        ns = len(self.surfaces)
+        coef = np.zeros((max(ns, 1), abi.OMCGPU_SURF_NCOEF))
+        stype = np.zeros(max(ns, 1), np.int32)
+        sbc = np.zeros(max(ns, 1), np.int32)
+        for i, s in enumerate(self.surfaces):
+            kind, nco = _SURF_KINDS[s.kind]
+            if len(s.coeffs) != nco:
+                raise ValueError(f"surface {s.id}: {s.kind} needs {nco} coefficients")
+            stype[i] = kind
+            coef[i, :nco] = s.coeffs
+            sbc[i] = _BCS[s.boundary]
+        v.update(n_surfaces=ns, surf_type=stype, surf_bc=sbc, surf_coef=coef,
+                 surf_id=np.array([s.id for s in self.surfaces] or [0], np.int32))
+
+        # universes: ids in order of first appearance (cells' universe attribute,
+        # fills and lattice entries), src/geometry_aux.cpp
+        univ_ids = []
+
+        def add_univ(u):
+            if u not in univ_ids:
+                univ_ids.append(u)
+        for c in self.cells:
+            add_univ(c.universe)
+        for c in self.cells:
+            if c.fill_type == "universe":
+                add_univ(c.fill)
+        for l in self.lattices:
+            for u in np.asarray(l.universes).reshape(-1):
+                add_univ(int(u))
+            if l.outer is not None:
+                add_univ(l.outer)
+        u_index = {u: i for i, u in enumerate(univ_ids)}
+        l_index = {l.id: i for i, l in enumerate(self.lattices)}
+        m_index = {m.id: i for i, m in enumerate(self.materials)}
+        self._u_index, self._m_index, self._l_index = u_index, m_index, l_index
+        self._c_index = {c.id: i for i, c in enumerate(self.cells)}
+
+        nc = len(self.cells)
+        ctype = np.zeros(nc, np.int32); cuniv = np.zeros(nc, np.int32)
+        cfill = np.full(nc, -1, np.int32); csimple = np.zeros(nc, np.int32)
+        rofs = [0]; rtok = []
+        mofs = [0]; cmat = []
+        kofs = [0]; ckt = []
+        trans = np.zeros((nc, 3))
+        for i, c in enumerate(self.cells):
+            toks, simple = region_tokens(c.region, s_index)
+            rtok += toks; rofs.append(len(rtok)); csimple[i] = int(simple)
+            cuniv[i] = u_index[c.universe]
+            trans[i] = c.translation
+            if c.fill_type == "material":
+                ctype[i] = abi.OMCGPU_FILL_MATERIAL
+                cmat.append(-1 if c.fill is None else m_index[c.fill.id])
+                T = c.temperature
+                if T is None and c.fill is not None and c.fill.temperature is not None:
+                    T = c.fill.temperature
+                if T is None:
+                    T = TEMPERATURE_DEFAULT
+                ckt.append(math.sqrt(K_BOLTZMANN * T))
+            elif c.fill_type == "universe":
+                ctype[i] = abi.OMCGPU_FILL_UNIVERSE
+                cfill[i] = u_index[c.fill]
+            else:
+                ctype[i] = abi.OMCGPU_FILL_LATTICE
+                cfill[i] = l_index[c.fill.id]
+            mofs.append(len(cmat)); kofs.append(len(ckt))
+        v.update(n_cells=nc, cell_id=np.array([c.id for c in self.cells], np.int32),
+                 cell_type=ctype, cell_universe=cuniv, cell_fill=cfill, cell_simple=csimple,
+                 cell_region_ofs=np.array(rofs, np.int32), region_tokens=np.array(rtok or [0], np.int32),
+                 cell_mat_ofs=np.array(mofs, np.int32), cell_material=np.array(cmat or [0], np.int32),
+                 cell_sqrtkT_ofs=np.array(kofs, np.int32), cell_sqrtkT=np.array(ckt or [0.0]),
+                 cell_translation=trans, cell_distribcell_index=np.full(nc, -1, np.int32),
+                 cell_offset_ofs=np.zeros(nc + 1, np.int32), cell_offset=np.zeros(1, np.int32))
+
+        nu = len(univ_ids)
+        uofs = [0]; ucells = []
+        for u in univ_ids:
+            ucells += [i for i, c in enumerate(self.cells) if c.universe == u]
+            uofs.append(len(ucells))
+        v.update(n_universes=nu, univ_cell_ofs=np.array(uofs, np.int32),
+                 univ_cells=np.array(ucells, np.int32))
+
+        nl = len(self.lattices)
+        lshape = np.ones((max(nl, 1), 3), np.int32); l3d = np.zeros(max(nl, 1), np.int32)
+        louter = np.full(max(nl, 1), -1, np.int32)
+        lpitch = np.zeros((max(nl, 1), 3)); lll = np.zeros((max(nl, 1), 3))
+        lofs = [0]; lun = []
+        for i, l in enumerate(self.lattices):
+            arr = np.asarray(l.universes)
+            if arr.ndim == 2:
+                arr = arr[None]
+            else:
+                l3d[i] = 1
+            nz, ny, nx = arr.shape
+            lshape[i] = (nx, ny, nz)
+            nd = 3 if l3d[i] else 2
+            lpitch[i, :nd] = l.pitch[:nd]
+            lll[i, :nd] = l.lower_left[:nd]
+            if l.outer is not None:
+                louter[i] = u_index[l.outer]
+            # rows are listed top-to-bottom: flip y (src/lattice.cpp:214-231)
+            flipped = arr[:, ::-1, :]
+            lun += [u_index[int(u)] for u in flipped.reshape(-1)]
+            lofs.append(len(lun))
+        v.update(n_lattices=nl, lat_shape=lshape, lat_is3d=l3d, lat_outer=louter, lat_pitch=lpitch,
+                 lat_lower_left=lll, lat_univ_ofs=np.array(lofs, np.int32),
+                 lat_universes=np.array(lun or [0], np.int32),
+                 lat_offset_ofs=np.zeros(max(nl, 1) + 1, np.int32),
+                 lat_offsets=np.zeros(1, np.int32))
+
+        # root universe = the one no cell / lattice is filled with; depth
+        filled = set()
+        for c in self.cells:
+            if c.fill_type == "universe":
+                filled.add(c.fill)
+        for l in self.lattices:
+            filled |= {int(u) for u in np.asarray(l.universes).reshape(-1)}
+            if l.outer is not None:
+                filled.add(l.outer)
+        roots = [u for u in univ_ids if u not in filled]
+        if len(roots) != 1:
+            raise ValueError(f"expected exactly one root universe, got {roots}")
+        v["root_universe"] = u_index[roots[0]]
+
+        def depth(u):
+            d = 1
+            for c in self.cells:
+                if c.universe != u:
+                    continue
+                if c.fill_type == "universe":
+                    d = max(d, 1 + depth(c.fill))
+                elif c.fill_type == "lattice":
+                    subs = {int(x) for x in np.asarray(c.fill.universes).reshape(-1)}
+                    if c.fill.outer is not None:
+                        subs.add(c.fill.outer)
+                    d = max(d, 1 + max(depth(s) for s in subs))
+            return d
+        v["n_coord_levels"] = depth(roots[0])
+        if v["n_coord_levels"] > abi.OMCGPU_MAX_COORD:
+            raise ValueError("geometry nests deeper than OMCGPU_MAX_COORD")
+        return v
+
+    def flatten_tallies(self, n_groups=0, group_edges=None) -> dict:
+        v = {}
+        nm = len(self.meshes)
+        mnd = np.zeros(max(nm, 1), np.int32); msh = np.ones((max(nm, 1), 3), np.int32)
+        mll = np.zeros((max(nm, 1), 3)); mw = np.ones((max(nm, 1), 3))
+        mesh_index = {}
+        for i, m in enumerate(self.meshes):
+            nd = len(m.dimension)
+            mnd[i] = nd; msh[i, :nd] = m.dimension; mll[i, :nd] = m.lower_left
+            # width = (upper_right - lower_left) / shape  (src/mesh.cpp RegularMesh ctor)
+            for k in range(nd):
+                mw[i, k] = (m.upper_right[k] - m.lower_left[k]) / m.dimension[k]
+            mesh_index[m.id] = i
+        v.update(n_meshes=nm, mesh_ndim=mnd, mesh_shape=msh, mesh_lower_left=mll, mesh_width=mw)
+
+        nf = len(self.filters)
+        ftype = np.zeros(max(nf, 1), np.int32); fnb = np.zeros(max(nf, 1), np.int32)
+        fmesh = np.full(max(nf, 1), -1, np.int32); fmg = np.zeros(max(nf, 1), np.int32)
+        fofs = [0]; fi = []; fd = []
+        f_index = {}
+        for i, f in enumerate(self.filters):
+            f_index[f.id] = i
+            if f.type == "mesh":
+                ftype[i] = abi.OMCGPU_FILTER_MESH
+                fmesh[i] = mesh_index[f.bins]
+                fnb[i] = int(np.prod(self.meshes[fmesh[i]].dimension))
+            elif f.type == "energy":
+                ftype[i] = abi.OMCGPU_FILTER_ENERGY
+                edges = [float(e) for e in f.bins]
+                fnb[i] = len(edges) - 1
+                fd += edges; fi += [0] * len(edges)
+                # EnergyFilter::set_bins: matches the transport group structure?
+                if group_edges is not None and len(edges) == n_groups + 1:
+                    fmg[i] = int(all(e == g for e, g in zip(edges, sorted(group_edges))))
+            else:
+                kind = {"cell": (abi.OMCGPU_FILTER_CELL, self._c_index, len(self.cells)),
+                        "material": (abi.OMCGPU_FILTER_MATERIAL, self._m_index, len(self.materials)),
+                        "universe": (abi.OMCGPU_FILTER_UNIVERSE, self._u_index, len(self._u_index))}[f.type]
+                ftype[i] = kind[0]
+                mp = [-1] * kind[2]
+                for b, ident in enumerate(f.bins):
+                    mp[kind[1][ident]] = b
+                fnb[i] = len(f.bins)
+                fi += mp; fd += [0.0] * len(mp)
+            fofs.append(len(fi))
+        v.update(n_filters=nf, filter_type=ftype, filter_n_bins=fnb, filter_mesh=fmesh,
+                 filter_matches_groups=fmg, filter_data_ofs=np.array(fofs, np.int32),
+                 filter_idata=np.array(fi or [0], np.int32), filter_ddata=np.array(fd or [0.0]))
+
+        nt = len(self.tallies)
+        tnf = np.zeros(max(nt, 1), np.int32); tf = np.zeros((max(nt, 1), abi.OMCGPU_MAX_FILTERS), np.int32)
+        tst = np.zeros((max(nt, 1), abi.OMCGPU_MAX_FILTERS), np.int32)
+        tns = np.zeros(max(nt, 1), np.int32); tsc = np.zeros((max(nt, 1), abi.OMCGPU_MAX_SCORES), np.int32)
+        tofs = [0]
+        for i, t in enumerate(self.tallies):
+            tnf[i] = len(t.filters)
+            stride = 1
+            for k in range(len(t.filters) - 1, -1, -1):   # src/tallies/tally.cpp:503-516
+                fidx = f_index[t.filters[k]]
+                tf[i, k] = fidx
+                tst[i, k] = stride
+                stride *= int(fnb[fidx])
+            tns[i] = len(t.scores)
+            tsc[i, :len(t.scores)] = [_SCORES[s] for s in t.scores]
+            tofs.append(tofs[-1] + stride * len(t.scores))
+        v.update(n_tallies=nt, tally_n_filters=tnf, tally_filters=tf, tally_strides=tst,
+                 tally_n_scores=tns, tally_scores=tsc, tally_result_ofs=np.array(tofs, np.int64))
+        return v
+
+    def tally_shape(self, i):
+        t = self.tallies[i]
+        fmap = {f.id: f for f in self.filters}
+        nb = 1
+        for fid in t.filters:
+            f = fmap[fid]
+            if f.type == "mesh":
+                m = [m for m in self.meshes if m.id == f.bins][0]
+                nb *= int(np.prod(m.dimension))
+            elif f.type == "energy":
+                nb *= len(f.bins) - 1
+            else:
+                nb *= len(f.bins)
+        return nb, len(t.scores)
+
+    def settings_fields(self) -> dict:
+        s = self.settings
+        return dict(run_CE=s["run_CE"], survival_biasing=int(s["survival_biasing"]),
+                    max_particle_events=s["max_particle_events"],
+                    create_delayed_neutrons=int(s["create_delayed_neutrons"]),
+                    weight_cutoff=s["weight_cutoff"], weight_survive=s["weight_survive"],
+                    energy_cutoff=s["energy_cutoff"], free_gas_threshold=s["free_gas_threshold"])
+
+
+def normalize_density(mat: Material, awr: Sequence[float]):
+    """Material::normalize_density, src/material.cpp:417-467 -> atom densities."""
+    dens = [float(d) for _, d in mat.components]
+    if mat.units == "macro":
+        density = 1.0 if mat.density is None else float(mat.density)
+        dens = [density for _ in dens]
+    elif mat.units == "sum":
+        density = 0.0
+        for d in dens:
+            density += d
+    elif mat.units in ("g/cc", "g/cm3"):
+        density = -float(mat.density)
+    elif mat.units == "kg/m3":
+        density = -1.0e-3 * float(mat.density)
+    elif mat.units == "atom/b-cm":
+        density = float(mat.density)
+    elif mat.units in ("atom/cc", "atom/cm3"):
+        density = 1.0e-24 * float(mat.density)
+    else:
+        raise ValueError(f"Unknown units {mat.units!r}")
+    percent_in_atom = dens[0] >= 0.0
+    density_in_atom = density >= 0.0
+    if not percent_in_atom:
+        dens = [-d / a for d, a in zip(dens, awr)]
+    total = 0.0
+    for d in dens:
+        total += d
+    dens = [d / total for d in dens]
+    if not density_in_atom:
+        sum_percent = 0.0
+        for d, a in zip(dens, awr):
+            sum_percent += d * a
+        sum_percent = 1.0 / sum_percent
+        density = -density * N_AVOGADRO / MASS_NEUTRON * sum_percent
+    return [d * density for d in dens]
