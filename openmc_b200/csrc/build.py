@@ -1,0 +1,50 @@
+"""Build libomcgpu.so (the product) in-tree with nvcc for sm_100a.
+
+    python -m openmc_b200.csrc.build [--force]
+
+-fmad=false keeps the device arithmetic free of fused multiply-adds so that it
+rounds like the reference's x86-64 build (and the oracle); the path is
+latency/bandwidth bound, so this costs nothing measurable.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libomcgpu.so")
+SOURCES = ["engine.cu"]
+HEADERS = ["common.h", "device.h", "cuda_emu.h", os.path.join("..", "..", "include", "omcgpu.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
+              "-Xptxas", "-v"]
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not (force or stale()):
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + ["-o", LIB] + \
+          [os.path.join(HERE, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    log = os.path.join(HERE, "build.log")
+    with open(log, "w") as f:
+        f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed, see " + log)
+    if verbose:
+        print(res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,136 @@
+// common.h -- shared definitions of the device engine.
+//
+// The event kernels are written once as `OMC_HD` functions over structure-of-
+// arrays particle state.  nvcc compiles them for sm_100a (the product,
+// libomcgpu.so).  A plain g++ compile of the very same sources with -DOMC_EMU
+// exists ONLY for the CPU unit tests under tests/ (tests/_emu, never loaded by
+// the package): it lets the host-side scheduler, queue logic and the device
+// functions be checked against the oracle without a GPU.  It is not a fallback:
+// omcgpu_init() of the product library fails when no CUDA device is present.
+#pragma once
+
+#include <stdint.h>
+
+#include "../../include/omcgpu.h"
+
+#if defined(__CUDACC__) && !defined(OMC_EMU)
+#define OMC_CUDA 1
+#define OMC_HD __device__ __forceinline__          /* device functions reading the constant-memory model */
+#define OMC_BOTH __host__ __device__ __forceinline__ /* pure functions also used by host code (RNG) */
+#define OMC_D __device__ __forceinline__
+#else
+#define OMC_CUDA 0
+#define OMC_HD inline
+#define OMC_BOTH inline
+#define OMC_D inline
+#include <cmath>
+#include <cstring>
+#endif
+
+namespace omc {
+
+// ---- constants: include/openmc/constants.h:49-54,61,81-83,112,337,377 ---------
+constexpr double TINY_BIT = 1e-8;
+constexpr double FP_PRECISION = 1e-14;
+constexpr double FP_REL_PRECISION = 1e-5;
+constexpr double FP_COINCIDENT = 1e-12;
+constexpr int MAX_SAMPLE = 100000;
+constexpr double PI = 3.141592653589793238462643383279502884;
+constexpr double INFTY = 1.7976931348623157e308; // std::numeric_limits<double>::max()
+constexpr double MASS_NEUTRON_EV = 939.56542052e6;
+constexpr double C_LIGHT = 2.99792458e10;
+constexpr int C_NONE = -1;
+constexpr int MATERIAL_VOID = -1;
+constexpr int SURFACE_NONE = 0;
+constexpr int32_t OP_UNION = OMCGPU_OP_UNION;
+constexpr int32_t OP_INTERSECTION = OMCGPU_OP_INTERSECTION;
+constexpr int32_t OP_COMPLEMENT = OMCGPU_OP_COMPLEMENT;
+constexpr int32_t OP_RIGHT_PAREN = OMCGPU_OP_RIGHT_PAREN;
+constexpr int32_t OP_LEFT_PAREN = OMCGPU_OP_LEFT_PAREN;
+
+OMC_HD double inf_d()
+{
+#if OMC_CUDA
+  return __longlong_as_double(0x7ff0000000000000LL);
+#else
+  return INFINITY;
+#endif
+}
+
+struct V3 {
+  double x, y, z;
+};
+OMC_HD V3 v3(double x, double y, double z)
+{
+  V3 v;
+  v.x = x;
+  v.y = y;
+  v.z = z;
+  return v;
+}
+OMC_HD double dot(V3 a, V3 b)
+{
+  return a.x * b.x + a.y * b.y + a.z * b.z;
+}
+OMC_HD double comp(V3 a, int i)
+{
+  return i == 0 ? a.x : (i == 1 ? a.y : a.z);
+}
+
+// -----------------------------------------------------------------------------
+// Particle state: structure of arrays in HBM (last
+// paragraph).  Level-indexed columns are level-major: col[level * cap + i].
+// -----------------------------------------------------------------------------
+struct PState {
+  int64_t cap; // stride between coordinate levels = particles allocated
+  // per level
+  double *rx, *ry, *rz, *ux, *uy, *uz;
+  int32_t *cell, *universe, *lattice, *lat_x, *lat_y, *lat_z;
+  // per particle
+  int32_t *n_coord, *cell_last0, *cell_instance, *surface, *material, *material_last;
+  double *sqrtkT, *sqrtkT_last;
+  double* E;
+  int32_t *g, *g_last;
+  double *wgt, *time;
+  uint64_t* seed;
+  int32_t *n_progeny, *n_event;
+  double *xs_total, *xs_absorption, *xs_fission, *xs_nu_fission;
+  int32_t *b_surface, *b_level_trans;
+  double *k_abs, *k_col, *k_trk, *k_leak;
+};
+
+// Source / fission banks as SoA columns (the 104-byte AoS SourceSite is only the
+// host-side wire format).
+struct Bank {
+  int64_t cap;
+  double *x, *y, *z, *u, *v, *w, *E, *time, *wgt;
+  int32_t* delayed_group;
+  int64_t *parent_id, *progeny_id;
+};
+
+// Work lists (event queues): indices of particles, filled by warp-aggregated
+// atomic appends (replaces SharedArray::thread_safe_append,
+// include/openmc/shared_array.h:71-89).
+struct Queue {
+  int32_t* idx;
+  int32_t* count; // device counter
+};
+
+// Per-generation constants + counters visible to every kernel.
+struct GenCtx {
+  int64_t n;          // histories this generation
+  int64_t id_offset;  // work_index
+  int64_t seed_base;  // particle_seed_base
+  int64_t master_seed;
+  uint64_t stride;
+  double keff;
+  int32_t tallies_active;
+  // device counters
+  int32_t* n_fission;  // fission bank fill
+  int32_t* n_lost;
+  unsigned long long* counters; // [0] events [1] xs lookups [2] collisions [3] crossings
+  double* tally_values;
+  int64_t fission_cap;
+};
+
+} // namespace omc

@@ -1,0 +1,1599 @@
+// device.h -- the per-particle event functions of the engine (host/device).
+//
+// Each function cites the reference lines whose behaviour it reproduces.  The
+// code is organised for the GPU: particle state is read from / written to SoA
+// columns (PState) one coordinate level at a time, so no per-thread arrays are
+// indexed dynamically; the read-only model lives behind one constant-memory
+// struct (`DM`) of device pointers.
+#pragma once
+
+#include "common.h"
+
+namespace omc {
+
+#if OMC_CUDA
+__constant__ omcgpu_model c_dm;
+#else
+static omcgpu_model c_dm;
+#endif
+#define DM c_dm
+
+// read-only loads go through the non-coherent path on the device
+template<class T>
+OMC_HD T ld(const T* p)
+{
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+// =============================================================================
+// RNG -- src/random_lcg.cpp:11-13 (constants), 32-44 (prn), 91-120 (future_seed)
+// =============================================================================
+constexpr uint64_t PRN_MULT = 6364136223846793005ULL;
+constexpr uint64_t PRN_ADD = 1442695040888963407ULL;
+
+OMC_BOTH double prn(uint64_t& seed)
+{
+  seed = PRN_MULT * seed + PRN_ADD;
+  uint64_t word = ((seed >> ((seed >> 59u) + 5u)) ^ seed) * 12605985483714917081ull;
+  uint64_t result = (word >> 43u) ^ word;
+  // ldexp(result, -64): uint64 -> double rounds to nearest, the scale is exact
+  return static_cast<double>(result) * 5.421010862427522170037264004349708557e-20;
+}
+
+OMC_BOTH uint64_t future_seed(uint64_t n, uint64_t seed)
+{
+  uint64_t g = PRN_MULT, c = PRN_ADD, g_new = 1, c_new = 0;
+  while (n > 0) {
+    if (n & 1) {
+      g_new *= g;
+      c_new = c_new * g + c;
+    }
+    c *= (g + 1);
+    g *= g;
+    n >>= 1;
+  }
+  return g_new * seed + c_new;
+}
+
+// include/openmc/search.h:14-20 -- index of the interval containing `value`
+template<class T>
+OMC_HD int64_t lower_bound_index(const T* a, int64_t n, T value)
+{
+  if (ld(a) == value)
+    return 0;
+  int64_t lo = 0, len = n; // std::lower_bound
+  while (len > 0) {
+    int64_t half = len >> 1;
+    if (ld(a + lo + half) < value) {
+      lo += half + 1;
+      len -= half + 1;
+    } else {
+      len = half;
+    }
+  }
+  return lo - 1;
+}
+
+// src/math_functions.cpp:763-792
+OMC_HD V3 rotate_angle(V3 u, double mu, uint64_t& seed)
+{
+  double phi = 2.0 * PI * prn(seed);
+  double sinphi = sin(phi);
+  double cosphi = cos(phi);
+  double a = sqrt(fmax(0., 1. - mu * mu));
+  double b = sqrt(fmax(0., 1. - u.z * u.z));
+  if (b > 1e-10) {
+    return v3(mu * u.x + a * (u.x * u.z * cosphi - u.y * sinphi) / b,
+      mu * u.y + a * (u.y * u.z * cosphi + u.x * sinphi) / b, mu * u.z - a * b * cosphi);
+  } else {
+    b = sqrt(1. - u.y * u.y);
+    return v3(mu * u.x + a * (-u.x * u.y * sinphi + u.z * cosphi) / b, mu * u.y + a * b * sinphi,
+      mu * u.z - a * (u.y * u.z * sinphi + u.x * cosphi) / b);
+  }
+}
+
+// src/math_functions.cpp:98-121 (recursion fused with the sum; same operation order)
+OMC_HD double evaluate_legendre(int n, const double* data, double x)
+{
+  double pm1 = 1.0, p = x;
+  double val = 0.5 * ld(data) * 1.0; // (0 + 0.5) * data[0] * pnx[0]
+  val = 0.0 + val;
+  if (n >= 1)
+    val += (1 + 0.5) * ld(data + 1) * p;
+  for (int l = 1; l < n; l++) {
+    double pn = ((2 * l + 1) * x * p - l * pm1) / (l + 1);
+    val += ((l + 1) + 0.5) * ld(data + l + 1) * pn;
+    pm1 = p;
+    p = pn;
+  }
+  return val;
+}
+
+// src/random_dist.cpp:20-39
+OMC_HD double maxwell_spectrum(double T, uint64_t& seed)
+{
+  double r1 = prn(seed);
+  double r2 = prn(seed);
+  double r3 = prn(seed);
+  double c = cos(PI / 2. * r3);
+  return -T * (log(r1) + log(r2) * c * c);
+}
+OMC_HD double watt_spectrum(double a, double b, uint64_t& seed)
+{
+  double w = maxwell_spectrum(a, seed);
+  double xi = -1. + (1. - (-1.)) * prn(seed);
+  return w + 0.25 * a * a * b + xi * sqrt(a * a * b * w);
+}
+
+// =============================================================================
+// Surfaces -- src/surface.cpp:116-130, 207-220, 354-375, 399-456, 598-648
+// =============================================================================
+OMC_HD double surf_evaluate(int s, V3 r)
+{
+  const double* c = DM.surf_coef + OMCGPU_SURF_NCOEF * s;
+  const double c0 = ld(c), c1 = ld(c + 1), c2 = ld(c + 2), c3 = ld(c + 3);
+  switch (ld(DM.surf_type + s)) {
+  case OMCGPU_SURF_XPLANE:
+    return r.x - c0;
+  case OMCGPU_SURF_YPLANE:
+    return r.y - c0;
+  case OMCGPU_SURF_ZPLANE:
+    return r.z - c0;
+  case OMCGPU_SURF_PLANE:
+    return c0 * r.x + c1 * r.y + c2 * r.z - c3;
+  case OMCGPU_SURF_XCYLINDER: {
+    const double a = r.y - c0, b = r.z - c1;
+    return a * a + b * b - c2 * c2;
+  }
+  case OMCGPU_SURF_YCYLINDER: {
+    const double a = r.x - c0, b = r.z - c1;
+    return a * a + b * b - c2 * c2;
+  }
+  case OMCGPU_SURF_ZCYLINDER: {
+    const double a = r.x - c0, b = r.y - c1;
+    return a * a + b * b - c2 * c2;
+  }
+  default: { // sphere
+    const double x = r.x - c0, y = r.y - c1, z = r.z - c2;
+    return x * x + y * y + z * z - c3 * c3;
+  }
+  }
+}
+
+OMC_HD V3 surf_normal(int s, V3 r)
+{
+  const double* c = DM.surf_coef + OMCGPU_SURF_NCOEF * s;
+  switch (ld(DM.surf_type + s)) {
+  case OMCGPU_SURF_XPLANE:
+    return v3(1., 0., 0.);
+  case OMCGPU_SURF_YPLANE:
+    return v3(0., 1., 0.);
+  case OMCGPU_SURF_ZPLANE:
+    return v3(0., 0., 1.);
+  case OMCGPU_SURF_PLANE:
+    return v3(ld(c), ld(c + 1), ld(c + 2));
+  case OMCGPU_SURF_XCYLINDER:
+    return v3(0.0, 2.0 * (r.y - ld(c)), 2.0 * (r.z - ld(c + 1)));
+  case OMCGPU_SURF_YCYLINDER:
+    return v3(2.0 * (r.x - ld(c)), 0.0, 2.0 * (r.z - ld(c + 1)));
+  case OMCGPU_SURF_ZCYLINDER:
+    return v3(2.0 * (r.x - ld(c)), 2.0 * (r.y - ld(c + 1)), 0.0);
+  default:
+    return v3(2.0 * (r.x - ld(c)), 2.0 * (r.y - ld(c + 1)), 2.0 * (r.z - ld(c + 2)));
+  }
+}
+
+OMC_HD bool surf_sense(int s, V3 r, V3 u)
+{
+  const double f = surf_evaluate(s, r);
+  if (fabs(f) < FP_COINCIDENT)
+    return dot(u, surf_normal(s, r)) > 0.0;
+  return f > 0.0;
+}
+
+OMC_HD double plane_distance(double f, double proj, bool coincident)
+{ // f = offset - r_i (axis planes) ; general plane passes f = -(A x + .. - D)
+  if (coincident || fabs(f) < FP_COINCIDENT || proj == 0.0)
+    return INFTY;
+  const double d = f / proj;
+  return d < 0.0 ? INFTY : d;
+}
+
+// quadratic a t^2 + 2 k t + c = 0 shared by cylinders (a = 1 - u_axis^2) and
+// the sphere (a = 1, no division): src/surface.cpp:399-445, 606-643
+template<bool DIVIDE>
+OMC_HD double quadric_distance(double a, double k, double c, bool coincident)
+{
+  const double quad = k * k - a * c;
+  if (quad < 0.0)
+    return INFTY;
+  if (coincident || fabs(c) < FP_COINCIDENT) {
+    if (k >= 0.0)
+      return INFTY;
+    return DIVIDE ? (-k + sqrt(quad)) / a : -k + sqrt(quad);
+  }
+  if (c < 0.0)
+    return DIVIDE ? (-k + sqrt(quad)) / a : -k + sqrt(quad);
+  const double d = DIVIDE ? (-k - sqrt(quad)) / a : -k - sqrt(quad);
+  return d < 0.0 ? INFTY : d;
+}
+
+OMC_HD double cylinder_distance(double u_axis, double q2, double q3, double u2, double u3,
+  double radius, bool coincident)
+{
+  const double a = 1.0 - u_axis * u_axis;
+  if (a == 0.0)
+    return INFTY;
+  const double k = q2 * u2 + q3 * u3;
+  const double c = q2 * q2 + q3 * q3 - radius * radius;
+  return quadric_distance<true>(a, k, c, coincident);
+}
+
+OMC_HD double surf_distance(int s, V3 r, V3 u, bool coincident)
+{
+  const double* c = DM.surf_coef + OMCGPU_SURF_NCOEF * s;
+  const double c0 = ld(c), c1 = ld(c + 1), c2 = ld(c + 2), c3 = ld(c + 3);
+  switch (ld(DM.surf_type + s)) {
+  case OMCGPU_SURF_XPLANE:
+    return plane_distance(c0 - r.x, u.x, coincident);
+  case OMCGPU_SURF_YPLANE:
+    return plane_distance(c0 - r.y, u.y, coincident);
+  case OMCGPU_SURF_ZPLANE:
+    return plane_distance(c0 - r.z, u.z, coincident);
+  case OMCGPU_SURF_PLANE: {
+    const double f = c0 * r.x + c1 * r.y + c2 * r.z - c3;
+    const double projection = c0 * u.x + c1 * u.y + c2 * u.z;
+    if (coincident || fabs(f) < FP_COINCIDENT || projection == 0.0)
+      return INFTY;
+    const double d = -f / projection;
+    return d < 0.0 ? INFTY : d;
+  }
+  case OMCGPU_SURF_XCYLINDER:
+    return cylinder_distance(u.x, r.y - c0, r.z - c1, u.y, u.z, c2, coincident);
+  case OMCGPU_SURF_YCYLINDER:
+    return cylinder_distance(u.y, r.x - c0, r.z - c1, u.x, u.z, c2, coincident);
+  case OMCGPU_SURF_ZCYLINDER:
+    return cylinder_distance(u.z, r.x - c0, r.y - c1, u.x, u.y, c2, coincident);
+  default: {
+    const double x = r.x - c0, y = r.y - c1, z = r.z - c2;
+    const double k = x * u.x + y * u.y + z * u.z;
+    const double cc = x * x + y * y + z * z - c3 * c3;
+    return quadric_distance<false>(1.0, k, cc, coincident);
+  }
+  }
+}
+
+// =============================================================================
+// Regions -- src/cell.cpp:910-936 (distance), 940-970 (contains_simple),
+// 974-1029 (contains_complex)
+// =============================================================================
+OMC_HD bool cell_contains(int c, V3 r, V3 u, int on_surface)
+{
+  const int t0 = ld(DM.cell_region_ofs + c), t1 = ld(DM.cell_region_ofs + c + 1);
+  const int32_t* tok = DM.region_tokens;
+  if (ld(DM.cell_simple + c)) {
+    for (int it = t0; it < t1; ++it) {
+      const int32_t token = ld(tok + it);
+      if (token == on_surface)
+        continue;
+      if (-token == on_surface)
+        return false;
+      if (surf_sense(abs(token) - 1, r, u) != (token > 0))
+        return false;
+    }
+    return true;
+  }
+  bool in_cell = true;
+  int total_depth = 0;
+  for (int it = t0; it < t1; ++it) {
+    const int32_t token = ld(tok + it);
+    if (token < OP_UNION) {
+      if (token == on_surface)
+        in_cell = true;
+      else if (-token == on_surface)
+        in_cell = false;
+      else
+        in_cell = (surf_sense(abs(token) - 1, r, u) == (token > 0));
+    } else if ((token == OP_UNION && in_cell) || (token == OP_INTERSECTION && !in_cell)) {
+      if (total_depth == 0)
+        return in_cell;
+      total_depth--;
+      int depth = 1;
+      do {
+        ++it;
+        const int32_t next_token = ld(tok + it);
+        if (next_token > OP_COMPLEMENT)
+          depth += (next_token == OP_RIGHT_PAREN) ? -1 : 1;
+      } while (depth > 0);
+    } else if (token == OP_LEFT_PAREN) {
+      total_depth++;
+    } else if (token == OP_RIGHT_PAREN) {
+      total_depth--;
+    }
+  }
+  return in_cell;
+}
+
+OMC_HD void cell_distance(int c, V3 r, V3 u, int on_surface, double& min_dist, int& i_surf)
+{
+  min_dist = INFTY;
+  i_surf = 2147483647;
+  const int t0 = ld(DM.cell_region_ofs + c), t1 = ld(DM.cell_region_ofs + c + 1);
+  const int abs_on = abs(on_surface);
+  for (int it = t0; it < t1; ++it) {
+    const int32_t token = ld(DM.region_tokens + it);
+    if (token >= OP_UNION)
+      continue;
+    const double d = surf_distance(abs(token) - 1, r, u, abs(token) == abs_on);
+    if (d < min_dist) {
+      if (min_dist - d >= FP_PRECISION * min_dist) {
+        min_dist = d;
+        i_surf = -token;
+      }
+    }
+  }
+}
+
+// =============================================================================
+// Rectangular lattices -- src/lattice.cpp:243-248, 252-306, 310-342, 352-377
+// =============================================================================
+struct LatIdx {
+  int x, y, z;
+};
+
+OMC_HD bool lat_valid(int l, LatIdx i)
+{
+  const int32_t* n = DM.lat_shape + 3 * l;
+  return i.x >= 0 && i.x < ld(n) && i.y >= 0 && i.y < ld(n + 1) && i.z >= 0 && i.z < ld(n + 2);
+}
+OMC_HD int lat_flat(int l, LatIdx i)
+{
+  const int32_t* n = DM.lat_shape + 3 * l;
+  const int nx = ld(n), ny = ld(n + 1);
+  return nx * ny * i.z + nx * i.y + i.x;
+}
+OMC_HD int lat_universe(int l, LatIdx i)
+{
+  return ld(DM.lat_universes + ld(DM.lat_univ_ofs + l) + lat_flat(l, i));
+}
+OMC_HD int lat_axis_index(double r, double ll, double pitch, double u)
+{
+  const double ix_ = (r - ll) / pitch;
+  const long long ix_close = llround(ix_);
+  if (fabs(ix_ - (double)ix_close) < FP_COINCIDENT)
+    return (u > 0) ? (int)ix_close : (int)ix_close - 1;
+  return (int)floor(ix_);
+}
+OMC_HD LatIdx lat_get_indices(int l, V3 r, V3 u)
+{
+  const double* ll = DM.lat_lower_left + 3 * l;
+  const double* p = DM.lat_pitch + 3 * l;
+  LatIdx i;
+  i.x = lat_axis_index(r.x, ld(ll), ld(p), u.x);
+  i.y = lat_axis_index(r.y, ld(ll + 1), ld(p + 1), u.y);
+  i.z = ld(DM.lat_is3d + l) ? lat_axis_index(r.z, ld(ll + 2), ld(p + 2), u.z) : 0;
+  return i;
+}
+OMC_HD V3 lat_local_position(int l, V3 r, LatIdx i)
+{
+  const double* ll = DM.lat_lower_left + 3 * l;
+  const double* p = DM.lat_pitch + 3 * l;
+  r.x -= (ld(ll) + (i.x + 0.5) * ld(p));
+  r.y -= (ld(ll + 1) + (i.y + 0.5) * ld(p + 1));
+  if (ld(DM.lat_is3d + l))
+    r.z -= (ld(ll + 2) + (i.z + 0.5) * ld(p + 2));
+  return r;
+}
+// returns distance; translation packed as (tx+1) | (ty+1)<<2 | (tz+1)<<4
+OMC_HD int pack_trans(int tx, int ty, int tz)
+{
+  return (tx + 1) | ((ty + 1) << 2) | ((tz + 1) << 4);
+}
+constexpr int TRANS_NONE = 1 | (1 << 2) | (1 << 4);
+OMC_HD double lat_distance(int l, V3 r, V3 u, int& trans)
+{
+  const double* p = DM.lat_pitch + 3 * l;
+  const double x0 = copysign(0.5 * ld(p), u.x);
+  const double y0 = copysign(0.5 * ld(p + 1), u.y);
+  double d = INFTY;
+  trans = TRANS_NONE;
+  if ((fabs(r.x - x0) > FP_PRECISION) && u.x != 0) {
+    d = (x0 - r.x) / u.x;
+    trans = pack_trans(u.x > 0 ? 1 : -1, 0, 0);
+  }
+  if ((fabs(r.y - y0) > FP_PRECISION) && u.y != 0) {
+    const double this_d = (y0 - r.y) / u.y;
+    if (this_d < d) {
+      d = this_d;
+      trans = pack_trans(0, u.y > 0 ? 1 : -1, 0);
+    }
+  }
+  if (ld(DM.lat_is3d + l)) {
+    const double z0 = copysign(0.5 * ld(p + 2), u.z);
+    if ((fabs(r.z - z0) > FP_PRECISION) && u.z != 0) {
+      const double this_d = (z0 - r.z) / u.z;
+      if (this_d < d) {
+        d = this_d;
+        trans = pack_trans(0, 0, u.z > 0 ? 1 : -1);
+      }
+    }
+  }
+  return d;
+}
+
+// =============================================================================
+// Per-particle accessors over the SoA columns
+// =============================================================================
+#define LV(col, lvl) (ps.col[(int64_t)(lvl)*ps.cap + i])
+
+OMC_HD V3 get_r(const PState& ps, int64_t i, int lvl)
+{
+  return v3(LV(rx, lvl), LV(ry, lvl), LV(rz, lvl));
+}
+OMC_HD V3 get_u(const PState& ps, int64_t i, int lvl)
+{
+  return v3(LV(ux, lvl), LV(uy, lvl), LV(uz, lvl));
+}
+OMC_HD void set_r(const PState& ps, int64_t i, int lvl, V3 r)
+{
+  LV(rx, lvl) = r.x;
+  LV(ry, lvl) = r.y;
+  LV(rz, lvl) = r.z;
+}
+OMC_HD void set_u(const PState& ps, int64_t i, int lvl, V3 u)
+{
+  LV(ux, lvl) = u.x;
+  LV(uy, lvl) = u.y;
+  LV(uz, lvl) = u.z;
+}
+OMC_HD void reset_level(const PState& ps, int64_t i, int lvl)
+{ // LocalCoord::reset, include/openmc/particle_data.h
+  LV(cell, lvl) = C_NONE;
+  LV(universe, lvl) = C_NONE;
+  LV(lattice, lvl) = C_NONE;
+  LV(lat_x, lvl) = 0;
+  LV(lat_y, lvl) = 0;
+  LV(lat_z, lvl) = 0;
+}
+
+// =============================================================================
+// Locate -- src/geometry.cpp:66-98, 102-252, 256-297 ; src/universe.cpp:40-60
+// The walk keeps only the current level in registers and streams the deeper
+// levels straight into their SoA columns.  Neighbour lists only change the
+// search order inside a universe, so the universe's own cell list is searched.
+// =============================================================================
+OMC_HD int cell_instance_at_level(const PState& ps, int64_t i, int level)
+{
+  const int c = LV(cell, level);
+  const int map = ld(DM.cell_distribcell_index + c);
+  if (map == C_NONE)
+    return C_NONE;
+  int instance = 0;
+  for (int k = 0; k < level; k++) {
+    const int c_k = LV(cell, k);
+    const int type = ld(DM.cell_type + c_k);
+    if (type == OMCGPU_FILL_UNIVERSE) {
+      instance += ld(DM.cell_offset + ld(DM.cell_offset_ofs + c_k) + map);
+    } else if (type == OMCGPU_FILL_LATTICE) {
+      instance += ld(DM.cell_offset + ld(DM.cell_offset_ofs + c_k) + map);
+      const int lat = LV(lattice, k + 1);
+      LatIdx li;
+      li.x = LV(lat_x, k + 1);
+      li.y = LV(lat_y, k + 1);
+      li.z = LV(lat_z, k + 1);
+      if (lat_valid(lat, li)) {
+        const int32_t* n = DM.lat_shape + 3 * lat;
+        instance += ld(DM.lat_offsets + ld(DM.lat_offset_ofs + lat) +
+                       ld(n) * ld(n + 1) * ld(n + 2) * map + lat_flat(lat, li));
+      }
+    }
+  }
+  return instance;
+}
+
+// Starting at level `lvl` (whose universe/r/u columns are already set), descend
+// until a material cell is found.  Returns false when the particle is in no cell
+// of the current universe (or left a lattice without an outer universe).
+OMC_HD bool find_cell_inner(const PState& ps, int64_t i, int lvl, int surface)
+{
+  V3 r = get_r(ps, i, lvl);
+  V3 u = get_u(ps, i, lvl);
+  int univ = LV(universe, lvl);
+  for (;; ++lvl) {
+    // Universe::find_cell
+    int found = C_NONE;
+    const int k1 = ld(DM.univ_cell_ofs + univ + 1);
+    for (int k = ld(DM.univ_cell_ofs + univ); k < k1; ++k) {
+      const int c = ld(DM.univ_cells + k);
+      if (cell_contains(c, r, u, surface)) {
+        found = c;
+        break;
+      }
+    }
+    if (found == C_NONE) {
+      ps.n_coord[i] = lvl + 1;
+      return false;
+    }
+    LV(cell, lvl) = found;
+    const int type = ld(DM.cell_type + found);
+    if (type == OMCGPU_FILL_MATERIAL) {
+      ps.n_coord[i] = lvl + 1;
+      int inst = 0;
+      if (ld(DM.cell_distribcell_index + found) >= 0)
+        inst = cell_instance_at_level(ps, i, lvl);
+      ps.cell_instance[i] = inst;
+      const int m0 = ld(DM.cell_mat_ofs + found), m1 = ld(DM.cell_mat_ofs + found + 1);
+      const int t0 = ld(DM.cell_sqrtkT_ofs + found), t1 = ld(DM.cell_sqrtkT_ofs + found + 1);
+      ps.material_last[i] = ps.material[i];
+      ps.material[i] = ld(DM.cell_material + m0 + ((m1 - m0) > 1 ? inst : 0));
+      ps.sqrtkT_last[i] = ps.sqrtkT[i];
+      ps.sqrtkT[i] = ld(DM.cell_sqrtkT + t0 + ((t1 - t0) > 1 ? inst : 0));
+      return true;
+    }
+    if (lvl + 1 >= OMCGPU_MAX_COORD) {
+      ps.n_coord[i] = lvl + 1;
+      return false;
+    }
+    const double* t = DM.cell_translation + 3 * found;
+    r.x -= ld(t);
+    r.y -= ld(t + 1);
+    r.z -= ld(t + 2);
+    const int nl = lvl + 1;
+    const int fill = ld(DM.cell_fill + found);
+    if (type == OMCGPU_FILL_UNIVERSE) {
+      univ = fill;
+      // lattice column of the new level stays C_NONE (levels were reset)
+    } else {
+      const LatIdx li = lat_get_indices(fill, r, u);
+      r = lat_local_position(fill, r, li);
+      LV(lattice, nl) = fill;
+      LV(lat_x, nl) = li.x;
+      LV(lat_y, nl) = li.y;
+      LV(lat_z, nl) = li.z;
+      if (lat_valid(fill, li)) {
+        univ = lat_universe(fill, li);
+      } else {
+        univ = ld(DM.lat_outer + fill);
+        if (univ == C_NONE) {
+          ps.n_coord[i] = nl;
+          return false;
+        }
+      }
+    }
+    LV(universe, nl) = univ;
+    set_r(ps, i, nl, r);
+    set_u(ps, i, nl, u);
+  }
+}
+
+OMC_HD void reset_deeper(const PState& ps, int64_t i, int n_coord)
+{
+  const int L = DM.n_coord_levels < OMCGPU_MAX_COORD ? DM.n_coord_levels : OMCGPU_MAX_COORD;
+  for (int l = n_coord; l < L; ++l)
+    reset_level(ps, i, l);
+}
+
+// exhaustive_find_cell / neighbor_list_find_cell with n_coord already set
+OMC_HD bool find_cell_from(const PState& ps, int64_t i, int n_coord, int surface)
+{
+  reset_deeper(ps, i, n_coord);
+  return find_cell_inner(ps, i, n_coord - 1, surface);
+}
+
+OMC_HD bool find_cell_from_root(const PState& ps, int64_t i, int surface)
+{
+  LV(universe, 0) = DM.root_universe;
+  return find_cell_from(ps, i, 1, surface);
+}
+
+// =============================================================================
+// distance_to_boundary -- src/geometry.cpp:361-453
+// =============================================================================
+struct Boundary {
+  double distance;
+  int surface;
+  int level;
+  int trans;
+};
+
+OMC_HD Boundary distance_to_boundary(const PState& ps, int64_t i, int n_coord, int surface,
+  bool& negative_lattice_distance)
+{
+  Boundary info;
+  info.distance = inf_d();
+  info.surface = SURFACE_NONE;
+  info.level = 0;
+  info.trans = TRANS_NONE;
+  double d_lat = inf_d();
+  int level_lat_trans = TRANS_NONE;
+  negative_lattice_distance = false;
+  for (int l = 0; l < n_coord; l++) {
+    const V3 r = get_r(ps, i, l);
+    const V3 u = get_u(ps, i, l);
+    const int c = LV(cell, l);
+    double d_surf;
+    int level_surf_cross;
+    cell_distance(c, r, u, surface, d_surf, level_surf_cross);
+    const int lat = LV(lattice, l);
+    if (lat != C_NONE) {
+      d_lat = lat_distance(lat, r, u, level_lat_trans);
+      if (d_lat < 0)
+        negative_lattice_distance = true;
+    }
+    const double d = info.distance;
+    if (d_surf < d_lat - FP_COINCIDENT) {
+      if (d == inf_d() || (d - d_surf) / d >= FP_REL_PRECISION) {
+        info.distance = d_surf;
+        if (ld(DM.cell_simple + c) || d_surf == INFTY) {
+          info.surface = level_surf_cross;
+        } else {
+          const V3 r_hit = v3(r.x + d_surf * u.x, r.y + d_surf * u.y, r.z + d_surf * u.z);
+          const V3 nrm = surf_normal(abs(level_surf_cross) - 1, r_hit);
+          info.surface = (dot(u, nrm) > 0) ? abs(level_surf_cross) : -abs(level_surf_cross);
+        }
+        info.trans = TRANS_NONE;
+        info.level = l + 1;
+      }
+    } else {
+      if (d == inf_d() || (d - d_lat) / d >= FP_REL_PRECISION) {
+        info.distance = d_lat;
+        info.surface = SURFACE_NONE;
+        info.trans = level_lat_trans;
+        info.level = l + 1;
+      }
+    }
+  }
+  return info;
+}
+
+// =============================================================================
+// Multigroup cross sections -- src/mgxs.cpp:599-675 (the (t,a) cache of the
+// reference is a pure memoisation of these two index functions; the device
+// recomputes them instead of carrying 48 bytes of cache per particle)
+// =============================================================================
+OMC_HD int mg_temperature_index(int m, double sqrtkT)
+{
+  const int b0 = ld(DM.mgm_blk_ofs + m);
+  const int nt = ld(DM.mgm_n_temps + m);
+  if (nt == 1)
+    return 0;
+  const double kT = sqrtkT * sqrtkT;
+  int best = 0;
+  double bestv = fabs(ld(DM.mgm_kTs + b0) - kT);
+  for (int t = 1; t < nt; ++t) {
+    const double v = fabs(ld(DM.mgm_kTs + b0 + t) - kT);
+    if (v < bestv) {
+      bestv = v;
+      best = t;
+    }
+  }
+  return best;
+}
+OMC_HD int mg_angle_index(int m, V3 u)
+{
+  if (ld(DM.mgm_isotropic + m))
+    return 0;
+  const int n_pol = ld(DM.mgm_n_pol + m), n_azi = ld(DM.mgm_n_azi + m);
+  const double my_pol = acos(u.z);
+  const double my_azi = atan2(u.y, u.x);
+  double delta_angle = PI / n_pol;
+  const int pp = (int)floor(my_pol / delta_angle);
+  delta_angle = 2. * PI / n_azi;
+  const int aa = (int)floor((my_azi + PI) / delta_angle);
+  return n_azi * pp + aa;
+}
+OMC_HD int mg_ba(int m, int t, int a)
+{
+  return ld(DM.blk_ang_ofs + ld(DM.mgm_blk_ofs + m) + t) + a;
+}
+
+// src/mgxs.cpp:537-586
+OMC_HD void mg_sample_fission_energy(int ba, int gin, int& dg, int& gout, uint64_t& seed)
+{
+  const int G = DM.mg_n_groups, DG = DM.mg_n_delayed;
+  const double nu_fission = ld(DM.mg_nu_fission + ba * G + gin);
+  double prob_prompt = ld(DM.mg_prompt_nu_fission + ba * G + gin);
+  const double xi_pd = prn(seed) * nu_fission;
+  const double xi_gout = prn(seed);
+  if (xi_pd <= prob_prompt) {
+    dg = -1;
+    double prob_gout = 0.;
+    const double* chi = DM.mg_chi_prompt + ((int64_t)ba * G + gin) * G;
+    for (gout = 0; gout < G; ++gout) {
+      prob_gout += ld(chi + gout);
+      if (xi_gout < prob_gout)
+        break;
+    }
+  } else {
+    for (dg = 0; dg < DG; ++dg) {
+      prob_prompt += ld(DM.mg_delayed_nu_fission + ((int64_t)ba * DG + dg) * G + gin);
+      if (xi_pd < prob_prompt)
+        break;
+    }
+    dg = dg < DG - 1 ? dg : DG - 1;
+    double prob_gout = 0.;
+    const double* chi = DM.mg_chi_delayed + (((int64_t)ba * DG + dg) * G + gin) * G;
+    for (gout = 0; gout < G; ++gout) {
+      prob_gout += ld(chi + gout);
+      if (xi_gout < prob_gout)
+        break;
+    }
+  }
+}
+
+// src/scattdata.cpp:158-170, 341-367, 528-558, 729-775
+OMC_HD void mg_sample_scatter(int ba, int gin, int& gout, double& mu, double& wgt, uint64_t& seed)
+{
+  const int G = DM.mg_n_groups;
+  const int gmin = ld(DM.sc_gmin + ba * G + gin), gmax = ld(DM.sc_gmax + ba * G + gin);
+  const int e0 = ld(DM.sc_gofs + ba * G + gin);
+  const int order = ld(DM.sc_order + ba);
+  const double xi = prn(seed);
+  double prob = 0.;
+  int i_gout = 0;
+  for (gout = gmin; gout < gmax; ++gout) {
+    prob += ld(DM.sc_energy + e0 + i_gout);
+    if (xi < prob)
+      break;
+    ++i_gout;
+  }
+  const int64_t d0 = (int64_t)ld(DM.sc_dofs + ba * G + gin) + (int64_t)i_gout * order;
+  const double* dist = DM.sc_dist + d0;
+  const int fmt = ld(DM.sc_format + ba);
+  if (fmt == OMCGPU_SCATT_LEGENDRE) {
+    const double Mx = ld(DM.sc_maxval + e0 + i_gout);
+    for (int samples = 0; samples < MAX_SAMPLE; ++samples) {
+      mu = 2. * prn(seed) - 1.;
+      const double f = evaluate_legendre(order - 1, dist, mu);
+      if (f > 0.) {
+        const double uu = prn(seed) * Mx;
+        if (uu <= f)
+          break;
+      }
+    }
+  } else if (fmt == OMCGPU_SCATT_HISTOGRAM) {
+    const double* mugrid = DM.sc_mu + ld(DM.sc_mu_ofs + ba);
+    const double xi2 = prn(seed);
+    int imu;
+    if (xi2 < ld(dist)) {
+      imu = 0;
+    } else { // std::upper_bound
+      int lo = 0, len = order;
+      while (len > 0) {
+        int half = len >> 1;
+        if (!(xi2 < ld(dist + lo + half))) {
+          lo += half + 1;
+          len -= half + 1;
+        } else {
+          len = half;
+        }
+      }
+      imu = lo;
+    }
+    mu = prn(seed) * ld(DM.sc_dmu + ba) + ld(mugrid + imu);
+    if (mu < -1.)
+      mu = -1.;
+    else if (mu > 1.)
+      mu = 1.;
+  } else {
+    const double* fmu = DM.sc_fmu + d0;
+    const double* mugrid = DM.sc_mu + ld(DM.sc_mu_ofs + ba);
+    const int NP = order;
+    const double xi2 = prn(seed);
+    double c_k = ld(dist);
+    int k;
+    for (k = 0; k < NP - 1; k++) {
+      const double c_k1 = ld(dist + k + 1);
+      if (xi2 < c_k1)
+        break;
+      c_k = c_k1;
+    }
+    k = k < NP - 2 ? k : NP - 2;
+    const double p0 = ld(fmu + k), mu0 = ld(mugrid + k);
+    const double p1 = ld(fmu + k + 1), mu1 = ld(mugrid + k + 1);
+    if (p0 == p1) {
+      mu = mu0 + (xi2 - c_k) / p0;
+    } else {
+      const double frac = (p1 - p0) / (mu1 - mu0);
+      mu = mu0 + (sqrt(fmax(0., p0 * p0 + 2. * frac * (xi2 - c_k))) - p0) / frac;
+    }
+    if (mu < -1.)
+      mu = -1.;
+    else if (mu > 1.)
+      mu = 1.;
+  }
+  wgt *= ld(DM.sc_mult + e0 + i_gout);
+}
+
+// ScattData::get_xs(SCATTER, gin) -- src/scattdata.cpp:174-225
+OMC_HD double mg_scatter_xs(int ba, int g)
+{
+  const int G = DM.mg_n_groups;
+  const int e0 = ld(DM.sc_gofs + ba * G + g);
+  const int n = ld(DM.sc_gmax + ba * G + g) - ld(DM.sc_gmin + ba * G + g) + 1;
+  double ip = 0.0;
+  for (int k = 0; k < n; ++k)
+    ip = ip + ld(DM.sc_mult + e0 + k) * ld(DM.sc_energy + e0 + k);
+  return ld(DM.sc_scattxs + ba * G + g) / ip;
+}
+
+// =============================================================================
+// Continuous-energy cross sections -- src/material.cpp:829-901,
+// src/nuclide.cpp:616-775, src/reaction.cpp:98-112
+// =============================================================================
+struct MicroXS {
+  double total, absorption, fission, nu_fission;
+  int index_grid;
+  double interp_factor;
+};
+
+// Hash bin of the union log grid: int(log(E/E_min)/spacing), src/material.cpp:833-834.
+// The device log() may differ from the host libm in the last ulp, which could
+// move an energy that sits on a bin edge into the neighbouring bin.  hash_edge[k]
+// is the smallest double the HOST libm maps to bin >= k (built once at init),
+// so one or two comparisons make the bin bit-identical to the reference's.
+OMC_HD int ce_log_index(double E)
+{
+  int k = (int)(log(E / DM.energy_min) / DM.log_spacing);
+  const int nb = DM.n_log_bins;
+  k = k < 0 ? 0 : (k > nb ? nb : k);
+  while (k > 0 && E < ld(DM.hash_edge + k))
+    --k;
+  while (k < nb && E >= ld(DM.hash_edge + k + 1))
+    ++k;
+  return k;
+}
+
+OMC_HD void ce_micro_xs(int nuc, int i_log, double E, MicroXS& micro)
+{
+  const int64_t g0 = ld(DM.nuc_grid_ofs + nuc);
+  const int64_t n_grid = ld(DM.nuc_grid_ofs + nuc + 1) - g0;
+  const double* energy = DM.nuc_energy + g0;
+  int i_grid;
+  if (E < ld(energy)) {
+    i_grid = 0;
+  } else if (E > ld(energy + n_grid - 1)) {
+    i_grid = (int)n_grid - 2;
+  } else {
+    const int32_t* gi = DM.nuc_grid_index + (int64_t)nuc * (DM.n_log_bins + 1) + i_log;
+    const int i_low = ld(gi);
+    const int i_high = ld(gi + 1) + 1;
+    i_grid = i_low + (int)lower_bound_index(energy + i_low, (int64_t)(i_high - i_low), E);
+  }
+  double e0 = ld(energy + i_grid), e1 = ld(energy + i_grid + 1);
+  if (e0 == e1) {
+    ++i_grid;
+    e0 = e1;
+    e1 = ld(energy + i_grid + 1);
+  }
+  const double f = (E - e0) / (e1 - e0);
+  micro.index_grid = i_grid;
+  micro.interp_factor = f;
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  // two adjacent 32-byte rows: exactly two sectors
+  const double2* row = reinterpret_cast<const double2*>(DM.nuc_xs) + 2 * (g0 + i_grid);
+  const double2 a01 = __ldg(row), a23 = __ldg(row + 1);
+  const double2 b01 = __ldg(row + 2), b23 = __ldg(row + 3);
+  const double a0 = a01.x, a1 = a01.y, a2 = a23.x, a3 = a23.y;
+  const double b0 = b01.x, b1 = b01.y, b2 = b23.x, b3 = b23.y;
+#else
+  const double* row = DM.nuc_xs + 4 * (g0 + i_grid);
+  const double a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3];
+  const double b0 = row[4], b1 = row[5], b2 = row[6], b3 = row[7];
+#endif
+  micro.total = (1.0 - f) * a0 + f * b0;
+  micro.absorption = (1.0 - f) * a1 + f * b1;
+  if (ld(DM.nuc_fissionable + nuc)) {
+    micro.fission = (1.0 - f) * a2 + f * b2;
+    micro.nu_fission = (1.0 - f) * a3 + f * b3;
+  } else {
+    micro.fission = 0.0;
+    micro.nu_fission = 0.0;
+  }
+}
+
+OMC_HD double ce_reaction_xs(int rx, const MicroXS& micro)
+{
+  const int thr = ld(DM.rx_threshold + rx);
+  if (micro.index_grid < thr)
+    return 0.0;
+  const double* v = DM.rx_xs + ld(DM.rx_xs_ofs + rx) + (micro.index_grid - thr);
+  return (1.0 - micro.interp_factor) * ld(v) + micro.interp_factor * ld(v + 1);
+}
+
+// Material::calculate_neutron_xs: out[4] = total, absorption, fission, nu-fission
+OMC_HD void ce_macro_xs(int m, double E, double& t, double& a, double& f, double& nf,
+  int32_t* i_grid_out, int max_nuc)
+{
+  t = a = f = nf = 0.0;
+  const int i_log = ce_log_index(E);
+  const int k0 = ld(DM.mat_nuc_ofs + m), k1 = ld(DM.mat_nuc_ofs + m + 1);
+  for (int k = k0; k < k1; ++k) {
+    MicroXS micro;
+    ce_micro_xs(ld(DM.mat_nuclide + k), i_log, E, micro);
+    const double atom_density = ld(DM.mat_atom_density + k);
+    t += atom_density * micro.total;
+    a += atom_density * micro.absorption;
+    f += atom_density * micro.fission;
+    nf += atom_density * micro.nu_fission;
+    if (i_grid_out && (k - k0) < max_nuc)
+      i_grid_out[k - k0] = micro.index_grid;
+  }
+}
+
+// src/endf.cpp:125-134 (Polynomial), 168-226 (Tabulated1D, lin-lin)
+OMC_HD double eval_function(int fn, double x)
+{
+  const int o0 = ld(DM.fn_ofs + fn), o1 = ld(DM.fn_ofs + fn + 1);
+  const double* d = DM.fn_data + o0;
+  const int n = o1 - o0;
+  if (ld(DM.fn_type + fn) == OMCGPU_FN_POLYNOMIAL) {
+    double y = 0.0;
+    for (int k = n - 1; k >= 0; --k)
+      y = y * x + ld(d + k);
+    return y;
+  }
+  const int np = n / 2;
+  const double* ys = d + np;
+  if (x < ld(d))
+    return ld(ys);
+  if (x > ld(d + np - 1))
+    return ld(ys + np - 1);
+  const int k = (int)lower_bound_index(d, (int64_t)np, x);
+  const double x0 = ld(d + k), x1 = ld(d + k + 1), y0 = ld(ys + k), y1 = ld(ys + k + 1);
+  const double r = (x - x0) / (x1 - x0);
+  return y0 + r * (y1 - y0);
+}
+
+// Nuclide::nu, src/nuclide.cpp:535-576 ; mode 0 prompt, 1 delayed, 2 total
+OMC_HD double ce_nu(int nuc, double E, int mode)
+{
+  if (!ld(DM.nuc_fissionable + nuc))
+    return 0.0;
+  const int rx = ld(DM.nuc_rx_ofs + nuc) + ld(DM.nuc_fission_rx + nuc);
+  const int p0 = ld(DM.rx_prod_ofs + rx), p1 = ld(DM.rx_prod_ofs + rx + 1);
+  if (mode == 0)
+    return eval_function(ld(DM.prod_yield_fn + p0), E);
+  if (mode == 1) {
+    if (ld(DM.nuc_n_precursor + nuc) > 0 && DM.create_delayed_neutrons) {
+      double nu = 0.0;
+      for (int k = p0 + 1; k < p1; ++k)
+        if (ld(DM.prod_emission + k) == 1)
+          nu += eval_function(ld(DM.prod_yield_fn + k), E);
+      return nu;
+    }
+    return 0.0;
+  }
+  const int tf = ld(DM.nuc_total_nu_fn + nuc);
+  if (tf >= 0 && DM.create_delayed_neutrons)
+    return eval_function(tf, E);
+  return eval_function(ld(DM.prod_yield_fn + p0), E);
+}
+
+// ReactionProduct::sample -> UncorrelatedAngleEnergy::sample (isotropic angle),
+// src/reaction_product.cpp:109-130, src/secondary_uncorrelated.cpp:53-66,
+// src/distribution_energy.cpp:49-52, 284-298, 309-327, 347-361
+OMC_HD void ce_sample_product(int prod, double E_in, double& E_out, double& mu, uint64_t& seed)
+{
+  mu = -1. + (1. - (-1.)) * prn(seed);
+  const double par0 = ld(DM.prod_par + 2 * prod), par1 = ld(DM.prod_par + 2 * prod + 1);
+  const int f0 = ld(DM.prod_fn + 2 * prod), f1 = ld(DM.prod_fn + 2 * prod + 1);
+  switch (ld(DM.prod_elaw + prod)) {
+  case OMCGPU_ELAW_LEVEL:
+    E_out = par1 * (E_in - par0);
+    break;
+  case OMCGPU_ELAW_MAXWELL: {
+    const double theta = eval_function(f0, E_in);
+    for (int k = 0; k < MAX_SAMPLE; ++k) {
+      E_out = maxwell_spectrum(theta, seed);
+      if (E_out <= E_in - par0)
+        break;
+    }
+    break;
+  }
+  case OMCGPU_ELAW_EVAPORATION: {
+    const double theta = eval_function(f0, E_in);
+    const double y = (E_in - par0) / theta;
+    const double v = 1.0 - exp(-y);
+    double x = 0.0;
+    for (int k = 0; k < MAX_SAMPLE; ++k) {
+      const double a1 = 1.0 - v * prn(seed);
+      const double a2 = 1.0 - v * prn(seed);
+      x = -log(a1 * a2);
+      if (x <= y)
+        break;
+    }
+    E_out = x * theta;
+    break;
+  }
+  case OMCGPU_ELAW_WATT: {
+    const double a = eval_function(f0, E_in);
+    const double b = eval_function(f1, E_in);
+    for (int k = 0; k < MAX_SAMPLE; ++k) {
+      E_out = watt_spectrum(a, b, seed);
+      if (E_out <= E_in - par0)
+        break;
+    }
+    break;
+  }
+  default:
+    E_out = E_in;
+  }
+}
+
+// src/physics.cpp:990-1041
+OMC_HD V3 sample_cxs_target_velocity(double awr, double E, V3 u, double kT, uint64_t& seed)
+{
+  const double beta_vn = sqrt(awr * E / kT);
+  const double alpha = 1.0 / (1.0 + sqrt(PI) * beta_vn / 2.0);
+  double beta_vt_sq = 0.0, mu = 0.0;
+  for (int it = 0; it < MAX_SAMPLE; ++it) {
+    const double r1 = prn(seed);
+    const double r2 = prn(seed);
+    if (prn(seed) < alpha) {
+      beta_vt_sq = -log(r1 * r2);
+    } else {
+      const double c = cos(PI / 2.0 * prn(seed));
+      beta_vt_sq = -log(r1) - log(r2) * c * c;
+    }
+    const double beta_vt = sqrt(beta_vt_sq);
+    mu = -1. + (1. - (-1.)) * prn(seed);
+    const double accept_prob =
+      sqrt(beta_vn * beta_vn + beta_vt_sq - 2 * beta_vn * beta_vt * mu) / (beta_vn + beta_vt);
+    if (prn(seed) < accept_prob)
+      break;
+  }
+  const double vt = sqrt(beta_vt_sq * kT / awr);
+  const V3 d = rotate_angle(u, mu, seed);
+  return v3(vt * d.x, vt * d.y, vt * d.z);
+}
+
+// =============================================================================
+// Fission bank append -- reserves `nu` consecutive slots with one atomic
+// (SharedArray::thread_safe_append semantics: sites that do not fit are dropped
+// and the progeny counter is not advanced for them)
+// =============================================================================
+OMC_HD int32_t atomic_add_i32(int32_t* p, int32_t v)
+{
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  return atomicAdd(p, v);
+#else
+  int32_t old = *p;
+  *p += v;
+  return old;
+#endif
+}
+OMC_HD void atomic_add_u64(unsigned long long* p, unsigned long long v)
+{
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
+
+OMC_HD void bank_store(const Bank& fb, int64_t slot, V3 r, V3 u, double E, double time, double wgt,
+  int dg, int64_t parent_id, int64_t progeny_id)
+{
+  fb.x[slot] = r.x;
+  fb.y[slot] = r.y;
+  fb.z[slot] = r.z;
+  fb.u[slot] = u.x;
+  fb.v[slot] = u.y;
+  fb.w[slot] = u.z;
+  fb.E[slot] = E;
+  fb.time[slot] = time;
+  fb.wgt[slot] = wgt;
+  fb.delayed_group[slot] = dg;
+  fb.parent_id[slot] = parent_id;
+  fb.progeny_id[slot] = progeny_id;
+}
+
+// =============================================================================
+// Collision: multigroup -- src/physics_mg.cpp:26-259
+// =============================================================================
+struct Collider { // registers of the colliding particle
+  V3 r, u;
+  double E, wgt, time, k_abs;
+  int g, material;
+  uint64_t seed;
+  int n_progeny;
+  int64_t id;
+  double xs_total, xs_absorption, xs_nu_fission;
+};
+
+OMC_HD void russian_roulette(Collider& p, double weight_survive)
+{ // src/physics_common.cpp:12-19
+  if (weight_survive * prn(p.seed) < p.wgt)
+    p.wgt = weight_survive;
+  else
+    p.wgt = 0.;
+}
+
+// shared by MG and CE: number of sites and slot reservation
+OMC_HD int fission_site_count(Collider& p, double nu_t)
+{
+  int nu = (int)nu_t;
+  if (prn(p.seed) <= (nu_t - nu))
+    ++nu;
+  return nu;
+}
+
+OMC_HD void collision_mg(Collider& p, int ba, const GenCtx& gc, const Bank& fb)
+{
+  const int G = DM.mg_n_groups;
+  if (ld(DM.mat_fissionable + p.material)) { // create_fission_sites :98-237
+    const double nu_t = p.wgt / gc.keff * 1.0 * p.xs_nu_fission / p.xs_total;
+    const int nu = fission_site_count(p, nu_t);
+    if (nu > 0) {
+      const int32_t base = atomic_add_i32(gc.n_fission, nu);
+      for (int k = 0; k < nu; ++k) {
+        const double mu = 2. * prn(p.seed) - 1.;
+        const double phi = 2. * PI * prn(p.seed);
+        const V3 su = v3(mu, sqrt(1. - mu * mu) * cos(phi), sqrt(1. - mu * mu) * sin(phi));
+        int dg, gout;
+        mg_sample_fission_energy(ba, p.g, dg, gout, p.seed);
+        double t = p.time;
+        if (dg != -1) {
+          const double decay_rate = ld(DM.mg_decay_rate + mg_ba(p.material, 0, 0) * DM.mg_n_delayed + dg);
+          t -= log(prn(p.seed)) / decay_rate;
+        }
+        const int64_t slot = (int64_t)base + k;
+        if (slot < gc.fission_cap) {
+          bank_store(fb, slot, p.r, su, (double)gout, t, 1.0, dg + 1, p.id, p.n_progeny);
+          p.n_progeny++;
+        }
+      }
+    }
+  }
+  if (p.xs_absorption > 0.) { // absorption :239-259
+    if (DM.survival_biasing) {
+      const double wgt_absorb = p.wgt * p.xs_absorption / p.xs_total;
+      p.wgt -= wgt_absorb;
+      p.k_abs += wgt_absorb * p.xs_nu_fission / p.xs_absorption;
+    } else if (p.xs_absorption > prn(p.seed) * p.xs_total) {
+      p.k_abs += p.wgt * p.xs_nu_fission / p.xs_absorption;
+      p.wgt = 0.0;
+    }
+  }
+  if (p.wgt == 0.0)
+    return;
+  int gout;
+  double mu;
+  mg_sample_scatter(ba, p.g, gout, mu, p.wgt, p.seed); // scatter :83-96
+  p.g = gout;
+  p.u = rotate_angle(p.u, mu, p.seed);
+  p.E = ld(DM.mg_energy_bin_avg + gout);
+  (void)G;
+  if (DM.survival_biasing && p.wgt < DM.weight_cutoff)
+    russian_roulette(p, DM.weight_survive);
+}
+
+// =============================================================================
+// Collision: continuous energy -- src/physics.cpp:93-285, 494-518, 638-818,
+// 1043-1167.  The reference reads the per-particle NuclideMicroXS cache that
+// calculate_xs filled at this energy (176 B x n_nuclides per particle); the
+// device recomputes the few entries it needs -- same numbers, no cache.
+// =============================================================================
+OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no_nuclide)
+{
+  no_nuclide = false;
+  const int m = p.material;
+  const int i_log = ce_log_index(p.E);
+  const double cutoff = prn(p.seed) * p.xs_total; // sample_nuclide :494-518
+  double prob = 0.0;
+  int nuc = -1;
+  MicroXS micro;
+  const int k1 = ld(DM.mat_nuc_ofs + m + 1);
+  for (int k = ld(DM.mat_nuc_ofs + m); k < k1; ++k) {
+    const int cand = ld(DM.mat_nuclide + k);
+    ce_micro_xs(cand, i_log, p.E, micro);
+    prob += ld(DM.mat_atom_density + k) * micro.total;
+    if (prob >= cutoff) {
+      nuc = cand;
+      break;
+    }
+  }
+  if (nuc < 0) {
+    no_nuclide = true;
+    p.wgt = 0.0;
+    return;
+  }
+  const int rx0 = ld(DM.nuc_rx_ofs + nuc);
+  if (ld(DM.nuc_fissionable + nuc) && micro.fission > 0.0) { // create_fission_sites :170-285
+    const int rx = rx0 + ld(DM.nuc_fission_rx + nuc);
+    const double nu_t = p.wgt / gc.keff * 1.0 * micro.nu_fission / micro.total;
+    const int nu = fission_site_count(p, nu_t);
+    if (nu > 0) {
+      const int32_t base = atomic_add_i32(gc.n_fission, nu);
+      const int p0 = ld(DM.rx_prod_ofs + rx);
+      for (int k = 0; k < nu; ++k) { // sample_fission_neutron :1043-1117
+        const double nu_tot = ce_nu(nuc, p.E, 2);
+        const double nu_d = ce_nu(nuc, p.E, 1);
+        const double beta = nu_d / nu_tot;
+        int group = 0;
+        double t = p.time;
+        if (prn(p.seed) < beta) {
+          const double xi = prn(p.seed) * nu_d;
+          double pr = 0.0;
+          const int n_prec = ld(DM.nuc_n_precursor + nuc);
+          for (group = 1; group < n_prec; ++group) {
+            pr += eval_function(ld(DM.prod_yield_fn + p0 + group), p.E);
+            if (xi < pr)
+              break;
+          }
+          group = group < n_prec ? group : n_prec;
+          t -= log(prn(p.seed)) / ld(DM.prod_decay_rate + p0 + group);
+        }
+        double E_out = 0.0, mu = 0.0;
+        for (int ns = 0; ns < MAX_SAMPLE; ++ns) {
+          ce_sample_product(p0 + group, p.E, E_out, mu, p.seed);
+          if (E_out < DM.energy_max)
+            break;
+        }
+        const V3 su = rotate_angle(p.u, mu, p.seed);
+        const int64_t slot = (int64_t)base + k;
+        if (slot < gc.fission_cap) {
+          bank_store(fb, slot, p.r, su, E_out, t, 1.0, group, p.id, p.n_progeny);
+          p.n_progeny++;
+        }
+      }
+    }
+  }
+  if (micro.absorption > 0.0) { // absorption :638-672
+    if (DM.survival_biasing) {
+      const double wgt_absorb = p.wgt * micro.absorption / micro.total;
+      p.wgt -= wgt_absorb;
+      p.k_abs += wgt_absorb * micro.nu_fission / micro.absorption;
+    } else if (micro.absorption > prn(p.seed) * micro.total) {
+      p.k_abs += p.wgt * micro.nu_fission / micro.absorption;
+      p.wgt = 0.0;
+    }
+  }
+  if (p.wgt == 0.0)
+    return;
+  // scatter :674-752
+  const double cut = prn(p.seed) * (micro.total - micro.absorption);
+  const double elastic = ce_reaction_xs(rx0, micro); // Nuclide::calculate_elastic_xs
+  if (elastic > cut) {                                 // elastic_scatter :754-818
+    const double kT = ld(DM.nuc_kT + nuc);
+    const double awr = ld(DM.nuc_awr + nuc);
+    double vel = sqrt(p.E);
+    V3 v_n = v3(vel * p.u.x, vel * p.u.y, vel * p.u.z);
+    V3 v_t = v3(0., 0., 0.);
+    if (!(p.E >= DM.free_gas_threshold * kT && awr > 1.0))
+      v_t = sample_cxs_target_velocity(awr, p.E, p.u, kT, p.seed);
+    const V3 v_cm = v3((v_n.x + awr * v_t.x) / (awr + 1.0), (v_n.y + awr * v_t.y) / (awr + 1.0),
+      (v_n.z + awr * v_t.z) / (awr + 1.0));
+    v_n = v3(v_n.x - v_cm.x, v_n.y - v_cm.y, v_n.z - v_cm.z);
+    vel = sqrt(v_n.x * v_n.x + v_n.y * v_n.y + v_n.z * v_n.z);
+    const double mu_cm = -1. + (1. - (-1.)) * prn(p.seed);
+    const V3 u_cm = v3(v_n.x / vel, v_n.y / vel, v_n.z / vel);
+    const V3 rot = rotate_angle(u_cm, mu_cm, p.seed);
+    v_n = v3(vel * rot.x + v_cm.x, vel * rot.y + v_cm.y, vel * rot.z + v_cm.z);
+    p.E = dot(v_n, v_n);
+    vel = sqrt(p.E);
+    p.u = v3(v_n.x / vel, v_n.y / vel, v_n.z / vel);
+  } else { // inelastic_scatter :1119-1167
+    double pr = elastic;
+    int rx = rx0;
+    const int rx_end = ld(DM.nuc_rx_ofs + nuc + 1);
+    for (int j = rx0; j < rx_end && pr < cut; ++j) {
+      if (!ld(DM.rx_inelastic + j))
+        continue;
+      rx = j;
+      pr += ce_reaction_xs(j, micro);
+    }
+    const double E_in = p.E;
+    const int prod = ld(DM.rx_prod_ofs + rx);
+    double E, mu;
+    ce_sample_product(prod, E_in, E, mu, p.seed);
+    if (ld(DM.rx_scatter_in_cm + rx)) {
+      const double E_cm = E;
+      const double A = ld(DM.nuc_awr + nuc);
+      E = E_cm + (E_in + 2.0 * mu * (A + 1.0) * sqrt(E_in * E_cm)) / ((A + 1.0) * (A + 1.0));
+      mu = mu * sqrt(E_cm / E) + 1.0 / (A + 1.0) * sqrt(E_in / E);
+    }
+    if (fabs(mu) > 1.0)
+      mu = copysign(1.0, mu);
+    p.E = E;
+    p.u = rotate_angle(p.u, mu, p.seed);
+    const double yield = eval_function(ld(DM.prod_yield_fn + prod), E_in);
+    if (!(floor(yield) == yield && yield > 0))
+      p.wgt *= yield;
+  }
+  if (DM.survival_biasing && p.wgt < DM.weight_cutoff)
+    russian_roulette(p, DM.weight_survive);
+}
+
+// =============================================================================
+// Tally scoring (tracklength) -- src/tallies/tally_scoring.cpp:31-141, 578-700,
+// 1622-1990, 2416-2541 ; src/mesh.cpp:874-929, 999-1146, 1328-1369 ;
+// src/tallies/filter_{mesh,energy,cell,material,universe}.cpp
+// =============================================================================
+OMC_D void tally_add(double* addr, double val)
+{
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  // warp-aggregated atomic: lanes that hit the same bin are summed first
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, (unsigned long long)addr);
+  const int leader = __ffs(peers) - 1;
+  const int lane = threadIdx.x & 31;
+  double sum = 0.0;
+  unsigned rem = peers;
+  while (rem) {
+    const int src = __ffs(rem) - 1;
+    sum += __shfl_sync(peers, val, src);
+    rem &= rem - 1;
+  }
+  if (lane == leader)
+    atomicAdd(addr, sum);
+#else
+  *addr += val;
+#endif
+}
+
+struct ScoreCtx { // what the scores need from the particle
+  double flux;
+  double xs_total, xs_absorption, xs_fission, xs_nu_fission;
+  int material, g, mg_ba;
+};
+
+OMC_HD double score_value(int score, const ScoreCtx& s, bool& skip)
+{
+  skip = false;
+  if (DM.run_CE) { // score_general_ce_nonanalog
+    switch (score) {
+    case OMCGPU_SCORE_FLUX:
+      return s.flux;
+    case OMCGPU_SCORE_TOTAL:
+      return s.xs_total * s.flux;
+    case OMCGPU_SCORE_SCATTER:
+      return (s.xs_total - s.xs_absorption) * s.flux;
+    case OMCGPU_SCORE_ABSORPTION:
+      return s.xs_absorption * s.flux;
+    case OMCGPU_SCORE_FISSION:
+      skip = (s.xs_fission == 0);
+      return s.xs_fission * s.flux;
+    default:
+      skip = (s.xs_fission == 0);
+      return s.xs_nu_fission * s.flux;
+    }
+  }
+  const int G = DM.mg_n_groups; // score_general_mg, tracklength branch
+  const bool fis = s.material >= 0 && ld(DM.mgm_fissionable + s.material);
+  switch (score) {
+  case OMCGPU_SCORE_FLUX:
+    return s.flux;
+  case OMCGPU_SCORE_TOTAL:
+    return s.xs_total * s.flux;
+  case OMCGPU_SCORE_ABSORPTION:
+    return s.xs_absorption * s.flux;
+  case OMCGPU_SCORE_SCATTER:
+    return s.material >= 0 ? s.flux * mg_scatter_xs(s.mg_ba, s.g) : 0.0;
+  case OMCGPU_SCORE_FISSION:
+    return fis ? s.flux * ld(DM.mg_fission + s.mg_ba * G + s.g) : s.flux * 0.;
+  default:
+    return fis ? s.flux * ld(DM.mg_nu_fission + s.mg_ba * G + s.g) : s.flux * 0.;
+  }
+}
+
+struct MeshDist {
+  int next_index;
+  double distance;
+};
+
+OMC_HD MeshDist mesh_grid_distance(int m, int idx, int k, double r0k, double uk)
+{ // RegularMesh::distance_to_grid_boundary, src/mesh.cpp:1352-1369
+  MeshDist d;
+  d.next_index = idx;
+  d.distance = INFTY;
+  if (fabs(uk) < FP_PRECISION)
+    return d;
+  const double ll = ld(DM.mesh_lower_left + 3 * m + k), w = ld(DM.mesh_width + 3 * m + k);
+  if (uk > 0 && idx <= ld(DM.mesh_shape + 3 * m + k)) {
+    d.next_index = idx + 1;
+    d.distance = ((ll + idx * w) - r0k) / uk;
+  } else if (!(uk > 0) && idx >= 1) {
+    d.next_index = idx - 1;
+    d.distance = ((ll + (idx - 1) * w) - r0k) / uk;
+  }
+  return d;
+}
+
+OMC_HD int mesh_index(int m, double r, int k)
+{
+  return (int)ceil((r - ld(DM.mesh_lower_left + 3 * m + k)) / ld(DM.mesh_width + 3 * m + k));
+}
+
+// Score one tally for one track r0 -> r1.  `bins`/`nb` hold the (<= MAX_COORD)
+// matches of each non-mesh filter; a mesh filter, if present at position
+// `mesh_pos`, streams its (bin, weight) pairs from the ray trace.
+struct TallyEval {
+  int nf;
+  int mesh_pos;
+  int mesh;
+  int nb[OMCGPU_MAX_FILTERS];
+  int bins[OMCGPU_MAX_FILTERS][OMCGPU_MAX_COORD];
+  int stride[OMCGPU_MAX_FILTERS];
+};
+
+OMC_D void tally_emit(const TallyEval& te, int t, int mesh_bin, double mesh_w, const ScoreCtx& sc,
+  double* values)
+{
+  const int ns = ld(DM.tally_n_scores + t);
+  const int32_t* scores = DM.tally_scores + OMCGPU_MAX_SCORES * t;
+  double* results = values + ld(DM.tally_result_ofs + t);
+  // cartesian product over the non-mesh filters (at most MAX_COORD^2 combos; 1 in practice)
+  int n0 = 1, n1 = 1, n2 = 1;
+  if (te.nf > 0)
+    n0 = (te.mesh_pos == 0) ? 1 : te.nb[0];
+  if (te.nf > 1)
+    n1 = (te.mesh_pos == 1) ? 1 : te.nb[1];
+  if (te.nf > 2)
+    n2 = (te.mesh_pos == 2) ? 1 : te.nb[2];
+  for (int a = 0; a < n0; ++a)
+    for (int b = 0; b < n1; ++b)
+      for (int c = 0; c < n2; ++c) {
+        int64_t index = 0;
+        if (te.nf > 0)
+          index += (int64_t)((te.mesh_pos == 0) ? mesh_bin : te.bins[0][a]) * te.stride[0];
+        if (te.nf > 1)
+          index += (int64_t)((te.mesh_pos == 1) ? mesh_bin : te.bins[1][b]) * te.stride[1];
+        if (te.nf > 2)
+          index += (int64_t)((te.mesh_pos == 2) ? mesh_bin : te.bins[2][c]) * te.stride[2];
+        for (int s = 0; s < ns; ++s) {
+          bool skip;
+          const double score = score_value(ld(scores + s), sc, skip);
+          if (!skip)
+            tally_add(results + index * ns + s, score * mesh_w);
+        }
+      }
+}
+
+OMC_D void score_tracklength(const PState& ps, int64_t i, int n_coord, V3 r0, V3 r1, V3 u,
+  double E_last, const ScoreCtx& sc, double* values)
+{
+  const int G = DM.mg_n_groups;
+  for (int t = 0; t < DM.n_tallies; ++t) {
+    TallyEval te;
+    te.nf = ld(DM.tally_n_filters + t);
+    te.mesh_pos = -1;
+    te.mesh = -1;
+    bool empty = false;
+    for (int k = 0; k < te.nf && !empty; ++k) {
+      const int f = ld(DM.tally_filters + OMCGPU_MAX_FILTERS * t + k);
+      te.stride[k] = ld(DM.tally_strides + OMCGPU_MAX_FILTERS * t + k);
+      te.nb[k] = 0;
+      const int o = ld(DM.filter_data_ofs + f);
+      switch (ld(DM.filter_type + f)) {
+      case OMCGPU_FILTER_MESH:
+        te.mesh_pos = k;
+        te.mesh = ld(DM.filter_mesh + f);
+        te.nb[k] = 1;
+        break;
+      case OMCGPU_FILTER_ENERGY: {
+        const int nbin = ld(DM.filter_n_bins + f);
+        if (!DM.run_CE && ld(DM.filter_matches_groups + f)) {
+          te.bins[k][0] = G - sc.g - 1;
+          te.nb[k] = 1;
+        } else {
+          const double* e = DM.filter_ddata + o;
+          if (E_last >= ld(e) && E_last <= ld(e + nbin)) {
+            te.bins[k][0] = (int)lower_bound_index(e, (int64_t)nbin + 1, E_last);
+            te.nb[k] = 1;
+          }
+        }
+        break;
+      }
+      case OMCGPU_FILTER_CELL:
+        for (int l = 0; l < n_coord; ++l) {
+          const int b = ld(DM.filter_idata + o + LV(cell, l));
+          if (b >= 0)
+            te.bins[k][te.nb[k]++] = b;
+        }
+        break;
+      case OMCGPU_FILTER_MATERIAL:
+        if (sc.material >= 0) {
+          const int b = ld(DM.filter_idata + o + sc.material);
+          if (b >= 0)
+            te.bins[k][te.nb[k]++] = b;
+        }
+        break;
+      default: // universe
+        for (int l = 0; l < n_coord; ++l) {
+          const int b = ld(DM.filter_idata + o + LV(universe, l));
+          if (b >= 0)
+            te.bins[k][te.nb[k]++] = b;
+        }
+        break;
+      }
+      if (te.nb[k] == 0)
+        empty = true;
+    }
+    if (empty)
+      continue;
+    if (te.mesh_pos < 0) {
+      tally_emit(te, t, 0, 1.0, sc, values);
+      continue;
+    }
+    // ---- StructuredMesh::raytrace_mesh, src/mesh.cpp:999-1118 -----------------
+    const int m = te.mesh;
+    const int nd = ld(DM.mesh_ndim + m);
+    const double dx = r1.x - r0.x, dy = r1.y - r0.y, dz = r1.z - r0.z;
+    const double total_distance = sqrt(dx * dx + dy * dy + dz * dz);
+    if (total_distance == 0.0)
+      continue;
+    int ijk[3] = {0, 0, 0};
+    bool in_mesh = true;
+    for (int k = 0; k < nd; ++k) {
+      ijk[k] = mesh_index(m, comp(r0, k) + TINY_BIT * comp(u, k), k);
+      if (ijk[k] < 1 || ijk[k] > ld(DM.mesh_shape + 3 * m + k))
+        in_mesh = false;
+    }
+    const int s0 = ld(DM.mesh_shape + 3 * m), s1 = ld(DM.mesh_shape + 3 * m + 1);
+#define MESH_BIN() \
+  (nd == 1 ? ijk[0] - 1 \
+           : (nd == 2 ? (ijk[1] - 1) * s0 + ijk[0] - 1 \
+                      : ((ijk[2] - 1) * s1 + (ijk[1] - 1)) * s0 + ijk[0] - 1))
+    if (total_distance < 2 * TINY_BIT) {
+      if (in_mesh)
+        tally_emit(te, t, MESH_BIN(), 1.0, sc, values);
+      continue;
+    }
+    MeshDist dist[3];
+    for (int k = 0; k < 3; ++k) {
+      dist[k].next_index = -1;
+      dist[k].distance = INFTY;
+    }
+    for (int k = 0; k < nd; ++k)
+      dist[k] = mesh_grid_distance(m, ijk[k], k, comp(r0, k), comp(u, k));
+    double traveled = 0.0;
+    for (int guard = 0; guard < 1000000; ++guard) {
+      if (in_mesh) {
+        int k = 0;
+        if (dist[1].distance < dist[k].distance)
+          k = 1;
+        if (dist[2].distance < dist[k].distance)
+          k = 2;
+        const double dk = dist[k].distance;
+        tally_emit(te, t, MESH_BIN(),
+          ((dk < total_distance ? dk : total_distance) - traveled) / total_distance, sc, values);
+        traveled = dk;
+        if (traveled >= total_distance)
+          break;
+        ijk[k] = dist[k].next_index;
+        dist[k] = mesh_grid_distance(m, ijk[k], k, comp(r0, k), comp(u, k));
+        in_mesh = (ijk[k] >= 1) && (ijk[k] <= ld(DM.mesh_shape + 3 * m + k));
+      } else {
+        int k_max = -1;
+        for (int k = 0; k < nd; ++k) {
+          if ((ijk[k] < 1 || ijk[k] > ld(DM.mesh_shape + 3 * m + k)) &&
+              (dist[k].distance > traveled)) {
+            traveled = dist[k].distance;
+            k_max = k;
+          }
+        }
+        if (k_max == -1)
+          traveled += TINY_BIT;
+        if (traveled >= total_distance)
+          break;
+        in_mesh = true;
+        for (int k = 0; k < nd; ++k) {
+          ijk[k] = mesh_index(m, comp(r0, k) + (traveled + TINY_BIT) * comp(u, k), k);
+          if (ijk[k] < 1 || ijk[k] > ld(DM.mesh_shape + 3 * m + k))
+            in_mesh = false;
+        }
+        for (int k = 0; k < nd; ++k)
+          dist[k] = mesh_grid_distance(m, ijk[k], k, comp(r0, k), comp(u, k));
+      }
+    }
+#undef MESH_BIN
+  }
+}
+
+} // namespace omc

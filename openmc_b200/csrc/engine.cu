@@ -1,0 +1,1635 @@
+// engine.cu -- event kernels, the event-loop scheduler and the C ABI of
+// include/omcgpu.h.
+//
+// Replaces, for one generation:
+//   transport_event_based            src/simulation.cpp:833-883
+//   process_init_events              src/event.cpp:62-71      -> k_init
+//   process_calculate_xs_events      src/event.cpp:73-105     -> k_xs
+//   process_advance_particle_events  src/event.cpp:107-128    -> k_advance
+//   process_surface_crossing_events  src/event.cpp:130-147    -> k_surface
+//   process_collision_events         src/event.cpp:149-166    -> k_collide
+//   process_death_events             src/event.cpp:168-177    -> k_reduce
+//   sort_fission_bank                src/bank.cpp:76-134      -> scan + k_scatter_bank
+//   synchronize_bank (sampling half) src/eigenvalue.cpp:152-178 -> k_gather_bank
+#include "device.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#if OMC_CUDA
+#include <cooperative_groups.h>
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+namespace cg = cooperative_groups;
+#else
+#include "cuda_emu.h"
+#include <cmath>
+#include <numeric>
+#endif
+
+namespace omc {
+
+constexpr int BLOCK = 256;
+
+// -----------------------------------------------------------------------------
+// kernel plumbing: every kernel is `body(tid, args)` for tid < n_ub.  Under
+// nvcc this is a __global__ launch; in the test-only host compile a loop.
+// -----------------------------------------------------------------------------
+static int64_t g_launches = 0;
+
+#if OMC_CUDA
+#define OMC_KERNEL(name, ArgT, body) \
+  __global__ void __launch_bounds__(BLOCK) name(int64_t n_ub, ArgT a) \
+  { \
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; \
+    if (tid < n_ub) \
+      body(tid, a); \
+  }
+#define OMC_LAUNCH(name, n_ub, stream, args) \
+  do { \
+    if ((n_ub) > 0) { \
+      name<<<(unsigned)(((n_ub) + BLOCK - 1) / BLOCK), BLOCK, 0, stream>>>((int64_t)(n_ub), args); \
+      ++g_launches; \
+    } \
+  } while (0)
+#else
+#define OMC_KERNEL(name, ArgT, body) \
+  void name(int64_t n_ub, ArgT a) \
+  { \
+    for (int64_t tid = 0; tid < n_ub; ++tid) \
+      body(tid, a); \
+  }
+#define OMC_LAUNCH(name, n_ub, stream, args) \
+  do { \
+    if ((n_ub) > 0) { \
+      name((int64_t)(n_ub), args); \
+      ++g_launches; \
+    } \
+  } while (0)
+#endif
+
+// warp-aggregated append (ballot + one atomic per warp), cf. north_star
+OMC_D void queue_append(const Queue& q, int32_t value)
+{
+#if OMC_CUDA
+  cg::coalesced_group g = cg::coalesced_threads();
+  int32_t base = 0;
+  if (g.thread_rank() == 0)
+    base = atomicAdd(q.count, (int32_t)g.size());
+  base = g.shfl(base, 0);
+  q.idx[base + g.thread_rank()] = value;
+#else
+  q.idx[(*q.count)++] = value;
+#endif
+}
+
+// -----------------------------------------------------------------------------
+// event bodies
+// -----------------------------------------------------------------------------
+struct EvArgs {
+  PState ps;
+  GenCtx gc;
+  Bank src;  // source bank (k_init)
+  Bank fb;   // fission bank (k_collide)
+  Queue q_in, q_a, q_b; // input list, and up to two output lists
+};
+
+enum { NEXT_DEAD = -1, NEXT_COLLISION = 0, NEXT_SURFACE = 1 };
+
+OMC_D void mark_lost(const PState& ps, const GenCtx& gc, int64_t i)
+{ // Particle::mark_as_lost, src/particle.cpp:762-785 (count + kill)
+  ps.wgt[i] = 0.0;
+  atomic_add_i32(gc.n_lost, 1);
+}
+
+// initialize_history + Particle::from_source + first locate
+// (src/simulation.cpp:573-649, src/particle.cpp:114-158, :176-193)
+OMC_D bool ev_init(const PState& ps, const GenCtx& gc, const Bank& src, int64_t i)
+{
+  const int L = DM.n_coord_levels < OMCGPU_MAX_COORD ? DM.n_coord_levels : OMCGPU_MAX_COORD;
+  for (int l = 0; l < L; ++l)
+    reset_level(ps, i, l);
+  set_r(ps, i, 0, v3(src.x[i], src.y[i], src.z[i]));
+  set_u(ps, i, 0, v3(src.u[i], src.v[i], src.w[i]));
+  ps.n_coord[i] = 1;
+  ps.surface[i] = SURFACE_NONE;
+  ps.material[i] = C_NONE;
+  ps.material_last[i] = C_NONE;
+  ps.sqrtkT[i] = -1.0;
+  ps.sqrtkT_last[i] = 0.0;
+  ps.cell_instance[i] = 0;
+  const double wgt = src.wgt[i];
+  ps.wgt[i] = wgt;
+  ps.time[i] = src.time[i];
+  if (DM.run_CE) {
+    ps.E[i] = src.E[i];
+    ps.g[i] = 0;
+  } else {
+    const int g = (int)src.E[i];
+    ps.g[i] = g;
+    ps.E[i] = ld(DM.mg_energy_bin_avg + g);
+  }
+  ps.n_progeny[i] = 0;
+  ps.n_event[i] = 0;
+  ps.k_abs[i] = 0.0;
+  ps.k_col[i] = 0.0;
+  ps.k_trk[i] = 0.0;
+  ps.k_leak[i] = 0.0;
+  ps.xs_total[i] = 0.0;
+  ps.xs_absorption[i] = 0.0;
+  ps.xs_fission[i] = 0.0;
+  ps.xs_nu_fission[i] = 0.0;
+  ps.b_surface[i] = 0;
+  ps.b_level_trans[i] = 0;
+  const int64_t id = gc.id_offset + i + 1;
+  const int64_t particle_seed = gc.seed_base + id;
+  ps.seed[i] = future_seed((uint64_t)particle_seed * gc.stride, (uint64_t)gc.master_seed);
+  if (wgt == 0.0)
+    return false;
+  if (!find_cell_from_root(ps, i, SURFACE_NONE)) {
+    mark_lost(ps, gc, i);
+    return false;
+  }
+  ps.cell_last0[i] = LV(cell, 0);
+  return true;
+}
+
+// Particle::event_calculate_xs, src/particle.cpp:160-230 (locate done at birth)
+OMC_D void ev_xs(const PState& ps, int64_t i)
+{
+  const int m = ps.material[i];
+  if (m == MATERIAL_VOID) {
+    ps.xs_total[i] = 0.0;
+    ps.xs_absorption[i] = 0.0;
+    ps.xs_fission[i] = 0.0;
+    ps.xs_nu_fission[i] = 0.0;
+    return;
+  }
+  if (DM.run_CE) {
+    if (m != ps.material_last[i] || ps.sqrtkT[i] != ps.sqrtkT_last[i]) {
+      double t, a, f, nf;
+      ce_macro_xs(m, ps.E[i], t, a, f, nf, nullptr, 0);
+      ps.xs_total[i] = t;
+      ps.xs_absorption[i] = a;
+      ps.xs_fission[i] = f;
+      ps.xs_nu_fission[i] = nf;
+    }
+  } else {
+    const int G = DM.mg_n_groups;
+    const int n_coord = ps.n_coord[i];
+    const int t = mg_temperature_index(m, ps.sqrtkT[i]);
+    const int a = mg_angle_index(m, get_u(ps, i, n_coord - 1));
+    const int ba = mg_ba(m, t, a);
+    const int g = ps.g[i];
+    ps.xs_total[i] = ld(DM.mg_total + ba * G + g) * 1.0;
+    ps.xs_absorption[i] = ld(DM.mg_absorption + ba * G + g) * 1.0;
+    ps.xs_nu_fission[i] = ld(DM.mgm_fissionable + m) ? ld(DM.mg_nu_fission + ba * G + g) * 1.0 : 0.;
+  }
+}
+
+// Particle::event_advance, src/particle.cpp:232-286
+OMC_D int ev_advance(const PState& ps, const GenCtx& gc, int64_t i)
+{
+  const int n_coord = ps.n_coord[i];
+  const int surface = ps.surface[i];
+  bool neg_lat;
+  const Boundary b = distance_to_boundary(ps, i, n_coord, surface, neg_lat);
+  if (neg_lat) {
+    mark_lost(ps, gc, i);
+    return NEXT_DEAD;
+  }
+  const double xs_total = ps.xs_total[i];
+  double d_coll;
+  if (xs_total == 0.0) {
+    d_coll = inf_d();
+  } else {
+    uint64_t seed = ps.seed[i];
+    d_coll = -log(prn(seed)) / xs_total;
+    ps.seed[i] = seed;
+  }
+  const double distance = b.distance < d_coll ? b.distance : d_coll;
+  const V3 r0 = get_r(ps, i, 0);
+  const V3 u0 = get_u(ps, i, 0);
+  for (int l = 0; l < n_coord; ++l) { // GeometryState::move_distance
+    LV(rx, l) += distance * LV(ux, l);
+    LV(ry, l) += distance * LV(uy, l);
+    LV(rz, l) += distance * LV(uz, l);
+  }
+  const int m = ps.material[i];
+  const double E = ps.E[i];
+  const int g = ps.g[i];
+  int ba = 0;
+  double speed;
+  if (DM.run_CE) { // Particle::speed, src/particle.cpp:46-73
+    speed = C_LIGHT * sqrt(E * (E + 2 * MASS_NEUTRON_EV)) / (E + MASS_NEUTRON_EV);
+  } else if (m >= 0) {
+    ba = mg_ba(m, mg_temperature_index(m, ps.sqrtkT[i]), mg_angle_index(m, u0));
+    speed = 1.0 / ld(DM.mg_inverse_velocity + ba * DM.mg_n_groups + g);
+  } else {
+    speed = inf_d();
+  }
+  ps.time[i] += distance / speed;
+  const double wgt = ps.wgt[i];
+  const double nu_fission = ps.xs_nu_fission[i];
+  if (gc.tallies_active && DM.n_tallies > 0) {
+    ScoreCtx sc;
+    sc.flux = wgt * distance;
+    sc.xs_total = xs_total;
+    sc.xs_absorption = ps.xs_absorption[i];
+    sc.xs_fission = ps.xs_fission[i];
+    sc.xs_nu_fission = nu_fission;
+    sc.material = m;
+    sc.g = g;
+    sc.mg_ba = ba;
+    if (!DM.run_CE && m >= 0) // score_general_mg uses the lowest level's direction
+      sc.mg_ba = mg_ba(m, mg_temperature_index(m, ps.sqrtkT[i]),
+        mg_angle_index(m, get_u(ps, i, n_coord - 1)));
+    const V3 r1 = get_r(ps, i, 0);
+    score_tracklength(ps, i, n_coord, r0, r1, u0, E, sc, gc.tally_values);
+  }
+  ps.k_trk[i] += wgt * distance * nu_fission;
+  ps.b_surface[i] = b.surface;
+  ps.b_level_trans[i] = b.level | (b.trans << 8);
+  return (d_coll > b.distance) ? NEXT_SURFACE : NEXT_COLLISION;
+}
+
+// Particle::event_revive_from_secondary, src/particle.cpp:417-425 (no secondaries)
+OMC_D bool ev_revive(const PState& ps, int64_t i)
+{
+  const int n_event = ps.n_event[i] + 1;
+  ps.n_event[i] = n_event;
+  if (n_event == DM.max_particle_events)
+    ps.wgt[i] = 0.0;
+  return ps.wgt[i] != 0.0;
+}
+
+// Particle::event_cross_surface + cross_surface + BCs + cross_lattice:
+// src/particle.cpp:288-329, 549-710 ; src/geometry.cpp:301-357 ;
+// src/boundary_condition.cpp:18-47
+OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
+{
+  ps.cell_last0[i] = LV(cell, 0);
+  const int blt = ps.b_level_trans[i];
+  const int n_coord = blt & 0xff;
+  const int trans = blt >> 8;
+  int surface = ps.b_surface[i];
+  ps.surface[i] = surface;
+  ps.n_coord[i] = n_coord;
+  if (trans != TRANS_NONE) {
+    // ---- cross_lattice ------------------------------------------------------
+    const int lvl = n_coord - 1;
+    const int lat = LV(lattice, lvl);
+    LatIdx li;
+    li.x = LV(lat_x, lvl) + ((trans & 3) - 1);
+    li.y = LV(lat_y, lvl) + (((trans >> 2) & 3) - 1);
+    li.z = LV(lat_z, lvl) + (((trans >> 4) & 3) - 1);
+    LV(lat_x, lvl) = li.x;
+    LV(lat_y, lvl) = li.y;
+    LV(lat_z, lvl) = li.z;
+    V3 r = get_r(ps, i, lvl - 1);
+    const double* t = DM.cell_translation + 3 * LV(cell, lvl - 1);
+    r.x -= ld(t);
+    r.y -= ld(t + 1);
+    r.z -= ld(t + 2);
+    set_r(ps, i, lvl, lat_local_position(lat, r, li));
+    bool found = false;
+    if (lat_valid(lat, li)) {
+      LV(universe, lvl) = lat_universe(lat, li);
+      found = find_cell_from(ps, i, n_coord, surface);
+    }
+    if (!found) {
+      ps.n_coord[i] = 1;
+      found = find_cell_from(ps, i, 1, surface);
+      if (!found)
+        mark_lost(ps, gc, i);
+    }
+  } else {
+    const int s = abs(surface) - 1;
+    const int bc = ld(DM.surf_bc + s);
+    if (bc == OMCGPU_BC_VACUUM) {
+      ps.k_leak[i] += ps.wgt[i];
+      ps.wgt[i] = 0.0;
+    } else if (bc == OMCGPU_BC_REFLECTIVE) {
+      if (n_coord != 1) {
+        mark_lost(ps, gc, i);
+      } else {
+        const V3 r = get_r(ps, i, 0);
+        V3 u = get_u(ps, i, 0);
+        V3 n = surf_normal(s, r); // Position::reflect, include/openmc/position.h:207-213
+        const double projection = dot(n, u);
+        const double magnitude = dot(n, n);
+        const double f = 2.0 * projection / magnitude;
+        u = v3(u.x - n.x * f, u.y - n.y * f, u.z - n.z * f);
+        const double nrm = sqrt(u.x * u.x + u.y * u.y + u.z * u.z);
+        u = v3(u.x / nrm, u.y / nrm, u.z / nrm);
+        set_u(ps, i, 0, u);
+        surface = -surface;
+        ps.surface[i] = surface;
+        if (!find_cell_from(ps, i, 1, surface))
+          mark_lost(ps, gc, i);
+      }
+    } else {
+      bool found = find_cell_from(ps, i, n_coord, surface);
+      if (!found) {
+        ps.n_coord[i] = 1;
+        found = find_cell_from(ps, i, 1, surface);
+      }
+      if (!found) {
+        ps.surface[i] = SURFACE_NONE;
+        ps.n_coord[i] = 1;
+        LV(rx, 0) += TINY_BIT * LV(ux, 0);
+        LV(ry, 0) += TINY_BIT * LV(uy, 0);
+        LV(rz, 0) += TINY_BIT * LV(uz, 0);
+        if (!find_cell_from(ps, i, 1, SURFACE_NONE))
+          mark_lost(ps, gc, i);
+      }
+    }
+  }
+  return ev_revive(ps, i);
+}
+
+// Particle::event_collide, src/particle.cpp:331-415
+OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_t i)
+{
+  Collider p;
+  p.r = get_r(ps, i, 0);
+  p.u = get_u(ps, i, 0);
+  p.E = ps.E[i];
+  p.wgt = ps.wgt[i];
+  p.time = ps.time[i];
+  p.g = ps.g[i];
+  p.material = ps.material[i];
+  p.seed = ps.seed[i];
+  p.n_progeny = ps.n_progeny[i];
+  p.id = gc.id_offset + i + 1;
+  p.xs_total = ps.xs_total[i];
+  p.xs_absorption = ps.xs_absorption[i];
+  p.xs_nu_fission = ps.xs_nu_fission[i];
+  p.k_abs = ps.k_abs[i];
+  ps.k_col[i] += p.wgt * p.xs_nu_fission / p.xs_total;
+  ps.surface[i] = SURFACE_NONE;
+  if (DM.run_CE) {
+    bool no_nuclide;
+    collision_ce(p, gc, fb, no_nuclide);
+    if (no_nuclide)
+      atomic_add_i32(gc.n_lost, 1);
+    if (p.E < DM.energy_cutoff) // src/physics.cpp:67-71
+      p.wgt = 0.0;
+  } else {
+    const int n_coord = ps.n_coord[i];
+    const int ba = mg_ba(p.material, mg_temperature_index(p.material, ps.sqrtkT[i]),
+      mg_angle_index(p.material, get_u(ps, i, n_coord - 1)));
+    collision_mg(p, ba, gc, fb);
+  }
+  const int n_coord = ps.n_coord[i];
+  for (int l = 0; l < n_coord; ++l) // directions of all levels follow level 0
+    set_u(ps, i, l, p.u);
+  ps.E[i] = p.E;
+  ps.g[i] = p.g;
+  ps.wgt[i] = p.wgt;
+  ps.seed[i] = p.seed;
+  ps.n_progeny[i] = p.n_progeny;
+  ps.k_abs[i] = p.k_abs;
+  ps.material_last[i] = C_NONE;
+  return ev_revive(ps, i);
+}
+
+// ---- kernels -----------------------------------------------------------------
+OMC_D void body_init(int64_t tid, const EvArgs& a)
+{
+  if (tid >= a.gc.n)
+    return;
+  if (ev_init(a.ps, a.gc, a.src, tid))
+    queue_append(a.q_a, (int32_t)tid);
+}
+OMC_KERNEL(k_init, EvArgs, body_init)
+
+OMC_D void body_xs(int64_t tid, const EvArgs& a)
+{
+  if (tid >= *a.q_in.count)
+    return;
+  ev_xs(a.ps, a.q_in.idx[tid]);
+}
+OMC_KERNEL(k_xs, EvArgs, body_xs)
+
+OMC_D void body_advance(int64_t tid, const EvArgs& a)
+{
+  if (tid >= *a.q_in.count)
+    return;
+  const int32_t i = a.q_in.idx[tid];
+  const int next = ev_advance(a.ps, a.gc, i);
+  if (next == NEXT_COLLISION)
+    queue_append(a.q_a, i);
+  else if (next == NEXT_SURFACE)
+    queue_append(a.q_b, i);
+}
+OMC_KERNEL(k_advance, EvArgs, body_advance)
+
+OMC_D void body_surface(int64_t tid, const EvArgs& a)
+{
+  if (tid >= *a.q_in.count)
+    return;
+  const int32_t i = a.q_in.idx[tid];
+  if (ev_surface(a.ps, a.gc, i))
+    queue_append(a.q_a, i);
+}
+OMC_KERNEL(k_surface, EvArgs, body_surface)
+
+OMC_D void body_collide(int64_t tid, const EvArgs& a)
+{
+  if (tid >= *a.q_in.count)
+    return;
+  const int32_t i = a.q_in.idx[tid];
+  if (ev_collide(a.ps, a.gc, a.fb, i))
+    queue_append(a.q_a, i);
+}
+OMC_KERNEL(k_collide, EvArgs, body_collide)
+
+// The tail of a generation (few particles left, launch-latency bound): one
+// thread runs the remaining events of one history to completion with the very
+// same event functions (cf. transport_history_based_single_particle,
+// src/simulation.cpp:804-821).
+OMC_D void body_tail(int64_t tid, const EvArgs& a)
+{
+  if (tid >= *a.q_in.count)
+    return;
+  const int32_t i = a.q_in.idx[tid];
+  unsigned long long n_xs = 0, n_coll = 0, n_cross = 0;
+  bool alive = true;
+  while (alive) {
+    ev_xs(a.ps, i);
+    ++n_xs;
+    const int next = ev_advance(a.ps, a.gc, i);
+    if (next == NEXT_COLLISION) {
+      alive = ev_collide(a.ps, a.gc, a.fb, i);
+      ++n_coll;
+    } else if (next == NEXT_SURFACE) {
+      alive = ev_surface(a.ps, a.gc, i);
+      ++n_cross;
+    } else {
+      alive = false;
+    }
+  }
+  atomic_add_u64(a.gc.counters + 1, n_xs);
+  atomic_add_u64(a.gc.counters + 2, n_coll);
+  atomic_add_u64(a.gc.counters + 3, n_cross);
+}
+OMC_KERNEL(k_tail, EvArgs, body_tail)
+
+// ---- deterministic reduction of the per-particle accumulators ------------------
+// (event_death, src/particle.cpp:475-512: global_tally_* += ..., total_weight)
+struct ReduceArgs {
+  PState ps;
+  Bank src;
+  int64_t n;
+  double* partial; // [n_chunks][6]
+  int64_t chunk;
+};
+OMC_D void body_reduce(int64_t tid, const ReduceArgs& a)
+{
+  const int64_t lo = tid * a.chunk;
+  int64_t hi = lo + a.chunk;
+  if (hi > a.n)
+    hi = a.n;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int64_t i = lo; i < hi; ++i) {
+    s[OMCGPU_K_COLLISION] += a.ps.k_col[i];
+    s[OMCGPU_K_ABSORPTION] += a.ps.k_abs[i];
+    s[OMCGPU_K_TRACKLENGTH] += a.ps.k_trk[i];
+    s[OMCGPU_LEAKAGE] += a.ps.k_leak[i];
+    s[4] += a.src.wgt[i];
+    s[5] += (double)a.ps.n_event[i];
+  }
+  for (int k = 0; k < 6; ++k)
+    a.partial[tid * 6 + k] = s[k];
+}
+OMC_KERNEL(k_reduce, ReduceArgs, body_reduce)
+
+// ---- bank kernels --------------------------------------------------------------
+struct BankArgs {
+  Bank a, b;
+  omcgpu_site* aos;
+  const int32_t* offs;    // exclusive scan of n_progeny
+  const int32_t* gather;  // comb indices
+  int64_t n;
+  int64_t id_offset;
+};
+OMC_D void bank_copy(const Bank& d, int64_t j, const Bank& s, int64_t k)
+{
+  d.x[j] = s.x[k];
+  d.y[j] = s.y[k];
+  d.z[j] = s.z[k];
+  d.u[j] = s.u[k];
+  d.v[j] = s.v[k];
+  d.w[j] = s.w[k];
+  d.E[j] = s.E[k];
+  d.time[j] = s.time[k];
+  d.wgt[j] = s.wgt[k];
+  d.delayed_group[j] = s.delayed_group[k];
+  d.parent_id[j] = s.parent_id[k];
+  d.progeny_id[j] = s.progeny_id[k];
+}
+OMC_D void body_scatter_bank(int64_t tid, const BankArgs& a)
+{ // sort_fission_bank, src/bank.cpp:111-125
+  if (tid >= a.n)
+    return;
+  const int64_t parent = a.a.parent_id[tid] - 1 - a.id_offset;
+  const int64_t dest = (int64_t)a.offs[parent] + a.a.progeny_id[tid];
+  bank_copy(a.b, dest, a.a, tid);
+}
+OMC_KERNEL(k_scatter_bank, BankArgs, body_scatter_bank)
+
+OMC_D void body_gather_bank(int64_t tid, const BankArgs& a)
+{ // temp_sites[index_temp] = fission_bank[idx], src/eigenvalue.cpp:166-177
+  if (tid >= a.n)
+    return;
+  bank_copy(a.b, tid, a.a, a.gather[tid]);
+}
+OMC_KERNEL(k_gather_bank, BankArgs, body_gather_bank)
+
+OMC_D void body_unpack(int64_t tid, const BankArgs& a)
+{
+  if (tid >= a.n)
+    return;
+  const omcgpu_site s = a.aos[tid];
+  a.a.x[tid] = s.r[0];
+  a.a.y[tid] = s.r[1];
+  a.a.z[tid] = s.r[2];
+  a.a.u[tid] = s.u[0];
+  a.a.v[tid] = s.u[1];
+  a.a.w[tid] = s.u[2];
+  a.a.E[tid] = s.E;
+  a.a.time[tid] = s.time;
+  a.a.wgt[tid] = s.wgt;
+  a.a.delayed_group[tid] = s.delayed_group;
+  a.a.parent_id[tid] = s.parent_id;
+  a.a.progeny_id[tid] = s.progeny_id;
+}
+OMC_KERNEL(k_unpack, BankArgs, body_unpack)
+
+OMC_D void body_pack(int64_t tid, const BankArgs& a)
+{
+  if (tid >= a.n)
+    return;
+  omcgpu_site s;
+  s.r[0] = a.a.x[tid];
+  s.r[1] = a.a.y[tid];
+  s.r[2] = a.a.z[tid];
+  s.u[0] = a.a.u[tid];
+  s.u[1] = a.a.v[tid];
+  s.u[2] = a.a.w[tid];
+  s.E = a.a.E[tid];
+  s.time = a.a.time[tid];
+  s.wgt = a.a.wgt[tid];
+  s.delayed_group = a.a.delayed_group[tid];
+  s.surf_id = 0;
+  s.particle = 0;
+  s.parent_nuclide = -1;
+  s.parent_id = a.a.parent_id[tid];
+  s.progeny_id = a.a.progeny_id[tid];
+  a.aos[tid] = s;
+}
+OMC_KERNEL(k_pack, BankArgs, body_pack)
+
+// ---- stand-alone probes ---------------------------------------------------------
+struct XsArgs {
+  const double* E;
+  const int32_t* material;
+  int64_t n;
+  double* out;
+  int32_t* i_grid;
+  int32_t max_nuc;
+};
+OMC_D void body_probe_xs(int64_t tid, const XsArgs& a)
+{
+  if (tid >= a.n)
+    return;
+  const int m = a.material[tid];
+  double t = 0, ab = 0, f = 0, nf = 0;
+  if (DM.run_CE) {
+    ce_macro_xs(m, a.E[tid], t, ab, f, nf, a.i_grid ? a.i_grid + tid * a.max_nuc : nullptr,
+      a.max_nuc);
+  } else {
+    const int G = DM.mg_n_groups;
+    const int g = (int)a.E[tid];
+    const int ba = mg_ba(m, mg_temperature_index(m, ld(DM.cell_sqrtkT)), 0);
+    t = ld(DM.mg_total + ba * G + g);
+    ab = ld(DM.mg_absorption + ba * G + g);
+    nf = ld(DM.mgm_fissionable + m) ? ld(DM.mg_nu_fission + ba * G + g) : 0.;
+  }
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  reinterpret_cast<double2*>(a.out)[2 * tid] = make_double2(t, ab);
+  reinterpret_cast<double2*>(a.out)[2 * tid + 1] = make_double2(f, nf);
+#else
+  a.out[4 * tid + 0] = t;
+  a.out[4 * tid + 1] = ab;
+  a.out[4 * tid + 2] = f;
+  a.out[4 * tid + 3] = nf;
+#endif
+}
+OMC_KERNEL(k_probe_xs, XsArgs, body_probe_xs)
+
+struct GeoArgs {
+  PState ps;
+  const double* xyz;
+  const double* uvw;
+  int64_t n;
+  int32_t *cell, *instance, *material, *n_coord;
+  double* distance;
+  int32_t *surface, *level, *lat_trans;
+};
+OMC_D void body_probe_geom(int64_t tid, const GeoArgs& a)
+{
+  if (tid >= a.n)
+    return;
+  const PState& ps = a.ps;
+  const int64_t i = tid;
+  const int L = DM.n_coord_levels < OMCGPU_MAX_COORD ? DM.n_coord_levels : OMCGPU_MAX_COORD;
+  for (int l = 0; l < L; ++l)
+    reset_level(ps, i, l);
+  set_r(ps, i, 0, v3(a.xyz[3 * tid], a.xyz[3 * tid + 1], a.xyz[3 * tid + 2]));
+  if (a.uvw)
+    set_u(ps, i, 0, v3(a.uvw[3 * tid], a.uvw[3 * tid + 1], a.uvw[3 * tid + 2]));
+  else
+    set_u(ps, i, 0, v3(0.0, 0.0, 1.0));
+  ps.material[i] = C_NONE;
+  ps.sqrtkT[i] = -1.0;
+  ps.cell_instance[i] = 0;
+  const bool found = find_cell_from_root(ps, i, SURFACE_NONE);
+  const int nc = ps.n_coord[i];
+  if (a.cell) {
+    a.cell[tid] = found ? LV(cell, nc - 1) : -1;
+    a.instance[tid] = found ? ps.cell_instance[i] : -1;
+    a.material[tid] = found ? ps.material[i] : -2;
+    a.n_coord[tid] = found ? nc : 0;
+  }
+  if (a.distance) {
+    if (!found) {
+      a.distance[tid] = -1.0;
+      a.surface[tid] = 0;
+      a.level[tid] = 0;
+      a.lat_trans[3 * tid] = a.lat_trans[3 * tid + 1] = a.lat_trans[3 * tid + 2] = 0;
+    } else {
+      bool neg;
+      const Boundary b = distance_to_boundary(ps, i, nc, SURFACE_NONE, neg);
+      a.distance[tid] = b.distance;
+      a.surface[tid] = b.surface;
+      a.level[tid] = b.level;
+      a.lat_trans[3 * tid] = (b.trans & 3) - 1;
+      a.lat_trans[3 * tid + 1] = ((b.trans >> 2) & 3) - 1;
+      a.lat_trans[3 * tid + 2] = ((b.trans >> 4) & 3) - 1;
+    }
+  }
+}
+OMC_KERNEL(k_probe_geom, GeoArgs, body_probe_geom)
+
+struct RngArgs {
+  const uint64_t* n;
+  const uint64_t* seed;
+  int64_t count;
+  int32_t per;
+  uint64_t* out_u;
+  double* out_d;
+};
+OMC_D void body_probe_rng(int64_t tid, const RngArgs& a)
+{
+  if (tid >= a.count)
+    return;
+  if (a.out_u) {
+    a.out_u[tid] = future_seed(a.n[tid], a.seed[tid]);
+  } else {
+    uint64_t s = a.seed[tid];
+    for (int j = 0; j < a.per; ++j)
+      a.out_d[tid * a.per + j] = prn(s);
+  }
+}
+OMC_KERNEL(k_probe_rng, RngArgs, body_probe_rng)
+
+// =============================================================================
+// host side
+// =============================================================================
+static char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* detail = "")
+{
+  std::snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+
+#define CUDA_OK(call) \
+  do { \
+    cudaError_t e_ = (call); \
+    if (e_ != cudaSuccess) \
+      return fail(OMCGPU_E_CUDA, "CUDA error: %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+struct Engine {
+  bool ready = false;
+  omcgpu_model hm;            // scalars + DEVICE pointers
+  std::vector<void*> dev_allocs;
+  int64_t cap = 0;            // max particles per generation
+  int64_t fis_cap = 0;        // fission bank capacity (3 * cap)
+  PState ps;
+  Bank src, fis, fis_sorted;
+  int64_t n_src = 0, n_fis = 0;
+  Queue q[4];
+  int32_t* d_counts = nullptr;   // [0..3] queue counts, [4] n_fission, [5] n_lost
+  unsigned long long* d_counters = nullptr; // [4]
+  int32_t* h_counts = nullptr;   // pinned
+  unsigned long long* h_counters = nullptr;
+  int32_t* d_offs = nullptr;     // progeny scan
+  int32_t* d_gather = nullptr;
+  void* d_scan_tmp = nullptr;
+  size_t scan_tmp_bytes = 0;
+  double* d_partial = nullptr;
+  double* h_partial = nullptr;
+  int64_t n_chunks = 0;
+  omcgpu_site* d_aos = nullptr;
+  omcgpu_site* h_aos = nullptr;  // pinned staging
+  double* d_tally = nullptr;
+  int64_t n_tally = 0;
+  cudaStream_t stream = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx0 = nullptr, evx1 = nullptr;
+  int64_t tail_threshold = 2048;
+  int64_t id_offset_last = 0;
+};
+static Engine G;
+
+template<class T>
+static int dev_alloc(T** p, size_t count)
+{
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+  if (e != cudaSuccess)
+    return fail(OMCGPU_E_ALLOCATE, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  cudaMemset(q, 0, std::max<size_t>(count, 1) * sizeof(T));
+  G.dev_allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return 0;
+}
+
+template<class T>
+static int upload(const T** field, size_t count)
+{
+  const T* host = *field;
+  T* d = nullptr;
+  int rc = dev_alloc(&d, count);
+  if (rc)
+    return rc;
+  if (host && count) {
+    cudaError_t e = cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess)
+      return fail(OMCGPU_E_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+  }
+  *field = d;
+  return 0;
+}
+
+static int alloc_bank(Bank& b, int64_t cap)
+{
+  b.cap = cap;
+  int rc = 0;
+  rc |= dev_alloc(&b.x, cap);
+  rc |= dev_alloc(&b.y, cap);
+  rc |= dev_alloc(&b.z, cap);
+  rc |= dev_alloc(&b.u, cap);
+  rc |= dev_alloc(&b.v, cap);
+  rc |= dev_alloc(&b.w, cap);
+  rc |= dev_alloc(&b.E, cap);
+  rc |= dev_alloc(&b.time, cap);
+  rc |= dev_alloc(&b.wgt, cap);
+  rc |= dev_alloc(&b.delayed_group, cap);
+  rc |= dev_alloc(&b.parent_id, cap);
+  rc |= dev_alloc(&b.progeny_id, cap);
+  return rc;
+}
+
+// smallest double E whose HOST hash bin int(log(E/E_min)/spacing) is >= k
+static double hash_edge_for(int k, double e_min, double spacing)
+{
+  auto bin = [&](double E) { return (int)(std::log(E / e_min) / spacing); };
+  double E = e_min * std::exp(k * spacing);
+  // walk to the exact transition in units of ulp
+  while (bin(E) >= k)
+    E = std::nextafter(E, 0.0);
+  while (bin(E) < k)
+    E = std::nextafter(E, INFINITY);
+  return E;
+}
+
+static int upload_model(const omcgpu_model* m)
+{
+  G.hm = *m;
+  omcgpu_model& h = G.hm;
+  const int ns = h.n_surfaces, nc = h.n_cells, nu = h.n_universes, nl = h.n_lattices;
+  const int nm = h.n_materials;
+  int rc = 0;
+#define UP(field, count) rc = rc ? rc : upload(&h.field, (size_t)(count))
+  UP(surf_type, ns);
+  UP(surf_bc, ns);
+  UP(surf_id, ns);
+  UP(surf_coef, (size_t)ns * OMCGPU_SURF_NCOEF);
+  const int n_tok = nc ? m->cell_region_ofs[nc] : 0;
+  const int n_cmat = nc ? m->cell_mat_ofs[nc] : 0;
+  const int n_ckt = nc ? m->cell_sqrtkT_ofs[nc] : 0;
+  const int n_coff = nc ? m->cell_offset_ofs[nc] : 0;
+  UP(cell_id, nc);
+  UP(cell_type, nc);
+  UP(cell_universe, nc);
+  UP(cell_fill, nc);
+  UP(cell_simple, nc);
+  UP(cell_region_ofs, nc + 1);
+  UP(region_tokens, n_tok);
+  UP(cell_mat_ofs, nc + 1);
+  UP(cell_material, n_cmat);
+  UP(cell_sqrtkT_ofs, nc + 1);
+  UP(cell_sqrtkT, n_ckt);
+  UP(cell_translation, (size_t)nc * 3);
+  UP(cell_distribcell_index, nc);
+  UP(cell_offset_ofs, nc + 1);
+  UP(cell_offset, n_coff);
+  const int n_uc = nu ? m->univ_cell_ofs[nu] : 0;
+  UP(univ_cell_ofs, nu + 1);
+  UP(univ_cells, n_uc);
+  const int n_lu = nl ? m->lat_univ_ofs[nl] : 0;
+  const int n_lo = nl ? m->lat_offset_ofs[nl] : 0;
+  UP(lat_shape, (size_t)nl * 3);
+  UP(lat_is3d, nl);
+  UP(lat_outer, nl);
+  UP(lat_pitch, (size_t)nl * 3);
+  UP(lat_lower_left, (size_t)nl * 3);
+  UP(lat_univ_ofs, nl + 1);
+  UP(lat_universes, n_lu);
+  UP(lat_offset_ofs, nl + 1);
+  UP(lat_offsets, n_lo);
+  const int n_mn = nm ? m->mat_nuc_ofs[nm] : 0;
+  UP(mat_id, nm);
+  UP(mat_fissionable, nm);
+  UP(mat_nuc_ofs, nm + 1);
+  UP(mat_nuclide, n_mn);
+  UP(mat_atom_density, n_mn);
+  if (h.run_CE) {
+    const int nn = h.n_nuclides;
+    const int64_t n_pts = m->nuc_grid_ofs[nn];
+    // hash-edge table from the HOST libm (see ce_log_index)
+    std::vector<double> edge(h.n_log_bins + 2);
+    edge[0] = 0.0;
+    for (int k = 1; k <= h.n_log_bins; ++k)
+      edge[k] = hash_edge_for(k, h.energy_min, h.log_spacing);
+    edge[h.n_log_bins + 1] = INFINITY;
+    h.hash_edge = edge.data();
+    UP(hash_edge, h.n_log_bins + 2);
+    UP(nuc_awr, nn);
+    UP(nuc_kT, nn);
+    UP(nuc_fissionable, nn);
+    UP(nuc_grid_ofs, nn + 1);
+    UP(nuc_energy, n_pts);
+    UP(nuc_xs, (size_t)n_pts * 4);
+    UP(nuc_grid_index, (size_t)nn * (h.n_log_bins + 1));
+    UP(nuc_rx_ofs, nn + 1);
+    UP(nuc_fission_rx, nn);
+    UP(nuc_n_precursor, nn);
+    UP(nuc_total_nu_fn, nn);
+    const int nr = h.n_reactions, np = h.n_products, nf = h.n_functions;
+    const int64_t n_rxs = nr ? m->rx_xs_ofs[nr] : 0;
+    UP(rx_mt, nr);
+    UP(rx_scatter_in_cm, nr);
+    UP(rx_inelastic, nr);
+    UP(rx_threshold, nr);
+    UP(rx_xs_ofs, nr + 1);
+    UP(rx_xs, n_rxs);
+    UP(rx_q_value, nr);
+    UP(rx_prod_ofs, nr + 1);
+    UP(prod_emission, np);
+    UP(prod_decay_rate, np);
+    UP(prod_yield_fn, np);
+    UP(prod_elaw, np);
+    UP(prod_par, (size_t)np * 2);
+    UP(prod_fn, (size_t)np * 2);
+    const int n_fd = nf ? m->fn_ofs[nf] : 0;
+    UP(fn_type, nf);
+    UP(fn_ofs, nf + 1);
+    UP(fn_data, n_fd);
+  } else {
+    const int Gn = h.mg_n_groups, DG = h.mg_n_delayed;
+    const int n_blk = m->mgm_blk_ofs[nm];
+    const int n_ba = m->blk_ang_ofs[n_blk];
+    UP(mg_energy_bin_avg, Gn);
+    UP(mg_energy_bins, Gn + 1);
+    UP(mgm_n_temps, nm);
+    UP(mgm_n_pol, nm);
+    UP(mgm_n_azi, nm);
+    UP(mgm_isotropic, nm);
+    UP(mgm_fissionable, nm);
+    UP(mgm_blk_ofs, nm + 1);
+    UP(mgm_kTs, n_blk);
+    UP(blk_ang_ofs, n_blk + 1);
+    UP(mg_total, (size_t)n_ba * Gn);
+    UP(mg_absorption, (size_t)n_ba * Gn);
+    UP(mg_nu_fission, (size_t)n_ba * Gn);
+    UP(mg_prompt_nu_fission, (size_t)n_ba * Gn);
+    UP(mg_fission, (size_t)n_ba * Gn);
+    UP(mg_inverse_velocity, (size_t)n_ba * Gn);
+    UP(mg_delayed_nu_fission, (size_t)n_ba * DG * Gn);
+    UP(mg_chi_prompt, (size_t)n_ba * Gn * Gn);
+    UP(mg_chi_delayed, (size_t)n_ba * DG * Gn * Gn);
+    UP(mg_decay_rate, (size_t)n_ba * DG);
+    // ragged scatter sizes
+    size_t n_e = 0, n_d = 0, n_mu = 0;
+    for (int ba = 0; ba < n_ba; ++ba) {
+      const int order = m->sc_order[ba];
+      for (int g = 0; g < Gn; ++g) {
+        const int ng = m->sc_gmax[ba * Gn + g] - m->sc_gmin[ba * Gn + g] + 1;
+        n_e = std::max<size_t>(n_e, (size_t)m->sc_gofs[ba * Gn + g] + ng);
+        n_d = std::max<size_t>(n_d, (size_t)m->sc_dofs[ba * Gn + g] + (size_t)ng * order);
+      }
+      const int fmt = m->sc_format[ba];
+      const int nmu = fmt == OMCGPU_SCATT_TABULAR ? order : (fmt == OMCGPU_SCATT_HISTOGRAM ? order + 1 : 1);
+      n_mu = std::max<size_t>(n_mu, (size_t)m->sc_mu_ofs[ba] + nmu);
+    }
+    UP(sc_format, n_ba);
+    UP(sc_order, n_ba);
+    UP(sc_gmin, (size_t)n_ba * Gn);
+    UP(sc_gmax, (size_t)n_ba * Gn);
+    UP(sc_gofs, (size_t)n_ba * Gn);
+    UP(sc_dofs, (size_t)n_ba * Gn);
+    UP(sc_scattxs, (size_t)n_ba * Gn);
+    UP(sc_energy, n_e);
+    UP(sc_mult, n_e);
+    UP(sc_maxval, n_e);
+    UP(sc_dist, n_d);
+    UP(sc_fmu, n_d);
+    UP(sc_mu_ofs, n_ba);
+    UP(sc_mu, n_mu);
+    UP(sc_dmu, n_ba);
+  }
+  const int nme = h.n_meshes, nfl = h.n_filters, nt = h.n_tallies;
+  UP(mesh_ndim, nme);
+  UP(mesh_shape, (size_t)nme * 3);
+  UP(mesh_lower_left, (size_t)nme * 3);
+  UP(mesh_width, (size_t)nme * 3);
+  const int n_fdat = nfl ? m->filter_data_ofs[nfl] : 0;
+  UP(filter_type, nfl);
+  UP(filter_n_bins, nfl);
+  UP(filter_mesh, nfl);
+  UP(filter_matches_groups, nfl);
+  UP(filter_data_ofs, nfl + 1);
+  UP(filter_idata, n_fdat);
+  UP(filter_ddata, n_fdat);
+  G.n_tally = nt ? m->tally_result_ofs[nt] : 0;
+  UP(tally_n_filters, nt);
+  UP(tally_filters, (size_t)nt * OMCGPU_MAX_FILTERS);
+  UP(tally_strides, (size_t)nt * OMCGPU_MAX_FILTERS);
+  UP(tally_n_scores, nt);
+  UP(tally_scores, (size_t)nt * OMCGPU_MAX_SCORES);
+  UP(tally_result_ofs, nt + 1);
+#undef UP
+  if (rc)
+    return rc;
+#if OMC_CUDA
+  CUDA_OK(cudaMemcpyToSymbol(c_dm, &h, sizeof(omcgpu_model)));
+#else
+  c_dm = h;
+#endif
+  return 0;
+}
+
+static int check_supported(const omcgpu_model* m)
+{
+  if (m->n_coord_levels > OMCGPU_MAX_COORD)
+    return fail(OMCGPU_E_UNSUPPORTED, "geometry nests deeper than OMCGPU_MAX_COORD%s");
+  for (int s = 0; s < m->n_surfaces; ++s) {
+    if (m->surf_type[s] < 0 || m->surf_type[s] > OMCGPU_SURF_SPHERE)
+      return fail(OMCGPU_E_UNSUPPORTED, "surface type not supported on the device%s");
+    if (m->surf_bc[s] < 0 || m->surf_bc[s] > OMCGPU_BC_REFLECTIVE)
+      return fail(OMCGPU_E_UNSUPPORTED, "boundary condition not supported on the device%s");
+  }
+  for (int t = 0; t < m->n_tallies; ++t) {
+    if (m->tally_n_filters[t] > OMCGPU_MAX_FILTERS || m->tally_n_scores[t] > OMCGPU_MAX_SCORES)
+      return fail(OMCGPU_E_UNSUPPORTED, "tally has too many filters or scores%s");
+    int n_mesh = 0;
+    for (int k = 0; k < m->tally_n_filters[t]; ++k)
+      if (m->filter_type[m->tally_filters[t * OMCGPU_MAX_FILTERS + k]] == OMCGPU_FILTER_MESH)
+        ++n_mesh;
+    if (n_mesh > 1)
+      return fail(OMCGPU_E_UNSUPPORTED, "more than one mesh filter per tally%s");
+  }
+  if (m->run_CE) {
+    for (int p = 0; p < m->n_products; ++p)
+      if (m->prod_elaw[p] < 0 || m->prod_elaw[p] > OMCGPU_ELAW_WATT)
+        return fail(OMCGPU_E_UNSUPPORTED, "secondary energy law not supported on the device%s");
+  }
+  return 0;
+}
+
+static EvArgs make_args(const omcgpu_gen_in* in)
+{
+  EvArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.ps = G.ps;
+  a.src = G.src;
+  a.fb = G.fis;
+  if (in) {
+    a.gc.n = in->n_particles;
+    a.gc.id_offset = in->id_offset;
+    a.gc.seed_base = in->particle_seed_base;
+    a.gc.master_seed = in->master_seed;
+    a.gc.stride = in->stride;
+    a.gc.keff = in->keff;
+    a.gc.tallies_active = in->tallies_active;
+  }
+  a.gc.n_fission = G.d_counts + 4;
+  a.gc.n_lost = G.d_counts + 5;
+  a.gc.counters = G.d_counters;
+  a.gc.tally_values = G.d_tally;
+  a.gc.fission_cap = G.fis_cap;
+  return a;
+}
+
+static int read_counts()
+{
+  CUDA_OK(cudaMemcpyAsync(G.h_counts, G.d_counts, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  return 0;
+}
+
+static int sort_fission_bank(int64_t n, int64_t id_offset)
+{
+  // exclusive scan of progeny_per_particle, then scatter (src/bank.cpp:76-134)
+#if OMC_CUDA
+  CUDA_OK(cub::DeviceScan::ExclusiveSum(G.d_scan_tmp, G.scan_tmp_bytes, G.ps.n_progeny, G.d_offs,
+    (int)n, G.stream));
+  ++g_launches;
+#else
+  std::exclusive_scan(G.ps.n_progeny, G.ps.n_progeny + n, G.d_offs, 0);
+#endif
+  BankArgs b;
+  std::memset(&b, 0, sizeof(b));
+  b.a = G.fis;
+  b.b = G.fis_sorted;
+  b.offs = G.d_offs;
+  b.n = G.n_fis;
+  b.id_offset = id_offset;
+  OMC_LAUNCH(k_scatter_bank, G.n_fis, G.stream, b);
+  return 0;
+}
+
+static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
+{
+  if (!G.ready)
+    return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  const int64_t n = in->n_particles;
+  if (n > G.cap || n > G.n_src)
+    return fail(OMCGPU_E_OUT_OF_BOUNDS, "n_particles exceeds the source bank / capacity%s");
+  std::memset(out, 0, sizeof(*out));
+  CUDA_OK(cudaMemsetAsync(G.d_counts, 0, 8 * sizeof(int32_t), G.stream));
+  CUDA_OK(cudaMemsetAsync(G.d_counters, 0, 4 * sizeof(unsigned long long), G.stream));
+  CUDA_OK(cudaEventRecord(G.ev0, G.stream));
+  EvArgs a = make_args(in);
+  int cur = 0; // queue roles: q[cur] = xs/advance list, q[2] collision, q[3] surface, q[1-cur] next
+  a.q_a = G.q[cur];
+  OMC_LAUNCH(k_init, n, G.stream, a);
+  int rc = read_counts();
+  if (rc)
+    return rc;
+  int64_t n_alive = G.h_counts[cur];
+  int64_t n_xs = 0, n_coll = 0, n_cross = 0;
+  double ms_xs = 0.0;
+  while (n_alive > 0) {
+    if (n_alive <= G.tail_threshold) {
+      a.q_in = G.q[cur];
+      OMC_LAUNCH(k_tail, n_alive, G.stream, a);
+      break;
+    }
+    const int nxt = 1 - cur;
+    // zero the three output counters (collision, surface, next)
+    CUDA_OK(cudaMemsetAsync(G.d_counts + nxt, 0, sizeof(int32_t), G.stream));
+    CUDA_OK(cudaMemsetAsync(G.d_counts + 2, 0, 2 * sizeof(int32_t), G.stream));
+    a.q_in = G.q[cur];
+    CUDA_OK(cudaEventRecord(G.evx0, G.stream));
+    OMC_LAUNCH(k_xs, n_alive, G.stream, a);
+    CUDA_OK(cudaEventRecord(G.evx1, G.stream));
+    a.q_a = G.q[2];
+    a.q_b = G.q[3];
+    OMC_LAUNCH(k_advance, n_alive, G.stream, a);
+    a.q_in = G.q[3];
+    a.q_a = G.q[nxt];
+    OMC_LAUNCH(k_surface, n_alive, G.stream, a);
+    a.q_in = G.q[2];
+    OMC_LAUNCH(k_collide, n_alive, G.stream, a);
+    rc = read_counts();
+    if (rc)
+      return rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, G.evx0, G.evx1);
+    ms_xs += ms;
+    n_xs += n_alive;
+    n_coll += G.h_counts[2];
+    n_cross += G.h_counts[3];
+    n_alive = G.h_counts[nxt];
+    cur = nxt;
+  }
+  // death: deterministic reduction of the per-particle accumulators
+  ReduceArgs r;
+  r.ps = G.ps;
+  r.src = G.src;
+  r.n = n;
+  r.partial = G.d_partial;
+  r.chunk = (n + G.n_chunks - 1) / G.n_chunks;
+  const int64_t used_chunks = (n + r.chunk - 1) / r.chunk;
+  OMC_LAUNCH(k_reduce, used_chunks, G.stream, r);
+  CUDA_OK(cudaMemcpyAsync(G.h_partial, G.d_partial, used_chunks * 6 * sizeof(double),
+    cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaMemcpyAsync(G.h_counters, G.d_counters, 4 * sizeof(unsigned long long),
+    cudaMemcpyDeviceToHost, G.stream));
+  rc = read_counts();
+  if (rc)
+    return rc;
+  double tot[6] = {0, 0, 0, 0, 0, 0};
+  for (int64_t c = 0; c < used_chunks; ++c)
+    for (int k = 0; k < 6; ++k)
+      tot[k] += G.h_partial[c * 6 + k];
+  for (int k = 0; k < 4; ++k)
+    out->global_tally[k] = tot[k];
+  out->total_weight = tot[4];
+  out->n_events = (int64_t)tot[5];
+  G.n_fis = std::min<int64_t>(G.h_counts[4], G.fis_cap);
+  out->n_fission = G.n_fis;
+  out->n_lost = G.h_counts[5];
+  out->n_xs_lookups = n_xs + (int64_t)G.h_counters[1];
+  out->n_collisions = n_coll + (int64_t)G.h_counters[2];
+  out->n_crossings = n_cross + (int64_t)G.h_counters[3];
+  rc = sort_fission_bank(n, in->id_offset);
+  if (rc)
+    return rc;
+  CUDA_OK(cudaEventRecord(G.ev1, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, G.ev0, G.ev1);
+  out->ms_transport = ms;
+  out->ms_xs = ms_xs;
+  G.id_offset_last = in->id_offset;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return fail(OMCGPU_E_CUDA, "kernel failure: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+} // namespace omc
+
+// =============================================================================
+// C ABI
+// =============================================================================
+using namespace omc;
+
+extern "C" {
+
+const char* omcgpu_last_error(void)
+{
+  return g_err;
+}
+
+int64_t omcgpu_kernel_launches(void)
+{
+  return g_launches;
+}
+
+int omcgpu_finalize(void)
+{
+  for (void* p : G.dev_allocs)
+    cudaFree(p);
+  G.dev_allocs.clear();
+  if (G.h_counts)
+    cudaFreeHost(G.h_counts);
+  if (G.h_counters)
+    cudaFreeHost(G.h_counters);
+  if (G.h_partial)
+    cudaFreeHost(G.h_partial);
+  if (G.h_aos)
+    cudaFreeHost(G.h_aos);
+  if (G.ev0) {
+    cudaEventDestroy(G.ev0);
+    cudaEventDestroy(G.ev1);
+    cudaEventDestroy(G.evx0);
+    cudaEventDestroy(G.evx1);
+  }
+  if (G.ready)
+    cudaStreamDestroy(G.stream);
+  G = Engine();
+  return 0;
+}
+
+int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
+{
+  if (!model || max_particles <= 0)
+    return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_init: bad arguments%s");
+  if (G.ready)
+    omcgpu_finalize();
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+    return fail(OMCGPU_E_CUDA, "no CUDA device available: the device path has no CPU fallback%s");
+  if (device < 0 || device >= n_dev)
+    return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_init: device index out of range%s");
+  CUDA_OK(cudaSetDevice(device));
+  int rc = check_supported(model);
+  if (rc)
+    return rc;
+  if (max_particles > 2000000000LL / 3)
+    return fail(OMCGPU_E_OUT_OF_BOUNDS, "max_particles too large for 32-bit work lists%s");
+  CUDA_OK(cudaStreamCreate(&G.stream));
+  rc = upload_model(model);
+  if (rc)
+    return rc;
+  const int64_t cap = max_particles;
+  G.cap = cap;
+  G.fis_cap = 3 * cap; // init_fission_bank(3 * work_per_rank), src/simulation.cpp:340
+  const int L = std::max(1, std::min<int>(model->n_coord_levels, OMCGPU_MAX_COORD));
+  PState& ps = G.ps;
+  ps.cap = cap;
+#define A(col, count) rc = rc ? rc : dev_alloc(&ps.col, (size_t)(count))
+  A(rx, cap * L); A(ry, cap * L); A(rz, cap * L); A(ux, cap * L); A(uy, cap * L); A(uz, cap * L);
+  A(cell, cap * L); A(universe, cap * L); A(lattice, cap * L);
+  A(lat_x, cap * L); A(lat_y, cap * L); A(lat_z, cap * L);
+  A(n_coord, cap); A(cell_last0, cap); A(cell_instance, cap); A(surface, cap);
+  A(material, cap); A(material_last, cap); A(sqrtkT, cap); A(sqrtkT_last, cap);
+  A(E, cap); A(g, cap); A(g_last, cap); A(wgt, cap); A(time, cap); A(seed, cap);
+  A(n_progeny, cap); A(n_event, cap);
+  A(xs_total, cap); A(xs_absorption, cap); A(xs_fission, cap); A(xs_nu_fission, cap);
+  A(b_surface, cap); A(b_level_trans, cap);
+  A(k_abs, cap); A(k_col, cap); A(k_trk, cap); A(k_leak, cap);
+#undef A
+  rc = rc ? rc : alloc_bank(G.src, cap);
+  rc = rc ? rc : alloc_bank(G.fis, G.fis_cap);
+  rc = rc ? rc : alloc_bank(G.fis_sorted, G.fis_cap);
+  rc = rc ? rc : dev_alloc(&G.d_counts, 8);
+  rc = rc ? rc : dev_alloc(&G.d_counters, 4);
+  for (int k = 0; k < 4; ++k) {
+    rc = rc ? rc : dev_alloc(&G.q[k].idx, cap);
+    G.q[k].count = G.d_counts + k;
+  }
+  rc = rc ? rc : dev_alloc(&G.d_offs, cap + 1);
+  rc = rc ? rc : dev_alloc(&G.d_gather, cap);
+  rc = rc ? rc : dev_alloc(&G.d_aos, G.fis_cap);
+  rc = rc ? rc : dev_alloc(&G.d_tally, G.n_tally);
+  G.n_chunks = 4096;
+  rc = rc ? rc : dev_alloc(&G.d_partial, G.n_chunks * 6);
+  if (rc)
+    return rc;
+#if OMC_CUDA
+  G.scan_tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, G.scan_tmp_bytes, G.ps.n_progeny, G.d_offs, (int)cap);
+  char* tmp = nullptr;
+  rc = dev_alloc(&tmp, G.scan_tmp_bytes);
+  if (rc)
+    return rc;
+  G.d_scan_tmp = tmp;
+#endif
+  CUDA_OK(cudaMallocHost((void**)&G.h_counts, 8 * sizeof(int32_t)));
+  CUDA_OK(cudaMallocHost((void**)&G.h_counters, 4 * sizeof(unsigned long long)));
+  CUDA_OK(cudaMallocHost((void**)&G.h_partial, G.n_chunks * 6 * sizeof(double)));
+  CUDA_OK(cudaMallocHost((void**)&G.h_aos, G.fis_cap * sizeof(omcgpu_site)));
+  CUDA_OK(cudaEventCreate(&G.ev0));
+  CUDA_OK(cudaEventCreate(&G.ev1));
+  CUDA_OK(cudaEventCreate(&G.evx0));
+  CUDA_OK(cudaEventCreate(&G.evx1));
+  if (const char* t = std::getenv("OMCGPU_TAIL_THRESHOLD"))
+    G.tail_threshold = std::atoll(t);
+  G.ready = true;
+  g_launches = 0;
+  return 0;
+}
+
+int omcgpu_set_source_bank(const omcgpu_site* source_bank, int64_t n)
+{
+  if (!G.ready)
+    return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  if (n > G.cap)
+    return fail(OMCGPU_E_OUT_OF_BOUNDS, "source bank larger than max_particles%s");
+  std::memcpy(G.h_aos, source_bank, n * sizeof(omcgpu_site));
+  CUDA_OK(cudaMemcpyAsync(G.d_aos, G.h_aos, n * sizeof(omcgpu_site), cudaMemcpyHostToDevice, G.stream));
+  BankArgs b;
+  std::memset(&b, 0, sizeof(b));
+  b.a = G.src;
+  b.aos = G.d_aos;
+  b.n = n;
+  OMC_LAUNCH(k_unpack, n, G.stream, b);
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  G.n_src = n;
+  return 0;
+}
+
+static int fetch_bank(const Bank& bank, omcgpu_site* out, int64_t n)
+{
+  BankArgs b;
+  std::memset(&b, 0, sizeof(b));
+  b.a = bank;
+  b.aos = G.d_aos;
+  b.n = n;
+  OMC_LAUNCH(k_pack, n, G.stream, b);
+  CUDA_OK(cudaMemcpyAsync(G.h_aos, G.d_aos, n * sizeof(omcgpu_site), cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  std::memcpy(out, G.h_aos, n * sizeof(omcgpu_site));
+  return 0;
+}
+
+int omcgpu_get_source_bank(omcgpu_site* source_bank, int64_t n)
+{
+  if (!G.ready || n > G.n_src)
+    return fail(OMCGPU_E_OUT_OF_BOUNDS, "omcgpu_get_source_bank: bad size%s");
+  return fetch_bank(G.src, source_bank, n);
+}
+
+int omcgpu_get_fission_bank(omcgpu_site* fission_bank, int64_t capacity, int64_t* n)
+{
+  if (!G.ready)
+    return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  const int64_t m = std::min<int64_t>(G.n_fis, capacity);
+  if (n)
+    *n = m;
+  return fetch_bank(G.fis_sorted, fission_bank, m);
+}
+
+int omcgpu_run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
+{
+  return run_generation(in, out);
+}
+
+int omcgpu_transport_generation(const omcgpu_gen_in* in, const omcgpu_site* source_bank,
+  omcgpu_site* fission_bank, int64_t fission_capacity, omcgpu_gen_out* out)
+{
+  int rc = omcgpu_set_source_bank(source_bank, in->n_particles);
+  if (rc)
+    return rc;
+  rc = run_generation(in, out);
+  if (rc)
+    return rc;
+  int64_t n = 0;
+  rc = omcgpu_get_fission_bank(fission_bank, fission_capacity, &n);
+  out->n_fission = n;
+  return rc;
+}
+
+int omcgpu_comb_fission_bank(int64_t start, int64_t total, int64_t n_particles, int64_t seed_id,
+  int64_t master_seed, uint64_t stride, int64_t* n_sampled)
+{
+  if (!G.ready)
+    return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  // The tooth positions are accumulated by repeated floating-point addition in
+  // the reference (src/eigenvalue.cpp:166-177); to select the very same sites the
+  // host does that short sequential recurrence and the device does the gather.
+  uint64_t seed = future_seed((uint64_t)seed_id * stride, (uint64_t)master_seed); // init_seed(id, STREAM_TRACKING)
+  const double teeth_distance = static_cast<double>(total) / n_particles;
+  const double teeth_offset = prn(seed) * teeth_distance;
+  const int64_t end = start + G.n_fis;
+  const int64_t tooth_start = (int64_t)std::ceil((start - teeth_offset) / teeth_distance);
+  const int64_t tooth_end = (int64_t)std::floor((end - teeth_offset) / teeth_distance) + 1;
+  const int64_t count = tooth_end - tooth_start;
+  if (count > G.cap)
+    return fail(OMCGPU_E_OUT_OF_BOUNDS, "comb selects more sites than max_particles%s");
+  int32_t* idx = reinterpret_cast<int32_t*>(G.h_aos);
+  double tooth = tooth_start * teeth_distance + teeth_offset;
+  for (int64_t i = 0; i < count; i++) {
+    idx[i] = (int32_t)((int64_t)std::floor(tooth) - start);
+    tooth += teeth_distance;
+  }
+  if (count > 0) {
+    CUDA_OK(cudaMemcpyAsync(G.d_gather, idx, count * sizeof(int32_t), cudaMemcpyHostToDevice, G.stream));
+    BankArgs b;
+    std::memset(&b, 0, sizeof(b));
+    b.a = G.fis_sorted;
+    b.b = G.src;
+    b.gather = G.d_gather;
+    b.n = count;
+    OMC_LAUNCH(k_gather_bank, count, G.stream, b);
+    CUDA_OK(cudaStreamSynchronize(G.stream));
+  }
+  G.n_src = count;
+  if (n_sampled)
+    *n_sampled = count;
+  return 0;
+}
+
+int omcgpu_bank_columns_device(int which, void** cols, int64_t* n, int64_t* capacity)
+{
+  if (!G.ready)
+    return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  const Bank& b = which == 0 ? G.src : G.fis_sorted;
+  cols[0] = b.x; cols[1] = b.y; cols[2] = b.z; cols[3] = b.u; cols[4] = b.v; cols[5] = b.w;
+  cols[6] = b.E; cols[7] = b.time; cols[8] = b.wgt; cols[9] = b.delayed_group;
+  cols[10] = b.parent_id; cols[11] = b.progeny_id;
+  if (n)
+    *n = which == 0 ? G.n_src : G.n_fis;
+  if (capacity)
+    *capacity = b.cap;
+  return 0;
+}
+
+int omcgpu_set_source_count(int64_t n)
+{
+  if (!G.ready || n > G.cap)
+    return fail(OMCGPU_E_OUT_OF_BOUNDS, "omcgpu_set_source_count: bad size%s");
+  G.n_src = n;
+  return 0;
+}
+
+int omcgpu_tally_results(int32_t tally, double* value, int64_t n)
+{
+  if (!G.ready || tally < 0 || tally >= G.hm.n_tallies)
+    return fail(OMCGPU_E_OUT_OF_BOUNDS, "omcgpu_tally_results: bad tally index%s");
+  std::vector<int64_t> ofs(G.hm.n_tallies + 1);
+  CUDA_OK(cudaMemcpy(ofs.data(), G.hm.tally_result_ofs, ofs.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  const int64_t len = ofs[tally + 1] - ofs[tally];
+  if (n != len)
+    return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_tally_results: size mismatch%s");
+  std::vector<double> tmp(len);
+  CUDA_OK(cudaMemcpy(tmp.data(), G.d_tally + ofs[tally], len * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemset(G.d_tally + ofs[tally], 0, len * sizeof(double)));
+  for (int64_t i = 0; i < len; ++i)
+    value[i] += tmp[i];
+  return 0;
+}
+
+int omcgpu_tally_values_device(double** values, int64_t* n)
+{
+  if (!G.ready)
+    return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  *values = G.d_tally;
+  *n = G.n_tally;
+  return 0;
+}
+
+int omcgpu_calculate_xs(const double* E, const int32_t* material, int64_t n, double* out,
+  int32_t* i_grid, int32_t max_nuc)
+{
+  if (!G.ready)
+    return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  double *dE = nullptr, *dout = nullptr;
+  int32_t *dm = nullptr, *dig = nullptr;
+  CUDA_OK(cudaMalloc((void**)&dE, n * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&dm, n * sizeof(int32_t)));
+  CUDA_OK(cudaMalloc((void**)&dout, n * 4 * sizeof(double)));
+  if (i_grid)
+    CUDA_OK(cudaMalloc((void**)&dig, n * max_nuc * sizeof(int32_t)));
+  CUDA_OK(cudaMemcpy(dE, E, n * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(dm, material, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  XsArgs a;
+  a.E = dE; a.material = dm; a.n = n; a.out = dout; a.i_grid = dig; a.max_nuc = max_nuc;
+  OMC_LAUNCH(k_probe_xs, n, G.stream, a);
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  CUDA_OK(cudaMemcpy(out, dout, n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (i_grid)
+    CUDA_OK(cudaMemcpy(i_grid, dig, n * max_nuc * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  cudaFree(dE); cudaFree(dm); cudaFree(dout);
+  if (dig)
+    cudaFree(dig);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return fail(OMCGPU_E_CUDA, "kernel failure: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int omcgpu_calculate_xs_device(const double* E, const int32_t* material, int64_t n, double* out,
+  float* ms)
+{
+  if (!G.ready)
+    return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  XsArgs a;
+  a.E = E; a.material = material; a.n = n; a.out = out; a.i_grid = nullptr; a.max_nuc = 0;
+  CUDA_OK(cudaEventRecord(G.evx0, G.stream));
+  OMC_LAUNCH(k_probe_xs, n, G.stream, a);
+  CUDA_OK(cudaEventRecord(G.evx1, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  if (ms)
+    cudaEventElapsedTime(ms, G.evx0, G.evx1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return fail(OMCGPU_E_CUDA, "kernel failure: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+static int geom_probe(const double* xyz, const double* uvw, int64_t n, int32_t* cell,
+  int32_t* instance, int32_t* material, int32_t* n_coord, double* distance, int32_t* surface,
+  int32_t* level, int32_t* lattice_trans)
+{
+  if (!G.ready)
+    return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  GeoArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.ps = G.ps;
+  a.n = n;
+  std::vector<void*> tmp;
+  auto dalloc = [&](size_t bytes) {
+    void* p = nullptr;
+    cudaMalloc(&p, bytes);
+    tmp.push_back(p);
+    return p;
+  };
+  for (int64_t done = 0; done < n; done += G.cap) {
+    const int64_t m = std::min<int64_t>(G.cap, n - done);
+    double* dx = (double*)dalloc(m * 3 * sizeof(double));
+    cudaMemcpy(dx, xyz + 3 * done, m * 3 * sizeof(double), cudaMemcpyHostToDevice);
+    a.xyz = dx;
+    a.uvw = nullptr;
+    if (uvw) {
+      double* du = (double*)dalloc(m * 3 * sizeof(double));
+      cudaMemcpy(du, uvw + 3 * done, m * 3 * sizeof(double), cudaMemcpyHostToDevice);
+      a.uvw = du;
+    }
+    a.n = m;
+    if (cell) {
+      a.cell = (int32_t*)dalloc(m * 4);
+      a.instance = (int32_t*)dalloc(m * 4);
+      a.material = (int32_t*)dalloc(m * 4);
+      a.n_coord = (int32_t*)dalloc(m * 4);
+    }
+    if (distance) {
+      a.distance = (double*)dalloc(m * 8);
+      a.surface = (int32_t*)dalloc(m * 4);
+      a.level = (int32_t*)dalloc(m * 4);
+      a.lat_trans = (int32_t*)dalloc(m * 12);
+    }
+    OMC_LAUNCH(k_probe_geom, m, G.stream, a);
+    cudaStreamSynchronize(G.stream);
+    if (cell) {
+      cudaMemcpy(cell + done, a.cell, m * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(instance + done, a.instance, m * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(material + done, a.material, m * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(n_coord + done, a.n_coord, m * 4, cudaMemcpyDeviceToHost);
+    }
+    if (distance) {
+      cudaMemcpy(distance + done, a.distance, m * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(surface + done, a.surface, m * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(level + done, a.level, m * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(lattice_trans + 3 * done, a.lat_trans, m * 12, cudaMemcpyDeviceToHost);
+    }
+    for (void* p : tmp)
+      cudaFree(p);
+    tmp.clear();
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return fail(OMCGPU_E_CUDA, "kernel failure: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int omcgpu_find_cell(const double* xyz, const double* uvw, int64_t n, int32_t* cell,
+  int32_t* instance, int32_t* material, int32_t* n_coord)
+{
+  return geom_probe(xyz, uvw, n, cell, instance, material, n_coord, nullptr, nullptr, nullptr, nullptr);
+}
+
+int omcgpu_distance_to_boundary(const double* xyz, const double* uvw, int64_t n, double* distance,
+  int32_t* surface, int32_t* level, int32_t* lattice_trans)
+{
+  return geom_probe(xyz, uvw, n, nullptr, nullptr, nullptr, nullptr, distance, surface, level,
+    lattice_trans);
+}
+
+static int rng_probe(const uint64_t* n, const uint64_t* seed, int64_t count, int32_t per,
+  uint64_t* out_u, double* out_d)
+{
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+    return fail(OMCGPU_E_CUDA, "no CUDA device available: the device path has no CPU fallback%s");
+  RngArgs a;
+  std::memset(&a, 0, sizeof(a));
+  uint64_t *dn = nullptr, *ds = nullptr, *du = nullptr;
+  double* dd = nullptr;
+  CUDA_OK(cudaMalloc((void**)&ds, count * 8));
+  CUDA_OK(cudaMemcpy(ds, seed, count * 8, cudaMemcpyHostToDevice));
+  if (n) {
+    CUDA_OK(cudaMalloc((void**)&dn, count * 8));
+    CUDA_OK(cudaMemcpy(dn, n, count * 8, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc((void**)&du, count * 8));
+  } else {
+    CUDA_OK(cudaMalloc((void**)&dd, count * per * 8));
+  }
+  a.n = dn; a.seed = ds; a.count = count; a.per = per; a.out_u = du; a.out_d = dd;
+  OMC_LAUNCH(k_probe_rng, count, 0, a);
+  CUDA_OK(cudaDeviceSynchronize());
+  if (out_u)
+    CUDA_OK(cudaMemcpy(out_u, du, count * 8, cudaMemcpyDeviceToHost));
+  else
+    CUDA_OK(cudaMemcpy(out_d, dd, count * per * 8, cudaMemcpyDeviceToHost));
+  cudaFree(ds);
+  if (dn) cudaFree(dn);
+  if (du) cudaFree(du);
+  if (dd) cudaFree(dd);
+  return 0;
+}
+
+int omcgpu_future_seed(const uint64_t* n, const uint64_t* seed, int64_t count, uint64_t* out)
+{
+  return rng_probe(n, seed, count, 0, out, nullptr);
+}
+
+int omcgpu_prn(const uint64_t* seed, int64_t n_seeds, int32_t count, double* out)
+{
+  return rng_probe(nullptr, seed, n_seeds, count, nullptr, out);
+}
+
+} // extern "C"
