@@ -1,0 +1,121 @@
+"""Multi-GPU plumbing: one process per GPU over torch.distributed (NCCL over
+NVLink/NVSwitch on the box, gloo in the CPU tests).
+
+The path shards the way the reference's MPI decomposition does:
+every rank owns the global source sites [work_index[r], work_index[r+1]) of a
+generation, geometry and data are replicated, and there is ONE exchange step
+per generation -- ``synchronize_bank`` (src/eigenvalue.cpp:86-365):
+
+1. all-gather of the per-rank fission-bank sizes -> start offsets and total
+   (replaces MPI_Exscan + MPI_Bcast, :100-112);
+2. every rank combs its (device-resident, sorted) fission bank with the SAME
+   generation seed (:152-178) -- omcgpu_comb_fission_bank;
+3. all-gather of the sampled counts (replaces MPI_Exscan + MPI_Allgather, :186-197);
+4. point-to-point exchange of contiguous runs of sites to their owners
+   (replaces MPI_Isend/Irecv, :224-348) -- batched isend/irecv of packed SoA rows
+   straight from / into the device bank columns;
+5. all-reduce of the k / leakage / weight globals and of tally VALUE arrays
+   (replaces MPI_Allreduce/MPI_Reduce, src/eigenvalue.cpp:63, src/tallies/tally.cpp:1014-1053).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+_COL_DTYPES = [torch.float64] * 9 + [torch.int32, torch.int64, torch.int64]
+
+
+class _CudaPtr:
+    """Expose a raw device pointer through __cuda_array_interface__."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2}
+
+
+def _column_tensor(ptr, n, dtype, on_gpu):
+    if n == 0:
+        return torch.zeros(0, dtype=dtype, device="cuda" if on_gpu else "cpu")
+    if on_gpu:
+        ts = {torch.float64: "<f8", torch.int32: "<i4", torch.int64: "<i8"}[dtype]
+        return torch.as_tensor(_CudaPtr(ptr, n, ts), device="cuda")
+    ct = {torch.float64: C.c_double, torch.int32: C.c_int32, torch.int64: C.c_int64}[dtype]
+    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,))
+    return torch.from_numpy(arr)
+
+
+class TorchComm:
+    def __init__(self, on_gpu: bool):
+        self.rank = dist.get_rank()
+        self.size = dist.get_world_size()
+        self.on_gpu = on_gpu
+        self.dev = "cuda" if on_gpu else "cpu"
+        self.exchange_bytes = 0
+
+    def allreduce_sum(self, a: np.ndarray) -> np.ndarray:
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def allgather_int(self, v: int):
+        t = torch.tensor([v], dtype=torch.int64, device=self.dev)
+        out = [torch.zeros_like(t) for _ in range(self.size)]
+        dist.all_gather(out, t)
+        return [int(x.item()) for x in out]
+
+    def _bank(self, engine, which, n):
+        cols, _, cap = engine.bank_columns_device(which)
+        return [_column_tensor(p, cap, dt, self.on_gpu) for p, dt in zip(cols, _COL_DTYPES)]
+
+    def synchronize_bank(self, sim, seed_id, n_fission):
+        eng = sim.engine
+        counts = self.allgather_int(n_fission)
+        total = sum(counts)
+        start = sum(counts[:self.rank])
+        n_s = eng.comb_fission_bank(start, total, sim.n_particles, seed_id, sim.seed, sim.stride)
+        sampled = self.allgather_int(n_s)
+        assert sum(sampled) == sim.n_particles, (sampled, sim.n_particles)
+        pos = np.concatenate([[0], np.cumsum(sampled)])        # bank_position
+        wi = sim.work_index
+        cols = self._bank(eng, 0, n_s)
+        # pack my sampled sites as rows of 12 x 8 bytes (ints widened / bit-cast)
+        mine = torch.stack([c[:n_s].to(torch.float64) if c.dtype == torch.float64 else
+                            c[:n_s].to(torch.int64).view(torch.float64) for c in cols], dim=1) \
+            if n_s > 0 else torch.zeros((0, 12), dtype=torch.float64, device=self.dev)
+        my_lo, my_hi = int(pos[self.rank]), int(pos[self.rank + 1])
+        need_lo, need_hi = wi[self.rank], wi[self.rank + 1]
+        new = torch.empty((need_hi - need_lo, 12), dtype=torch.float64, device=self.dev)
+        ops, recvs = [], []
+        for peer in range(self.size):
+            # what I hold that `peer` owns
+            lo, hi = max(my_lo, wi[peer]), min(my_hi, wi[peer + 1])
+            if hi > lo:
+                chunk = mine[lo - my_lo:hi - my_lo]
+                if peer == self.rank:
+                    new[lo - need_lo:hi - need_lo] = chunk
+                else:
+                    ops.append(dist.P2POp(dist.isend, chunk.contiguous(), peer))
+                    self.exchange_bytes += chunk.numel() * 8
+            # what `peer` holds that I own
+            lo, hi = max(int(pos[peer]), need_lo), min(int(pos[peer + 1]), need_hi)
+            if hi > lo and peer != self.rank:
+                buf = torch.empty((hi - lo, 12), dtype=torch.float64, device=self.dev)
+                recvs.append((lo - need_lo, hi - need_lo, buf))
+                ops.append(dist.P2POp(dist.irecv, buf, peer))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for a, b, buf in recvs:
+            new[a:b] = buf
+        n_new = need_hi - need_lo
+        for k, c in enumerate(cols):
+            if c.dtype == torch.float64:
+                c[:n_new] = new[:, k]
+            else:
+                c[:n_new] = new[:, k].contiguous().view(torch.int64).to(c.dtype)
+        if self.on_gpu:
+            torch.cuda.synchronize()
+        eng.set_source_count(n_new)

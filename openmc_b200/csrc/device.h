@@ -840,12 +840,12 @@ OMC_HD int ce_log_index(double E)
 {
   int k = (int)(log(E / DM.energy_min) / DM.log_spacing);
   const int nb = DM.n_log_bins;
-  k = k < 0 ? 0 : (k > nb ? nb : k);
+  k = k < 0 ? 0 : (k > nb - 1 ? nb - 1 : k);
   while (k > 0 && E < ld(DM.hash_edge + k))
     --k;
-  while (k < nb && E >= ld(DM.hash_edge + k + 1))
+  while (k < nb - 1 && E >= ld(DM.hash_edge + k + 1))
     ++k;
-  return k;
+  return k; // clamped to the last valid window, see oracle.cpp ce_log_index
 }
 
 OMC_HD void ce_micro_xs(int nuc, int i_log, double E, MicroXS& micro)

@@ -180,3 +180,47 @@ def pincell_multigroup(mesh_dim=100, energy_bins=500):
     m.tallies = [Tally(1, [1], ["flux", "fission", "nu-fission"]), Tally(2, [2], ["flux"])]
     box = [-pitch / 2, -pitch / 2, -1, pitch / 2, pitch / 2, 1]
     return m, c5g7_library(False), box, True
+
+
+# ----------------------------------------------------------------------------
+# Config C2: UO2 pincell, continuous energy, synthetic library
+# ----------------------------------------------------------------------------
+def pincell_ce(n_grid=100000, mesh_dim=100, energy_bins=500, tallies=True, library=None):
+    """examples/pincell/build_xml.py:11-120 geometry/settings (fuel, gap, clad,
+    borated water in a reflective 1.25984 cm box; 100x100 mesh {flux, fission,
+    nu-fission} + 500-bin flux spectrum) with the 10-nuclide synthetic library of
+    openmc_b200.nuclide (no S(a,b), one temperature)."""
+    from . import nuclide as nd
+    m = Model()
+    uo2 = m.material(name="UO2 fuel at 2.4% wt enrichment", units="g/cm3", density=10.29769,
+                     components=[("U235", 0.024 * 238.0 / 235.0 / (1 + 0.024 * (238.0 / 235.0 - 1))),
+                                 ("U238", 1.0 - 0.024 * 238.0 / 235.0 / (1 + 0.024 * (238.0 / 235.0 - 1))),
+                                 ("O16", 2.0)])
+    helium = m.material(name="Helium for gap", units="g/cm3", density=0.001598,
+                        components=[("He4", 1.0)])
+    zirc = m.material(name="Zircaloy 4", units="g/cm3", density=6.55,
+                      components=[("Sn120", -0.014), ("Fe56", -0.00265), ("Zr90", -0.60),
+                                  ("Zr91", -0.38335)])
+    water = m.material(name="Borated water", units="g/cm3", density=0.740582,
+                       components=[("B10", 8.0e-6), ("H1", 5.0e-2), ("O16", 2.4e-2)])
+    pitch = 1.25984
+    s_fo = m.surface("z-cylinder", [0.0, 0.0, 0.39218]).id
+    s_ci = m.surface("z-cylinder", [0.0, 0.0, 0.40005]).id
+    s_co = m.surface("z-cylinder", [0.0, 0.0, 0.45720]).id
+    x0 = m.surface("x-plane", [-pitch / 2], "reflective").id
+    x1 = m.surface("x-plane", [pitch / 2], "reflective").id
+    y0 = m.surface("y-plane", [-pitch / 2], "reflective").id
+    y1 = m.surface("y-plane", [pitch / 2], "reflective").id
+    m.cell(region=f"-{s_fo}", fill=uo2)
+    m.cell(region=f"{s_fo} -{s_ci}", fill=helium)
+    m.cell(region=f"{s_ci} -{s_co}", fill=zirc)
+    m.cell(region=f"{s_co} {x0} -{x1} {y0} -{y1}", fill=water)
+    if tallies:
+        m.meshes = [Mesh(1, [mesh_dim, mesh_dim], [-pitch / 2, -pitch / 2], [pitch / 2, pitch / 2])]
+        edges = np.logspace(np.log10(1e-5), np.log10(20.0e6), energy_bins + 1)
+        m.filters = [Filter(1, "mesh", 1), Filter(2, "energy", list(edges))]
+        m.tallies = [Tally(1, [1], ["flux", "fission", "nu-fission"]), Tally(2, [2], ["flux"])]
+    if library is None:
+        library = nd.synthetic_library(nd.PINCELL_NUCLIDES, n_grid)
+    box = [-pitch / 2, -pitch / 2, -1, pitch / 2, pitch / 2, 1]
+    return m, library, box, True

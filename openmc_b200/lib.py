@@ -254,12 +254,14 @@ def comb_indices(start, n_local, total, n_particles, seed_id, master_seed=DEFAUL
     end = start + n_local
     tooth_start = math.ceil((start - teeth_offset) / teeth_distance)
     tooth_end = math.floor((end - teeth_offset) / teeth_distance) + 1
-    idx = np.empty(max(tooth_end - tooth_start, 0), np.int64)
-    tooth = tooth_start * teeth_distance + teeth_offset
-    for k in range(idx.size):
-        idx[k] = math.floor(tooth) - start
-        tooth += teeth_distance
-    return idx
+    count = max(tooth_end - tooth_start, 0)
+    # tooth += teeth_distance, repeated: np.cumsum accumulates left to right in
+    # double precision, i.e. exactly the reference's sequential recurrence
+    steps = np.full(count, teeth_distance)
+    if count:
+        steps[0] = tooth_start * teeth_distance + teeth_offset
+    teeth = np.cumsum(steps)
+    return np.floor(teeth).astype(np.int64) - start
 
 
 class Simulation:

@@ -1101,8 +1101,17 @@ double eval_function(int f, double x)
 }
 
 int ce_log_index(double E)
-{ // src/material.cpp:833-834
-  return std::log(E / M->energy_min) / M->log_spacing;
+{ // src/material.cpp:833-834.  For E within rounding of energy_max the reference's
+  // index equals n_log_bins and Nuclide::calculate_xs reads grid_index[M + 1], one
+  // past the end of the table (undefined behaviour that cannot be restated); both
+  // the oracle and the device clamp to the last valid window [M-1, M], which holds
+  // the same grid interval.  Energies below energy_min never reach the hash.
+  int i = std::log(E / M->energy_min) / M->log_spacing;
+  if (i > M->n_log_bins - 1)
+    i = M->n_log_bins - 1;
+  if (i < 0)
+    i = 0;
+  return i;
 }
 
 void ce_micro_xs(int i_nuclide, int i_log_union, double E, MicroXS& micro)

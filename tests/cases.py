@@ -37,3 +37,33 @@ def build(name):
 
 def fmt(x):
     return "%.6E" % x
+
+
+_CE_CACHE = {}
+
+
+def build_ce(n_grid=4000, tallies=True, mesh_dim=8, energy_bins=16):
+    """small synthetic CE pincell (config C2 geometry, 10 nuclides) for parity tests"""
+    from openmc_b200 import nuclide
+    key = (n_grid, tallies, mesh_dim, energy_bins)
+    if key not in _CE_CACHE:
+        m, libx, box, of = examples.pincell_ce(n_grid=n_grid, mesh_dim=mesh_dim,
+                                               energy_bins=energy_bins, tallies=tallies)
+        _CE_CACHE[key] = (nuclide.build_ce_model(m, libx), box, of, libx)
+    return _CE_CACHE[key]
+
+
+def xs_probe_energies(model, libx, n, seed=7):
+    """log-uniform energies + the edge cases of SURVEY Appendix B.1: exact grid
+    points, first/last points, out-of-range values, hash-bin edges."""
+    import numpy as np
+    g = np.random.default_rng(seed)
+    e_min, e_max = float(model["energy_min"]), float(model["energy_max"])
+    E = np.exp(g.uniform(np.log(e_min), np.log(e_max), n))
+    grid = np.asarray(model["nuc_energy"])
+    pick = grid[g.integers(0, grid.size, n // 10)]
+    spacing = float(model["log_spacing"])
+    edges = e_min * np.exp(spacing * g.integers(1, int(model["n_log_bins"]), n // 10))
+    near = np.concatenate([np.nextafter(edges, 0), edges, np.nextafter(edges, np.inf)])
+    special = np.array([e_min, e_max, e_min * 0.5, e_max * 1.5, np.nextafter(e_min, 1), np.nextafter(e_max, 0)])
+    return np.concatenate([E, pick, np.nextafter(pick, 0), np.nextafter(pick, np.inf), near, special])
