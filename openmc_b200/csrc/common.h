@@ -97,6 +97,9 @@ struct PState {
   double *xs_total, *xs_absorption, *xs_fission, *xs_nu_fission;
   int32_t *b_surface, *b_level_trans;
   double *k_abs, *k_col, *k_trk, *k_leak;
+  // the last flight, kept for the tally-scoring kernel: start point (r_last of
+  // include/openmc/particle_data.h) and flight distance
+  double *rlx, *rly, *rlz, *adv_dist;
 };
 
 // Source / fission banks as SoA columns (the 104-byte AoS SourceSite is only the

@@ -1315,6 +1315,15 @@ OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no
 // 1622-1990, 2416-2541 ; src/mesh.cpp:874-929, 999-1146, 1328-1369 ;
 // src/tallies/filter_{mesh,energy,cell,material,universe}.cpp
 // =============================================================================
+OMC_D void atomic_add_f64(double* addr, double val)
+{
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  atomicAdd(addr, val); // result unused -> RED.E.ADD.F64
+#else
+  *addr += val;
+#endif
+}
+
 OMC_D void tally_add(double* addr, double val)
 {
 #if OMC_CUDA && defined(__CUDA_ARCH__)
@@ -1410,9 +1419,127 @@ OMC_HD int mesh_index(int m, double r, int k)
   return (int)ceil((r - ld(DM.mesh_lower_left + 3 * m + k)) / ld(DM.mesh_width + 3 * m + k));
 }
 
-// Score one tally for one track r0 -> r1.  `bins`/`nb` hold the (<= MAX_COORD)
-// matches of each non-mesh filter; a mesh filter, if present at position
-// `mesh_pos`, streams its (bin, weight) pairs from the ray trace.
+// StructuredMesh::raytrace_mesh, src/mesh.cpp:999-1118, over the part [t0, t1]
+// of the track r0 + t u, 0 <= t <= total.  (t0, t1) = (0, total) is the
+// reference's loop verbatim.  A track can be cut into consecutive parts that
+// are traced independently (k_score hands the parts of long tracks to different
+// lanes): every crossing distance is measured from r0 with the reference's
+// formula, so the parts emit the same (bin, length) pairs as the whole track,
+// with the pair that straddles a cut emitted as two pieces.
+// emit(bin, w): w = fraction of `total` spent in mesh bin `bin`.
+template<class Emit>
+OMC_D void mesh_march(int m, V3 r0, V3 u, double total, double t0, double t1, Emit& emit)
+{
+  const int nd = ld(DM.mesh_ndim + m);
+  const int s0 = ld(DM.mesh_shape + 3 * m), s1 = ld(DM.mesh_shape + 3 * m + 1),
+            s2 = ld(DM.mesh_shape + 3 * m + 2);
+  // the first part starts TINY_BIT inside (mesh.cpp:1021); a later part starts at
+  // its cut, where the cell is decided by position alone
+  const double ts = (t0 == 0.0) ? TINY_BIT : t0;
+  int i0 = mesh_index(m, r0.x + ts * u.x, 0);
+  int i1 = nd > 1 ? mesh_index(m, r0.y + ts * u.y, 1) : 1;
+  int i2 = nd > 2 ? mesh_index(m, r0.z + ts * u.z, 2) : 1;
+  const int n1 = nd > 1 ? s1 : 1, n2 = nd > 2 ? s2 : 1;
+#define MESH_IN() (i0 >= 1 && i0 <= s0 && i1 >= 1 && i1 <= n1 && i2 >= 1 && i2 <= n2)
+#define MESH_BIN() (((i2 - 1) * n1 + (i1 - 1)) * s0 + i0 - 1)
+  bool in_mesh = MESH_IN();
+  if (total < 2 * TINY_BIT) {
+    if (in_mesh)
+      emit(MESH_BIN(), 1.0);
+    return;
+  }
+  MeshDist d0 = mesh_grid_distance(m, i0, 0, r0.x, u.x), d1, d2;
+  d1.next_index = d2.next_index = -1;
+  d1.distance = d2.distance = INFTY;
+  if (nd > 1)
+    d1 = mesh_grid_distance(m, i1, 1, r0.y, u.y);
+  if (nd > 2)
+    d2 = mesh_grid_distance(m, i2, 2, r0.z, u.z);
+  double traveled = t0;
+  for (int guard = 0; guard < 1000000; ++guard) {
+    if (in_mesh) {
+      int k = 0;
+      double dk = d0.distance;
+      if (d1.distance < dk) {
+        k = 1;
+        dk = d1.distance;
+      }
+      if (d2.distance < dk) {
+        k = 2;
+        dk = d2.distance;
+      }
+      emit(MESH_BIN(), ((dk < t1 ? dk : t1) - traveled) / total);
+      traveled = dk;
+      if (traveled >= t1)
+        break;
+      if (k == 0) {
+        i0 = d0.next_index;
+        d0 = mesh_grid_distance(m, i0, 0, r0.x, u.x);
+      } else if (k == 1) {
+        i1 = d1.next_index;
+        d1 = mesh_grid_distance(m, i1, 1, r0.y, u.y);
+      } else {
+        i2 = d2.next_index;
+        d2 = mesh_grid_distance(m, i2, 2, r0.z, u.z);
+      }
+      in_mesh = MESH_IN();
+    } else {
+      int k_max = -1;
+      if ((i0 < 1 || i0 > s0) && d0.distance > traveled) {
+        traveled = d0.distance;
+        k_max = 0;
+      }
+      if (nd > 1 && (i1 < 1 || i1 > s1) && d1.distance > traveled) {
+        traveled = d1.distance;
+        k_max = 1;
+      }
+      if (nd > 2 && (i2 < 1 || i2 > s2) && d2.distance > traveled) {
+        traveled = d2.distance;
+        k_max = 2;
+      }
+      if (k_max == -1)
+        traveled += TINY_BIT;
+      if (traveled >= t1)
+        break;
+      const double tt = traveled + TINY_BIT;
+      i0 = mesh_index(m, r0.x + tt * u.x, 0);
+      if (nd > 1)
+        i1 = mesh_index(m, r0.y + tt * u.y, 1);
+      if (nd > 2)
+        i2 = mesh_index(m, r0.z + tt * u.z, 2);
+      in_mesh = MESH_IN();
+      d0 = mesh_grid_distance(m, i0, 0, r0.x, u.x);
+      if (nd > 1)
+        d1 = mesh_grid_distance(m, i1, 1, r0.y, u.y);
+      if (nd > 2)
+        d2 = mesh_grid_distance(m, i2, 2, r0.z, u.z);
+    }
+  }
+#undef MESH_IN
+#undef MESH_BIN
+}
+
+// Number of mesh cells the track r0 -> r1 visits (exact for a track inside the
+// mesh, an estimate otherwise) -- only used to balance work between lanes.
+OMC_HD int mesh_cells_visited(int m, V3 r0, V3 r1, V3 u)
+{
+  const int nd = ld(DM.mesh_ndim + m);
+  int n = 1;
+  for (int k = 0; k < nd; ++k) {
+    const int sk = ld(DM.mesh_shape + 3 * m + k);
+    int a = mesh_index(m, comp(r0, k) + TINY_BIT * comp(u, k), k);
+    int b = mesh_index(m, comp(r1, k), k);
+    a = a < 0 ? 0 : (a > sk + 1 ? sk + 1 : a);
+    b = b < 0 ? 0 : (b > sk + 1 ? sk + 1 : b);
+    n += a > b ? a - b : b - a;
+  }
+  return n;
+}
+
+// A tally evaluated for one track: the matches of its non-mesh filters
+// (FilterBinIter, src/tallies/tally_scoring.cpp:31-141); a mesh filter, if
+// present at position `mesh_pos`, streams its (bin, weight) pairs from the ray
+// trace.
 struct TallyEval {
   int nf;
   int mesh_pos;
@@ -1421,6 +1548,67 @@ struct TallyEval {
   int bins[OMCGPU_MAX_FILTERS][OMCGPU_MAX_COORD];
   int stride[OMCGPU_MAX_FILTERS];
 };
+
+// returns false when some filter of tally t has no matching bin
+OMC_HD bool tally_prepare(const PState& ps, int64_t i, int n_coord, int t, double E_last,
+  const ScoreCtx& sc, TallyEval& te)
+{
+  const int G = DM.mg_n_groups;
+  te.nf = ld(DM.tally_n_filters + t);
+  te.mesh_pos = -1;
+  te.mesh = -1;
+  for (int k = 0; k < te.nf; ++k) {
+    const int f = ld(DM.tally_filters + OMCGPU_MAX_FILTERS * t + k);
+    te.stride[k] = ld(DM.tally_strides + OMCGPU_MAX_FILTERS * t + k);
+    te.nb[k] = 0;
+    const int o = ld(DM.filter_data_ofs + f);
+    switch (ld(DM.filter_type + f)) {
+    case OMCGPU_FILTER_MESH:
+      te.mesh_pos = k;
+      te.mesh = ld(DM.filter_mesh + f);
+      te.nb[k] = 1;
+      break;
+    case OMCGPU_FILTER_ENERGY: {
+      const int nbin = ld(DM.filter_n_bins + f);
+      if (!DM.run_CE && ld(DM.filter_matches_groups + f)) {
+        te.bins[k][0] = G - sc.g - 1;
+        te.nb[k] = 1;
+      } else {
+        const double* e = DM.filter_ddata + o;
+        if (E_last >= ld(e) && E_last <= ld(e + nbin)) {
+          te.bins[k][0] = (int)lower_bound_index(e, (int64_t)nbin + 1, E_last);
+          te.nb[k] = 1;
+        }
+      }
+      break;
+    }
+    case OMCGPU_FILTER_CELL:
+      for (int l = 0; l < n_coord; ++l) {
+        const int b = ld(DM.filter_idata + o + LV(cell, l));
+        if (b >= 0)
+          te.bins[k][te.nb[k]++] = b;
+      }
+      break;
+    case OMCGPU_FILTER_MATERIAL:
+      if (sc.material >= 0) {
+        const int b = ld(DM.filter_idata + o + sc.material);
+        if (b >= 0)
+          te.bins[k][te.nb[k]++] = b;
+      }
+      break;
+    default: // universe
+      for (int l = 0; l < n_coord; ++l) {
+        const int b = ld(DM.filter_idata + o + LV(universe, l));
+        if (b >= 0)
+          te.bins[k][te.nb[k]++] = b;
+      }
+      break;
+    }
+    if (te.nb[k] == 0)
+      return false;
+  }
+  return true;
+}
 
 OMC_D void tally_emit(const TallyEval& te, int t, int mesh_bin, double mesh_w, const ScoreCtx& sc,
   double* values)
@@ -1455,144 +1643,44 @@ OMC_D void tally_emit(const TallyEval& te, int t, int mesh_bin, double mesh_w, c
       }
 }
 
+struct GenericEmit { // one lane scores its whole track: any filter combination
+  const TallyEval* te;
+  int t;
+  const ScoreCtx* sc;
+  double* values;
+  OMC_D void operator()(int bin, double w) const { tally_emit(*te, t, bin, w, *sc, values); }
+};
+
+// Track geometry of the mesh ray trace: total_distance is |r1 - r0|, not the
+// flight distance (src/mesh.cpp:1008-1010)
+OMC_HD double track_length(V3 r0, V3 r1)
+{
+  const double dx = r1.x - r0.x, dy = r1.y - r0.y, dz = r1.z - r0.z;
+  return sqrt(dx * dx + dy * dy + dz * dz);
+}
+
+// score_tracklength_tally by ONE lane for ONE track (the tail kernel and the
+// rare tallies with several matches per filter); src/tallies/tally_scoring.cpp:2416-2541
 OMC_D void score_tracklength(const PState& ps, int64_t i, int n_coord, V3 r0, V3 r1, V3 u,
   double E_last, const ScoreCtx& sc, double* values)
 {
-  const int G = DM.mg_n_groups;
   for (int t = 0; t < DM.n_tallies; ++t) {
     TallyEval te;
-    te.nf = ld(DM.tally_n_filters + t);
-    te.mesh_pos = -1;
-    te.mesh = -1;
-    bool empty = false;
-    for (int k = 0; k < te.nf && !empty; ++k) {
-      const int f = ld(DM.tally_filters + OMCGPU_MAX_FILTERS * t + k);
-      te.stride[k] = ld(DM.tally_strides + OMCGPU_MAX_FILTERS * t + k);
-      te.nb[k] = 0;
-      const int o = ld(DM.filter_data_ofs + f);
-      switch (ld(DM.filter_type + f)) {
-      case OMCGPU_FILTER_MESH:
-        te.mesh_pos = k;
-        te.mesh = ld(DM.filter_mesh + f);
-        te.nb[k] = 1;
-        break;
-      case OMCGPU_FILTER_ENERGY: {
-        const int nbin = ld(DM.filter_n_bins + f);
-        if (!DM.run_CE && ld(DM.filter_matches_groups + f)) {
-          te.bins[k][0] = G - sc.g - 1;
-          te.nb[k] = 1;
-        } else {
-          const double* e = DM.filter_ddata + o;
-          if (E_last >= ld(e) && E_last <= ld(e + nbin)) {
-            te.bins[k][0] = (int)lower_bound_index(e, (int64_t)nbin + 1, E_last);
-            te.nb[k] = 1;
-          }
-        }
-        break;
-      }
-      case OMCGPU_FILTER_CELL:
-        for (int l = 0; l < n_coord; ++l) {
-          const int b = ld(DM.filter_idata + o + LV(cell, l));
-          if (b >= 0)
-            te.bins[k][te.nb[k]++] = b;
-        }
-        break;
-      case OMCGPU_FILTER_MATERIAL:
-        if (sc.material >= 0) {
-          const int b = ld(DM.filter_idata + o + sc.material);
-          if (b >= 0)
-            te.bins[k][te.nb[k]++] = b;
-        }
-        break;
-      default: // universe
-        for (int l = 0; l < n_coord; ++l) {
-          const int b = ld(DM.filter_idata + o + LV(universe, l));
-          if (b >= 0)
-            te.bins[k][te.nb[k]++] = b;
-        }
-        break;
-      }
-      if (te.nb[k] == 0)
-        empty = true;
-    }
-    if (empty)
+    if (!tally_prepare(ps, i, n_coord, t, E_last, sc, te))
       continue;
     if (te.mesh_pos < 0) {
       tally_emit(te, t, 0, 1.0, sc, values);
       continue;
     }
-    // ---- StructuredMesh::raytrace_mesh, src/mesh.cpp:999-1118 -----------------
-    const int m = te.mesh;
-    const int nd = ld(DM.mesh_ndim + m);
-    const double dx = r1.x - r0.x, dy = r1.y - r0.y, dz = r1.z - r0.z;
-    const double total_distance = sqrt(dx * dx + dy * dy + dz * dz);
-    if (total_distance == 0.0)
+    const double total = track_length(r0, r1);
+    if (total == 0.0)
       continue;
-    int ijk[3] = {0, 0, 0};
-    bool in_mesh = true;
-    for (int k = 0; k < nd; ++k) {
-      ijk[k] = mesh_index(m, comp(r0, k) + TINY_BIT * comp(u, k), k);
-      if (ijk[k] < 1 || ijk[k] > ld(DM.mesh_shape + 3 * m + k))
-        in_mesh = false;
-    }
-    const int s0 = ld(DM.mesh_shape + 3 * m), s1 = ld(DM.mesh_shape + 3 * m + 1);
-#define MESH_BIN() \
-  (nd == 1 ? ijk[0] - 1 \
-           : (nd == 2 ? (ijk[1] - 1) * s0 + ijk[0] - 1 \
-                      : ((ijk[2] - 1) * s1 + (ijk[1] - 1)) * s0 + ijk[0] - 1))
-    if (total_distance < 2 * TINY_BIT) {
-      if (in_mesh)
-        tally_emit(te, t, MESH_BIN(), 1.0, sc, values);
-      continue;
-    }
-    MeshDist dist[3];
-    for (int k = 0; k < 3; ++k) {
-      dist[k].next_index = -1;
-      dist[k].distance = INFTY;
-    }
-    for (int k = 0; k < nd; ++k)
-      dist[k] = mesh_grid_distance(m, ijk[k], k, comp(r0, k), comp(u, k));
-    double traveled = 0.0;
-    for (int guard = 0; guard < 1000000; ++guard) {
-      if (in_mesh) {
-        int k = 0;
-        if (dist[1].distance < dist[k].distance)
-          k = 1;
-        if (dist[2].distance < dist[k].distance)
-          k = 2;
-        const double dk = dist[k].distance;
-        tally_emit(te, t, MESH_BIN(),
-          ((dk < total_distance ? dk : total_distance) - traveled) / total_distance, sc, values);
-        traveled = dk;
-        if (traveled >= total_distance)
-          break;
-        ijk[k] = dist[k].next_index;
-        dist[k] = mesh_grid_distance(m, ijk[k], k, comp(r0, k), comp(u, k));
-        in_mesh = (ijk[k] >= 1) && (ijk[k] <= ld(DM.mesh_shape + 3 * m + k));
-      } else {
-        int k_max = -1;
-        for (int k = 0; k < nd; ++k) {
-          if ((ijk[k] < 1 || ijk[k] > ld(DM.mesh_shape + 3 * m + k)) &&
-              (dist[k].distance > traveled)) {
-            traveled = dist[k].distance;
-            k_max = k;
-          }
-        }
-        if (k_max == -1)
-          traveled += TINY_BIT;
-        if (traveled >= total_distance)
-          break;
-        in_mesh = true;
-        for (int k = 0; k < nd; ++k) {
-          ijk[k] = mesh_index(m, comp(r0, k) + (traveled + TINY_BIT) * comp(u, k), k);
-          if (ijk[k] < 1 || ijk[k] > ld(DM.mesh_shape + 3 * m + k))
-            in_mesh = false;
-        }
-        for (int k = 0; k < nd; ++k)
-          dist[k] = mesh_grid_distance(m, ijk[k], k, comp(r0, k), comp(u, k));
-      }
-    }
-#undef MESH_BIN
+    GenericEmit em;
+    em.te = &te;
+    em.t = t;
+    em.sc = &sc;
+    em.values = values;
+    mesh_march(te.mesh, r0, u, total, 0.0, total, em);
   }
 }
 

@@ -191,8 +191,28 @@ OMC_D void ev_xs(const PState& ps, int64_t i)
   }
 }
 
+// what the scores need from a particle in flight (read after the move, before
+// the next event changes it)
+OMC_D void load_score_ctx(const PState& ps, int64_t i, int n_coord, double distance, ScoreCtx& sc)
+{
+  const int m = ps.material[i];
+  sc.flux = ps.wgt[i] * distance;
+  sc.xs_total = ps.xs_total[i];
+  sc.xs_absorption = ps.xs_absorption[i];
+  sc.xs_fission = ps.xs_fission[i];
+  sc.xs_nu_fission = ps.xs_nu_fission[i];
+  sc.material = m;
+  sc.g = ps.g[i];
+  sc.mg_ba = 0;
+  if (!DM.run_CE && m >= 0) // score_general_mg uses the lowest level's direction
+    sc.mg_ba = mg_ba(m, mg_temperature_index(m, ps.sqrtkT[i]),
+      mg_angle_index(m, get_u(ps, i, n_coord - 1)));
+}
+
 // Particle::event_advance, src/particle.cpp:232-286
-OMC_D int ev_advance(const PState& ps, const GenCtx& gc, int64_t i)
+// score_inline: this lane scores its own track (tail kernel); otherwise the
+// flight is recorded for k_score, which runs on the same work list next.
+OMC_D int ev_advance(const PState& ps, const GenCtx& gc, int64_t i, bool score_inline)
 {
   const int n_coord = ps.n_coord[i];
   const int surface = ps.surface[i];
@@ -236,20 +256,16 @@ OMC_D int ev_advance(const PState& ps, const GenCtx& gc, int64_t i)
   const double wgt = ps.wgt[i];
   const double nu_fission = ps.xs_nu_fission[i];
   if (gc.tallies_active && DM.n_tallies > 0) {
-    ScoreCtx sc;
-    sc.flux = wgt * distance;
-    sc.xs_total = xs_total;
-    sc.xs_absorption = ps.xs_absorption[i];
-    sc.xs_fission = ps.xs_fission[i];
-    sc.xs_nu_fission = nu_fission;
-    sc.material = m;
-    sc.g = g;
-    sc.mg_ba = ba;
-    if (!DM.run_CE && m >= 0) // score_general_mg uses the lowest level's direction
-      sc.mg_ba = mg_ba(m, mg_temperature_index(m, ps.sqrtkT[i]),
-        mg_angle_index(m, get_u(ps, i, n_coord - 1)));
-    const V3 r1 = get_r(ps, i, 0);
-    score_tracklength(ps, i, n_coord, r0, r1, u0, E, sc, gc.tally_values);
+    if (score_inline) {
+      ScoreCtx sc;
+      load_score_ctx(ps, i, n_coord, distance, sc);
+      score_tracklength(ps, i, n_coord, r0, get_r(ps, i, 0), u0, E, sc, gc.tally_values);
+    } else {
+      ps.rlx[i] = r0.x;
+      ps.rly[i] = r0.y;
+      ps.rlz[i] = r0.z;
+      ps.adv_dist[i] = distance;
+    }
   }
   ps.k_trk[i] += wgt * distance * nu_fission;
   ps.b_surface[i] = b.surface;
@@ -421,13 +437,241 @@ OMC_D void body_advance(int64_t tid, const EvArgs& a)
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = a.q_in.idx[tid];
-  const int next = ev_advance(a.ps, a.gc, i);
+  const int next = ev_advance(a.ps, a.gc, i, false);
   if (next == NEXT_COLLISION)
     queue_append(a.q_a, i);
   else if (next == NEXT_SURFACE)
     queue_append(a.q_b, i);
 }
 OMC_KERNEL(k_advance, EvArgs, body_advance)
+
+// -----------------------------------------------------------------------------
+// k_score -- tracklength tally scoring for the flights k_advance just recorded
+// (score_tracklength_tally, src/tallies/tally_scoring.cpp:2416-2541).
+//
+// One lane evaluates the filters of one flight.  The mesh ray trace, whose
+// length differs wildly from flight to flight, is NOT done lane-per-flight:
+// every flight is cut into parts of about SCORE_PART mesh cells, a warp prefix
+// sum turns the 32 flights of a warp into one list of parts, and the lanes
+// trace the parts round-robin from a shared-memory copy of the flight data --
+// so a warp's work is the sum of its flights' cells, not 32 x the longest one.
+// -----------------------------------------------------------------------------
+constexpr int SCORE_PART = 8;   // mesh cells per part
+constexpr int SCORE_NVAL = OMCGPU_MAX_SCORES;
+
+struct PartEmit { // simple tally: one bin per non-mesh filter -> base index
+  double* results;
+  int64_t base;
+  int mesh_stride, ns;
+  double val[SCORE_NVAL];
+  OMC_D void operator()(int bin, double w) const
+  {
+    double* r = results + (base + (int64_t)bin * mesh_stride) * ns;
+    for (int s = 0; s < ns; ++s)
+      if (val[s] != 0.0)
+        atomic_add_f64(r + s, val[s] * w);
+  }
+};
+
+// part boundaries: identical expression for the end of part c and the start of c+1
+OMC_HD double part_bound(int c, int nc, double total)
+{
+  return c >= nc ? total : (c * total) / nc;
+}
+
+// lane-side preparation of tally t for flight i; returns the number of parts
+// (0: nothing to trace cooperatively)
+OMC_D int score_prepare(const PState& ps, int64_t i, int t, const ScoreCtx& sc, int n_coord,
+  V3 r0, V3 r1, V3 u, double E, double* values, double& total, int64_t& base, double* val)
+{
+  TallyEval te;
+  if (!tally_prepare(ps, i, n_coord, t, E, sc, te))
+    return 0;
+  if (te.mesh_pos < 0) {
+    tally_emit(te, t, 0, 1.0, sc, values);
+    return 0;
+  }
+  total = track_length(r0, r1);
+  if (total == 0.0)
+    return 0;
+  bool simple = true;
+  base = 0;
+  for (int k = 0; k < te.nf; ++k) {
+    if (k == te.mesh_pos)
+      continue;
+    if (te.nb[k] != 1)
+      simple = false;
+    base += (int64_t)te.bins[k][0] * te.stride[k];
+  }
+  if (!simple) { // several matches per filter: this lane traces the whole flight
+    GenericEmit em;
+    em.te = &te;
+    em.t = t;
+    em.sc = &sc;
+    em.values = values;
+    mesh_march(te.mesh, r0, u, total, 0.0, total, em);
+    return 0;
+  }
+  const int ns = ld(DM.tally_n_scores + t);
+  bool any = false;
+  for (int s = 0; s < SCORE_NVAL; ++s) {
+    val[s] = 0.0;
+    if (s < ns) {
+      bool skip;
+      const double v = score_value(ld(DM.tally_scores + OMCGPU_MAX_SCORES * t + s), sc, skip);
+      if (!skip)
+        val[s] = v;
+      any = any || val[s] != 0.0;
+    }
+  }
+  if (!any)
+    return 0;
+  if (total < 2 * TINY_BIT)
+    return 1;
+  const int cells = mesh_cells_visited(te.mesh, r0, r1, u);
+  const int nc = (cells + SCORE_PART - 1) / SCORE_PART;
+  return nc < 1 ? 1 : nc;
+}
+
+// position of the mesh filter and its stride are properties of the tally
+OMC_HD void tally_mesh_info(int t, int& mesh, int& mesh_stride)
+{
+  mesh = -1;
+  mesh_stride = 0;
+  const int nf = ld(DM.tally_n_filters + t);
+  for (int k = 0; k < nf; ++k) {
+    const int f = ld(DM.tally_filters + OMCGPU_MAX_FILTERS * t + k);
+    if (ld(DM.filter_type + f) == OMCGPU_FILTER_MESH) {
+      mesh = ld(DM.filter_mesh + f);
+      mesh_stride = ld(DM.tally_strides + OMCGPU_MAX_FILTERS * t + k);
+    }
+  }
+}
+
+#if OMC_CUDA
+__global__ void __launch_bounds__(BLOCK) k_score(int64_t n_ub, EvArgs a)
+{
+  constexpr int WARPS = BLOCK / 32;
+  __shared__ double s_d[WARPS][7 + SCORE_NVAL][32]; // r0, u, total, val[]
+  __shared__ int64_t s_base[WARPS][32];
+  __shared__ int s_incl[WARPS][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const PState& ps = a.ps;
+  const int64_t n = *a.q_in.count;
+  const bool active = tid < n;
+  int64_t i = 0;
+  int n_coord = 0;
+  V3 r0 = v3(0, 0, 0), r1 = r0, u = r0;
+  double E = 0.0;
+  ScoreCtx sc;
+  if (active) {
+    i = a.q_in.idx[tid];
+    n_coord = ps.n_coord[i];
+    r0 = v3(ps.rlx[i], ps.rly[i], ps.rlz[i]);
+    r1 = get_r(ps, i, 0);
+    u = get_u(ps, i, 0);
+    E = ps.E[i];
+    load_score_ctx(ps, i, n_coord, ps.adv_dist[i], sc);
+  }
+  for (int t = 0; t < DM.n_tallies; ++t) {
+    double total = 0.0, val[SCORE_NVAL];
+    int64_t base = 0;
+    int nc = 0;
+    if (active)
+      nc = score_prepare(ps, i, t, sc, n_coord, r0, r1, u, E, a.gc.tally_values, total, base, val);
+    int mesh, mesh_stride;
+    tally_mesh_info(t, mesh, mesh_stride);
+    if (mesh < 0)
+      continue; // warp-uniform: a property of the tally
+    int incl = nc; // inclusive warp scan of the part counts
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d)
+        incl += v;
+    }
+    const int n_parts = __shfl_sync(0xffffffffu, incl, 31);
+    if (n_parts == 0)
+      continue;
+    __syncwarp();
+    s_incl[warp][lane] = incl;
+    if (nc > 0) {
+      s_d[warp][0][lane] = r0.x;
+      s_d[warp][1][lane] = r0.y;
+      s_d[warp][2][lane] = r0.z;
+      s_d[warp][3][lane] = u.x;
+      s_d[warp][4][lane] = u.y;
+      s_d[warp][5][lane] = u.z;
+      s_d[warp][6][lane] = total;
+      for (int s = 0; s < SCORE_NVAL; ++s)
+        s_d[warp][7 + s][lane] = val[s];
+      s_base[warp][lane] = base;
+    }
+    __syncwarp();
+    PartEmit em;
+    em.results = a.gc.tally_values + ld(DM.tally_result_ofs + t);
+    em.mesh_stride = mesh_stride;
+    em.ns = ld(DM.tally_n_scores + t);
+    for (int item = lane; item < n_parts; item += 32) {
+      int o = 0; // owner: first lane whose inclusive count exceeds item
+      for (int step = 16; step > 0; step >>= 1)
+        if (s_incl[warp][o + step - 1] <= item)
+          o += step;
+      const int c = item - (o > 0 ? s_incl[warp][o - 1] : 0);
+      const int onc = s_incl[warp][o] - (o > 0 ? s_incl[warp][o - 1] : 0);
+      const V3 pr0 = v3(s_d[warp][0][o], s_d[warp][1][o], s_d[warp][2][o]);
+      const V3 pu = v3(s_d[warp][3][o], s_d[warp][4][o], s_d[warp][5][o]);
+      const double ptotal = s_d[warp][6][o];
+      for (int s = 0; s < SCORE_NVAL; ++s)
+        em.val[s] = s_d[warp][7 + s][o];
+      em.base = s_base[warp][o];
+      mesh_march(mesh, pr0, pu, ptotal, part_bound(c, onc, ptotal), part_bound(c + 1, onc, ptotal), em);
+    }
+  }
+}
+#define LAUNCH_SCORE(n_ub, stream, args) \
+  do { \
+    if ((n_ub) > 0) { \
+      k_score<<<(unsigned)(((n_ub) + BLOCK - 1) / BLOCK), BLOCK, 0, stream>>>((int64_t)(n_ub), args); \
+      ++g_launches; \
+    } \
+  } while (0)
+#else
+// host compile (tests only): same preparation, same parts, traced one after another
+void k_score(int64_t n_ub, EvArgs a)
+{
+  const PState& ps = a.ps;
+  const int64_t n = *a.q_in.count;
+  for (int64_t tid = 0; tid < n_ub && tid < n; ++tid) {
+    const int64_t i = a.q_in.idx[tid];
+    const int n_coord = ps.n_coord[i];
+    const V3 r0 = v3(ps.rlx[i], ps.rly[i], ps.rlz[i]);
+    const V3 r1 = get_r(ps, i, 0);
+    const V3 u = get_u(ps, i, 0);
+    ScoreCtx sc;
+    load_score_ctx(ps, i, n_coord, ps.adv_dist[i], sc);
+    for (int t = 0; t < DM.n_tallies; ++t) {
+      PartEmit em;
+      double total = 0.0;
+      const int nc = score_prepare(ps, i, t, sc, n_coord, r0, r1, u, ps.E[i], a.gc.tally_values,
+        total, em.base, em.val);
+      int mesh;
+      tally_mesh_info(t, mesh, em.mesh_stride);
+      em.results = a.gc.tally_values + DM.tally_result_ofs[t];
+      em.ns = DM.tally_n_scores[t];
+      for (int c = 0; c < nc; ++c)
+        mesh_march(mesh, r0, u, total, part_bound(c, nc, total), part_bound(c + 1, nc, total), em);
+    }
+  }
+}
+#define LAUNCH_SCORE(n_ub, stream, args) \
+  do { \
+    if ((n_ub) > 0) { \
+      k_score((int64_t)(n_ub), args); \
+      ++g_launches; \
+    } \
+  } while (0)
+#endif
 
 OMC_D void body_surface(int64_t tid, const EvArgs& a)
 {
@@ -463,7 +707,7 @@ OMC_D void body_tail(int64_t tid, const EvArgs& a)
   while (alive) {
     ev_xs(a.ps, i);
     ++n_xs;
-    const int next = ev_advance(a.ps, a.gc, i);
+    const int next = ev_advance(a.ps, a.gc, i, true);
     if (next == NEXT_COLLISION) {
       alive = ev_collide(a.ps, a.gc, a.fb, i);
       ++n_coll;
@@ -1116,6 +1360,8 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
     a.q_a = G.q[2];
     a.q_b = G.q[3];
     OMC_LAUNCH(k_advance, n_alive, G.stream, a);
+    if (in->tallies_active && G.hm.n_tallies > 0)
+      LAUNCH_SCORE(n_alive, G.stream, a);
     a.q_in = G.q[3];
     a.q_a = G.q[nxt];
     OMC_LAUNCH(k_surface, n_alive, G.stream, a);
@@ -1261,6 +1507,7 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   A(xs_total, cap); A(xs_absorption, cap); A(xs_fission, cap); A(xs_nu_fission, cap);
   A(b_surface, cap); A(b_level_trans, cap);
   A(k_abs, cap); A(k_col, cap); A(k_trk, cap); A(k_leak, cap);
+  A(rlx, cap); A(rly, cap); A(rlz, cap); A(adv_dist, cap);
 #undef A
   rc = rc ? rc : alloc_bank(G.src, cap);
   rc = rc ? rc : alloc_bank(G.fis, G.fis_cap);
