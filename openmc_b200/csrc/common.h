@@ -97,9 +97,23 @@ struct PState {
   double *xs_total, *xs_absorption, *xs_fission, *xs_nu_fission;
   int32_t *b_surface, *b_level_trans;
   double *k_abs, *k_col, *k_trk, *k_leak;
-  // the last flight, kept for the tally-scoring kernel: start point (r_last of
-  // include/openmc/particle_data.h) and flight distance
-  double *rlx, *rly, *rlz, *adv_dist;
+};
+
+// Flight records: what tracklength scoring needs from one flight, written by
+// k_advance at the flight's position in the work list (coalesced) and by the
+// tail kernel through an atomic append; consumed by k_score.  Self-contained,
+// so scoring does not depend on particle state that later events overwrite.
+struct Flights {
+  int64_t cap;
+  double *x, *y, *z;       // start point (r_last of include/openmc/particle_data.h)
+  double *ux, *uy, *uz;    // direction at level 0
+  double *total;           // |r1 - r0| (src/mesh.cpp:1008-1010)
+  double *flux;            // wgt * flight distance
+  double *E;
+  double *xs_t, *xs_a, *xs_f, *xs_nf;
+  int32_t *material, *g, *mg_ba;
+  int32_t *pidx;           // particle (for cell/universe filters), -1 when logged by the tail
+  int32_t *count;          // records appended by the tail kernel
 };
 
 // Source / fission banks as SoA columns (the 104-byte AoS SourceSite is only the
@@ -128,6 +142,8 @@ struct GenCtx {
   uint64_t stride;
   double keff;
   int32_t tallies_active;
+  int32_t score_part; // mesh cells per part handed to one lane by k_score
+  int32_t tally_needs_cells; // some tally has a cell/universe filter (needs live particle state)
   // device counters
   int32_t* n_fission;  // fission bank fill
   int32_t* n_lost;

@@ -1318,7 +1318,8 @@ OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no
 OMC_D void atomic_add_f64(double* addr, double val)
 {
 #if OMC_CUDA && defined(__CUDA_ARCH__)
-  atomicAdd(addr, val); // result unused -> RED.E.ADD.F64
+  // tally arrays are global memory: skip the generic-address dispatch of atomicAdd
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(val) : "memory");
 #else
   *addr += val;
 #endif
@@ -1340,7 +1341,7 @@ OMC_D void tally_add(double* addr, double val)
     rem &= rem - 1;
   }
   if (lane == leader)
-    atomicAdd(addr, sum);
+    atomic_add_f64(addr, sum);
 #else
   *addr += val;
 #endif
@@ -1396,27 +1397,30 @@ struct MeshDist {
   double distance;
 };
 
-OMC_HD MeshDist mesh_grid_distance(int m, int idx, int k, double r0k, double uk)
-{ // RegularMesh::distance_to_grid_boundary, src/mesh.cpp:1352-1369
+// RegularMesh::distance_to_grid_boundary, src/mesh.cpp:1352-1369, for one axis
+// held in registers.  Written without branches (the three axes and the two
+// directions would otherwise split a warp six ways): the edge ahead is index
+// idx (u > 0) or idx - 1 (u <= 0) and the quotient is discarded when there is
+// no edge ahead.
+struct MeshAxis {
+  double r0, u, ll, w;
+  int idx, shape;
+};
+OMC_HD MeshDist mesh_axis_distance(const MeshAxis& a)
+{
+  const bool pos = a.u > 0;
+  const int edge = pos ? a.idx : a.idx - 1;
+  const bool ok = !(fabs(a.u) < FP_PRECISION) && (pos ? a.idx <= a.shape : a.idx >= 1);
+  const double q = ((a.ll + edge * a.w) - a.r0) / a.u;
   MeshDist d;
-  d.next_index = idx;
-  d.distance = INFTY;
-  if (fabs(uk) < FP_PRECISION)
-    return d;
-  const double ll = ld(DM.mesh_lower_left + 3 * m + k), w = ld(DM.mesh_width + 3 * m + k);
-  if (uk > 0 && idx <= ld(DM.mesh_shape + 3 * m + k)) {
-    d.next_index = idx + 1;
-    d.distance = ((ll + idx * w) - r0k) / uk;
-  } else if (!(uk > 0) && idx >= 1) {
-    d.next_index = idx - 1;
-    d.distance = ((ll + (idx - 1) * w) - r0k) / uk;
-  }
+  d.distance = ok ? q : INFTY;
+  d.next_index = ok ? (pos ? a.idx + 1 : a.idx - 1) : a.idx;
   return d;
 }
 
-OMC_HD int mesh_index(int m, double r, int k)
+OMC_HD int mesh_index(double r, double ll, double w)
 {
-  return (int)ceil((r - ld(DM.mesh_lower_left + 3 * m + k)) / ld(DM.mesh_width + 3 * m + k));
+  return (int)ceil((r - ll) / w);
 }
 
 // StructuredMesh::raytrace_mesh, src/mesh.cpp:999-1118, over the part [t0, t1]
@@ -1431,30 +1435,43 @@ template<class Emit>
 OMC_D void mesh_march(int m, V3 r0, V3 u, double total, double t0, double t1, Emit& emit)
 {
   const int nd = ld(DM.mesh_ndim + m);
-  const int s0 = ld(DM.mesh_shape + 3 * m), s1 = ld(DM.mesh_shape + 3 * m + 1),
-            s2 = ld(DM.mesh_shape + 3 * m + 2);
+  MeshAxis a0, a1, a2;
+  a0.r0 = r0.x; a0.u = u.x;
+  a1.r0 = r0.y; a1.u = u.y;
+  a2.r0 = r0.z; a2.u = u.z;
+  a0.ll = ld(DM.mesh_lower_left + 3 * m); a0.w = ld(DM.mesh_width + 3 * m);
+  a0.shape = ld(DM.mesh_shape + 3 * m);
+  // a missing axis is one cell that is never left
+  a1.ll = a2.ll = 0.0; a1.w = a2.w = 1.0; a1.shape = a2.shape = 1;
+  if (nd > 1) {
+    a1.ll = ld(DM.mesh_lower_left + 3 * m + 1); a1.w = ld(DM.mesh_width + 3 * m + 1);
+    a1.shape = ld(DM.mesh_shape + 3 * m + 1);
+  }
+  if (nd > 2) {
+    a2.ll = ld(DM.mesh_lower_left + 3 * m + 2); a2.w = ld(DM.mesh_width + 3 * m + 2);
+    a2.shape = ld(DM.mesh_shape + 3 * m + 2);
+  }
   // the first part starts TINY_BIT inside (mesh.cpp:1021); a later part starts at
   // its cut, where the cell is decided by position alone
   const double ts = (t0 == 0.0) ? TINY_BIT : t0;
-  int i0 = mesh_index(m, r0.x + ts * u.x, 0);
-  int i1 = nd > 1 ? mesh_index(m, r0.y + ts * u.y, 1) : 1;
-  int i2 = nd > 2 ? mesh_index(m, r0.z + ts * u.z, 2) : 1;
-  const int n1 = nd > 1 ? s1 : 1, n2 = nd > 2 ? s2 : 1;
-#define MESH_IN() (i0 >= 1 && i0 <= s0 && i1 >= 1 && i1 <= n1 && i2 >= 1 && i2 <= n2)
-#define MESH_BIN() (((i2 - 1) * n1 + (i1 - 1)) * s0 + i0 - 1)
-  bool in_mesh = MESH_IN();
+  a0.idx = mesh_index(a0.r0 + ts * a0.u, a0.ll, a0.w);
+  a1.idx = nd > 1 ? mesh_index(a1.r0 + ts * a1.u, a1.ll, a1.w) : 1;
+  a2.idx = nd > 2 ? mesh_index(a2.r0 + ts * a2.u, a2.ll, a2.w) : 1;
+#define MESH_OUT(a) ((a).idx < 1 || (a).idx > (a).shape)
+#define MESH_BIN() (((a2.idx - 1) * a1.shape + (a1.idx - 1)) * a0.shape + a0.idx - 1)
+  bool in_mesh = !(MESH_OUT(a0) || MESH_OUT(a1) || MESH_OUT(a2));
   if (total < 2 * TINY_BIT) {
     if (in_mesh)
       emit(MESH_BIN(), 1.0);
     return;
   }
-  MeshDist d0 = mesh_grid_distance(m, i0, 0, r0.x, u.x), d1, d2;
+  MeshDist d0 = mesh_axis_distance(a0), d1, d2;
   d1.next_index = d2.next_index = -1;
   d1.distance = d2.distance = INFTY;
   if (nd > 1)
-    d1 = mesh_grid_distance(m, i1, 1, r0.y, u.y);
+    d1 = mesh_axis_distance(a1);
   if (nd > 2)
-    d2 = mesh_grid_distance(m, i2, 2, r0.z, u.z);
+    d2 = mesh_axis_distance(a2);
   double traveled = t0;
   for (int guard = 0; guard < 1000000; ++guard) {
     if (in_mesh) {
@@ -1472,28 +1489,34 @@ OMC_D void mesh_march(int m, V3 r0, V3 u, double total, double t0, double t1, Em
       traveled = dk;
       if (traveled >= t1)
         break;
+      // step across the nearest edge: select the axis, one distance, select back
+      MeshAxis ak = k == 0 ? a0 : (k == 1 ? a1 : a2);
+      ak.idx = k == 0 ? d0.next_index : (k == 1 ? d1.next_index : d2.next_index);
+      const MeshDist dn = mesh_axis_distance(ak);
       if (k == 0) {
-        i0 = d0.next_index;
-        d0 = mesh_grid_distance(m, i0, 0, r0.x, u.x);
-      } else if (k == 1) {
-        i1 = d1.next_index;
-        d1 = mesh_grid_distance(m, i1, 1, r0.y, u.y);
-      } else {
-        i2 = d2.next_index;
-        d2 = mesh_grid_distance(m, i2, 2, r0.z, u.z);
+        a0.idx = ak.idx;
+        d0 = dn;
       }
-      in_mesh = MESH_IN();
+      if (k == 1) {
+        a1.idx = ak.idx;
+        d1 = dn;
+      }
+      if (k == 2) {
+        a2.idx = ak.idx;
+        d2 = dn;
+      }
+      in_mesh = !MESH_OUT(ak);
     } else {
       int k_max = -1;
-      if ((i0 < 1 || i0 > s0) && d0.distance > traveled) {
+      if (MESH_OUT(a0) && d0.distance > traveled) {
         traveled = d0.distance;
         k_max = 0;
       }
-      if (nd > 1 && (i1 < 1 || i1 > s1) && d1.distance > traveled) {
+      if (nd > 1 && MESH_OUT(a1) && d1.distance > traveled) {
         traveled = d1.distance;
         k_max = 1;
       }
-      if (nd > 2 && (i2 < 1 || i2 > s2) && d2.distance > traveled) {
+      if (nd > 2 && MESH_OUT(a2) && d2.distance > traveled) {
         traveled = d2.distance;
         k_max = 2;
       }
@@ -1502,20 +1525,20 @@ OMC_D void mesh_march(int m, V3 r0, V3 u, double total, double t0, double t1, Em
       if (traveled >= t1)
         break;
       const double tt = traveled + TINY_BIT;
-      i0 = mesh_index(m, r0.x + tt * u.x, 0);
+      a0.idx = mesh_index(a0.r0 + tt * a0.u, a0.ll, a0.w);
       if (nd > 1)
-        i1 = mesh_index(m, r0.y + tt * u.y, 1);
+        a1.idx = mesh_index(a1.r0 + tt * a1.u, a1.ll, a1.w);
       if (nd > 2)
-        i2 = mesh_index(m, r0.z + tt * u.z, 2);
-      in_mesh = MESH_IN();
-      d0 = mesh_grid_distance(m, i0, 0, r0.x, u.x);
+        a2.idx = mesh_index(a2.r0 + tt * a2.u, a2.ll, a2.w);
+      in_mesh = !(MESH_OUT(a0) || MESH_OUT(a1) || MESH_OUT(a2));
+      d0 = mesh_axis_distance(a0);
       if (nd > 1)
-        d1 = mesh_grid_distance(m, i1, 1, r0.y, u.y);
+        d1 = mesh_axis_distance(a1);
       if (nd > 2)
-        d2 = mesh_grid_distance(m, i2, 2, r0.z, u.z);
+        d2 = mesh_axis_distance(a2);
     }
   }
-#undef MESH_IN
+#undef MESH_OUT
 #undef MESH_BIN
 }
 
@@ -1527,8 +1550,9 @@ OMC_HD int mesh_cells_visited(int m, V3 r0, V3 r1, V3 u)
   int n = 1;
   for (int k = 0; k < nd; ++k) {
     const int sk = ld(DM.mesh_shape + 3 * m + k);
-    int a = mesh_index(m, comp(r0, k) + TINY_BIT * comp(u, k), k);
-    int b = mesh_index(m, comp(r1, k), k);
+    const double ll = ld(DM.mesh_lower_left + 3 * m + k), w = ld(DM.mesh_width + 3 * m + k);
+    int a = mesh_index(comp(r0, k) + TINY_BIT * comp(u, k), ll, w);
+    int b = mesh_index(comp(r1, k), ll, w);
     a = a < 0 ? 0 : (a > sk + 1 ? sk + 1 : a);
     b = b < 0 ? 0 : (b > sk + 1 ? sk + 1 : b);
     n += a > b ? a - b : b - a;

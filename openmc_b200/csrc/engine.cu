@@ -96,6 +96,8 @@ struct EvArgs {
   Bank src;  // source bank (k_init)
   Bank fb;   // fission bank (k_collide)
   Queue q_in, q_a, q_b; // input list, and up to two output lists
+  Flights fl;           // flight records for k_score
+  const int32_t* n_flights; // how many records k_score reads (work-list or tail-log count)
 };
 
 enum { NEXT_DEAD = -1, NEXT_COLLISION = 0, NEXT_SURFACE = 1 };
@@ -209,10 +211,53 @@ OMC_D void load_score_ctx(const PState& ps, int64_t i, int n_coord, double dista
       mg_angle_index(m, get_u(ps, i, n_coord - 1)));
 }
 
+// flight record for k_score
+OMC_D void record_flight(const Flights& fl, int64_t slot, const PState& ps, int64_t i, int n_coord,
+  V3 r0, V3 u0, double E, double distance, int32_t pidx)
+{
+  ScoreCtx sc;
+  load_score_ctx(ps, i, n_coord, distance, sc);
+  fl.x[slot] = r0.x;
+  fl.y[slot] = r0.y;
+  fl.z[slot] = r0.z;
+  fl.ux[slot] = u0.x;
+  fl.uy[slot] = u0.y;
+  fl.uz[slot] = u0.z;
+  fl.total[slot] = track_length(r0, get_r(ps, i, 0));
+  fl.flux[slot] = sc.flux;
+  fl.E[slot] = E;
+  fl.xs_t[slot] = sc.xs_total;
+  fl.xs_a[slot] = sc.xs_absorption;
+  fl.xs_f[slot] = sc.xs_fission;
+  fl.xs_nf[slot] = sc.xs_nu_fission;
+  fl.material[slot] = sc.material;
+  fl.g[slot] = sc.g;
+  fl.mg_ba[slot] = sc.mg_ba;
+  fl.pidx[slot] = pidx;
+}
+
+// reserve one slot of the tail's flight log (warp-aggregated); -1 when full
+OMC_D int64_t flight_log_reserve(const Flights& fl)
+{
+#if OMC_CUDA
+  cg::coalesced_group g = cg::coalesced_threads();
+  int32_t base = 0;
+  if (g.thread_rank() == 0)
+    base = atomicAdd(fl.count, (int32_t)g.size());
+  base = g.shfl(base, 0);
+  const int64_t slot = (int64_t)base + g.thread_rank();
+#else
+  const int64_t slot = (*fl.count)++;
+#endif
+  return slot < fl.cap ? slot : -1;
+}
+
 // Particle::event_advance, src/particle.cpp:232-286
-// score_inline: this lane scores its own track (tail kernel); otherwise the
-// flight is recorded for k_score, which runs on the same work list next.
-OMC_D int ev_advance(const PState& ps, const GenCtx& gc, int64_t i, bool score_inline)
+// Tally scoring: slot >= 0 -- the flight is recorded at fl[slot] for k_score
+// (sweeps); slot == SLOT_LOG -- appended to the tail's flight log, scored by this
+// lane only if the log is full or a tally needs the particle's cells.
+constexpr int64_t SLOT_LOG = -1;
+OMC_D int ev_advance(const PState& ps, const GenCtx& gc, const Flights& fl, int64_t i, int64_t slot)
 {
   const int n_coord = ps.n_coord[i];
   const int surface = ps.surface[i];
@@ -256,15 +301,18 @@ OMC_D int ev_advance(const PState& ps, const GenCtx& gc, int64_t i, bool score_i
   const double wgt = ps.wgt[i];
   const double nu_fission = ps.xs_nu_fission[i];
   if (gc.tallies_active && DM.n_tallies > 0) {
-    if (score_inline) {
+    int32_t pidx = (int32_t)i;
+    if (slot == SLOT_LOG) {
+      pidx = -1;
+      if (!gc.tally_needs_cells)
+        slot = flight_log_reserve(fl);
+    }
+    if (slot >= 0) {
+      record_flight(fl, slot, ps, i, n_coord, r0, u0, E, distance, pidx);
+    } else {
       ScoreCtx sc;
       load_score_ctx(ps, i, n_coord, distance, sc);
       score_tracklength(ps, i, n_coord, r0, get_r(ps, i, 0), u0, E, sc, gc.tally_values);
-    } else {
-      ps.rlx[i] = r0.x;
-      ps.rly[i] = r0.y;
-      ps.rlz[i] = r0.z;
-      ps.adv_dist[i] = distance;
     }
   }
   ps.k_trk[i] += wgt * distance * nu_fission;
@@ -437,7 +485,7 @@ OMC_D void body_advance(int64_t tid, const EvArgs& a)
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = a.q_in.idx[tid];
-  const int next = ev_advance(a.ps, a.gc, i, false);
+  const int next = ev_advance(a.ps, a.gc, a.fl, i, tid);
   if (next == NEXT_COLLISION)
     queue_append(a.q_a, i);
   else if (next == NEXT_SURFACE)
@@ -456,7 +504,6 @@ OMC_KERNEL(k_advance, EvArgs, body_advance)
 // trace the parts round-robin from a shared-memory copy of the flight data --
 // so a warp's work is the sum of its flights' cells, not 32 x the longest one.
 // -----------------------------------------------------------------------------
-constexpr int SCORE_PART = 8;   // mesh cells per part
 constexpr int SCORE_NVAL = OMCGPU_MAX_SCORES;
 
 struct PartEmit { // simple tally: one bin per non-mesh filter -> base index
@@ -467,7 +514,8 @@ struct PartEmit { // simple tally: one bin per non-mesh filter -> base index
   OMC_D void operator()(int bin, double w) const
   {
     double* r = results + (base + (int64_t)bin * mesh_stride) * ns;
-    for (int s = 0; s < ns; ++s)
+#pragma unroll
+    for (int s = 0; s < SCORE_NVAL; ++s) // val[s] == 0 beyond ns; compile-time indices keep val in registers
       if (val[s] != 0.0)
         atomic_add_f64(r + s, val[s] * w);
   }
@@ -479,20 +527,65 @@ OMC_HD double part_bound(int c, int nc, double total)
   return c >= nc ? total : (c * total) / nc;
 }
 
-// lane-side preparation of tally t for flight i; returns the number of parts
-// (0: nothing to trace cooperatively)
-OMC_D int score_prepare(const PState& ps, int64_t i, int t, const ScoreCtx& sc, int n_coord,
-  V3 r0, V3 r1, V3 u, double E, double* values, double& total, int64_t& base, double* val)
+// rare path kept out of line so that it does not cost the hot path registers
+#if OMC_CUDA
+__device__ __noinline__
+#else
+inline
+#endif
+void score_mesh_generic(const TallyEval& te, int t, const ScoreCtx& sc, double* values, V3 r0, V3 u,
+  double total)
+{
+  GenericEmit em;
+  em.te = &te;
+  em.t = t;
+  em.sc = &sc;
+  em.values = values;
+  mesh_march(te.mesh, r0, u, total, 0.0, total, em);
+}
+
+// one flight record in registers
+struct Flight {
+  V3 r0, u;
+  double total, E;
+  ScoreCtx sc;
+  int32_t pidx;
+};
+OMC_D Flight load_flight(const Flights& fl, int64_t j)
+{
+  Flight f;
+  f.r0 = v3(fl.x[j], fl.y[j], fl.z[j]);
+  f.u = v3(fl.ux[j], fl.uy[j], fl.uz[j]);
+  f.total = fl.total[j];
+  f.E = fl.E[j];
+  f.sc.flux = fl.flux[j];
+  f.sc.xs_total = fl.xs_t[j];
+  f.sc.xs_absorption = fl.xs_a[j];
+  f.sc.xs_fission = fl.xs_f[j];
+  f.sc.xs_nu_fission = fl.xs_nf[j];
+  f.sc.material = fl.material[j];
+  f.sc.g = fl.g[j];
+  f.sc.mg_ba = fl.mg_ba[j];
+  f.pidx = fl.pidx[j];
+  return f;
+}
+
+// lane-side preparation of tally t for one flight: evaluates the filters,
+// scores tallies without a mesh filter at once, and returns the number of parts
+// the mesh ray trace is cut into (0: nothing to trace cooperatively)
+OMC_D int score_prepare(const PState& ps, const Flight& f, int t, double* values, int score_part,
+  int64_t& base, double* val)
 {
   TallyEval te;
-  if (!tally_prepare(ps, i, n_coord, t, E, sc, te))
+  const int64_t i = f.pidx; // cell / universe filters read the particle's coordinate levels
+  const int n_coord = f.pidx >= 0 ? ps.n_coord[i] : 0;
+  if (!tally_prepare(ps, i, n_coord, t, f.E, f.sc, te))
     return 0;
   if (te.mesh_pos < 0) {
-    tally_emit(te, t, 0, 1.0, sc, values);
+    tally_emit(te, t, 0, 1.0, f.sc, values);
     return 0;
   }
-  total = track_length(r0, r1);
-  if (total == 0.0)
+  if (f.total == 0.0)
     return 0;
   bool simple = true;
   base = 0;
@@ -504,21 +597,17 @@ OMC_D int score_prepare(const PState& ps, int64_t i, int t, const ScoreCtx& sc, 
     base += (int64_t)te.bins[k][0] * te.stride[k];
   }
   if (!simple) { // several matches per filter: this lane traces the whole flight
-    GenericEmit em;
-    em.te = &te;
-    em.t = t;
-    em.sc = &sc;
-    em.values = values;
-    mesh_march(te.mesh, r0, u, total, 0.0, total, em);
+    score_mesh_generic(te, t, f.sc, values, f.r0, f.u, f.total);
     return 0;
   }
   const int ns = ld(DM.tally_n_scores + t);
   bool any = false;
+#pragma unroll
   for (int s = 0; s < SCORE_NVAL; ++s) {
     val[s] = 0.0;
     if (s < ns) {
       bool skip;
-      const double v = score_value(ld(DM.tally_scores + OMCGPU_MAX_SCORES * t + s), sc, skip);
+      const double v = score_value(ld(DM.tally_scores + OMCGPU_MAX_SCORES * t + s), f.sc, skip);
       if (!skip)
         val[s] = v;
       any = any || val[s] != 0.0;
@@ -526,10 +615,11 @@ OMC_D int score_prepare(const PState& ps, int64_t i, int t, const ScoreCtx& sc, 
   }
   if (!any)
     return 0;
-  if (total < 2 * TINY_BIT)
+  if (f.total < 2 * TINY_BIT)
     return 1;
-  const int cells = mesh_cells_visited(te.mesh, r0, r1, u);
-  const int nc = (cells + SCORE_PART - 1) / SCORE_PART;
+  const V3 r1 = v3(f.r0.x + f.total * f.u.x, f.r0.y + f.total * f.u.y, f.r0.z + f.total * f.u.z);
+  const int cells = mesh_cells_visited(te.mesh, f.r0, r1, f.u);
+  const int nc = (cells + score_part - 1) / score_part;
   return nc < 1 ? 1 : nc;
 }
 
@@ -549,7 +639,37 @@ OMC_HD void tally_mesh_info(int t, int& mesh, int& mesh_stride)
 }
 
 #if OMC_CUDA
-__global__ void __launch_bounds__(BLOCK) k_score(int64_t n_ub, EvArgs a)
+// Everything one lane does for its own flight and tally t, out of line: nothing
+// of the flight stays in registers while the lanes trace parts afterwards.
+// sd points at this lane's column of the warp's staging area (stride 32 doubles).
+__constant__ PState c_ps; // the particle columns never move after omcgpu_init
+
+__constant__ Flights c_fl;
+
+__device__ __noinline__ int score_lane(int64_t j, int t, double* values, int score_part, double* sd,
+  int64_t* sbase)
+{
+  const Flight f = load_flight(c_fl, j);
+  double val[SCORE_NVAL];
+  int64_t base = 0;
+  const int nc = score_prepare(c_ps, f, t, values, score_part, base, val);
+  if (nc > 0) {
+    sd[0 * 32] = f.r0.x;
+    sd[1 * 32] = f.r0.y;
+    sd[2 * 32] = f.r0.z;
+    sd[3 * 32] = f.u.x;
+    sd[4 * 32] = f.u.y;
+    sd[5 * 32] = f.u.z;
+    sd[6 * 32] = f.total;
+#pragma unroll
+    for (int s = 0; s < SCORE_NVAL; ++s)
+      sd[(7 + s) * 32] = val[s];
+    *sbase = base;
+  }
+  return nc;
+}
+
+__global__ void __launch_bounds__(BLOCK, 2) k_score(int64_t n_ub, EvArgs a)
 {
   constexpr int WARPS = BLOCK / 32;
   __shared__ double s_d[WARPS][7 + SCORE_NVAL][32]; // r0, u, total, val[]
@@ -557,29 +677,13 @@ __global__ void __launch_bounds__(BLOCK) k_score(int64_t n_ub, EvArgs a)
   __shared__ int s_incl[WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const PState& ps = a.ps;
-  const int64_t n = *a.q_in.count;
+  const int64_t n = *a.n_flights < a.fl.cap ? *a.n_flights : a.fl.cap;
   const bool active = tid < n;
-  int64_t i = 0;
-  int n_coord = 0;
-  V3 r0 = v3(0, 0, 0), r1 = r0, u = r0;
-  double E = 0.0;
-  ScoreCtx sc;
-  if (active) {
-    i = a.q_in.idx[tid];
-    n_coord = ps.n_coord[i];
-    r0 = v3(ps.rlx[i], ps.rly[i], ps.rlz[i]);
-    r1 = get_r(ps, i, 0);
-    u = get_u(ps, i, 0);
-    E = ps.E[i];
-    load_score_ctx(ps, i, n_coord, ps.adv_dist[i], sc);
-  }
   for (int t = 0; t < DM.n_tallies; ++t) {
-    double total = 0.0, val[SCORE_NVAL];
-    int64_t base = 0;
+    __syncwarp(); // lanes leave the part loop of the previous tally at different times
     int nc = 0;
-    if (active)
-      nc = score_prepare(ps, i, t, sc, n_coord, r0, r1, u, E, a.gc.tally_values, total, base, val);
+    if (active) // loads the flight, evaluates the filters, publishes r0/u/total/val/base
+      nc = score_lane(tid, t, a.gc.tally_values, a.gc.score_part, &s_d[warp][0][lane], &s_base[warp][lane]);
     int mesh, mesh_stride;
     tally_mesh_info(t, mesh, mesh_stride);
     if (mesh < 0)
@@ -593,20 +697,7 @@ __global__ void __launch_bounds__(BLOCK) k_score(int64_t n_ub, EvArgs a)
     const int n_parts = __shfl_sync(0xffffffffu, incl, 31);
     if (n_parts == 0)
       continue;
-    __syncwarp();
     s_incl[warp][lane] = incl;
-    if (nc > 0) {
-      s_d[warp][0][lane] = r0.x;
-      s_d[warp][1][lane] = r0.y;
-      s_d[warp][2][lane] = r0.z;
-      s_d[warp][3][lane] = u.x;
-      s_d[warp][4][lane] = u.y;
-      s_d[warp][5][lane] = u.z;
-      s_d[warp][6][lane] = total;
-      for (int s = 0; s < SCORE_NVAL; ++s)
-        s_d[warp][7 + s][lane] = val[s];
-      s_base[warp][lane] = base;
-    }
     __syncwarp();
     PartEmit em;
     em.results = a.gc.tally_values + ld(DM.tally_result_ofs + t);
@@ -622,6 +713,7 @@ __global__ void __launch_bounds__(BLOCK) k_score(int64_t n_ub, EvArgs a)
       const V3 pr0 = v3(s_d[warp][0][o], s_d[warp][1][o], s_d[warp][2][o]);
       const V3 pu = v3(s_d[warp][3][o], s_d[warp][4][o], s_d[warp][5][o]);
       const double ptotal = s_d[warp][6][o];
+#pragma unroll
       for (int s = 0; s < SCORE_NVAL; ++s)
         em.val[s] = s_d[warp][7 + s][o];
       em.base = s_base[warp][o];
@@ -640,27 +732,18 @@ __global__ void __launch_bounds__(BLOCK) k_score(int64_t n_ub, EvArgs a)
 // host compile (tests only): same preparation, same parts, traced one after another
 void k_score(int64_t n_ub, EvArgs a)
 {
-  const PState& ps = a.ps;
-  const int64_t n = *a.q_in.count;
+  const int64_t n = *a.n_flights < a.fl.cap ? *a.n_flights : a.fl.cap;
   for (int64_t tid = 0; tid < n_ub && tid < n; ++tid) {
-    const int64_t i = a.q_in.idx[tid];
-    const int n_coord = ps.n_coord[i];
-    const V3 r0 = v3(ps.rlx[i], ps.rly[i], ps.rlz[i]);
-    const V3 r1 = get_r(ps, i, 0);
-    const V3 u = get_u(ps, i, 0);
-    ScoreCtx sc;
-    load_score_ctx(ps, i, n_coord, ps.adv_dist[i], sc);
+    const Flight f = load_flight(a.fl, tid);
     for (int t = 0; t < DM.n_tallies; ++t) {
       PartEmit em;
-      double total = 0.0;
-      const int nc = score_prepare(ps, i, t, sc, n_coord, r0, r1, u, ps.E[i], a.gc.tally_values,
-        total, em.base, em.val);
+      const int nc = score_prepare(a.ps, f, t, a.gc.tally_values, a.gc.score_part, em.base, em.val);
       int mesh;
       tally_mesh_info(t, mesh, em.mesh_stride);
       em.results = a.gc.tally_values + DM.tally_result_ofs[t];
       em.ns = DM.tally_n_scores[t];
       for (int c = 0; c < nc; ++c)
-        mesh_march(mesh, r0, u, total, part_bound(c, nc, total), part_bound(c + 1, nc, total), em);
+        mesh_march(mesh, f.r0, f.u, f.total, part_bound(c, nc, f.total), part_bound(c + 1, nc, f.total), em);
     }
   }
 }
@@ -707,7 +790,7 @@ OMC_D void body_tail(int64_t tid, const EvArgs& a)
   while (alive) {
     ev_xs(a.ps, i);
     ++n_xs;
-    const int next = ev_advance(a.ps, a.gc, i, true);
+    const int next = ev_advance(a.ps, a.gc, a.fl, i, SLOT_LOG);
     if (next == NEXT_COLLISION) {
       alive = ev_collide(a.ps, a.gc, a.fb, i);
       ++n_coll;
@@ -723,6 +806,19 @@ OMC_D void body_tail(int64_t tid, const EvArgs& a)
   atomic_add_u64(a.gc.counters + 3, n_cross);
 }
 OMC_KERNEL(k_tail, EvArgs, body_tail)
+// few, long-running threads: small blocks spread them over all SMs
+constexpr int TAIL_BLOCK = 64;
+#if OMC_CUDA
+#define LAUNCH_TAIL(n_ub, stream, args) \
+  do { \
+    if ((n_ub) > 0) { \
+      k_tail<<<(unsigned)(((n_ub) + TAIL_BLOCK - 1) / TAIL_BLOCK), TAIL_BLOCK, 0, stream>>>((int64_t)(n_ub), args); \
+      ++g_launches; \
+    } \
+  } while (0)
+#else
+#define LAUNCH_TAIL(n_ub, stream, args) OMC_LAUNCH(k_tail, n_ub, stream, args)
+#endif
 
 // ---- deterministic reduction of the per-particle accumulators ------------------
 // (event_death, src/particle.cpp:475-512: global_tally_* += ..., total_weight)
@@ -978,6 +1074,8 @@ struct Engine {
   int64_t cap = 0;            // max particles per generation
   int64_t fis_cap = 0;        // fission bank capacity (3 * cap)
   PState ps;
+  Flights fl;
+  bool tally_needs_cells = false;
   Bank src, fis, fis_sorted;
   int64_t n_src = 0, n_fis = 0;
   Queue q[4];
@@ -999,6 +1097,7 @@ struct Engine {
   cudaStream_t stream = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx0 = nullptr, evx1 = nullptr;
   int64_t tail_threshold = 2048;
+  int score_part = 8;
   int64_t id_offset_last = 0;
 };
 static Engine G;
@@ -1291,6 +1390,9 @@ static EvArgs make_args(const omcgpu_gen_in* in)
   a.gc.counters = G.d_counters;
   a.gc.tally_values = G.d_tally;
   a.gc.fission_cap = G.fis_cap;
+  a.gc.score_part = G.score_part;
+  a.gc.tally_needs_cells = G.tally_needs_cells ? 1 : 0;
+  a.fl = G.fl;
   return a;
 }
 
@@ -1346,7 +1448,14 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
   while (n_alive > 0) {
     if (n_alive <= G.tail_threshold) {
       a.q_in = G.q[cur];
-      OMC_LAUNCH(k_tail, n_alive, G.stream, a);
+      LAUNCH_TAIL(n_alive, G.stream, a);
+      if (in->tallies_active && G.hm.n_tallies > 0 && !G.tally_needs_cells) {
+        rc = read_counts(); // flights the tail logged
+        if (rc)
+          return rc;
+        a.n_flights = G.fl.count;
+        LAUNCH_SCORE(std::min<int64_t>(G.h_counts[6], G.fl.cap), G.stream, a);
+      }
       break;
     }
     const int nxt = 1 - cur;
@@ -1360,8 +1469,10 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
     a.q_a = G.q[2];
     a.q_b = G.q[3];
     OMC_LAUNCH(k_advance, n_alive, G.stream, a);
-    if (in->tallies_active && G.hm.n_tallies > 0)
+    if (in->tallies_active && G.hm.n_tallies > 0) {
+      a.n_flights = G.q[cur].count;
       LAUNCH_SCORE(n_alive, G.stream, a);
+    }
     a.q_in = G.q[3];
     a.q_a = G.q[nxt];
     OMC_LAUNCH(k_surface, n_alive, G.stream, a);
@@ -1490,6 +1601,10 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   rc = upload_model(model);
   if (rc)
     return rc;
+  if (const char* t = std::getenv("OMCGPU_TAIL_THRESHOLD"))
+    G.tail_threshold = std::atoll(t);
+  if (const char* t = std::getenv("OMCGPU_SCORE_PART"))
+    G.score_part = std::max(1, std::atoi(t));
   const int64_t cap = max_particles;
   G.cap = cap;
   G.fis_cap = 3 * cap; // init_fission_bank(3 * work_per_rank), src/simulation.cpp:340
@@ -1507,7 +1622,6 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   A(xs_total, cap); A(xs_absorption, cap); A(xs_fission, cap); A(xs_nu_fission, cap);
   A(b_surface, cap); A(b_level_trans, cap);
   A(k_abs, cap); A(k_col, cap); A(k_trk, cap); A(k_leak, cap);
-  A(rlx, cap); A(rly, cap); A(rlz, cap); A(adv_dist, cap);
 #undef A
   rc = rc ? rc : alloc_bank(G.src, cap);
   rc = rc ? rc : alloc_bank(G.fis, G.fis_cap);
@@ -1535,6 +1649,27 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
     return rc;
   G.d_scan_tmp = tmp;
 #endif
+  {
+    // flight records: one per work-list position in a sweep; the tail kernel logs
+    // up to 64 flights per history it takes over (beyond that it scores inline)
+    Flights& fl = G.fl;
+    fl.cap = std::max<int64_t>(cap, 64 * std::min<int64_t>(cap, G.tail_threshold));
+#define F(col) rc = rc ? rc : dev_alloc(&fl.col, (size_t)fl.cap)
+    F(x); F(y); F(z); F(ux); F(uy); F(uz); F(total); F(flux); F(E);
+    F(xs_t); F(xs_a); F(xs_f); F(xs_nf); F(material); F(g); F(mg_ba); F(pidx);
+#undef F
+    fl.count = G.d_counts + 6;
+    if (rc)
+      return rc;
+    G.tally_needs_cells = false;
+    for (int f = 0; f < model->n_filters; ++f)
+      if (model->filter_type[f] == OMCGPU_FILTER_CELL || model->filter_type[f] == OMCGPU_FILTER_UNIVERSE)
+        G.tally_needs_cells = true;
+  }
+#if OMC_CUDA
+  CUDA_OK(cudaMemcpyToSymbol(c_ps, &G.ps, sizeof(PState)));
+  CUDA_OK(cudaMemcpyToSymbol(c_fl, &G.fl, sizeof(Flights)));
+#endif
   CUDA_OK(cudaMallocHost((void**)&G.h_counts, 8 * sizeof(int32_t)));
   CUDA_OK(cudaMallocHost((void**)&G.h_counters, 4 * sizeof(unsigned long long)));
   CUDA_OK(cudaMallocHost((void**)&G.h_partial, G.n_chunks * 6 * sizeof(double)));
@@ -1543,8 +1678,6 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   CUDA_OK(cudaEventCreate(&G.ev1));
   CUDA_OK(cudaEventCreate(&G.evx0));
   CUDA_OK(cudaEventCreate(&G.evx1));
-  if (const char* t = std::getenv("OMCGPU_TAIL_THRESHOLD"))
-    G.tail_threshold = std::atoll(t);
   G.ready = true;
   g_launches = 0;
   return 0;
