@@ -78,25 +78,51 @@ OMC_HD double comp(V3 a, int i)
 }
 
 // -----------------------------------------------------------------------------
-// Particle state: structure of arrays in HBM (last
-// paragraph).  Level-indexed columns are level-major: col[level * cap + i].
+// Particle state in HBM (last paragraph): a structure of
+// arrays whose elements are 32-byte SECTORS, not scalars.  Work lists hold
+// particle indices in arbitrary order, so a warp's accesses to a column are a
+// gather; with one scalar per column every 8-byte access would move a whole
+// 32-byte sector.  Fields that one event kernel reads together therefore share
+// a sector (a "group": 4 doubles, or doubles and int32 mixed), and a gather
+// moves only bytes the kernel uses.  `Col<T, S>` is a field inside a group:
+// element i lives at p[i * S], S = group size in units of T.  Level-indexed
+// fields are level-major: index (level * cap + i).
 // -----------------------------------------------------------------------------
+template<class T, int S>
+struct Col {
+  T* p;
+#if defined(__CUDACC__) && !defined(OMC_EMU)
+  __host__ __device__ __forceinline__
+#else
+  inline
+#endif
+  T& operator[](int64_t i) const { return p[i * S]; }
+};
+
 struct PState {
   int64_t cap; // stride between coordinate levels = particles allocated
-  // per level
-  double *rx, *ry, *rz, *ux, *uy, *uz;
-  int32_t *cell, *universe, *lattice, *lat_x, *lat_y, *lat_z;
-  // per particle
-  int32_t *n_coord, *cell_last0, *cell_instance, *surface, *material, *material_last;
-  double *sqrtkT, *sqrtkT_last;
-  double* E;
-  int32_t *g, *g_last;
-  double *wgt, *time;
-  uint64_t* seed;
-  int32_t *n_progeny, *n_event;
-  double *xs_total, *xs_absorption, *xs_fission, *xs_nu_fission;
-  int32_t *b_surface, *b_level_trans;
-  double *k_abs, *k_col, *k_trk, *k_leak;
+  // group A[level]: position + which cell / lattice the level is in
+  Col<double, 4> rx, ry, rz;
+  Col<int32_t, 8> cell, lattice;
+  // group B[level]: direction + universe
+  Col<double, 4> ux, uy, uz;
+  Col<int32_t, 8> universe;
+  // group C[level] (16 bytes): lattice indices, touched only inside lattices
+  Col<int32_t, 4> lat_x, lat_y, lat_z;
+  // group P1: what a flight and a collision update
+  Col<double, 4> E, wgt, time;
+  Col<uint64_t, 4> seed;
+  // group P2: macroscopic cross sections (written by k_xs)
+  Col<double, 4> xs_total, xs_absorption, xs_fission, xs_nu_fission;
+  // group P3: k-effective / leakage accumulators of the history
+  Col<double, 4> k_abs, k_col, k_trk, k_leak;
+  // group P4: integer state
+  Col<int32_t, 8> n_coord, surface, material, material_last, cell_instance, cell_last0, g, n_event;
+  // group P5: temperatures + the boundary found by the last flight
+  Col<double, 4> sqrtkT, sqrtkT_last;
+  Col<int32_t, 8> b_surface, b_level_trans, g_last;
+  // plain column (scanned by cub for the fission-bank sort)
+  int32_t* n_progeny;
 };
 
 // Flight records: what tracklength scoring needs from one flight, written by

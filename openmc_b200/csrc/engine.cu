@@ -1096,7 +1096,7 @@ struct Engine {
   int64_t n_tally = 0;
   cudaStream_t stream = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx0 = nullptr, evx1 = nullptr;
-  int64_t tail_threshold = 2048;
+  int64_t tail_threshold = 16384;
   int score_part = 8;
   int64_t id_offset_last = 0;
 };
@@ -1611,18 +1611,37 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   const int L = std::max(1, std::min<int>(model->n_coord_levels, OMCGPU_MAX_COORD));
   PState& ps = G.ps;
   ps.cap = cap;
-#define A(col, count) rc = rc ? rc : dev_alloc(&ps.col, (size_t)(count))
-  A(rx, cap * L); A(ry, cap * L); A(rz, cap * L); A(ux, cap * L); A(uy, cap * L); A(uz, cap * L);
-  A(cell, cap * L); A(universe, cap * L); A(lattice, cap * L);
-  A(lat_x, cap * L); A(lat_y, cap * L); A(lat_z, cap * L);
-  A(n_coord, cap); A(cell_last0, cap); A(cell_instance, cap); A(surface, cap);
-  A(material, cap); A(material_last, cap); A(sqrtkT, cap); A(sqrtkT_last, cap);
-  A(E, cap); A(g, cap); A(g_last, cap); A(wgt, cap); A(time, cap); A(seed, cap);
-  A(n_progeny, cap); A(n_event, cap);
-  A(xs_total, cap); A(xs_absorption, cap); A(xs_fission, cap); A(xs_nu_fission, cap);
-  A(b_surface, cap); A(b_level_trans, cap);
-  A(k_abs, cap); A(k_col, cap); A(k_trk, cap); A(k_leak, cap);
-#undef A
+  {
+    // sector groups (see PState): one allocation per group, fields at fixed slots
+    char *gA = nullptr, *gB = nullptr, *gC = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr,
+         *p4 = nullptr, *p5 = nullptr;
+    rc = rc ? rc : dev_alloc(&gA, (size_t)cap * L * 32);
+    rc = rc ? rc : dev_alloc(&gB, (size_t)cap * L * 32);
+    rc = rc ? rc : dev_alloc(&gC, (size_t)cap * L * 16);
+    rc = rc ? rc : dev_alloc(&p1, (size_t)cap * 32);
+    rc = rc ? rc : dev_alloc(&p2, (size_t)cap * 32);
+    rc = rc ? rc : dev_alloc(&p3, (size_t)cap * 32);
+    rc = rc ? rc : dev_alloc(&p4, (size_t)cap * 32);
+    rc = rc ? rc : dev_alloc(&p5, (size_t)cap * 32);
+    rc = rc ? rc : dev_alloc(&ps.n_progeny, (size_t)cap);
+    if (rc)
+      return rc;
+#define D(col, base, slot) ps.col.p = reinterpret_cast<double*>(base) + (slot)
+#define I(col, base, slot) ps.col.p = reinterpret_cast<int32_t*>(base) + (slot)
+    D(rx, gA, 0); D(ry, gA, 1); D(rz, gA, 2); I(cell, gA, 6); I(lattice, gA, 7);
+    D(ux, gB, 0); D(uy, gB, 1); D(uz, gB, 2); I(universe, gB, 6);
+    I(lat_x, gC, 0); I(lat_y, gC, 1); I(lat_z, gC, 2);
+    D(E, p1, 0); D(wgt, p1, 1); D(time, p1, 2);
+    ps.seed.p = reinterpret_cast<uint64_t*>(p1) + 3;
+    D(xs_total, p2, 0); D(xs_absorption, p2, 1); D(xs_fission, p2, 2); D(xs_nu_fission, p2, 3);
+    D(k_abs, p3, 0); D(k_col, p3, 1); D(k_trk, p3, 2); D(k_leak, p3, 3);
+    I(n_coord, p4, 0); I(surface, p4, 1); I(material, p4, 2); I(material_last, p4, 3);
+    I(cell_instance, p4, 4); I(cell_last0, p4, 5); I(g, p4, 6); I(n_event, p4, 7);
+    D(sqrtkT, p5, 0); D(sqrtkT_last, p5, 1);
+    I(b_surface, p5, 4); I(b_level_trans, p5, 5); I(g_last, p5, 6);
+#undef D
+#undef I
+  }
   rc = rc ? rc : alloc_bank(G.src, cap);
   rc = rc ? rc : alloc_bank(G.fis, G.fis_cap);
   rc = rc ? rc : alloc_bank(G.fis_sorted, G.fis_cap);
