@@ -1,0 +1,78 @@
+"""N > 1 path on the CPU tier: world_size-2 `gloo`, the engine sources
+host-compiled (tests/_emu), through the same TorchComm / Simulation code the
+GPU bench uses with NCCL.  The bank exchange must reproduce the single-rank run:
+particle ids and seeds are global (src/simulation.cpp:592, 613-616) and every
+rank combs with the same seed (src/eigenvalue.cpp:152-178), so the source bank
+after synchronize_bank is identical and k differs only by fp reduction order."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+N, BATCHES, INACTIVE = 1500, 5, 2
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(name, emu_path, comm):
+    import cases
+    from openmc_b200 import lib
+    from oracle.binding import Oracle
+    model, box, of = cases.build(name)
+    full = Oracle(model).sample_initial_source(N, box, of)
+    rank, size = (comm.rank, comm.size) if comm else (0, 1)
+    # this rank's share of the global source bank (calculate_work, src/simulation.cpp:657-680)
+    lo = sum(N // size + (1 if r < N % size else 0) for r in range(rank))
+    hi = lo + N // size + (1 if rank < N % size else 0)
+    sim = lib.Simulation(lib.Engine(emu_path), model, N, BATCHES, INACTIVE, full[lo:hi], comm=comm)
+    k = sim.run()
+    bank = sim.get_source_bank()
+    tallies = [t[:, :, 1].copy() for t in sim.tally_results]
+    kgen = list(sim.k_generation)
+    sim.simulation_finalize()
+    return dict(k=k, kgen=kgen, bank=bank, lo=lo, tallies=tallies)
+
+
+def _worker(rank, size, port, name, emu_path, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    from openmc_b200.comm import TorchComm
+    r = _run(name, emu_path, TorchComm(on_gpu=False))
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), k=np.array(r["k"]), kgen=np.array(r["kgen"]),
+             bank=r["bank"], lo=r["lo"], **{f"t{i}": t for i, t in enumerate(r["tallies"])})
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["mg_legendre", "mg_temperature_multi"])
+def test_two_ranks_equal_one_rank(emu_lib, name, tmp_path):
+    single = _run(name, emu_lib, None)
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, name, emu_lib, str(tmp_path)), nprocs=2, join=True)
+    r0 = np.load(tmp_path / "rank0.npz")
+    r1 = np.load(tmp_path / "rank1.npz")
+    np.testing.assert_allclose(r0["kgen"], single["kgen"], rtol=1e-12)
+    np.testing.assert_allclose(r1["kgen"], single["kgen"], rtol=1e-12)
+    np.testing.assert_allclose(r0["k"], single["k"], rtol=1e-9)
+    # the redistributed source bank: rank r holds global sites [work_index[r], work_index[r+1])
+    bank = np.concatenate([r0["bank"], r1["bank"]])
+    assert int(r1["lo"]) == r0["bank"].size
+    for f in ("r", "u", "E", "wgt", "delayed_group", "parent_id", "progeny_id"):
+        assert np.array_equal(bank[f], single["bank"][f]), f
+    for i, t in enumerate(single["tallies"]):
+        np.testing.assert_allclose(r0[f"t{i}"], t, rtol=1e-10, atol=1e-300)
