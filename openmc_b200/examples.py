@@ -44,6 +44,40 @@ def slab_2g_library(order=1, names=("mat_1",)):
     return lib
 
 
+def mg_basic():
+    """tests/regression_tests/mg_basic/test.py:12-95: six slab regions holding the
+    same 2-group data as Legendre, 33-point tabular, 33-bin histogram, fission
+    matrix, angle-dependent (2 x 2) and a microscopic combination."""
+    lib = slab_2g_library(1, names=("mat_1", "mat_6"))
+    mat_1 = lib.xsdatas["mat_1"]
+    mat_2 = mat_1.convert_scatter_format("tabular", 33)
+    mat_2.name = "mat_2"
+    lib.add_xsdata(mat_2)
+    mat_3 = mat_1.convert_scatter_format("histogram", 33)
+    mat_3.name = "mat_3"
+    lib.add_xsdata(mat_3)
+    nu = [2.50, 2.50]
+    fiss = np.array([0.002817, 0.097])
+    mat_4 = XSdata("mat_4", 2)
+    mat_4.order = 1
+    mat_4.set_nu_fission(np.outer(np.multiply(nu, fiss), [1., 0.]))
+    mat_4.set_absorption(mat_1.data[294.0]["absorption"])
+    mat_4.set_scatter_matrix(mat_1.data[294.0]["scatter_matrix"])
+    mat_4.set_total(mat_1.data[294.0]["total"])
+    lib.add_xsdata(mat_4)
+    mat_5 = mat_1.convert_representation("angle", 2, 2)
+    mat_5.name = "mat_5"
+    lib.add_xsdata(mat_5)
+    names = ["base leg", "base tab", "base hist", "base matrix", "base ang", "micro"]
+    m, box, of = slab_mg(num_regions=6, mat_names=names)
+    micro = m.materials[-1]
+    micro.macroscopic = None
+    micro.units = "sum"
+    micro.density = None
+    micro.components = [("mat_1", 0.5), ("mat_6", 0.5)]
+    return m, lib, box, of
+
+
 def slab_mg(num_regions=1, mat_names=None):
     """openmc.examples.slab_mg, openmc/examples.py:557-656: 1-D slab, reflective
     at x=0, vacuum at x=929.45, uniform box source over the first region."""

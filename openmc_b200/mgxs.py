@@ -105,6 +105,57 @@ class XSdata:
     def n_ang(self):
         return self.num_polar * self.num_azimuthal
 
+    # -- library-side conversions (openmc/mgxs_library.py; used by the mg_basic recipe) --
+    def _clone(self, name=None):
+        import copy
+        x = copy.deepcopy(self)
+        if name is not None:
+            x.name = name
+        return x
+
+    def convert_scatter_format(self, target_format, target_order):
+        """XSdata.convert_scatter_format, openmc/mgxs_library.py:1787-1866, for a
+        Legendre source: 'tabular' evaluates the series on linspace(-1, 1, n);
+        'histogram' Simpson-integrates a 257-point sampling of every bin."""
+        from scipy.integrate import simpson
+        from scipy.special import eval_legendre
+        assert self.scatter_format == "legendre" and target_format in ("tabular", "histogram")
+        x = self._clone()
+        x.scatter_format = target_format
+        x.order = target_order
+        n_src = self.order + 1
+        for T in self.temperatures:
+            orig = np.asarray(self.data[T]["scatter_matrix"], dtype=float)
+            new = np.zeros(orig.shape[:-1] + (target_order,))
+            if target_format == "tabular":
+                mu = np.linspace(-1, 1, target_order)
+                for imu in range(len(mu)):
+                    for l in range(n_src):
+                        new[..., imu] += ((l + 0.5) * eval_legendre(l, mu[imu]) * orig[..., l])
+            else:
+                mu = np.linspace(-1, 1, target_order + 1)
+                for h in range(target_order):
+                    mu_fine = np.linspace(mu[h], mu[h + 1], 257)     # _NMU, mgxs_library.py:34
+                    fine = np.zeros(new.shape[:-1] + (257,))
+                    for imu in range(len(mu_fine)):
+                        for l in range(n_src):
+                            fine[..., imu] += ((l + 0.5) * eval_legendre(l, mu_fine[imu]) * orig[..., l])
+                    new[..., h] = simpson(fine, x=mu_fine)
+            x.data[T]["scatter_matrix"] = new
+        return x
+
+    def convert_representation(self, target, num_polar, num_azimuthal):
+        """isotropic -> angle: every array is copied into each (polar, azimuthal)
+        bin, openmc/mgxs_library.py:1688-1785."""
+        assert self.representation == "isotropic" and target == "angle"
+        x = self._clone()
+        x.representation = "angle"
+        x.num_polar, x.num_azimuthal = num_polar, num_azimuthal
+        for T in self.temperatures:
+            for key, orig in self.data[T].items():
+                x.data[T][key] = np.resize(orig, (num_polar, num_azimuthal) + np.asarray(orig).shape)
+        return x
+
     def order_data(self):
         return self.order + 1 if self.scatter_format == "legendre" else self.order
 

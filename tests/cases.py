@@ -10,6 +10,8 @@ GOLDEN = {
     "mg_max_order": ("1.009220E+00", "9.571832E-03", []),
     # tests/regression_tests/mg_survival_biasing/results_true.dat
     "mg_survival_biasing": ("9.889968E-01", "9.144186E-03", []),
+    # tests/regression_tests/mg_basic/results_true.dat
+    "mg_basic": ("1.004679E+00", "1.329350E-02", []),
     # tests/regression_tests/mg_temperature_multi/results_true.dat
     "mg_temperature_multi": ("1.309371E+00", "6.765039E-03",
                              [("2.532303E+01", "1.282689E+02"), ("9.336894E+01", "1.743765E+03")]),
@@ -29,6 +31,9 @@ def build(name):
         m, box, of = examples.slab_mg()
         m.settings["survival_biasing"] = 1
         return mgxs.build_mg_model(m, examples.slab_2g_library(1)), box, of
+    if name == "mg_basic":
+        m, lib, box, of = examples.mg_basic()
+        return mgxs.build_mg_model(m, lib), box, of
     if name == "mg_temperature_multi":
         m, lib, box, of = examples.mg_temperature_multi()
         return mgxs.build_mg_model(m, lib), box, of

@@ -14,7 +14,7 @@ from oracle.binding import Oracle
 
 
 @pytest.mark.parametrize("threshold", ["0", "64", "100000"])
-@pytest.mark.parametrize("name", ["mg_legendre", "mg_survival_biasing", "mg_temperature_multi"])
+@pytest.mark.parametrize("name", ["mg_legendre", "mg_survival_biasing", "mg_temperature_multi", "mg_basic"])
 def test_golden_through_engine(emu_lib, name, threshold, monkeypatch):
     monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)
     model, box, of = cases.build(name)
