@@ -36,6 +36,10 @@ inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new EmuEvent; return 0
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return 0; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+enum { cudaEventDisableTiming = 2, cudaLimitMaxL2FetchGranularity = 5 };
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new EmuEvent; return 0; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
+inline cudaError_t cudaDeviceSetLimit(int, size_t) { return 0; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
 {
   *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();

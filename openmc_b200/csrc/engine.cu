@@ -97,7 +97,7 @@ struct EvArgs {
   Bank fb;   // fission bank (k_collide)
   Queue q_in, q_a, q_b; // input list, and up to two output lists
   Flights fl;           // flight records for k_score
-  const int32_t* n_flights; // how many records k_score reads (work-list or tail-log count)
+  int32_t fl_buf;       // which of the two record buffers `fl` is (c_fl[fl_buf])
 };
 
 enum { NEXT_DEAD = -1, NEXT_COLLISION = 0, NEXT_SURFACE = 1 };
@@ -644,12 +644,12 @@ OMC_HD void tally_mesh_info(int t, int& mesh, int& mesh_stride)
 // sd points at this lane's column of the warp's staging area (stride 32 doubles).
 __constant__ PState c_ps; // the particle columns never move after omcgpu_init
 
-__constant__ Flights c_fl;
+__constant__ Flights c_fl[2]; // double-buffered: k_score(sweep s) overlaps k_advance(sweep s+1)
 
-__device__ __noinline__ int score_lane(int64_t j, int t, double* values, int score_part, double* sd,
-  int64_t* sbase)
+__device__ __noinline__ int score_lane(int64_t j, int buf, int t, double* values, int score_part,
+  double* sd, int64_t* sbase)
 {
-  const Flight f = load_flight(c_fl, j);
+  const Flight f = load_flight(c_fl[buf], j);
   double val[SCORE_NVAL];
   int64_t base = 0;
   const int nc = score_prepare(c_ps, f, t, values, score_part, base, val);
@@ -677,13 +677,12 @@ __global__ void __launch_bounds__(BLOCK, 2) k_score(int64_t n_ub, EvArgs a)
   __shared__ int s_incl[WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t n = *a.n_flights < a.fl.cap ? *a.n_flights : a.fl.cap;
-  const bool active = tid < n;
+  const bool active = tid < n_ub; // the host passes the exact number of records
   for (int t = 0; t < DM.n_tallies; ++t) {
     __syncwarp(); // lanes leave the part loop of the previous tally at different times
     int nc = 0;
     if (active) // loads the flight, evaluates the filters, publishes r0/u/total/val/base
-      nc = score_lane(tid, t, a.gc.tally_values, a.gc.score_part, &s_d[warp][0][lane], &s_base[warp][lane]);
+      nc = score_lane(tid, a.fl_buf, t, a.gc.tally_values, a.gc.score_part, &s_d[warp][0][lane], &s_base[warp][lane]);
     int mesh, mesh_stride;
     tally_mesh_info(t, mesh, mesh_stride);
     if (mesh < 0)
@@ -732,8 +731,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_score(int64_t n_ub, EvArgs a)
 // host compile (tests only): same preparation, same parts, traced one after another
 void k_score(int64_t n_ub, EvArgs a)
 {
-  const int64_t n = *a.n_flights < a.fl.cap ? *a.n_flights : a.fl.cap;
-  for (int64_t tid = 0; tid < n_ub && tid < n; ++tid) {
+  for (int64_t tid = 0; tid < n_ub; ++tid) {
     const Flight f = load_flight(a.fl, tid);
     for (int t = 0; t < DM.n_tallies; ++t) {
       PartEmit em;
@@ -1074,8 +1072,11 @@ struct Engine {
   int64_t cap = 0;            // max particles per generation
   int64_t fis_cap = 0;        // fission bank capacity (3 * cap)
   PState ps;
-  Flights fl;
+  Flights fl[2];
   bool tally_needs_cells = false;
+  bool overlap = true;        // run k_score / k_surface / k_collide on their own streams
+  cudaStream_t s_score = 0, s_surf = 0, s_coll = 0;
+  cudaEvent_t e_adv = nullptr, e_surf = nullptr, e_coll = nullptr, e_score[2] = {nullptr, nullptr};
   Bank src, fis, fis_sorted;
   int64_t n_src = 0, n_fis = 0;
   Queue q[4];
@@ -1392,7 +1393,8 @@ static EvArgs make_args(const omcgpu_gen_in* in)
   a.gc.fission_cap = G.fis_cap;
   a.gc.score_part = G.score_part;
   a.gc.tally_needs_cells = G.tally_needs_cells ? 1 : 0;
-  a.fl = G.fl;
+  a.fl = G.fl[0];
+  a.fl_buf = 0;
   return a;
 }
 
@@ -1445,20 +1447,36 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
   int64_t n_alive = G.h_counts[cur];
   int64_t n_xs = 0, n_coll = 0, n_cross = 0;
   double ms_xs = 0.0;
+  const bool score = in->tallies_active && G.hm.n_tallies > 0;
+  // Streams: the three consumers of a flight (tally scoring, surface crossing,
+  // collision) touch disjoint data and run side by side; k_score reads only the
+  // flight records, which are double-buffered, so it also overlaps the next
+  // sweep's k_xs / k_advance.
+  cudaStream_t st_score = G.overlap ? G.s_score : G.stream;
+  cudaStream_t st_surf = G.overlap ? G.s_surf : G.stream;
+  cudaStream_t st_coll = G.overlap ? G.s_coll : G.stream;
+  bool score_pending[2] = {false, false};
+  int64_t sweep = 0;
   while (n_alive > 0) {
     if (n_alive <= G.tail_threshold) {
+      for (int b = 0; b < 2; ++b)
+        if (score_pending[b] && G.overlap)
+          CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_score[b], 0));
+      score_pending[0] = score_pending[1] = false;
       a.q_in = G.q[cur];
+      a.fl = G.fl[0];
+      a.fl_buf = 0;
       LAUNCH_TAIL(n_alive, G.stream, a);
-      if (in->tallies_active && G.hm.n_tallies > 0 && !G.tally_needs_cells) {
+      if (score && !G.tally_needs_cells) {
         rc = read_counts(); // flights the tail logged
         if (rc)
           return rc;
-        a.n_flights = G.fl.count;
-        LAUNCH_SCORE(std::min<int64_t>(G.h_counts[6], G.fl.cap), G.stream, a);
+        LAUNCH_SCORE(std::min<int64_t>(G.h_counts[6], G.fl[0].cap), G.stream, a);
       }
       break;
     }
     const int nxt = 1 - cur;
+    const int buf = (int)(sweep & 1);
     // zero the three output counters (collision, surface, next)
     CUDA_OK(cudaMemsetAsync(G.d_counts + nxt, 0, sizeof(int32_t), G.stream));
     CUDA_OK(cudaMemsetAsync(G.d_counts + 2, 0, 2 * sizeof(int32_t), G.stream));
@@ -1468,16 +1486,43 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
     CUDA_OK(cudaEventRecord(G.evx1, G.stream));
     a.q_a = G.q[2];
     a.q_b = G.q[3];
+    a.fl = G.fl[buf];
+    a.fl_buf = buf;
+    if (score && score_pending[buf] && G.overlap) // records of sweep-2 must have been consumed
+      CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_score[buf], 0));
     OMC_LAUNCH(k_advance, n_alive, G.stream, a);
-    if (in->tallies_active && G.hm.n_tallies > 0) {
-      a.n_flights = G.q[cur].count;
+    // cell / universe filters read the live coordinate levels: score before the
+    // crossing and collision kernels may change them
+    const bool score_in_order = score && G.tally_needs_cells;
+    if (score_in_order)
       LAUNCH_SCORE(n_alive, G.stream, a);
+    if (G.overlap)
+      CUDA_OK(cudaEventRecord(G.e_adv, G.stream));
+    if (score && !score_in_order) {
+      if (G.overlap)
+        CUDA_OK(cudaStreamWaitEvent(st_score, G.e_adv, 0));
+      LAUNCH_SCORE(n_alive, st_score, a);
+      if (G.overlap) {
+        CUDA_OK(cudaEventRecord(G.e_score[buf], st_score));
+        score_pending[buf] = true;
+      }
     }
     a.q_in = G.q[3];
     a.q_a = G.q[nxt];
-    OMC_LAUNCH(k_surface, n_alive, G.stream, a);
+    if (G.overlap)
+      CUDA_OK(cudaStreamWaitEvent(st_surf, G.e_adv, 0));
+    OMC_LAUNCH(k_surface, n_alive, st_surf, a);
     a.q_in = G.q[2];
-    OMC_LAUNCH(k_collide, n_alive, G.stream, a);
+    if (G.overlap) {
+      CUDA_OK(cudaEventRecord(G.e_surf, st_surf));
+      CUDA_OK(cudaStreamWaitEvent(st_coll, G.e_adv, 0));
+    }
+    OMC_LAUNCH(k_collide, n_alive, st_coll, a);
+    if (G.overlap) {
+      CUDA_OK(cudaEventRecord(G.e_coll, st_coll));
+      CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_surf, 0));
+      CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_coll, 0));
+    }
     rc = read_counts();
     if (rc)
       return rc;
@@ -1489,7 +1534,11 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
     n_cross += G.h_counts[3];
     n_alive = G.h_counts[nxt];
     cur = nxt;
+    ++sweep;
   }
+  for (int b = 0; b < 2; ++b)
+    if (score_pending[b] && G.overlap)
+      CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_score[b], 0));
   // death: deterministic reduction of the per-particle accumulators
   ReduceArgs r;
   r.ps = G.ps;
@@ -1573,9 +1622,18 @@ int omcgpu_finalize(void)
     cudaEventDestroy(G.ev1);
     cudaEventDestroy(G.evx0);
     cudaEventDestroy(G.evx1);
+    cudaEventDestroy(G.e_adv);
+    cudaEventDestroy(G.e_surf);
+    cudaEventDestroy(G.e_coll);
+    cudaEventDestroy(G.e_score[0]);
+    cudaEventDestroy(G.e_score[1]);
   }
-  if (G.ready)
+  if (G.ready) {
     cudaStreamDestroy(G.stream);
+    cudaStreamDestroy(G.s_score);
+    cudaStreamDestroy(G.s_surf);
+    cudaStreamDestroy(G.s_coll);
+  }
   G = Engine();
   return 0;
 }
@@ -1598,6 +1656,13 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   if (max_particles > 2000000000LL / 3)
     return fail(OMCGPU_E_OUT_OF_BOUNDS, "max_particles too large for 32-bit work lists%s");
   CUDA_OK(cudaStreamCreate(&G.stream));
+  CUDA_OK(cudaStreamCreate(&G.s_score));
+  CUDA_OK(cudaStreamCreate(&G.s_surf));
+  CUDA_OK(cudaStreamCreate(&G.s_coll));
+  if (const char* t = std::getenv("OMCGPU_OVERLAP"))
+    G.overlap = std::atoi(t) != 0;
+  // particle state is gathered in 32-byte sectors (PState): do not let L2 fetch 64
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
   rc = upload_model(model);
   if (rc)
     return rc;
@@ -1671,13 +1736,15 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   {
     // flight records: one per work-list position in a sweep; the tail kernel logs
     // up to 64 flights per history it takes over (beyond that it scores inline)
-    Flights& fl = G.fl;
-    fl.cap = std::max<int64_t>(cap, 64 * std::min<int64_t>(cap, G.tail_threshold));
+    for (int b = 0; b < 2; ++b) {
+      Flights& fl = G.fl[b];
+      fl.cap = std::max<int64_t>(cap, b == 0 ? 64 * std::min<int64_t>(cap, G.tail_threshold) : 0);
 #define F(col) rc = rc ? rc : dev_alloc(&fl.col, (size_t)fl.cap)
-    F(x); F(y); F(z); F(ux); F(uy); F(uz); F(total); F(flux); F(E);
-    F(xs_t); F(xs_a); F(xs_f); F(xs_nf); F(material); F(g); F(mg_ba); F(pidx);
+      F(x); F(y); F(z); F(ux); F(uy); F(uz); F(total); F(flux); F(E);
+      F(xs_t); F(xs_a); F(xs_f); F(xs_nf); F(material); F(g); F(mg_ba); F(pidx);
 #undef F
-    fl.count = G.d_counts + 6;
+      fl.count = G.d_counts + 6;
+    }
     if (rc)
       return rc;
     G.tally_needs_cells = false;
@@ -1687,7 +1754,7 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   }
 #if OMC_CUDA
   CUDA_OK(cudaMemcpyToSymbol(c_ps, &G.ps, sizeof(PState)));
-  CUDA_OK(cudaMemcpyToSymbol(c_fl, &G.fl, sizeof(Flights)));
+  CUDA_OK(cudaMemcpyToSymbol(c_fl, G.fl, 2 * sizeof(Flights)));
 #endif
   CUDA_OK(cudaMallocHost((void**)&G.h_counts, 8 * sizeof(int32_t)));
   CUDA_OK(cudaMallocHost((void**)&G.h_counters, 4 * sizeof(unsigned long long)));
@@ -1697,6 +1764,11 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   CUDA_OK(cudaEventCreate(&G.ev1));
   CUDA_OK(cudaEventCreate(&G.evx0));
   CUDA_OK(cudaEventCreate(&G.evx1));
+  CUDA_OK(cudaEventCreateWithFlags(&G.e_adv, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&G.e_surf, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&G.e_coll, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&G.e_score[0], cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&G.e_score[1], cudaEventDisableTiming));
   G.ready = true;
   g_launches = 0;
   return 0;

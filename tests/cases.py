@@ -72,3 +72,21 @@ def xs_probe_energies(model, libx, n, seed=7):
     near = np.concatenate([np.nextafter(edges, 0), edges, np.nextafter(edges, np.inf)])
     special = np.array([e_min, e_max, e_min * 0.5, e_max * 1.5, np.nextafter(e_min, 1), np.nextafter(e_max, 0)])
     return np.concatenate([E, pick, np.nextafter(pick, 0), np.nextafter(pick, np.inf), near, special])
+
+
+def save_model_npz(path, model):
+    """every omcgpu_model field (arrays and scalars) of a ModelHandle -> one .npz"""
+    import numpy as np
+    from openmc_b200 import _abi as abi
+    out = {}
+    for name, (dt, is_ptr) in abi.model_field_types().items():
+        out[name] = model[name] if is_ptr else np.array(model[name])
+    np.savez_compressed(path, **out)
+
+
+def load_model_npz(path):
+    import numpy as np
+    from openmc_b200 import _abi as abi
+    z = np.load(path)
+    types = abi.model_field_types()
+    return abi.ModelHandle({k: (z[k] if types[k][1] else z[k].item()) for k in z.files})

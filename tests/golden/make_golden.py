@@ -88,9 +88,14 @@ def kat():
 
 
 def oracle_vectors():
-    model, box, of, libx = cases.build_ce(n_grid=4000)
+    """The flattened model itself is part of the fixture (ce_model.npz): the
+    synthetic library is generated with numpy transcendental functions whose last
+    bit may differ between machines, and the fixture must not depend on that."""
+    model, box, of, libx = cases.build_ce(n_grid=1000)
+    cases.save_model_npz(os.path.join(HERE, "ce_model.npz"), model)
+    model = cases.load_model_npz(os.path.join(HERE, "ce_model.npz"))
     o = binding.Oracle(model)
-    E = cases.xs_probe_energies(model, libx, 4000)
+    E = cases.xs_probe_energies(model, libx, 3000)
     out = {"E": E}
     for mat in range(int(model["n_materials"])):
         xs, ig = o.calculate_xs(E, np.full(E.size, mat, np.int32), 4)

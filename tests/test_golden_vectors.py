@@ -90,7 +90,7 @@ def test_reference_unit_test_known_answers(kat, orc):
 
 
 def _check_lookup(eng):
-    model, box, of, libx = cases.build_ce(n_grid=4000)
+    model = cases.load_model_npz(os.path.join(G, "ce_model.npz"))
     v = np.load(os.path.join(G, "ce_lookup.npz"))
     eng.init(model, 0, 1024)
     for mat in range(int(model["n_materials"])):
@@ -101,7 +101,7 @@ def _check_lookup(eng):
 
 
 def _check_geometry(eng):
-    model, box, of, libx = cases.build_ce(n_grid=4000)
+    model = cases.load_model_npz(os.path.join(G, "ce_model.npz"))
     v = np.load(os.path.join(G, "geometry.npz"))
     eng.init(model, 0, 32768)
     cell, inst, mat, nco = eng.find_cell(v["xyz"], v["uvw"])
