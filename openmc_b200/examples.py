@@ -258,3 +258,179 @@ def pincell_ce(n_grid=100000, mesh_dim=100, energy_bins=500, tallies=True, libra
         library = nd.synthetic_library(nd.PINCELL_NUCLIDES, n_grid)
     box = [-pitch / 2, -pitch / 2, -1, pitch / 2, pitch / 2, 1]
     return m, library, box, True
+
+
+# ----------------------------------------------------------------------------
+# config C3: 17 x 17 PWR assembly, continuous energy (examples/assembly/assembly.py:20-122)
+# ----------------------------------------------------------------------------
+ASSEMBLY_NUCLIDES = [
+    ("U234", 92, 234, True, False, False), ("U235", 92, 235, True, True, True),
+    ("U238", 92, 238, True, True, False), ("O16", 8, 16, False, False, False),
+    ("Zr90", 40, 90, False, True, False), ("Zr91", 40, 91, False, False, False),
+    ("Zr92", 40, 92, False, False, False), ("Zr94", 40, 94, False, False, False),
+    ("Zr96", 40, 96, False, False, False), ("H1", 1, 1, False, False, False),
+    ("B10", 5, 10, False, False, False), ("B11", 5, 11, False, False, False),
+]
+# guide-tube positions (row, column) of examples/assembly/assembly.py:86-94
+GUIDE_TUBES = [(2, 5), (2, 8), (2, 11), (3, 3), (3, 13), (5, 2), (5, 5), (5, 8), (5, 11), (5, 14),
+               (8, 2), (8, 5), (8, 8), (8, 11), (8, 14), (11, 2), (11, 5), (11, 8), (11, 11), (11, 14),
+               (13, 3), (13, 13), (14, 5), (14, 8), (14, 11)]
+
+
+def _pin_universes(m: Model, fuel, clad, water, u_fuel, u_gt, r_fo=0.39218, r_co=0.45720):
+    """fuel-pin and guide-tube universes (assembly.py:49-73); cells of a universe
+    are listed inside-out like the reference builds them"""
+    fo = m.surface("z-cylinder", [0.0, 0.0, r_fo]).id
+    co = m.surface("z-cylinder", [0.0, 0.0, r_co]).id
+    m.cell(region=f"-{fo}", fill=fuel, universe=u_fuel)
+    m.cell(region=f"{fo} -{co}", fill=clad, universe=u_fuel)
+    m.cell(region=f"{co}", fill=water, universe=u_fuel)
+    m.cell(region=f"-{fo}", fill=water, universe=u_gt)
+    m.cell(region=f"{fo} -{co}", fill=clad, universe=u_gt)
+    m.cell(region=f"{co}", fill=water, universe=u_gt)
+
+
+def assembly_ce(n_grid=100000, mesh_dim=17, tallies=True, library=None):
+    """examples/assembly/assembly.py geometry (17 x 17 lattice, 25 guide tubes,
+    reflective box, pitch 21.42 cm) with synthetic nuclides of the same names,
+    no S(a,b); pin-wise mesh {flux, fission} tally (BASELINE.json config C3)."""
+    from . import nuclide as nd
+    m = Model()
+    fuel = m.material(name="Fuel", units="g/cm3", density=10.29769,
+                      components=[("U234", 4.4843e-6), ("U235", 5.5815e-4), ("U238", 2.2408e-2),
+                                  ("O16", 4.5829e-2)])
+    clad = m.material(name="Cladding", units="g/cm3", density=6.55,
+                      components=[("Zr90", 2.1827e-2), ("Zr91", 4.7600e-3), ("Zr92", 7.2758e-3),
+                                  ("Zr94", 7.3734e-3), ("Zr96", 1.1879e-3)])
+    water = m.material(name="Hot borated water", units="g/cm3", density=0.740582,
+                       components=[("H1", 4.9457e-2), ("O16", 2.4672e-2), ("B10", 8.0042e-6),
+                                   ("B11", 3.2218e-5)])
+    _pin_universes(m, fuel, clad, water, u_fuel=1, u_gt=2)
+    pitch = 21.42
+    univ = np.full((17, 17), 1)
+    for r, c in GUIDE_TUBES:
+        univ[r, c] = 2
+    lat = m.lattice(pitch=(pitch / 17, pitch / 17), lower_left=(-pitch / 2, -pitch / 2),
+                    universes=univ.tolist())
+    x0 = m.surface("x-plane", [-pitch / 2], "reflective").id
+    x1 = m.surface("x-plane", [pitch / 2], "reflective").id
+    y0 = m.surface("y-plane", [-pitch / 2], "reflective").id
+    y1 = m.surface("y-plane", [pitch / 2], "reflective").id
+    m.cell(region=f"{x0} -{x1} {y0} -{y1}", fill=lat, universe=0)
+    if tallies:
+        m.meshes = [Mesh(1, [mesh_dim, mesh_dim], [-pitch / 2, -pitch / 2], [pitch / 2, pitch / 2])]
+        m.filters = [Filter(1, "mesh", 1)]
+        m.tallies = [Tally(1, [1], ["flux", "fission"])]
+    if library is None:
+        library = nd.synthetic_library(ASSEMBLY_NUCLIDES, n_grid)
+    box = [-pitch / 2, -pitch / 2, -1, pitch / 2, pitch / 2, 1]
+    return m, library, box, True
+
+
+# ----------------------------------------------------------------------------
+# config C4: C5G7-style 2-D core, multigroup, lattices of lattices
+# ----------------------------------------------------------------------------
+def c5g7_core_library():
+    """UO2 / water: the literal C5G7 data above.  MOX (three enrichments), guide
+    tube and fission chamber sets are GENERATED from them by fixed scalings (the
+    benchmark's own tables are not in the reference tree): MOX raises thermal
+    absorption / fission and hardens chi slightly; the guide tube is water with
+    10 % less scattering; the fission chamber is a guide tube with a trace of
+    fission.  Synthetic, stated as such (BASELINE.json: 'generated by script')."""
+    lib = c5g7_library()
+    uo2 = lib.xsdatas["UO2"].data[294.0]
+    h2o = lib.xsdatas["LWTR"].data[294.0]
+
+    def fuel_like(name, k_abs, k_fis):
+        x = XSdata(name, 7)
+        x.order = 0
+        sc = np.array(uo2["scatter_matrix"])
+        ab = np.array(_UO2_ABS) * np.array([1.0, 1.0, 1.1, 1.2, k_abs, k_abs, k_abs])
+        fi = np.array(_UO2_FIS) * np.array([1.0, 1.0, 1.05, 1.1, k_fis, k_fis, k_fis])
+        nu = np.array(_UO2_NUFIS) / np.array(_UO2_FIS) * 1.17        # nu of Pu-bearing fuel
+        x.set_absorption(ab)
+        x.set_scatter_matrix(sc)
+        x.set_total(ab + sc.sum(axis=(1, 2)))
+        x.set_fission(fi)
+        x.set_nu_fission(fi * nu)
+        x.set_chi(_UO2_CHI)
+        return x
+
+    for name, ka, kf in (("MOX43", 2.0, 1.6), ("MOX70", 2.7, 2.2), ("MOX87", 3.1, 2.6)):
+        lib.add_xsdata(fuel_like(name, ka, kf))
+    gt = XSdata("GT", 7)
+    gt.order = 0
+    sc = np.array(h2o["scatter_matrix"]) * 0.9
+    gt.set_absorption(np.array(_H2O_ABS) * 0.9)
+    gt.set_scatter_matrix(sc)
+    gt.set_total(np.array(_H2O_ABS) * 0.9 + sc.sum(axis=(1, 2)))
+    lib.add_xsdata(gt)
+    fc = XSdata("FC", 7)
+    fc.order = 0
+    fis = np.array(_UO2_FIS) * 1.0e-6
+    fc.set_absorption(np.array(_H2O_ABS) * 0.9 + fis)
+    fc.set_scatter_matrix(sc)
+    fc.set_total(np.array(_H2O_ABS) * 0.9 + fis + sc.sum(axis=(1, 2)))
+    fc.set_fission(fis)
+    fc.set_nu_fission(fis * 2.5)
+    fc.set_chi(_UO2_CHI)
+    lib.add_xsdata(fc)
+    return lib
+
+
+def c5g7_core(mesh_dim=510, tallies=True):
+    """Quarter core: 2 x 2 fuel assemblies (UO2 / MOX checkerboard) + reflector,
+    each assembly a 17 x 17 pin lattice inside a 3 x 3 core lattice (3 coordinate
+    levels); reflective on the west / north faces, vacuum on the east / south ones;
+    fine mesh {flux, fission} tally (BASELINE.json config C4)."""
+    m = Model()
+    names = ["UO2", "MOX43", "MOX70", "MOX87", "GT", "FC", "LWTR"]
+    mats = {n: m.material(name=n, macroscopic=n, units="macro", density=1.0) for n in names}
+    r_pin = 0.54
+    cyl = m.surface("z-cylinder", [0.0, 0.0, r_pin]).id
+    pin_u = {}
+    for k, n in enumerate(["UO2", "MOX43", "MOX70", "MOX87", "GT", "FC"]):
+        u = 10 + k
+        pin_u[n] = u
+        m.cell(region=f"-{cyl}", fill=mats[n], universe=u)
+        m.cell(region=f"{cyl}", fill=mats["LWTR"], universe=u)
+    u_water = 20
+    m.cell(region="", fill=mats["LWTR"], universe=u_water)     # infinite water cell
+    pitch = 1.26
+    w = 17 * pitch
+
+    def assembly(kind):
+        a = np.full((17, 17), pin_u["UO2"])
+        if kind == "MOX":      # enrichment zoning: 4.3 % rim, 7.0 % next ring, 8.7 % interior
+            a[:, :] = pin_u["MOX87"]
+            a[1:-1, 1:-1][[0, -1], :] = pin_u["MOX70"]
+            a[1:-1, 1:-1][:, [0, -1]] = pin_u["MOX70"]
+            a[[0, -1], :] = pin_u["MOX43"]
+            a[:, [0, -1]] = pin_u["MOX43"]
+        for r, c in GUIDE_TUBES:
+            a[r, c] = pin_u["GT"]
+        a[8, 8] = pin_u["FC"]
+        return a.tolist()
+
+    u_asm = {}
+    for k, kind in enumerate(("UO2", "MOX")):
+        lat = m.lattice(pitch=(pitch, pitch), lower_left=(-w / 2, -w / 2), universes=assembly(kind))
+        u = 30 + k
+        u_asm[kind] = u
+        m.cell(region="", fill=lat, universe=u)
+    core = m.lattice(pitch=(w, w), lower_left=(0.0, -3 * w),
+                     universes=[[u_asm["UO2"], u_asm["MOX"], u_water],
+                                [u_asm["MOX"], u_asm["UO2"], u_water],
+                                [u_water, u_water, u_water]])
+    x0 = m.surface("x-plane", [0.0], "reflective").id
+    x1 = m.surface("x-plane", [3 * w], "vacuum").id
+    y0 = m.surface("y-plane", [-3 * w], "vacuum").id
+    y1 = m.surface("y-plane", [0.0], "reflective").id
+    m.cell(region=f"{x0} -{x1} {y0} -{y1}", fill=core, universe=0)
+    m.settings["legendre_to_tabular"] = True
+    if tallies:
+        m.meshes = [Mesh(1, [mesh_dim, mesh_dim], [0.0, -3 * w], [3 * w, 0.0])]
+        m.filters = [Filter(1, "mesh", 1)]
+        m.tallies = [Tally(1, [1], ["flux", "fission"])]
+    box = [0.0, -2 * w, -1, 2 * w, 0.0, 1]
+    return m, c5g7_core_library(), box, True

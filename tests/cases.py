@@ -90,3 +90,35 @@ def load_model_npz(path):
     z = np.load(path)
     types = abi.model_field_types()
     return abi.ModelHandle({k: (z[k] if types[k][1] else z[k].item()) for k in z.files})
+
+
+def build_lattice(name):
+    """lattice configurations: 'assembly' = config C3 (17 x 17, CE, 2 levels),
+    'c5g7' = config C4 (lattice of lattices, MG, 3 levels); small grids / meshes"""
+    from openmc_b200 import nuclide
+    key = ("lattice", name)
+    if key not in _CE_CACHE:
+        if name == "assembly":
+            m, libx, box, of = examples.assembly_ce(n_grid=2000)
+            _CE_CACHE[key] = (nuclide.build_ce_model(m, libx), box, of)
+        else:
+            m, lib, box, of = examples.c5g7_core(mesh_dim=51)
+            _CE_CACHE[key] = (mgxs.build_mg_model(m, lib), box, of)
+    return _CE_CACHE[key]
+
+
+def geometry_probe_points(box, n, seed=4, margin=0.05):
+    """random points / directions over the source box (a little beyond it), plus
+    points placed exactly on lattice / pin-cell boundaries (coincidence rules)"""
+    import numpy as np
+    g = np.random.default_rng(seed)
+    box = np.asarray(box, float)
+    lo, hi = box[:3] - margin * (box[3:] - box[:3]), box[3:] + margin * (box[3:] - box[:3])
+    xyz = lo + g.uniform(size=(n, 3)) * (hi - lo)
+    uvw = g.normal(size=(n, 3))
+    uvw /= np.linalg.norm(uvw, axis=1)[:, None]
+    k = n // 10
+    pitch = 1.26
+    xyz[:k, 0] = np.round(xyz[:k, 0] / pitch) * pitch          # on x lattice planes
+    xyz[k:2 * k, 1] = np.round(xyz[k:2 * k, 1] / pitch) * pitch  # on y lattice planes
+    return xyz, uvw

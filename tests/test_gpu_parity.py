@@ -151,3 +151,76 @@ def test_ce_eigenvalue_statistics(gpu_engine):
         assert np.all(np.abs(z[ok]) < 5.0), np.abs(z[ok]).max()
         assert np.mean(z[ok] ** 2) < 2.5
     sim.simulation_finalize()
+
+
+# ------------------------------------------------------------------------------
+# lattices (configs C3 / C4)
+# ------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["assembly", "c5g7"])
+def test_lattice_geometry_bit_exact(gpu_engine, name):
+    """cell / instance / material / level, crossing surface tokens and lattice
+    translations bit-exact on 2- and 3-level lattice geometry, incl. points placed
+    on lattice planes; distances to 1e-12"""
+    model, box, of = cases.build_lattice(name)
+    o = Oracle(model)
+    gpu_engine.init(model, 0, 200000)
+    xyz, uvw = cases.geometry_probe_points(box, 200000)
+    for a, b in zip(gpu_engine.find_cell(xyz, uvw), o.find_cell(xyz, uvw)):
+        assert np.array_equal(a, b)
+    dg, sg, lg, tg = gpu_engine.distance_to_boundary(xyz, uvw)
+    do, so, lo_, to = o.distance_to_boundary(xyz, uvw)
+    assert np.array_equal(sg, so) and np.array_equal(lg, lo_) and np.array_equal(tg, to)
+    np.testing.assert_allclose(dg, do, rtol=1e-12)
+    gpu_engine.finalize()
+
+
+@pytest.mark.parametrize("threshold", ["0", "16384"])
+def test_c5g7_generation_matches_oracle(gpu_engine, threshold, monkeypatch):
+    """lattice-of-lattices MG core: same sorted fission bank as the oracle"""
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)
+    model, box, of = cases.build_lattice("c5g7")
+    o = Oracle(model)
+    n = 20000
+    src = o.sample_initial_source(n, box, of)
+    gpu_engine.init(model, 0, n)
+    gi = gpu_engine.gen_in(n, 0, 0, 1.0, True)
+    fb, out = gpu_engine.transport_generation(gi, src)
+    fb_o, out_o = o.transport_generation(gi, src)
+    assert out.n_lost == 0
+    # a last-ulp libm difference may flip a rare discrete decision
+    assert abs(out.n_fission - out_o.n_fission) <= 5
+    assert abs(out.n_events - out_o.n_events) <= 1e-4 * out_o.n_events
+    np.testing.assert_allclose(out.global_tally[:], out_o.global_tally[:], rtol=1e-4)
+    if out.n_fission == out_o.n_fission:
+        same = np.mean(fb["parent_id"] == fb_o["parent_id"])
+        assert same > 0.99
+    m = int(model["tally_result_ofs"][1])
+    v = np.zeros(m); gpu_engine.tally_results(0, v)
+    vo = o.tally_results(0, m)
+    assert abs(v.sum() - vo.sum()) < 1e-4 * vo.sum()
+    gpu_engine.finalize()
+
+
+def test_assembly_eigenvalue_statistics(gpu_engine):
+    """config C3 (17 x 17 CE assembly): k within 3 combined sigma of the oracle,
+    pin-mesh tallies pass a z-test"""
+    model, box, of = cases.build_lattice("assembly")
+    o = Oracle(model)
+    n, nb, ni = 4000, 12, 4
+    src = o.sample_initial_source(n, box, of)
+    r = o.run_eigenvalue(src, nb, ni, master_seed=1)
+    sim = lib.Simulation(gpu_engine, model, n, nb, ni, src, seed=777)
+    k = sim.run()
+    assert sim.stats["n_lost"] == 0
+    sig = np.hypot(k[1], r["k_combined"][1])
+    assert abs(k[0] - r["k_combined"][0]) < 3 * sig, (k, r["k_combined"])
+    nreal = nb - ni
+    mean_g, std_g = sim.tally_mean_std(0)
+    hi = int(model["tally_result_ofs"][1])
+    mean_o = r["tally_sum"][:hi] / nreal
+    var_o = np.maximum(r["tally_sum_sq"][:hi] / nreal - mean_o ** 2, 0) / (nreal - 1)
+    z = (mean_g.ravel() - mean_o) / np.sqrt(std_g.ravel() ** 2 + var_o + 1e-300)
+    ok = np.isfinite(z) & (mean_o > 0)
+    assert np.all(np.abs(z[ok]) < 5.0), np.abs(z[ok]).max()
+    assert np.mean(z[ok] ** 2) < 2.5
+    sim.simulation_finalize()
