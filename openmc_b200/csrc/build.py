@@ -28,6 +28,20 @@ def stale():
     return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SOURCES + HEADERS)
 
 
+def build_variant(name, defines):
+    """experiment builds (openmc_b200/csrc/variants/<name>.so), selected with OMCGPU_LIB"""
+    out = os.path.join(HERE, "variants", name + ".so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out] + \
+          [os.path.join(HERE, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed")
+    return out
+
+
 def build(force=False, verbose=False):
     if not (force or stale()):
         return LIB

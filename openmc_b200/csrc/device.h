@@ -905,23 +905,159 @@ OMC_HD double ce_reaction_xs(int rx, const MicroXS& micro)
   return (1.0 - micro.interp_factor) * ld(v) + micro.interp_factor * ld(v + 1);
 }
 
-// Material::calculate_neutron_xs: out[4] = total, absorption, fission, nu-fission
+// Material::calculate_neutron_xs: out[4] = total, absorption, fission, nu-fission.
+//
+// The reference walks the nuclides one after another; each walk is a chain of
+// dependent gathers (hash pair -> ~4 search probes -> energy pair -> two xs
+// rows), so one lane would have a single load in flight.  Here XS_BATCH
+// nuclides advance through that chain in lockstep -- the loads of one stage are
+// independent across the batch and overlap -- and the partial sums are then
+// added in nuclide order, so every sum sees the same operands in the same order
+// as the reference (results are bit-identical to the one-at-a-time walk).
+constexpr int XS_BATCH = 4;
+
 OMC_HD void ce_macro_xs(int m, double E, double& t, double& a, double& f, double& nf,
   int32_t* i_grid_out, int max_nuc)
 {
   t = a = f = nf = 0.0;
   const int i_log = ce_log_index(E);
   const int k0 = ld(DM.mat_nuc_ofs + m), k1 = ld(DM.mat_nuc_ofs + m + 1);
-  for (int k = k0; k < k1; ++k) {
-    MicroXS micro;
-    ce_micro_xs(ld(DM.mat_nuclide + k), i_log, E, micro);
-    const double atom_density = ld(DM.mat_atom_density + k);
-    t += atom_density * micro.total;
-    a += atom_density * micro.absorption;
-    f += atom_density * micro.fission;
-    nf += atom_density * micro.nu_fission;
-    if (i_grid_out && (k - k0) < max_nuc)
-      i_grid_out[k - k0] = micro.index_grid;
+  const int n_bins1 = DM.n_log_bins + 1;
+  for (int kb = k0; kb < k1; kb += XS_BATCH) {
+    int nuc[XS_BATCH];
+    const double* energy[XS_BATCH];
+    int64_t g0[XS_BATCH];
+    int lo[XS_BATCH], len[XS_BATCH], base[XS_BATCH], i_grid[XS_BATCH];
+    bool live[XS_BATCH], first_hit[XS_BATCH];
+    // stage 1: which nuclides, where their grids start
+#pragma unroll
+    for (int j = 0; j < XS_BATCH; ++j) {
+      live[j] = kb + j < k1;
+      nuc[j] = ld(DM.mat_nuclide + (live[j] ? kb + j : kb));
+    }
+    int n_grid[XS_BATCH];
+#pragma unroll
+    for (int j = 0; j < XS_BATCH; ++j) {
+      g0[j] = ld(DM.nuc_grid_ofs + nuc[j]);
+      n_grid[j] = (int)(ld(DM.nuc_grid_ofs + nuc[j] + 1) - g0[j]);
+      energy[j] = DM.nuc_energy + g0[j];
+    }
+    // stage 2: grid ends (clipping, src/nuclide.cpp:725-728) and the hash window (:732-737)
+    double e_first[XS_BATCH], e_last[XS_BATCH];
+    int i_low[XS_BATCH], i_high[XS_BATCH];
+#pragma unroll
+    for (int j = 0; j < XS_BATCH; ++j) {
+      e_first[j] = ld(energy[j]);
+      e_last[j] = ld(energy[j] + n_grid[j] - 1);
+      const int32_t* gi = DM.nuc_grid_index + (int64_t)nuc[j] * n_bins1 + i_log;
+      i_low[j] = ld(gi);
+      i_high[j] = ld(gi + 1) + 1;
+    }
+    double e_window0[XS_BATCH];
+#pragma unroll
+    for (int j = 0; j < XS_BATCH; ++j)
+      e_window0[j] = ld(energy[j] + i_low[j]);
+#pragma unroll
+    for (int j = 0; j < XS_BATCH; ++j) {
+      base[j] = i_low[j];
+      lo[j] = 0;
+      len[j] = i_high[j] - i_low[j];
+      first_hit[j] = false;
+      i_grid[j] = 0;
+      if (E < e_first[j]) {
+        len[j] = 0;
+        base[j] = -1; // i_grid = 0
+      } else if (E > e_last[j]) {
+        len[j] = 0;
+        base[j] = -2; // i_grid = n_grid - 2
+      } else if (e_window0[j] == E) { // lower_bound_index: a[0] == value -> 0
+        len[j] = 0;
+        first_hit[j] = true;
+      }
+    }
+    // stage 3: std::lower_bound over the window, all nuclides of the batch in step
+    bool any = true;
+    while (any) {
+      any = false;
+      double probe[XS_BATCH];
+#pragma unroll
+      for (int j = 0; j < XS_BATCH; ++j)
+        if (len[j] > 0)
+          probe[j] = ld(energy[j] + base[j] + lo[j] + (len[j] >> 1));
+#pragma unroll
+      for (int j = 0; j < XS_BATCH; ++j)
+        if (len[j] > 0) {
+          const int half = len[j] >> 1;
+          if (probe[j] < E) {
+            lo[j] += half + 1;
+            len[j] -= half + 1;
+          } else {
+            len[j] = half;
+          }
+          any = any || len[j] > 0;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < XS_BATCH; ++j) {
+      if (base[j] == -1)
+        i_grid[j] = 0;
+      else if (base[j] == -2)
+        i_grid[j] = n_grid[j] - 2;
+      else
+        i_grid[j] = first_hit[j] ? i_low[j] : i_low[j] + lo[j] - 1;
+    }
+    // stage 4: bracketing energies (+ duplicate-point bump, :741-742)
+    double e0[XS_BATCH], e1[XS_BATCH];
+#pragma unroll
+    for (int j = 0; j < XS_BATCH; ++j) {
+      e0[j] = ld(energy[j] + i_grid[j]);
+      e1[j] = ld(energy[j] + i_grid[j] + 1);
+    }
+#pragma unroll
+    for (int j = 0; j < XS_BATCH; ++j)
+      if (e0[j] == e1[j]) {
+        ++i_grid[j];
+        e0[j] = e1[j];
+        e1[j] = ld(energy[j] + i_grid[j] + 1);
+      }
+    // stage 5: the two xs rows (two adjacent 32-byte sectors), density, fissionable flag
+    double ra[XS_BATCH][4], rb[XS_BATCH][4], rho[XS_BATCH];
+    int fis[XS_BATCH];
+#pragma unroll
+    for (int j = 0; j < XS_BATCH; ++j) {
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+      const double2* row = reinterpret_cast<const double2*>(DM.nuc_xs) + 2 * (g0[j] + i_grid[j]);
+      const double2 a01 = __ldg(row), a23 = __ldg(row + 1), b01 = __ldg(row + 2), b23 = __ldg(row + 3);
+      ra[j][0] = a01.x; ra[j][1] = a01.y; ra[j][2] = a23.x; ra[j][3] = a23.y;
+      rb[j][0] = b01.x; rb[j][1] = b01.y; rb[j][2] = b23.x; rb[j][3] = b23.y;
+#else
+      const double* row = DM.nuc_xs + 4 * (g0[j] + i_grid[j]);
+      for (int c = 0; c < 4; ++c) {
+        ra[j][c] = row[c];
+        rb[j][c] = row[4 + c];
+      }
+#endif
+      rho[j] = ld(DM.mat_atom_density + (live[j] ? kb + j : kb));
+      fis[j] = ld(DM.nuc_fissionable + nuc[j]);
+    }
+    // accumulate in nuclide order (src/material.cpp:893-899)
+#pragma unroll
+    for (int j = 0; j < XS_BATCH; ++j) {
+      if (!live[j])
+        continue;
+      const double fr = (E - e0[j]) / (e1[j] - e0[j]);
+      t += rho[j] * ((1.0 - fr) * ra[j][0] + fr * rb[j][0]);
+      a += rho[j] * ((1.0 - fr) * ra[j][1] + fr * rb[j][1]);
+      if (fis[j]) {
+        f += rho[j] * ((1.0 - fr) * ra[j][2] + fr * rb[j][2]);
+        nf += rho[j] * ((1.0 - fr) * ra[j][3] + fr * rb[j][3]);
+      } else {
+        f += rho[j] * 0.0;
+        nf += rho[j] * 0.0;
+      }
+      if (i_grid_out && (kb + j - k0) < max_nuc)
+        i_grid_out[kb + j - k0] = i_grid[j];
+    }
   }
 }
 

@@ -42,13 +42,14 @@ constexpr int BLOCK = 256;
 static int64_t g_launches = 0;
 
 #if OMC_CUDA
-#define OMC_KERNEL(name, ArgT, body) \
-  __global__ void __launch_bounds__(BLOCK) name(int64_t n_ub, ArgT a) \
+#define OMC_KERNEL_MB(name, ArgT, body, MINBLOCKS) \
+  __global__ void __launch_bounds__(BLOCK, MINBLOCKS) name(int64_t n_ub, ArgT a) \
   { \
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; \
     if (tid < n_ub) \
       body(tid, a); \
   }
+#define OMC_KERNEL(name, ArgT, body) OMC_KERNEL_MB(name, ArgT, body, 1)
 #define OMC_LAUNCH(name, n_ub, stream, args) \
   do { \
     if ((n_ub) > 0) { \
@@ -57,6 +58,7 @@ static int64_t g_launches = 0;
     } \
   } while (0)
 #else
+#define OMC_KERNEL_MB(name, ArgT, body, MINBLOCKS) OMC_KERNEL(name, ArgT, body)
 #define OMC_KERNEL(name, ArgT, body) \
   void name(int64_t n_ub, ArgT a) \
   { \
@@ -478,7 +480,7 @@ OMC_D void body_xs(int64_t tid, const EvArgs& a)
     return;
   ev_xs(a.ps, a.q_in.idx[tid]);
 }
-OMC_KERNEL(k_xs, EvArgs, body_xs)
+OMC_KERNEL_MB(k_xs, EvArgs, body_xs, 2)
 
 OMC_D void body_advance(int64_t tid, const EvArgs& a)
 {
@@ -505,6 +507,9 @@ OMC_KERNEL(k_advance, EvArgs, body_advance)
 // so a warp's work is the sum of its flights' cells, not 32 x the longest one.
 // -----------------------------------------------------------------------------
 constexpr int SCORE_NVAL = OMCGPU_MAX_SCORES;
+#ifndef SCORE_MINBLOCKS
+#define SCORE_MINBLOCKS 2 /* resident blocks per SM the register budget of k_score allows */
+#endif
 
 struct PartEmit { // simple tally: one bin per non-mesh filter -> base index
   double* results;
@@ -669,7 +674,7 @@ __device__ __noinline__ int score_lane(int64_t j, int buf, int t, double* values
   return nc;
 }
 
-__global__ void __launch_bounds__(BLOCK, 2) k_score(int64_t n_ub, EvArgs a)
+__global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, EvArgs a)
 {
   constexpr int WARPS = BLOCK / 32;
   __shared__ double s_d[WARPS][7 + SCORE_NVAL][32]; // r0, u, total, val[]
@@ -969,7 +974,7 @@ OMC_D void body_probe_xs(int64_t tid, const XsArgs& a)
   a.out[4 * tid + 3] = nf;
 #endif
 }
-OMC_KERNEL(k_probe_xs, XsArgs, body_probe_xs)
+OMC_KERNEL_MB(k_probe_xs, XsArgs, body_probe_xs, 2)
 
 struct GeoArgs {
   PState ps;

@@ -26,7 +26,7 @@ import numpy as np
 from . import _abi as abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(_HERE, "csrc", "libomcgpu.so")
+DEFAULT_LIB = os.environ.get("OMCGPU_LIB") or os.path.join(_HERE, "csrc", "libomcgpu.so")
 
 DEFAULT_SEED = 1            # include/openmc/random_lcg.h:17
 DEFAULT_STRIDE = 152917     # include/openmc/random_lcg.h:18
