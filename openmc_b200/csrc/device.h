@@ -914,7 +914,11 @@ OMC_HD double ce_reaction_xs(int rx, const MicroXS& micro)
 // independent across the batch and overlap -- and the partial sums are then
 // added in nuclide order, so every sum sees the same operands in the same order
 // as the reference (results are bit-identical to the one-at-a-time walk).
-constexpr int XS_BATCH = 4;
+#ifndef OMC_XS_BATCH
+#define OMC_XS_BATCH 1 /* measured on C2 (3-5 nuclides per material, L2-resident data): batching costs
+                          more in occupancy (139 vs 46 registers) than it gains; see profiles/README.md */
+#endif
+constexpr int XS_BATCH = OMC_XS_BATCH;
 
 OMC_HD void ce_macro_xs(int m, double E, double& t, double& a, double& f, double& nf,
   int32_t* i_grid_out, int max_nuc)

@@ -100,6 +100,7 @@ struct EvArgs {
   Queue q_in, q_a, q_b; // input list, and up to two output lists
   Flights fl;           // flight records for k_score
   int32_t fl_buf;       // which of the two record buffers `fl` is (c_fl[fl_buf])
+  const int32_t* n_flights; // device count of records (its ring slot outlives the sweep)
 };
 
 enum { NEXT_DEAD = -1, NEXT_COLLISION = 0, NEXT_SURFACE = 1 };
@@ -682,7 +683,8 @@ __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, 
   __shared__ int s_incl[WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = tid < n_ub; // the host passes the exact number of records
+  const int64_t n = *a.n_flights < a.fl.cap ? *a.n_flights : a.fl.cap;
+  const bool active = tid < n;
   for (int t = 0; t < DM.n_tallies; ++t) {
     __syncwarp(); // lanes leave the part loop of the previous tally at different times
     int nc = 0;
@@ -736,7 +738,8 @@ __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, 
 // host compile (tests only): same preparation, same parts, traced one after another
 void k_score(int64_t n_ub, EvArgs a)
 {
-  for (int64_t tid = 0; tid < n_ub; ++tid) {
+  const int64_t n = *a.n_flights < a.fl.cap ? *a.n_flights : a.fl.cap;
+  for (int64_t tid = 0; tid < n_ub && tid < n; ++tid) {
     const Flight f = load_flight(a.fl, tid);
     for (int t = 0; t < DM.n_tallies; ++t) {
       PartEmit em;
@@ -1070,6 +1073,10 @@ static int fail(int code, const char* fmt, const char* detail = "")
       return fail(OMCGPU_E_CUDA, "CUDA error: %s", cudaGetErrorString(e_)); \
   } while (0)
 
+constexpr int RING = 32;              // sweeps whose counters stay readable
+constexpr int RING_OFS = 8;           // d_counts: [0] alive after k_init, [4] fission sites, [5] lost, [6] tail flight log
+constexpr int N_COUNTS = RING_OFS + 4 * RING;
+
 struct Engine {
   bool ready = false;
   omcgpu_model hm;            // scalars + DEVICE pointers
@@ -1101,7 +1108,9 @@ struct Engine {
   double* d_tally = nullptr;
   int64_t n_tally = 0;
   cudaStream_t stream = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evx0 = nullptr, evx1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evx0[RING] = {}, evx1[RING] = {}, evp0 = nullptr, evp1 = nullptr;
+  int64_t sync_every = 8;       // sweeps the host lets run between two counter read-backs
   int64_t tail_threshold = 16384;
   int score_part = 8;
   int64_t id_offset_last = 0;
@@ -1405,7 +1414,7 @@ static EvArgs make_args(const omcgpu_gen_in* in)
 
 static int read_counts()
 {
-  CUDA_OK(cudaMemcpyAsync(G.h_counts, G.d_counts, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaMemcpyAsync(G.h_counts, G.d_counts, N_COUNTS * sizeof(int32_t), cudaMemcpyDeviceToHost, G.stream));
   CUDA_OK(cudaStreamSynchronize(G.stream));
   return 0;
 }
@@ -1439,17 +1448,25 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
   if (n > G.cap || n > G.n_src)
     return fail(OMCGPU_E_OUT_OF_BOUNDS, "n_particles exceeds the source bank / capacity%s");
   std::memset(out, 0, sizeof(*out));
-  CUDA_OK(cudaMemsetAsync(G.d_counts, 0, 8 * sizeof(int32_t), G.stream));
+  CUDA_OK(cudaMemsetAsync(G.d_counts, 0, N_COUNTS * sizeof(int32_t), G.stream));
   CUDA_OK(cudaMemsetAsync(G.d_counters, 0, 4 * sizeof(unsigned long long), G.stream));
   CUDA_OK(cudaEventRecord(G.ev0, G.stream));
   EvArgs a = make_args(in);
-  int cur = 0; // queue roles: q[cur] = xs/advance list, q[2] collision, q[3] surface, q[1-cur] next
+  // Work lists: q[0] / q[1] alternate as "alive" list (input of k_xs / k_advance)
+  // and "next" list; q[2] collisions, q[3] crossings.  Their COUNTERS come from a
+  // ring with one slot {collision, crossing, next} per sweep, so that the host
+  // can let several sweeps run ahead without reading anything back: a kernel
+  // always finds its input count in device memory, launched over the last count
+  // the host knows (counts never grow within a generation).
+  int cur = 0;
   a.q_a = G.q[cur];
+  a.q_a.count = G.d_counts + 0;
   OMC_LAUNCH(k_init, n, G.stream, a);
   int rc = read_counts();
   if (rc)
     return rc;
-  int64_t n_alive = G.h_counts[cur];
+  int64_t n_alive = G.h_counts[0]; // last count read back: upper bound of the lists
+  int32_t* alive_count = G.d_counts + 0;
   int64_t n_xs = 0, n_coll = 0, n_cross = 0;
   double ms_xs = 0.0;
   const bool score = in->tallies_active && G.hm.n_tallies > 0;
@@ -1461,38 +1478,26 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
   cudaStream_t st_surf = G.overlap ? G.s_surf : G.stream;
   cudaStream_t st_coll = G.overlap ? G.s_coll : G.stream;
   bool score_pending[2] = {false, false};
-  int64_t sweep = 0;
-  while (n_alive > 0) {
-    if (n_alive <= G.tail_threshold) {
-      for (int b = 0; b < 2; ++b)
-        if (score_pending[b] && G.overlap)
-          CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_score[b], 0));
-      score_pending[0] = score_pending[1] = false;
-      a.q_in = G.q[cur];
-      a.fl = G.fl[0];
-      a.fl_buf = 0;
-      LAUNCH_TAIL(n_alive, G.stream, a);
-      if (score && !G.tally_needs_cells) {
-        rc = read_counts(); // flights the tail logged
-        if (rc)
-          return rc;
-        LAUNCH_SCORE(std::min<int64_t>(G.h_counts[6], G.fl[0].cap), G.stream, a);
-      }
-      break;
-    }
+  int64_t sweep = 0, synced = 0; // sweeps issued / sweeps whose counters the host has read
+  int64_t n_in_first = n_alive;  // input count of sweep `synced`
+  while (n_alive > 0 && n_alive > G.tail_threshold) {
     const int nxt = 1 - cur;
     const int buf = (int)(sweep & 1);
-    // zero the three output counters (collision, surface, next)
-    CUDA_OK(cudaMemsetAsync(G.d_counts + nxt, 0, sizeof(int32_t), G.stream));
-    CUDA_OK(cudaMemsetAsync(G.d_counts + 2, 0, 2 * sizeof(int32_t), G.stream));
+    int32_t* slot = G.d_counts + RING_OFS + 4 * (sweep % RING);
+    CUDA_OK(cudaMemsetAsync(slot, 0, 4 * sizeof(int32_t), G.stream));
     a.q_in = G.q[cur];
-    CUDA_OK(cudaEventRecord(G.evx0, G.stream));
+    a.q_in.count = alive_count;
+    const int ev = (int)(sweep % RING);
+    CUDA_OK(cudaEventRecord(G.evx0[ev], G.stream));
     OMC_LAUNCH(k_xs, n_alive, G.stream, a);
-    CUDA_OK(cudaEventRecord(G.evx1, G.stream));
+    CUDA_OK(cudaEventRecord(G.evx1[ev], G.stream));
     a.q_a = G.q[2];
+    a.q_a.count = slot + 0;
     a.q_b = G.q[3];
+    a.q_b.count = slot + 1;
     a.fl = G.fl[buf];
     a.fl_buf = buf;
+    a.n_flights = alive_count;
     if (score && score_pending[buf] && G.overlap) // records of sweep-2 must have been consumed
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_score[buf], 0));
     OMC_LAUNCH(k_advance, n_alive, G.stream, a);
@@ -1513,11 +1518,14 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
       }
     }
     a.q_in = G.q[3];
+    a.q_in.count = slot + 1;
     a.q_a = G.q[nxt];
+    a.q_a.count = slot + 2;
     if (G.overlap)
       CUDA_OK(cudaStreamWaitEvent(st_surf, G.e_adv, 0));
     OMC_LAUNCH(k_surface, n_alive, st_surf, a);
     a.q_in = G.q[2];
+    a.q_in.count = slot + 0;
     if (G.overlap) {
       CUDA_OK(cudaEventRecord(G.e_surf, st_surf));
       CUDA_OK(cudaStreamWaitEvent(st_coll, G.e_adv, 0));
@@ -1528,22 +1536,49 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_surf, 0));
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_coll, 0));
     }
+    alive_count = slot + 2;
+    cur = nxt;
+    ++sweep;
+    // read the counters back every SYNC_EVERY sweeps (and account for the sweeps since)
+    if (sweep - synced >= G.sync_every) {
+      rc = read_counts();
+      if (rc)
+        return rc;
+      for (; synced < sweep; ++synced) {
+        const int32_t* h = G.h_counts + RING_OFS + 4 * (synced % RING);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, G.evx0[synced % RING], G.evx1[synced % RING]);
+        ms_xs += ms;
+        n_xs += n_in_first;
+        n_coll += h[0];
+        n_cross += h[1];
+        n_in_first = h[2];
+      }
+      n_alive = n_in_first;
+    }
+  }
+  if (synced < sweep) { // cannot happen with the loop above, kept for safety
     rc = read_counts();
     if (rc)
       return rc;
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, G.evx0, G.evx1);
-    ms_xs += ms;
-    n_xs += n_alive;
-    n_coll += G.h_counts[2];
-    n_cross += G.h_counts[3];
-    n_alive = G.h_counts[nxt];
-    cur = nxt;
-    ++sweep;
   }
   for (int b = 0; b < 2; ++b)
     if (score_pending[b] && G.overlap)
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_score[b], 0));
+  if (n_alive > 0) { // the tail: one lane per remaining history
+    a.q_in = G.q[cur];
+    a.q_in.count = alive_count;
+    a.fl = G.fl[0];
+    a.fl_buf = 0;
+    LAUNCH_TAIL(n_alive, G.stream, a);
+    if (score && !G.tally_needs_cells) {
+      rc = read_counts(); // flights the tail logged
+      if (rc)
+        return rc;
+      a.n_flights = G.fl[0].count;
+      LAUNCH_SCORE(std::min<int64_t>(G.h_counts[6], G.fl[0].cap), G.stream, a);
+    }
+  }
   // death: deterministic reduction of the per-particle accumulators
   ReduceArgs r;
   r.ps = G.ps;
@@ -1625,8 +1660,12 @@ int omcgpu_finalize(void)
   if (G.ev0) {
     cudaEventDestroy(G.ev0);
     cudaEventDestroy(G.ev1);
-    cudaEventDestroy(G.evx0);
-    cudaEventDestroy(G.evx1);
+    for (int k = 0; k < RING; ++k) {
+      cudaEventDestroy(G.evx0[k]);
+      cudaEventDestroy(G.evx1[k]);
+    }
+    cudaEventDestroy(G.evp0);
+    cudaEventDestroy(G.evp1);
     cudaEventDestroy(G.e_adv);
     cudaEventDestroy(G.e_surf);
     cudaEventDestroy(G.e_coll);
@@ -1715,7 +1754,7 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   rc = rc ? rc : alloc_bank(G.src, cap);
   rc = rc ? rc : alloc_bank(G.fis, G.fis_cap);
   rc = rc ? rc : alloc_bank(G.fis_sorted, G.fis_cap);
-  rc = rc ? rc : dev_alloc(&G.d_counts, 8);
+  rc = rc ? rc : dev_alloc(&G.d_counts, N_COUNTS);
   rc = rc ? rc : dev_alloc(&G.d_counters, 4);
   for (int k = 0; k < 4; ++k) {
     rc = rc ? rc : dev_alloc(&G.q[k].idx, cap);
@@ -1761,14 +1800,20 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   CUDA_OK(cudaMemcpyToSymbol(c_ps, &G.ps, sizeof(PState)));
   CUDA_OK(cudaMemcpyToSymbol(c_fl, G.fl, 2 * sizeof(Flights)));
 #endif
-  CUDA_OK(cudaMallocHost((void**)&G.h_counts, 8 * sizeof(int32_t)));
+  CUDA_OK(cudaMallocHost((void**)&G.h_counts, N_COUNTS * sizeof(int32_t)));
   CUDA_OK(cudaMallocHost((void**)&G.h_counters, 4 * sizeof(unsigned long long)));
   CUDA_OK(cudaMallocHost((void**)&G.h_partial, G.n_chunks * 6 * sizeof(double)));
   CUDA_OK(cudaMallocHost((void**)&G.h_aos, G.fis_cap * sizeof(omcgpu_site)));
   CUDA_OK(cudaEventCreate(&G.ev0));
   CUDA_OK(cudaEventCreate(&G.ev1));
-  CUDA_OK(cudaEventCreate(&G.evx0));
-  CUDA_OK(cudaEventCreate(&G.evx1));
+  for (int k = 0; k < RING; ++k) {
+    CUDA_OK(cudaEventCreate(&G.evx0[k]));
+    CUDA_OK(cudaEventCreate(&G.evx1[k]));
+  }
+  CUDA_OK(cudaEventCreate(&G.evp0));
+  CUDA_OK(cudaEventCreate(&G.evp1));
+  if (const char* t = std::getenv("OMCGPU_SYNC_EVERY"))
+    G.sync_every = std::min<int64_t>(std::max<int64_t>(1, std::atoll(t)), RING / 2);
   CUDA_OK(cudaEventCreateWithFlags(&G.e_adv, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&G.e_surf, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&G.e_coll, cudaEventDisableTiming));
@@ -1975,12 +2020,12 @@ int omcgpu_calculate_xs_device(const double* E, const int32_t* material, int64_t
     return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
   XsArgs a;
   a.E = E; a.material = material; a.n = n; a.out = out; a.i_grid = nullptr; a.max_nuc = 0;
-  CUDA_OK(cudaEventRecord(G.evx0, G.stream));
+  CUDA_OK(cudaEventRecord(G.evp0, G.stream));
   OMC_LAUNCH(k_probe_xs, n, G.stream, a);
-  CUDA_OK(cudaEventRecord(G.evx1, G.stream));
+  CUDA_OK(cudaEventRecord(G.evp1, G.stream));
   CUDA_OK(cudaStreamSynchronize(G.stream));
   if (ms)
-    cudaEventElapsedTime(ms, G.evx0, G.evx1);
+    cudaEventElapsedTime(ms, G.evp0, G.evp1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return fail(OMCGPU_E_CUDA, "kernel failure: %s", cudaGetErrorString(e));
