@@ -1572,7 +1572,7 @@ OMC_HD int mesh_index(double r, double ll, double w)
 // with the pair that straddles a cut emitted as two pieces.
 // emit(bin, w): w = fraction of `total` spent in mesh bin `bin`.
 template<class Emit>
-OMC_D void mesh_march(int m, V3 r0, V3 u, double total, double t0, double t1, Emit& emit)
+OMC_D void mesh_march_exact(int m, V3 r0, V3 u, double total, double t0, double t1, Emit& emit)
 {
   const int nd = ld(DM.mesh_ndim + m);
   MeshAxis a0, a1, a2;
@@ -1680,6 +1680,94 @@ OMC_D void mesh_march(int m, V3 r0, V3 u, double total, double t0, double t1, Em
   }
 #undef MESH_OUT
 #undef MESH_BIN
+}
+
+// The same ray trace as a DDA (Amanatides & Woo) for a part that starts INSIDE
+// the mesh -- the case of every flight when the mesh covers the geometry.  The
+// first crossing of each axis uses the reference's formula; the j-th one after it
+// is tmax0 + j * (w / |u|) instead of a fresh division, and a length fraction is
+// (length * 1/total).  Crossing distances therefore differ from the reference's
+// by a few ulp (never accumulating: j multiplies, it is not a running sum), i.e.
+// bin sequences are the same and segment lengths agree to ~1e-14 relative; tally
+// sums are not bit-reproducible in the reference either (atomic order).  A part
+// that starts outside the mesh takes the exact routine above.  A straight track
+// cannot re-enter a box mesh, so leaving it ends the part.
+template<class Emit>
+OMC_D void mesh_march(int m, V3 r0, V3 u, double total, double t0, double t1, Emit& emit)
+{
+  const int nd = ld(DM.mesh_ndim + m);
+  const double ts = (t0 == 0.0) ? TINY_BIT : t0;
+  double tmax0[3], tdel[3];
+  int idx[3], left[3], stride[3];
+  bool in_mesh = true;
+  int bin = 0, cells = 1;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    tmax0[k] = INFTY;
+    tdel[k] = 0.0;
+    idx[k] = 1;
+    left[k] = 0;
+    stride[k] = 0;
+    if (k < nd) {
+      const double ll = ld(DM.mesh_lower_left + 3 * m + k), w = ld(DM.mesh_width + 3 * m + k);
+      const int shape = ld(DM.mesh_shape + 3 * m + k);
+      const double rk = comp(r0, k), uk = comp(u, k);
+      idx[k] = mesh_index(rk + ts * uk, ll, w);
+      in_mesh = in_mesh && idx[k] >= 1 && idx[k] <= shape;
+      const bool pos = uk > 0;
+      if (!(fabs(uk) < FP_PRECISION)) {
+        tmax0[k] = ((ll + (pos ? idx[k] : idx[k] - 1) * w) - rk) / uk;
+        tdel[k] = w / fabs(uk);
+      }
+      left[k] = pos ? shape - idx[k] : idx[k] - 1; // cells ahead before the mesh ends
+      stride[k] = pos ? cells : -cells;
+      bin += (idx[k] - 1) * cells;
+      cells *= shape;
+    }
+  }
+  if (!in_mesh || total < 2 * TINY_BIT) {
+    mesh_march_exact(m, r0, u, total, t0, t1, emit);
+    return;
+  }
+  const double inv_total = 1.0 / total;
+  double t_0 = tmax0[0], t_1 = tmax0[1], t_2 = tmax0[2];
+  int j0 = 0, j1 = 0, j2 = 0;
+  double traveled = t0;
+  for (int guard = 0; guard < 1000000; ++guard) {
+    int k = 0;
+    double dk = t_0;
+    if (t_1 < dk) {
+      k = 1;
+      dk = t_1;
+    }
+    if (t_2 < dk) {
+      k = 2;
+      dk = t_2;
+    }
+    emit(bin, ((dk < t1 ? dk : t1) - traveled) * inv_total);
+    traveled = dk;
+    if (traveled >= t1)
+      break;
+    if (k == 0) {
+      if (j0 == left[0])
+        break;
+      ++j0;
+      bin += stride[0];
+      t_0 = tmax0[0] + j0 * tdel[0];
+    } else if (k == 1) {
+      if (j1 == left[1])
+        break;
+      ++j1;
+      bin += stride[1];
+      t_1 = tmax0[1] + j1 * tdel[1];
+    } else {
+      if (j2 == left[2])
+        break;
+      ++j2;
+      bin += stride[2];
+      t_2 = tmax0[2] + j2 * tdel[2];
+    }
+  }
 }
 
 // Number of mesh cells the track r0 -> r1 visits (exact for a track inside the
