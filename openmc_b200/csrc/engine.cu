@@ -496,6 +496,24 @@ OMC_D void body_advance(int64_t tid, const EvArgs& a)
 }
 OMC_KERNEL(k_advance, EvArgs, body_advance)
 
+// calculate-xs and advance events of the same work list in one pass: every
+// alive particle goes through both in every sweep, so unless the xs list is to be
+// re-ordered in between, one kernel saves a launch and one round trip of the
+// particle's sectors through L2
+OMC_D void body_xs_advance(int64_t tid, const EvArgs& a)
+{
+  if (tid >= *a.q_in.count)
+    return;
+  const int32_t i = a.q_in.idx[tid];
+  ev_xs(a.ps, i);
+  const int next = ev_advance(a.ps, a.gc, a.fl, i, tid);
+  if (next == NEXT_COLLISION)
+    queue_append(a.q_a, i);
+  else if (next == NEXT_SURFACE)
+    queue_append(a.q_b, i);
+}
+OMC_KERNEL(k_xs_advance, EvArgs, body_xs_advance)
+
 // -----------------------------------------------------------------------------
 // k_score -- tracklength tally scoring for the flights k_advance just recorded
 // (score_tracklength_tally, src/tallies/tally_scoring.cpp:2416-2541).
@@ -1110,6 +1128,7 @@ struct Engine {
   cudaStream_t stream = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evx0[RING] = {}, evx1[RING] = {}, evp0 = nullptr, evp1 = nullptr;
+  bool fuse_xs = true;          // k_xs + k_advance as one kernel (ms_xs then covers both)
   int64_t sync_every = 8;       // sweeps the host lets run between two counter read-backs
   int64_t tail_threshold = 16384;
   int score_part = 8;
@@ -1488,9 +1507,6 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
     a.q_in = G.q[cur];
     a.q_in.count = alive_count;
     const int ev = (int)(sweep % RING);
-    CUDA_OK(cudaEventRecord(G.evx0[ev], G.stream));
-    OMC_LAUNCH(k_xs, n_alive, G.stream, a);
-    CUDA_OK(cudaEventRecord(G.evx1[ev], G.stream));
     a.q_a = G.q[2];
     a.q_a.count = slot + 0;
     a.q_b = G.q[3];
@@ -1500,7 +1516,15 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
     a.n_flights = alive_count;
     if (score && score_pending[buf] && G.overlap) // records of sweep-2 must have been consumed
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_score[buf], 0));
-    OMC_LAUNCH(k_advance, n_alive, G.stream, a);
+    CUDA_OK(cudaEventRecord(G.evx0[ev], G.stream));
+    if (G.fuse_xs) {
+      OMC_LAUNCH(k_xs_advance, n_alive, G.stream, a);
+      CUDA_OK(cudaEventRecord(G.evx1[ev], G.stream));
+    } else {
+      OMC_LAUNCH(k_xs, n_alive, G.stream, a);
+      CUDA_OK(cudaEventRecord(G.evx1[ev], G.stream));
+      OMC_LAUNCH(k_advance, n_alive, G.stream, a);
+    }
     // cell / universe filters read the live coordinate levels: score before the
     // crossing and collision kernels may change them
     const bool score_in_order = score && G.tally_needs_cells;
@@ -1703,6 +1727,8 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   CUDA_OK(cudaStreamCreate(&G.s_score));
   CUDA_OK(cudaStreamCreate(&G.s_surf));
   CUDA_OK(cudaStreamCreate(&G.s_coll));
+  if (const char* t = std::getenv("OMCGPU_FUSE_XS"))
+    G.fuse_xs = std::atoi(t) != 0;
   if (const char* t = std::getenv("OMCGPU_OVERLAP"))
     G.overlap = std::atoi(t) != 0;
   // particle state is gathered in 32-byte sectors (PState): do not let L2 fetch 64
