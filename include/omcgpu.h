@@ -187,6 +187,12 @@ typedef struct omcgpu_model {
   int32_t n_universes;
   const int32_t* univ_cell_ofs;   /* [n_universes+1]                                   */
   const int32_t* univ_cells;      /* Universe::cells_ in search order                  */
+  /* derived by omcgpu_init (ignored on input): cells whose region names a surface
+   * half-space -- the search list after a surface crossing, in place of the
+   * reference's run-time neighbour lists (src/geometry.cpp:256-282).  Token slot
+   * 2*s is surface s negative side (-(s+1)), 2*s+1 its positive side. */
+  const int32_t* tok_cell_ofs;    /* [2*n_surfaces+1]                                  */
+  const int32_t* tok_cells;       /* cell indices, ascending                           */
 
   /* ---- rectangular lattices: model::lattices (src/lattice.cpp:162-377) ---- */
   int32_t n_lattices;

@@ -503,15 +503,32 @@ OMC_HD bool find_cell_inner(const PState& ps, int64_t i, int lvl, int surface)
   V3 r = get_r(ps, i, lvl);
   V3 u = get_u(ps, i, lvl);
   int univ = LV(universe, lvl);
+  bool crossed = surface != SURFACE_NONE; // first level searched after a surface crossing
   for (;; ++lvl) {
-    // Universe::find_cell
     int found = C_NONE;
-    const int k1 = ld(DM.univ_cell_ofs + univ + 1);
-    for (int k = ld(DM.univ_cell_ofs + univ); k < k1; ++k) {
-      const int c = ld(DM.univ_cells + k);
-      if (cell_contains(c, r, u, surface)) {
-        found = c;
-        break;
+    if (crossed) {
+      // the cell entered through a surface names that half-space in its region
+      // (cells of a valid model do not overlap): search those cells of this
+      // universe first -- same result as the full list, far fewer candidates
+      const int slot = 2 * (abs(surface) - 1) + (surface > 0 ? 1 : 0);
+      const int k1 = ld(DM.tok_cell_ofs + slot + 1);
+      for (int k = ld(DM.tok_cell_ofs + slot); k < k1; ++k) {
+        const int c = ld(DM.tok_cells + k);
+        if (ld(DM.cell_universe + c) == univ && cell_contains(c, r, u, surface)) {
+          found = c;
+          break;
+        }
+      }
+      crossed = false;
+    }
+    if (found == C_NONE) { // Universe::find_cell
+      const int k1 = ld(DM.univ_cell_ofs + univ + 1);
+      for (int k = ld(DM.univ_cell_ofs + univ); k < k1; ++k) {
+        const int c = ld(DM.univ_cells + k);
+        if (cell_contains(c, r, u, surface)) {
+          found = c;
+          break;
+        }
       }
     }
     if (found == C_NONE) {

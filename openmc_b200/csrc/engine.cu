@@ -1232,6 +1232,31 @@ static int upload_model(const omcgpu_model* m)
   const int n_uc = nu ? m->univ_cell_ofs[nu] : 0;
   UP(univ_cell_ofs, nu + 1);
   UP(univ_cells, n_uc);
+  // surface half-space -> cells that name it (a cell with unions / complements is
+  // listed under both sides of every surface it names)
+  std::vector<std::vector<int32_t>> by_tok(2 * (size_t)ns);
+  for (int c = 0; c < nc; ++c)
+    for (int k = m->cell_region_ofs[c]; k < m->cell_region_ofs[c + 1]; ++k) {
+      const int32_t tok = m->region_tokens[k];
+      if (tok >= OMCGPU_OP_UNION || tok == 0)
+        continue;
+      const int sfc = std::abs(tok) - 1;
+      for (int side = 0; side < 2; ++side)
+        if (!m->cell_simple[c] || side == (tok > 0 ? 1 : 0)) {
+          auto& v = by_tok[2 * (size_t)sfc + side];
+          if (v.empty() || v.back() != c)
+            v.push_back(c);
+        }
+    }
+  std::vector<int32_t> tok_ofs(2 * (size_t)ns + 1, 0), tok_cells;
+  for (size_t t = 0; t < by_tok.size(); ++t) {
+    tok_cells.insert(tok_cells.end(), by_tok[t].begin(), by_tok[t].end());
+    tok_ofs[t + 1] = (int32_t)tok_cells.size();
+  }
+  h.tok_cell_ofs = tok_ofs.data();
+  h.tok_cells = tok_cells.data();
+  UP(tok_cell_ofs, tok_ofs.size());
+  UP(tok_cells, tok_cells.size());
   const int n_lu = nl ? m->lat_univ_ofs[nl] : 0;
   const int n_lo = nl ? m->lat_offset_ofs[nl] : 0;
   UP(lat_shape, (size_t)nl * 3);

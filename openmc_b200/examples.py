@@ -434,3 +434,142 @@ def c5g7_core(mesh_dim=510, tallies=True):
         m.tallies = [Tally(1, [1], ["flux", "fission"])]
     box = [0.0, -2 * w, -1, 2 * w, 0.0, 1]
     return m, c5g7_core_library(), box, True
+
+
+# ----------------------------------------------------------------------------
+# config C5: Hoogenboom-Martin full core (openmc/examples.py:94-439), continuous
+# energy, fuel expanded to a depleted-fuel-like set of synthetic nuclides
+# ----------------------------------------------------------------------------
+_STRUCT_ZA = {"U234": (92, 234), "U235": (92, 235), "U238": (92, 238), "Xe135": (54, 135), "O16": (8, 16),
+              "Zr90": (40, 90), "Zr91": (40, 91), "Zr92": (40, 92), "Zr94": (40, 94), "Zr96": (40, 96),
+              "H1": (1, 1), "B10": (5, 10), "B11": (5, 11), "Fe54": (26, 54), "Fe56": (26, 56),
+              "Fe57": (26, 57), "Fe58": (26, 58), "Ni58": (28, 58), "Ni60": (28, 60), "Mn55": (25, 55),
+              "Cr52": (24, 52), "C0": (6, 12), "Cu63": (29, 63)}
+
+
+def pwr_core_nuclides(n_fuel_nuclides=300):
+    """(name, Z, A, fissionable, inelastic, delayed) for the structural nuclides of
+    pwr_core plus synthetic fission products / actinides FPnnn filling the fuel up
+    to n_fuel_nuclides"""
+    out = []
+    for name, (Z, A) in _STRUCT_ZA.items():
+        fis = name in ("U234", "U235", "U238")
+        out.append((name, Z, A, fis, name in ("U235", "U238", "Fe56", "Zr90"), name == "U235"))
+    g = np.random.default_rng(5)
+    for k in range(max(n_fuel_nuclides - 5, 0)):
+        Z = int(g.integers(30, 96))
+        A = int(round(Z * 2.45 + g.integers(-3, 4)))
+        out.append((f"FP{k:03d}", Z, A, bool(Z >= 90 and g.uniform() < 0.3), False, False))
+    return out
+
+
+def pwr_core_ce(n_grid=100000, n_fuel_nuclides=300, tallies=False, library=None):
+    """OECD/NEA Monte Carlo performance benchmark geometry, verbatim from
+    openmc/examples.py:255-425 (241 assemblies of 17 x 17 pins in a 21 x 21 core
+    lattice, lower / upper halves, axial reflector regions, vacuum outside), no
+    S(a,b).  The fuel's five nuclides are joined by synthetic ones with log-uniform
+    random densities (seed 5) -- the xs-lookup stress case (BASELINE.json C5)."""
+    from . import nuclide as nd
+    m = Model()
+    nucs = pwr_core_nuclides(n_fuel_nuclides)
+    g = np.random.default_rng(5)
+    extra = [(n[0], float(np.exp(g.uniform(np.log(1e-9), np.log(1e-5))))) for n in nucs[len(_STRUCT_ZA):]]
+    fuel = m.material(id=1, name="UOX fuel", units="g/cm3", density=10.062,
+                      components=[("U234", 4.9476e-6), ("U235", 4.8218e-4), ("U238", 2.1504e-2),
+                                  ("Xe135", 1.0801e-8), ("O16", 4.5737e-2)] + extra)
+    clad = m.material(id=2, name="Zircaloy", units="g/cm3", density=5.77,
+                      components=[("Zr90", 0.5145), ("Zr91", 0.1122), ("Zr92", 0.1715),
+                                  ("Zr94", 0.1738), ("Zr96", 0.0280)])
+    water_c = [("H1", 2.0), ("O16", 1.0), ("B10", 6.490e-4), ("B11", 2.689e-3)]
+    cold = m.material(id=3, name="Cold borated water", units="atom/b-cm", density=0.07416, components=water_c)
+    hot = m.material(id=4, name="Hot borated water", units="atom/b-cm", density=0.06614, components=water_c)
+    rpv = m.material(id=5, name="Reactor pressure vessel steel", units="g/cm3", density=7.9, components=[
+        ("Fe54", -0.05437098), ("Fe56", -0.88500663), ("Fe57", -0.0208008), ("Fe58", -0.00282159),
+        ("Ni58", -0.0067198), ("Ni60", -0.0026776), ("Mn55", -0.01), ("Cr52", -0.002092475),
+        ("C0", -0.0025), ("Cu63", -0.0013696)])
+
+    def steel_water(id, name, density, h1, o16, b10, b11, fe54, fe56, fe57, fe58, ni58, mn55, cr52):
+        return m.material(id=id, name=name, units="g/cm3", density=density, components=[
+            ("H1", -h1), ("O16", -o16), ("B10", -b10), ("B11", -b11), ("Fe54", -fe54), ("Fe56", -fe56),
+            ("Fe57", -fe57), ("Fe58", -fe58), ("Ni58", -ni58), ("Mn55", -mn55), ("Cr52", -cr52)])
+    lower_rad = steel_water(6, "Lower radial reflector", 4.32, 0.0095661, 0.0759107, 3.08409e-5, 1.40499e-4,
+                            0.035620772088, 0.579805982228, 0.01362750048, 0.001848545204,
+                            0.055298376566, 0.0182870, 0.145407678031)
+    upper_rad = steel_water(7, "Upper radial reflector / Top plate region", 4.28, 0.0086117, 0.0683369,
+                            2.77638e-5, 1.26481e-4, 0.035953677186, 0.585224740891, 0.01375486056,
+                            0.001865821363, 0.055815129186, 0.0184579, 0.146766614995)
+    bot_plate = steel_water(8, "Bottom plate region", 7.184, 0.0011505, 0.0091296, 3.70915e-6, 1.68974e-5,
+                            0.03855611055, 0.627585036425, 0.014750478, 0.002000875025, 0.059855207342,
+                            0.0197940, 0.157390026871)
+    bot_nozzle = steel_water(9, "Bottom nozzle region", 2.53, 0.0245014, 0.1944274, 7.89917e-5, 3.59854e-4,
+                             0.030411411144, 0.495012237964, 0.01163454624, 0.001578204652,
+                             0.047211231662, 0.0156126, 0.124142524198)
+    top_nozzle = steel_water(10, "Top nozzle region", 1.746, 0.0358870, 0.2847761, 1.15699e-4, 5.27075e-4,
+                             0.02644016154, 0.43037146399, 0.0101152584, 0.00137211607, 0.04104621835,
+                             0.0135739, 0.107931450781)
+
+    def zr_water(id, name, density, h1, o16, b10, b11, z90, z91, z92, z94, z96):
+        return m.material(id=id, name=name, units="g/cm3", density=density, components=[
+            ("H1", -h1), ("O16", -o16), ("B10", -b10), ("B11", -b11), ("Zr90", -z90), ("Zr91", -z91),
+            ("Zr92", -z92), ("Zr94", -z94), ("Zr96", -z96)])
+    top_fa = zr_water(11, "Top of fuel assemblies", 3.044, 0.0162913, 0.1292776, 5.25228e-5, 2.39272e-4,
+                      0.43313403903, 0.09549277374, 0.14759527104, 0.15280552077, 0.02511169542)
+    bot_fa = zr_water(12, "Bottom of fuel assemblies", 1.762, 0.0292856, 0.2323919, 9.44159e-5, 4.30120e-4,
+                      0.3741373658, 0.0824858164, 0.1274914944, 0.1319920622, 0.0216912612)
+
+    for sid, r in ((1, 0.41), (2, 0.475), (3, 0.56), (4, 0.62), (5, 187.6), (6, 209.0), (7, 229.0)):
+        m.surface("z-cylinder", [0.0, 0.0, r], id=sid)
+    m.surface("z-cylinder", [0.0, 0.0, 249.0], "vacuum", id=8)
+    for sid, z, bc in ((31, -229.0, "vacuum"), (32, -199.0, "transmission"), (33, -193.0, "transmission"),
+                       (34, -183.0, "transmission"), (35, 0.0, "transmission"), (36, 183.0, "transmission"),
+                       (37, 203.0, "transmission"), (38, 215.0, "transmission"), (39, 223.0, "vacuum")):
+        m.surface("z-plane", [z], bc, id=sid)
+
+    def pin(u, base, inner, outer, s_in, s_out):
+        m.cell(id=base, region=f"-{s_in}", fill=inner, universe=u)
+        m.cell(id=base + 1, region=f"{s_in} -{s_out}", fill=clad, universe=u)
+        m.cell(id=base + 2, region=f"{s_out}", fill=outer, universe=u)
+    pin(1, 21, fuel, cold, 1, 2)
+    pin(2, 24, cold, cold, 3, 4)
+    pin(3, 27, fuel, hot, 1, 2)
+    pin(4, 30, hot, hot, 3, 4)
+    tube_x = [5, 8, 11, 3, 13, 2, 5, 8, 11, 14, 2, 5, 8, 11, 14, 2, 5, 8, 11, 14, 3, 13, 5, 8, 11]
+    tube_y = [2, 2, 2, 3, 3, 5, 5, 5, 5, 5, 8, 8, 8, 8, 8, 11, 11, 11, 11, 11, 13, 13, 14, 14, 14]
+
+    def assembly(u_fuel, u_tube, lid):
+        a = np.full((17, 17), u_fuel)
+        a[tube_x, tube_y] = u_tube
+        return m.lattice(id=lid, pitch=(1.26, 1.26), lower_left=(-10.71, -10.71), universes=a.tolist())
+    l100 = assembly(1, 2, 100)
+    l101 = assembly(3, 4, 101)
+    m.cell(id=50, region="34 -35", fill=cold, universe=5)
+    m.cell(id=70, region="35 -36", fill=hot, universe=7)
+    m.cell(id=60, region="34 -35", fill=l100, universe=6)
+    m.cell(id=80, region="35 -36", fill=l101, universe=8)
+    widths = [0, 0, 7, 11, 13, 15, 15, 17, 17, 17, 17, 17, 17, 17, 15, 15, 13, 11, 7, 0, 0]
+
+    def core(u_water, u_fa, lid):
+        rows = [[u_water] * ((21 - w) // 2) + [u_fa] * w + [u_water] * (21 - w - (21 - w) // 2) for w in widths]
+        return m.lattice(id=lid, pitch=(21.42, 21.42), lower_left=(-224.91, -224.91), universes=rows)
+    l200 = core(5, 6, 200)
+    l201 = core(7, 8, 201)
+    m.cell(id=1, region="-6 34 -35", fill=l200, universe=0)
+    m.cell(id=2, region="-6 35 -36", fill=l201, universe=0)
+    m.cell(id=3, region="-7 31 -32", fill=bot_plate, universe=0)
+    m.cell(id=4, region="-5 32 -33", fill=bot_nozzle, universe=0)
+    m.cell(id=5, region="-5 33 -34", fill=bot_fa, universe=0)
+    m.cell(id=6, region="-5 36 -37", fill=top_fa, universe=0)
+    m.cell(id=7, region="-5 37 -38", fill=top_nozzle, universe=0)
+    m.cell(id=8, region="-7 38 -39", fill=upper_rad, universe=0)
+    m.cell(id=9, region="6 -7 32 -38", fill=bot_nozzle, universe=0)
+    m.cell(id=10, region="7 -8 31 -39", fill=rpv, universe=0)
+    m.cell(id=11, region="5 -6 32 -34", fill=lower_rad, universe=0)
+    m.cell(id=12, region="5 -6 36 -38", fill=upper_rad, universe=0)
+    if tallies:
+        m.meshes = [Mesh(1, [21 * 17, 21 * 17], [-224.91, -224.91], [224.91, 224.91])]
+        m.filters = [Filter(1, "mesh", 1)]
+        m.tallies = [Tally(1, [1], ["flux", "fission"])]
+    if library is None:
+        library = nd.synthetic_library(nucs, n_grid)
+    box = [-160.0, -160.0, -183.0, 160.0, 160.0, 183.0]
+    return m, library, box, False

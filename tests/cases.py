@@ -94,12 +94,16 @@ def load_model_npz(path):
 
 def build_lattice(name):
     """lattice configurations: 'assembly' = config C3 (17 x 17, CE, 2 levels),
-    'c5g7' = config C4 (lattice of lattices, MG, 3 levels); small grids / meshes"""
+    'c5g7' = config C4 (lattice of lattices, MG, 3 levels), 'pwr_core' = config C5
+    (Hoogenboom-Martin full core, CE, 3 levels, z-planes); small grids / meshes"""
     from openmc_b200 import nuclide
     key = ("lattice", name)
     if key not in _CE_CACHE:
         if name == "assembly":
             m, libx, box, of = examples.assembly_ce(n_grid=2000)
+            _CE_CACHE[key] = (nuclide.build_ce_model(m, libx), box, of)
+        elif name == "pwr_core":     # config C5 geometry, 40-nuclide fuel, small grids
+            m, libx, box, of = examples.pwr_core_ce(n_grid=600, n_fuel_nuclides=40, tallies=True)
             _CE_CACHE[key] = (nuclide.build_ce_model(m, libx), box, of)
         else:
             m, lib, box, of = examples.c5g7_core(mesh_dim=51)

@@ -156,7 +156,7 @@ def test_ce_eigenvalue_statistics(gpu_engine):
 # ------------------------------------------------------------------------------
 # lattices (configs C3 / C4)
 # ------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["assembly", "c5g7"])
+@pytest.mark.parametrize("name", ["assembly", "c5g7", "pwr_core"])
 def test_lattice_geometry_bit_exact(gpu_engine, name):
     """cell / instance / material / level, crossing surface tokens and lattice
     translations bit-exact on 2- and 3-level lattice geometry, incl. points placed

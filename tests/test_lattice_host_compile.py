@@ -8,7 +8,7 @@ from openmc_b200 import lib
 from oracle.binding import Oracle
 
 
-@pytest.mark.parametrize("name", ["assembly", "c5g7"])
+@pytest.mark.parametrize("name", ["assembly", "c5g7", "pwr_core"])
 def test_lattice_geometry_bit_exact(emu_lib, name):
     model, box, of = cases.build_lattice(name)
     o = Oracle(model)
@@ -26,7 +26,7 @@ def test_lattice_geometry_bit_exact(emu_lib, name):
 
 
 @pytest.mark.parametrize("threshold", ["0", "100000"])
-@pytest.mark.parametrize("name", ["assembly", "c5g7"])
+@pytest.mark.parametrize("name", ["assembly", "c5g7", "pwr_core"])
 def test_lattice_generation_matches_oracle(emu_lib, name, threshold, monkeypatch):
     monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)
     model, box, of = cases.build_lattice(name)
