@@ -202,8 +202,17 @@ def main():
     # ---- end to end through host buffers ("e2e"): the reference-facing call
     e2e = None
     if not args.no_e2e:
-        bank = eng.get_source_bank(n_local)
-        fis = np.zeros(3 * n_local, dtype=bank.dtype)
+        # The reference-facing call on HOST buffers: libopenmc's simulation::source_bank
+        # (page-locked once, as allocate_banks would) goes H2D, the generation runs, and
+        # the next source bank comes back D2H.  N = 1: omcgpu_next_generation (device sort
+        # + comb = transport_event_based + synchronize_bank).  N > 1: per-rank
+        # omcgpu_transport_generation returning the sorted fission bank to the host.
+        bank = np.ascontiguousarray(eng.get_source_bank(n_local))
+        eng.host_register(bank)
+        fis = None
+        if world > 1:
+            fis = np.zeros(3 * n_local, dtype=bank.dtype)
+            eng.host_register(fis)
         gen0 = sim.current_batch
         h2d = d2h = 0
         barrier()
@@ -211,23 +220,29 @@ def main():
         keff = sim.keff
         for s in range(args.steps):
             gi = eng.gen_in(n_local, work_lo, (gen0 + s) * n_global, keff, True)
-            fb, out = eng.transport_generation(gi, bank, fis)
             h2d += bank.nbytes
-            d2h += fb.nbytes + 96
-            if world == 1:     # host-side comb, as libopenmc's synchronize_bank would
-                idx = lib.comb_indices(0, fb.size, fb.size, n_local, gen0 + s + 1)
-                bank = np.ascontiguousarray(fb[idx])
+            if world == 1:
+                out = eng.next_generation(gi, bank, gen0 + s + 1)
+                d2h += bank.nbytes + 96
+            else:
+                fb, out = eng.transport_generation(gi, bank, fis)
+                d2h += fb.nbytes + 96
             keff = out.global_tally[2] / n_local
         barrier()
         dt_e = time.perf_counter() - t0
+        eng.host_unregister(bank)
+        if fis is not None:
+            eng.host_unregister(fis)
         if world > 1:
             t = torch.tensor([dt_e], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt_e = float(t[0])
         e2e = {"value": n_global * args.steps / dt_e, "unit": "particles/s",
                "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
-               "note": "omcgpu_transport_generation on host SourceSite buffers + host-side comb"
-                       + ("" if world == 1 else " (per-rank banks, no inter-rank rebalance in this leg)")}
+               "note": ("omcgpu_next_generation on the page-locked host SourceSite bank: H2D source, event "
+                        "loop, device sort + comb, D2H next source" if world == 1 else
+                        "omcgpu_transport_generation on page-locked host banks, per rank (no inter-rank "
+                        "rebalance in this leg)")}
 
     # ---- roofline of the dominant kernel (k_xs) from live CUDA-event timings
     peaks = {}

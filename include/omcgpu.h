@@ -373,6 +373,23 @@ int64_t omcgpu_kernel_launches(void);
 int omcgpu_transport_generation(const omcgpu_gen_in* in, const omcgpu_site* source_bank,
   omcgpu_site* fission_bank, int64_t fission_capacity, omcgpu_gen_out* out);
 
+/* One generation of a single-process run INCLUDING the sampling half of
+ * synchronize_bank() (src/eigenvalue.cpp:152-178): source_bank (host,
+ * in->n_particles sites) goes H2D, the event loop runs, the fission bank is
+ * sorted and combed on the device with seed_id = simulation::total_gen +
+ * overall_generation(), and the NEXT source bank comes back D2H into the same
+ * buffer -- what libopenmc holds in simulation::source_bank after
+ * finalize_generation() (src/simulation.cpp:522-571) when n_procs == 1.  The
+ * sorted fission bank stays readable through omcgpu_get_fission_bank(). */
+int omcgpu_next_generation(const omcgpu_gen_in* in, omcgpu_site* source_bank, int64_t seed_id,
+  omcgpu_gen_out* out);
+
+/* Page-lock a host bank (simulation::source_bank / fission_bank, allocated once
+ * in allocate_banks(), src/simulation.cpp:332-357) so that the calls above DMA
+ * straight from / into it instead of through the library's staging buffer. */
+int omcgpu_host_register(void* p, int64_t bytes);
+int omcgpu_host_unregister(void* p);
+
 /* The same pieces separately, for a device-resident bank between generations. */
 int omcgpu_set_source_bank(const omcgpu_site* source_bank, int64_t n);
 int omcgpu_get_source_bank(omcgpu_site* source_bank, int64_t n);

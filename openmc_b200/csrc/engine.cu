@@ -33,7 +33,13 @@ namespace cg = cooperative_groups;
 
 namespace omc {
 
-constexpr int BLOCK = 256;
+#ifndef OMC_BLOCK
+#define OMC_BLOCK 256
+#endif
+constexpr int BLOCK = OMC_BLOCK;
+#ifndef XA_MINBLOCKS
+#define XA_MINBLOCKS 1 /* resident blocks per SM asked of the fused event kernels (register cap) */
+#endif
 
 // -----------------------------------------------------------------------------
 // kernel plumbing: every kernel is `body(tid, args)` for tid < n_ub.  Under
@@ -101,9 +107,12 @@ struct EvArgs {
   Flights fl;           // flight records for k_score
   int32_t fl_buf;       // which of the two record buffers `fl` is (c_fl[fl_buf])
   const int32_t* n_flights; // device count of records (its ring slot outlives the sweep)
+  int32_t first_event;      // k_tail: event the histories of q_in are waiting for (NEXT_NONE: a flight)
 };
 
-enum { NEXT_DEAD = -1, NEXT_COLLISION = 0, NEXT_SURFACE = 1 };
+enum { NEXT_NONE = -2, NEXT_DEAD = -1, NEXT_COLLISION = 0, NEXT_SURFACE = 1 };
+constexpr int32_t PIDX_LOGGED = -1;    // flight logged by the tail: no particle state to consult
+constexpr int32_t PIDX_NO_FLIGHT = -2; // work-list position whose history made no flight this sweep
 
 OMC_D void mark_lost(const PState& ps, const GenCtx& gc, int64_t i)
 { // Particle::mark_as_lost, src/particle.cpp:762-785 (count + kill)
@@ -306,7 +315,7 @@ OMC_D int ev_advance(const PState& ps, const GenCtx& gc, const Flights& fl, int6
   if (gc.tallies_active && DM.n_tallies > 0) {
     int32_t pidx = (int32_t)i;
     if (slot == SLOT_LOG) {
-      pidx = -1;
+      pidx = PIDX_LOGGED;
       if (!gc.tally_needs_cells)
         slot = flight_log_reserve(fl);
     }
@@ -483,16 +492,32 @@ OMC_D void body_xs(int64_t tid, const EvArgs& a)
 }
 OMC_KERNEL_MB(k_xs, EvArgs, body_xs, 2)
 
-OMC_D void body_advance(int64_t tid, const EvArgs& a)
+// a work-list position that records no flight this sweep must say so: k_score
+// walks positions, and the record left there by an earlier sweep is stale
+OMC_D void no_flight(const EvArgs& a, int64_t tid)
 {
-  if (tid >= *a.q_in.count)
-    return;
-  const int32_t i = a.q_in.idx[tid];
+  if (a.gc.tallies_active && DM.n_tallies > 0 && tid < a.fl.cap)
+    a.fl.pidx[tid] = PIDX_NO_FLIGHT;
+}
+
+// flight of particle i recorded at work-list position tid, then routed to the
+// collision (q_a) or crossing (q_b) list
+OMC_D void advance_and_route(int64_t tid, const EvArgs& a, int32_t i)
+{
   const int next = ev_advance(a.ps, a.gc, a.fl, i, tid);
   if (next == NEXT_COLLISION)
     queue_append(a.q_a, i);
   else if (next == NEXT_SURFACE)
     queue_append(a.q_b, i);
+  else
+    no_flight(a, tid);
+}
+
+OMC_D void body_advance(int64_t tid, const EvArgs& a)
+{
+  if (tid >= *a.q_in.count)
+    return;
+  advance_and_route(tid, a, a.q_in.idx[tid]);
 }
 OMC_KERNEL(k_advance, EvArgs, body_advance)
 
@@ -506,13 +531,44 @@ OMC_D void body_xs_advance(int64_t tid, const EvArgs& a)
     return;
   const int32_t i = a.q_in.idx[tid];
   ev_xs(a.ps, i);
-  const int next = ev_advance(a.ps, a.gc, a.fl, i, tid);
-  if (next == NEXT_COLLISION)
-    queue_append(a.q_a, i);
-  else if (next == NEXT_SURFACE)
-    queue_append(a.q_b, i);
+  advance_and_route(tid, a, i);
 }
-OMC_KERNEL(k_xs_advance, EvArgs, body_xs_advance)
+OMC_KERNEL_MB(k_xs_advance, EvArgs, body_xs_advance, XA_MINBLOCKS)
+
+// Sweep mode 2 (run_sweeps_paired): a crossing or a collision is always followed,
+// for the survivor, by a cross-section lookup and a flight.  One kernel per list
+// does all three for its particles -- every lane of a warp walks the same event
+// sequence, so nothing diverges that did not before -- and routes the survivor
+// straight into the NEXT sweep's collision / crossing list.  A particle's
+// sectors then travel through L2 once per sweep instead of twice, and the merged
+// "alive" list (one append + one gather per particle and sweep) disappears.
+OMC_D void body_surface_xa(int64_t tid, const EvArgs& a)
+{
+  if (tid >= *a.q_in.count)
+    return;
+  const int32_t i = a.q_in.idx[tid];
+  if (ev_surface(a.ps, a.gc, i)) {
+    ev_xs(a.ps, i);
+    advance_and_route(tid, a, i);
+  } else {
+    no_flight(a, tid);
+  }
+}
+OMC_KERNEL_MB(k_surface_xa, EvArgs, body_surface_xa, XA_MINBLOCKS)
+
+OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
+{
+  if (tid >= *a.q_in.count)
+    return;
+  const int32_t i = a.q_in.idx[tid];
+  if (ev_collide(a.ps, a.gc, a.fb, i)) {
+    ev_xs(a.ps, i);
+    advance_and_route(tid, a, i);
+  } else {
+    no_flight(a, tid);
+  }
+}
+OMC_KERNEL_MB(k_collide_xa, EvArgs, body_collide_xa, XA_MINBLOCKS)
 
 // -----------------------------------------------------------------------------
 // k_score -- tracklength tally scoring for the flights k_advance just recorded
@@ -668,7 +724,7 @@ OMC_HD void tally_mesh_info(int t, int& mesh, int& mesh_stride)
 // sd points at this lane's column of the warp's staging area (stride 32 doubles).
 __constant__ PState c_ps; // the particle columns never move after omcgpu_init
 
-__constant__ Flights c_fl[2]; // double-buffered: k_score(sweep s) overlaps k_advance(sweep s+1)
+__constant__ Flights c_fl[4]; // [list kind][parity]: k_score(sweep s) overlaps the event kernels of sweep s+1
 
 __device__ __noinline__ int score_lane(int64_t j, int buf, int t, double* values, int score_part,
   double* sd, int64_t* sbase)
@@ -700,9 +756,13 @@ __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, 
   __shared__ int64_t s_base[WARPS][32];
   __shared__ int s_incl[WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n = *a.n_flights < a.fl.cap ? *a.n_flights : a.fl.cap;
-  const bool active = tid < n;
+  // grid-stride over blocks of flights: with a capped grid (G.score_ctas) the kernel
+  // occupies only part of every SM for the whole sweep, so that its RED traffic
+  // shares the SM with the latency-bound event kernels of the next sweep
+  for (int64_t base = (int64_t)blockIdx.x * BLOCK; base < n && base < n_ub; base += (int64_t)gridDim.x * BLOCK) {
+  const int64_t tid = base + threadIdx.x;
+  const bool active = tid < n && a.fl.pidx[tid] != PIDX_NO_FLIGHT;
   for (int t = 0; t < DM.n_tallies; ++t) {
     __syncwarp(); // lanes leave the part loop of the previous tally at different times
     int nc = 0;
@@ -744,11 +804,17 @@ __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, 
       mesh_march(mesh, pr0, pu, ptotal, part_bound(c, onc, ptotal), part_bound(c + 1, onc, ptotal), em);
     }
   }
+  __syncwarp(); // the staging area is reused by the next block of flights
+  }
 }
+static int g_score_grid_cap = 0; // 0: one block per BLOCK flights; else at most this many blocks
 #define LAUNCH_SCORE(n_ub, stream, args) \
   do { \
     if ((n_ub) > 0) { \
-      k_score<<<(unsigned)(((n_ub) + BLOCK - 1) / BLOCK), BLOCK, 0, stream>>>((int64_t)(n_ub), args); \
+      unsigned grid_ = (unsigned)(((n_ub) + BLOCK - 1) / BLOCK); \
+      if (g_score_grid_cap > 0 && grid_ > (unsigned)g_score_grid_cap) \
+        grid_ = (unsigned)g_score_grid_cap; \
+      k_score<<<grid_, BLOCK, 0, stream>>>((int64_t)(n_ub), args); \
       ++g_launches; \
     } \
   } while (0)
@@ -758,6 +824,8 @@ void k_score(int64_t n_ub, EvArgs a)
 {
   const int64_t n = *a.n_flights < a.fl.cap ? *a.n_flights : a.fl.cap;
   for (int64_t tid = 0; tid < n_ub && tid < n; ++tid) {
+    if (a.fl.pidx[tid] == PIDX_NO_FLIGHT)
+      continue;
     const Flight f = load_flight(a.fl, tid);
     for (int t = 0; t < DM.n_tallies; ++t) {
       PartEmit em;
@@ -810,11 +878,14 @@ OMC_D void body_tail(int64_t tid, const EvArgs& a)
     return;
   const int32_t i = a.q_in.idx[tid];
   unsigned long long n_xs = 0, n_coll = 0, n_cross = 0;
-  bool alive = true;
-  while (alive) {
-    ev_xs(a.ps, i);
-    ++n_xs;
-    const int next = ev_advance(a.ps, a.gc, a.fl, i, SLOT_LOG);
+  int next = a.first_event; // what the histories of this list are waiting for
+  for (;;) {
+    if (next == NEXT_NONE) {
+      ev_xs(a.ps, i);
+      ++n_xs;
+      next = ev_advance(a.ps, a.gc, a.fl, i, SLOT_LOG);
+    }
+    bool alive;
     if (next == NEXT_COLLISION) {
       alive = ev_collide(a.ps, a.gc, a.fb, i);
       ++n_coll;
@@ -822,8 +893,11 @@ OMC_D void body_tail(int64_t tid, const EvArgs& a)
       alive = ev_surface(a.ps, a.gc, i);
       ++n_cross;
     } else {
-      alive = false;
+      break;
     }
+    if (!alive)
+      break;
+    next = NEXT_NONE;
   }
   atomic_add_u64(a.gc.counters + 1, n_xs);
   atomic_add_u64(a.gc.counters + 2, n_coll);
@@ -1102,7 +1176,7 @@ struct Engine {
   int64_t cap = 0;            // max particles per generation
   int64_t fis_cap = 0;        // fission bank capacity (3 * cap)
   PState ps;
-  Flights fl[2];
+  Flights fl[4];              // [0],[1]: double buffer of sweep mode 1; mode 2 uses [kind * 2 + parity]
   bool tally_needs_cells = false;
   bool overlap = true;        // run k_score / k_surface / k_collide on their own streams
   cudaStream_t s_score = 0, s_surf = 0, s_coll = 0;
@@ -1110,6 +1184,7 @@ struct Engine {
   Bank src, fis, fis_sorted;
   int64_t n_src = 0, n_fis = 0;
   Queue q[4];
+  Queue q_alive;              // sweep mode 2: histories alive after k_init
   int32_t* d_counts = nullptr;   // [0..3] queue counts, [4] n_fission, [5] n_lost
   unsigned long long* d_counters = nullptr; // [4]
   int32_t* h_counts = nullptr;   // pinned
@@ -1129,6 +1204,9 @@ struct Engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evx0[RING] = {}, evx1[RING] = {}, evp0 = nullptr, evp1 = nullptr;
   bool fuse_xs = true;          // k_xs + k_advance as one kernel (ms_xs then covers both)
+  int sweep_mode = 2;           // 1: xs+advance | surface | collide over a merged alive list; 2: paired lists
+  int score_ctas = 0;           // >0: k_score grid capped at this many blocks per SM (persistent, co-resident)
+  int n_sm = 148;
   int64_t sync_every = 8;       // sweeps the host lets run between two counter read-backs
   int64_t tail_threshold = 16384;
   int score_part = 8;
@@ -1453,6 +1531,7 @@ static EvArgs make_args(const omcgpu_gen_in* in)
   a.gc.tally_needs_cells = G.tally_needs_cells ? 1 : 0;
   a.fl = G.fl[0];
   a.fl_buf = 0;
+  a.first_event = NEXT_NONE;
   return a;
 }
 
@@ -1484,18 +1563,15 @@ static int sort_fission_bank(int64_t n, int64_t id_offset)
   return 0;
 }
 
-static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
+struct SweepStats {
+  int64_t n_xs = 0, n_coll = 0, n_cross = 0;
+  double ms_xs = 0.0;
+};
+
+// ---- sweep mode 1: one merged alive list; xs+advance, then crossing / collision --
+static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, SweepStats& st)
 {
-  if (!G.ready)
-    return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
-  const int64_t n = in->n_particles;
-  if (n > G.cap || n > G.n_src)
-    return fail(OMCGPU_E_OUT_OF_BOUNDS, "n_particles exceeds the source bank / capacity%s");
-  std::memset(out, 0, sizeof(*out));
-  CUDA_OK(cudaMemsetAsync(G.d_counts, 0, N_COUNTS * sizeof(int32_t), G.stream));
-  CUDA_OK(cudaMemsetAsync(G.d_counters, 0, 4 * sizeof(unsigned long long), G.stream));
-  CUDA_OK(cudaEventRecord(G.ev0, G.stream));
-  EvArgs a = make_args(in);
+  int rc = 0;
   // Work lists: q[0] / q[1] alternate as "alive" list (input of k_xs / k_advance)
   // and "next" list; q[2] collisions, q[3] crossings.  Their COUNTERS come from a
   // ring with one slot {collision, crossing, next} per sweep, so that the host
@@ -1506,7 +1582,7 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
   a.q_a = G.q[cur];
   a.q_a.count = G.d_counts + 0;
   OMC_LAUNCH(k_init, n, G.stream, a);
-  int rc = read_counts();
+  rc = read_counts();
   if (rc)
     return rc;
   int64_t n_alive = G.h_counts[0]; // last count read back: upper bound of the lists
@@ -1628,6 +1704,198 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
       LAUNCH_SCORE(std::min<int64_t>(G.h_counts[6], G.fl[0].cap), G.stream, a);
     }
   }
+  st.n_xs = n_xs;
+  st.n_coll = n_coll;
+  st.n_cross = n_cross;
+  st.ms_xs = ms_xs;
+  return 0;
+}
+
+// ---- sweep mode 2: paired lists ----------------------------------------------------
+// Lists of "generation" g (g = 0 after the first flight): C[g & 1] = histories
+// waiting for a collision, S[g & 1] = for a crossing; their counters live in ring
+// slot g.  Sweep s turns the lists of generation s into those of s + 1 with
+// k_collide_xa and k_surface_xa side by side; the flights they record go to
+// fl[kind * 2 + parity] and are scored by k_score on its own stream while sweep
+// s + 1 runs.
+static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, SweepStats& st)
+{
+  auto slot_of = [](int64_t g) { return G.d_counts + RING_OFS + 4 * (g % RING); };
+  const bool score = in->tallies_active && G.hm.n_tallies > 0;
+  cudaStream_t st_score = G.overlap ? G.s_score : G.stream;
+  cudaStream_t st_surf = G.overlap ? G.s_surf : G.stream;
+  cudaStream_t st_coll = G.overlap ? G.s_coll : G.stream;
+  bool score_pending[2] = {false, false};
+  a.q_a = G.q_alive;
+  a.q_a.count = G.d_counts + 0;
+  OMC_LAUNCH(k_init, n, G.stream, a);
+  int rc = read_counts();
+  if (rc)
+    return rc;
+  const int64_t n_alive0 = G.h_counts[0];
+  st.n_xs = n_alive0;
+  // first flight: generation-0 lists
+  CUDA_OK(cudaMemsetAsync(slot_of(0), 0, 4 * sizeof(int32_t), G.stream));
+  a.q_in = G.q_alive;
+  a.q_in.count = G.d_counts + 0;
+  a.q_a = G.q[0];
+  a.q_a.count = slot_of(0) + 0;
+  a.q_b = G.q[2];
+  a.q_b.count = slot_of(0) + 1;
+  a.fl = G.fl[0];
+  a.fl_buf = 0;
+  a.n_flights = G.d_counts + 0;
+  CUDA_OK(cudaEventRecord(G.evx0[0], G.stream));
+  OMC_LAUNCH(k_xs_advance, n_alive0, G.stream, a);
+  CUDA_OK(cudaEventRecord(G.evx1[0], G.stream));
+  if (score) {
+    if (G.overlap) {
+      CUDA_OK(cudaEventRecord(G.e_adv, G.stream));
+      CUDA_OK(cudaStreamWaitEvent(st_score, G.e_adv, 0));
+    }
+    LAUNCH_SCORE(n_alive0, st_score, a);
+    if (G.overlap) {
+      CUDA_OK(cudaEventRecord(G.e_score[0], st_score));
+      score_pending[0] = true;
+      if (G.tally_needs_cells)
+        CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_score[0], 0));
+    }
+  }
+  rc = read_counts();
+  if (rc)
+    return rc;
+  {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, G.evx0[0], G.evx1[0]);
+    st.ms_xs += ms;
+  }
+  int64_t sweep = 0;  // next sweep to issue = generation of its input lists
+  int64_t known = 0;  // newest generation whose counters the host has read
+  int64_t n_alive = (int64_t)G.h_counts[RING_OFS + 0] + G.h_counts[RING_OFS + 1];
+  while (n_alive > 0 && n_alive > G.tail_threshold) {
+    const int pi = (int)(sweep & 1), po = 1 - pi;
+    const int ev = (int)((sweep + 1) % RING);
+    int32_t* in_slot = slot_of(sweep);
+    int32_t* out_slot = slot_of(sweep + 1);
+    CUDA_OK(cudaMemsetAsync(out_slot, 0, 4 * sizeof(int32_t), G.stream));
+    if (score && score_pending[po] && G.overlap) // the records of sweep - 2 must have been consumed
+      CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_score[po], 0));
+    CUDA_OK(cudaEventRecord(G.evx0[ev], G.stream));
+    if (G.overlap)
+      CUDA_OK(cudaEventRecord(G.e_adv, G.stream));
+    a.q_a = G.q[po];
+    a.q_a.count = out_slot + 0;
+    a.q_b = G.q[2 + po];
+    a.q_b.count = out_slot + 1;
+    // crossings
+    a.q_in = G.q[2 + pi];
+    a.q_in.count = in_slot + 1;
+    a.fl = G.fl[0 * 2 + po];
+    a.fl_buf = 0 * 2 + po;
+    if (G.overlap)
+      CUDA_OK(cudaStreamWaitEvent(st_surf, G.e_adv, 0));
+    OMC_LAUNCH(k_surface_xa, n_alive, st_surf, a);
+    if (G.overlap)
+      CUDA_OK(cudaEventRecord(G.e_surf, st_surf));
+    // collisions
+    a.q_in = G.q[pi];
+    a.q_in.count = in_slot + 0;
+    a.fl = G.fl[1 * 2 + po];
+    a.fl_buf = 1 * 2 + po;
+    if (G.overlap)
+      CUDA_OK(cudaStreamWaitEvent(st_coll, G.e_adv, 0));
+    OMC_LAUNCH(k_collide_xa, n_alive, st_coll, a);
+    if (G.overlap) {
+      CUDA_OK(cudaEventRecord(G.e_coll, st_coll));
+      CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_surf, 0));
+      CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_coll, 0));
+    }
+    CUDA_OK(cudaEventRecord(G.evx1[ev], G.stream));
+    if (score) {
+      if (G.overlap) {
+        CUDA_OK(cudaStreamWaitEvent(st_score, G.e_surf, 0));
+      }
+      a.fl = G.fl[0 * 2 + po];
+      a.fl_buf = 0 * 2 + po;
+      a.n_flights = in_slot + 1;
+      LAUNCH_SCORE(n_alive, st_score, a);
+      if (G.overlap)
+        CUDA_OK(cudaStreamWaitEvent(st_score, G.e_coll, 0));
+      a.fl = G.fl[1 * 2 + po];
+      a.fl_buf = 1 * 2 + po;
+      a.n_flights = in_slot + 0;
+      LAUNCH_SCORE(n_alive, st_score, a);
+      if (G.overlap) {
+        CUDA_OK(cudaEventRecord(G.e_score[po], st_score));
+        score_pending[po] = true;
+        if (G.tally_needs_cells) // cell / universe filters read the live coordinate levels
+          CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_score[po], 0));
+      }
+    }
+    ++sweep;
+    if (sweep - known >= G.sync_every) {
+      rc = read_counts();
+      if (rc)
+        return rc;
+      for (; known < sweep; ++known) { // account for sweep `known`: consumed generation known, made known + 1
+        const int32_t* hin = G.h_counts + RING_OFS + 4 * (known % RING);
+        const int32_t* hout = G.h_counts + RING_OFS + 4 * ((known + 1) % RING);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, G.evx0[(known + 1) % RING], G.evx1[(known + 1) % RING]);
+        st.ms_xs += ms;
+        st.n_coll += hin[0];
+        st.n_cross += hin[1];
+        st.n_xs += (int64_t)hout[0] + hout[1];
+        n_alive = (int64_t)hout[0] + hout[1];
+      }
+    }
+  }
+  for (int b = 0; b < 2; ++b)
+    if (score_pending[b] && G.overlap)
+      CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_score[b], 0));
+  if (n_alive > 0) { // the tail: one lane per remaining history, both lists into one flight log
+    const int pi = (int)(sweep & 1);
+    int32_t* in_slot = slot_of(sweep);
+    a.fl = G.fl[0];
+    a.fl_buf = 0;
+    a.q_in = G.q[pi];
+    a.q_in.count = in_slot + 0;
+    a.first_event = NEXT_COLLISION;
+    LAUNCH_TAIL(n_alive, G.stream, a);
+    a.q_in = G.q[2 + pi];
+    a.q_in.count = in_slot + 1;
+    a.first_event = NEXT_SURFACE;
+    LAUNCH_TAIL(n_alive, G.stream, a);
+    a.first_event = NEXT_NONE;
+    if (score && !G.tally_needs_cells) {
+      rc = read_counts(); // flights the tail logged
+      if (rc)
+        return rc;
+      a.n_flights = G.fl[0].count;
+      LAUNCH_SCORE(std::min<int64_t>(G.h_counts[6], G.fl[0].cap), G.stream, a);
+    }
+  }
+  return 0;
+}
+
+static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
+{
+  if (!G.ready)
+    return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  const int64_t n = in->n_particles;
+  if (n > G.cap || n > G.n_src)
+    return fail(OMCGPU_E_OUT_OF_BOUNDS, "n_particles exceeds the source bank / capacity%s");
+  std::memset(out, 0, sizeof(*out));
+  CUDA_OK(cudaMemsetAsync(G.d_counts, 0, N_COUNTS * sizeof(int32_t), G.stream));
+  CUDA_OK(cudaMemsetAsync(G.d_counters, 0, 4 * sizeof(unsigned long long), G.stream));
+  CUDA_OK(cudaEventRecord(G.ev0, G.stream));
+  EvArgs a = make_args(in);
+  SweepStats st;
+  int rc = G.sweep_mode == 2 ? run_sweeps_paired(a, in, n, st) : run_sweeps_merged(a, in, n, st);
+  if (rc)
+    return rc;
+  const int64_t n_xs = st.n_xs, n_coll = st.n_coll, n_cross = st.n_cross;
+  const double ms_xs = st.ms_xs;
   // death: deterministic reduction of the per-particle accumulators
   ReduceArgs r;
   r.ps = G.ps;
@@ -1756,6 +2024,18 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
     G.fuse_xs = std::atoi(t) != 0;
   if (const char* t = std::getenv("OMCGPU_OVERLAP"))
     G.overlap = std::atoi(t) != 0;
+  if (const char* t = std::getenv("OMCGPU_SWEEP"))
+    G.sweep_mode = std::atoi(t) == 1 ? 1 : 2;
+  if (const char* t = std::getenv("OMCGPU_SCORE_CTAS"))
+    G.score_ctas = std::max(0, std::atoi(t));
+#if OMC_CUDA
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess)
+      G.n_sm = prop.multiProcessorCount;
+    g_score_grid_cap = G.score_ctas * G.n_sm;
+  }
+#endif
   // particle state is gathered in 32-byte sectors (PState): do not let L2 fetch 64
   cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
   rc = upload_model(model);
@@ -1811,6 +2091,8 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
     rc = rc ? rc : dev_alloc(&G.q[k].idx, cap);
     G.q[k].count = G.d_counts + k;
   }
+  rc = rc ? rc : dev_alloc(&G.q_alive.idx, cap);
+  G.q_alive.count = G.d_counts + 0;
   rc = rc ? rc : dev_alloc(&G.d_offs, cap + 1);
   rc = rc ? rc : dev_alloc(&G.d_gather, cap);
   rc = rc ? rc : dev_alloc(&G.d_aos, G.fis_cap);
@@ -1831,7 +2113,7 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   {
     // flight records: one per work-list position in a sweep; the tail kernel logs
     // up to 64 flights per history it takes over (beyond that it scores inline)
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       Flights& fl = G.fl[b];
       fl.cap = std::max<int64_t>(cap, b == 0 ? 64 * std::min<int64_t>(cap, G.tail_threshold) : 0);
 #define F(col) rc = rc ? rc : dev_alloc(&fl.col, (size_t)fl.cap)
@@ -1849,7 +2131,7 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   }
 #if OMC_CUDA
   CUDA_OK(cudaMemcpyToSymbol(c_ps, &G.ps, sizeof(PState)));
-  CUDA_OK(cudaMemcpyToSymbol(c_fl, G.fl, 2 * sizeof(Flights)));
+  CUDA_OK(cudaMemcpyToSymbol(c_fl, G.fl, 4 * sizeof(Flights)));
 #endif
   CUDA_OK(cudaMallocHost((void**)&G.h_counts, N_COUNTS * sizeof(int32_t)));
   CUDA_OK(cudaMallocHost((void**)&G.h_counters, 4 * sizeof(unsigned long long)));
@@ -1875,22 +2157,80 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   return 0;
 }
 
-int omcgpu_set_source_bank(const omcgpu_site* source_bank, int64_t n)
+// a host buffer the CUDA driver knows (cudaMallocHost / omcgpu_host_register) is
+// copied straight from / to; anything else goes through the pinned staging area
+static bool is_pinned(const void* p)
+{
+#if OMC_CUDA
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeHost;
+#else
+  (void)p;
+  return false;
+#endif
+}
+
+int omcgpu_host_register(void* p, int64_t bytes)
+{
+#if OMC_CUDA
+  if (!p || bytes <= 0)
+    return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_host_register: bad arguments%s");
+  cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess)
+    return fail(OMCGPU_E_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e));
+#else
+  (void)p;
+  (void)bytes;
+#endif
+  return 0;
+}
+
+int omcgpu_host_unregister(void* p)
+{
+#if OMC_CUDA
+  cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess)
+    return fail(OMCGPU_E_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e));
+#else
+  (void)p;
+#endif
+  return 0;
+}
+
+// H2D of a SourceSite[] + unpack into the SoA source bank; asynchronous on
+// G.stream when the buffer is pinned (the caller synchronises before returning)
+static int set_source_bank_async(const omcgpu_site* source_bank, int64_t n)
 {
   if (!G.ready)
     return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
   if (n > G.cap)
     return fail(OMCGPU_E_OUT_OF_BOUNDS, "source bank larger than max_particles%s");
-  std::memcpy(G.h_aos, source_bank, n * sizeof(omcgpu_site));
-  CUDA_OK(cudaMemcpyAsync(G.d_aos, G.h_aos, n * sizeof(omcgpu_site), cudaMemcpyHostToDevice, G.stream));
+  const omcgpu_site* from = source_bank;
+  if (!is_pinned(source_bank)) {
+    std::memcpy(G.h_aos, source_bank, n * sizeof(omcgpu_site));
+    from = G.h_aos;
+  }
+  CUDA_OK(cudaMemcpyAsync(G.d_aos, from, n * sizeof(omcgpu_site), cudaMemcpyHostToDevice, G.stream));
   BankArgs b;
   std::memset(&b, 0, sizeof(b));
   b.a = G.src;
   b.aos = G.d_aos;
   b.n = n;
   OMC_LAUNCH(k_unpack, n, G.stream, b);
-  CUDA_OK(cudaStreamSynchronize(G.stream));
   G.n_src = n;
+  return 0;
+}
+
+int omcgpu_set_source_bank(const omcgpu_site* source_bank, int64_t n)
+{
+  int rc = set_source_bank_async(source_bank, n);
+  if (rc)
+    return rc;
+  CUDA_OK(cudaStreamSynchronize(G.stream));
   return 0;
 }
 
@@ -1902,9 +2242,12 @@ static int fetch_bank(const Bank& bank, omcgpu_site* out, int64_t n)
   b.aos = G.d_aos;
   b.n = n;
   OMC_LAUNCH(k_pack, n, G.stream, b);
-  CUDA_OK(cudaMemcpyAsync(G.h_aos, G.d_aos, n * sizeof(omcgpu_site), cudaMemcpyDeviceToHost, G.stream));
+  const bool direct = is_pinned(out);
+  CUDA_OK(cudaMemcpyAsync(direct ? out : G.h_aos, G.d_aos, n * sizeof(omcgpu_site), cudaMemcpyDeviceToHost,
+    G.stream));
   CUDA_OK(cudaStreamSynchronize(G.stream));
-  std::memcpy(out, G.h_aos, n * sizeof(omcgpu_site));
+  if (!direct)
+    std::memcpy(out, G.h_aos, n * sizeof(omcgpu_site));
   return 0;
 }
 
@@ -1933,7 +2276,7 @@ int omcgpu_run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
 int omcgpu_transport_generation(const omcgpu_gen_in* in, const omcgpu_site* source_bank,
   omcgpu_site* fission_bank, int64_t fission_capacity, omcgpu_gen_out* out)
 {
-  int rc = omcgpu_set_source_bank(source_bank, in->n_particles);
+  int rc = set_source_bank_async(source_bank, in->n_particles);
   if (rc)
     return rc;
   rc = run_generation(in, out);
@@ -1943,6 +2286,30 @@ int omcgpu_transport_generation(const omcgpu_gen_in* in, const omcgpu_site* sour
   rc = omcgpu_get_fission_bank(fission_bank, fission_capacity, &n);
   out->n_fission = n;
   return rc;
+}
+
+int omcgpu_comb_fission_bank(int64_t start, int64_t total, int64_t n_particles, int64_t seed_id,
+  int64_t master_seed, uint64_t stride, int64_t* n_sampled);
+
+int omcgpu_next_generation(const omcgpu_gen_in* in, omcgpu_site* source_bank, int64_t seed_id,
+  omcgpu_gen_out* out)
+{
+  int rc = set_source_bank_async(source_bank, in->n_particles);
+  if (rc)
+    return rc;
+  rc = run_generation(in, out);
+  if (rc)
+    return rc;
+  if (out->n_fission == 0)
+    return fail(OMCGPU_E_PHYSICS, "no fission sites banked%s");
+  int64_t n_sampled = 0;
+  rc = omcgpu_comb_fission_bank(0, out->n_fission, in->n_particles, seed_id, in->master_seed, in->stride,
+    &n_sampled);
+  if (rc)
+    return rc;
+  if (n_sampled != in->n_particles)
+    return fail(OMCGPU_E_PHYSICS, "comb did not select n_particles sites%s");
+  return fetch_bank(G.src, source_bank, n_sampled);
 }
 
 int omcgpu_comb_fission_bank(int64_t start, int64_t total, int64_t n_particles, int64_t seed_id,

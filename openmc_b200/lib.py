@@ -113,6 +113,21 @@ class Engine:
             fission_bank.ctypes.data_as(C.c_void_p), C.c_int64(fission_bank.size), C.byref(out)))
         return fission_bank[:out.n_fission], out
 
+    def next_generation(self, gen_in: abi.GenIn, source_bank: np.ndarray, seed_id: int) -> abi.GenOut:
+        """transport_event_based() + synchronize_bank() of a single-process run on the host
+        source bank, which is replaced IN PLACE by the next generation's source."""
+        assert source_bank.dtype == abi.site_dtype and source_bank.flags.c_contiguous
+        out = abi.GenOut()
+        self._check(self.lib.omcgpu_next_generation(
+            C.byref(gen_in), source_bank.ctypes.data_as(C.c_void_p), C.c_int64(seed_id), C.byref(out)))
+        return out
+
+    def host_register(self, a: np.ndarray):
+        self._check(self.lib.omcgpu_host_register(a.ctypes.data_as(C.c_void_p), C.c_int64(a.nbytes)))
+
+    def host_unregister(self, a: np.ndarray):
+        self._check(self.lib.omcgpu_host_unregister(a.ctypes.data_as(C.c_void_p)))
+
     def comb_fission_bank(self, start, total, n_particles, seed_id, master_seed=DEFAULT_SEED,
                           stride=DEFAULT_STRIDE) -> int:
         n = C.c_int64(0)

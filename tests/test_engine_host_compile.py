@@ -13,10 +13,12 @@ from openmc_b200 import lib
 from oracle.binding import Oracle
 
 
+@pytest.mark.parametrize("sweep", ["1", "2"])   # merged alive list | paired collision / crossing lists
 @pytest.mark.parametrize("threshold", ["0", "64", "100000"])
 @pytest.mark.parametrize("name", ["mg_legendre", "mg_survival_biasing", "mg_temperature_multi", "mg_basic"])
-def test_golden_through_engine(emu_lib, name, threshold, monkeypatch):
+def test_golden_through_engine(emu_lib, name, threshold, sweep, monkeypatch):
     monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)
+    monkeypatch.setenv("OMCGPU_SWEEP", sweep)
     model, box, of = cases.build(name)
     src = Oracle(model).sample_initial_source(1000, box, of)
     sim = lib.Simulation(lib.Engine(emu_lib), model, 1000, 10, 5, src)
@@ -61,6 +63,26 @@ def test_resident_equals_host_buffers(emu_lib):
         ks.append(sim.run())
         sim.simulation_finalize()
     assert ks[0] == ks[1]
+
+
+def test_next_generation_equals_transport_plus_host_comb(emu_lib):
+    """omcgpu_next_generation (device comb, source bank replaced in place) selects the
+    very sites that transport_generation + the host-side comb of synchronize_bank do."""
+    model, box, of = cases.build("mg_legendre")
+    src = Oracle(model).sample_initial_source(1500, box, of)
+    eng = lib.Engine(emu_lib)
+    eng.init(model, 0, 2048)
+    a, b = src.copy(), src.copy()
+    eng.host_register(b)
+    for g in range(3):
+        gi = eng.gen_in(1500, 0, g * 1500, 1.0, False)
+        fb, out_a = eng.transport_generation(gi, a)
+        a = np.ascontiguousarray(fb[lib.comb_indices(0, fb.size, fb.size, 1500, g + 1)])
+        out_b = eng.next_generation(gi, b, g + 1)
+        assert out_a.n_fission == out_b.n_fission
+        assert a.tobytes() == b.tobytes()
+    eng.host_unregister(b)
+    eng.finalize()
 
 
 def test_comb_matches_oracle(emu_lib):

@@ -43,10 +43,11 @@ def test_geometry_bit_exact(gpu_engine, name):
     gpu_engine.finalize()
 
 
-@pytest.mark.parametrize("threshold", ["0", "2048"])
+@pytest.mark.parametrize("threshold,sweep", [("0", "2"), ("2048", "2"), ("0", "1")])
 @pytest.mark.parametrize("name", list(cases.GOLDEN))
-def test_reference_goldens_on_gpu(gpu_engine, name, threshold, monkeypatch):
+def test_reference_goldens_on_gpu(gpu_engine, name, threshold, sweep, monkeypatch):
     monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)
+    monkeypatch.setenv("OMCGPU_SWEEP", sweep)   # paired lists (default) | merged alive list
     model, box, of = cases.build(name)
     src = Oracle(model).sample_initial_source(1000, box, of)
     sim = lib.Simulation(gpu_engine, model, 1000, 10, 5, src)
