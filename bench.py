@@ -39,7 +39,10 @@ def parse():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--particles", type=int, default=1_000_000, help="histories per generation per GPU")
     ap.add_argument("--n-grid", type=int, default=100_000, help="energy-grid points per nuclide")
-    ap.add_argument("--workload", default="pincell_ce", choices=["pincell_ce", "pincell_mg"])
+    ap.add_argument("--workload", default="pincell_ce",
+                    choices=["pincell_ce", "pincell_mg", "assembly_ce", "c5g7_core", "pwr_core_ce"],
+                    help="pincell_ce = config C2 (the bench line); the others are C1, C3, C4, C5")
+    ap.add_argument("--n-fuel-nuclides", type=int, default=300, help="pwr_core_ce: nuclides in the fuel")
     ap.add_argument("--cpu-sample", type=int, default=60_000, help="histories of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -48,10 +51,22 @@ def parse():
 
 def build_workload(args):
     from openmc_b200 import examples, mgxs, nuclide
-    if args.workload == "pincell_ce":
+    w = args.workload
+    if w == "pincell_ce":
         m, libx, box, of = examples.pincell_ce(n_grid=args.n_grid)
         return nuclide.build_ce_model(m, libx), box, of, \
             f"UO2 pincell CE, synthetic library 10 nuclides x {args.n_grid} pts (config C2)"
+    if w == "assembly_ce":
+        m, libx, box, of = examples.assembly_ce(n_grid=args.n_grid)
+        return nuclide.build_ce_model(m, libx), box, of, \
+            f"17x17 assembly CE, synthetic library x {args.n_grid} pts, pin-wise mesh tally (config C3)"
+    if w == "pwr_core_ce":
+        m, libx, box, of = examples.pwr_core_ce(n_grid=args.n_grid, n_fuel_nuclides=args.n_fuel_nuclides)
+        return nuclide.build_ce_model(m, libx), box, of, \
+            f"Hoogenboom-Martin full core CE, {args.n_fuel_nuclides}-nuclide fuel x {args.n_grid} pts (config C5)"
+    if w == "c5g7_core":
+        m, libx, box, of = examples.c5g7_core()
+        return mgxs.build_mg_model(m, libx), box, of, "C5G7-style 2-D core MG, 510x510 mesh tally (config C4)"
     m, libx, box, of = examples.pincell_multigroup()
     return mgxs.build_mg_model(m, libx), box, of, "pincell_multigroup 7-group C5G7 (config C1)"
 
@@ -114,7 +129,7 @@ def cpu_baseline(args, src, n_sample, cores):
     import multiprocessing as mp
     n_sample = min(n_sample, src.size)
     per = max(n_sample // cores, 1)
-    margs = dict(workload=args.workload, n_grid=args.n_grid)
+    margs = dict(workload=args.workload, n_grid=args.n_grid, n_fuel_nuclides=args.n_fuel_nuclides)
     jobs = [(margs, src[k * per:(k + 1) * per].copy(), k * per, 0) for k in range(cores)]
     jobs = [j for j in jobs if j[1].size]
     ctx = mp.get_context("spawn")
@@ -253,13 +268,15 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     n_nuc = np.diff(np.asarray(model["mat_nuc_ofs"]))
     roof = None
-    if args.workload == "pincell_ce" and st["ms_xs"] > 0:
+    if bool(model["run_CE"]) and st["ms_xs"] > 0:
         # algorithmic bytes per item: 60 + 88 * n_nuclides(material); the
         # per-material item counts come from the lookup micro-benchmark below
-        roof = xs_roofline(eng, model, n_local, peak, peaks)
-        roof["in_loop"] = {"ms_xs_total": st["ms_xs"] / world if world > 1 else st["ms_xs"],
+        roof = xs_roofline(eng, model, n_local, peak, peaks, box)
+        roof["in_loop"] = {"what": "device time of the event kernels that contain the lookup (k_xs_advance; "
+                                   "k_surface_xa + k_collide_xa in sweep mode 2), all generations timed",
+                           "ms_total": st["ms_xs"],
                            "share_of_transport": st["ms_xs"] / max(st["ms_transport"], 1e-9),
-                           "items": st["n_xs_lookups"]}
+                           "lookups": st["n_xs_lookups"]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -274,8 +291,10 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "particles_per_generation_per_gpu": n_local,
                        "global_particles_per_generation": n_global,
-                       "l2": "working set (48 MB xs + particle state 0.3 GB) exceeds L2; no flush",
-                       "tallies": "100x100 mesh {flux,fission,nu-fission} + 500-bin spectrum, active",
+                       "l2": "working set (cross-section tables + particle state + flight records, > 0.4 GB "
+                             "at 1e6 histories) exceeds L2; no flush",
+                       "tallies": "the config's tallies, active (C2: 100x100 mesh {flux,fission,nu-fission} "
+                                  "+ 500-bin spectrum)",
                        "parallelism": f"particles split over {world} GPU(s), replicated data"},
             "device_ms_per_step": st["ms_transport"] / args.steps,
             "events_per_particle": st["n_events"] / (n_global * args.steps),
@@ -290,16 +309,20 @@ def main():
         dist.destroy_process_group()
 
 
-def xs_roofline(eng, model, n, peak, peaks):
-    """macro-xs lookup kernel alone on a device-resident work list (E log-uniform,
-    materials by the pincell's volume fractions): achieved algorithmic GB/s."""
+def xs_roofline(eng, model, n, peak, peaks, box):
+    """macro-xs lookup kernel alone on a device-resident work list (E log-uniform over
+    the library's range, materials by their volume fractions inside the source box --
+    found with the device find_cell probe on uniform points): achieved algorithmic GB/s."""
     import ctypes as C
     import torch
     g = np.random.default_rng(7)
     e_min, e_max = float(model["energy_min"]), float(model["energy_max"])
     E = np.exp(g.uniform(np.log(e_min), np.log(e_max), n))
-    vol = np.array([0.3044, 0.0123, 0.0970, 0.5863])          # fuel, gap, clad, water
-    mat = g.choice(4, size=n, p=vol / vol.sum()).astype(np.int32)
+    box = np.asarray(box, float)
+    xyz = box[:3] + g.uniform(size=(n, 3)) * (box[3:] - box[:3])
+    mat = eng.find_cell(xyz)[2].astype(np.int32)
+    good = mat[mat >= 0]
+    mat = np.where(mat >= 0, mat, good[0] if good.size else 0).astype(np.int32)
     n_nuc = np.diff(np.asarray(model["mat_nuc_ofs"]))
     alg_bytes = float(np.sum(60 + 88 * n_nuc[mat]))
     dE = torch.from_numpy(E).cuda()

@@ -118,6 +118,7 @@ extern "C" {
 #define OMCGPU_K_TRACKLENGTH 2
 #define OMCGPU_LEAKAGE       3
 
+#define OMCGPU_FINE_PER_LOG_BIN 16 /* fine-hash bins per bin of the reference's log grid */
 #define OMCGPU_MAX_COORD  6      /* deepest universe nesting kept per particle */
 
 /* ------------------------------------------------------------------------- */
@@ -219,6 +220,13 @@ typedef struct omcgpu_model {
   int32_t n_log_bins;             /* settings::n_log_bins (8000)                       */
   double log_spacing;             /* simulation::log_spacing                           */
   const double* hash_edge;        /* [n_log_bins+2] smallest E whose host-libm hash bin is k */
+  /* derived by omcgpu_init (ignored on input): fine hash, OMCGPU_FINE_PER_LOG_BIN
+   * equal-lethargy bins per reference bin; fine_window[nuc][bin] = {lo, hi}
+   * brackets the number of grid points below any energy of the (widened) bin */
+  int32_t n_fine_bins;
+  int32_t reserved_ce;
+  double fine_inv_spacing;        /* n_fine_bins / log(energy_max / energy_min)       */
+  const int32_t* fine_window;     /* [n_nuclides][n_fine_bins][2]                      */
   const double* nuc_awr;          /* [n_nuclides]                                      */
   const double* nuc_kT;           /* [n_nuclides] kT of the single loaded temperature  */
   const int32_t* nuc_fissionable; /* [n_nuclides]                                      */

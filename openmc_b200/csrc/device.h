@@ -865,28 +865,83 @@ OMC_HD int ce_log_index(double E)
   return k; // clamped to the last valid window, see oracle.cpp ce_log_index
 }
 
-OMC_HD void ce_micro_xs(int nuc, int i_log, double E, MicroXS& micro)
+// Fine hash (derived by omcgpu_init): DM.n_fine_bins = FINE_PER_LOG_BIN x n_log_bins
+// equal-lethargy bins; fine_window[nuc][j] = {lo, hi} brackets, for every energy the
+// device may map to bin j, K = the number of grid points below E.  The windows are
+// built from bin edges widened by 1e-6 of a bin, so the bin does not have to be
+// bit-exact (the device log() may differ from libm in the last ulp) and holds ~1
+// point: the ~4 dependent probes of the search inside the reference's 8000-bin
+// window shrink to 0-2.  The grid index is still the reference's: for E strictly
+// between two points every bracketing window yields i_grid = K - 1; an E that sits
+// ON a grid point, below the first or above the last point takes the reference's
+// own window (ce_grid_index_reference), because lower_bound_index
+// (include/openmc/search.h:14-20) then depends on where that window starts.
+OMC_HD int ce_fine_index(double E)
 {
-  const int64_t g0 = ld(DM.nuc_grid_ofs + nuc);
-  const int64_t n_grid = ld(DM.nuc_grid_ofs + nuc + 1) - g0;
-  const double* energy = DM.nuc_energy + g0;
+  const int nf = DM.n_fine_bins;
+  int j = (int)(log(E / DM.energy_min) * DM.fine_inv_spacing);
+  return j < 0 ? 0 : (j > nf - 1 ? nf - 1 : j);
+}
+
+// Nuclide::calculate_xs, src/nuclide.cpp:725-742, with the reference's hash window
+OMC_HD int ce_grid_index_reference(int nuc, const double* energy, int n_grid, double E)
+{
   int i_grid;
   if (E < ld(energy)) {
     i_grid = 0;
   } else if (E > ld(energy + n_grid - 1)) {
-    i_grid = (int)n_grid - 2;
+    i_grid = n_grid - 2;
   } else {
+    const int i_log = ce_log_index(E);
     const int32_t* gi = DM.nuc_grid_index + (int64_t)nuc * (DM.n_log_bins + 1) + i_log;
     const int i_low = ld(gi);
     const int i_high = ld(gi + 1) + 1;
     i_grid = i_low + (int)lower_bound_index(energy + i_low, (int64_t)(i_high - i_low), E);
   }
-  double e0 = ld(energy + i_grid), e1 = ld(energy + i_grid + 1);
-  if (e0 == e1) {
+  if (ld(energy + i_grid) == ld(energy + i_grid + 1))
     ++i_grid;
-    e0 = e1;
-    e1 = ld(energy + i_grid + 1);
+  return i_grid;
+}
+
+// grid index + the bracketing energies
+OMC_HD int ce_grid_index(int nuc, int j_fine, const double* energy, int n_grid, double E, double& e0,
+  double& e1)
+{
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  const int2 w = __ldg(reinterpret_cast<const int2*>(DM.fine_window) + (int64_t)nuc * DM.n_fine_bins + j_fine);
+  int lo = w.x, len = w.y - w.x;
+#else
+  const int32_t* w = DM.fine_window + 2 * ((int64_t)nuc * DM.n_fine_bins + j_fine);
+  int lo = w[0], len = w[1] - w[0];
+#endif
+  while (len > 0) { // first index in [lo, hi] whose energy is >= E
+    const int half = len >> 1;
+    if (ld(energy + lo + half) < E) {
+      lo += half + 1;
+      len -= half + 1;
+    } else {
+      len = half;
+    }
   }
+  if (lo >= 1 && lo <= n_grid - 1) {
+    e1 = ld(energy + lo);
+    if (e1 != E) {
+      e0 = ld(energy + lo - 1);
+      return lo - 1;
+    }
+  }
+  const int i_grid = ce_grid_index_reference(nuc, energy, n_grid, E);
+  e0 = ld(energy + i_grid);
+  e1 = ld(energy + i_grid + 1);
+  return i_grid;
+}
+
+OMC_HD void ce_micro_xs(int nuc, int j_fine, double E, MicroXS& micro)
+{
+  const int64_t g0 = ld(DM.nuc_grid_ofs + nuc);
+  const int n_grid = (int)(ld(DM.nuc_grid_ofs + nuc + 1) - g0);
+  double e0, e1;
+  const int i_grid = ce_grid_index(nuc, j_fine, DM.nuc_energy + g0, n_grid, E, e0, e1);
   const double f = (E - e0) / (e1 - e0);
   micro.index_grid = i_grid;
   micro.interp_factor = f;
@@ -922,163 +977,26 @@ OMC_HD double ce_reaction_xs(int rx, const MicroXS& micro)
   return (1.0 - micro.interp_factor) * ld(v) + micro.interp_factor * ld(v + 1);
 }
 
-// Material::calculate_neutron_xs: out[4] = total, absorption, fission, nu-fission.
-//
-// The reference walks the nuclides one after another; each walk is a chain of
-// dependent gathers (hash pair -> ~4 search probes -> energy pair -> two xs
-// rows), so one lane would have a single load in flight.  Here XS_BATCH
-// nuclides advance through that chain in lockstep -- the loads of one stage are
-// independent across the batch and overlap -- and the partial sums are then
-// added in nuclide order, so every sum sees the same operands in the same order
-// as the reference (results are bit-identical to the one-at-a-time walk).
-#ifndef OMC_XS_BATCH
-#define OMC_XS_BATCH 1 /* measured on C2 (3-5 nuclides per material, L2-resident data): batching costs
-                          more in occupancy (139 vs 46 registers) than it gains; see profiles/README.md */
-#endif
-constexpr int XS_BATCH = OMC_XS_BATCH;
-
+// Material::calculate_neutron_xs (src/material.cpp:829-901): out = total, absorption,
+// fission, nu-fission, accumulated in nuclide order.  (Walking several nuclides of a
+// material in lockstep was measured slower on C2 -- it costs more in registers, i.e.
+// occupancy, than the overlapped loads gain; profiles/README.md, step r07.)
 OMC_HD void ce_macro_xs(int m, double E, double& t, double& a, double& f, double& nf,
   int32_t* i_grid_out, int max_nuc)
 {
   t = a = f = nf = 0.0;
-  const int i_log = ce_log_index(E);
+  const int j_fine = ce_fine_index(E);
   const int k0 = ld(DM.mat_nuc_ofs + m), k1 = ld(DM.mat_nuc_ofs + m + 1);
-  const int n_bins1 = DM.n_log_bins + 1;
-  for (int kb = k0; kb < k1; kb += XS_BATCH) {
-    int nuc[XS_BATCH];
-    const double* energy[XS_BATCH];
-    int64_t g0[XS_BATCH];
-    int lo[XS_BATCH], len[XS_BATCH], base[XS_BATCH], i_grid[XS_BATCH];
-    bool live[XS_BATCH], first_hit[XS_BATCH];
-    // stage 1: which nuclides, where their grids start
-#pragma unroll
-    for (int j = 0; j < XS_BATCH; ++j) {
-      live[j] = kb + j < k1;
-      nuc[j] = ld(DM.mat_nuclide + (live[j] ? kb + j : kb));
-    }
-    int n_grid[XS_BATCH];
-#pragma unroll
-    for (int j = 0; j < XS_BATCH; ++j) {
-      g0[j] = ld(DM.nuc_grid_ofs + nuc[j]);
-      n_grid[j] = (int)(ld(DM.nuc_grid_ofs + nuc[j] + 1) - g0[j]);
-      energy[j] = DM.nuc_energy + g0[j];
-    }
-    // stage 2: grid ends (clipping, src/nuclide.cpp:725-728) and the hash window (:732-737)
-    double e_first[XS_BATCH], e_last[XS_BATCH];
-    int i_low[XS_BATCH], i_high[XS_BATCH];
-#pragma unroll
-    for (int j = 0; j < XS_BATCH; ++j) {
-      e_first[j] = ld(energy[j]);
-      e_last[j] = ld(energy[j] + n_grid[j] - 1);
-      const int32_t* gi = DM.nuc_grid_index + (int64_t)nuc[j] * n_bins1 + i_log;
-      i_low[j] = ld(gi);
-      i_high[j] = ld(gi + 1) + 1;
-    }
-    double e_window0[XS_BATCH];
-#pragma unroll
-    for (int j = 0; j < XS_BATCH; ++j)
-      e_window0[j] = ld(energy[j] + i_low[j]);
-#pragma unroll
-    for (int j = 0; j < XS_BATCH; ++j) {
-      base[j] = i_low[j];
-      lo[j] = 0;
-      len[j] = i_high[j] - i_low[j];
-      first_hit[j] = false;
-      i_grid[j] = 0;
-      if (E < e_first[j]) {
-        len[j] = 0;
-        base[j] = -1; // i_grid = 0
-      } else if (E > e_last[j]) {
-        len[j] = 0;
-        base[j] = -2; // i_grid = n_grid - 2
-      } else if (e_window0[j] == E) { // lower_bound_index: a[0] == value -> 0
-        len[j] = 0;
-        first_hit[j] = true;
-      }
-    }
-    // stage 3: std::lower_bound over the window, all nuclides of the batch in step
-    bool any = true;
-    while (any) {
-      any = false;
-      double probe[XS_BATCH];
-#pragma unroll
-      for (int j = 0; j < XS_BATCH; ++j)
-        if (len[j] > 0)
-          probe[j] = ld(energy[j] + base[j] + lo[j] + (len[j] >> 1));
-#pragma unroll
-      for (int j = 0; j < XS_BATCH; ++j)
-        if (len[j] > 0) {
-          const int half = len[j] >> 1;
-          if (probe[j] < E) {
-            lo[j] += half + 1;
-            len[j] -= half + 1;
-          } else {
-            len[j] = half;
-          }
-          any = any || len[j] > 0;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < XS_BATCH; ++j) {
-      if (base[j] == -1)
-        i_grid[j] = 0;
-      else if (base[j] == -2)
-        i_grid[j] = n_grid[j] - 2;
-      else
-        i_grid[j] = first_hit[j] ? i_low[j] : i_low[j] + lo[j] - 1;
-    }
-    // stage 4: bracketing energies (+ duplicate-point bump, :741-742)
-    double e0[XS_BATCH], e1[XS_BATCH];
-#pragma unroll
-    for (int j = 0; j < XS_BATCH; ++j) {
-      e0[j] = ld(energy[j] + i_grid[j]);
-      e1[j] = ld(energy[j] + i_grid[j] + 1);
-    }
-#pragma unroll
-    for (int j = 0; j < XS_BATCH; ++j)
-      if (e0[j] == e1[j]) {
-        ++i_grid[j];
-        e0[j] = e1[j];
-        e1[j] = ld(energy[j] + i_grid[j] + 1);
-      }
-    // stage 5: the two xs rows (two adjacent 32-byte sectors), density, fissionable flag
-    double ra[XS_BATCH][4], rb[XS_BATCH][4], rho[XS_BATCH];
-    int fis[XS_BATCH];
-#pragma unroll
-    for (int j = 0; j < XS_BATCH; ++j) {
-#if OMC_CUDA && defined(__CUDA_ARCH__)
-      const double2* row = reinterpret_cast<const double2*>(DM.nuc_xs) + 2 * (g0[j] + i_grid[j]);
-      const double2 a01 = __ldg(row), a23 = __ldg(row + 1), b01 = __ldg(row + 2), b23 = __ldg(row + 3);
-      ra[j][0] = a01.x; ra[j][1] = a01.y; ra[j][2] = a23.x; ra[j][3] = a23.y;
-      rb[j][0] = b01.x; rb[j][1] = b01.y; rb[j][2] = b23.x; rb[j][3] = b23.y;
-#else
-      const double* row = DM.nuc_xs + 4 * (g0[j] + i_grid[j]);
-      for (int c = 0; c < 4; ++c) {
-        ra[j][c] = row[c];
-        rb[j][c] = row[4 + c];
-      }
-#endif
-      rho[j] = ld(DM.mat_atom_density + (live[j] ? kb + j : kb));
-      fis[j] = ld(DM.nuc_fissionable + nuc[j]);
-    }
-    // accumulate in nuclide order (src/material.cpp:893-899)
-#pragma unroll
-    for (int j = 0; j < XS_BATCH; ++j) {
-      if (!live[j])
-        continue;
-      const double fr = (E - e0[j]) / (e1[j] - e0[j]);
-      t += rho[j] * ((1.0 - fr) * ra[j][0] + fr * rb[j][0]);
-      a += rho[j] * ((1.0 - fr) * ra[j][1] + fr * rb[j][1]);
-      if (fis[j]) {
-        f += rho[j] * ((1.0 - fr) * ra[j][2] + fr * rb[j][2]);
-        nf += rho[j] * ((1.0 - fr) * ra[j][3] + fr * rb[j][3]);
-      } else {
-        f += rho[j] * 0.0;
-        nf += rho[j] * 0.0;
-      }
-      if (i_grid_out && (kb + j - k0) < max_nuc)
-        i_grid_out[kb + j - k0] = i_grid[j];
-    }
+  for (int k = k0; k < k1; ++k) {
+    MicroXS micro;
+    ce_micro_xs(ld(DM.mat_nuclide + k), j_fine, E, micro);
+    const double rho = ld(DM.mat_atom_density + k);
+    t += rho * micro.total;
+    a += rho * micro.absorption;
+    f += rho * micro.fission;
+    nf += rho * micro.nu_fission;
+    if (i_grid_out && (k - k0) < max_nuc)
+      i_grid_out[k - k0] = micro.index_grid;
   }
 }
 
@@ -1340,7 +1258,7 @@ OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no
 {
   no_nuclide = false;
   const int m = p.material;
-  const int i_log = ce_log_index(p.E);
+  const int i_log = ce_fine_index(p.E); // fine-hash bin handed to ce_micro_xs
   const double cutoff = prn(p.seed) * p.xs_total; // sample_nuclide :494-518
   double prob = 0.0;
   int nuc = -1;

@@ -38,7 +38,10 @@ namespace omc {
 #endif
 constexpr int BLOCK = OMC_BLOCK;
 #ifndef XA_MINBLOCKS
-#define XA_MINBLOCKS 1 /* resident blocks per SM asked of the fused event kernels (register cap) */
+#define XA_MINBLOCKS 3 /* resident blocks per SM asked of k_xs_advance / k_surface_xa (register cap) */
+#endif
+#ifndef CX_MINBLOCKS
+#define CX_MINBLOCKS 2 /* the same for k_collide / k_collide_xa */
 #endif
 
 // -----------------------------------------------------------------------------
@@ -92,6 +95,50 @@ OMC_D void queue_append(const Queue& q, int32_t value)
   q.idx[base + g.thread_rank()] = value;
 #else
   q.idx[(*q.count)++] = value;
+#endif
+}
+
+// The event kernels are chains of dependent gathers (work-list entry -> particle
+// sectors -> model data), and the particle's sectors mostly miss L2.  Asking L2
+// for all of them as soon as the particle index is known turns a chain of DRAM
+// round trips into one (the later loads find their sector in L2 or in flight);
+// a prefetch holds no register.
+OMC_D void prefetch_l2(const void* p)
+{
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(p)));
+#else
+  (void)p;
+#endif
+}
+
+#if OMC_CUDA
+__constant__ int c_prefetch = 1; // OMCGPU_PREFETCH=0 turns the sector prefetch off (A/B measurements)
+#endif
+
+OMC_D void prefetch_particle(const PState& ps, int64_t i, bool collision)
+{
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  if (!c_prefetch)
+    return;
+  prefetch_l2(&ps.n_coord[i]);  // P4
+  prefetch_l2(&ps.E[i]);        // P1
+  prefetch_l2(&ps.xs_total[i]); // P2
+  prefetch_l2(&ps.k_abs[i]);    // P3
+  prefetch_l2(&ps.sqrtkT[i]);   // P5
+  const int L = DM.n_coord_levels < 3 ? DM.n_coord_levels : 3;
+  for (int l = 0; l < L; ++l) {
+    prefetch_l2(&ps.rx[(int64_t)l * ps.cap + i]); // A[l]
+    prefetch_l2(&ps.ux[(int64_t)l * ps.cap + i]); // B[l]
+    if (DM.n_lattices > 0 && l > 0)
+      prefetch_l2(&ps.lat_x[(int64_t)l * ps.cap + i]); // C[l]
+  }
+  if (collision)
+    prefetch_l2(ps.n_progeny + i);
+#else
+  (void)ps;
+  (void)i;
+  (void)collision;
 #endif
 }
 
@@ -530,6 +577,7 @@ OMC_D void body_xs_advance(int64_t tid, const EvArgs& a)
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = a.q_in.idx[tid];
+  prefetch_particle(a.ps, i, false);
   ev_xs(a.ps, i);
   advance_and_route(tid, a, i);
 }
@@ -547,6 +595,7 @@ OMC_D void body_surface_xa(int64_t tid, const EvArgs& a)
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = a.q_in.idx[tid];
+  prefetch_particle(a.ps, i, false);
   if (ev_surface(a.ps, a.gc, i)) {
     ev_xs(a.ps, i);
     advance_and_route(tid, a, i);
@@ -561,6 +610,7 @@ OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = a.q_in.idx[tid];
+  prefetch_particle(a.ps, i, true);
   if (ev_collide(a.ps, a.gc, a.fb, i)) {
     ev_xs(a.ps, i);
     advance_and_route(tid, a, i);
@@ -568,7 +618,7 @@ OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
     no_flight(a, tid);
   }
 }
-OMC_KERNEL_MB(k_collide_xa, EvArgs, body_collide_xa, XA_MINBLOCKS)
+OMC_KERNEL_MB(k_collide_xa, EvArgs, body_collide_xa, CX_MINBLOCKS)
 
 // -----------------------------------------------------------------------------
 // k_score -- tracklength tally scoring for the flights k_advance just recorded
@@ -853,6 +903,7 @@ OMC_D void body_surface(int64_t tid, const EvArgs& a)
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = a.q_in.idx[tid];
+  prefetch_particle(a.ps, i, false);
   if (ev_surface(a.ps, a.gc, i))
     queue_append(a.q_a, i);
 }
@@ -863,10 +914,11 @@ OMC_D void body_collide(int64_t tid, const EvArgs& a)
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = a.q_in.idx[tid];
+  prefetch_particle(a.ps, i, true);
   if (ev_collide(a.ps, a.gc, a.fb, i))
     queue_append(a.q_a, i);
 }
-OMC_KERNEL(k_collide, EvArgs, body_collide)
+OMC_KERNEL_MB(k_collide, EvArgs, body_collide, CX_MINBLOCKS)
 
 // The tail of a generation (few particles left, launch-latency bound): one
 // thread runs the remaining events of one history to completion with the very
@@ -1370,6 +1422,40 @@ static int upload_model(const omcgpu_model* m)
     UP(nuc_energy, n_pts);
     UP(nuc_xs, (size_t)n_pts * 4);
     UP(nuc_grid_index, (size_t)nn * (h.n_log_bins + 1));
+    // fine hash (see ce_fine_index): per nuclide one merge of the sorted grid with
+    // the sorted, widened bin edges
+    std::vector<int32_t> fine;
+    {
+      int per = OMCGPU_FINE_PER_LOG_BIN;
+      if (const char* t = std::getenv("OMCGPU_FINE_PER_LOG_BIN"))
+        per = std::max(1, std::atoi(t));
+      const int nf = h.n_log_bins * per;
+      h.n_fine_bins = nf;
+      const double total = h.log_spacing * h.n_log_bins;
+      h.fine_inv_spacing = nf / total;
+      const double sp = total / nf, widen = 1e-6;
+      std::vector<double> e_lo(nf), e_hi(nf);
+      for (int j = 0; j < nf; ++j) {
+        e_lo[j] = j == 0 ? 0.0 : h.energy_min * std::exp((j - widen) * sp) * (1.0 - 1e-12);
+        e_hi[j] = j == nf - 1 ? INFINITY : h.energy_min * std::exp((j + 1 + widen) * sp) * (1.0 + 1e-12);
+      }
+      fine.resize((size_t)nn * nf * 2);
+      for (int k = 0; k < nn; ++k) {
+        const double* e = m->nuc_energy + m->nuc_grid_ofs[k];
+        const int64_t ng = m->nuc_grid_ofs[k + 1] - m->nuc_grid_ofs[k];
+        int64_t c_lo = 0, c_hi = 0; // number of grid points below the edge (edges ascend)
+        for (int j = 0; j < nf; ++j) {
+          while (c_lo < ng && e[c_lo] < e_lo[j])
+            ++c_lo;
+          while (c_hi < ng && e[c_hi] < e_hi[j])
+            ++c_hi;
+          fine[((size_t)k * nf + j) * 2 + 0] = (int32_t)c_lo;
+          fine[((size_t)k * nf + j) * 2 + 1] = (int32_t)c_hi;
+        }
+      }
+      h.fine_window = fine.data();
+    }
+    UP(fine_window, fine.size());
     UP(nuc_rx_ofs, nn + 1);
     UP(nuc_fission_rx, nn);
     UP(nuc_n_precursor, nn);
@@ -2016,10 +2102,25 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
     return rc;
   if (max_particles > 2000000000LL / 3)
     return fail(OMCGPU_E_OUT_OF_BOUNDS, "max_particles too large for 32-bit work lists%s");
+#if OMC_CUDA
+  {
+    // the event kernels are the critical path of a sweep; k_score only has to be done
+    // two sweeps later, so its blocks take the SM slots the event kernels leave
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const char* t = std::getenv("OMCGPU_PRIORITY");
+    const bool use = !t || std::atoi(t) != 0;
+    CUDA_OK(cudaStreamCreateWithPriority(&G.stream, cudaStreamDefault, use ? prio_hi : prio_lo));
+    CUDA_OK(cudaStreamCreateWithPriority(&G.s_surf, cudaStreamDefault, use ? prio_hi : prio_lo));
+    CUDA_OK(cudaStreamCreateWithPriority(&G.s_coll, cudaStreamDefault, use ? prio_hi : prio_lo));
+    CUDA_OK(cudaStreamCreateWithPriority(&G.s_score, cudaStreamDefault, prio_lo));
+  }
+#else
   CUDA_OK(cudaStreamCreate(&G.stream));
   CUDA_OK(cudaStreamCreate(&G.s_score));
   CUDA_OK(cudaStreamCreate(&G.s_surf));
   CUDA_OK(cudaStreamCreate(&G.s_coll));
+#endif
   if (const char* t = std::getenv("OMCGPU_FUSE_XS"))
     G.fuse_xs = std::atoi(t) != 0;
   if (const char* t = std::getenv("OMCGPU_OVERLAP"))
@@ -2130,6 +2231,12 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
         G.tally_needs_cells = true;
   }
 #if OMC_CUDA
+  {
+    int pf = 1;
+    if (const char* t = std::getenv("OMCGPU_PREFETCH"))
+      pf = std::atoi(t) != 0;
+    CUDA_OK(cudaMemcpyToSymbol(c_prefetch, &pf, sizeof(int)));
+  }
   CUDA_OK(cudaMemcpyToSymbol(c_ps, &G.ps, sizeof(PState)));
   CUDA_OK(cudaMemcpyToSymbol(c_fl, G.fl, 4 * sizeof(Flights)));
 #endif
@@ -2411,8 +2518,10 @@ int omcgpu_calculate_xs(const double* E, const int32_t* material, int64_t n, dou
   CUDA_OK(cudaMalloc((void**)&dE, n * sizeof(double)));
   CUDA_OK(cudaMalloc((void**)&dm, n * sizeof(int32_t)));
   CUDA_OK(cudaMalloc((void**)&dout, n * 4 * sizeof(double)));
-  if (i_grid)
+  if (i_grid) { // entries beyond the material's nuclide count stay 0
     CUDA_OK(cudaMalloc((void**)&dig, n * max_nuc * sizeof(int32_t)));
+    CUDA_OK(cudaMemset(dig, 0, n * max_nuc * sizeof(int32_t)));
+  }
   CUDA_OK(cudaMemcpy(dE, E, n * sizeof(double), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(dm, material, n * sizeof(int32_t), cudaMemcpyHostToDevice));
   XsArgs a;

@@ -70,6 +70,11 @@ def xs_probe_energies(model, libx, n, seed=7):
     spacing = float(model["log_spacing"])
     edges = e_min * np.exp(spacing * g.integers(1, int(model["n_log_bins"]), n // 10))
     near = np.concatenate([np.nextafter(edges, 0), edges, np.nextafter(edges, np.inf)])
+    # edges of the device's fine hash (OMCGPU_FINE_PER_LOG_BIN bins per reference bin)
+    from openmc_b200 import _abi as abi
+    per = abi.OMCGPU_FINE_PER_LOG_BIN
+    fine = e_min * np.exp(spacing / per * g.integers(1, int(model["n_log_bins"]) * per, n // 10))
+    near = np.concatenate([near, np.nextafter(fine, 0), fine, np.nextafter(fine, np.inf)])
     special = np.array([e_min, e_max, e_min * 0.5, e_max * 1.5, np.nextafter(e_min, 1), np.nextafter(e_max, 0)])
     return np.concatenate([E, pick, np.nextafter(pick, 0), np.nextafter(pick, np.inf), near, special])
 
