@@ -123,6 +123,9 @@ struct PState {
   Col<int32_t, 8> b_surface, b_level_trans, g_last;
   // plain column (scanned by cub for the fission-bank sort)
   int32_t* n_progeny;
+  // plain column: the event the history waits for after this sweep (0 none / dead,
+  // 1 collision, 2 crossing) -- input of the order-preserving list build
+  uint8_t* next_ev;
 };
 
 // Flight records: what tracklength scoring needs from one flight, written by

@@ -23,6 +23,8 @@
 #if OMC_CUDA
 #include <cooperative_groups.h>
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/discard_iterator.h>
 #include <cuda_runtime.h>
 namespace cg = cooperative_groups;
 #else
@@ -113,7 +115,7 @@ OMC_D void prefetch_l2(const void* p)
 }
 
 #if OMC_CUDA
-__constant__ int c_prefetch = 1; // OMCGPU_PREFETCH=0 turns the sector prefetch off (A/B measurements)
+__constant__ int c_prefetch = 0; // OMCGPU_PREFETCH=1 turns the sector prefetch on (A/B measurements)
 #endif
 
 OMC_D void prefetch_particle(const PState& ps, int64_t i, bool collision)
@@ -155,6 +157,7 @@ struct EvArgs {
   int32_t fl_buf;       // which of the two record buffers `fl` is (c_fl[fl_buf])
   const int32_t* n_flights; // device count of records (its ring slot outlives the sweep)
   int32_t first_event;      // k_tail: event the histories of q_in are waiting for (NEXT_NONE: a flight)
+  int32_t ordered;          // survivors are flagged in ps.next_ev (lists built in index order) instead of appended
 };
 
 enum { NEXT_NONE = -2, NEXT_DEAD = -1, NEXT_COLLISION = 0, NEXT_SURFACE = 1 };
@@ -552,6 +555,12 @@ OMC_D void no_flight(const EvArgs& a, int64_t tid)
 OMC_D void advance_and_route(int64_t tid, const EvArgs& a, int32_t i)
 {
   const int next = ev_advance(a.ps, a.gc, a.fl, i, tid);
+  if (a.ordered) {
+    a.ps.next_ev[i] = next == NEXT_COLLISION ? 1 : (next == NEXT_SURFACE ? 2 : 0);
+    if (next == NEXT_DEAD)
+      no_flight(a, tid);
+    return;
+  }
   if (next == NEXT_COLLISION)
     queue_append(a.q_a, i);
   else if (next == NEXT_SURFACE)
@@ -601,6 +610,8 @@ OMC_D void body_surface_xa(int64_t tid, const EvArgs& a)
     advance_and_route(tid, a, i);
   } else {
     no_flight(a, tid);
+    if (a.ordered)
+      a.ps.next_ev[i] = 0;
   }
 }
 OMC_KERNEL_MB(k_surface_xa, EvArgs, body_surface_xa, XA_MINBLOCKS)
@@ -616,6 +627,8 @@ OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
     advance_and_route(tid, a, i);
   } else {
     no_flight(a, tid);
+    if (a.ordered)
+      a.ps.next_ev[i] = 0;
   }
 }
 OMC_KERNEL_MB(k_collide_xa, EvArgs, body_collide_xa, CX_MINBLOCKS)
@@ -1256,6 +1269,9 @@ struct Engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evx0[RING] = {}, evx1[RING] = {}, evp0 = nullptr, evp1 = nullptr;
   bool fuse_xs = true;          // k_xs + k_advance as one kernel (ms_xs then covers both)
+  bool ordered = true;          // sweep mode 2: lists rebuilt in particle-index order after every sweep
+  void* d_part_tmp = nullptr;   // cub::DevicePartition scratch
+  size_t part_tmp_bytes = 0;
   int sweep_mode = 2;           // 1: xs+advance | surface | collide over a merged alive list; 2: paired lists
   int score_ctas = 0;           // >0: k_score grid capped at this many blocks per SM (persistent, co-resident)
   int n_sm = 148;
@@ -1797,6 +1813,42 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
   return 0;
 }
 
+// Order-preserving list build: the histories flagged 1 in ps.next_ev go to `coll`,
+// those flagged 2 to `surf`, both in ascending particle index, and the two counts
+// to counts[0..1].  Appending with atomics instead leaves every list in the order
+// the warps happened to finish: after a few sweeps a warp's 32 particles are 32
+// unrelated sectors of every column.  Index order keeps a warp's gathers within a
+// few neighbouring lines and DRAM pages.
+#if OMC_CUDA
+struct FlagIs {
+  const uint8_t* f;
+  uint8_t v;
+  __device__ __forceinline__ bool operator()(int i) const { return f[i] == v; }
+};
+#endif
+static int build_lists(int64_t n, int32_t* coll, int32_t* surf, int32_t* counts, cudaStream_t stream)
+{
+#if OMC_CUDA
+  FlagIs is_coll{G.ps.next_ev, 1}, is_surf{G.ps.next_ev, 2};
+  thrust::counting_iterator<int32_t> ids(0);
+  thrust::discard_iterator<> none;
+  size_t bytes = G.part_tmp_bytes;
+  CUDA_OK(cub::DevicePartition::If(G.d_part_tmp, bytes, ids, coll, surf, none, counts, (int)n, is_coll,
+    is_surf, stream));
+  g_launches += 2;
+#else
+  (void)stream;
+  counts[0] = counts[1] = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (G.ps.next_ev[i] == 1)
+      coll[counts[0]++] = (int32_t)i;
+    else if (G.ps.next_ev[i] == 2)
+      surf[counts[1]++] = (int32_t)i;
+  }
+#endif
+  return 0;
+}
+
 // ---- sweep mode 2: paired lists ----------------------------------------------------
 // Lists of "generation" g (g = 0 after the first flight): C[g & 1] = histories
 // waiting for a collision, S[g & 1] = for a crossing; their counters live in ring
@@ -1831,8 +1883,16 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
   a.fl = G.fl[0];
   a.fl_buf = 0;
   a.n_flights = G.d_counts + 0;
+  a.ordered = G.ordered ? 1 : 0;
+  if (G.ordered) // histories that never fly (zero weight, lost at birth) carry no flag
+    CUDA_OK(cudaMemsetAsync(G.ps.next_ev, 0, (size_t)n, G.stream));
   CUDA_OK(cudaEventRecord(G.evx0[0], G.stream));
   OMC_LAUNCH(k_xs_advance, n_alive0, G.stream, a);
+  if (G.ordered) {
+    rc = build_lists(n, G.q[0].idx, G.q[2].idx, slot_of(0), G.stream);
+    if (rc)
+      return rc;
+  }
   CUDA_OK(cudaEventRecord(G.evx1[0], G.stream));
   if (score) {
     if (G.overlap) {
@@ -1895,6 +1955,11 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       CUDA_OK(cudaEventRecord(G.e_coll, st_coll));
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_surf, 0));
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_coll, 0));
+    }
+    if (G.ordered) {
+      rc = build_lists(n, G.q[po].idx, G.q[2 + po].idx, out_slot, G.stream);
+      if (rc)
+        return rc;
     }
     CUDA_OK(cudaEventRecord(G.evx1[ev], G.stream));
     if (score) {
@@ -2109,7 +2174,7 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     const char* t = std::getenv("OMCGPU_PRIORITY");
-    const bool use = !t || std::atoi(t) != 0;
+    const bool use = t && std::atoi(t) != 0; // measured: no gain on C2 (profiles/README.md r10), default off
     CUDA_OK(cudaStreamCreateWithPriority(&G.stream, cudaStreamDefault, use ? prio_hi : prio_lo));
     CUDA_OK(cudaStreamCreateWithPriority(&G.s_surf, cudaStreamDefault, use ? prio_hi : prio_lo));
     CUDA_OK(cudaStreamCreateWithPriority(&G.s_coll, cudaStreamDefault, use ? prio_hi : prio_lo));
@@ -2127,6 +2192,8 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
     G.overlap = std::atoi(t) != 0;
   if (const char* t = std::getenv("OMCGPU_SWEEP"))
     G.sweep_mode = std::atoi(t) == 1 ? 1 : 2;
+  if (const char* t = std::getenv("OMCGPU_ORDERED"))
+    G.ordered = std::atoi(t) != 0;
   if (const char* t = std::getenv("OMCGPU_SCORE_CTAS"))
     G.score_ctas = std::max(0, std::atoi(t));
 #if OMC_CUDA
@@ -2165,6 +2232,7 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
     rc = rc ? rc : dev_alloc(&p4, (size_t)cap * 32);
     rc = rc ? rc : dev_alloc(&p5, (size_t)cap * 32);
     rc = rc ? rc : dev_alloc(&ps.n_progeny, (size_t)cap);
+    rc = rc ? rc : dev_alloc(&ps.next_ev, (size_t)cap);
     if (rc)
       return rc;
 #define D(col, base, slot) ps.col.p = reinterpret_cast<double*>(base) + (slot)
@@ -2210,6 +2278,19 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   if (rc)
     return rc;
   G.d_scan_tmp = tmp;
+  {
+    FlagIs f1{nullptr, 1}, f2{nullptr, 2};
+    thrust::counting_iterator<int32_t> ids(0);
+    thrust::discard_iterator<> none;
+    G.part_tmp_bytes = 0;
+    cub::DevicePartition::If(nullptr, G.part_tmp_bytes, ids, (int32_t*)nullptr, (int32_t*)nullptr, none,
+      (int32_t*)nullptr, (int)cap, f1, f2);
+    char* ptmp = nullptr;
+    rc = dev_alloc(&ptmp, G.part_tmp_bytes + 16);
+    if (rc)
+      return rc;
+    G.d_part_tmp = ptmp;
+  }
 #endif
   {
     // flight records: one per work-list position in a sweep; the tail kernel logs
@@ -2232,7 +2313,7 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   }
 #if OMC_CUDA
   {
-    int pf = 1;
+    int pf = 0; // measured: no gain on C2 (profiles/README.md r10), default off
     if (const char* t = std::getenv("OMCGPU_PREFETCH"))
       pf = std::atoi(t) != 0;
     CUDA_OK(cudaMemcpyToSymbol(c_prefetch, &pf, sizeof(int)));
