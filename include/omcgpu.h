@@ -221,12 +221,12 @@ typedef struct omcgpu_model {
   double log_spacing;             /* simulation::log_spacing                           */
   const double* hash_edge;        /* [n_log_bins+2] smallest E whose host-libm hash bin is k */
   /* derived by omcgpu_init (ignored on input): fine hash, OMCGPU_FINE_PER_LOG_BIN
-   * equal-lethargy bins per reference bin; fine_window[nuc][bin] = {lo, hi}
+   * equal-lethargy bins per reference bin; fine_window[bin][nuc] = {lo, hi}
    * brackets the number of grid points below any energy of the (widened) bin */
   int32_t n_fine_bins;
   int32_t reserved_ce;
   double fine_inv_spacing;        /* n_fine_bins / log(energy_max / energy_min)       */
-  const int32_t* fine_window;     /* [n_nuclides][n_fine_bins][2]                      */
+  const int32_t* fine_window;     /* [n_fine_bins][n_nuclides][2]                      */
   const double* nuc_awr;          /* [n_nuclides]                                      */
   const double* nuc_kT;           /* [n_nuclides] kT of the single loaded temperature  */
   const int32_t* nuc_fissionable; /* [n_nuclides]                                      */

@@ -866,7 +866,8 @@ OMC_HD int ce_log_index(double E)
 }
 
 // Fine hash (derived by omcgpu_init): DM.n_fine_bins = FINE_PER_LOG_BIN x n_log_bins
-// equal-lethargy bins; fine_window[nuc][j] = {lo, hi} brackets, for every energy the
+// equal-lethargy bins; fine_window[j][nuc] = {lo, hi} (bin-major: the nuclides of a
+// material share the sectors of bin j) brackets, for every energy the
 // device may map to bin j, K = the number of grid points below E.  The windows are
 // built from bin edges widened by 1e-6 of a bin, so the bin does not have to be
 // bit-exact (the device log() may differ from libm in the last ulp) and holds ~1
@@ -908,10 +909,10 @@ OMC_HD int ce_grid_index(int nuc, int j_fine, const double* energy, int n_grid, 
   double& e1)
 {
 #if OMC_CUDA && defined(__CUDA_ARCH__)
-  const int2 w = __ldg(reinterpret_cast<const int2*>(DM.fine_window) + (int64_t)nuc * DM.n_fine_bins + j_fine);
+  const int2 w = __ldg(reinterpret_cast<const int2*>(DM.fine_window) + (int64_t)j_fine * DM.n_nuclides + nuc);
   int lo = w.x, len = w.y - w.x;
 #else
-  const int32_t* w = DM.fine_window + 2 * ((int64_t)nuc * DM.n_fine_bins + j_fine);
+  const int32_t* w = DM.fine_window + 2 * ((int64_t)j_fine * DM.n_nuclides + nuc);
   int lo = w[0], len = w[1] - w[0];
 #endif
   while (len > 0) { // first index in [lo, hi] whose energy is >= E
@@ -977,16 +978,134 @@ OMC_HD double ce_reaction_xs(int rx, const MicroXS& micro)
   return (1.0 - micro.interp_factor) * ld(v) + micro.interp_factor * ld(v + 1);
 }
 
+// Materials with many nuclides (depleted fuel, config C5: ~300): NB nuclides walk the
+// lookup chain (window -> probes -> bracketing energies -> two xs rows) in lockstep, so
+// that the loads of one stage are independent and overlap; the partial sums are added
+// in nuclide order afterwards, i.e. every sum sees the same operands in the same order
+// as the one-at-a-time walk (bit-identical results).
+#ifndef OMC_XS_BATCH
+#define OMC_XS_BATCH 4
+#endif
+#ifndef OMC_XS_BATCH_MIN
+#define OMC_XS_BATCH_MIN 16 /* nuclides in the material from which the lockstep walk is used */
+#endif
+template<int NB>
+OMC_HD void ce_macro_xs_batch(int k0, int k1, int j_fine, double E, double& t, double& a, double& f,
+  double& nf, int32_t* i_grid_out, int max_nuc)
+{
+  for (int kb = k0; kb < k1; kb += NB) {
+    int nuc[NB], n_grid[NB], lo[NB], len[NB], ig[NB];
+    const double* energy[NB];
+    int64_t g0[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      nuc[j] = ld(DM.mat_nuclide + (kb + j < k1 ? kb + j : k1 - 1));
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      g0[j] = ld(DM.nuc_grid_ofs + nuc[j]);
+      n_grid[j] = (int)(ld(DM.nuc_grid_ofs + nuc[j] + 1) - g0[j]);
+      energy[j] = DM.nuc_energy + g0[j];
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+      const int2 w = __ldg(reinterpret_cast<const int2*>(DM.fine_window) + (int64_t)j_fine * DM.n_nuclides + nuc[j]);
+      lo[j] = w.x;
+      len[j] = w.y - w.x;
+#else
+      const int32_t* w = DM.fine_window + 2 * ((int64_t)j_fine * DM.n_nuclides + nuc[j]);
+      lo[j] = w[0];
+      len[j] = w[1] - w[0];
+#endif
+    }
+    bool any = true;
+    while (any) { // lower bound of E inside every window, in step
+      any = false;
+      double probe[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (len[j] > 0)
+          probe[j] = ld(energy[j] + lo[j] + (len[j] >> 1));
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (len[j] > 0) {
+          const int half = len[j] >> 1;
+          if (probe[j] < E) {
+            lo[j] += half + 1;
+            len[j] -= half + 1;
+          } else {
+            len[j] = half;
+          }
+          any = any || len[j] > 0;
+        }
+    }
+    double e0[NB], e1[NB];
+    bool fast[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      fast[j] = lo[j] >= 1 && lo[j] <= n_grid[j] - 1;
+      const int k = fast[j] ? lo[j] : 1;
+      e1[j] = ld(energy[j] + k);
+      e0[j] = ld(energy[j] + k - 1);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (fast[j] && e1[j] != E) {
+        ig[j] = lo[j] - 1;
+      } else { // on a grid point or outside the grid: the reference's own window decides
+        ig[j] = ce_grid_index_reference(nuc[j], energy[j], n_grid[j], E);
+        e0[j] = ld(energy[j] + ig[j]);
+        e1[j] = ld(energy[j] + ig[j] + 1);
+      }
+    }
+    double ra[NB][4], rb[NB][4], rho[NB];
+    int fis[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+      const double2* row = reinterpret_cast<const double2*>(DM.nuc_xs) + 2 * (g0[j] + ig[j]);
+      const double2 a01 = __ldg(row), a23 = __ldg(row + 1), b01 = __ldg(row + 2), b23 = __ldg(row + 3);
+      ra[j][0] = a01.x; ra[j][1] = a01.y; ra[j][2] = a23.x; ra[j][3] = a23.y;
+      rb[j][0] = b01.x; rb[j][1] = b01.y; rb[j][2] = b23.x; rb[j][3] = b23.y;
+#else
+      const double* row = DM.nuc_xs + 4 * (g0[j] + ig[j]);
+      for (int c = 0; c < 4; ++c) {
+        ra[j][c] = row[c];
+        rb[j][c] = row[4 + c];
+      }
+#endif
+      rho[j] = ld(DM.mat_atom_density + (kb + j < k1 ? kb + j : k1 - 1));
+      fis[j] = ld(DM.nuc_fissionable + nuc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (kb + j >= k1)
+        continue;
+      const double fr = (E - e0[j]) / (e1[j] - e0[j]);
+      t += rho[j] * ((1.0 - fr) * ra[j][0] + fr * rb[j][0]);
+      a += rho[j] * ((1.0 - fr) * ra[j][1] + fr * rb[j][1]);
+      f += rho[j] * (fis[j] ? (1.0 - fr) * ra[j][2] + fr * rb[j][2] : 0.0);
+      nf += rho[j] * (fis[j] ? (1.0 - fr) * ra[j][3] + fr * rb[j][3] : 0.0);
+      if (i_grid_out && (kb + j - k0) < max_nuc)
+        i_grid_out[kb + j - k0] = ig[j];
+    }
+  }
+}
+
 // Material::calculate_neutron_xs (src/material.cpp:829-901): out = total, absorption,
-// fission, nu-fission, accumulated in nuclide order.  (Walking several nuclides of a
-// material in lockstep was measured slower on C2 -- it costs more in registers, i.e.
-// occupancy, than the overlapped loads gain; profiles/README.md, step r07.)
+// fission, nu-fission, accumulated in nuclide order.  Few nuclides (C2/C3: 1-5 per
+// material): one at a time -- measured faster there than the lockstep walk, which
+// costs registers (profiles/README.md, step r07).
+// BX: the kernel was compiled for models with many-nuclide materials (its register
+// budget covers the lockstep walk); the host picks the kernel flavour per model.
+template<bool BX>
 OMC_HD void ce_macro_xs(int m, double E, double& t, double& a, double& f, double& nf,
   int32_t* i_grid_out, int max_nuc)
 {
   t = a = f = nf = 0.0;
   const int j_fine = ce_fine_index(E);
   const int k0 = ld(DM.mat_nuc_ofs + m), k1 = ld(DM.mat_nuc_ofs + m + 1);
+  if (BX && k1 - k0 >= OMC_XS_BATCH_MIN) {
+    ce_macro_xs_batch<OMC_XS_BATCH>(k0, k1, j_fine, E, t, a, f, nf, i_grid_out, max_nuc);
+    return;
+  }
   for (int k = k0; k < k1; ++k) {
     MicroXS micro;
     ce_micro_xs(ld(DM.mat_nuclide + k), j_fine, E, micro);
@@ -1515,8 +1634,14 @@ OMC_HD int mesh_index(double r, double ll, double w)
 // formula, so the parts emit the same (bin, length) pairs as the whole track,
 // with the pair that straddles a cut emitted as two pieces.
 // emit(bin, w): w = fraction of `total` spent in mesh bin `bin`.
+// (kept out of line on the device: the rare path of k_score, whose hot loop is the DDA below)
 template<class Emit>
-OMC_D void mesh_march_exact(int m, V3 r0, V3 u, double total, double t0, double t1, Emit& emit)
+#if OMC_CUDA
+__device__ __noinline__
+#else
+inline
+#endif
+void mesh_march_exact(int m, V3 r0, V3 u, double total, double t0, double t1, Emit& emit)
 {
   const int nd = ld(DM.mesh_ndim + m);
   MeshAxis a0, a1, a2;

@@ -40,10 +40,10 @@ namespace omc {
 #endif
 constexpr int BLOCK = OMC_BLOCK;
 #ifndef XA_MINBLOCKS
-#define XA_MINBLOCKS 3 /* resident blocks per SM asked of k_xs_advance / k_surface_xa (register cap) */
+#define XA_MINBLOCKS 4 /* resident blocks per SM asked of k_xs_advance / k_surface_xa (register cap) */
 #endif
 #ifndef CX_MINBLOCKS
-#define CX_MINBLOCKS 2 /* the same for k_collide / k_collide_xa */
+#define CX_MINBLOCKS 3 /* the same for k_collide / k_collide_xa (measured: profiles/README.md r10-r11) */
 #endif
 
 // -----------------------------------------------------------------------------
@@ -84,6 +84,18 @@ static int64_t g_launches = 0;
     } \
   } while (0)
 #endif
+
+// kernels that contain the cross-section lookup exist in two flavours: `name` (one
+// nuclide at a time) and `name_b` (lockstep walk for many-nuclide materials, larger
+// register budget); G.batch_xs is decided per model in omcgpu_init
+#define LAUNCH_XS(name, n_ub, stream, args) \
+  do { \
+    if (batch_xs_enabled()) \
+      OMC_LAUNCH(name##_b, n_ub, stream, args); \
+    else \
+      OMC_LAUNCH(name, n_ub, stream, args); \
+  } while (0)
+static bool batch_xs_enabled();
 
 // warp-aggregated append (ballot + one atomic per warp), cf. north_star
 OMC_D void queue_append(const Queue& q, int32_t value)
@@ -223,6 +235,7 @@ OMC_D bool ev_init(const PState& ps, const GenCtx& gc, const Bank& src, int64_t 
 }
 
 // Particle::event_calculate_xs, src/particle.cpp:160-230 (locate done at birth)
+template<bool BX = false>
 OMC_D void ev_xs(const PState& ps, int64_t i)
 {
   const int m = ps.material[i];
@@ -236,7 +249,7 @@ OMC_D void ev_xs(const PState& ps, int64_t i)
   if (DM.run_CE) {
     if (m != ps.material_last[i] || ps.sqrtkT[i] != ps.sqrtkT_last[i]) {
       double t, a, f, nf;
-      ce_macro_xs(m, ps.E[i], t, a, f, nf, nullptr, 0);
+      ce_macro_xs<BX>(m, ps.E[i], t, a, f, nf, nullptr, 0);
       ps.xs_total[i] = t;
       ps.xs_absorption[i] = a;
       ps.xs_fission[i] = f;
@@ -534,13 +547,15 @@ OMC_D void body_init(int64_t tid, const EvArgs& a)
 }
 OMC_KERNEL(k_init, EvArgs, body_init)
 
+template<bool BX>
 OMC_D void body_xs(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
     return;
-  ev_xs(a.ps, a.q_in.idx[tid]);
+  ev_xs<BX>(a.ps, a.q_in.idx[tid]);
 }
-OMC_KERNEL_MB(k_xs, EvArgs, body_xs, 2)
+OMC_KERNEL_MB(k_xs, EvArgs, body_xs<false>, 2)
+OMC_KERNEL_MB(k_xs_b, EvArgs, body_xs<true>, 2)
 
 // a work-list position that records no flight this sweep must say so: k_score
 // walks positions, and the record left there by an earlier sweep is stale
@@ -581,16 +596,18 @@ OMC_KERNEL(k_advance, EvArgs, body_advance)
 // alive particle goes through both in every sweep, so unless the xs list is to be
 // re-ordered in between, one kernel saves a launch and one round trip of the
 // particle's sectors through L2
+template<bool BX>
 OMC_D void body_xs_advance(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = a.q_in.idx[tid];
   prefetch_particle(a.ps, i, false);
-  ev_xs(a.ps, i);
+  ev_xs<BX>(a.ps, i);
   advance_and_route(tid, a, i);
 }
-OMC_KERNEL_MB(k_xs_advance, EvArgs, body_xs_advance, XA_MINBLOCKS)
+OMC_KERNEL_MB(k_xs_advance, EvArgs, body_xs_advance<false>, XA_MINBLOCKS)
+OMC_KERNEL_MB(k_xs_advance_b, EvArgs, body_xs_advance<true>, 2)
 
 // Sweep mode 2 (run_sweeps_paired): a crossing or a collision is always followed,
 // for the survivor, by a cross-section lookup and a flight.  One kernel per list
@@ -599,6 +616,7 @@ OMC_KERNEL_MB(k_xs_advance, EvArgs, body_xs_advance, XA_MINBLOCKS)
 // straight into the NEXT sweep's collision / crossing list.  A particle's
 // sectors then travel through L2 once per sweep instead of twice, and the merged
 // "alive" list (one append + one gather per particle and sweep) disappears.
+template<bool BX>
 OMC_D void body_surface_xa(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
@@ -606,7 +624,7 @@ OMC_D void body_surface_xa(int64_t tid, const EvArgs& a)
   const int32_t i = a.q_in.idx[tid];
   prefetch_particle(a.ps, i, false);
   if (ev_surface(a.ps, a.gc, i)) {
-    ev_xs(a.ps, i);
+    ev_xs<BX>(a.ps, i);
     advance_and_route(tid, a, i);
   } else {
     no_flight(a, tid);
@@ -614,8 +632,10 @@ OMC_D void body_surface_xa(int64_t tid, const EvArgs& a)
       a.ps.next_ev[i] = 0;
   }
 }
-OMC_KERNEL_MB(k_surface_xa, EvArgs, body_surface_xa, XA_MINBLOCKS)
+OMC_KERNEL_MB(k_surface_xa, EvArgs, body_surface_xa<false>, XA_MINBLOCKS)
+OMC_KERNEL_MB(k_surface_xa_b, EvArgs, body_surface_xa<true>, 2)
 
+template<bool BX>
 OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
@@ -623,7 +643,7 @@ OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
   const int32_t i = a.q_in.idx[tid];
   prefetch_particle(a.ps, i, true);
   if (ev_collide(a.ps, a.gc, a.fb, i)) {
-    ev_xs(a.ps, i);
+    ev_xs<BX>(a.ps, i);
     advance_and_route(tid, a, i);
   } else {
     no_flight(a, tid);
@@ -631,7 +651,8 @@ OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
       a.ps.next_ev[i] = 0;
   }
 }
-OMC_KERNEL_MB(k_collide_xa, EvArgs, body_collide_xa, CX_MINBLOCKS)
+OMC_KERNEL_MB(k_collide_xa, EvArgs, body_collide_xa<false>, CX_MINBLOCKS)
+OMC_KERNEL_MB(k_collide_xa_b, EvArgs, body_collide_xa<true>, 2)
 
 // -----------------------------------------------------------------------------
 // k_score -- tracklength tally scoring for the flights k_advance just recorded
@@ -649,16 +670,19 @@ constexpr int SCORE_NVAL = OMCGPU_MAX_SCORES;
 #define SCORE_MINBLOCKS 2 /* resident blocks per SM the register budget of k_score allows */
 #endif
 
-struct PartEmit { // simple tally: one bin per non-mesh filter -> base index
+// simple tally: one bin per non-mesh filter -> base index.  NS = scores actually emitted
+// per mesh cell (the loop below is compile-time: no issue slots for absent scores)
+template<int NS>
+struct PartEmit {
   double* results;
   int64_t base;
   int mesh_stride, ns;
-  double val[SCORE_NVAL];
+  double val[NS];
   OMC_D void operator()(int bin, double w) const
   {
     double* r = results + (base + (int64_t)bin * mesh_stride) * ns;
 #pragma unroll
-    for (int s = 0; s < SCORE_NVAL; ++s) // val[s] == 0 beyond ns; compile-time indices keep val in registers
+    for (int s = 0; s < NS; ++s) // compile-time indices keep val in registers
       if (val[s] != 0.0)
         atomic_add_f64(r + s, val[s] * w);
   }
@@ -812,6 +836,33 @@ __device__ __noinline__ int score_lane(int64_t j, int buf, int t, double* values
   return nc;
 }
 
+// the lanes of a warp trace the parts of the warp's 32 flights round-robin
+template<int NS>
+__device__ __forceinline__ void score_parts(int mesh, int mesh_stride, int ns, double* results, int n_parts,
+  int lane, const int* incl, const double (*sd)[32], const int64_t* sbase)
+{
+  PartEmit<NS> em;
+  em.results = results;
+  em.mesh_stride = mesh_stride;
+  em.ns = ns;
+  for (int item = lane; item < n_parts; item += 32) {
+    int o = 0; // owner: first lane whose inclusive count exceeds item
+    for (int step = 16; step > 0; step >>= 1)
+      if (incl[o + step - 1] <= item)
+        o += step;
+    const int c = item - (o > 0 ? incl[o - 1] : 0);
+    const int onc = incl[o] - (o > 0 ? incl[o - 1] : 0);
+    const V3 pr0 = v3(sd[0][o], sd[1][o], sd[2][o]);
+    const V3 pu = v3(sd[3][o], sd[4][o], sd[5][o]);
+    const double ptotal = sd[6][o];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      em.val[s] = sd[7 + s][o];
+    em.base = sbase[o];
+    mesh_march(mesh, pr0, pu, ptotal, part_bound(c, onc, ptotal), part_bound(c + 1, onc, ptotal), em);
+  }
+}
+
 __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, EvArgs a)
 {
   constexpr int WARPS = BLOCK / 32;
@@ -846,26 +897,15 @@ __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, 
       continue;
     s_incl[warp][lane] = incl;
     __syncwarp();
-    PartEmit em;
-    em.results = a.gc.tally_values + ld(DM.tally_result_ofs + t);
-    em.mesh_stride = mesh_stride;
-    em.ns = ld(DM.tally_n_scores + t);
-    for (int item = lane; item < n_parts; item += 32) {
-      int o = 0; // owner: first lane whose inclusive count exceeds item
-      for (int step = 16; step > 0; step >>= 1)
-        if (s_incl[warp][o + step - 1] <= item)
-          o += step;
-      const int c = item - (o > 0 ? s_incl[warp][o - 1] : 0);
-      const int onc = s_incl[warp][o] - (o > 0 ? s_incl[warp][o - 1] : 0);
-      const V3 pr0 = v3(s_d[warp][0][o], s_d[warp][1][o], s_d[warp][2][o]);
-      const V3 pu = v3(s_d[warp][3][o], s_d[warp][4][o], s_d[warp][5][o]);
-      const double ptotal = s_d[warp][6][o];
-#pragma unroll
-      for (int s = 0; s < SCORE_NVAL; ++s)
-        em.val[s] = s_d[warp][7 + s][o];
-      em.base = s_base[warp][o];
-      mesh_march(mesh, pr0, pu, ptotal, part_bound(c, onc, ptotal), part_bound(c + 1, onc, ptotal), em);
-    }
+    const int ns = ld(DM.tally_n_scores + t);
+    double* results = a.gc.tally_values + ld(DM.tally_result_ofs + t);
+    // warp-uniform: a property of the tally
+    if (ns == 1)
+      score_parts<1>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp]);
+    else if (ns <= 3)
+      score_parts<3>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp]);
+    else
+      score_parts<SCORE_NVAL>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp]);
   }
   __syncwarp(); // the staging area is reused by the next block of flights
   }
@@ -891,7 +931,7 @@ void k_score(int64_t n_ub, EvArgs a)
       continue;
     const Flight f = load_flight(a.fl, tid);
     for (int t = 0; t < DM.n_tallies; ++t) {
-      PartEmit em;
+      PartEmit<SCORE_NVAL> em;
       const int nc = score_prepare(a.ps, f, t, a.gc.tally_values, a.gc.score_part, em.base, em.val);
       int mesh;
       tally_mesh_info(t, mesh, em.mesh_stride);
@@ -1107,6 +1147,7 @@ struct XsArgs {
   int32_t* i_grid;
   int32_t max_nuc;
 };
+template<bool BX>
 OMC_D void body_probe_xs(int64_t tid, const XsArgs& a)
 {
   if (tid >= a.n)
@@ -1114,7 +1155,7 @@ OMC_D void body_probe_xs(int64_t tid, const XsArgs& a)
   const int m = a.material[tid];
   double t = 0, ab = 0, f = 0, nf = 0;
   if (DM.run_CE) {
-    ce_macro_xs(m, a.E[tid], t, ab, f, nf, a.i_grid ? a.i_grid + tid * a.max_nuc : nullptr,
+    ce_macro_xs<BX>(m, a.E[tid], t, ab, f, nf, a.i_grid ? a.i_grid + tid * a.max_nuc : nullptr,
       a.max_nuc);
   } else {
     const int G = DM.mg_n_groups;
@@ -1134,7 +1175,8 @@ OMC_D void body_probe_xs(int64_t tid, const XsArgs& a)
   a.out[4 * tid + 3] = nf;
 #endif
 }
-OMC_KERNEL_MB(k_probe_xs, XsArgs, body_probe_xs, 2)
+OMC_KERNEL_MB(k_probe_xs, XsArgs, body_probe_xs<false>, 2)
+OMC_KERNEL_MB(k_probe_xs_b, XsArgs, body_probe_xs<true>, 2)
 
 struct GeoArgs {
   PState ps;
@@ -1272,6 +1314,7 @@ struct Engine {
   bool ordered = true;          // sweep mode 2: lists rebuilt in particle-index order after every sweep
   void* d_part_tmp = nullptr;   // cub::DevicePartition scratch
   size_t part_tmp_bytes = 0;
+  bool batch_xs = false;        // some material has >= OMC_XS_BATCH_MIN nuclides: lockstep lookup kernels
   int sweep_mode = 2;           // 1: xs+advance | surface | collide over a merged alive list; 2: paired lists
   int score_ctas = 0;           // >0: k_score grid capped at this many blocks per SM (persistent, co-resident)
   int n_sm = 148;
@@ -1281,6 +1324,10 @@ struct Engine {
   int64_t id_offset_last = 0;
 };
 static Engine G;
+static bool batch_xs_enabled()
+{
+  return G.batch_xs;
+}
 
 template<class T>
 static int dev_alloc(T** p, size_t count)
@@ -1465,8 +1512,8 @@ static int upload_model(const omcgpu_model* m)
             ++c_lo;
           while (c_hi < ng && e[c_hi] < e_hi[j])
             ++c_hi;
-          fine[((size_t)k * nf + j) * 2 + 0] = (int32_t)c_lo;
-          fine[((size_t)k * nf + j) * 2 + 1] = (int32_t)c_hi;
+          fine[((size_t)j * nn + k) * 2 + 0] = (int32_t)c_lo; // bin-major: the nuclides of a material
+          fine[((size_t)j * nn + k) * 2 + 1] = (int32_t)c_hi; // share the sectors of one bin
         }
       }
       h.fine_window = fine.data();
@@ -1721,10 +1768,10 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_score[buf], 0));
     CUDA_OK(cudaEventRecord(G.evx0[ev], G.stream));
     if (G.fuse_xs) {
-      OMC_LAUNCH(k_xs_advance, n_alive, G.stream, a);
+      LAUNCH_XS(k_xs_advance, n_alive, G.stream, a);
       CUDA_OK(cudaEventRecord(G.evx1[ev], G.stream));
     } else {
-      OMC_LAUNCH(k_xs, n_alive, G.stream, a);
+      LAUNCH_XS(k_xs, n_alive, G.stream, a);
       CUDA_OK(cudaEventRecord(G.evx1[ev], G.stream));
       OMC_LAUNCH(k_advance, n_alive, G.stream, a);
     }
@@ -1887,7 +1934,7 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
   if (G.ordered) // histories that never fly (zero weight, lost at birth) carry no flag
     CUDA_OK(cudaMemsetAsync(G.ps.next_ev, 0, (size_t)n, G.stream));
   CUDA_OK(cudaEventRecord(G.evx0[0], G.stream));
-  OMC_LAUNCH(k_xs_advance, n_alive0, G.stream, a);
+  LAUNCH_XS(k_xs_advance, n_alive0, G.stream, a);
   if (G.ordered) {
     rc = build_lists(n, G.q[0].idx, G.q[2].idx, slot_of(0), G.stream);
     if (rc)
@@ -1940,7 +1987,7 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     a.fl_buf = 0 * 2 + po;
     if (G.overlap)
       CUDA_OK(cudaStreamWaitEvent(st_surf, G.e_adv, 0));
-    OMC_LAUNCH(k_surface_xa, n_alive, st_surf, a);
+    LAUNCH_XS(k_surface_xa, n_alive, st_surf, a);
     if (G.overlap)
       CUDA_OK(cudaEventRecord(G.e_surf, st_surf));
     // collisions
@@ -1950,7 +1997,7 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     a.fl_buf = 1 * 2 + po;
     if (G.overlap)
       CUDA_OK(cudaStreamWaitEvent(st_coll, G.e_adv, 0));
-    OMC_LAUNCH(k_collide_xa, n_alive, st_coll, a);
+    LAUNCH_XS(k_collide_xa, n_alive, st_coll, a);
     if (G.overlap) {
       CUDA_OK(cudaEventRecord(G.e_coll, st_coll));
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_surf, 0));
@@ -2192,6 +2239,13 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
     G.overlap = std::atoi(t) != 0;
   if (const char* t = std::getenv("OMCGPU_SWEEP"))
     G.sweep_mode = std::atoi(t) == 1 ? 1 : 2;
+  G.batch_xs = false;
+  if (model->run_CE)
+    for (int m = 0; m < model->n_materials; ++m)
+      if (model->mat_nuc_ofs[m + 1] - model->mat_nuc_ofs[m] >= OMC_XS_BATCH_MIN)
+        G.batch_xs = true;
+  if (const char* t = std::getenv("OMCGPU_BATCH_XS"))
+    G.batch_xs = std::atoi(t) != 0;
   if (const char* t = std::getenv("OMCGPU_ORDERED"))
     G.ordered = std::atoi(t) != 0;
   if (const char* t = std::getenv("OMCGPU_SCORE_CTAS"))
@@ -2607,7 +2661,7 @@ int omcgpu_calculate_xs(const double* E, const int32_t* material, int64_t n, dou
   CUDA_OK(cudaMemcpy(dm, material, n * sizeof(int32_t), cudaMemcpyHostToDevice));
   XsArgs a;
   a.E = dE; a.material = dm; a.n = n; a.out = dout; a.i_grid = dig; a.max_nuc = max_nuc;
-  OMC_LAUNCH(k_probe_xs, n, G.stream, a);
+  LAUNCH_XS(k_probe_xs, n, G.stream, a);
   CUDA_OK(cudaStreamSynchronize(G.stream));
   CUDA_OK(cudaMemcpy(out, dout, n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
   if (i_grid)
@@ -2629,7 +2683,7 @@ int omcgpu_calculate_xs_device(const double* E, const int32_t* material, int64_t
   XsArgs a;
   a.E = E; a.material = material; a.n = n; a.out = out; a.i_grid = nullptr; a.max_nuc = 0;
   CUDA_OK(cudaEventRecord(G.evp0, G.stream));
-  OMC_LAUNCH(k_probe_xs, n, G.stream, a);
+  LAUNCH_XS(k_probe_xs, n, G.stream, a);
   CUDA_OK(cudaEventRecord(G.evp1, G.stream));
   CUDA_OK(cudaStreamSynchronize(G.stream));
   if (ms)

@@ -175,6 +175,42 @@ def test_lattice_geometry_bit_exact(gpu_engine, name):
     gpu_engine.finalize()
 
 
+def test_many_nuclide_lookup(gpu_engine):
+    """config C5 fuel (40 nuclides here) through the lockstep lookup kernels: grid indices
+    bit-exact, macroscopic cross sections to 1e-12 (north_star)"""
+    model, box, of = cases.build_lattice("pwr_core")
+    n_nuc = np.diff(np.asarray(model["mat_nuc_ofs"]))
+    mat = int(np.argmax(n_nuc))
+    o = Oracle(model)
+    gpu_engine.init(model, 0, 1024)
+    E = cases.xs_probe_energies(model, None, 100000)
+    mats = np.full(E.size, mat, np.int32)
+    xs_g, ig_g = gpu_engine.calculate_xs(E, mats, int(n_nuc[mat]))
+    xs_o, ig_o = o.calculate_xs(E, mats, int(n_nuc[mat]))
+    assert np.array_equal(ig_g, ig_o)
+    np.testing.assert_allclose(xs_g, xs_o, rtol=1e-12, atol=0)
+    gpu_engine.finalize()
+
+
+@pytest.mark.parametrize("threshold", ["0", "4096"])
+def test_pwr_core_generation_matches_oracle(gpu_engine, threshold, monkeypatch):
+    """config C5 (full core, 3 levels, 40-nuclide fuel): one generation against the oracle"""
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)
+    model, box, of = cases.build_lattice("pwr_core")
+    o = Oracle(model)
+    n = 20000
+    src = o.sample_initial_source(n, box, of)
+    gpu_engine.init(model, 0, n)
+    gi = gpu_engine.gen_in(n, 0, 0, 1.0, True)
+    fb, out = gpu_engine.transport_generation(gi, src)
+    fb_o, out_o = o.transport_generation(gi, src)
+    assert out.n_lost == 0
+    assert abs(out.n_fission - out_o.n_fission) <= 20
+    assert abs(out.n_events - out_o.n_events) <= 2e-4 * out_o.n_events
+    np.testing.assert_allclose(out.global_tally[:], out_o.global_tally[:], rtol=2e-4)
+    gpu_engine.finalize()
+
+
 @pytest.mark.parametrize("threshold", ["0", "16384"])
 def test_c5g7_generation_matches_oracle(gpu_engine, threshold, monkeypatch):
     """lattice-of-lattices MG core: same sorted fission bank as the oracle"""

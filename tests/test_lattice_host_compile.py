@@ -48,3 +48,21 @@ def test_lattice_generation_matches_oracle(emu_lib, name, threshold, monkeypatch
     v = np.zeros(m); eng.tally_results(0, v)
     np.testing.assert_allclose(v, o.tally_results(0, m), rtol=1e-11, atol=1e-300)
     eng.finalize()
+
+
+def test_many_nuclide_lookup_bit_exact(emu_lib):
+    """config C5 fuel (40 nuclides here): the lockstep lookup kernels (batches of 4 nuclides)
+    give the grid indices and the sums of the one-at-a-time walk, bit for bit"""
+    model, box, of = cases.build_lattice("pwr_core")
+    n_nuc = np.diff(np.asarray(model["mat_nuc_ofs"]))
+    mat = int(np.argmax(n_nuc))
+    assert n_nuc[mat] >= 16
+    o = Oracle(model)
+    eng = lib.Engine(emu_lib)
+    eng.init(model, 0, 1024)
+    E = cases.xs_probe_energies(model, None, 4000)
+    mats = np.full(E.size, mat, np.int32)
+    xs_e, ig_e = eng.calculate_xs(E, mats, int(n_nuc[mat]))
+    xs_o, ig_o = o.calculate_xs(E, mats, int(n_nuc[mat]))
+    assert np.array_equal(ig_e, ig_o) and np.array_equal(xs_e, xs_o)
+    eng.finalize()
