@@ -271,7 +271,7 @@ def main():
     if bool(model["run_CE"]) and st["ms_xs"] > 0:
         # algorithmic bytes per item: 60 + 88 * n_nuclides(material); the
         # per-material item counts come from the lookup micro-benchmark below
-        roof = xs_roofline(eng, model, n_local, peak, peaks, box)
+        roof = xs_roofline(eng, model, n_local, peak, peaks, box, args.workload)
         roof["in_loop"] = {"what": "device time of the event kernels that contain the lookup (k_xs_advance; "
                                    "k_surface_xa + k_collide_xa in sweep mode 2), all generations timed",
                            "ms_total": st["ms_xs"],
@@ -309,7 +309,7 @@ def main():
         dist.destroy_process_group()
 
 
-def xs_roofline(eng, model, n, peak, peaks, box):
+def xs_roofline(eng, model, n, peak, peaks, box, args_workload="pincell_ce"):
     """macro-xs lookup kernel alone on a device-resident work list (E log-uniform over
     the library's range, materials by their volume fractions inside the source box --
     found with the device find_cell probe on uniform points): achieved algorithmic GB/s."""
@@ -338,10 +338,20 @@ def xs_roofline(eng, model, n, peak, peaks, box):
             best.append(ms.value)
     t = float(np.mean(best)) * 1e-3
     achieved = alg_bytes / t / 1e9
+    # DRAM bytes of one such launch from the committed `ncu --set full` capture of this very
+    # command (profiles/traffic.json, written from profiles/*_probe_xs_ncu.txt); None if absent
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tj.get(args_workload)
+        if ent and int(ent.get("lookups", 0)) == int(n):
+            traffic = float(ent["dram_bytes_per_launch"])
+    except Exception:
+        pass
     return {"bound": "hbm", "kernel": "k_probe_xs (macro-xs lookup, same device function as k_xs)",
             "achieved": achieved, "peak": peak,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-            "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": t * 1e3,
             "lookups_per_s": n / t, "nuclide_lookups_per_s": float(np.sum(n_nuc[mat])) / t}
 

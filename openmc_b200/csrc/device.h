@@ -1513,7 +1513,9 @@ OMC_D void atomic_add_f64(double* addr, double val)
 {
 #if OMC_CUDA && defined(__CUDA_ARCH__)
   // tally arrays are global memory: skip the generic-address dispatch of atomicAdd
-  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(val) : "memory");
+  // (no "memory" clobber: tally arrays are never read by the kernels that add to them, and
+  // the clobber would make the compiler reload every hoisted model constant after each add)
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(val));
 #else
   *addr += val;
 #endif
@@ -1817,25 +1819,22 @@ OMC_D void mesh_march(int m, V3 r0, V3 u, double total, double t0, double t1, Em
     traveled = dk;
     if (traveled >= t1)
       break;
-    if (k == 0) {
-      if (j0 == left[0])
-        break;
-      ++j0;
-      bin += stride[0];
-      t_0 = tmax0[0] + j0 * tdel[0];
-    } else if (k == 1) {
-      if (j1 == left[1])
-        break;
-      ++j1;
-      bin += stride[1];
-      t_1 = tmax0[1] + j1 * tdel[1];
-    } else {
-      if (j2 == left[2])
-        break;
-      ++j2;
-      bin += stride[2];
-      t_2 = tmax0[2] + j2 * tdel[2];
-    }
+    // step across the nearest edge without branching on the axis (the lanes of a warp
+    // cross different axes: an if / else chain would run the three bodies one after
+    // another)
+    const bool k0 = k == 0, k1 = k == 1;
+    int jk = k0 ? j0 : (k1 ? j1 : j2);
+    if (jk == (k0 ? left[0] : (k1 ? left[1] : left[2])))
+      break;
+    ++jk;
+    bin += k0 ? stride[0] : (k1 ? stride[1] : stride[2]);
+    const double tn = (k0 ? tmax0[0] : (k1 ? tmax0[1] : tmax0[2])) + jk * (k0 ? tdel[0] : (k1 ? tdel[1] : tdel[2]));
+    j0 = k0 ? jk : j0;
+    j1 = k1 ? jk : j1;
+    j2 = (k0 || k1) ? j2 : jk;
+    t_0 = k0 ? tn : t_0;
+    t_1 = k1 ? tn : t_1;
+    t_2 = (k0 || k1) ? t_2 : tn;
   }
 }
 
