@@ -173,7 +173,7 @@ def main():
     eng = lib.Engine()
     n_local = args.particles
     n_global = n_local * world
-    eng.init(model, local_rank, n_local + 16)
+    eng.init(model, local_rank, n_local)
     work_lo = rank * n_local
     src = source.sample_initial_source(eng, n_local, box, of, id_offset=work_lo)
 

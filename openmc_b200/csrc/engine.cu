@@ -2305,7 +2305,11 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
 #undef D
 #undef I
   }
-  rc = rc ? rc : alloc_bank(G.src, cap);
+  // A rank's comb may select more sites than its share of the next generation (they
+  // travel to their owners afterwards, src/eigenvalue.cpp:186-348): the source bank
+  // and the gather list hold up to 25 % + 1024 more than max_particles.
+  const int64_t src_cap = cap + cap / 4 + 1024;
+  rc = rc ? rc : alloc_bank(G.src, src_cap);
   rc = rc ? rc : alloc_bank(G.fis, G.fis_cap);
   rc = rc ? rc : alloc_bank(G.fis_sorted, G.fis_cap);
   rc = rc ? rc : dev_alloc(&G.d_counts, N_COUNTS);
@@ -2317,7 +2321,7 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   rc = rc ? rc : dev_alloc(&G.q_alive.idx, cap);
   G.q_alive.count = G.d_counts + 0;
   rc = rc ? rc : dev_alloc(&G.d_offs, cap + 1);
-  rc = rc ? rc : dev_alloc(&G.d_gather, cap);
+  rc = rc ? rc : dev_alloc(&G.d_gather, src_cap);
   rc = rc ? rc : dev_alloc(&G.d_aos, G.fis_cap);
   rc = rc ? rc : dev_alloc(&G.d_tally, G.n_tally);
   G.n_chunks = 4096;
@@ -2569,8 +2573,8 @@ int omcgpu_comb_fission_bank(int64_t start, int64_t total, int64_t n_particles, 
   const int64_t tooth_start = (int64_t)std::ceil((start - teeth_offset) / teeth_distance);
   const int64_t tooth_end = (int64_t)std::floor((end - teeth_offset) / teeth_distance) + 1;
   const int64_t count = tooth_end - tooth_start;
-  if (count > G.cap)
-    return fail(OMCGPU_E_OUT_OF_BOUNDS, "comb selects more sites than max_particles%s");
+  if (count > G.src.cap)
+    return fail(OMCGPU_E_OUT_OF_BOUNDS, "comb selects more sites than the source bank holds (1.25 max_particles + 1024)%s");
   int32_t* idx = reinterpret_cast<int32_t*>(G.h_aos);
   double tooth = tooth_start * teeth_distance + teeth_offset;
   for (int64_t i = 0; i < count; i++) {

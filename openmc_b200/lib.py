@@ -304,7 +304,7 @@ class Simulation:
 
     # -- openmc_simulation_init, src/simulation.cpp:75-167 -----------------------
     def simulation_init(self):
-        self.engine.init(self.model, self.device, max(self.work + 16, 1024))
+        self.engine.init(self.model, self.device, max(self.work, 1))   # work_per_rank, as allocate_banks
         self.source_bank = self._initial_source.copy()
         self.engine.set_source_bank(self.source_bank)
         self.current_batch = 0
