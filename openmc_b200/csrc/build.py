@@ -33,7 +33,8 @@ def build_variant(name, defines):
     out = os.path.join(HERE, "variants", name + ".so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out] + \
+    extra = [d if d.startswith("-") else "-D" + d for d in defines]   # raw nvcc flags pass through
+    cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + extra + ["-o", out] + \
           [os.path.join(HERE, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

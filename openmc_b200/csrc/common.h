@@ -178,6 +178,8 @@ struct GenCtx {
   int32_t* n_lost;
   unsigned long long* counters; // [0] events [1] xs lookups [2] collisions [3] crossings
   double* tally_values;
+  int64_t tally_replica_stride; // doubles between two replicas of the VALUE arrays (k_score spreads its REDs)
+  int32_t tally_replicas;
   int64_t fission_cap;
 };
 

@@ -871,6 +871,10 @@ __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, 
   __shared__ int s_incl[WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n = *a.n_flights < a.fl.cap ? *a.n_flights : a.fl.cap;
+  // Small tallies are replicated: REDs to one address serialise in the L2 slice that owns
+  // it (measured, profiles/r13_red_peak.txt: 143 G RED/s into 30 000 doubles, 210 G/s into
+  // >= 300 000), so every block adds into its own replica; omcgpu_tally_results folds them.
+  double* values = a.gc.tally_values + (int64_t)(blockIdx.x % a.gc.tally_replicas) * a.gc.tally_replica_stride;
   // grid-stride over blocks of flights: with a capped grid (G.score_ctas) the kernel
   // occupies only part of every SM for the whole sweep, so that its RED traffic
   // shares the SM with the latency-bound event kernels of the next sweep
@@ -881,7 +885,7 @@ __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, 
     __syncwarp(); // lanes leave the part loop of the previous tally at different times
     int nc = 0;
     if (active) // loads the flight, evaluates the filters, publishes r0/u/total/val/base
-      nc = score_lane(tid, a.fl_buf, t, a.gc.tally_values, a.gc.score_part, &s_d[warp][0][lane], &s_base[warp][lane]);
+      nc = score_lane(tid, a.fl_buf, t, values, a.gc.score_part, &s_d[warp][0][lane], &s_base[warp][lane]);
     int mesh, mesh_stride;
     tally_mesh_info(t, mesh, mesh_stride);
     if (mesh < 0)
@@ -898,7 +902,7 @@ __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, 
     s_incl[warp][lane] = incl;
     __syncwarp();
     const int ns = ld(DM.tally_n_scores + t);
-    double* results = a.gc.tally_values + ld(DM.tally_result_ofs + t);
+    double* results = values + ld(DM.tally_result_ofs + t);
     // warp-uniform: a property of the tally
     if (ns == 1)
       score_parts<1>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp]);
@@ -1051,6 +1055,25 @@ OMC_D void body_reduce(int64_t tid, const ReduceArgs& a)
     a.partial[tid * 6 + k] = s[k];
 }
 OMC_KERNEL(k_reduce, ReduceArgs, body_reduce)
+
+// ---- fold the replicas of the tally VALUE arrays into replica 0 --------------------
+struct FoldArgs {
+  double* v;
+  int64_t n, stride;
+  int32_t replicas;
+};
+OMC_D void body_fold_tally(int64_t tid, const FoldArgs& a)
+{
+  if (tid >= a.n)
+    return;
+  double s = a.v[tid];
+  for (int r = 1; r < a.replicas; ++r) {
+    s += a.v[r * a.stride + tid];
+    a.v[r * a.stride + tid] = 0.0;
+  }
+  a.v[tid] = s;
+}
+OMC_KERNEL(k_fold_tally, FoldArgs, body_fold_tally)
 
 // ---- bank kernels --------------------------------------------------------------
 struct BankArgs {
@@ -1307,6 +1330,8 @@ struct Engine {
   omcgpu_site* h_aos = nullptr;  // pinned staging
   double* d_tally = nullptr;
   int64_t n_tally = 0;
+  int tally_replicas = 1;       // copies of the VALUE arrays k_score spreads its REDs over
+  int64_t tally_stride = 0;
   cudaStream_t stream = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evx0[RING] = {}, evx1[RING] = {}, evp0 = nullptr, evp1 = nullptr;
@@ -1675,6 +1700,8 @@ static EvArgs make_args(const omcgpu_gen_in* in)
   a.gc.n_lost = G.d_counts + 5;
   a.gc.counters = G.d_counters;
   a.gc.tally_values = G.d_tally;
+  a.gc.tally_replicas = G.tally_replicas;
+  a.gc.tally_replica_stride = G.tally_stride;
   a.gc.fission_cap = G.fis_cap;
   a.gc.score_part = G.score_part;
   a.gc.tally_needs_cells = G.tally_needs_cells ? 1 : 0;
@@ -2323,7 +2350,17 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   rc = rc ? rc : dev_alloc(&G.d_offs, cap + 1);
   rc = rc ? rc : dev_alloc(&G.d_gather, src_cap);
   rc = rc ? rc : dev_alloc(&G.d_aos, G.fis_cap);
-  rc = rc ? rc : dev_alloc(&G.d_tally, G.n_tally);
+  {
+    // replicate while all copies together stay L2-resident (<= 4 M doubles)
+    int r = 8;
+    if (const char* t = std::getenv("OMCGPU_TALLY_REPLICAS"))
+      r = std::max(1, std::atoi(t));
+    while (r > 1 && (int64_t)r * G.n_tally > (4 << 20))
+      r >>= 1;
+    G.tally_replicas = G.n_tally > 0 ? r : 1;
+    G.tally_stride = (G.n_tally + 15) / 16 * 16;
+  }
+  rc = rc ? rc : dev_alloc(&G.d_tally, (size_t)G.tally_stride * G.tally_replicas);
   G.n_chunks = 4096;
   rc = rc ? rc : dev_alloc(&G.d_partial, G.n_chunks * 6);
   if (rc)
@@ -2630,6 +2667,15 @@ int omcgpu_tally_results(int32_t tally, double* value, int64_t n)
   const int64_t len = ofs[tally + 1] - ofs[tally];
   if (n != len)
     return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_tally_results: size mismatch%s");
+  if (G.tally_replicas > 1) {
+    FoldArgs f;
+    f.v = G.d_tally + ofs[tally];
+    f.n = len;
+    f.stride = G.tally_stride;
+    f.replicas = G.tally_replicas;
+    OMC_LAUNCH(k_fold_tally, len, G.stream, f);
+    CUDA_OK(cudaStreamSynchronize(G.stream));
+  }
   std::vector<double> tmp(len);
   CUDA_OK(cudaMemcpy(tmp.data(), G.d_tally + ofs[tally], len * sizeof(double), cudaMemcpyDeviceToHost));
   CUDA_OK(cudaMemset(G.d_tally + ofs[tally], 0, len * sizeof(double)));
@@ -2642,6 +2688,15 @@ int omcgpu_tally_values_device(double** values, int64_t* n)
 {
   if (!G.ready)
     return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  if (G.tally_replicas > 1 && G.n_tally > 0) { // hand out one array: fold the replicas first
+    FoldArgs f;
+    f.v = G.d_tally;
+    f.n = G.n_tally;
+    f.stride = G.tally_stride;
+    f.replicas = G.tally_replicas;
+    OMC_LAUNCH(k_fold_tally, G.n_tally, G.stream, f);
+    CUDA_OK(cudaStreamSynchronize(G.stream));
+  }
   *values = G.d_tally;
   *n = G.n_tally;
   return 0;
