@@ -37,7 +37,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--particles", type=int, default=1_000_000, help="histories per generation per GPU")
+    ap.add_argument("--particles", type=int, default=4_000_000,
+                    help="histories per generation per GPU (throughput = 17.5 ms fixed + 99 ms per 1e6 on C2: "
+                         "profiles/r16_matrix.log; the survey's range is 1e6-1e7)")
     ap.add_argument("--n-grid", type=int, default=100_000, help="energy-grid points per nuclide")
     ap.add_argument("--workload", default="pincell_ce",
                     choices=["pincell_ce", "pincell_mg", "assembly_ce", "c5g7_core", "pwr_core_ce"],
@@ -271,7 +273,7 @@ def main():
     if bool(model["run_CE"]) and st["ms_xs"] > 0:
         # algorithmic bytes per item: 60 + 88 * n_nuclides(material); the
         # per-material item counts come from the lookup micro-benchmark below
-        roof = xs_roofline(eng, model, n_local, peak, peaks, box, args.workload)
+        roof = xs_roofline(eng, model, min(n_local, 1_000_000), peak, peaks, box, args.workload)
         roof["in_loop"] = {"what": "device time of the event kernels that contain the lookup (k_xs_advance; "
                                    "k_surface_xa + k_collide_xa in sweep mode 2), all generations timed",
                            "ms_total": st["ms_xs"],

@@ -18,11 +18,13 @@
 #define OMC_HD __device__ __forceinline__          /* device functions reading the constant-memory model */
 #define OMC_BOTH __host__ __device__ __forceinline__ /* pure functions also used by host code (RNG) */
 #define OMC_D __device__ __forceinline__
+#define OMC_OOL __device__ __noinline__            /* out of line: called from many places, rarely hot (code size / icache) */
 #else
 #define OMC_CUDA 0
 #define OMC_HD inline
 #define OMC_BOTH inline
 #define OMC_D inline
+#define OMC_OOL inline
 #include <cmath>
 #include <cstring>
 #endif

@@ -13,6 +13,7 @@ namespace omc {
 
 #if OMC_CUDA
 __constant__ omcgpu_model c_dm;
+__constant__ PState c_ps; // the particle columns never move after omcgpu_init (out-of-line device functions read it)
 #else
 static omcgpu_model c_dm;
 #endif
@@ -79,7 +80,7 @@ OMC_HD int64_t lower_bound_index(const T* a, int64_t n, T value)
 }
 
 // src/math_functions.cpp:763-792
-OMC_HD V3 rotate_angle(V3 u, double mu, uint64_t& seed)
+OMC_OOL V3 rotate_angle(V3 u, double mu, uint64_t& seed)
 {
   double phi = 2.0 * PI * prn(seed);
   double sinphi = sin(phi);
@@ -594,11 +595,27 @@ OMC_HD void reset_deeper(const PState& ps, int64_t i, int n_coord)
     reset_level(ps, i, l);
 }
 
-// exhaustive_find_cell / neighbor_list_find_cell with n_coord already set
+// exhaustive_find_cell / neighbor_list_find_cell with n_coord already set.
+// Out of line on the device: the crossing event calls it from six places, and inlined
+// copies made k_surface_xa 247 KB of SASS -- with the GPU nearly empty (the last ~100
+// sweeps of a generation) a quarter of its stall cycles were instruction fetches
+// (profiles/README.md, r17).
+#if OMC_CUDA
+__device__ __noinline__ bool find_cell_from_ool(int64_t i, int n_coord, int surface)
+{
+  reset_deeper(c_ps, i, n_coord);
+  return find_cell_inner(c_ps, i, n_coord - 1, surface);
+}
+#endif
 OMC_HD bool find_cell_from(const PState& ps, int64_t i, int n_coord, int surface)
 {
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  (void)ps;
+  return find_cell_from_ool(i, n_coord, surface);
+#else
   reset_deeper(ps, i, n_coord);
   return find_cell_inner(ps, i, n_coord - 1, surface);
+#endif
 }
 
 OMC_HD bool find_cell_from_root(const PState& ps, int64_t i, int surface)
@@ -885,7 +902,7 @@ OMC_HD int ce_fine_index(double E)
 }
 
 // Nuclide::calculate_xs, src/nuclide.cpp:725-742, with the reference's hash window
-OMC_HD int ce_grid_index_reference(int nuc, const double* energy, int n_grid, double E)
+OMC_OOL int ce_grid_index_reference(int nuc, const double* energy, int n_grid, double E)
 {
   int i_grid;
   if (E < ld(energy)) {
@@ -1120,7 +1137,7 @@ OMC_HD void ce_macro_xs(int m, double E, double& t, double& a, double& f, double
 }
 
 // src/endf.cpp:125-134 (Polynomial), 168-226 (Tabulated1D, lin-lin)
-OMC_HD double eval_function(int fn, double x)
+OMC_OOL double eval_function(int fn, double x)
 {
   const int o0 = ld(DM.fn_ofs + fn), o1 = ld(DM.fn_ofs + fn + 1);
   const double* d = DM.fn_data + o0;
@@ -1144,7 +1161,7 @@ OMC_HD double eval_function(int fn, double x)
 }
 
 // Nuclide::nu, src/nuclide.cpp:535-576 ; mode 0 prompt, 1 delayed, 2 total
-OMC_HD double ce_nu(int nuc, double E, int mode)
+OMC_OOL double ce_nu(int nuc, double E, int mode)
 {
   if (!ld(DM.nuc_fissionable + nuc))
     return 0.0;
@@ -1171,7 +1188,7 @@ OMC_HD double ce_nu(int nuc, double E, int mode)
 // ReactionProduct::sample -> UncorrelatedAngleEnergy::sample (isotropic angle),
 // src/reaction_product.cpp:109-130, src/secondary_uncorrelated.cpp:53-66,
 // src/distribution_energy.cpp:49-52, 284-298, 309-327, 347-361
-OMC_HD void ce_sample_product(int prod, double E_in, double& E_out, double& mu, uint64_t& seed)
+OMC_OOL void ce_sample_product(int prod, double E_in, double& E_out, double& mu, uint64_t& seed)
 {
   mu = -1. + (1. - (-1.)) * prn(seed);
   const double par0 = ld(DM.prod_par + 2 * prod), par1 = ld(DM.prod_par + 2 * prod + 1);
@@ -1981,7 +1998,7 @@ OMC_HD double track_length(V3 r0, V3 r1)
 
 // score_tracklength_tally by ONE lane for ONE track (the tail kernel and the
 // rare tallies with several matches per filter); src/tallies/tally_scoring.cpp:2416-2541
-OMC_D void score_tracklength(const PState& ps, int64_t i, int n_coord, V3 r0, V3 r1, V3 u,
+OMC_OOL void score_tracklength(const PState& ps, int64_t i, int n_coord, V3 r0, V3 r1, V3 u,
   double E_last, const ScoreCtx& sc, double* values)
 {
   for (int t = 0; t < DM.n_tallies; ++t) {

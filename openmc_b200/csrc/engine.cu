@@ -809,7 +809,6 @@ OMC_HD void tally_mesh_info(int t, int& mesh, int& mesh_stride)
 // Everything one lane does for its own flight and tally t, out of line: nothing
 // of the flight stays in registers while the lanes trace parts afterwards.
 // sd points at this lane's column of the warp's staging area (stride 32 doubles).
-__constant__ PState c_ps; // the particle columns never move after omcgpu_init
 
 __constant__ Flights c_fl[4]; // [list kind][parity]: k_score(sweep s) overlaps the event kernels of sweep s+1
 
@@ -1354,9 +1353,25 @@ static bool batch_xs_enabled()
   return G.batch_xs;
 }
 
+// The continuous-energy tables (energy grids, xs rows, hash tables) are carved from one
+// allocation so that ONE access-policy window can ask L2 to keep them resident while
+// particle state and flight records stream through (OMCGPU_L2_PERSIST=1).
+static char* g_arena = nullptr;
+static size_t g_arena_size = 0, g_arena_used = 0;
+static bool g_arena_on = false;
+
 template<class T>
 static int dev_alloc(T** p, size_t count)
 {
+  if (g_arena_on) {
+    const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) / 256 * 256;
+    if (g_arena_used + bytes <= g_arena_size) {
+      *p = reinterpret_cast<T*>(g_arena + g_arena_used);
+      cudaMemset(*p, 0, bytes);
+      g_arena_used += bytes;
+      return 0;
+    }
+  }
   void* q = nullptr;
   cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
   if (e != cudaSuccess)
@@ -1507,6 +1522,20 @@ static int upload_model(const omcgpu_model* m)
     UP(nuc_kT, nn);
     UP(nuc_fissionable, nn);
     UP(nuc_grid_ofs, nn + 1);
+    {
+      int per = OMCGPU_FINE_PER_LOG_BIN;
+      if (const char* t = std::getenv("OMCGPU_FINE_PER_LOG_BIN"))
+        per = std::max(1, std::atoi(t));
+      g_arena_size = (size_t)n_pts * 8 + (size_t)n_pts * 32 + (size_t)nn * (h.n_log_bins + 1) * 4 +
+                     (size_t)nn * h.n_log_bins * per * 8 + 4096;
+      g_arena_used = 0;
+      void* q = nullptr;
+      if (cudaMalloc(&q, g_arena_size) != cudaSuccess)
+        return fail(OMCGPU_E_ALLOCATE, "cudaMalloc of the cross-section arena failed%s");
+      G.dev_allocs.push_back(q);
+      g_arena = static_cast<char*>(q);
+      g_arena_on = true;
+    }
     UP(nuc_energy, n_pts);
     UP(nuc_xs, (size_t)n_pts * 4);
     UP(nuc_grid_index, (size_t)nn * (h.n_log_bins + 1));
@@ -1544,6 +1573,7 @@ static int upload_model(const omcgpu_model* m)
       h.fine_window = fine.data();
     }
     UP(fine_window, fine.size());
+    g_arena_on = false;
     UP(nuc_rx_ofs, nn + 1);
     UP(nuc_fission_rx, nn);
     UP(nuc_n_precursor, nn);
@@ -2286,10 +2316,38 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   }
 #endif
   // particle state is gathered in 32-byte sectors (PState): do not let L2 fetch 64
-  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+  {
+    int gran = 32;
+    if (const char* t = std::getenv("OMCGPU_L2_FETCH"))
+      gran = std::atoi(t);
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+  }
+  g_arena = nullptr;
+  g_arena_size = g_arena_used = 0;
   rc = upload_model(model);
   if (rc)
     return rc;
+#if OMC_CUDA
+  if (const char* t = std::getenv("OMCGPU_L2_PERSIST")) {
+    if (std::atoi(t) != 0 && g_arena && g_arena_used > 0) {
+      cudaDeviceProp prop;
+      cudaGetDeviceProperties(&prop, device);
+      const size_t want = std::min<size_t>(g_arena_used, (size_t)prop.persistingL2CacheMaxSize);
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      cudaStreamAttrValue attr;
+      std::memset(&attr, 0, sizeof(attr));
+      attr.accessPolicyWindow.base_ptr = g_arena;
+      attr.accessPolicyWindow.num_bytes = std::min<size_t>(g_arena_used, (size_t)prop.accessPolicyMaxWindowSize);
+      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      for (cudaStream_t st : {G.stream, G.s_surf, G.s_coll})
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+      std::fprintf(stderr, "omcgpu: L2 persisting window %zu MB of %zu MB tables (max %d MB)\n", want >> 20,
+        g_arena_used >> 20, prop.persistingL2CacheMaxSize >> 20);
+    }
+  }
+#endif
   if (const char* t = std::getenv("OMCGPU_TAIL_THRESHOLD"))
     G.tail_threshold = std::atoll(t);
   if (const char* t = std::getenv("OMCGPU_SCORE_PART"))
