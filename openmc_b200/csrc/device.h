@@ -1114,12 +1114,12 @@ OMC_HD void ce_macro_xs_batch(int k0, int k1, int j_fine, double E, double& t, d
 // budget covers the lockstep walk); the host picks the kernel flavour per model.
 template<bool BX>
 OMC_HD void ce_macro_xs(int m, double E, double& t, double& a, double& f, double& nf,
-  int32_t* i_grid_out, int max_nuc)
+  int32_t* i_grid_out, int max_nuc, int batch_min = OMC_XS_BATCH_MIN)
 {
   t = a = f = nf = 0.0;
   const int j_fine = ce_fine_index(E);
   const int k0 = ld(DM.mat_nuc_ofs + m), k1 = ld(DM.mat_nuc_ofs + m + 1);
-  if (BX && k1 - k0 >= OMC_XS_BATCH_MIN) {
+  if (BX && k1 - k0 >= batch_min) {
     ce_macro_xs_batch<OMC_XS_BATCH>(k0, k1, j_fine, E, t, a, f, nf, i_grid_out, max_nuc);
     return;
   }

@@ -88,14 +88,22 @@ static int64_t g_launches = 0;
 // kernels that contain the cross-section lookup exist in two flavours: `name` (one
 // nuclide at a time) and `name_b` (lockstep walk for many-nuclide materials, larger
 // register budget); G.batch_xs is decided per model in omcgpu_init
+// With few histories alive (the last ~100 sweeps of a generation, the tail) a sweep costs
+// the latency of ONE event chain, occupancy is irrelevant, and the lockstep walk -- which
+// shortens the lookup's 4 dependent gathers per nuclide to 4 per batch -- is used for every
+// material (xs_batch_min = 1).
 #define LAUNCH_XS(name, n_ub, stream, args) \
   do { \
-    if (batch_xs_enabled()) \
+    const bool low_ = (int64_t)(n_ub) < low_count_threshold(); \
+    (args).xs_batch_min = low_ ? 1 : OMC_XS_BATCH_MIN; \
+    if (batch_xs_enabled() || low_) \
       OMC_LAUNCH(name##_b, n_ub, stream, args); \
     else \
       OMC_LAUNCH(name, n_ub, stream, args); \
   } while (0)
 static bool batch_xs_enabled();
+static int64_t low_count_threshold();
+static int tail_batch_min();
 
 // warp-aggregated append (ballot + one atomic per warp), cf. north_star
 OMC_D void queue_append(const Queue& q, int32_t value)
@@ -169,6 +177,7 @@ struct EvArgs {
   int32_t fl_buf;       // which of the two record buffers `fl` is (c_fl[fl_buf])
   const int32_t* n_flights; // device count of records (its ring slot outlives the sweep)
   int32_t first_event;      // k_tail: event the histories of q_in are waiting for (NEXT_NONE: a flight)
+  int32_t xs_batch_min;     // lockstep kernels: nuclides in a material from which the lockstep walk is used
   int32_t ordered;          // survivors are flagged in ps.next_ev (lists built in index order) instead of appended
 };
 
@@ -236,7 +245,7 @@ OMC_D bool ev_init(const PState& ps, const GenCtx& gc, const Bank& src, int64_t 
 
 // Particle::event_calculate_xs, src/particle.cpp:160-230 (locate done at birth)
 template<bool BX = false>
-OMC_D void ev_xs(const PState& ps, int64_t i)
+OMC_D void ev_xs(const PState& ps, int64_t i, int batch_min = OMC_XS_BATCH_MIN)
 {
   const int m = ps.material[i];
   if (m == MATERIAL_VOID) {
@@ -249,7 +258,7 @@ OMC_D void ev_xs(const PState& ps, int64_t i)
   if (DM.run_CE) {
     if (m != ps.material_last[i] || ps.sqrtkT[i] != ps.sqrtkT_last[i]) {
       double t, a, f, nf;
-      ce_macro_xs<BX>(m, ps.E[i], t, a, f, nf, nullptr, 0);
+      ce_macro_xs<BX>(m, ps.E[i], t, a, f, nf, nullptr, 0, batch_min);
       ps.xs_total[i] = t;
       ps.xs_absorption[i] = a;
       ps.xs_fission[i] = f;
@@ -552,7 +561,7 @@ OMC_D void body_xs(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
     return;
-  ev_xs<BX>(a.ps, a.q_in.idx[tid]);
+  ev_xs<BX>(a.ps, a.q_in.idx[tid], a.xs_batch_min);
 }
 OMC_KERNEL_MB(k_xs, EvArgs, body_xs<false>, 2)
 OMC_KERNEL_MB(k_xs_b, EvArgs, body_xs<true>, 2)
@@ -603,7 +612,7 @@ OMC_D void body_xs_advance(int64_t tid, const EvArgs& a)
     return;
   const int32_t i = a.q_in.idx[tid];
   prefetch_particle(a.ps, i, false);
-  ev_xs<BX>(a.ps, i);
+  ev_xs<BX>(a.ps, i, a.xs_batch_min);
   advance_and_route(tid, a, i);
 }
 OMC_KERNEL_MB(k_xs_advance, EvArgs, body_xs_advance<false>, XA_MINBLOCKS)
@@ -624,7 +633,7 @@ OMC_D void body_surface_xa(int64_t tid, const EvArgs& a)
   const int32_t i = a.q_in.idx[tid];
   prefetch_particle(a.ps, i, false);
   if (ev_surface(a.ps, a.gc, i)) {
-    ev_xs<BX>(a.ps, i);
+    ev_xs<BX>(a.ps, i, a.xs_batch_min);
     advance_and_route(tid, a, i);
   } else {
     no_flight(a, tid);
@@ -643,7 +652,7 @@ OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
   const int32_t i = a.q_in.idx[tid];
   prefetch_particle(a.ps, i, true);
   if (ev_collide(a.ps, a.gc, a.fb, i)) {
-    ev_xs<BX>(a.ps, i);
+    ev_xs<BX>(a.ps, i, a.xs_batch_min);
     advance_and_route(tid, a, i);
   } else {
     no_flight(a, tid);
@@ -989,7 +998,7 @@ OMC_D void body_tail(int64_t tid, const EvArgs& a)
   int next = a.first_event; // what the histories of this list are waiting for
   for (;;) {
     if (next == NEXT_NONE) {
-      ev_xs(a.ps, i);
+      ev_xs<true>(a.ps, i, a.xs_batch_min); // few long-running threads: chain length, not registers, matters
       ++n_xs;
       next = ev_advance(a.ps, a.gc, a.fl, i, SLOT_LOG);
     }
@@ -1017,13 +1026,18 @@ constexpr int TAIL_BLOCK = 64;
 #if OMC_CUDA
 #define LAUNCH_TAIL(n_ub, stream, args) \
   do { \
+    (args).xs_batch_min = tail_batch_min(); \
     if ((n_ub) > 0) { \
       k_tail<<<(unsigned)(((n_ub) + TAIL_BLOCK - 1) / TAIL_BLOCK), TAIL_BLOCK, 0, stream>>>((int64_t)(n_ub), args); \
       ++g_launches; \
     } \
   } while (0)
 #else
-#define LAUNCH_TAIL(n_ub, stream, args) OMC_LAUNCH(k_tail, n_ub, stream, args)
+#define LAUNCH_TAIL(n_ub, stream, args) \
+  do { \
+    (args).xs_batch_min = tail_batch_min(); \
+    OMC_LAUNCH(k_tail, n_ub, stream, args); \
+  } while (0)
 #endif
 
 // ---- deterministic reduction of the per-particle accumulators ------------------
@@ -1168,6 +1182,7 @@ struct XsArgs {
   double* out;
   int32_t* i_grid;
   int32_t max_nuc;
+  int32_t xs_batch_min;
 };
 template<bool BX>
 OMC_D void body_probe_xs(int64_t tid, const XsArgs& a)
@@ -1178,7 +1193,7 @@ OMC_D void body_probe_xs(int64_t tid, const XsArgs& a)
   double t = 0, ab = 0, f = 0, nf = 0;
   if (DM.run_CE) {
     ce_macro_xs<BX>(m, a.E[tid], t, ab, f, nf, a.i_grid ? a.i_grid + tid * a.max_nuc : nullptr,
-      a.max_nuc);
+      a.max_nuc, a.xs_batch_min);
   } else {
     const int G = DM.mg_n_groups;
     const int g = (int)a.E[tid];
@@ -1338,6 +1353,8 @@ struct Engine {
   bool ordered = true;          // sweep mode 2: lists rebuilt in particle-index order after every sweep
   void* d_part_tmp = nullptr;   // cub::DevicePartition scratch
   size_t part_tmp_bytes = 0;
+  int64_t low_count = 0;        // OMCGPU_LOW_COUNT: below this many alive histories sweeps and tail use the lockstep
+                                // lookup for every material (measured: no gain, profiles/r19_matrix.log; default off)
   bool batch_xs = false;        // some material has >= OMC_XS_BATCH_MIN nuclides: lockstep lookup kernels
   int sweep_mode = 2;           // 1: xs+advance | surface | collide over a merged alive list; 2: paired lists
   int score_ctas = 0;           // >0: k_score grid capped at this many blocks per SM (persistent, co-resident)
@@ -1351,6 +1368,14 @@ static Engine G;
 static bool batch_xs_enabled()
 {
   return G.batch_xs;
+}
+static int64_t low_count_threshold()
+{
+  return G.low_count;
+}
+static int tail_batch_min()
+{
+  return G.low_count > 0 ? 1 : OMC_XS_BATCH_MIN;
 }
 
 // The continuous-energy tables (energy grids, xs rows, hash tables) are carved from one
@@ -2301,6 +2326,8 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
     for (int m = 0; m < model->n_materials; ++m)
       if (model->mat_nuc_ofs[m + 1] - model->mat_nuc_ofs[m] >= OMC_XS_BATCH_MIN)
         G.batch_xs = true;
+  if (const char* t = std::getenv("OMCGPU_LOW_COUNT"))
+    G.low_count = std::atoll(t);
   if (const char* t = std::getenv("OMCGPU_BATCH_XS"))
     G.batch_xs = std::atoi(t) != 0;
   if (const char* t = std::getenv("OMCGPU_ORDERED"))
