@@ -16,6 +16,7 @@ from openmc_b200 import _abi as abi
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liboracle.so")
 REF_LIB = os.path.join(HERE, "_ref", "libref_helpers.so")
+REF_GEOM_LIB = os.path.join(HERE, "_ref", "libref_geom.so")
 
 
 def build(force=False):
@@ -24,7 +25,11 @@ def build(force=False):
     hdr = abi.HEADER
     stale = (not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src)
              or os.path.getmtime(LIB) < os.path.getmtime(hdr))
-    if force or stale or (os.path.isdir("/root/reference/src") and not os.path.exists(REF_LIB)):
+    have_ref = os.path.isdir("/root/reference/src")
+    shim = os.path.join(HERE, "ref_geom_shim.cpp")
+    ref_stale = have_ref and (not os.path.exists(REF_LIB) or not os.path.exists(REF_GEOM_LIB)
+                              or os.path.getmtime(REF_GEOM_LIB) < os.path.getmtime(shim))
+    if force or stale or ref_stale:
         subprocess.check_call(["make", "-s", "-C", HERE])
 
 

@@ -1,0 +1,104 @@
+"""Doorway to the reference's OWN geometry code for the tests: emits a geometry.xml
+text (format: docs/source/io_formats/geometry.rst, read by src/surface.cpp:1195+,
+src/cell.cpp:1170+, src/lattice.cpp:162-232) from this repo's small model description
+and asks oracle/_ref/libref_geom.so -- the unmodified reference translation units --
+where points are and how far their next boundary is."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "oracle", "_ref", "libref_geom.so")
+
+
+def _fmt(x):
+    return " ".join(repr(float(v)) for v in x)
+
+
+LATTICE_ID_BASE = 100000   # universes and lattices share one id space in geometry.xml
+                           # (a cell's fill is looked up as a universe first, src/geometry_aux.cpp:
+                           # 90-106); this repo's description refers to lattices by object
+
+
+def geometry_xml(m) -> str:
+    out = ["<?xml version='1.0' encoding='utf-8'?>", "<geometry>"]
+    for s in m.surfaces:
+        bc = "" if s.boundary in ("transmission", None) else f' boundary="{s.boundary}"'
+        out.append(f'  <surface id="{s.id}" type="{s.kind}" coeffs="{_fmt(s.coeffs)}"{bc}/>')
+    for c in m.cells:
+        a = [f'id="{c.id}"', f'universe="{c.universe}"']
+        if c.fill_type == "material":
+            a.append('material="void"' if c.fill is None else f'material="{c.fill.id}"')
+        elif c.fill_type == "universe":
+            a.append(f'fill="{c.fill}"')
+        else:
+            a.append(f'fill="{LATTICE_ID_BASE + c.fill.id}"')
+        if c.region:
+            a.append(f'region="{c.region}"')
+        if any(float(t) != 0.0 for t in c.translation):
+            a.append(f'translation="{_fmt(c.translation)}"')
+        out.append("  <cell " + " ".join(a) + "/>")
+    for l in m.lattices:
+        arr = np.asarray(l.universes)
+        if arr.ndim == 2:
+            ny, nx = arr.shape
+            dim = f"{nx} {ny}"
+            nd = 2
+            slabs = [arr]
+        else:
+            nz, ny, nx = arr.shape
+            dim = f"{nx} {ny} {nz}"
+            nd = 3
+            slabs = list(arr)
+        out.append(f'  <lattice id="{LATTICE_ID_BASE + l.id}">')
+        out.append(f"    <pitch>{_fmt(l.pitch[:nd])}</pitch>")
+        out.append(f"    <dimension>{dim}</dimension>")
+        out.append(f"    <lower_left>{_fmt(l.lower_left[:nd])}</lower_left>")
+        if l.outer is not None:
+            out.append(f"    <outer>{l.outer}</outer>")
+        rows = []
+        for slab in slabs:
+            rows += [" ".join(str(int(u)) for u in row) for row in slab]
+        out.append("    <universes>\n" + "\n".join(rows) + "\n    </universes>")
+        out.append("  </lattice>")
+    out.append("</geometry>")
+    return "\n".join(out)
+
+
+class ReferenceGeometry:
+    def __init__(self, m):
+        if not os.path.exists(LIB):
+            raise FileNotFoundError(LIB)
+        self.lib = L = C.CDLL(LIB)
+        L.ref_geom_error.restype = C.c_char_p
+        ids = np.array([mat.id for mat in m.materials], np.int32)
+        rc = L.ref_geom_load(geometry_xml(m).encode(), ids.ctypes.data_as(C.c_void_p), C.c_int(ids.size))
+        if rc:
+            raise RuntimeError(L.ref_geom_error().decode())
+        c = np.zeros(6, np.int32)
+        L.ref_geom_counts(c.ctypes.data_as(C.c_void_p))
+        self.n_surfaces, self.n_cells, self.n_universes, self.n_lattices, self.n_coord_levels, self.root = \
+            (int(x) for x in c)
+
+    def find_cell(self, xyz, uvw):
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        uvw = np.ascontiguousarray(uvw, np.float64)
+        n = xyz.shape[0]
+        cid = np.zeros(n, np.int32); inst = np.zeros(n, np.int32)
+        mat = np.zeros(n, np.int32); nco = np.zeros(n, np.int32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        if self.lib.ref_geom_find_cell(C.c_int64(n), p(xyz), p(uvw), p(cid), p(inst), p(mat), p(nco)):
+            raise RuntimeError(self.lib.ref_geom_error().decode())
+        return cid, inst, mat, nco
+
+    def distance_to_boundary(self, xyz, uvw):
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        uvw = np.ascontiguousarray(uvw, np.float64)
+        n = xyz.shape[0]
+        d = np.zeros(n); s = np.zeros(n, np.int32); lv = np.zeros(n, np.int32)
+        lt = np.zeros((n, 3), np.int32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        if self.lib.ref_geom_distance(C.c_int64(n), p(xyz), p(uvw), p(d), p(s), p(lv), p(lt)):
+            raise RuntimeError(self.lib.ref_geom_error().decode())
+        return d, s, lv, lt

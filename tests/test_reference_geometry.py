@@ -1,0 +1,73 @@
+"""The oracle's geometry (and, through the committed vectors, the CUDA path) against the
+REFERENCE ITSELF: src/surface.cpp, cell.cpp, lattice.cpp, universe.cpp, geometry.cpp,
+geometry_aux.cpp compiled unmodified from /root/reference into
+oracle/_ref/libref_geom.so (oracle/Makefile), fed a geometry.xml text of each
+BASELINE.json configuration.  Cell, instance, material, coordinate depth, crossing
+surface token, level and lattice translation must be bit-exact; so must the distance."""
+import os
+
+import numpy as np
+import pytest
+
+import ref_geometry
+import reference_cases as rc
+from oracle.binding import Oracle
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+needs_ref = pytest.mark.skipif(not os.path.exists(ref_geometry.LIB),
+                               reason="oracle/_ref/libref_geom.so not built (no /root/reference here)")
+
+
+def _compare(model, found, answers, dist, xyz, uvw, engine):
+    cid, inst, mat, nco = found
+    d, s, lv, lt = dist
+    c2, i2, m2, n2 = engine.find_cell(xyz, uvw)
+    ids = np.asarray(model["cell_id"])
+    assert np.array_equal(np.where(c2 >= 0, ids[np.clip(c2, 0, None)], -1), cid)
+    assert np.array_equal(i2, inst) and np.array_equal(m2, mat) and np.array_equal(n2, nco)
+    d2, s2, lv2, lt2 = engine.distance_to_boundary(xyz, uvw)
+    assert np.array_equal(s2, s) and np.array_equal(lv2, lv) and np.array_equal(lt2, lt)
+    return d2, d
+
+
+@needs_ref
+@pytest.mark.parametrize("name", rc.NAMES)
+def test_oracle_geometry_equals_reference(name):
+    m, model, box = rc.build(name)
+    ref = ref_geometry.ReferenceGeometry(m)
+    assert ref.n_surfaces == int(model["n_surfaces"]) and ref.n_cells == int(model["n_cells"])
+    assert ref.n_universes == int(model["n_universes"]) and ref.n_lattices == int(model["n_lattices"])
+    xyz, uvw = rc.probe_points(box, 20000)
+    wx, wu = rc.walk(ref, xyz[:3000], uvw[:3000])
+    xyz, uvw = np.concatenate([xyz, wx]), np.concatenate([uvw, wu])
+    found, dist = ref.find_cell(xyz, uvw), ref.distance_to_boundary(xyz, uvw)
+    assert np.mean(found[0] >= 0) > 0.4   # the rest probes "no cell here" (outside / past a boundary)
+    d2, d = _compare(model, found, None, dist, xyz, uvw, Oracle(model))
+    assert np.array_equal(d2, d)               # same arithmetic, same libm: identical doubles
+
+
+@pytest.mark.parametrize("name", rc.NAMES)
+def test_committed_reference_vectors_are_reproduced_by_the_oracle(name):
+    """the vectors the GPU tier uses (tests/golden/refgeom_*.npz, written by
+    tests/golden/make_reference_geometry.py from the reference library)"""
+    m, model, box = rc.build(name)
+    v = np.load(os.path.join(GOLDEN, f"refgeom_{name}.npz"))
+    found = (v["cell_id"], v["instance"], v["material"], v["n_coord"])
+    dist = (v["distance"], v["surface"], v["level"], v["lattice_trans"])
+    d2, d = _compare(model, found, None, dist, v["xyz"], v["uvw"], Oracle(model))
+    assert np.array_equal(d2, d)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", rc.NAMES)
+def test_gpu_geometry_equals_reference_vectors(gpu_engine, name):
+    """CUDA path vs vectors computed by the reference's own geometry code: indices
+    bit-exact, distances to 1e-12 (device sqrt / division are IEEE, -fmad=false)"""
+    m, model, box = rc.build(name)
+    v = np.load(os.path.join(GOLDEN, f"refgeom_{name}.npz"))
+    gpu_engine.init(model, 0, 65536)
+    found = (v["cell_id"], v["instance"], v["material"], v["n_coord"])
+    dist = (v["distance"], v["surface"], v["level"], v["lattice_trans"])
+    d2, d = _compare(model, found, None, dist, v["xyz"], v["uvw"], gpu_engine)
+    np.testing.assert_allclose(d2, d, rtol=1e-12)
+    gpu_engine.finalize()
