@@ -8,8 +8,11 @@
 //
 // Everything below the includes is link-time filler for symbols those translation units
 // mention but never reach on this path (HDF5 writers, DAGMC, tallies, nuclide tables).
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <new>
 #include <stdexcept>
 #include <string>
 
@@ -25,6 +28,15 @@
 #include "openmc/hdf5_interface.h"
 #include "openmc/lattice.h"
 #include "openmc/material.h"
+#include "openmc/nuclide.h"
+#include "openmc/photon.h"
+#include "openmc/simulation.h"
+#include "openmc/thermal.h"
+#include "openmc/urr.h"
+#include "openmc/wmp.h"
+#include "openmc/endf.h"
+#include "openmc/message_passing.h"
+#include "openmc/cross_sections.h"
 #include "openmc/particle.h"
 #include "openmc/particle_data.h"
 #include "openmc/settings.h"
@@ -37,7 +49,8 @@ hid_t H5T_NATIVE_DOUBLE_g, H5T_NATIVE_FLOAT_g, H5T_NATIVE_INT_g, H5T_NATIVE_UINT
   H5T_NATIVE_LLONG_g, H5T_NATIVE_ULLONG_g, H5T_NATIVE_SCHAR_g, H5T_NATIVE_UCHAR_g, H5T_NATIVE_SHORT_g,
   H5T_NATIVE_USHORT_g, H5T_C_S1_g;
 
-int OPENMC_E_UNASSIGNED {-1}, OPENMC_E_OUT_OF_BOUNDS {-3}, OPENMC_E_INVALID_ID {-7}, OPENMC_E_GEOMETRY {-10};
+int OPENMC_E_UNASSIGNED {-1}, OPENMC_E_OUT_OF_BOUNDS {-3}, OPENMC_E_INVALID_ID {-7}, OPENMC_E_GEOMETRY {-10},
+  OPENMC_E_DATA {-11};
 char openmc_err_msg[256];
 
 // containers of incomplete-at-link-time element types: zero bytes are a valid empty
@@ -48,8 +61,8 @@ EMPTY_VECTOR(_ZN6openmc5model13tally_filtersE);
 EMPTY_VECTOR(_ZN6openmc5model12tally_derivsE);
 EMPTY_VECTOR(_ZN6openmc5model14active_talliesE);
 EMPTY_VECTOR(_ZN6openmc5model18pulse_height_cellsE);
-EMPTY_VECTOR(_ZN6openmc4data8nuclidesE);
 EMPTY_VECTOR(_ZN6openmc4data8elementsE);
+EMPTY_VECTOR(_ZN6openmc4data13thermal_scattE);
 EMPTY_VECTOR(_ZN6openmc8settings20source_write_surf_idE); // std::unordered_set is NOT valid zeroed: never touched
 // type_info objects only named by dynamic_casts in code that is never reached
 alignas(16) char filler_ti_filter[64] asm("_ZTIN6openmc6FilterE") = {0};
@@ -97,6 +110,51 @@ hid_t open_group(hid_t, const char*) { return 0; }
 void write_int(hid_t, int, const hsize_t*, const char*, const int*, bool) {}
 }
 
+// ---- filler for src/nuclide.cpp (its HDF5 constructor and the data kinds this path
+//      does not use: thermal scattering, probability tables, multipole, photons) --------
+[[noreturn]] static void unreachable(const char* what)
+{
+  throw std::runtime_error(std::string("reference filler reached: ") + what);
+}
+void read_attr(hid_t, const char*, hid_t, void*) { unreachable("read_attr"); }
+hid_t file_open(const std::string&, char, bool) { unreachable("file_open"); }
+vector<hsize_t> attribute_shape(hid_t, const char*) { return {}; }
+vector<std::string> dataset_names(hid_t) { return {}; }
+vector<std::string> group_names(hid_t) { return {}; }
+std::string object_name(hid_t) { return ""; }
+hid_t open_object(hid_t, const std::string&) { return 0; }
+void close_object(hid_t) {}
+extern "C" {
+bool attribute_exists(hid_t, const char*) { return false; }
+size_t attribute_typesize(hid_t, const char*) { return 0; }
+void read_attr_string(hid_t, const char*, size_t, char*) {}
+void file_close(hid_t) {}
+}
+void read_multipole_data(int) { unreachable("read_multipole_data"); }
+UrrData::UrrData(hid_t) { unreachable("UrrData"); }
+bool UrrData::has_negative() const { return false; }
+std::tuple<double, double, double> WindowedMultipole::evaluate(double, double) const { unreachable("wmp"); }
+void ThermalScattering::calculate_xs(double, double, int*, double*, double*, uint64_t*) const { unreachable("sab"); }
+PhotonInteraction::PhotonInteraction(hid_t) { unreachable("PhotonInteraction"); }
+PhotonInteraction::~PhotonInteraction() {}
+Reaction::Reaction(hid_t, const vector<int>&, std::string) { unreachable("Reaction"); }
+double Reaction::collapse_rate(int64_t, span<const double>, span<const double>, const vector<double>&) const
+{
+  unreachable("collapse_rate");
+}
+namespace mpi {
+bool master {true};
+}
+namespace simulation {
+double log_spacing {0.0};
+}
+extern "C" {
+bool need_depletion_rx = false;
+bool photon_transport = false;
+int verbosity = 0;
+}
+
+void Particle::mark_as_lost(const char* message) { throw std::runtime_error(message); } // key function: emits the vtable
 void Particle::cross_vacuum_bc(const Surface&) {}
 void Particle::cross_reflective_bc(const Surface&, Direction) {}
 void Particle::cross_periodic_bc(const Surface&, Position, Direction, int) {}
@@ -105,11 +163,22 @@ double Material::temperature() const { return 293.6; }
 namespace model {
 std::unordered_map<int32_t, int32_t> material_map;
 }
+// (data::nuclides, data::temperature_min / _max, data::energy_min / _max come from the
+// reference's src/nuclide.cpp, compiled into this library as well)
 namespace data {
-double temperature_min {0.0};
-double temperature_max {1.0e30};
+std::map<LibraryKey, std::size_t> library_map;
+vector<Library> libraries;
+std::unordered_map<std::string, int> element_map;
 } // namespace data
 namespace settings {
+bool create_delayed_neutrons {true};
+bool delayed_photon_scaling {true};
+bool res_scat_on {false};
+bool temperature_multipole {false};
+bool urr_ptables_on {false};
+int n_log_bins {8000};
+vector<std::string> res_scat_nuclides;
+array<double, 2> temperature_range {0.0, 0.0};
 bool check_overlaps {false};
 bool material_cell_offsets {false};
 std::string path_input;
@@ -224,6 +293,98 @@ int ref_geom_distance(int64_t n, const double* xyz, const double* uvw, double* d
       level[k] = b.coord_level();
       for (int d = 0; d < 3; ++d)
         lattice_trans[3 * k + d] = b.lattice_translation()[d];
+    }
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+} // extern "C"
+
+// =============================================================================
+// Cross-section lookup: the reference's Nuclide::init_grid (src/nuclide.cpp:502-533) and
+// Nuclide::calculate_xs (:616-839) on pointwise tables handed in as arrays.  The HDF5
+// constructor is bypassed: the object is raw zeroed storage (valid empty containers) with
+// the members the lookup reads filled in by hand; everything computed is reference code.
+// =============================================================================
+static Nuclide* make_nuclide(int index, int64_t n, const double* energy, const double* xs4, bool fissionable,
+  double kT)
+{
+  void* raw = ::operator new(sizeof(Nuclide));
+  std::memset(raw, 0, sizeof(Nuclide));
+  Nuclide* nuc = static_cast<Nuclide*>(raw);
+  new (&nuc->name_) std::string("N" + std::to_string(index));
+  nuc->index_ = index;
+  nuc->awr_ = 1.0;
+  nuc->fissionable_ = fissionable;
+  nuc->kTs_.push_back(kT);
+  nuc->grid_.emplace_back();
+  nuc->grid_[0].energy.assign(energy, energy + n);
+  xt::xtensor<double, 2> t({(size_t)n, (size_t)5}, 0.0); // total, absorption, fission, nu-fission, photon prod.
+  for (int64_t i = 0; i < n; ++i)
+    for (int c = 0; c < 4; ++c)
+      t(i, c) = xs4[4 * i + c];
+  nuc->xs_.push_back(std::move(t));
+  return nuc;
+}
+
+extern "C" {
+
+int ref_xs_load(int n_nuc, const int64_t* grid_ofs, const double* energy, const double* xs4,
+  const int32_t* fissionable, const double* kT, int n_log_bins, double e_min, double e_max)
+{
+  try {
+    for (auto& u : data::nuclides)
+      u.release(); // hand-made objects: never run the reference destructor on them
+    data::nuclides.clear();
+    settings::n_log_bins = n_log_bins;
+    settings::temperature_method = TemperatureMethod::NEAREST;
+    data::energy_min[0] = e_min;
+    data::energy_max[0] = e_max;
+    simulation::log_spacing = std::log(e_max / e_min) / n_log_bins; // src/cross_sections.cpp:298-300
+    for (int k = 0; k < n_nuc; ++k) {
+      const int64_t o = grid_ofs[k], n = grid_ofs[k + 1] - o;
+      data::nuclides.emplace_back(make_nuclide(k, n, energy + o, xs4 + 4 * o, fissionable[k] != 0, kT[k]));
+      data::nuclides.back()->init_grid();
+    }
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+int ref_xs_grid_index(int nuc, int32_t* out, int64_t n)
+{
+  const auto& gi = data::nuclides[nuc]->grid_[0].grid_index;
+  if ((int64_t)gi.size() != n)
+    return -1;
+  for (int64_t i = 0; i < n; ++i)
+    out[i] = gi[i];
+  return 0;
+}
+
+// out[k] = total, absorption, fission, nu-fission of nuclide `nuc` at E[k]
+int ref_xs_micro(int nuc, int64_t n, const double* E, double sqrtkT, double* out, int32_t* i_grid,
+  double* interp)
+{
+  try {
+    Particle p;
+    p.sqrtkT() = sqrtkT;
+    for (int64_t k = 0; k < n; ++k) {
+      p.E() = E[k];
+      // Material::calculate_neutron_xs, src/material.cpp:833-834
+      const int i_log_union = std::log(p.E() / data::energy_min[0]) / simulation::log_spacing;
+      data::nuclides[nuc]->calculate_xs(C_NONE, i_log_union, 0.0, p);
+      const auto& micro = p.neutron_xs(nuc);
+      out[4 * k + 0] = micro.total;
+      out[4 * k + 1] = micro.absorption;
+      out[4 * k + 2] = micro.fission;
+      out[4 * k + 3] = micro.nu_fission;
+      i_grid[k] = micro.index_grid;
+      interp[k] = micro.interp_factor;
     }
   } catch (const std::exception& e) {
     std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());

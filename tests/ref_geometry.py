@@ -102,3 +102,58 @@ class ReferenceGeometry:
         if self.lib.ref_geom_distance(C.c_int64(n), p(xyz), p(uvw), p(d), p(s), p(lv), p(lt)):
             raise RuntimeError(self.lib.ref_geom_error().decode())
         return d, s, lv, lt
+
+
+class ReferenceXS:
+    """The reference's Nuclide::init_grid + Nuclide::calculate_xs (src/nuclide.cpp:502-533,
+    616-839, compiled unmodified) on the pointwise tables of a flattened CE model."""
+
+    def __init__(self, model):
+        if not os.path.exists(LIB):
+            raise FileNotFoundError(LIB)
+        self.lib = L = C.CDLL(LIB)
+        L.ref_geom_error.restype = C.c_char_p
+        self.model = model
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.nn = int(model["n_nuclides"])
+        self.ofs = np.ascontiguousarray(model["nuc_grid_ofs"], np.int64)
+        en = np.ascontiguousarray(model["nuc_energy"], np.float64)
+        xs = np.ascontiguousarray(model["nuc_xs"], np.float64)
+        fis = np.ascontiguousarray(model["nuc_fissionable"], np.int32)
+        kT = np.ascontiguousarray(model["nuc_kT"], np.float64)
+        self.n_log_bins = int(model["n_log_bins"])
+        self.e_min, self.e_max = float(model["energy_min"]), float(model["energy_max"])
+        if L.ref_xs_load(C.c_int(self.nn), p(self.ofs), p(en), p(xs), p(fis), p(kT), C.c_int(self.n_log_bins),
+                         C.c_double(self.e_min), C.c_double(self.e_max)):
+            raise RuntimeError(L.ref_geom_error().decode())
+
+    def in_range(self, E):
+        """energies the reference can be asked about: outside [E_min, E_max) its hash
+        lookup indexes past the table (src/nuclide.cpp:732-733; transport never gets there)"""
+        E = np.asarray(E, float)
+        return np.ascontiguousarray(E[(E >= self.e_min) & (E < self.e_max * (1 - 1e-9))])
+
+    def grid_index(self, nuc):
+        gi = np.zeros(self.n_log_bins + 1, np.int32)
+        assert self.lib.ref_xs_grid_index(C.c_int(nuc), gi.ctypes.data_as(C.c_void_p), C.c_int64(gi.size)) == 0
+        return gi
+
+    def micro(self, nuc, E, sqrtkT=0.15906):
+        E = np.ascontiguousarray(E, np.float64)
+        out = np.zeros((E.size, 4)); ig = np.zeros(E.size, np.int32); fr = np.zeros(E.size)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        if self.lib.ref_xs_micro(C.c_int(int(nuc)), C.c_int64(E.size), p(E), C.c_double(sqrtkT), p(out), p(ig), p(fr)):
+            raise RuntimeError(self.lib.ref_geom_error().decode())
+        return out, ig, fr
+
+    def macro(self, mat, E):
+        """sum over the material's nuclides in order (src/material.cpp:893-899); returns the
+        sums [n][4] and the grid indices [n][n_nuclides of the material]"""
+        m = self.model
+        k0, k1 = int(m["mat_nuc_ofs"][mat]), int(m["mat_nuc_ofs"][mat + 1])
+        tot = np.zeros((np.size(E), 4)); igs = []
+        for k in range(k0, k1):
+            out, ig, _ = self.micro(int(m["mat_nuclide"][k]), E)
+            tot += float(m["mat_atom_density"][k]) * out
+            igs.append(ig)
+        return tot, (np.stack(igs, 1) if igs else np.zeros((np.size(E), 0), np.int32))
