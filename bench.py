@@ -45,7 +45,7 @@ def parse():
                     choices=["pincell_ce", "pincell_mg", "assembly_ce", "c5g7_core", "pwr_core_ce"],
                     help="pincell_ce = config C2 (the bench line); the others are C1, C3, C4, C5")
     ap.add_argument("--n-fuel-nuclides", type=int, default=300, help="pwr_core_ce: nuclides in the fuel")
-    ap.add_argument("--cpu-sample", type=int, default=60_000, help="histories of the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=160_000, help="histories of the cpu_baseline sample (~25 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
