@@ -43,7 +43,7 @@ constexpr int BLOCK = OMC_BLOCK;
 #define XA_MINBLOCKS 4 /* resident blocks per SM asked of k_xs_advance / k_surface_xa (register cap) */
 #endif
 #ifndef CX_MINBLOCKS
-#define CX_MINBLOCKS 3 /* the same for k_collide / k_collide_xa (measured: profiles/README.md r10-r11) */
+#define CX_MINBLOCKS 4 /* the same for k_collide / k_collide_xa (measured: profiles/README.md r10-r11, r21) */
 #endif
 
 // -----------------------------------------------------------------------------
@@ -676,7 +676,7 @@ OMC_KERNEL_MB(k_collide_xa_b, EvArgs, body_collide_xa<true>, 2)
 // -----------------------------------------------------------------------------
 constexpr int SCORE_NVAL = OMCGPU_MAX_SCORES;
 #ifndef SCORE_MINBLOCKS
-#define SCORE_MINBLOCKS 2 /* resident blocks per SM the register budget of k_score allows */
+#define SCORE_MINBLOCKS 3 /* resident blocks per SM asked of k_score (80 registers; measured r21: +3 % at 4e6 histories) */
 #endif
 
 // simple tally: one bin per non-mesh filter -> base index.  NS = scores actually emitted
