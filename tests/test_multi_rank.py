@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-N, BATCHES, INACTIVE = 1500, 5, 2
+N, BATCHES, INACTIVE = 1502, 5, 2
 
 
 def _free_port():
@@ -59,19 +59,21 @@ def _worker(rank, size, port, name, emu_path, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["mg_legendre", "mg_temperature_multi"])
-def test_two_ranks_equal_one_rank(emu_lib, name, tmp_path):
+@pytest.mark.parametrize("name,size", [("mg_legendre", 2), ("mg_temperature_multi", 2), ("mg_legendre", 4)])
+def test_ranks_equal_one_rank(emu_lib, name, size, tmp_path):
+    """world sizes 2 and 4 (N = 1500 is not divisible by 4: uneven shares, and a rank's sampled
+    sites go to several owners)"""
     single = _run(name, emu_lib, None)
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, name, emu_lib, str(tmp_path)), nprocs=2, join=True)
-    r0 = np.load(tmp_path / "rank0.npz")
-    r1 = np.load(tmp_path / "rank1.npz")
-    np.testing.assert_allclose(r0["kgen"], single["kgen"], rtol=1e-12)
-    np.testing.assert_allclose(r1["kgen"], single["kgen"], rtol=1e-12)
+    mp.spawn(_worker, args=(size, port, name, emu_lib, str(tmp_path)), nprocs=size, join=True)
+    ranks = [np.load(tmp_path / f"rank{r}.npz") for r in range(size)]
+    r0 = ranks[0]
+    for r in ranks:
+        np.testing.assert_allclose(r["kgen"], single["kgen"], rtol=1e-12)
     np.testing.assert_allclose(r0["k"], single["k"], rtol=1e-9)
     # the redistributed source bank: rank r holds global sites [work_index[r], work_index[r+1])
-    bank = np.concatenate([r0["bank"], r1["bank"]])
-    assert int(r1["lo"]) == r0["bank"].size
+    bank = np.concatenate([r["bank"] for r in ranks])
+    assert int(ranks[1]["lo"]) == r0["bank"].size
     for f in ("r", "u", "E", "wgt", "delayed_group", "parent_id", "progeny_id"):
         assert np.array_equal(bank[f], single["bank"][f]), f
     for i, t in enumerate(single["tallies"]):
