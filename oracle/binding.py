@@ -114,6 +114,21 @@ class Oracle:
                                   C.c_int32(max_nuc))
         return out, ig
 
+    def mesh_bins_crossed(self, mesh, r0, r1, u, cap_per_track=512):
+        """(ofs, bins, length fractions) of StructuredMesh::bins_crossed for tracks r0 -> r1"""
+        self.load()
+        r0 = np.ascontiguousarray(r0, np.float64); r1 = np.ascontiguousarray(r1, np.float64)
+        u = np.ascontiguousarray(u, np.float64)
+        n = r0.shape[0]
+        cap = n * cap_per_track
+        ofs = np.zeros(n + 1, np.int64); bins = np.zeros(cap, np.int32); lengths = np.zeros(cap)
+        self.lib.orc_mesh_bins_crossed.restype = C.c_int64
+        tot = self.lib.orc_mesh_bins_crossed(C.c_int(mesh), C.c_int64(n), _p(r0, C.c_double), _p(r1, C.c_double),
+                                             _p(u, C.c_double), _p(ofs, C.c_int64), _p(bins, C.c_int32),
+                                             _p(lengths, C.c_double), C.c_int64(cap))
+        assert tot >= 0
+        return ofs, bins[:tot], lengths[:tot]
+
     # ---- transport -----------------------------------------------------------
     def sample_initial_source(self, n, box, only_fissionable=False, master_seed=1,
                               stride=152917, id_offset=0, watt=(0.988e6, 2.249e-6)):

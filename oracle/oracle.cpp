@@ -2147,6 +2147,31 @@ int orc_distance_to_boundary(const double* xyz, const double* uvw, int64_t n, do
   return 0;
 }
 
+// StructuredMesh::bins_crossed (src/mesh.cpp:999-1146) for n tracks r0 -> r1: track k's
+// (bin, length fraction) pairs are out[ofs[k] .. ofs[k+1]); returns the number of pairs
+int64_t orc_mesh_bins_crossed(int mesh, int64_t n, const double* r0, const double* r1, const double* u,
+  int64_t* ofs, int32_t* bins, double* lengths, int64_t cap)
+{
+  Match match;
+  int64_t total = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    match.bins.clear();
+    match.weights.clear();
+    mesh_bins_crossed(mesh, Vec3 {r0[3 * k], r0[3 * k + 1], r0[3 * k + 2]},
+      Vec3 {r1[3 * k], r1[3 * k + 1], r1[3 * k + 2]}, Vec3 {u[3 * k], u[3 * k + 1], u[3 * k + 2]}, match);
+    ofs[k] = total;
+    if (total + (int64_t)match.bins.size() > cap)
+      return -1;
+    for (size_t j = 0; j < match.bins.size(); ++j) {
+      bins[total + j] = match.bins[j];
+      lengths[total + j] = match.weights[j];
+    }
+    total += match.bins.size();
+  }
+  ofs[n] = total;
+  return total;
+}
+
 int orc_calculate_xs(const double* E, const int32_t* material, int64_t n, double* out,
   int32_t* i_grid, int32_t max_nuc)
 {

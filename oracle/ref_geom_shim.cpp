@@ -28,6 +28,9 @@
 #include "openmc/hdf5_interface.h"
 #include "openmc/lattice.h"
 #include "openmc/material.h"
+#include "openmc/mesh.h"
+#include "openmc/output.h"
+#include "openmc/timer.h"
 #include "openmc/nuclide.h"
 #include "openmc/photon.h"
 #include "openmc/simulation.h"
@@ -49,8 +52,8 @@ hid_t H5T_NATIVE_DOUBLE_g, H5T_NATIVE_FLOAT_g, H5T_NATIVE_INT_g, H5T_NATIVE_UINT
   H5T_NATIVE_LLONG_g, H5T_NATIVE_ULLONG_g, H5T_NATIVE_SCHAR_g, H5T_NATIVE_UCHAR_g, H5T_NATIVE_SHORT_g,
   H5T_NATIVE_USHORT_g, H5T_C_S1_g;
 
-int OPENMC_E_UNASSIGNED {-1}, OPENMC_E_OUT_OF_BOUNDS {-3}, OPENMC_E_INVALID_ID {-7}, OPENMC_E_GEOMETRY {-10},
-  OPENMC_E_DATA {-11};
+int OPENMC_E_UNASSIGNED {-1}, OPENMC_E_ALLOCATE {-2}, OPENMC_E_OUT_OF_BOUNDS {-3}, OPENMC_E_INVALID_ARGUMENT {-5},
+  OPENMC_E_INVALID_TYPE {-6}, OPENMC_E_INVALID_ID {-7}, OPENMC_E_GEOMETRY {-10}, OPENMC_E_DATA {-11};
 char openmc_err_msg[256];
 
 // containers of incomplete-at-link-time element types: zero bytes are a valid empty
@@ -77,6 +80,7 @@ namespace openmc {
 
 template<> const hid_t H5TypeMap<double>::type_id = 0;
 template<> const hid_t H5TypeMap<int>::type_id = 0;
+template<> const hid_t H5TypeMap<bool>::type_id = 0;
 
 [[noreturn]] void fatal_error(const std::string& message, int)
 {
@@ -123,10 +127,20 @@ vector<std::string> dataset_names(hid_t) { return {}; }
 vector<std::string> group_names(hid_t) { return {}; }
 std::string object_name(hid_t) { return ""; }
 hid_t open_object(hid_t, const std::string&) { return 0; }
+void write_attr(hid_t, int, const hsize_t*, const char*, hid_t, const void*) {}
+void header(const char*, int) {}
+void Timer::start() {}
+void Timer::stop() {}
+double Timer::elapsed() { return 0.0; }
+void Particle::cross_surface(const Surface&) { unreachable("Particle::cross_surface"); }
+void Particle::from_source(const SourceSite*) { unreachable("Particle::from_source"); }
 void close_object(hid_t) {}
 extern "C" {
 bool attribute_exists(hid_t, const char*) { return false; }
 size_t attribute_typesize(hid_t, const char*) { return 0; }
+size_t dataset_typesize(hid_t, const char*) { return 0; }
+void read_string(hid_t, const char*, size_t, char*, bool) {}
+void write_attr_string(hid_t, const char*, const char*) {}
 void read_attr_string(hid_t, const char*, size_t, char*) {}
 void file_close(hid_t) {}
 }
@@ -144,7 +158,9 @@ double Reaction::collapse_rate(int64_t, span<const double>, span<const double>, 
 }
 namespace mpi {
 bool master {true};
-}
+int rank {0};
+int n_procs {1};
+} // namespace mpi
 namespace simulation {
 double log_spacing {0.0};
 }
@@ -391,6 +407,64 @@ int ref_xs_micro(int nuc, int64_t n, const double* E, double sqrtkT, double* out
     return -1;
   }
   return 0;
+}
+
+} // extern "C"
+
+// =============================================================================
+// Mesh ray trace of the tracklength tallies: the reference's RegularMesh
+// (src/mesh.cpp:999-1146, 1249-1369) built from a <mesh> element.
+// =============================================================================
+extern "C" {
+
+int ref_mesh_load(const char* xml)
+{
+  try {
+    model::meshes.clear();
+    model::mesh_map.clear();
+    pugi::xml_document doc;
+    if (!doc.load_string(xml))
+      throw std::runtime_error("cannot parse the mesh xml");
+    for (auto node : doc.document_element().children("mesh")) {
+      model::meshes.push_back(make_unique<RegularMesh>(node));
+      model::mesh_map[model::meshes.back()->id_] = model::meshes.size() - 1;
+    }
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+// bins_crossed for n tracks r0 -> r1 (u = direction); track k's (bin, length fraction)
+// pairs are out[ofs[k] .. ofs[k+1]); returns the number of pairs or -1 (cap too small)
+int64_t ref_mesh_bins_crossed(int mesh, int64_t n, const double* r0, const double* r1, const double* u,
+  int64_t* ofs, int32_t* bins, double* lengths, int64_t cap)
+{
+  try {
+    vector<int> b;
+    vector<double> l;
+    int64_t total = 0;
+    for (int64_t k = 0; k < n; ++k) {
+      b.clear();
+      l.clear();
+      model::meshes[mesh]->bins_crossed({r0[3 * k], r0[3 * k + 1], r0[3 * k + 2]},
+        {r1[3 * k], r1[3 * k + 1], r1[3 * k + 2]}, {u[3 * k], u[3 * k + 1], u[3 * k + 2]}, b, l);
+      ofs[k] = total;
+      if (total + (int64_t)b.size() > cap)
+        return -1;
+      for (size_t j = 0; j < b.size(); ++j) {
+        bins[total + j] = b[j];
+        lengths[total + j] = l[j];
+      }
+      total += b.size();
+    }
+    ofs[n] = total;
+    return total;
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -2;
+  }
 }
 
 } // extern "C"

@@ -157,3 +157,34 @@ class ReferenceXS:
             tot += float(m["mat_atom_density"][k]) * out
             igs.append(ig)
         return tot, (np.stack(igs, 1) if igs else np.zeros((np.size(E), 0), np.int32))
+
+
+class ReferenceMesh:
+    """The reference's RegularMesh (src/mesh.cpp, compiled unmodified) built from <mesh> elements."""
+
+    def __init__(self, meshes):
+        if not os.path.exists(LIB):
+            raise FileNotFoundError(LIB)
+        self.lib = L = C.CDLL(LIB)
+        L.ref_geom_error.restype = C.c_char_p
+        L.ref_mesh_bins_crossed.restype = C.c_int64
+        x = ["<tallies>"]
+        for m in meshes:
+            x.append(f'  <mesh id="{m.id}"><dimension>{" ".join(str(int(d)) for d in m.dimension)}</dimension>'
+                     f"<lower_left>{_fmt(m.lower_left)}</lower_left><upper_right>{_fmt(m.upper_right)}</upper_right></mesh>")
+        x.append("</tallies>")
+        if L.ref_mesh_load("\n".join(x).encode()):
+            raise RuntimeError(L.ref_geom_error().decode())
+
+    def bins_crossed(self, mesh, r0, r1, u, cap_per_track=512):
+        r0 = np.ascontiguousarray(r0, np.float64); r1 = np.ascontiguousarray(r1, np.float64)
+        u = np.ascontiguousarray(u, np.float64)
+        n = r0.shape[0]
+        cap = n * cap_per_track
+        ofs = np.zeros(n + 1, np.int64); bins = np.zeros(cap, np.int32); lengths = np.zeros(cap)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        tot = self.lib.ref_mesh_bins_crossed(C.c_int(mesh), C.c_int64(n), p(r0), p(r1), p(u), p(ofs), p(bins),
+                                             p(lengths), C.c_int64(cap))
+        if tot < 0:
+            raise RuntimeError(self.lib.ref_geom_error().decode() or "capacity")
+        return ofs, bins[:tot], lengths[:tot]
