@@ -1547,17 +1547,14 @@ OMC_D void tally_add(double* addr, double val)
   // RED -- measured: a match_any + shuffle loop per score cost 12 % of k_score for a
   // 500-bin spectrum tally and saved almost no atomics (profiles/README.md).
   const unsigned active = __activemask();
-  int same;
-  __match_all_sync(active, (unsigned long long)addr, &same);
-  if (same) {
-    double sum = val;
+  if (active == 0xffffffffu) { // (a partial warp -- lanes in different filter branches -- adds directly)
+    int same;
+    __match_all_sync(active, (unsigned long long)addr, &same);
+    if (same) {
+      double sum = val;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const double o = __shfl_xor_sync(active, sum, d);
-      if (active == 0xffffffffu)
-        sum += o;
-    }
-    if (active == 0xffffffffu) {
+      for (int d = 16; d > 0; d >>= 1)
+        sum += __shfl_xor_sync(active, sum, d);
       if ((threadIdx.x & 31) == 0)
         atomic_add_f64(addr, sum);
       return;

@@ -683,13 +683,17 @@ constexpr int SCORE_NVAL = OMCGPU_MAX_SCORES;
 // per mesh cell (the loop below is compile-time: no issue slots for absent scores)
 template<int NS>
 struct PartEmit {
-  double* results;
-  int64_t base;
-  int mesh_stride, ns;
+  double* r0;     // results + base * ns: the part's row of bin 0
+  int bin_stride; // doubles between two mesh bins = mesh_stride * ns
   double val[NS];
+  OMC_D void set(double* results, int64_t base, int mesh_stride, int ns)
+  {
+    r0 = results + base * ns;
+    bin_stride = mesh_stride * ns;
+  }
   OMC_D void operator()(int bin, double w) const
   {
-    double* r = results + (base + (int64_t)bin * mesh_stride) * ns;
+    double* r = r0 + (int64_t)bin * bin_stride; // one wide multiply-add per mesh cell
 #pragma unroll
     for (int s = 0; s < NS; ++s) // compile-time indices keep val in registers
       if (val[s] != 0.0)
@@ -850,9 +854,6 @@ __device__ __forceinline__ void score_parts(int mesh, int mesh_stride, int ns, d
   int lane, const int* incl, const double (*sd)[32], const int64_t* sbase)
 {
   PartEmit<NS> em;
-  em.results = results;
-  em.mesh_stride = mesh_stride;
-  em.ns = ns;
   for (int item = lane; item < n_parts; item += 32) {
     int o = 0; // owner: first lane whose inclusive count exceeds item
     for (int step = 16; step > 0; step >>= 1)
@@ -866,7 +867,7 @@ __device__ __forceinline__ void score_parts(int mesh, int mesh_stride, int ns, d
 #pragma unroll
     for (int s = 0; s < NS; ++s)
       em.val[s] = sd[7 + s][o];
-    em.base = sbase[o];
+    em.set(results, sbase[o], mesh_stride, ns);
     mesh_march(mesh, pr0, pu, ptotal, part_bound(c, onc, ptotal), part_bound(c + 1, onc, ptotal), em);
   }
 }
@@ -944,11 +945,11 @@ void k_score(int64_t n_ub, EvArgs a)
     const Flight f = load_flight(a.fl, tid);
     for (int t = 0; t < DM.n_tallies; ++t) {
       PartEmit<SCORE_NVAL> em;
-      const int nc = score_prepare(a.ps, f, t, a.gc.tally_values, a.gc.score_part, em.base, em.val);
-      int mesh;
-      tally_mesh_info(t, mesh, em.mesh_stride);
-      em.results = a.gc.tally_values + DM.tally_result_ofs[t];
-      em.ns = DM.tally_n_scores[t];
+      int64_t base = 0;
+      const int nc = score_prepare(a.ps, f, t, a.gc.tally_values, a.gc.score_part, base, em.val);
+      int mesh, mesh_stride;
+      tally_mesh_info(t, mesh, mesh_stride);
+      em.set(a.gc.tally_values + DM.tally_result_ofs[t], base, mesh_stride, DM.tally_n_scores[t]);
       for (int c = 0; c < nc; ++c)
         mesh_march(mesh, f.r0, f.u, f.total, part_bound(c, nc, f.total), part_bound(c + 1, nc, f.total), em);
     }
