@@ -556,6 +556,37 @@ OMC_D void body_init(int64_t tid, const EvArgs& a)
 }
 OMC_KERNEL(k_init, EvArgs, body_init)
 
+// Sort key of a calculate-xs work item: (material, lethargy) -- particles of one material
+// with neighbouring energies sit next to each other in the sorted list, so a warp's
+// gathers of the hash window, the probes and the xs rows of a nuclide fall into the same
+// few sectors (many-nuclide materials: the tables are far larger than L2).  Positions
+// beyond the list's count get the largest key.
+struct KeyArgs {
+  PState ps;
+  Queue q_in;
+  uint32_t* keys;
+  int32_t* vals;
+};
+OMC_D void body_xs_keys(int64_t tid, const KeyArgs& a)
+{
+  uint32_t key = 0xffffffffu;
+  int32_t i = 0;
+  if (tid < *a.q_in.count) {
+    i = a.q_in.idx[tid];
+    const int m = a.ps.material[i];
+    if (m >= 0 && DM.run_CE) {
+      double u = log(a.ps.E[i] / DM.energy_min) * DM.fine_inv_spacing * 8.0; // 1/8 of a fine-hash bin
+      u = u < 0.0 ? 0.0 : (u > 16777215.0 ? 16777215.0 : u);
+      key = ((uint32_t)(m < 254 ? m : 254) << 24) | (uint32_t)u;
+    } else {
+      key = 0xff000000u;
+    }
+  }
+  a.keys[tid] = key;
+  a.vals[tid] = i;
+}
+OMC_KERNEL(k_xs_keys, KeyArgs, body_xs_keys)
+
 template<bool BX>
 OMC_D void body_xs(int64_t tid, const EvArgs& a)
 {
@@ -970,7 +1001,10 @@ OMC_D void body_surface(int64_t tid, const EvArgs& a)
     return;
   const int32_t i = a.q_in.idx[tid];
   prefetch_particle(a.ps, i, false);
-  if (ev_surface(a.ps, a.gc, i))
+  const bool alive = ev_surface(a.ps, a.gc, i);
+  if (a.ordered)
+    a.ps.next_ev[i] = alive ? 3 : 0; // 3: waits for its next flight
+  else if (alive)
     queue_append(a.q_a, i);
 }
 OMC_KERNEL(k_surface, EvArgs, body_surface)
@@ -981,7 +1015,10 @@ OMC_D void body_collide(int64_t tid, const EvArgs& a)
     return;
   const int32_t i = a.q_in.idx[tid];
   prefetch_particle(a.ps, i, true);
-  if (ev_collide(a.ps, a.gc, a.fb, i))
+  const bool alive = ev_collide(a.ps, a.gc, a.fb, i);
+  if (a.ordered)
+    a.ps.next_ev[i] = alive ? 3 : 0;
+  else if (alive)
     queue_append(a.q_a, i);
 }
 OMC_KERNEL_MB(k_collide, EvArgs, body_collide, CX_MINBLOCKS)
@@ -1351,6 +1388,11 @@ struct Engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evx0[RING] = {}, evx1[RING] = {}, evp0 = nullptr, evp1 = nullptr;
   bool fuse_xs = true;          // k_xs + k_advance as one kernel (ms_xs then covers both)
+  bool sort_xs = false;         // sweep mode 1, unfused: k_xs runs over the list sorted by (material, energy)
+  uint32_t *d_keys = nullptr, *d_keys_out = nullptr;
+  int32_t *d_vals = nullptr, *d_vals_out = nullptr;
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
   bool ordered = true;          // sweep mode 2: lists rebuilt in particle-index order after every sweep
   void* d_part_tmp = nullptr;   // cub::DevicePartition scratch
   size_t part_tmp_bytes = 0;
@@ -1800,6 +1842,43 @@ struct SweepStats {
   double ms_xs = 0.0;
 };
 
+// Order-preserving list build: the histories flagged 1 in ps.next_ev go to `coll`,
+// those flagged 2 to `surf`, both in ascending particle index, and the two counts
+// to counts[0..1].  Appending with atomics instead leaves every list in the order
+// the warps happened to finish: after a few sweeps a warp's 32 particles are 32
+// unrelated sectors of every column.  Index order keeps a warp's gathers within a
+// few neighbouring lines and DRAM pages.
+#if OMC_CUDA
+struct FlagIs {
+  const uint8_t* f;
+  uint8_t v;
+  __device__ __forceinline__ bool operator()(int i) const { return f[i] == v; }
+};
+#endif
+static int build_lists(int64_t n, int32_t* coll, int32_t* surf, int32_t* counts, cudaStream_t stream,
+  uint8_t v1 = 1, uint8_t v2 = 2)
+{
+#if OMC_CUDA
+  FlagIs is_coll{G.ps.next_ev, v1}, is_surf{G.ps.next_ev, v2};
+  thrust::counting_iterator<int32_t> ids(0);
+  thrust::discard_iterator<> none;
+  size_t bytes = G.part_tmp_bytes;
+  CUDA_OK(cub::DevicePartition::If(G.d_part_tmp, bytes, ids, coll, surf, none, counts, (int)n, is_coll,
+    is_surf, stream));
+  g_launches += 2;
+#else
+  (void)stream;
+  counts[0] = counts[1] = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (G.ps.next_ev[i] == v1)
+      coll[counts[0]++] = (int32_t)i;
+    else if (G.ps.next_ev[i] == v2)
+      surf[counts[1]++] = (int32_t)i;
+  }
+#endif
+  return 0;
+}
+
 // ---- sweep mode 1: one merged alive list; xs+advance, then crossing / collision --
 static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, SweepStats& st)
 {
@@ -1819,6 +1898,9 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     return rc;
   int64_t n_alive = G.h_counts[0]; // last count read back: upper bound of the lists
   int32_t* alive_count = G.d_counts + 0;
+  a.ordered = G.ordered ? 1 : 0;
+  if (G.ordered)
+    CUDA_OK(cudaMemsetAsync(G.ps.next_ev, 0, (size_t)n, G.stream));
   int64_t n_xs = 0, n_coll = 0, n_cross = 0;
   double ms_xs = 0.0;
   const bool score = in->tallies_active && G.hm.n_tallies > 0;
@@ -1854,9 +1936,41 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       LAUNCH_XS(k_xs_advance, n_alive, G.stream, a);
       CUDA_OK(cudaEventRecord(G.evx1[ev], G.stream));
     } else {
-      LAUNCH_XS(k_xs, n_alive, G.stream, a);
+      if (G.sort_xs) {
+        KeyArgs ka;
+        ka.ps = G.ps;
+        ka.q_in = a.q_in;
+        ka.keys = G.d_keys;
+        ka.vals = G.d_vals;
+        OMC_LAUNCH(k_xs_keys, n_alive, G.stream, ka);
+#if OMC_CUDA
+        size_t bytes = G.sort_tmp_bytes;
+        CUDA_OK(cub::DeviceRadixSort::SortPairs(G.d_sort_tmp, bytes, G.d_keys, G.d_keys_out, G.d_vals, G.d_vals_out,
+          (int)n_alive, 0, 32, G.stream));
+        g_launches += 4;
+#else
+        {
+          std::vector<std::pair<uint32_t, int32_t>> kv((size_t)n_alive);
+          for (int64_t k = 0; k < n_alive; ++k)
+            kv[k] = {G.d_keys[k], G.d_vals[k]};
+          std::stable_sort(kv.begin(), kv.end(), [](auto& x, auto& y) { return x.first < y.first; });
+          for (int64_t k = 0; k < n_alive; ++k)
+            G.d_vals_out[k] = kv[k].second;
+        }
+#endif
+        EvArgs ax = a; // the same histories, in (material, energy) order
+        ax.q_in.idx = G.d_vals_out;
+        LAUNCH_XS(k_xs, n_alive, G.stream, ax);
+      } else {
+        LAUNCH_XS(k_xs, n_alive, G.stream, a);
+      }
       CUDA_OK(cudaEventRecord(G.evx1[ev], G.stream));
       OMC_LAUNCH(k_advance, n_alive, G.stream, a);
+    }
+    if (G.ordered) { // collision / crossing lists in particle-index order (see build_lists)
+      rc = build_lists(n, G.q[2].idx, G.q[3].idx, slot, G.stream);
+      if (rc)
+        return rc;
     }
     // cell / universe filters read the live coordinate levels: score before the
     // crossing and collision kernels may change them
@@ -1892,6 +2006,11 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       CUDA_OK(cudaEventRecord(G.e_coll, st_coll));
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_surf, 0));
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_coll, 0));
+    }
+    if (G.ordered) { // the next alive list: survivors of both kernels, in index order (counts: slot[2], slot[3] = 0)
+      rc = build_lists(n, G.q[nxt].idx, G.d_gather, slot + 2, G.stream, 3, 255);
+      if (rc)
+        return rc;
     }
     alive_count = slot + 2;
     cur = nxt;
@@ -1940,42 +2059,6 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
   st.n_coll = n_coll;
   st.n_cross = n_cross;
   st.ms_xs = ms_xs;
-  return 0;
-}
-
-// Order-preserving list build: the histories flagged 1 in ps.next_ev go to `coll`,
-// those flagged 2 to `surf`, both in ascending particle index, and the two counts
-// to counts[0..1].  Appending with atomics instead leaves every list in the order
-// the warps happened to finish: after a few sweeps a warp's 32 particles are 32
-// unrelated sectors of every column.  Index order keeps a warp's gathers within a
-// few neighbouring lines and DRAM pages.
-#if OMC_CUDA
-struct FlagIs {
-  const uint8_t* f;
-  uint8_t v;
-  __device__ __forceinline__ bool operator()(int i) const { return f[i] == v; }
-};
-#endif
-static int build_lists(int64_t n, int32_t* coll, int32_t* surf, int32_t* counts, cudaStream_t stream)
-{
-#if OMC_CUDA
-  FlagIs is_coll{G.ps.next_ev, 1}, is_surf{G.ps.next_ev, 2};
-  thrust::counting_iterator<int32_t> ids(0);
-  thrust::discard_iterator<> none;
-  size_t bytes = G.part_tmp_bytes;
-  CUDA_OK(cub::DevicePartition::If(G.d_part_tmp, bytes, ids, coll, surf, none, counts, (int)n, is_coll,
-    is_surf, stream));
-  g_launches += 2;
-#else
-  (void)stream;
-  counts[0] = counts[1] = 0;
-  for (int64_t i = 0; i < n; ++i) {
-    if (G.ps.next_ev[i] == 1)
-      coll[counts[0]++] = (int32_t)i;
-    else if (G.ps.next_ev[i] == 2)
-      surf[counts[1]++] = (int32_t)i;
-  }
-#endif
   return 0;
 }
 
@@ -2327,6 +2410,17 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
     for (int m = 0; m < model->n_materials; ++m)
       if (model->mat_nuc_ofs[m + 1] - model->mat_nuc_ofs[m] >= OMC_XS_BATCH_MIN)
         G.batch_xs = true;
+  // many-nuclide materials (tables far larger than L2): the lookup runs as its own kernel
+  // over the work list sorted by (material, energy) -- measured on C5: lookup kernel 2x,
+  // whole step +35 % (profiles/r25_matrix.log); with 1-5 nuclides per material (C2, C3)
+  // the fused, index-ordered sweeps are faster
+  G.sort_xs = G.batch_xs;
+  if (const char* t = std::getenv("OMCGPU_SORT_XS"))
+    G.sort_xs = std::atoi(t) != 0;
+  if (G.sort_xs) { // needs the stand-alone lookup kernel over a merged alive list
+    G.sweep_mode = 1;
+    G.fuse_xs = false;
+  }
   if (const char* t = std::getenv("OMCGPU_LOW_COUNT"))
     G.low_count = std::atoll(t);
   if (const char* t = std::getenv("OMCGPU_BATCH_XS"))
@@ -2433,6 +2527,20 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   }
   rc = rc ? rc : dev_alloc(&G.q_alive.idx, cap);
   G.q_alive.count = G.d_counts + 0;
+  if (G.sort_xs) {
+    rc = rc ? rc : dev_alloc(&G.d_keys, cap);
+    rc = rc ? rc : dev_alloc(&G.d_keys_out, cap);
+    rc = rc ? rc : dev_alloc(&G.d_vals, cap);
+    rc = rc ? rc : dev_alloc(&G.d_vals_out, cap);
+#if OMC_CUDA
+    G.sort_tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, G.sort_tmp_bytes, G.d_keys, G.d_keys_out, G.d_vals, G.d_vals_out,
+      (int)cap, 0, 32);
+    char* stmp = nullptr;
+    rc = rc ? rc : dev_alloc(&stmp, G.sort_tmp_bytes + 16);
+    G.d_sort_tmp = stmp;
+#endif
+  }
   rc = rc ? rc : dev_alloc(&G.d_offs, cap + 1);
   rc = rc ? rc : dev_alloc(&G.d_gather, src_cap);
   rc = rc ? rc : dev_alloc(&G.d_aos, G.fis_cap);
