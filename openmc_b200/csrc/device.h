@@ -1110,6 +1110,88 @@ OMC_HD void ce_macro_xs_batch(int k0, int k1, int j_fine, double E, double& t, d
 // fission, nu-fission, accumulated in nuclide order.  Few nuclides (C2/C3: 1-5 per
 // material): one at a time -- measured faster there than the lockstep walk, which
 // costs registers (profiles/README.md, step r07).
+// Total cross sections of NB nuclides of a material (entries kb .. kb+NB-1, clamped to
+// k1-1) at one energy, walked in lockstep -- the sampling walk of sample_nuclide
+// (src/physics.cpp:494-518) over a many-nuclide material needs up to n of them in a row.
+// sig_t[j] is bit-identical to ce_micro_xs(...).total.
+template<int NB>
+OMC_HD void ce_total_xs_batch(int kb, int k1, int j_fine, double E, double* sig_t)
+{
+  int nuc[NB], n_grid[NB], lo[NB], len[NB], ig[NB];
+  const double* energy[NB];
+  int64_t g0[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j)
+    nuc[j] = ld(DM.mat_nuclide + (kb + j < k1 ? kb + j : k1 - 1));
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    g0[j] = ld(DM.nuc_grid_ofs + nuc[j]);
+    n_grid[j] = (int)(ld(DM.nuc_grid_ofs + nuc[j] + 1) - g0[j]);
+    energy[j] = DM.nuc_energy + g0[j];
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+    const int2 w = __ldg(reinterpret_cast<const int2*>(DM.fine_window) + (int64_t)j_fine * DM.n_nuclides + nuc[j]);
+    lo[j] = w.x;
+    len[j] = w.y - w.x;
+#else
+    const int32_t* w = DM.fine_window + 2 * ((int64_t)j_fine * DM.n_nuclides + nuc[j]);
+    lo[j] = w[0];
+    len[j] = w[1] - w[0];
+#endif
+  }
+  bool any = true;
+  while (any) {
+    any = false;
+    double probe[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      if (len[j] > 0)
+        probe[j] = ld(energy[j] + lo[j] + (len[j] >> 1));
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      if (len[j] > 0) {
+        const int half = len[j] >> 1;
+        if (probe[j] < E) {
+          lo[j] += half + 1;
+          len[j] -= half + 1;
+        } else {
+          len[j] = half;
+        }
+        any = any || len[j] > 0;
+      }
+  }
+  double e0[NB], e1[NB];
+  bool fast[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    fast[j] = lo[j] >= 1 && lo[j] <= n_grid[j] - 1;
+    const int k = fast[j] ? lo[j] : 1;
+    e1[j] = ld(energy[j] + k);
+    e0[j] = ld(energy[j] + k - 1);
+  }
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    if (fast[j] && e1[j] != E) {
+      ig[j] = lo[j] - 1;
+    } else {
+      ig[j] = ce_grid_index_reference(nuc[j], energy[j], n_grid[j], E);
+      e0[j] = ld(energy[j] + ig[j]);
+      e1[j] = ld(energy[j] + ig[j] + 1);
+    }
+  }
+  double a0[NB], b0[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const double* row = DM.nuc_xs + 4 * (g0[j] + ig[j]);
+    a0[j] = ld(row);
+    b0[j] = ld(row + 4);
+  }
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const double fr = (E - e0[j]) / (e1[j] - e0[j]);
+    sig_t[j] = (1.0 - fr) * a0[j] + fr * b0[j];
+  }
+}
+
 // BX: the kernel was compiled for models with many-nuclide materials (its register
 // budget covers the lockstep walk); the host picks the kernel flavour per model.
 template<bool BX>
@@ -1390,6 +1472,7 @@ OMC_HD void collision_mg(Collider& p, int ba, const GenCtx& gc, const Bank& fb)
 // calculate_xs filled at this energy (176 B x n_nuclides per particle); the
 // device recomputes the few entries it needs -- same numbers, no cache.
 // =============================================================================
+template<bool BX = false>
 OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no_nuclide)
 {
   no_nuclide = false;
@@ -1399,14 +1482,33 @@ OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no
   double prob = 0.0;
   int nuc = -1;
   MicroXS micro;
-  const int k1 = ld(DM.mat_nuc_ofs + m + 1);
-  for (int k = ld(DM.mat_nuc_ofs + m); k < k1; ++k) {
-    const int cand = ld(DM.mat_nuclide + k);
-    ce_micro_xs(cand, i_log, p.E, micro);
-    prob += ld(DM.mat_atom_density + k) * micro.total;
-    if (prob >= cutoff) {
-      nuc = cand;
-      break;
+  const int k0 = ld(DM.mat_nuc_ofs + m), k1 = ld(DM.mat_nuc_ofs + m + 1);
+  if (BX && k1 - k0 >= OMC_XS_BATCH_MIN) {
+    // many-nuclide material: the totals come in lockstep batches, the walk itself keeps
+    // the reference's order (same partial sums, same nuclide chosen)
+    for (int kb = k0; kb < k1 && nuc < 0; kb += OMC_XS_BATCH) {
+      double sig_t[OMC_XS_BATCH];
+      ce_total_xs_batch<OMC_XS_BATCH>(kb, k1, i_log, p.E, sig_t);
+#pragma unroll
+      for (int j = 0; j < OMC_XS_BATCH; ++j) {
+        if (nuc >= 0 || kb + j >= k1)
+          continue;
+        prob += ld(DM.mat_atom_density + kb + j) * sig_t[j];
+        if (prob >= cutoff)
+          nuc = ld(DM.mat_nuclide + kb + j);
+      }
+    }
+    if (nuc >= 0)
+      ce_micro_xs(nuc, i_log, p.E, micro);
+  } else {
+    for (int k = k0; k < k1; ++k) {
+      const int cand = ld(DM.mat_nuclide + k);
+      ce_micro_xs(cand, i_log, p.E, micro);
+      prob += ld(DM.mat_atom_density + k) * micro.total;
+      if (prob >= cutoff) {
+        nuc = cand;
+        break;
+      }
     }
   }
   if (nuc < 0) {

@@ -501,6 +501,7 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
 }
 
 // Particle::event_collide, src/particle.cpp:331-415
+template<bool BX = false>
 OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_t i)
 {
   Collider p;
@@ -522,7 +523,7 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
   ps.surface[i] = SURFACE_NONE;
   if (DM.run_CE) {
     bool no_nuclide;
-    collision_ce(p, gc, fb, no_nuclide);
+    collision_ce<BX>(p, gc, fb, no_nuclide);
     if (no_nuclide)
       atomic_add_i32(gc.n_lost, 1);
     if (p.E < DM.energy_cutoff) // src/physics.cpp:67-71
@@ -682,7 +683,7 @@ OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
     return;
   const int32_t i = a.q_in.idx[tid];
   prefetch_particle(a.ps, i, true);
-  if (ev_collide(a.ps, a.gc, a.fb, i)) {
+  if (ev_collide<BX>(a.ps, a.gc, a.fb, i)) {
     ev_xs<BX>(a.ps, i, a.xs_batch_min);
     advance_and_route(tid, a, i);
   } else {
@@ -1009,19 +1010,21 @@ OMC_D void body_surface(int64_t tid, const EvArgs& a)
 }
 OMC_KERNEL(k_surface, EvArgs, body_surface)
 
+template<bool BX>
 OMC_D void body_collide(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = a.q_in.idx[tid];
   prefetch_particle(a.ps, i, true);
-  const bool alive = ev_collide(a.ps, a.gc, a.fb, i);
+  const bool alive = ev_collide<BX>(a.ps, a.gc, a.fb, i);
   if (a.ordered)
     a.ps.next_ev[i] = alive ? 3 : 0;
   else if (alive)
     queue_append(a.q_a, i);
 }
-OMC_KERNEL_MB(k_collide, EvArgs, body_collide, CX_MINBLOCKS)
+OMC_KERNEL_MB(k_collide, EvArgs, body_collide<false>, CX_MINBLOCKS)
+OMC_KERNEL_MB(k_collide_b, EvArgs, body_collide<true>, 2)
 
 // The tail of a generation (few particles left, launch-latency bound): one
 // thread runs the remaining events of one history to completion with the very
@@ -1042,7 +1045,7 @@ OMC_D void body_tail(int64_t tid, const EvArgs& a)
     }
     bool alive;
     if (next == NEXT_COLLISION) {
-      alive = ev_collide(a.ps, a.gc, a.fb, i);
+      alive = ev_collide<true>(a.ps, a.gc, a.fb, i);
       ++n_coll;
     } else if (next == NEXT_SURFACE) {
       alive = ev_surface(a.ps, a.gc, i);
@@ -1389,6 +1392,7 @@ struct Engine {
   cudaEvent_t evx0[RING] = {}, evx1[RING] = {}, evp0 = nullptr, evp1 = nullptr;
   bool fuse_xs = true;          // k_xs + k_advance as one kernel (ms_xs then covers both)
   bool sort_xs = false;         // sweep mode 1, unfused: k_xs runs over the list sorted by (material, energy)
+  bool sort_coll = true;        // ... and so does k_collide (OMCGPU_SORT_COLL=0: index order)
   uint32_t *d_keys = nullptr, *d_keys_out = nullptr;
   int32_t *d_vals = nullptr, *d_vals_out = nullptr;
   void* d_sort_tmp = nullptr;
@@ -1879,6 +1883,31 @@ static int build_lists(int64_t n, int32_t* coll, int32_t* surf, int32_t* counts,
   return 0;
 }
 
+// work list `q` re-ordered by (material, energy) into G.d_vals_out (see body_xs_keys)
+static int sort_by_energy(const Queue& q, int64_t n_ub, cudaStream_t stream)
+{
+  KeyArgs ka;
+  ka.ps = G.ps;
+  ka.q_in = q;
+  ka.keys = G.d_keys;
+  ka.vals = G.d_vals;
+  OMC_LAUNCH(k_xs_keys, n_ub, stream, ka);
+#if OMC_CUDA
+  size_t bytes = G.sort_tmp_bytes;
+  CUDA_OK(cub::DeviceRadixSort::SortPairs(G.d_sort_tmp, bytes, G.d_keys, G.d_keys_out, G.d_vals, G.d_vals_out,
+    (int)n_ub, 0, 32, stream));
+  g_launches += 4;
+#else
+  std::vector<std::pair<uint32_t, int32_t>> kv((size_t)n_ub);
+  for (int64_t k = 0; k < n_ub; ++k)
+    kv[k] = {G.d_keys[k], G.d_vals[k]};
+  std::stable_sort(kv.begin(), kv.end(), [](auto& x, auto& y) { return x.first < y.first; });
+  for (int64_t k = 0; k < n_ub; ++k)
+    G.d_vals_out[k] = kv[k].second;
+#endif
+  return 0;
+}
+
 // ---- sweep mode 1: one merged alive list; xs+advance, then crossing / collision --
 static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, SweepStats& st)
 {
@@ -1937,27 +1966,9 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       CUDA_OK(cudaEventRecord(G.evx1[ev], G.stream));
     } else {
       if (G.sort_xs) {
-        KeyArgs ka;
-        ka.ps = G.ps;
-        ka.q_in = a.q_in;
-        ka.keys = G.d_keys;
-        ka.vals = G.d_vals;
-        OMC_LAUNCH(k_xs_keys, n_alive, G.stream, ka);
-#if OMC_CUDA
-        size_t bytes = G.sort_tmp_bytes;
-        CUDA_OK(cub::DeviceRadixSort::SortPairs(G.d_sort_tmp, bytes, G.d_keys, G.d_keys_out, G.d_vals, G.d_vals_out,
-          (int)n_alive, 0, 32, G.stream));
-        g_launches += 4;
-#else
-        {
-          std::vector<std::pair<uint32_t, int32_t>> kv((size_t)n_alive);
-          for (int64_t k = 0; k < n_alive; ++k)
-            kv[k] = {G.d_keys[k], G.d_vals[k]};
-          std::stable_sort(kv.begin(), kv.end(), [](auto& x, auto& y) { return x.first < y.first; });
-          for (int64_t k = 0; k < n_alive; ++k)
-            G.d_vals_out[k] = kv[k].second;
-        }
-#endif
+        rc = sort_by_energy(a.q_in, n_alive, G.stream);
+        if (rc)
+          return rc;
         EvArgs ax = a; // the same histories, in (material, energy) order
         ax.q_in.idx = G.d_vals_out;
         LAUNCH_XS(k_xs, n_alive, G.stream, ax);
@@ -2001,7 +2012,18 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       CUDA_OK(cudaEventRecord(G.e_surf, st_surf));
       CUDA_OK(cudaStreamWaitEvent(st_coll, G.e_adv, 0));
     }
-    OMC_LAUNCH(k_collide, n_alive, st_coll, a);
+    if (G.sort_xs && G.sort_coll) {
+      // the nuclide-sampling walk of a many-nuclide material is a run of lookups: same
+      // ordering, same coalescing (the sort buffers are free again: the lookup is done)
+      rc = sort_by_energy(a.q_in, n_alive, st_coll);
+      if (rc)
+        return rc;
+      EvArgs ac = a;
+      ac.q_in.idx = G.d_vals_out;
+      LAUNCH_XS(k_collide, n_alive, st_coll, ac);
+    } else {
+      LAUNCH_XS(k_collide, n_alive, st_coll, a);
+    }
     if (G.overlap) {
       CUDA_OK(cudaEventRecord(G.e_coll, st_coll));
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_surf, 0));
@@ -2417,6 +2439,8 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   G.sort_xs = G.batch_xs;
   if (const char* t = std::getenv("OMCGPU_SORT_XS"))
     G.sort_xs = std::atoi(t) != 0;
+  if (const char* t = std::getenv("OMCGPU_SORT_COLL"))
+    G.sort_coll = std::atoi(t) != 0;
   if (G.sort_xs) { // needs the stand-alone lookup kernel over a merged alive list
     G.sweep_mode = 1;
     G.fuse_xs = false;
