@@ -1392,7 +1392,7 @@ struct Engine {
   cudaEvent_t evx0[RING] = {}, evx1[RING] = {}, evp0 = nullptr, evp1 = nullptr;
   bool fuse_xs = true;          // k_xs + k_advance as one kernel (ms_xs then covers both)
   bool sort_xs = false;         // sweep mode 1, unfused: k_xs runs over the list sorted by (material, energy)
-  bool sort_coll = true;        // ... and so does k_collide (OMCGPU_SORT_COLL=0: index order)
+  bool sort_coll = false;       // OMCGPU_SORT_COLL=1: k_collide in that order too (measured on C5: 211 vs 202 ms, off)
   uint32_t *d_keys = nullptr, *d_keys_out = nullptr;
   int32_t *d_vals = nullptr, *d_vals_out = nullptr;
   void* d_sort_tmp = nullptr;
