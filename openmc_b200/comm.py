@@ -54,6 +54,28 @@ class TorchComm:
         self.on_gpu = on_gpu
         self.dev = "cuda" if on_gpu else "cpu"
         self.exchange_bytes = 0
+        self._connect_all()
+
+    def _connect_all(self):
+        """One tiny send/recv with every peer: NCCL sets a point-to-point connection up on first
+        use (tens to hundreds of ms per pair), and which neighbours a rank trades sites with
+        changes from generation to generation -- without this a timed generation can pay for a
+        connection (first 8-GPU run: 190 ms per generation outside the device loop)."""
+        if self.size == 1:
+            return
+        ops, keep = [], []
+        for peer in range(self.size):
+            if peer == self.rank:
+                continue
+            s = torch.zeros(1, dtype=torch.float64, device=self.dev)
+            r = torch.zeros(1, dtype=torch.float64, device=self.dev)
+            keep += [s, r]
+            ops.append(dist.P2POp(dist.isend, s, peer))
+            ops.append(dist.P2POp(dist.irecv, r, peer))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        if self.on_gpu:
+            torch.cuda.synchronize()
 
     def allreduce_sum(self, a: np.ndarray) -> np.ndarray:
         t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.dev)
@@ -81,41 +103,45 @@ class TorchComm:
         pos = np.concatenate([[0], np.cumsum(sampled)])        # bank_position
         wi = sim.work_index
         cols = self._bank(eng, 0, n_s)
-        # pack my sampled sites as rows of 12 x 8 bytes (ints widened / bit-cast)
-        mine = torch.stack([c[:n_s].to(torch.float64) if c.dtype == torch.float64 else
-                            c[:n_s].to(torch.int64).view(torch.float64) for c in cols], dim=1) \
-            if n_s > 0 else torch.zeros((0, 12), dtype=torch.float64, device=self.dev)
         my_lo, my_hi = int(pos[self.rank]), int(pos[self.rank + 1])
         need_lo, need_hi = wi[self.rank], wi[self.rank + 1]
-        new = torch.empty((need_hi - need_lo, 12), dtype=torch.float64, device=self.dev)
+        n_new = need_hi - need_lo
+
+        def pack(lo, hi):
+            # rows [lo, hi) (global site numbers) of my sampled sites as 12 x 8 bytes (ints
+            # widened / bit-cast): only the rows that change owner are packed
+            return torch.stack([c[lo - my_lo:hi - my_lo] if c.dtype == torch.float64 else
+                                c[lo - my_lo:hi - my_lo].to(torch.int64).view(torch.float64)
+                                for c in cols], dim=1).contiguous()
+
         ops, recvs = [], []
         for peer in range(self.size):
-            # what I hold that `peer` owns
-            lo, hi = max(my_lo, wi[peer]), min(my_hi, wi[peer + 1])
+            if peer == self.rank:
+                continue
+            lo, hi = max(my_lo, wi[peer]), min(my_hi, wi[peer + 1])          # what I hold that `peer` owns
             if hi > lo:
-                chunk = mine[lo - my_lo:hi - my_lo]
-                if peer == self.rank:
-                    new[lo - need_lo:hi - need_lo] = chunk
-                else:
-                    ops.append(dist.P2POp(dist.isend, chunk.contiguous(), peer))
-                    self.exchange_bytes += chunk.numel() * 8
-            # what `peer` holds that I own
-            lo, hi = max(int(pos[peer]), need_lo), min(int(pos[peer + 1]), need_hi)
-            if hi > lo and peer != self.rank:
+                chunk = pack(lo, hi)
+                ops.append(dist.P2POp(dist.isend, chunk, peer))
+                self.exchange_bytes += chunk.numel() * 8
+            lo, hi = max(int(pos[peer]), need_lo), min(int(pos[peer + 1]), need_hi)   # what `peer` holds that I own
+            if hi > lo:
                 buf = torch.empty((hi - lo, 12), dtype=torch.float64, device=self.dev)
                 recvs.append((lo - need_lo, hi - need_lo, buf))
                 ops.append(dist.P2POp(dist.irecv, buf, peer))
+        # the sites that stay: one contiguous shift per column (send chunks were packed above)
+        keep_lo, keep_hi = max(my_lo, need_lo), min(my_hi, need_hi)
+        if keep_hi > keep_lo and keep_lo - my_lo != keep_lo - need_lo:
+            for c in cols:
+                c[keep_lo - need_lo:keep_hi - need_lo] = c[keep_lo - my_lo:keep_hi - my_lo].clone()
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
         for a, b, buf in recvs:
-            new[a:b] = buf
-        n_new = need_hi - need_lo
-        for k, c in enumerate(cols):
-            if c.dtype == torch.float64:
-                c[:n_new] = new[:, k]
-            else:
-                c[:n_new] = new[:, k].contiguous().view(torch.int64).to(c.dtype)
+            for k, c in enumerate(cols):
+                if c.dtype == torch.float64:
+                    c[a:b] = buf[:, k]
+                else:
+                    c[a:b] = buf[:, k].contiguous().view(torch.int64).to(c.dtype)
         if self.on_gpu:
             torch.cuda.synchronize()
         eng.set_source_count(n_new)
