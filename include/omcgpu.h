@@ -414,6 +414,13 @@ int omcgpu_get_fission_bank(omcgpu_site* fission_bank, int64_t capacity, int64_t
 int omcgpu_comb_fission_bank(int64_t start, int64_t total, int64_t n_particles,
   int64_t seed_id, int64_t master_seed, uint64_t stride, int64_t* n_sampled);
 
+/* The host half of that comb on its own (no device needed): the indices, relative to
+ * `start`, of the sites among this rank's n_local sorted fission sites that the comb
+ * selects -- bit-identical to the reference's recurrence tooth += teeth_distance. */
+int omcgpu_comb_indices(int64_t start, int64_t n_local, int64_t total, int64_t n_particles,
+  int64_t seed_id, int64_t master_seed, uint64_t stride, int32_t* idx, int64_t capacity,
+  int64_t* n_sampled);
+
 /* Device pointers of the SoA bank columns for the multi-GPU exchange
  * (src/eigenvalue.cpp:186-348): which = 0 source bank, 1 fission bank.
  * cols[0..8] = x y z u v w E time wgt (double*), cols[9] = delayed_group

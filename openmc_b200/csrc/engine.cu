@@ -2813,29 +2813,81 @@ int omcgpu_next_generation(const omcgpu_gen_in* in, omcgpu_site* source_bank, in
   return fetch_bank(G.src, source_bank, n_sampled);
 }
 
+// The comb's tooth positions are a floating-point recurrence in the reference,
+// tooth += teeth_distance (src/eigenvalue.cpp:166-177), and floor(tooth) picks the site, so
+// the very same roundings must be reproduced -- but not one dependent add per tooth (10 ms
+// per generation at 4e6 sites).  While tooth stays inside one binade [2^k, 2^(k+1)) every
+// tooth is a multiple of u = 2^(k-52) and fl(tooth + d) = tooth + D u exactly, D = d / u
+// rounded to nearest (no tie, exact sum below 2^(k+1)): the teeth of a binade are an integer
+// progression, filled by a loop without a dependency chain; one real addition crosses into
+// the next binade.  Anything irregular (tie, d >= tooth, zero) takes the plain recurrence.
+static void comb_teeth(double tooth, double d, int64_t count, int64_t start, int32_t* idx)
+{
+  const int64_t LIMIT = (int64_t)1 << 53;
+  int64_t i = 0;
+  while (i < count) {
+    int e = 0;
+    if (tooth > 0.0)
+      std::frexp(tooth, &e);
+    const int k = e - 1, sh = 52 - k; // tooth in [2^k, 2^(k+1)), floor = mantissa integer >> sh
+    bool block = tooth > 0.0 && d > 0.0 && sh >= 1 && sh <= 62 && d < std::ldexp(1.0, k);
+    int64_t D = 0, T = 0;
+    if (block) {
+      const double q = std::ldexp(d, sh); // d / u, exact
+      const double qr = std::nearbyint(q);
+      block = std::fabs(q - std::floor(q) - 0.5) != 0.0 && qr >= 1.0 && qr < 4503599627370496.0;
+      D = (int64_t)qr;
+      T = (int64_t)std::ldexp(tooth, sh);
+    }
+    if (!block) {
+      idx[i++] = (int32_t)((int64_t)std::floor(tooth) - start);
+      tooth += d;
+      continue;
+    }
+    // teeth j = 0..m of this block: T + j D; the exact sum of the next add stays below 2^(k+1)
+    int64_t m = (LIMIT - 1 - T) / D;
+    if (m > count - i - 1)
+      m = count - i - 1;
+    int32_t* out = idx + i;
+    for (int64_t j = 0; j <= m; ++j)
+      out[j] = (int32_t)(((T + j * D) >> sh) - start);
+    i += m + 1;
+    tooth = std::ldexp((double)(T + m * D), -sh); // the last tooth filled, then one real addition
+    tooth += d;
+  }
+}
+
+// Host half of the comb (needs no device): which of this rank's n_local sorted sites the
+// uniform comb selects, as indices relative to `start`.
+int omcgpu_comb_indices(int64_t start, int64_t n_local, int64_t total, int64_t n_particles, int64_t seed_id,
+  int64_t master_seed, uint64_t stride, int32_t* idx, int64_t capacity, int64_t* n_sampled)
+{
+  uint64_t seed = future_seed((uint64_t)seed_id * stride, (uint64_t)master_seed); // init_seed(id, STREAM_TRACKING)
+  const double teeth_distance = static_cast<double>(total) / n_particles;
+  const double teeth_offset = prn(seed) * teeth_distance;
+  const int64_t end = start + n_local;
+  const int64_t tooth_start = (int64_t)std::ceil((start - teeth_offset) / teeth_distance);
+  const int64_t tooth_end = (int64_t)std::floor((end - teeth_offset) / teeth_distance) + 1;
+  const int64_t count = tooth_end - tooth_start > 0 ? tooth_end - tooth_start : 0;
+  if (n_sampled)
+    *n_sampled = count;
+  if (count > capacity)
+    return fail(OMCGPU_E_OUT_OF_BOUNDS, "comb selects more sites than the caller's buffer holds%s");
+  comb_teeth(tooth_start * teeth_distance + teeth_offset, teeth_distance, count, start, idx);
+  return 0;
+}
+
 int omcgpu_comb_fission_bank(int64_t start, int64_t total, int64_t n_particles, int64_t seed_id,
   int64_t master_seed, uint64_t stride, int64_t* n_sampled)
 {
   if (!G.ready)
     return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
-  // The tooth positions are accumulated by repeated floating-point addition in
-  // the reference (src/eigenvalue.cpp:166-177); to select the very same sites the
-  // host does that short sequential recurrence and the device does the gather.
-  uint64_t seed = future_seed((uint64_t)seed_id * stride, (uint64_t)master_seed); // init_seed(id, STREAM_TRACKING)
-  const double teeth_distance = static_cast<double>(total) / n_particles;
-  const double teeth_offset = prn(seed) * teeth_distance;
-  const int64_t end = start + G.n_fis;
-  const int64_t tooth_start = (int64_t)std::ceil((start - teeth_offset) / teeth_distance);
-  const int64_t tooth_end = (int64_t)std::floor((end - teeth_offset) / teeth_distance) + 1;
-  const int64_t count = tooth_end - tooth_start;
-  if (count > G.src.cap)
-    return fail(OMCGPU_E_OUT_OF_BOUNDS, "comb selects more sites than the source bank holds (1.25 max_particles + 1024)%s");
+  // the host finds the teeth (comb_teeth: the reference's recurrence, binade by binade),
+  // the device does the gather
   int32_t* idx = reinterpret_cast<int32_t*>(G.h_aos);
-  double tooth = tooth_start * teeth_distance + teeth_offset;
-  for (int64_t i = 0; i < count; i++) {
-    idx[i] = (int32_t)((int64_t)std::floor(tooth) - start);
-    tooth += teeth_distance;
-  }
+  int64_t count = 0;
+  if (omcgpu_comb_indices(start, G.n_fis, total, n_particles, seed_id, master_seed, stride, idx, G.src.cap, &count))
+    return fail(OMCGPU_E_OUT_OF_BOUNDS, "comb selects more sites than the source bank holds (1.25 max_particles + 1024)%s");
   if (count > 0) {
     CUDA_OK(cudaMemcpyAsync(G.d_gather, idx, count * sizeof(int32_t), cudaMemcpyHostToDevice, G.stream));
     BankArgs b;

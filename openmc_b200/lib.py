@@ -136,6 +136,17 @@ class Engine:
             C.c_int64(master_seed), C.c_uint64(stride), C.byref(n)))
         return n.value
 
+    def comb_indices(self, start, n_local, total, n_particles, seed_id, master_seed=DEFAULT_SEED,
+                     stride=DEFAULT_STRIDE) -> np.ndarray:
+        """host half of the comb (omcgpu_comb_indices): selected sites relative to `start`"""
+        idx = np.zeros(int(n_particles) + int(n_local) + 16, np.int32)
+        n = C.c_int64(0)
+        self._check(self.lib.omcgpu_comb_indices(
+            C.c_int64(start), C.c_int64(n_local), C.c_int64(total), C.c_int64(n_particles),
+            C.c_int64(seed_id), C.c_int64(master_seed), C.c_uint64(stride), _p(idx, C.c_int32),
+            C.c_int64(idx.size), C.byref(n)))
+        return idx[:n.value].astype(np.int64)
+
     def bank_columns_device(self, which: int):
         cols = (C.c_void_p * 12)()
         n = C.c_int64(0)

@@ -85,6 +85,27 @@ def test_next_generation_equals_transport_plus_host_comb(emu_lib):
     eng.finalize()
 
 
+def test_comb_teeth_equal_the_recurrence(emu_lib):
+    """omcgpu_comb_indices fills the teeth binade by binade (integer progressions); the
+    selected sites must equal the reference's recurrence tooth += teeth_distance exactly --
+    also when teeth_distance has few mantissa bits (ties), is < 1 or > 2, on rank slices"""
+    eng = lib.Engine(emu_lib)
+    g = np.random.default_rng(3)
+    cases_ = [(1234, 1000), (999, 1000), (3000, 1000), (1000, 1000), (1250, 1000), (1500, 1000),
+              (2_000_000, 1 << 20), ((1 << 21) + 1, 1 << 20), (1_048_577, 1 << 20), (5, 4000), (4_123_457, 4_000_000)]
+    cases_ += [(int(t), int(n)) for t, n in zip(g.integers(1, 3_000_000, 12), g.integers(1, 1_500_000, 12))]
+    for total, n in cases_:
+        for seed_id in (1, 7, 123):
+            a = lib.comb_indices(0, total, total, n, seed_id)
+            b = eng.comb_indices(0, total, total, n, seed_id)
+            assert np.array_equal(a, b), (total, n, seed_id)
+        lo = total // 3                       # a rank that holds sites [lo, lo + n_local)
+        n_local = total // 2
+        a = lib.comb_indices(lo, n_local, total, n, 5)
+        b = eng.comb_indices(lo, n_local, total, n, 5)
+        assert np.array_equal(a, b), (total, n, "slice")
+
+
 def test_comb_matches_oracle(emu_lib):
     model, box, of = cases.build("mg_legendre")
     o = Oracle(model)
