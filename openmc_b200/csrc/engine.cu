@@ -2849,8 +2849,11 @@ static void comb_teeth(double tooth, double d, int64_t count, int64_t start, int
     if (m > count - i - 1)
       m = count - i - 1;
     int32_t* out = idx + i;
-    for (int64_t j = 0; j <= m; ++j)
-      out[j] = (int32_t)(((T + j * D) >> sh) - start);
+    int64_t Tj = T; // (integer add: a one-cycle chain instead of the 4-cycle floating-point one)
+    for (int64_t j = 0; j <= m; ++j) {
+      out[j] = (int32_t)((Tj >> sh) - start);
+      Tj += D;
+    }
     i += m + 1;
     tooth = std::ldexp((double)(T + m * D), -sh); // the last tooth filled, then one real addition
     tooth += d;
