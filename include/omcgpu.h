@@ -62,6 +62,9 @@ extern "C" {
 #define OMCGPU_SURF_YCYLINDER 5   /* coef: x0 z0 r             */
 #define OMCGPU_SURF_ZCYLINDER 6   /* coef: x0 y0 r             */
 #define OMCGPU_SURF_SPHERE    7   /* coef: x0 y0 z0 r          */
+#define OMCGPU_SURF_XCONE     8   /* coef: x0 y0 z0 r^2  (src/surface.cpp:688-742) */
+#define OMCGPU_SURF_YCONE     9
+#define OMCGPU_SURF_ZCONE     10
 #define OMCGPU_SURF_NCOEF     4   /* doubles stored per surface */
 
 /* boundary conditions: src/boundary_condition.cpp:18-62 */

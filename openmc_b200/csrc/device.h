@@ -158,9 +158,21 @@ OMC_HD double surf_evaluate(int s, V3 r)
     const double a = r.x - c0, b = r.y - c1;
     return a * a + b * b - c2 * c2;
   }
-  default: { // sphere
+  case OMCGPU_SURF_SPHERE: {
     const double x = r.x - c0, y = r.y - c1, z = r.z - c2;
     return x * x + y * y + z * z - c3 * c3;
+  }
+  case OMCGPU_SURF_XCONE: { // axis_aligned_cone_evaluate, src/surface.cpp:688-696
+    const double r1 = r.x - c0, r2 = r.y - c1, r3 = r.z - c2;
+    return r2 * r2 + r3 * r3 - c3 * r1 * r1;
+  }
+  case OMCGPU_SURF_YCONE: {
+    const double r1 = r.y - c1, r2 = r.x - c0, r3 = r.z - c2;
+    return r2 * r2 + r3 * r3 - c3 * r1 * r1;
+  }
+  default: { // z-cone
+    const double r1 = r.z - c2, r2 = r.x - c0, r3 = r.y - c1;
+    return r2 * r2 + r3 * r3 - c3 * r1 * r1;
   }
   }
 }
@@ -183,8 +195,14 @@ OMC_HD V3 surf_normal(int s, V3 r)
     return v3(2.0 * (r.x - ld(c)), 0.0, 2.0 * (r.z - ld(c + 1)));
   case OMCGPU_SURF_ZCYLINDER:
     return v3(2.0 * (r.x - ld(c)), 2.0 * (r.y - ld(c + 1)), 0.0);
-  default:
+  case OMCGPU_SURF_SPHERE:
     return v3(2.0 * (r.x - ld(c)), 2.0 * (r.y - ld(c + 1)), 2.0 * (r.z - ld(c + 2)));
+  case OMCGPU_SURF_XCONE: // axis_aligned_cone_normal, src/surface.cpp:747-756
+    return v3(-2.0 * ld(c + 3) * (r.x - ld(c)), 2.0 * (r.y - ld(c + 1)), 2.0 * (r.z - ld(c + 2)));
+  case OMCGPU_SURF_YCONE:
+    return v3(2.0 * (r.x - ld(c)), -2.0 * ld(c + 3) * (r.y - ld(c + 1)), 2.0 * (r.z - ld(c + 2)));
+  default:
+    return v3(2.0 * (r.x - ld(c)), 2.0 * (r.y - ld(c + 1)), -2.0 * ld(c + 3) * (r.z - ld(c + 2)));
   }
 }
 
@@ -234,6 +252,38 @@ OMC_HD double cylinder_distance(double u_axis, double q2, double q3, double u2, 
   return quadric_distance<true>(a, k, c, coincident);
 }
 
+// axis_aligned_cone_distance, src/surface.cpp:701-742 (index 1 = the cone's axis)
+OMC_HD double cone_distance(double r1, double r2, double r3, double u1, double u2, double u3, double radius_sq,
+  bool coincident)
+{
+  const double a = u2 * u2 + u3 * u3 - radius_sq * u1 * u1;
+  const double k = r2 * u2 + r3 * u3 - radius_sq * r1 * u1;
+  const double c = r2 * r2 + r3 * r3 - radius_sq * r1 * r1;
+  double quad = k * k - a * c;
+  double d;
+  if (quad < 0.0) {
+    return INFTY;
+  } else if (coincident || fabs(c) < FP_COINCIDENT) {
+    if (k >= 0.0)
+      d = (-k - sqrt(quad)) / a;
+    else
+      d = (-k + sqrt(quad)) / a;
+  } else {
+    quad = sqrt(quad);
+    d = (-k - quad) / a;
+    const double b = (-k + quad) / a;
+    if (d < 0.0) {
+      if (b > 0.0)
+        d = b;
+    } else if (b > 0.0 && b < d) {
+      d = b;
+    }
+  }
+  if (d <= 0.0)
+    return INFTY;
+  return d;
+}
+
 OMC_HD double surf_distance(int s, V3 r, V3 u, bool coincident)
 {
   const double* c = DM.surf_coef + OMCGPU_SURF_NCOEF * s;
@@ -259,12 +309,18 @@ OMC_HD double surf_distance(int s, V3 r, V3 u, bool coincident)
     return cylinder_distance(u.y, r.x - c0, r.z - c1, u.x, u.z, c2, coincident);
   case OMCGPU_SURF_ZCYLINDER:
     return cylinder_distance(u.z, r.x - c0, r.y - c1, u.x, u.y, c2, coincident);
-  default: {
+  case OMCGPU_SURF_SPHERE: {
     const double x = r.x - c0, y = r.y - c1, z = r.z - c2;
     const double k = x * u.x + y * u.y + z * u.z;
     const double cc = x * x + y * y + z * z - c3 * c3;
     return quadric_distance<false>(1.0, k, cc, coincident);
   }
+  case OMCGPU_SURF_XCONE:
+    return cone_distance(r.x - c0, r.y - c1, r.z - c2, u.x, u.y, u.z, c3, coincident);
+  case OMCGPU_SURF_YCONE:
+    return cone_distance(r.y - c1, r.x - c0, r.z - c2, u.y, u.x, u.z, c3, coincident);
+  default:
+    return cone_distance(r.z - c2, r.x - c0, r.y - c1, u.z, u.x, u.y, c3, coincident);
   }
 }
 

@@ -1759,7 +1759,7 @@ static int check_supported(const omcgpu_model* m)
   if (m->n_coord_levels > OMCGPU_MAX_COORD)
     return fail(OMCGPU_E_UNSUPPORTED, "geometry nests deeper than OMCGPU_MAX_COORD%s");
   for (int s = 0; s < m->n_surfaces; ++s) {
-    if (m->surf_type[s] < 0 || m->surf_type[s] > OMCGPU_SURF_SPHERE)
+    if (m->surf_type[s] < 0 || m->surf_type[s] > OMCGPU_SURF_ZCONE)
       return fail(OMCGPU_E_UNSUPPORTED, "surface type not supported on the device%s");
     if (m->surf_bc[s] < 0 || m->surf_bc[s] > OMCGPU_BC_REFLECTIVE)
       return fail(OMCGPU_E_UNSUPPORTED, "boundary condition not supported on the device%s");

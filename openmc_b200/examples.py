@@ -199,6 +199,34 @@ def mg_temperature_multi():
     return m, c5g7_library(True), box, True
 
 
+def surface_zoo():
+    """Every surface kind the device path supports in one MG model (sphere, x / y / z cones,
+    x / y cylinders, a general plane, axis planes) with union / complement regions -- not one
+    of BASELINE.json's configurations, a geometry test case: the reference's own surface code
+    is asked about the same points (tests/test_reference_geometry.py)."""
+    m = Model()
+    uo2 = m.material(name="UO2 fuel", macroscopic="UO2", units="macro", density=1.0)
+    water = m.material(name="Water", macroscopic="LWTR", units="macro", density=1.0)
+    m.surface("sphere", [0.0, 0.0, 0.0, 10.0], "vacuum")            # 1
+    m.surface("x-cylinder", [0.0, 0.0, 2.0])                         # 2
+    m.surface("y-cylinder", [1.0, -1.0, 1.5])                        # 3
+    m.surface("plane", [1.0, 1.0, 0.5, 1.0])                         # 4
+    m.surface("z-cone", [0.0, 0.0, -3.0, 0.25])                      # 5
+    m.surface("x-cone", [2.0, 1.0, 0.0, 0.5])                        # 6
+    m.surface("y-cone", [0.0, -2.0, 1.0, 1.0])                       # 7
+    m.surface("z-plane", [4.0])                                      # 8
+    m.surface("sphere", [3.0, 3.0, 3.0, 2.0])                        # 9
+    m.cell(region="-9", fill=uo2)
+    m.cell(region="-1 9 -2", fill=water)
+    m.cell(region="-1 9 2 -3", fill=uo2)
+    m.cell(region="-1 9 2 3 -5 -8", fill=water)
+    m.cell(region="-1 9 2 3 (5 | 8) (-6 | -7)", fill=uo2)
+    m.cell(region="-1 9 2 3 (5 | 8) 6 7 4", fill=water)
+    m.cell(region="-1 9 2 3 (5 | 8) 6 7 ~(4)", fill=uo2)
+    box = [-8.0, -8.0, -8.0, 8.0, 8.0, 8.0]
+    return m, c5g7_library(False), box, False
+
+
 def pincell_multigroup(mesh_dim=100, energy_bins=500):
     """Config C1: examples/pincell_multigroup/build_xml.py:14-149 (7-group C5G7
     UO2/LWTR pin, reflective box, 100x100 mesh {flux, fission, nu-fission} and a

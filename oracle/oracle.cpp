@@ -296,6 +296,19 @@ double surf_evaluate(int s, Vec3 r)
     const double x = r.x - c[0], y = r.y - c[1], z = r.z - c[2];
     return x * x + y * y + z * z - c[3] * c[3];
   }
+  // axis_aligned_cone_evaluate, src/surface.cpp:688-696 (r1 along the cone's axis)
+  case OMCGPU_SURF_XCONE: {
+    const double r1 = r.x - c[0], r2 = r.y - c[1], r3 = r.z - c[2];
+    return r2 * r2 + r3 * r3 - c[3] * r1 * r1;
+  }
+  case OMCGPU_SURF_YCONE: {
+    const double r1 = r.y - c[1], r2 = r.x - c[0], r3 = r.z - c[2];
+    return r2 * r2 + r3 * r3 - c[3] * r1 * r1;
+  }
+  case OMCGPU_SURF_ZCONE: {
+    const double r1 = r.z - c[2], r2 = r.x - c[0], r3 = r.y - c[1];
+    return r2 * r2 + r3 * r3 - c[3] * r1 * r1;
+  }
   }
   return 0.0;
 }
@@ -320,6 +333,13 @@ Vec3 surf_normal(int s, Vec3 r)
     return {2.0 * (r.x - c[0]), 2.0 * (r.y - c[1]), 0.0};
   case OMCGPU_SURF_SPHERE:
     return {2.0 * (r.x - c[0]), 2.0 * (r.y - c[1]), 2.0 * (r.z - c[2])};
+  // axis_aligned_cone_normal, src/surface.cpp:747-756
+  case OMCGPU_SURF_XCONE:
+    return {-2.0 * c[3] * (r.x - c[0]), 2.0 * (r.y - c[1]), 2.0 * (r.z - c[2])};
+  case OMCGPU_SURF_YCONE:
+    return {2.0 * (r.x - c[0]), -2.0 * c[3] * (r.y - c[1]), 2.0 * (r.z - c[2])};
+  case OMCGPU_SURF_ZCONE:
+    return {2.0 * (r.x - c[0]), 2.0 * (r.y - c[1]), -2.0 * c[3] * (r.z - c[2])};
   }
   return {0, 0, 0};
 }
@@ -371,6 +391,42 @@ double cylinder_axis_distance(double u1, double r2, double r3, double u2, double
   }
 }
 
+// axis_aligned_cone_distance, src/surface.cpp:701-742 (index 1 = the cone's axis)
+double cone_axis_distance(double r1, double r2, double r3, double u1, double u2, double u3, double radius_sq,
+  bool coincident)
+{
+  const double a = u2 * u2 + u3 * u3 - radius_sq * u1 * u1;
+  const double k = r2 * u2 + r3 * u3 - radius_sq * r1 * u1;
+  const double c = r2 * r2 + r3 * r3 - radius_sq * r1 * r1;
+  double quad = k * k - a * c;
+  double d;
+  if (quad < 0.0) {
+    return INFTY;
+  } else if (coincident || std::abs(c) < FP_COINCIDENT) {
+    if (k >= 0.0) {
+      d = (-k - std::sqrt(quad)) / a;
+    } else {
+      d = (-k + std::sqrt(quad)) / a;
+    }
+  } else {
+    quad = std::sqrt(quad);
+    d = (-k - quad) / a;
+    const double b = (-k + quad) / a;
+    if (d < 0.0) {
+      if (b > 0.0)
+        d = b;
+    } else {
+      if (b > 0.0) {
+        if (b < d)
+          d = b;
+      }
+    }
+  }
+  if (d <= 0.0)
+    return INFTY;
+  return d;
+}
+
 double surf_distance(int s, Vec3 r, Vec3 u, bool coincident)
 {
   const double* c = M->surf_coef + OMCGPU_SURF_NCOEF * s;
@@ -417,6 +473,12 @@ double surf_distance(int s, Vec3 r, Vec3 u, bool coincident)
       return d;
     }
   }
+  case OMCGPU_SURF_XCONE:
+    return cone_axis_distance(r.x - c[0], r.y - c[1], r.z - c[2], u.x, u.y, u.z, c[3], coincident);
+  case OMCGPU_SURF_YCONE:
+    return cone_axis_distance(r.y - c[1], r.x - c[0], r.z - c[2], u.y, u.x, u.z, c[3], coincident);
+  case OMCGPU_SURF_ZCONE:
+    return cone_axis_distance(r.z - c[2], r.x - c[0], r.y - c[1], u.z, u.x, u.y, c[3], coincident);
   }
   return INFTY;
 }

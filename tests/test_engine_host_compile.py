@@ -113,3 +113,28 @@ def test_comb_matches_oracle(emu_lib):
         a = o.comb_indices(0, total, total, n, seed_id=7)
         b = lib.comb_indices(0, total, total, n, seed_id=7)
         assert np.array_equal(a, b) and a.size == n
+
+
+@pytest.mark.parametrize("threshold", ["0", "100000"])
+def test_surface_zoo_generation_matches_oracle(emu_lib, threshold, monkeypatch):
+    """one generation through spheres, cones, x / y cylinders, a general plane, union and
+    complement regions and a vacuum sphere: same events, same sorted fission bank"""
+    import reference_cases as rc
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)
+    m, model, box = rc.build("surface_zoo")
+    o = Oracle(model)
+    n = 1500
+    src = o.sample_initial_source(n, box, False)
+    eng = lib.Engine(emu_lib)
+    eng.init(model, 0, 2048)
+    gi = eng.gen_in(n, 0, 0, 1.0, False)
+    fb, out = eng.transport_generation(gi, src)
+    fb_o, out_o = o.transport_generation(gi, src)
+    assert out.n_lost == 0 and out_o.n_lost == 0
+    assert out.n_fission == out_o.n_fission and out.n_events == out_o.n_events
+    assert out.n_crossings == out_o.n_crossings and out.n_collisions == out_o.n_collisions
+    assert out.global_tally[3] > 0                       # leakage through the vacuum sphere
+    for f in ("r", "u", "E", "wgt", "parent_id", "progeny_id"):
+        assert np.array_equal(fb[f], fb_o[f]), f
+    np.testing.assert_allclose(out.global_tally[:], out_o.global_tally[:], rtol=1e-13)
+    eng.finalize()

@@ -261,3 +261,23 @@ def test_assembly_eigenvalue_statistics(gpu_engine):
     assert np.all(np.abs(z[ok]) < 5.0), np.abs(z[ok]).max()
     assert np.mean(z[ok] ** 2) < 2.5
     sim.simulation_finalize()
+
+
+def test_surface_zoo_generation_matches_oracle(gpu_engine, monkeypatch):
+    """spheres, cones, x / y cylinders, a general plane, union / complement regions, vacuum
+    sphere: one generation against the oracle"""
+    import reference_cases as rc
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", "2048")
+    m, model, box = rc.build("surface_zoo")
+    o = Oracle(model)
+    n = 20000
+    src = o.sample_initial_source(n, box, False)
+    gpu_engine.init(model, 0, n)
+    gi = gpu_engine.gen_in(n, 0, 0, 1.0, False)
+    fb, out = gpu_engine.transport_generation(gi, src)
+    fb_o, out_o = o.transport_generation(gi, src)
+    assert out.n_lost == 0
+    assert abs(out.n_fission - out_o.n_fission) <= 5
+    assert abs(out.n_events - out_o.n_events) <= 2e-4 * out_o.n_events
+    np.testing.assert_allclose(out.global_tally[:], out_o.global_tally[:], rtol=2e-4)
+    gpu_engine.finalize()

@@ -58,6 +58,22 @@ def test_committed_reference_vectors_are_reproduced_by_the_oracle(name):
     assert np.array_equal(d2, d)
 
 
+@pytest.mark.parametrize("name", rc.NAMES)
+def test_engine_sources_equal_reference_vectors(emu_lib, name):
+    """the DEVICE functions (openmc_b200/csrc/device.h, host-compiled for the tests) against
+    the reference vectors -- same libm on the host: distances identical too"""
+    from openmc_b200 import lib
+    m, model, box = rc.build(name)
+    v = np.load(os.path.join(GOLDEN, f"refgeom_{name}.npz"))
+    eng = lib.Engine(emu_lib)
+    eng.init(model, 0, 65536)
+    found = (v["cell_id"], v["instance"], v["material"], v["n_coord"])
+    dist = (v["distance"], v["surface"], v["level"], v["lattice_trans"])
+    d2, d = _compare(model, found, None, dist, v["xyz"], v["uvw"], eng)
+    assert np.array_equal(d2, d)
+    eng.finalize()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", rc.NAMES)
 def test_gpu_geometry_equals_reference_vectors(gpu_engine, name):
