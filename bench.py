@@ -219,17 +219,14 @@ def main():
     # ---- end to end through host buffers ("e2e"): the reference-facing call
     e2e = None
     if not args.no_e2e:
-        # The reference-facing call on HOST buffers: libopenmc's simulation::source_bank
+        # The reference-facing calls on HOST buffers: libopenmc's simulation::source_bank
         # (page-locked once, as allocate_banks would) goes H2D, the generation runs, and
-        # the next source bank comes back D2H.  N = 1: omcgpu_next_generation (device sort
-        # + comb = transport_event_based + synchronize_bank).  N > 1: per-rank
-        # omcgpu_transport_generation returning the sorted fission bank to the host.
+        # the NEXT source bank comes back D2H.  N = 1: omcgpu_next_generation (device sort
+        # + comb = transport_event_based + synchronize_bank).  N > 1: omcgpu_set_source_bank,
+        # omcgpu_run_generation, the inter-rank comb + exchange of synchronize_bank on the
+        # device banks (comm.py), omcgpu_get_source_bank into the same host bank.
         bank = np.ascontiguousarray(eng.get_source_bank(n_local))
         eng.host_register(bank)
-        fis = None
-        if world > 1:
-            fis = np.zeros(3 * n_local, dtype=bank.dtype)
-            eng.host_register(fis)
         gen0 = sim.current_batch
         h2d = d2h = 0
         barrier()
@@ -240,16 +237,19 @@ def main():
             h2d += bank.nbytes
             if world == 1:
                 out = eng.next_generation(gi, bank, gen0 + s + 1)
-                d2h += bank.nbytes + 96
+                k_gen = out.global_tally[2] / n_local
             else:
-                fb, out = eng.transport_generation(gi, bank, fis)
-                d2h += fb.nbytes + 96
-            keff = out.global_tally[2] / n_local
+                eng.set_source_bank(bank)
+                out = eng.run_generation(gi)
+                g = comm.allreduce_sum(np.array(out.global_tally[:] + [out.total_weight]))
+                comm.synchronize_bank(sim, gen0 + s + 1, out.n_fission)
+                eng.get_source_bank(n_local, out=bank)
+                k_gen = g[2] / n_global
+            d2h += bank.nbytes + 96
+            keff = k_gen
         barrier()
         dt_e = time.perf_counter() - t0
         eng.host_unregister(bank)
-        if fis is not None:
-            eng.host_unregister(fis)
         if world > 1:
             t = torch.tensor([dt_e], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -258,8 +258,8 @@ def main():
                "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                "note": ("omcgpu_next_generation on the page-locked host SourceSite bank: H2D source, event "
                         "loop, device sort + comb, D2H next source" if world == 1 else
-                        "omcgpu_transport_generation on page-locked host banks, per rank (no inter-rank "
-                        "rebalance in this leg)")}
+                        "per rank: H2D of the page-locked host source bank, event loop, device comb + NCCL "
+                        "exchange of the sites that change owner, D2H of the next source bank")}
 
     # ---- roofline of the dominant kernel (k_xs) from live CUDA-event timings
     peaks = {}

@@ -79,10 +79,12 @@ class Engine:
         self._check(self.lib.omcgpu_set_source_bank(bank.ctypes.data_as(C.c_void_p),
                                                     C.c_int64(bank.size)))
 
-    def get_source_bank(self, n: int) -> np.ndarray:
-        bank = np.zeros(n, abi.site_dtype)
+    def get_source_bank(self, n: int, out: np.ndarray | None = None) -> np.ndarray:
+        """device source bank -> host; `out` (e.g. a page-locked bank) is filled in place"""
+        bank = np.zeros(n, abi.site_dtype) if out is None else out
+        assert bank.dtype == abi.site_dtype and bank.size >= n and bank.flags.c_contiguous
         self._check(self.lib.omcgpu_get_source_bank(bank.ctypes.data_as(C.c_void_p), C.c_int64(n)))
-        return bank
+        return bank[:n]
 
     def get_fission_bank(self, capacity: int) -> np.ndarray:
         bank = np.zeros(capacity, abi.site_dtype)
