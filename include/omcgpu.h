@@ -183,6 +183,8 @@ typedef struct omcgpu_model {
   const int32_t* cell_sqrtkT_ofs; /* [n_cells+1] into cell_sqrtkT                      */
   const double* cell_sqrtkT;      /* sqrt(k_B T) per instance (or 1 entry)             */
   const double* cell_translation; /* [n_cells][3]                                      */
+  const int32_t* cell_rotated;    /* [n_cells] fill cell has a rotation (Cell::rotation_ non-empty)   */
+  const double* cell_rotation;    /* [n_cells][9] rotation matrix as Cell::set_rotation stores it (src/cell.cpp:48-90) */
   const int32_t* cell_distribcell_index; /* -1 = none                                  */
   const int32_t* cell_offset_ofs; /* [n_cells+1] into cell_offset                      */
   const int32_t* cell_offset;     /* Cell::offset_[map]                                */

@@ -398,6 +398,14 @@ OMC_HD void cell_distance(int c, V3 r, V3 u, int on_surface, double& min_dist, i
 // =============================================================================
 // Rectangular lattices -- src/lattice.cpp:243-248, 252-306, 310-342, 352-377
 // =============================================================================
+// Position::rotate with the fill cell's matrix, include/openmc/position.h:97-104
+OMC_HD V3 cell_rotate(int c, V3 v)
+{
+  const double* m = DM.cell_rotation + 9 * c;
+  return v3(v.x * ld(m) + v.y * ld(m + 1) + v.z * ld(m + 2), v.x * ld(m + 3) + v.y * ld(m + 4) + v.z * ld(m + 5),
+    v.x * ld(m + 6) + v.y * ld(m + 7) + v.z * ld(m + 8));
+}
+
 struct LatIdx {
   int x, y, z;
 };
@@ -616,6 +624,10 @@ OMC_HD bool find_cell_inner(const PState& ps, int64_t i, int lvl, int surface)
     r.x -= ld(t);
     r.y -= ld(t + 1);
     r.z -= ld(t + 2);
+    if (ld(DM.cell_rotated + found)) { // LocalCoord::rotate, src/geometry.cpp:200-203, 219-222
+      r = cell_rotate(found, r);
+      u = cell_rotate(found, u);
+    }
     const int nl = lvl + 1;
     const int fill = ld(DM.cell_fill + found);
     if (type == OMCGPU_FILL_UNIVERSE) {
@@ -651,6 +663,7 @@ OMC_HD void reset_deeper(const PState& ps, int64_t i, int n_coord)
     reset_level(ps, i, l);
 }
 
+// (cell_rotate is defined with the lattice helpers above)
 // exhaustive_find_cell / neighbor_list_find_cell with n_coord already set.
 // Out of line on the device: the crossing event calls it from six places, and inlined
 // copies made k_surface_xa 247 KB of SASS -- with the GPU nearly empty (the last ~100

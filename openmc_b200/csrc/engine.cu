@@ -439,10 +439,13 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
     LV(lat_y, lvl) = li.y;
     LV(lat_z, lvl) = li.z;
     V3 r = get_r(ps, i, lvl - 1);
-    const double* t = DM.cell_translation + 3 * LV(cell, lvl - 1);
+    const int c_up = LV(cell, lvl - 1);
+    const double* t = DM.cell_translation + 3 * c_up;
     r.x -= ld(t);
     r.y -= ld(t + 1);
     r.z -= ld(t + 2);
+    if (ld(DM.cell_rotated + c_up)) // src/geometry.cpp:324-326
+      r = cell_rotate(c_up, r);
     set_r(ps, i, lvl, lat_local_position(lat, r, li));
     bool found = false;
     if (lat_valid(lat, li)) {
@@ -535,8 +538,17 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
     collision_mg(p, ba, gc, fb);
   }
   const int n_coord = ps.n_coord[i];
-  for (int l = 0; l < n_coord; ++l) // directions of all levels follow level 0
-    set_u(ps, i, l, p.u);
+  { // directions of all levels follow level 0, through the rotations of rotated fills
+    // (src/particle.cpp:396-406)
+    V3 ul = p.u;
+    set_u(ps, i, 0, ul);
+    for (int l = 1; l < n_coord; ++l) {
+      const int c_up = LV(cell, l - 1);
+      if (ld(DM.cell_rotated + c_up))
+        ul = cell_rotate(c_up, ul);
+      set_u(ps, i, l, ul);
+    }
+  }
   ps.E[i] = p.E;
   ps.g[i] = p.g;
   ps.wgt[i] = p.wgt;
@@ -1531,6 +1543,8 @@ static int upload_model(const omcgpu_model* m)
   UP(cell_sqrtkT_ofs, nc + 1);
   UP(cell_sqrtkT, n_ckt);
   UP(cell_translation, (size_t)nc * 3);
+  UP(cell_rotated, nc);
+  UP(cell_rotation, (size_t)nc * 9);
   UP(cell_distribcell_index, nc);
   UP(cell_offset_ofs, nc + 1);
   UP(cell_offset, n_coff);

@@ -227,6 +227,34 @@ def surface_zoo():
     return m, c5g7_library(False), box, False
 
 
+def rotated_fills():
+    """A 3 x 3 lattice of pin universes placed, translated and ROTATED, inside a box next to a
+    rotated and translated single pin universe -- geometry test case for rotated fills
+    (Cell::rotation_, src/cell.cpp:48-90; src/geometry.cpp:200-222, 324-326)."""
+    m = Model()
+    uo2 = m.material(name="UO2 fuel", macroscopic="UO2", units="macro", density=1.0)
+    water = m.material(name="Water", macroscopic="LWTR", units="macro", density=1.0)
+    cyl = m.surface("z-cylinder", [0.1, -0.05, 0.4])                 # 1 (off-centre: rotation visible)
+    px = m.surface("x-plane", [0.0])                                 # 2 half fuel / half water pin
+    m.cell(region="-1 -2", fill=uo2, universe=1)
+    m.cell(region="-1 2", fill=water, universe=1)
+    m.cell(region="1", fill=water, universe=1)
+    m.cell(region="", fill=water, universe=2)                        # all space: the lattice's outer universe
+    lat = m.lattice(pitch=(1.2, 1.2), lower_left=(-1.8, -1.8), universes=[[1, 1, 1], [1, 1, 1], [1, 1, 1]],
+                    outer=2)
+    b = [m.surface("x-plane", [-4.0], "reflective"), m.surface("x-plane", [4.0], "reflective"),
+         m.surface("y-plane", [-4.0], "reflective"), m.surface("y-plane", [4.0], "reflective"),
+         m.surface("z-plane", [-3.0], "reflective"), m.surface("z-plane", [3.0], "reflective")]
+    s1 = m.surface("sphere", [-1.5, 0.5, 0.2, 2.0])                  # holds the lattice
+    s2 = m.surface("sphere", [2.2, -1.0, -0.3, 1.2])                 # holds the single pin
+    m.cell(region=f"-{s1.id}", fill=lat, universe=0, translation=(-1.5, 0.5, 0.2), rotation=(20.0, -35.0, 50.0))
+    m.cell(region=f"-{s2.id}", fill=1, universe=0, translation=(2.2, -1.0, -0.3), rotation=(0.0, 0.0, 77.0))
+    m.cell(region=f"{s1.id} {s2.id} {b[0].id} -{b[1].id} {b[2].id} -{b[3].id} {b[4].id} -{b[5].id}", fill=water,
+           universe=0)
+    box = [-4.0, -4.0, -3.0, 4.0, 4.0, 3.0]
+    return m, c5g7_library(False), box, False
+
+
 def pincell_multigroup(mesh_dim=100, energy_bins=500):
     """Config C1: examples/pincell_multigroup/build_xml.py:14-149 (7-group C5G7
     UO2/LWTR pin, reflective box, 100x100 mesh {flux, fission, nu-fission} and a

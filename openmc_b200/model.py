@@ -78,6 +78,7 @@ class Cell:
     universe: int = 0
     temperature: Optional[float] = None
     translation: Sequence[float] = (0.0, 0.0, 0.0)
+    rotation: Optional[Sequence[float]] = None   # (phi, theta, psi) in degrees, fill cells only
     fill_type: str = "material"        # 'material' | 'universe' | 'lattice'
 
 
@@ -246,6 +247,25 @@ def region_tokens(spec: str, surface_index: dict):
     return out, simple
 
 
+def rotation_matrix(angles):
+    """Cell::set_rotation, src/cell.cpp:60-85: the (inverse) rotation matrix for the angles
+    (phi, theta, psi) in degrees, term for term (math.sin / cos are the C library's)."""
+    import math
+    phi = -angles[0] * math.pi / 180.0
+    theta = -angles[1] * math.pi / 180.0
+    psi = -angles[2] * math.pi / 180.0
+    c, s_ = math.cos, math.sin
+    return [c(theta) * c(psi),
+            -c(phi) * s_(psi) + s_(phi) * s_(theta) * c(psi),
+            s_(phi) * s_(psi) + c(phi) * s_(theta) * c(psi),
+            c(theta) * s_(psi),
+            c(phi) * c(psi) + s_(phi) * s_(theta) * s_(psi),
+            -s_(phi) * c(psi) + c(phi) * s_(theta) * s_(psi),
+            -s_(theta),
+            s_(phi) * c(theta),
+            c(phi) * c(theta)]
+
+
 # ----------------------------------------------------------------------------
 # the model
 # ----------------------------------------------------------------------------
@@ -345,11 +365,17 @@ class Model:
         mofs = [0]; cmat = []
         kofs = [0]; ckt = []
         trans = np.zeros((nc, 3))
+        rotated = np.zeros(nc, np.int32); rot = np.zeros((nc, 9))
         for i, c in enumerate(self.cells):
             toks, simple = region_tokens(c.region, s_index)
             rtok += toks; rofs.append(len(rtok)); csimple[i] = int(simple)
             cuniv[i] = u_index[c.universe]
             trans[i] = c.translation
+            if c.rotation is not None:
+                if c.fill_type == "material":
+                    raise ValueError(f"cell {c.id}: cannot rotate a material cell")
+                rotated[i] = 1
+                rot[i] = rotation_matrix(c.rotation)
             if c.fill_type == "material":
                 ctype[i] = abi.OMCGPU_FILL_MATERIAL
                 cmat.append(-1 if c.fill is None else m_index[c.fill.id])
@@ -371,7 +397,8 @@ class Model:
                  cell_region_ofs=np.array(rofs, np.int32), region_tokens=np.array(rtok or [0], np.int32),
                  cell_mat_ofs=np.array(mofs, np.int32), cell_material=np.array(cmat or [0], np.int32),
                  cell_sqrtkT_ofs=np.array(kofs, np.int32), cell_sqrtkT=np.array(ckt or [0.0]),
-                 cell_translation=trans, cell_distribcell_index=np.full(nc, -1, np.int32),
+                 cell_translation=trans, cell_rotated=rotated, cell_rotation=rot,
+                 cell_distribcell_index=np.full(nc, -1, np.int32),
                  cell_offset_ofs=np.zeros(nc + 1, np.int32), cell_offset=np.zeros(1, np.int32))
 
         nu = len(univ_ids)

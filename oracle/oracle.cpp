@@ -706,6 +706,14 @@ bool universe_find_cell(Particle& p)
   return false;
 }
 
+// Position::rotate with a fill cell's matrix, include/openmc/position.h:97-104
+Vec3 cell_rotate(int c, Vec3 v)
+{
+  const double* m = M->cell_rotation + 9 * c;
+  return {v.x * m[0] + v.y * m[1] + v.z * m[2], v.x * m[3] + v.y * m[4] + v.z * m[5],
+    v.x * m[6] + v.y * m[7] + v.z * m[8]};
+}
+
 bool find_cell_inner(Particle& p)
 {
   for (;; ++p.n_coord) {
@@ -737,6 +745,10 @@ bool find_cell_inner(Particle& p)
       coord.r.x -= t[0];
       coord.r.y -= t[1];
       coord.r.z -= t[2];
+      if (M->cell_rotated[i_cell]) { // LocalCoord::rotate, src/geometry.cpp:200-203
+        coord.r = cell_rotate(i_cell, coord.r);
+        coord.u = cell_rotate(i_cell, coord.u);
+      }
     } else {
       int lat = M->cell_fill[i_cell];
       coord.r = p.r_local();
@@ -744,6 +756,10 @@ bool find_cell_inner(Particle& p)
       coord.r.x -= t[0];
       coord.r.y -= t[1];
       coord.r.z -= t[2];
+      if (M->cell_rotated[i_cell]) { // src/geometry.cpp:219-222
+        coord.r = cell_rotate(i_cell, coord.r);
+        coord.u = cell_rotate(i_cell, coord.u);
+      }
       lat_get_indices(lat, coord.r, coord.u, coord.lat_idx);
       coord.r = lat_local_position(lat, coord.r, coord.lat_idx);
       coord.lattice = lat;
@@ -794,6 +810,8 @@ void cross_lattice(Particle& p, const BoundaryInfo& b)
   r.x -= t[0];
   r.y -= t[1];
   r.z -= t[2];
+  if (M->cell_rotated[upper.cell]) // src/geometry.cpp:324-326
+    r = cell_rotate(upper.cell, r);
   p.r_local() = lat_local_position(lat, r, coord.lat_idx);
   if (!lat_valid(lat, coord.lat_idx)) {
     p.n_coord = 1;
@@ -2002,8 +2020,12 @@ void event_collide(Particle& p)
   RS.n_coll++;
   p.fission = false;
   p.material_last = C_NONE;
-  for (int j = 0; j < p.n_coord - 1; ++j)
-    p.coord[j + 1].u = p.coord[j].u;
+  for (int j = 0; j < p.n_coord - 1; ++j) { // src/particle.cpp:396-406
+    if (M->cell_rotated[p.coord[j].cell])
+      p.coord[j + 1].u = cell_rotate(p.coord[j].cell, p.coord[j].u);
+    else
+      p.coord[j + 1].u = p.coord[j].u;
+  }
 }
 
 void event_revive(Particle& p)

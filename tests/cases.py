@@ -94,7 +94,12 @@ def load_model_npz(path):
     from openmc_b200 import _abi as abi
     z = np.load(path)
     types = abi.model_field_types()
-    return abi.ModelHandle({k: (z[k] if types[k][1] else z[k].item()) for k in z.files})
+    vals = {k: (z[k] if types[k][1] else z[k].item()) for k in z.files if k in types}
+    # per-cell fields added to the ABI after a fixture was written: no rotated fills
+    nc = int(vals["n_cells"])
+    vals.setdefault("cell_rotated", np.zeros(nc, np.int32))
+    vals.setdefault("cell_rotation", np.zeros(9 * nc))
+    return abi.ModelHandle(vals)
 
 
 def build_lattice(name):

@@ -38,6 +38,8 @@ def geometry_xml(m) -> str:
             a.append(f'region="{c.region}"')
         if any(float(t) != 0.0 for t in c.translation):
             a.append(f'translation="{_fmt(c.translation)}"')
+        if getattr(c, "rotation", None) is not None:
+            a.append(f'rotation="{_fmt(c.rotation)}"')
         out.append("  <cell " + " ".join(a) + "/>")
     for l in m.lattices:
         arr = np.asarray(l.universes)

@@ -263,12 +263,13 @@ def test_assembly_eigenvalue_statistics(gpu_engine):
     sim.simulation_finalize()
 
 
-def test_surface_zoo_generation_matches_oracle(gpu_engine, monkeypatch):
+@pytest.mark.parametrize("case", ["surface_zoo", "rotated_fills"])
+def test_surface_zoo_generation_matches_oracle(gpu_engine, case, monkeypatch):
     """spheres, cones, x / y cylinders, a general plane, union / complement regions, vacuum
-    sphere: one generation against the oracle"""
+    sphere; translated + rotated universe and lattice fills: one generation against the oracle"""
     import reference_cases as rc
     monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", "2048")
-    m, model, box = rc.build("surface_zoo")
+    m, model, box = rc.build(case)
     o = Oracle(model)
     n = 20000
     src = o.sample_initial_source(n, box, False)
