@@ -71,6 +71,7 @@ extern "C" {
 #define OMCGPU_BC_NONE        0   /* transmission */
 #define OMCGPU_BC_VACUUM      1
 #define OMCGPU_BC_REFLECTIVE  2
+#define OMCGPU_BC_PERIODIC    3   /* translational, between two planes (src/boundary_condition.cpp:66-155) */
 
 /* cell fill: include/openmc/cell.h Fill enum */
 #define OMCGPU_FILL_MATERIAL  0
@@ -166,6 +167,8 @@ typedef struct omcgpu_model {
   int32_t n_surfaces;
   const int32_t* surf_type;       /* [n_surfaces] OMCGPU_SURF_*                        */
   const int32_t* surf_bc;         /* [n_surfaces] OMCGPU_BC_*                          */
+  const int32_t* surf_periodic;   /* [n_surfaces] partner surface of a periodic BC, else -1 */
+  const double* surf_periodic_shift; /* [n_surfaces][3] added to r when this periodic surface is struck */
   const int32_t* surf_id;         /* [n_surfaces] user ids (messages only)             */
   const double* surf_coef;        /* [n_surfaces][OMCGPU_SURF_NCOEF]                   */
 

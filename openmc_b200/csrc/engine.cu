@@ -464,6 +464,22 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
     if (bc == OMCGPU_BC_VACUUM) {
       ps.k_leak[i] += ps.wgt[i];
       ps.wgt[i] = 0.0;
+    } else if (bc == OMCGPU_BC_PERIODIC) {
+      // TranslationalPeriodicBC::handle_particle + Particle::cross_periodic_bc,
+      // src/boundary_condition.cpp:129-155, src/particle.cpp:712-760
+      if (n_coord != 1) {
+        mark_lost(ps, gc, i);
+      } else {
+        const double* t = DM.surf_periodic_shift + 3 * s;
+        LV(rx, 0) += ld(t);
+        LV(ry, 0) += ld(t + 1);
+        LV(rz, 0) += ld(t + 2);
+        const int partner = ld(DM.surf_periodic + s) + 1;
+        surface = surface > 0 ? partner : -partner;
+        ps.surface[i] = surface;
+        if (!find_cell_from(ps, i, 1, surface))
+          mark_lost(ps, gc, i);
+      }
     } else if (bc == OMCGPU_BC_REFLECTIVE) {
       if (n_coord != 1) {
         mark_lost(ps, gc, i);
@@ -1525,6 +1541,8 @@ static int upload_model(const omcgpu_model* m)
 #define UP(field, count) rc = rc ? rc : upload(&h.field, (size_t)(count))
   UP(surf_type, ns);
   UP(surf_bc, ns);
+  UP(surf_periodic, ns);
+  UP(surf_periodic_shift, (size_t)ns * 3);
   UP(surf_id, ns);
   UP(surf_coef, (size_t)ns * OMCGPU_SURF_NCOEF);
   const int n_tok = nc ? m->cell_region_ofs[nc] : 0;
@@ -1775,8 +1793,11 @@ static int check_supported(const omcgpu_model* m)
   for (int s = 0; s < m->n_surfaces; ++s) {
     if (m->surf_type[s] < 0 || m->surf_type[s] > OMCGPU_SURF_ZCONE)
       return fail(OMCGPU_E_UNSUPPORTED, "surface type not supported on the device%s");
-    if (m->surf_bc[s] < 0 || m->surf_bc[s] > OMCGPU_BC_REFLECTIVE)
+    if (m->surf_bc[s] < 0 || m->surf_bc[s] > OMCGPU_BC_PERIODIC)
       return fail(OMCGPU_E_UNSUPPORTED, "boundary condition not supported on the device%s");
+    if (m->surf_bc[s] == OMCGPU_BC_PERIODIC &&
+        (m->surf_type[s] > OMCGPU_SURF_PLANE || m->surf_periodic[s] < 0 || m->surf_periodic[s] >= m->n_surfaces))
+      return fail(OMCGPU_E_UNSUPPORTED, "periodic boundary: only translational, between two planes%s");
   }
   for (int t = 0; t < m->n_tallies; ++t) {
     if (m->tally_n_filters[t] > OMCGPU_MAX_FILTERS || m->tally_n_scores[t] > OMCGPU_MAX_SCORES)

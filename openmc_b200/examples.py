@@ -227,6 +227,27 @@ def surface_zoo():
     return m, c5g7_library(False), box, False
 
 
+def periodic_box():
+    """Fuel pin in a box with translational periodic boundaries in x (paired by id), in y
+    (general planes with a non-unit normal; the two unpaired periodic surfaces pair up,
+    src/surface.cpp:1279-1313); reflective in z -- test case for TranslationalPeriodicBC
+    (src/boundary_condition.cpp:66-155)."""
+    m = Model()
+    uo2 = m.material(name="UO2 fuel", macroscopic="UO2", units="macro", density=1.0)
+    water = m.material(name="Water", macroscopic="LWTR", units="macro", density=1.0)
+    m.surface("z-cylinder", [0.1, 0.0, 0.45])                                        # 1
+    m.surface("x-plane", [-0.7], "periodic", periodic_surface_id=3)                  # 2
+    m.surface("x-plane", [0.9], "periodic", periodic_surface_id=2)                   # 3
+    m.surface("plane", [0.0, 2.0, 0.0, -1.1], "periodic")                            # 4 (unpaired): y = -0.55
+    m.surface("plane", [0.0, 2.0, 0.0, 1.0], "periodic")                             # 5 (unpaired): y = 0.5
+    m.surface("z-plane", [-1.0], "reflective")                                       # 6
+    m.surface("z-plane", [1.0], "reflective")                                        # 7
+    m.cell(region="-1 6 -7", fill=uo2)
+    m.cell(region="1 2 -3 4 -5 6 -7", fill=water)
+    box = [-0.7, -0.55, -1.0, 0.9, 0.5, 1.0]
+    return m, c5g7_library(False), box, False
+
+
 def rotated_fills():
     """A 3 x 3 lattice of pin universes placed, translated and ROTATED, inside a box next to a
     rotated and translated single pin universe -- geometry test case for rotated fills

@@ -40,7 +40,7 @@ _SURF_KINDS = {
     "z-cone": (abi.OMCGPU_SURF_ZCONE, 4),
 }
 _BCS = {"transmission": abi.OMCGPU_BC_NONE, "vacuum": abi.OMCGPU_BC_VACUUM,
-        "reflective": abi.OMCGPU_BC_REFLECTIVE}
+        "reflective": abi.OMCGPU_BC_REFLECTIVE, "periodic": abi.OMCGPU_BC_PERIODIC}
 _SCORES = {"flux": abi.OMCGPU_SCORE_FLUX, "total": abi.OMCGPU_SCORE_TOTAL,
            "absorption": abi.OMCGPU_SCORE_ABSORPTION, "fission": abi.OMCGPU_SCORE_FISSION,
            "nu-fission": abi.OMCGPU_SCORE_NU_FISSION, "scatter": abi.OMCGPU_SCORE_SCATTER}
@@ -56,6 +56,7 @@ class Surface:
     kind: str
     coeffs: Sequence[float]
     boundary: str = "transmission"
+    periodic_surface_id: Optional[int] = None   # partner of a 'periodic' plane
 
 
 @dataclass
@@ -288,8 +289,9 @@ class Model:
                              temperature_tolerance=10.0)
 
     # -- convenience constructors ------------------------------------------------
-    def surface(self, kind, coeffs, boundary="transmission", id=None):
-        s = Surface(id if id is not None else len(self.surfaces) + 1, kind, list(coeffs), boundary)
+    def surface(self, kind, coeffs, boundary="transmission", id=None, periodic_surface_id=None):
+        s = Surface(id if id is not None else len(self.surfaces) + 1, kind, list(coeffs), boundary,
+                    periodic_surface_id)
         self.surfaces.append(s)
         return s
 
@@ -317,6 +319,62 @@ class Model:
         self.lattices.append(l)
         return l
 
+    def _periodic_pairs(self, s_index):
+        """TranslationalPeriodicBC (src/boundary_condition.cpp:66-127): the translation between
+        two parallel periodic planes, u (d2 - d1) with u the first plane's normal at the origin
+        and d the signed distance of a plane from the origin along u.  Pairs come from
+        periodic_surface_id, or the two unpaired periodic surfaces (src/surface.cpp:1279-1313)."""
+        ns = len(self.surfaces)
+        partner = np.full(max(ns, 1), -1, np.int32)
+        shift = np.zeros((max(ns, 1), 3))
+        per = [s for s in self.surfaces if s.boundary == "periodic"]
+        pairs = set()
+        loose = []
+        for s in per:
+            if s.periodic_surface_id is not None:
+                pairs.add((min(s.id, s.periodic_surface_id), max(s.id, s.periodic_surface_id)))
+            else:
+                loose.append(s.id)
+        if len(loose) == 2:
+            pairs.add((min(loose), max(loose)))
+        elif loose:
+            raise ValueError("periodic surfaces without a partner")
+
+        def plane(s):
+            if s.kind == "x-plane":
+                return (1.0, 0.0, 0.0, s.coeffs[0])
+            if s.kind == "y-plane":
+                return (0.0, 1.0, 0.0, s.coeffs[0])
+            if s.kind == "z-plane":
+                return (0.0, 0.0, 1.0, s.coeffs[0])
+            if s.kind == "plane":
+                return tuple(s.coeffs)
+            raise ValueError("translational periodic BCs need planes")
+
+        def signed_distance(pl, u):
+            # evaluate(origin) = -D; distance(origin, +-u): d = -f / projection, src/surface.cpp:207-220, 354-366
+            a, b, c, d0 = pl
+            e = -d0
+            if abs(e) <= 1e-12:
+                return 0.0
+            sign = -1.0 if e > 1e-12 else 1.0       # direction -u (e > 0) or +u (e < 0)
+            proj = sign * (a * u[0] + b * u[1] + c * u[2])
+            dist = -e / proj
+            if dist < 0.0:
+                dist = float("inf")
+            return -dist if e > 1e-12 else dist
+
+        for lo, hi in sorted(pairs):
+            i, j = s_index[lo], s_index[hi]
+            p1, p2 = plane(self.surfaces[i]), plane(self.surfaces[j])
+            u = p1[:3]
+            d1, d2 = signed_distance(p1, u), signed_distance(p2, u)
+            t = [u[k] * (d2 - d1) for k in range(3)]
+            partner[i], partner[j] = j, i
+            shift[i] = t
+            shift[j] = [-x for x in t]
+        return partner, shift
+
     # -- flattening --------------------------------------------------------------
     def flatten_geometry(self) -> dict:
         v = {}
@@ -332,7 +390,9 @@ class Model:
             stype[i] = kind
             coef[i, :nco] = s.coeffs
             sbc[i] = _BCS[s.boundary]
-        v.update(n_surfaces=ns, surf_type=stype, surf_bc=sbc, surf_coef=coef,
+        partner, shift = self._periodic_pairs({s.id: i for i, s in enumerate(self.surfaces)})
+        v.update(n_surfaces=ns, surf_type=stype, surf_bc=sbc, surf_coef=coef, surf_periodic=partner,
+                 surf_periodic_shift=shift,
                  surf_id=np.array([s.id for s in self.surfaces] or [0], np.int32))
 
         # universes: ids in order of first appearance (cells' universe attribute,

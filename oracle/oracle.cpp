@@ -1954,6 +1954,22 @@ void cross_surface(Particle& p)
     p.wgt = 0.0;
     return;
   }
+  if (bc == OMCGPU_BC_PERIODIC) { // TranslationalPeriodicBC::handle_particle + cross_periodic_bc :712-760
+    if (p.n_coord != 1) {
+      mark_as_lost(p, "Cannot transfer particle across surface in a lower universe.");
+      return;
+    }
+    const double* t = M->surf_periodic_shift + 3 * s;
+    p.r().x += t[0];
+    p.r().y += t[1];
+    p.r().z += t[2];
+    const int partner = M->surf_periodic[s] + 1;
+    p.surface = p.surface > 0 ? partner : -partner;
+    p.n_coord = 1;
+    if (!neighbor_list_find_cell(p))
+      mark_as_lost(p, "Couldn't find particle after hitting periodic boundary");
+    return;
+  }
   if (bc == OMCGPU_BC_REFLECTIVE) { // ReflectiveBC + cross_reflective_bc :657-710
     Vec3 n = surf_normal(s, p.r());
     Vec3 u = p.u();

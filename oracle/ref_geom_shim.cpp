@@ -173,7 +173,15 @@ int verbosity = 0;
 void Particle::mark_as_lost(const char* message) { throw std::runtime_error(message); } // key function: emits the vtable
 void Particle::cross_vacuum_bc(const Surface&) {}
 void Particle::cross_reflective_bc(const Surface&, Direction) {}
-void Particle::cross_periodic_bc(const Surface&, Position, Direction, int) {}
+// records what the reference's periodic boundary condition hands to the particle
+static double g_bc_r[3], g_bc_u[3];
+static int g_bc_surface = 0;
+void Particle::cross_periodic_bc(const Surface&, Position new_r, Direction new_u, int new_surface)
+{
+  g_bc_r[0] = new_r.x; g_bc_r[1] = new_r.y; g_bc_r[2] = new_r.z;
+  g_bc_u[0] = new_u.x; g_bc_u[1] = new_u.y; g_bc_u[2] = new_u.z;
+  g_bc_surface = new_surface;
+}
 double Material::temperature() const { return 293.6; }
 
 namespace model {
@@ -247,6 +255,34 @@ int ref_geom_load(const char* xml, const int32_t* material_ids, int n_materials)
         c->sqrtkT_.push_back(0.15906);
     finalize_cell_densities(); // no cell carries a density here: every multiplier becomes 1
     model::n_coord_levels = maximum_levels(model::root_universe);
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+// BoundaryCondition::handle_particle of the surface a particle struck (token = signed
+// surface index + 1): TranslationalPeriodicBC (src/boundary_condition.cpp:129-155) computes
+// the new position and surface token; new_surface = 0 if the surface has no periodic BC
+int ref_geom_periodic(int64_t n, const int32_t* token, const double* xyz, const double* uvw, double* new_xyz,
+  int32_t* new_token)
+{
+  try {
+    Particle p;
+    for (int64_t k = 0; k < n; ++k) {
+      const int s = std::abs(token[k]) - 1;
+      const auto& surf = *model::surfaces[s];
+      p.r() = {xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2]};
+      p.u() = {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]};
+      p.surface() = token[k];
+      g_bc_surface = 0;
+      if (surf.bc_ && surf.bc_->type() == "periodic")
+        surf.bc_->handle_particle(p, surf);
+      new_token[k] = g_bc_surface;
+      for (int d = 0; d < 3; ++d)
+        new_xyz[3 * k + d] = g_bc_surface ? g_bc_r[d] : xyz[3 * k + d];
+    }
   } catch (const std::exception& e) {
     std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
     return -1;

@@ -25,6 +25,8 @@ def geometry_xml(m) -> str:
     out = ["<?xml version='1.0' encoding='utf-8'?>", "<geometry>"]
     for s in m.surfaces:
         bc = "" if s.boundary in ("transmission", None) else f' boundary="{s.boundary}"'
+        if getattr(s, "periodic_surface_id", None) is not None:
+            bc += f' periodic_surface_id="{s.periodic_surface_id}"'
         out.append(f'  <surface id="{s.id}" type="{s.kind}" coeffs="{_fmt(s.coeffs)}"{bc}/>')
     for c in m.cells:
         a = [f'id="{c.id}"', f'universe="{c.universe}"']
@@ -93,6 +95,18 @@ class ReferenceGeometry:
         if self.lib.ref_geom_find_cell(C.c_int64(n), p(xyz), p(uvw), p(cid), p(inst), p(mat), p(nco)):
             raise RuntimeError(self.lib.ref_geom_error().decode())
         return cid, inst, mat, nco
+
+    def periodic(self, token, xyz, uvw):
+        """what the reference's periodic BC does to particles that struck surface `token`
+        (signed index + 1): new positions and new surface tokens (0: not a periodic surface)"""
+        token = np.ascontiguousarray(token, np.int32)
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        uvw = np.ascontiguousarray(uvw, np.float64)
+        new_xyz = np.zeros_like(xyz); new_token = np.zeros_like(token)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        if self.lib.ref_geom_periodic(C.c_int64(token.size), p(token), p(xyz), p(uvw), p(new_xyz), p(new_token)):
+            raise RuntimeError(self.lib.ref_geom_error().decode())
+        return new_xyz, new_token
 
     def distance_to_boundary(self, xyz, uvw):
         xyz = np.ascontiguousarray(xyz, np.float64)

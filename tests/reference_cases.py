@@ -6,7 +6,7 @@ import numpy as np
 import cases
 from openmc_b200 import examples, mgxs, nuclide
 
-NAMES = ["pincell_ce", "pincell_mg", "assembly_ce", "c5g7_core", "pwr_core_ce", "surface_zoo", "rotated_fills"]
+NAMES = ["pincell_ce", "pincell_mg", "assembly_ce", "c5g7_core", "pwr_core_ce", "surface_zoo", "rotated_fills", "periodic_box"]
 _CACHE = {}
 
 
@@ -23,6 +23,9 @@ def build(name):
             model = nuclide.build_ce_model(m, lib)
         elif name == "c5g7_core":         # C4
             m, lib, box, of = examples.c5g7_core(mesh_dim=17, tallies=False)
+            model = mgxs.build_mg_model(m, lib)
+        elif name == "periodic_box":      # translational periodic planes (axis and oblique)
+            m, lib, box, of = examples.periodic_box()
             model = mgxs.build_mg_model(m, lib)
         elif name == "rotated_fills":     # translated + rotated universe and lattice fills
             m, lib, box, of = examples.rotated_fills()

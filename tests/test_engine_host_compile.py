@@ -116,11 +116,12 @@ def test_comb_matches_oracle(emu_lib):
 
 
 @pytest.mark.parametrize("threshold", ["0", "100000"])
-@pytest.mark.parametrize("case", ["surface_zoo", "rotated_fills"])
+@pytest.mark.parametrize("case", ["surface_zoo", "rotated_fills", "periodic_box"])
 def test_surface_zoo_generation_matches_oracle(emu_lib, case, threshold, monkeypatch):
     """one generation through spheres, cones, x / y cylinders, a general plane, union and
     complement regions and a vacuum sphere -- and through translated + rotated universe and
-    lattice fills (directions re-rotated after every collision, src/particle.cpp:396-406):
+    lattice fills (directions re-rotated after every collision, src/particle.cpp:396-406), and
+    through translational periodic boundaries:
     same events, same sorted fission bank"""
     import reference_cases as rc
     monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)

@@ -46,6 +46,28 @@ def test_oracle_geometry_equals_reference(name):
     assert np.array_equal(d2, d)               # same arithmetic, same libm: identical doubles
 
 
+@needs_ref
+def test_periodic_boundary_equals_reference():
+    """TranslationalPeriodicBC::handle_particle of the reference (pairs given by id, the two
+    unpaired surfaces paired up, general planes with a non-unit normal): the flattener's partner table and
+    translation vectors move a particle to the identical position and surface token"""
+    m, model, box = rc.build("periodic_box")
+    ref = ref_geometry.ReferenceGeometry(m)
+    g = np.random.default_rng(2)
+    n = 5000
+    lo, hi = np.array(box[:3]), np.array(box[3:])
+    xyz = lo + g.uniform(size=(n, 3)) * (hi - lo)
+    uvw = g.normal(size=(n, 3)); uvw /= np.linalg.norm(uvw, axis=1)[:, None]
+    tok = g.choice([2, -2, 3, -3, 4, -4, 5, -5, 6, 1], size=n).astype(np.int32)
+    new_xyz, new_tok = ref.periodic(tok, xyz, uvw)
+    part = np.asarray(model["surf_periodic"])
+    sh = np.asarray(model["surf_periodic_shift"]).reshape(-1, 3)
+    s = np.abs(tok) - 1
+    assert np.array_equal(new_tok, np.where(part[s] >= 0, np.sign(tok) * (part[s] + 1), 0))
+    assert np.array_equal(new_xyz, np.where((part[s] >= 0)[:, None], xyz + sh[s], xyz))
+    assert set(np.unique(new_tok)) == {-5, -4, -3, -2, 0, 2, 3, 4, 5}
+
+
 @pytest.mark.parametrize("name", rc.NAMES)
 def test_committed_reference_vectors_are_reproduced_by_the_oracle(name):
     """the vectors the GPU tier uses (tests/golden/refgeom_*.npz, written by
