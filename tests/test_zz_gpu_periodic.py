@@ -1,5 +1,5 @@
-"""GPU tier, translational periodic boundaries (added last in round 1; the device code was
-checked on the CPU tier against the oracle and the reference's own BC code): one generation
+"""GPU tier, translational periodic boundaries (the device code is also checked on the CPU
+tier against the oracle and the reference's own BC code): one generation
 in a box with periodic x planes, periodic oblique planes and reflective z planes."""
 import numpy as np
 import pytest
