@@ -66,3 +66,33 @@ def test_many_nuclide_lookup_bit_exact(emu_lib):
     xs_o, ig_o = o.calculate_xs(E, mats, int(n_nuc[mat]))
     assert np.array_equal(ig_e, ig_o) and np.array_equal(xs_e, xs_o)
     eng.finalize()
+
+
+@pytest.mark.parametrize("env", [
+    {"OMCGPU_SORT_COLL": "1"},                             # collision list in (material, energy) order too
+    {"OMCGPU_SORT_XS": "0"},                               # fused, index-ordered sweeps with the lockstep lookup
+    {"OMCGPU_SORT_XS": "0", "OMCGPU_SWEEP": "1"},          # merged sweep, fused lookup
+    {"OMCGPU_ORDERED": "0"},                               # lists appended with atomics
+    {"OMCGPU_LOW_COUNT": "100000"},                        # lockstep lookup for every material
+    {"OMCGPU_BATCH_XS": "0", "OMCGPU_SORT_XS": "0"},       # one nuclide at a time
+])
+def test_many_nuclide_scheduling_variants_bank_the_same_sites(emu_lib, env, monkeypatch):
+    """config C5 (40-nuclide fuel here): every optional path of the many-nuclide machinery
+    leaves the histories' arithmetic alone -- identical events and fission bank"""
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", "64")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    model, box, of = cases.build_lattice("pwr_core")
+    o = Oracle(model)
+    n = 800
+    src = o.sample_initial_source(n, box, of)
+    eng = lib.Engine(emu_lib)
+    eng.init(model, 0, 1024)
+    gi = eng.gen_in(n, 0, 0, 1.0, True)
+    fb, out = eng.transport_generation(gi, src)
+    fb_o, out_o = o.transport_generation(gi, src)
+    assert out.n_lost == 0
+    assert out.n_fission == out_o.n_fission and out.n_events == out_o.n_events
+    for f in ("r", "u", "E", "wgt", "parent_id", "progeny_id"):
+        assert np.array_equal(fb[f], fb_o[f]), f
+    eng.finalize()
