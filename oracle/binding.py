@@ -114,6 +114,13 @@ class Oracle:
                                   C.c_int32(max_nuc))
         return out, ig
 
+    def eval_function(self, fn, x):
+        self.load()
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.zeros_like(x)
+        self.lib.orc_eval_function(C.c_int(fn), C.c_int64(x.size), _p(x, C.c_double), _p(y, C.c_double))
+        return y
+
     def mesh_bins_crossed(self, mesh, r0, r1, u, cap_per_track=512):
         """(ofs, bins, length fractions) of StructuredMesh::bins_crossed for tracks r0 -> r1"""
         self.load()

@@ -2247,6 +2247,14 @@ int orc_distance_to_boundary(const double* xyz, const double* uvw, int64_t n, do
   return 0;
 }
 
+// Function1D evaluation of function `fn` of the loaded model at n abscissae
+int orc_eval_function(int fn, int64_t n, const double* x, double* y)
+{
+  for (int64_t k = 0; k < n; ++k)
+    y[k] = eval_function(fn, x[k]);
+  return 0;
+}
+
 // StructuredMesh::bins_crossed (src/mesh.cpp:999-1146) for n tracks r0 -> r1: track k's
 // (bin, length fraction) pairs are out[ofs[k] .. ofs[k+1]); returns the number of pairs
 int64_t orc_mesh_bins_crossed(int mesh, int64_t n, const double* r0, const double* r1, const double* u,

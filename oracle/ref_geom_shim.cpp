@@ -16,7 +16,19 @@
 #include <stdexcept>
 #include <string>
 
+#include <map>
+#include <memory>
+#include <unordered_map>
+#include <vector>
+
 #include "pugixml.hpp"
+
+// Tabulated1D keeps its table private and is otherwise only constructible from an HDF5
+// dataset: the test doorway below fills the members by hand (access control does not
+// change the layout the reference's translation units were compiled with)
+#define private public
+#include "openmc/endf.h"
+#undef private
 
 #include "openmc/capi.h"
 #include "openmc/cell.h"
@@ -501,6 +513,35 @@ int64_t ref_mesh_bins_crossed(int mesh, int64_t n, const double* r0, const doubl
     std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
     return -2;
   }
+}
+
+} // extern "C"
+
+// =============================================================================
+// Function1D evaluation (src/endf.cpp:125-134 Polynomial, :167-226 Tabulated1D) -- used for
+// nu(E), the Watt / Maxwell / evaporation parameters and product yields.
+// =============================================================================
+extern "C" {
+
+int ref_eval_polynomial(const double* coef, int n_coef, int64_t n, const double* x, double* y)
+{
+  Polynomial f(vector<double>(coef, coef + n_coef));
+  for (int64_t k = 0; k < n; ++k)
+    y[k] = f(x[k]);
+  return 0;
+}
+
+// one lin-lin region (n_regions_ == 0 in the reference)
+int ref_eval_tabulated(const double* xs, const double* ys, int n_pairs, int64_t n, const double* x, double* y)
+{
+  Tabulated1D f;
+  f.n_regions_ = 0;
+  f.n_pairs_ = n_pairs;
+  f.x_.assign(xs, xs + n_pairs);
+  f.y_.assign(ys, ys + n_pairs);
+  for (int64_t k = 0; k < n; ++k)
+    y[k] = f(x[k]);
+  return 0;
 }
 
 } // extern "C"

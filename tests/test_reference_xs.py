@@ -65,3 +65,36 @@ def test_gpu_lookup_equals_reference_vectors(gpu_engine):
         assert np.array_equal(ig_g[:, :n_nuc], v[f"ig{mat}"])                  # bit-exact
         np.testing.assert_allclose(xs_g, v[f"xs{mat}"], rtol=1e-12, atol=0)     # north_star tolerance
     gpu_engine.finalize()
+
+
+@needs_ref
+def test_function1d_evaluation_equals_reference():
+    """every Polynomial / Tabulated1D of the synthetic library (nu(E), Watt a(E) b(E), Maxwell
+    theta(E), yields) through the reference's own operator() (src/endf.cpp, compiled
+    unmodified): identical values inside, on and outside the tabulated range"""
+    import ctypes as C
+    from openmc_b200 import _abi as abi
+    model, box, of, libx = cases.build_ce(n_grid=2000)
+    L = C.CDLL(ref_geometry.LIB)
+    o = Oracle(model)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    fn_ofs = np.asarray(model["fn_ofs"]); fn_type = np.asarray(model["fn_type"]); data = np.asarray(model["fn_data"])
+    g = np.random.default_rng(3)
+    n_tab = n_pol = 0
+    for f in range(int(model["n_functions"])):
+        d = np.ascontiguousarray(data[fn_ofs[f]:fn_ofs[f + 1]])
+        x = np.exp(g.uniform(np.log(1e-6), np.log(3e7), 3000))
+        want = np.zeros_like(x)
+        if fn_type[f] == abi.OMCGPU_FN_POLYNOMIAL:
+            assert L.ref_eval_polynomial(p(d), C.c_int(d.size), C.c_int64(x.size), p(x), p(want)) == 0
+            n_pol += 1
+        else:
+            k = d.size // 2
+            xs, ys = np.ascontiguousarray(d[:k]), np.ascontiguousarray(d[k:])
+            x = np.ascontiguousarray(np.concatenate([x, xs, np.nextafter(xs, 0), np.nextafter(xs, np.inf),
+                                                     [xs[0] * 0.5, xs[-1] * 2.0]]))
+            want = np.zeros_like(x)
+            assert L.ref_eval_tabulated(p(xs), p(ys), C.c_int(k), C.c_int64(x.size), p(x), p(want)) == 0
+            n_tab += 1
+        assert np.array_equal(o.eval_function(f, x), want), f
+    assert n_tab > 0 and n_pol > 0
