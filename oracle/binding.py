@@ -114,6 +114,14 @@ class Oracle:
                                   C.c_int32(max_nuc))
         return out, ig
 
+    def sample_product(self, prod, E_in, seeds):
+        self.load()
+        E_in = np.ascontiguousarray(E_in, np.float64); seeds = np.ascontiguousarray(seeds, np.uint64)
+        E_out = np.zeros_like(E_in); mu = np.zeros_like(E_in); s_out = np.zeros_like(seeds)
+        self.lib.orc_sample_product(C.c_int(prod), C.c_int64(E_in.size), _p(E_in, C.c_double), _p(seeds, C.c_uint64),
+                                    _p(E_out, C.c_double), _p(mu, C.c_double), _p(s_out, C.c_uint64))
+        return E_out, mu, s_out
+
     def eval_function(self, fn, x):
         self.load()
         x = np.ascontiguousarray(x, np.float64)

@@ -2247,6 +2247,18 @@ int orc_distance_to_boundary(const double* xyz, const double* uvw, int64_t n, do
   return 0;
 }
 
+// ReactionProduct::sample of product `prod` of the loaded model (isotropic angle + energy law)
+int orc_sample_product(int prod, int64_t n, const double* E_in, const uint64_t* seed_in, double* E_out,
+  double* mu_out, uint64_t* seed_out)
+{
+  for (int64_t k = 0; k < n; ++k) {
+    uint64_t seed = seed_in[k];
+    ce_sample_product(prod, E_in[k], E_out[k], mu_out[k], &seed);
+    seed_out[k] = seed;
+  }
+  return 0;
+}
+
 // Function1D evaluation of function `fn` of the loaded model at n abscissae
 int orc_eval_function(int fn, int64_t n, const double* x, double* y)
 {

@@ -16,10 +16,26 @@
 #include <stdexcept>
 #include <string>
 
+#include <algorithm>
+#include <array>
+#include <complex>
+#include <fstream>
+#include <functional>
+#include <iomanip>
+#include <iostream>
+#include <limits>
 #include <map>
 #include <memory>
+#include <numeric>
+#include <set>
+#include <sstream>
+#include <tuple>
 #include <unordered_map>
+#include <unordered_set>
+#include <utility>
 #include <vector>
+
+#include "openmc/hdf5_interface.h" // (pulls its own library headers in before `private` is redefined)
 
 #include "pugixml.hpp"
 
@@ -28,6 +44,7 @@
 // change the layout the reference's translation units were compiled with)
 #define private public
 #include "openmc/endf.h"
+#include "openmc/distribution_energy.h"
 #undef private
 
 #include "openmc/capi.h"
@@ -37,6 +54,7 @@
 #include "openmc/file_utils.h"
 #include "openmc/geometry.h"
 #include "openmc/geometry_aux.h"
+#include "openmc/random_dist.h"
 #include "openmc/hdf5_interface.h"
 #include "openmc/lattice.h"
 #include "openmc/material.h"
@@ -541,6 +559,73 @@ int ref_eval_tabulated(const double* xs, const double* ys, int n_pairs, int64_t 
   f.y_.assign(ys, ys + n_pairs);
   for (int64_t k = 0; k < n; ++k)
     y[k] = f(x[k]);
+  return 0;
+}
+
+} // extern "C"
+
+// =============================================================================
+// Secondary energy laws (src/distribution_energy.cpp: LevelInelastic :42-55, MaxwellEnergy
+// :274-298, Evaporation :301-327, WattEnergy :333-361) behind an isotropic
+// UncorrelatedAngleEnergy (src/secondary_uncorrelated.cpp:53-66: mu first, then the energy).
+// The objects are raw storage with the members filled by hand; sample() is called
+// non-virtually.
+// =============================================================================
+static void fill_tab(Tabulated1D* t, const double* xs, const double* ys, int n)
+{
+  new (t) Tabulated1D();
+  t->n_regions_ = 0;
+  t->n_pairs_ = n;
+  t->x_.assign(xs, xs + n);
+  t->y_.assign(ys, ys + n);
+}
+
+extern "C" {
+
+// law: 1 level (par0 = threshold, par1 = mass ratio), 2 Maxwell, 3 evaporation, 4 Watt
+// (par0 = restriction energy u; table 0 = theta or a, table 1 = b)
+int ref_sample_energy_law(int law, double par0, double par1, const double* x0, const double* y0, int n0,
+  const double* x1, const double* y1, int n1, int64_t n, const double* E_in, const uint64_t* seed_in,
+  double* E_out, double* mu_out, uint64_t* seed_out)
+{
+  try {
+    alignas(16) static char raw[sizeof(WattEnergy) + sizeof(MaxwellEnergy) + sizeof(Evaporation) + sizeof(LevelInelastic)];
+    std::memset(raw, 0, sizeof(raw));
+    auto* level = reinterpret_cast<LevelInelastic*>(raw);
+    auto* maxwell = reinterpret_cast<MaxwellEnergy*>(raw);
+    auto* evap = reinterpret_cast<Evaporation*>(raw);
+    auto* watt = reinterpret_cast<WattEnergy*>(raw);
+    if (law == 1) {
+      level->threshold_ = par0;
+      level->mass_ratio_ = par1;
+    } else if (law == 2) {
+      fill_tab(&maxwell->theta_, x0, y0, n0);
+      maxwell->u_ = par0;
+    } else if (law == 3) {
+      fill_tab(&evap->theta_, x0, y0, n0);
+      evap->u_ = par0;
+    } else if (law == 4) {
+      fill_tab(&watt->a_, x0, y0, n0);
+      fill_tab(&watt->b_, x1, y1, n1);
+      watt->u_ = par0;
+    } else {
+      throw std::runtime_error("unknown energy law");
+    }
+    for (int64_t k = 0; k < n; ++k) {
+      uint64_t seed = seed_in[k];
+      mu_out[k] = uniform_distribution(-1., 1., &seed); // isotropic UncorrelatedAngleEnergy
+      switch (law) {
+      case 1: E_out[k] = level->LevelInelastic::sample(E_in[k], &seed); break;
+      case 2: E_out[k] = maxwell->MaxwellEnergy::sample(E_in[k], &seed); break;
+      case 3: E_out[k] = evap->Evaporation::sample(E_in[k], &seed); break;
+      default: E_out[k] = watt->WattEnergy::sample(E_in[k], &seed); break;
+      }
+      seed_out[k] = seed;
+    }
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
   return 0;
 }
 

@@ -98,3 +98,54 @@ def test_function1d_evaluation_equals_reference():
             n_tab += 1
         assert np.array_equal(o.eval_function(f, x), want), f
     assert n_tab > 0 and n_pol > 0
+
+
+@needs_ref
+def test_secondary_energy_laws_equal_reference():
+    """every reaction product of the synthetic library (level inelastic, Maxwell, evaporation,
+    Watt behind an isotropic UncorrelatedAngleEnergy) sampled by the reference's own
+    distribution_energy.cpp from the same seeds: identical mu, outgoing energy and seed
+    afterwards (the rejection loops consume the same random numbers)"""
+    import ctypes as C
+    from openmc_b200 import _abi as abi
+    model, box, of, libx = cases.build_ce(n_grid=2000)
+    L = C.CDLL(ref_geometry.LIB)
+    L.ref_geom_error.restype = C.c_char_p
+    o = Oracle(model)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    fn_ofs = np.asarray(model["fn_ofs"]); fn_type = np.asarray(model["fn_type"]); data = np.asarray(model["fn_data"])
+    elaw = np.asarray(model["prod_elaw"]); par = np.asarray(model["prod_par"]).reshape(-1, 2)
+    pfn = np.asarray(model["prod_fn"]).reshape(-1, 2)
+    g = np.random.default_rng(11)
+    seen = set()
+    for prod in range(int(model["n_products"])):
+        law = int(elaw[prod])
+        if law == abi.OMCGPU_ELAW_NONE:
+            continue
+        tabs = []
+        ok = True
+        for k in range(2 if law == abi.OMCGPU_ELAW_WATT else (0 if law == abi.OMCGPU_ELAW_LEVEL else 1)):
+            f = int(pfn[prod, k])
+            if fn_type[f] != abi.OMCGPU_FN_TABULATED1D:
+                ok = False
+                break
+            d = data[fn_ofs[f]:fn_ofs[f + 1]]
+            tabs.append((np.ascontiguousarray(d[:d.size // 2]), np.ascontiguousarray(d[d.size // 2:])))
+        if not ok:
+            continue
+        while len(tabs) < 2:
+            tabs.append((np.zeros(1), np.zeros(1)))
+        n = 4000
+        lo = max(par[prod, 0] * 1.0001, 1e-3) + 1.0          # above the threshold / restriction energy
+        E_in = np.ascontiguousarray(np.exp(g.uniform(np.log(lo), np.log(1.9e7), n)))
+        seeds = g.integers(1, 2**63, n, dtype=np.uint64)
+        E_r = np.zeros(n); mu_r = np.zeros(n); s_r = np.zeros(n, np.uint64)
+        rc = L.ref_sample_energy_law(C.c_int(law), C.c_double(par[prod, 0]), C.c_double(par[prod, 1]),
+                                     p(tabs[0][0]), p(tabs[0][1]), C.c_int(tabs[0][0].size),
+                                     p(tabs[1][0]), p(tabs[1][1]), C.c_int(tabs[1][0].size),
+                                     C.c_int64(n), p(E_in), p(seeds), p(E_r), p(mu_r), p(s_r))
+        assert rc == 0, L.ref_geom_error()
+        E_o, mu_o, s_o = o.sample_product(prod, E_in, seeds)
+        assert np.array_equal(mu_o, mu_r) and np.array_equal(E_o, E_r) and np.array_equal(s_o, s_r), (prod, law)
+        seen.add(law)
+    assert abi.OMCGPU_ELAW_WATT in seen and len(seen) >= 2, seen
