@@ -2247,6 +2247,21 @@ int orc_distance_to_boundary(const double* xyz, const double* uvw, int64_t n, do
   return 0;
 }
 
+// sample_cxs_target_velocity (src/physics.cpp:990-1041) for n (E, u, seed) triples
+int orc_sample_cxs_target_velocity(double awr, double kT, int64_t n, const double* E, const double* uvw,
+  const uint64_t* seed_in, double* v_target, uint64_t* seed_out)
+{
+  for (int64_t k = 0; k < n; ++k) {
+    uint64_t seed = seed_in[k];
+    const Vec3 v = sample_cxs_target_velocity(awr, E[k], Vec3 {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]}, kT, &seed);
+    v_target[3 * k] = v.x;
+    v_target[3 * k + 1] = v.y;
+    v_target[3 * k + 2] = v.z;
+    seed_out[k] = seed;
+  }
+  return 0;
+}
+
 // ReactionProduct::sample of product `prod` of the loaded model (isotropic angle + energy law)
 int orc_sample_product(int prod, int64_t n, const double* E_in, const uint64_t* seed_in, double* E_out,
   double* mu_out, uint64_t* seed_out)

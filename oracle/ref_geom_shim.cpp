@@ -57,7 +57,20 @@
 #include "openmc/random_dist.h"
 #include "openmc/hdf5_interface.h"
 #include "openmc/lattice.h"
+#include "openmc/bank.h"
+#include "openmc/bremsstrahlung.h"
+#include "openmc/distribution_angle.h"
+#include "openmc/distribution_multi.h"
+#include "openmc/eigenvalue.h"
+#include "openmc/ifp.h"
 #include "openmc/material.h"
+#include "openmc/ncrystal_interface.h"
+#include "openmc/physics.h"
+#include "openmc/physics_common.h"
+#include "openmc/reaction.h"
+#include "openmc/reaction_product.h"
+#include "openmc/secondary_uncorrelated.h"
+#include "openmc/weight_windows.h"
 #include "openmc/mesh.h"
 #include "openmc/output.h"
 #include "openmc/timer.h"
@@ -200,6 +213,34 @@ bool photon_transport = false;
 int verbosity = 0;
 }
 
+// ---- filler for src/physics.cpp (compiled for sample_cxs_target_velocity; the collision
+//      chain itself needs fully built nuclides / materials and is not driven here) ----------
+double Reaction::xs(const NuclideMicroXS&) const { unreachable("Reaction::xs"); }
+void ReactionProduct::sample(double, double&, double&, uint64_t*) const { unreachable("ReactionProduct::sample"); }
+void ThermalData::sample(const NuclideMicroXS&, double, double*, double*, uint64_t*) { unreachable("ThermalData"); }
+void PhotonInteraction::compton_scatter(double, bool, double*, double*, int*, uint64_t*) const { unreachable("photon"); }
+double PhotonInteraction::rayleigh_scatter(double, uint64_t*) const { unreachable("photon"); }
+void PhotonInteraction::pair_production(double, double*, double*, double*, double*, uint64_t*) const { unreachable("photon"); }
+void PhotonInteraction::atomic_relaxation(int, Particle&) const { unreachable("photon"); }
+void NCrystalMat::scatter(Particle&) const { unreachable("ncrystal"); }
+double AngleDistribution::sample(double, uint64_t*) const { unreachable("AngleDistribution::sample"); }
+void thick_target_bremsstrahlung(Particle&, double*) { unreachable("bremsstrahlung"); }
+bool Particle::create_secondary(double, Direction, double, ParticleType) { unreachable("create_secondary"); }
+void Particle::write_restart() const {}
+void apply_weight_windows(Particle&) {}
+void ifp(const Particle&, int64_t) {}
+Direction isotropic_direction(uint64_t*) { unreachable("isotropic_direction"); }
+std::string reaction_name(int) { return ""; }
+void russian_roulette(Particle&, double) { unreachable("russian_roulette"); }
+double ufs_get_weight(const Particle&) { return 1.0; }
+alignas(16) char filler_ti_uae[64] asm("_ZTIN6openmc23UncorrelatedAngleEnergyE") = {0};
+namespace simulation {
+SharedArray<SourceSite> fission_bank;
+}
+extern "C" {
+double keff = 1.0;
+}
+
 void Particle::mark_as_lost(const char* message) { throw std::runtime_error(message); } // key function: emits the vtable
 void Particle::cross_vacuum_bc(const Surface&) {}
 void Particle::cross_reflective_bc(const Surface&, Direction) {}
@@ -225,6 +266,23 @@ vector<Library> libraries;
 std::unordered_map<std::string, int> element_map;
 } // namespace data
 namespace settings {
+bool create_fission_neutrons {true};
+ElectronTreatment electron_treatment {ElectronTreatment::LED};
+array<double, 4> energy_cutoff {0.0, 1000.0, 0.0, 0.0};
+array<double, 4> time_cutoff {INFTY, INFTY, INFTY, INFTY};
+double free_gas_threshold {400.0};
+bool ifp_on {false};
+int max_secondaries {10000};
+double res_scat_energy_min {0.01};
+double res_scat_energy_max {1000.0};
+ResScatMethod res_scat_method {ResScatMethod::rvs};
+bool survival_biasing {false};
+bool survival_normalization {false};
+bool ufs_on {false};
+bool use_decay_photons {false};
+double weight_cutoff {0.25};
+double weight_survive {1.0};
+bool weight_window_checkpoint_collision {true};
 bool create_delayed_neutrons {true};
 bool delayed_photon_scaling {true};
 bool res_scat_on {false};
@@ -620,6 +678,33 @@ int ref_sample_energy_law(int law, double par0, double par1, const double* x0, c
       case 3: E_out[k] = evap->Evaporation::sample(E_in[k], &seed); break;
       default: E_out[k] = watt->WattEnergy::sample(E_in[k], &seed); break;
       }
+      seed_out[k] = seed;
+    }
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+} // extern "C"
+
+// =============================================================================
+// Free-gas target velocity of elastic scattering: sample_cxs_target_velocity,
+// src/physics.cpp:990-1041 (constant cross section approximation).
+// =============================================================================
+extern "C" {
+
+int ref_sample_cxs_target_velocity(double awr, double kT, int64_t n, const double* E, const double* uvw,
+  const uint64_t* seed_in, double* v_target, uint64_t* seed_out)
+{
+  try {
+    for (int64_t k = 0; k < n; ++k) {
+      uint64_t seed = seed_in[k];
+      const Direction v = sample_cxs_target_velocity(awr, E[k], {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]}, kT, &seed);
+      v_target[3 * k] = v.x;
+      v_target[3 * k + 1] = v.y;
+      v_target[3 * k + 2] = v.z;
       seed_out[k] = seed;
     }
   } catch (const std::exception& e) {

@@ -149,3 +149,29 @@ def test_secondary_energy_laws_equal_reference():
         assert np.array_equal(mu_o, mu_r) and np.array_equal(E_o, E_r) and np.array_equal(s_o, s_r), (prod, law)
         seen.add(law)
     assert abi.OMCGPU_ELAW_WATT in seen and len(seen) >= 2, seen
+
+
+@needs_ref
+def test_free_gas_target_velocity_equals_reference():
+    """sample_cxs_target_velocity of the reference's src/physics.cpp (compiled unmodified):
+    the rejection loop of the free-gas kernel consumes the same random numbers and returns the
+    identical target velocity -- light and heavy targets, thermal to epithermal energies"""
+    import ctypes as C
+    model, box, of, libx = cases.build_ce(n_grid=500)
+    L = C.CDLL(ref_geometry.LIB)
+    o = Oracle(model); o.load()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    g = np.random.default_rng(17)
+    n = 20000
+    kT = 0.0253
+    for awr in (0.9992, 15.86, 236.0):
+        E = np.ascontiguousarray(np.exp(g.uniform(np.log(1e-4), np.log(400 * kT), n)))
+        u = g.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
+        u = np.ascontiguousarray(u)
+        seeds = g.integers(1, 2**63, n, dtype=np.uint64)
+        out = []
+        for fn in (L.ref_sample_cxs_target_velocity, o.lib.orc_sample_cxs_target_velocity):
+            v = np.zeros((n, 3)); s = np.zeros(n, np.uint64)
+            assert fn(C.c_double(awr), C.c_double(kT), C.c_int64(n), p(E), p(u), p(seeds), p(v), p(s)) == 0
+            out.append((v, s))
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), awr
