@@ -114,6 +114,16 @@ class Oracle:
                                   C.c_int32(max_nuc))
         return out, ig
 
+    def geom_track(self, xyz, uvw, steps):
+        self.load()
+        xyz = np.ascontiguousarray(xyz, np.float64); uvw = np.ascontiguousarray(uvw, np.float64)
+        n = xyz.shape[0]
+        cid = np.zeros((n, steps), np.int32); mat = np.zeros((n, steps), np.int32)
+        nco = np.zeros((n, steps), np.int32); d = np.zeros((n, steps))
+        self.lib.orc_geom_track(C.c_int64(n), _p(xyz, C.c_double), _p(uvw, C.c_double), C.c_int(steps),
+                                _p(cid, C.c_int32), _p(mat, C.c_int32), _p(nco, C.c_int32), _p(d, C.c_double))
+        return cid, mat, nco, d
+
     def sample_product(self, prod, E_in, seeds):
         self.load()
         E_in = np.ascontiguousarray(E_in, np.float64); seeds = np.ascontiguousarray(seeds, np.uint64)

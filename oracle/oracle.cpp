@@ -2247,6 +2247,47 @@ int orc_distance_to_boundary(const double* xyz, const double* uvw, int64_t n, do
   return 0;
 }
 
+// Straight-line tracking with the crossing logic of event_cross_surface (transmission
+// surfaces and lattice boundaries; a track ends at a surface with a boundary condition).
+// per step: cell id (-1 ended at a BC, -2 lost), material, depth, flight distance.
+int orc_geom_track(int64_t n, const double* xyz, const double* uvw, int steps, int32_t* cell_id,
+  int32_t* material, int32_t* n_coord, double* distance)
+{
+  for (int64_t k = 0; k < n; ++k) {
+    for (int s = 0; s < steps; ++s) {
+      cell_id[k * steps + s] = -1;
+      material[k * steps + s] = -1;
+      n_coord[k * steps + s] = 0;
+      distance[k * steps + s] = 0.0;
+    }
+    Particle p;
+    p.r() = {xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2]};
+    p.u() = {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]};
+    if (!exhaustive_find_cell(p))
+      continue;
+    for (int s = 0; s < steps; ++s) {
+      p.boundary = distance_to_boundary(p);
+      if (!(p.boundary.distance < 1e30))
+        break;
+      for (int j = 0; j < p.n_coord; ++j)
+        p.coord[j].r = p.coord[j].r + p.boundary.distance * p.coord[j].u;
+      const bool lattice = p.boundary.lat_trans[0] != 0 || p.boundary.lat_trans[1] != 0 || p.boundary.lat_trans[2] != 0;
+      if (!lattice && M->surf_bc[std::abs(p.boundary.surface) - 1] != OMCGPU_BC_NONE)
+        break; // ended at a boundary condition
+      event_cross_surface(p);
+      distance[k * steps + s] = p.boundary.distance;
+      if (p.lost) {
+        cell_id[k * steps + s] = -2;
+        break;
+      }
+      cell_id[k * steps + s] = M->cell_id[p.coord[p.n_coord - 1].cell];
+      material[k * steps + s] = p.material;
+      n_coord[k * steps + s] = p.n_coord;
+    }
+  }
+  return 0;
+}
+
 // sample_cxs_target_velocity (src/physics.cpp:990-1041) for n (E, u, seed) triples
 int orc_sample_cxs_target_velocity(double awr, double kT, int64_t n, const double* E, const double* uvw,
   const uint64_t* seed_in, double* v_target, uint64_t* seed_out)

@@ -715,3 +715,81 @@ int ref_sample_cxs_target_velocity(double awr, double kT, int64_t n, const doubl
 }
 
 } // extern "C"
+
+// =============================================================================
+// Straight-line tracking through the geometry with the reference's own crossing logic:
+// distance_to_boundary, GeometryState::move_distance, and then what
+// Particle::event_cross_surface does (src/particle.cpp:288-329) -- cross_lattice
+// (src/geometry.cpp:301-357) for a lattice boundary; for a transmission surface the
+// neighbour-list search, the exhaustive fallback and the TINY_BIT nudge of
+// Particle::cross_surface (src/particle.cpp:549-629).  A track ends at a surface with a
+// boundary condition (those are pinned separately) or when the particle is lost.
+// per step: cell id (-1 ended at a BC, -2 lost), material, depth, flight distance.
+// =============================================================================
+extern "C" {
+
+int ref_geom_track(int64_t n, const double* xyz, const double* uvw, int steps, int32_t* cell_id, int32_t* material,
+  int32_t* n_coord, double* distance)
+{
+  try {
+    GeometryState p;
+    for (int64_t k = 0; k < n; ++k) {
+      for (int s = 0; s < steps; ++s) {
+        cell_id[k * steps + s] = -1;
+        material[k * steps + s] = -1;
+        n_coord[k * steps + s] = 0;
+        distance[k * steps + s] = 0.0;
+      }
+      p.init_from_r_u({xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2]}, {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]});
+      if (!exhaustive_find_cell(p))
+        continue;
+      for (int s = 0; s < steps; ++s) {
+        const BoundaryInfo b = distance_to_boundary(p);
+        if (!(b.distance() < 1e30))
+          break;
+        p.move_distance(b.distance());
+        for (int j = 0; j < p.n_coord(); ++j)
+          p.cell_last(j) = p.coord(j).cell();
+        p.n_coord_last() = p.n_coord();
+        p.surface() = b.surface();
+        p.n_coord() = b.coord_level();
+        bool lost = false;
+        if (b.lattice_translation()[0] != 0 || b.lattice_translation()[1] != 0 || b.lattice_translation()[2] != 0) {
+          try {
+            cross_lattice(p, b);
+          } catch (const std::exception&) { // mark_as_lost of a GeometryState throws in this build
+            lost = true;
+          }
+        } else {
+          const auto& surf = *model::surfaces[std::abs(p.surface()) - 1];
+          if (surf.bc_)
+            break; // ended at a boundary condition
+          if (!neighbor_list_find_cell(p)) {
+            p.n_coord() = 1;
+            if (!exhaustive_find_cell(p)) {
+              p.surface() = SURFACE_NONE;
+              p.n_coord() = 1;
+              p.r() += TINY_BIT * p.u();
+              if (!exhaustive_find_cell(p))
+                lost = true;
+            }
+          }
+        }
+        distance[k * steps + s] = b.distance();
+        if (lost) {
+          cell_id[k * steps + s] = -2;
+          break;
+        }
+        cell_id[k * steps + s] = model::cells[p.lowest_coord().cell()]->id_;
+        material[k * steps + s] = p.material();
+        n_coord[k * steps + s] = p.n_coord();
+      }
+    }
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+} // extern "C"

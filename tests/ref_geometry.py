@@ -96,6 +96,17 @@ class ReferenceGeometry:
             raise RuntimeError(self.lib.ref_geom_error().decode())
         return cid, inst, mat, nco
 
+    def track(self, xyz, uvw, steps):
+        """straight-line tracking with the reference's crossing logic (ref_geom_track)"""
+        xyz = np.ascontiguousarray(xyz, np.float64); uvw = np.ascontiguousarray(uvw, np.float64)
+        n = xyz.shape[0]
+        cid = np.zeros((n, steps), np.int32); mat = np.zeros((n, steps), np.int32)
+        nco = np.zeros((n, steps), np.int32); d = np.zeros((n, steps))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        if self.lib.ref_geom_track(C.c_int64(n), p(xyz), p(uvw), C.c_int(steps), p(cid), p(mat), p(nco), p(d)):
+            raise RuntimeError(self.lib.ref_geom_error().decode())
+        return cid, mat, nco, d
+
     def periodic(self, token, xyz, uvw):
         """what the reference's periodic BC does to particles that struck surface `token`
         (signed index + 1): new positions and new surface tokens (0: not a periodic surface)"""

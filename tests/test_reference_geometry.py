@@ -47,6 +47,23 @@ def test_oracle_geometry_equals_reference(name):
 
 
 @needs_ref
+@pytest.mark.parametrize("name", ["assembly_ce", "c5g7_core", "pwr_core_ce", "rotated_fills", "surface_zoo"])
+def test_tracking_through_the_geometry_equals_reference(name):
+    """straight-line tracks driven by the reference's own crossing logic (cross_lattice, the
+    neighbour-list search with its exhaustive fallback): after every crossing the oracle is in
+    the same cell, material and depth, and flies the identical distance"""
+    m, model, box = rc.build(name)
+    ref = ref_geometry.ReferenceGeometry(m)
+    xyz, uvw = rc.probe_points(box, 4000, seed=41)
+    steps = 30
+    cr, mr, nr, dr = ref.track(xyz, uvw, steps)
+    co, mo, no, do = Oracle(model).geom_track(xyz, uvw, steps)
+    assert np.count_nonzero(cr >= 0) > 2000
+    assert np.array_equal(co, cr) and np.array_equal(mo, mr) and np.array_equal(no, nr)
+    assert np.array_equal(do, dr)
+
+
+@needs_ref
 def test_periodic_boundary_equals_reference():
     """TranslationalPeriodicBC::handle_particle of the reference (pairs given by id, the two
     unpaired surfaces paired up, general planes with a non-unit normal): the flattener's partner table and
