@@ -2247,6 +2247,26 @@ int orc_distance_to_boundary(const double* xyz, const double* uvw, int64_t n, do
   return 0;
 }
 
+// the reflected direction of ReflectiveBC (the arithmetic of cross_surface's reflective branch)
+int orc_reflect(int64_t n, const int32_t* surface, const double* xyz, const double* uvw, double* new_uvw)
+{
+  for (int64_t k = 0; k < n; ++k) {
+    const int s = std::abs(surface[k]) - 1;
+    Vec3 r {xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2]};
+    Vec3 u {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]};
+    Vec3 nrm = surf_normal(s, r);
+    const double projection = dot(nrm, u);
+    const double magnitude = dot(nrm, nrm);
+    nrm = nrm * (2.0 * projection / magnitude);
+    u = u - nrm;
+    u = u / norm(u);
+    new_uvw[3 * k] = u.x;
+    new_uvw[3 * k + 1] = u.y;
+    new_uvw[3 * k + 2] = u.z;
+  }
+  return 0;
+}
+
 // Straight-line tracking with the crossing logic of event_cross_surface (transmission
 // surfaces and lattice boundaries; a track ends at a surface with a boundary condition).
 // per step: cell id (-1 ended at a BC, -2 lost), material, depth, flight distance.

@@ -241,12 +241,16 @@ extern "C" {
 double keff = 1.0;
 }
 
-void Particle::mark_as_lost(const char* message) { throw std::runtime_error(message); } // key function: emits the vtable
-void Particle::cross_vacuum_bc(const Surface&) {}
-void Particle::cross_reflective_bc(const Surface&, Direction) {}
-// records what the reference's periodic boundary condition hands to the particle
 static double g_bc_r[3], g_bc_u[3];
 static int g_bc_surface = 0;
+void Particle::mark_as_lost(const char* message) { throw std::runtime_error(message); } // key function: emits the vtable
+void Particle::cross_vacuum_bc(const Surface&) {}
+void Particle::cross_reflective_bc(const Surface&, Direction new_u)
+{ // records what the reference's reflective boundary condition hands to the particle
+  g_bc_u[0] = new_u.x; g_bc_u[1] = new_u.y; g_bc_u[2] = new_u.z;
+  g_bc_surface = 1;
+}
+// (g_bc_r / g_bc_u / g_bc_surface: what a boundary condition handed to the particle)
 void Particle::cross_periodic_bc(const Surface&, Position new_r, Direction new_u, int new_surface)
 {
   g_bc_r[0] = new_r.x; g_bc_r[1] = new_r.y; g_bc_r[2] = new_r.z;
@@ -370,6 +374,30 @@ int ref_geom_periodic(int64_t n, const int32_t* token, const double* xyz, const 
       new_token[k] = g_bc_surface;
       for (int d = 0; d < 3; ++d)
         new_xyz[3 * k + d] = g_bc_surface ? g_bc_r[d] : xyz[3 * k + d];
+    }
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+// ReflectiveBC::handle_particle (src/boundary_condition.cpp:48-61: Surface::reflect, then
+// normalisation) of the surface struck: the new direction (unchanged for other surfaces)
+int ref_geom_reflect(int64_t n, const int32_t* token, const double* xyz, const double* uvw, double* new_uvw)
+{
+  try {
+    Particle p;
+    for (int64_t k = 0; k < n; ++k) {
+      const auto& surf = *model::surfaces[std::abs(token[k]) - 1];
+      p.r() = {xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2]};
+      p.u() = {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]};
+      p.surface() = token[k];
+      g_bc_surface = 0;
+      if (surf.bc_ && surf.bc_->type() == "reflective")
+        surf.bc_->handle_particle(p, surf);
+      for (int d = 0; d < 3; ++d)
+        new_uvw[3 * k + d] = g_bc_surface ? g_bc_u[d] : uvw[3 * k + d];
     }
   } catch (const std::exception& e) {
     std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());

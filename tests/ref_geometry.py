@@ -107,6 +107,16 @@ class ReferenceGeometry:
             raise RuntimeError(self.lib.ref_geom_error().decode())
         return cid, mat, nco, d
 
+    def reflect(self, token, xyz, uvw):
+        """new directions from the reference's ReflectiveBC for particles on surface `token`"""
+        token = np.ascontiguousarray(token, np.int32)
+        xyz = np.ascontiguousarray(xyz, np.float64); uvw = np.ascontiguousarray(uvw, np.float64)
+        new = np.zeros_like(uvw)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        if self.lib.ref_geom_reflect(C.c_int64(token.size), p(token), p(xyz), p(uvw), p(new)):
+            raise RuntimeError(self.lib.ref_geom_error().decode())
+        return new
+
     def periodic(self, token, xyz, uvw):
         """what the reference's periodic BC does to particles that struck surface `token`
         (signed index + 1): new positions and new surface tokens (0: not a periodic surface)"""

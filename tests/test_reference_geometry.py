@@ -64,6 +64,34 @@ def test_tracking_through_the_geometry_equals_reference(name):
 
 
 @needs_ref
+def test_reflective_boundary_equals_reference():
+    """ReflectiveBC::handle_particle of the reference on every surface kind (planes, general
+    plane, cylinders, spheres, cones made reflective for the purpose): identical new directions"""
+    import ctypes as C
+    import copy
+    from openmc_b200 import examples, mgxs
+    m, lib_, box, of = examples.surface_zoo()
+    m = copy.deepcopy(m)
+    for s in m.surfaces:
+        s.boundary = "reflective"
+    model = mgxs.build_mg_model(m, lib_)
+    ref = ref_geometry.ReferenceGeometry(m)
+    o = Oracle(model); o.load()
+    g = np.random.default_rng(8)
+    n = 9000
+    xyz = np.ascontiguousarray(g.uniform(-8, 8, size=(n, 3)))
+    uvw = g.normal(size=(n, 3)); uvw /= np.linalg.norm(uvw, axis=1)[:, None]
+    uvw = np.ascontiguousarray(uvw)
+    tok = ((np.arange(n) % len(m.surfaces)) + 1).astype(np.int32) * g.choice([-1, 1], n).astype(np.int32)
+    want = ref.reflect(tok, xyz, uvw)
+    got = np.zeros_like(uvw)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert o.lib.orc_reflect(C.c_int64(n), p(np.ascontiguousarray(tok)), p(xyz), p(uvw), p(got)) == 0
+    assert np.array_equal(got, want)
+    assert not np.array_equal(want, uvw)
+
+
+@needs_ref
 def test_periodic_boundary_equals_reference():
     """TranslationalPeriodicBC::handle_particle of the reference (pairs given by id, the two
     unpaired surfaces paired up, general planes with a non-unit normal): the flattener's partner table and
