@@ -2323,6 +2323,27 @@ int orc_sample_cxs_target_velocity(double awr, double kT, int64_t n, const doubl
   return 0;
 }
 
+// elastic_scatter (src/physics.cpp:754-818) off nuclide `nuc` of the loaded model
+int orc_elastic_scatter(int nuc, double kT, int64_t n, const double* E, const double* uvw,
+  const uint64_t* seed_in, double* E_out, double* uvw_out, double* mu_out, uint64_t* seed_out)
+{
+  for (int64_t k = 0; k < n; ++k) {
+    Particle p;
+    p.E = E[k];
+    p.u() = {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]};
+    p.stream = 0;
+    p.seeds[0] = seed_in[k];
+    ce_elastic_scatter(nuc, kT, p);
+    E_out[k] = p.E;
+    uvw_out[3 * k] = p.u().x;
+    uvw_out[3 * k + 1] = p.u().y;
+    uvw_out[3 * k + 2] = p.u().z;
+    mu_out[k] = p.mu;
+    seed_out[k] = p.seeds[0];
+  }
+  return 0;
+}
+
 // ReactionProduct::sample of product `prod` of the loaded model (isotropic angle + energy law)
 int orc_sample_product(int prod, int64_t n, const double* E_in, const uint64_t* seed_in, double* E_out,
   double* mu_out, uint64_t* seed_out)

@@ -223,7 +223,6 @@ double PhotonInteraction::rayleigh_scatter(double, uint64_t*) const { unreachabl
 void PhotonInteraction::pair_production(double, double*, double*, double*, double*, uint64_t*) const { unreachable("photon"); }
 void PhotonInteraction::atomic_relaxation(int, Particle&) const { unreachable("photon"); }
 void NCrystalMat::scatter(Particle&) const { unreachable("ncrystal"); }
-double AngleDistribution::sample(double, uint64_t*) const { unreachable("AngleDistribution::sample"); }
 void thick_target_bremsstrahlung(Particle&, double*) { unreachable("bremsstrahlung"); }
 bool Particle::create_secondary(double, Direction, double, ParticleType) { unreachable("create_secondary"); }
 void Particle::write_restart() const {}
@@ -233,7 +232,6 @@ Direction isotropic_direction(uint64_t*) { unreachable("isotropic_direction"); }
 std::string reaction_name(int) { return ""; }
 void russian_roulette(Particle&, double) { unreachable("russian_roulette"); }
 double ufs_get_weight(const Particle&) { return 1.0; }
-alignas(16) char filler_ti_uae[64] asm("_ZTIN6openmc23UncorrelatedAngleEnergyE") = {0};
 namespace simulation {
 SharedArray<SourceSite> fission_bank;
 }
@@ -812,6 +810,68 @@ int ref_geom_track(int64_t n, const double* xyz, const double* uvw, int steps, i
         material[k * steps + s] = p.material();
         n_coord[k * steps + s] = p.n_coord();
       }
+    }
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+} // extern "C"
+
+// =============================================================================
+// Elastic scattering kinematics: elastic_scatter of src/physics.cpp:754-818 (target
+// velocity :836-866, free-gas kernel :990-1041, CM <-> LAB transforms, rotate_angle) on a
+// hand-made nuclide (awr, non-resonant) and an elastic reaction whose only product carries
+// an isotropic UncorrelatedAngleEnergy -- built by the reference's OWN constructor: with
+// the HDF5 stand-ins reporting "no angle / energy group" it yields exactly that.
+// =============================================================================
+extern "C" {
+
+int ref_elastic_scatter(double awr, double kT, int64_t n, const double* E, const double* uvw,
+  const uint64_t* seed_in, double* E_out, double* uvw_out, double* mu_out, uint64_t* seed_out)
+{
+  try {
+    for (auto& u : data::nuclides)
+      u.release();
+    data::nuclides.clear();
+    const double grid[2] = {1.0e-5, 2.0e7};
+    const double xs4[8] = {1, 0, 0, 0, 1, 0, 0, 0};
+    data::nuclides.emplace_back(make_nuclide(0, 2, grid, xs4, false, kT));
+    data::nuclides[0]->awr_ = awr;
+    settings::free_gas_threshold = 400.0;
+    // the reaction: raw storage, one product with one isotropic distribution
+    static Reaction* rx = nullptr;
+    if (!rx) {
+      rx = static_cast<Reaction*>(::operator new(sizeof(Reaction)));
+      std::memset(static_cast<void*>(rx), 0, sizeof(Reaction));
+      rx->mt_ = 2;
+      rx->scatter_in_cm_ = true;
+      auto* prod = static_cast<ReactionProduct*>(::operator new(sizeof(ReactionProduct)));
+      std::memset(static_cast<void*>(prod), 0, sizeof(ReactionProduct));
+      prod->distribution_.push_back(std::make_unique<UncorrelatedAngleEnergy>(hid_t(0)));
+      // products_ = {prod}: libstdc++'s vector is three pointers (begin, end, end of storage)
+      ReactionProduct* three[3] = {prod, prod + 1, prod + 1};
+      std::memcpy(static_cast<void*>(&rx->products_), three, sizeof(three));
+    }
+    if (model::n_coord_levels < 1)
+      model::n_coord_levels = 1; // no geometry loaded: the particle still needs its base coordinate level
+    Particle p;
+    p.stream() = STREAM_TRACKING;
+    for (int64_t k = 0; k < n; ++k) {
+      p.E() = E[k];
+      p.u() = {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]};
+      p.seeds(STREAM_TRACKING) = seed_in[k];
+      p.neutron_xs(0).use_ptable = false;
+      p.neutron_xs(0).elastic = 1.0;
+      elastic_scatter(0, *rx, kT, p);
+      E_out[k] = p.E();
+      uvw_out[3 * k] = p.u().x;
+      uvw_out[3 * k + 1] = p.u().y;
+      uvw_out[3 * k + 2] = p.u().z;
+      mu_out[k] = p.mu();
+      seed_out[k] = p.seeds(STREAM_TRACKING);
     }
   } catch (const std::exception& e) {
     std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());

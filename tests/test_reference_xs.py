@@ -175,3 +175,35 @@ def test_free_gas_target_velocity_equals_reference():
             assert fn(C.c_double(awr), C.c_double(kT), C.c_int64(n), p(E), p(u), p(seeds), p(v), p(s)) == 0
             out.append((v, s))
         assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]), awr
+
+
+@needs_ref
+def test_elastic_scattering_equals_reference():
+    """elastic_scatter of the reference's src/physics.cpp (target velocity with its threshold
+    for a target at rest, CM <-> LAB transforms, isotropic CM angle, rotate_angle) against the
+    oracle's restatement for every nuclide of the synthetic library: identical outgoing
+    energy, direction, lab cosine and seed -- thermal energies (free gas) up to 1 MeV"""
+    import ctypes as C
+    model, box, of, libx = cases.build_ce(n_grid=500)
+    L = C.CDLL(ref_geometry.LIB)
+    L.ref_geom_error.restype = C.c_char_p
+    o = Oracle(model); o.load()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    g = np.random.default_rng(23)
+    n = 20000
+    kT = 0.0253
+    awrs = np.asarray(model["nuc_awr"])
+    for nuc in range(int(model["n_nuclides"])):
+        E = np.ascontiguousarray(np.exp(g.uniform(np.log(1e-4), np.log(1e6), n)))
+        u = g.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
+        u = np.ascontiguousarray(u)
+        seeds = g.integers(1, 2**63, n, dtype=np.uint64)
+        res = []
+        for fn, first in ((L.ref_elastic_scatter, C.c_double(float(awrs[nuc]))), (o.lib.orc_elastic_scatter, C.c_int(nuc))):
+            Eo = np.zeros(n); uo = np.zeros((n, 3)); mu = np.zeros(n); so = np.zeros(n, np.uint64)
+            rc = fn(first, C.c_double(kT), C.c_int64(n), p(E), p(u), p(seeds), p(Eo), p(uo), p(mu), p(so))
+            assert rc == 0, L.ref_geom_error()
+            res.append((Eo, uo, mu, so))
+        for a, b in zip(res[0], res[1]):
+            assert np.array_equal(a, b), (nuc, float(awrs[nuc]))
+    # (afterwards the reference library holds the one hand-made nuclide; ReferenceXS reloads its own)
