@@ -2344,6 +2344,54 @@ int orc_elastic_scatter(int nuc, double kT, int64_t n, const double* E, const do
   return 0;
 }
 
+// inelastic_scatter (src/physics.cpp:1119-1167) through reaction `rx` (global index) of nuclide `nuc`
+int orc_inelastic_scatter(int nuc, int rx, int64_t n, const double* E, const double* uvw,
+  const uint64_t* seed_in, double* E_out, double* uvw_out, double* mu_out, double* wgt_out, uint64_t* seed_out)
+{
+  for (int64_t k = 0; k < n; ++k) {
+    Particle p;
+    p.E = E[k];
+    p.wgt = 1.0;
+    p.u() = {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]};
+    p.stream = 0;
+    p.seeds[0] = seed_in[k];
+    ce_inelastic_scatter(nuc, rx, p);
+    E_out[k] = p.E;
+    uvw_out[3 * k] = p.u().x;
+    uvw_out[3 * k + 1] = p.u().y;
+    uvw_out[3 * k + 2] = p.u().z;
+    mu_out[k] = p.mu;
+    wgt_out[k] = p.wgt;
+    seed_out[k] = p.seeds[0];
+  }
+  return 0;
+}
+
+// sample_fission_neutron (src/physics.cpp:1043-1117) of nuclide `nuc`, fission reaction `rx` (global index)
+int orc_fission_neutron(int nuc, int rx, int64_t n, const double* E, const double* uvw,
+  const uint64_t* seed_in, double* E_out, double* uvw_out, int32_t* group_out, double* time_out,
+  uint64_t* seed_out)
+{
+  for (int64_t k = 0; k < n; ++k) {
+    Particle p;
+    p.E = E[k];
+    p.u() = {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]};
+    p.stream = 0;
+    p.seeds[0] = seed_in[k];
+    omcgpu_site site;
+    std::memset(&site, 0, sizeof(site));
+    ce_sample_fission_neutron(nuc, rx, &site, p);
+    E_out[k] = site.E;
+    uvw_out[3 * k] = site.u[0];
+    uvw_out[3 * k + 1] = site.u[1];
+    uvw_out[3 * k + 2] = site.u[2];
+    group_out[k] = site.delayed_group;
+    time_out[k] = site.time;
+    seed_out[k] = p.seeds[0];
+  }
+  return 0;
+}
+
 // ReactionProduct::sample of product `prod` of the loaded model (isotropic angle + energy law)
 int orc_sample_product(int prod, int64_t n, const double* E_in, const uint64_t* seed_in, double* E_out,
   double* mu_out, uint64_t* seed_out)

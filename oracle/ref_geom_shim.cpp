@@ -45,6 +45,7 @@
 #define private public
 #include "openmc/endf.h"
 #include "openmc/distribution_energy.h"
+#include "openmc/secondary_uncorrelated.h"
 #undef private
 
 #include "openmc/capi.h"
@@ -216,7 +217,9 @@ int verbosity = 0;
 // ---- filler for src/physics.cpp (compiled for sample_cxs_target_velocity; the collision
 //      chain itself needs fully built nuclides / materials and is not driven here) ----------
 double Reaction::xs(const NuclideMicroXS&) const { unreachable("Reaction::xs"); }
-void ReactionProduct::sample(double, double&, double&, uint64_t*) const { unreachable("ReactionProduct::sample"); }
+// ---- filler for src/reaction_product.cpp / src/chain.cpp (compiled for ReactionProduct::sample; their HDF5 / XML readers are not driven) ----
+int reaction_type(std::string) { unreachable("reaction_type"); }
+ParticleType str_to_particle_type(std::string) { unreachable("str_to_particle_type"); }
 void ThermalData::sample(const NuclideMicroXS&, double, double*, double*, uint64_t*) { unreachable("ThermalData"); }
 void PhotonInteraction::compton_scatter(double, bool, double*, double*, int*, uint64_t*) const { unreachable("photon"); }
 double PhotonInteraction::rayleigh_scatter(double, uint64_t*) const { unreachable("photon"); }
@@ -871,6 +874,186 @@ int ref_elastic_scatter(double awr, double kT, int64_t n, const double* E, const
       uvw_out[3 * k + 1] = p.u().y;
       uvw_out[3 * k + 2] = p.u().z;
       mu_out[k] = p.mu();
+      seed_out[k] = p.seeds(STREAM_TRACKING);
+    }
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+} // extern "C"
+
+// =============================================================================
+// Inelastic scattering and fission neutron emission through the reference's own
+// physics.cpp: inelastic_scatter (:1119-1167: ReactionProduct::sample, CM -> LAB, rotate_angle,
+// yield) and sample_fission_neutron (:1043-1117: Nuclide::nu total / delayed, precursor group,
+// emission time, energy resampling above the maximum, rotate_angle).  The reaction is hand
+// made: raw zeroed storage for Reaction / ReactionProduct (their only constructors read
+// HDF5), members filled in place; energy laws are copy-constructed from zeroed storage so
+// that they carry their vtable; the UncorrelatedAngleEnergy comes from its real constructor.
+// =============================================================================
+namespace {
+
+Reaction* g_rx = nullptr;
+ReactionProduct* g_prod = nullptr;
+int g_n_prod = 0;
+
+Function1D* make_fn(int is_polynomial, const double* d, int n)
+{
+  if (is_polynomial)
+    return new Polynomial(vector<double>(d, d + n));
+  auto* t = new Tabulated1D();
+  t->n_regions_ = 0;
+  t->n_pairs_ = n / 2;
+  t->x_.assign(d, d + n / 2);
+  t->y_.assign(d + n / 2, d + n);
+  return t;
+}
+
+template<class T>
+T* from_zero()
+{
+  alignas(16) static char z[sizeof(T)];
+  std::memset(z, 0, sizeof(T));
+  return new T(*reinterpret_cast<const T*>(z)); // the implicit copy constructor sets the vtable
+}
+
+} // namespace
+
+extern "C" {
+
+int ref_rx_begin(int scatter_in_cm, double awr, double kT, int n_precursor, int fissionable,
+  int total_nu_is_polynomial, const double* total_nu, int n_total_nu, int n_products, double e_max)
+{
+  try {
+    for (auto& u : data::nuclides)
+      u.release();
+    data::nuclides.clear();
+    const double grid[2] = {1.0e-5, 2.0e7};
+    const double xs4[8] = {1, 0, 0, 0, 1, 0, 0, 0};
+    data::nuclides.emplace_back(make_nuclide(0, 2, grid, xs4, fissionable != 0, kT));
+    Nuclide& nuc = *data::nuclides[0];
+    nuc.awr_ = awr;
+    nuc.n_precursor_ = n_precursor;
+    if (n_total_nu > 0)
+      nuc.total_nu_.reset(make_fn(total_nu_is_polynomial, total_nu, n_total_nu));
+    settings::create_delayed_neutrons = true;
+    data::energy_max[0] = e_max;
+    g_rx = static_cast<Reaction*>(::operator new(sizeof(Reaction))); // earlier ones are left alone
+    std::memset(static_cast<void*>(g_rx), 0, sizeof(Reaction));
+    g_rx->mt_ = fissionable ? 18 : 51;
+    g_rx->scatter_in_cm_ = scatter_in_cm != 0;
+    g_n_prod = n_products;
+    g_prod = static_cast<ReactionProduct*>(::operator new(sizeof(ReactionProduct) * n_products));
+    std::memset(static_cast<void*>(g_prod), 0, sizeof(ReactionProduct) * n_products);
+    ReactionProduct* three[3] = {g_prod, g_prod + n_products, g_prod + n_products};
+    std::memcpy(static_cast<void*>(&g_rx->products_), three, sizeof(three));
+    if (fissionable)
+      nuc.fission_rx_.push_back(g_rx);
+    if (model::n_coord_levels < 1)
+      model::n_coord_levels = 1;
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+// law as in ref_sample_energy_law; emission 0 prompt, 1 delayed, 2 total
+int ref_rx_product(int i, int law, double par0, double par1, const double* x0, const double* y0, int n0,
+  const double* x1, const double* y1, int n1, int yield_is_polynomial, const double* yield, int n_yield,
+  int emission, double decay_rate)
+{
+  try {
+    if (i < 0 || i >= g_n_prod)
+      throw std::runtime_error("product index");
+    ReactionProduct& prod = g_prod[i];
+    prod.particle_ = ParticleType::neutron;
+    prod.emission_mode_ = static_cast<ReactionProduct::EmissionMode>(emission);
+    prod.decay_rate_ = decay_rate;
+    prod.parent_nuclide_ = -1;
+    prod.yield_.reset(make_fn(yield_is_polynomial, yield, n_yield));
+    auto* uae = new UncorrelatedAngleEnergy(hid_t(0)); // "no angle / energy group": isotropic, no law yet
+    if (law == 1) {
+      auto* e = from_zero<LevelInelastic>();
+      e->threshold_ = par0;
+      e->mass_ratio_ = par1;
+      uae->energy_.reset(e);
+    } else if (law == 2) {
+      auto* e = from_zero<MaxwellEnergy>();
+      fill_tab(&e->theta_, x0, y0, n0);
+      e->u_ = par0;
+      uae->energy_.reset(e);
+    } else if (law == 3) {
+      auto* e = from_zero<Evaporation>();
+      fill_tab(&e->theta_, x0, y0, n0);
+      e->u_ = par0;
+      uae->energy_.reset(e);
+    } else if (law == 4) {
+      auto* e = from_zero<WattEnergy>();
+      fill_tab(&e->a_, x0, y0, n0);
+      fill_tab(&e->b_, x1, y1, n1);
+      e->u_ = par0;
+      uae->energy_.reset(e);
+    } else {
+      throw std::runtime_error("unknown energy law");
+    }
+    prod.distribution_.push_back(unique_ptr<AngleEnergy>(uae));
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+int ref_rx_inelastic(int64_t n, const double* E, const double* uvw, const uint64_t* seed_in, double* E_out,
+  double* uvw_out, double* mu_out, double* wgt_out, uint64_t* seed_out)
+{
+  try {
+    Particle p;
+    p.stream() = STREAM_TRACKING;
+    for (int64_t k = 0; k < n; ++k) {
+      p.E() = E[k];
+      p.wgt() = 1.0;
+      p.u() = {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]};
+      p.seeds(STREAM_TRACKING) = seed_in[k];
+      inelastic_scatter(*data::nuclides[0], *g_rx, p);
+      E_out[k] = p.E();
+      uvw_out[3 * k] = p.u().x;
+      uvw_out[3 * k + 1] = p.u().y;
+      uvw_out[3 * k + 2] = p.u().z;
+      mu_out[k] = p.mu();
+      wgt_out[k] = p.wgt();
+      seed_out[k] = p.seeds(STREAM_TRACKING);
+    }
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+int ref_rx_fission_neutron(int64_t n, const double* E, const double* uvw, const uint64_t* seed_in,
+  double* E_out, double* uvw_out, int32_t* group_out, double* time_out, uint64_t* seed_out)
+{
+  try {
+    Particle p;
+    p.stream() = STREAM_TRACKING;
+    for (int64_t k = 0; k < n; ++k) {
+      p.E() = E[k];
+      p.u() = {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]};
+      p.seeds(STREAM_TRACKING) = seed_in[k];
+      SourceSite site;
+      site.time = 0.0;
+      sample_fission_neutron(0, *g_rx, &site, p);
+      E_out[k] = site.E;
+      uvw_out[3 * k] = site.u.x;
+      uvw_out[3 * k + 1] = site.u.y;
+      uvw_out[3 * k + 2] = site.u.z;
+      group_out[k] = site.delayed_group;
+      time_out[k] = site.time;
       seed_out[k] = p.seeds(STREAM_TRACKING);
     }
   } catch (const std::exception& e) {

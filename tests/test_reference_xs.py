@@ -207,3 +207,100 @@ def test_elastic_scattering_equals_reference():
         for a, b in zip(res[0], res[1]):
             assert np.array_equal(a, b), (nuc, float(awrs[nuc]))
     # (afterwards the reference library holds the one hand-made nuclide; ReferenceXS reloads its own)
+
+
+def _reaction_into_reference(L, model, nuc, rx, fissionable):
+    """hand the products of reaction `rx` (global index) of nuclide `nuc` to the reference
+    library's hand-made Reaction; returns False when a law's parameter is not a table"""
+    import ctypes as C
+    from openmc_b200 import _abi as abi
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    fn_ofs = np.asarray(model["fn_ofs"]); fn_type = np.asarray(model["fn_type"]); data = np.asarray(model["fn_data"])
+    elaw = np.asarray(model["prod_elaw"]); par = np.asarray(model["prod_par"]).reshape(-1, 2)
+    pfn = np.asarray(model["prod_fn"]).reshape(-1, 2)
+    fn = lambda f: np.ascontiguousarray(data[fn_ofs[f]:fn_ofs[f + 1]])
+    p0, p1 = int(model["rx_prod_ofs"][rx]), int(model["rx_prod_ofs"][rx + 1])
+    tn = int(model["nuc_total_nu_fn"][nuc]) if fissionable else -1
+    tn_d = fn(tn) if tn >= 0 else np.zeros(1)
+    rc = L.ref_rx_begin(C.c_int(int(model["rx_scatter_in_cm"][rx])), C.c_double(float(model["nuc_awr"][nuc])),
+                        C.c_double(0.0253), C.c_int(int(model["nuc_n_precursor"][nuc])), C.c_int(int(fissionable)),
+                        C.c_int(int(tn >= 0 and fn_type[tn] == abi.OMCGPU_FN_POLYNOMIAL)), p(tn_d),
+                        C.c_int(tn_d.size if tn >= 0 else 0), C.c_int(p1 - p0), C.c_double(float(model["energy_max"])))
+    assert rc == 0, L.ref_geom_error()
+    for i, prod in enumerate(range(p0, p1)):
+        law = int(elaw[prod])
+        if law == abi.OMCGPU_ELAW_NONE:
+            return False
+        tabs = []
+        for k in range(2 if law == abi.OMCGPU_ELAW_WATT else (0 if law == abi.OMCGPU_ELAW_LEVEL else 1)):
+            f = int(pfn[prod, k])
+            if fn_type[f] != abi.OMCGPU_FN_TABULATED1D:
+                return False
+            d = fn(f)
+            tabs.append((np.ascontiguousarray(d[:d.size // 2]), np.ascontiguousarray(d[d.size // 2:])))
+        while len(tabs) < 2:
+            tabs.append((np.zeros(1), np.zeros(1)))
+        y = int(model["prod_yield_fn"][prod]); y_d = fn(y)
+        rc = L.ref_rx_product(C.c_int(i), C.c_int(law), C.c_double(par[prod, 0]), C.c_double(par[prod, 1]),
+                              p(tabs[0][0]), p(tabs[0][1]), C.c_int(tabs[0][0].size),
+                              p(tabs[1][0]), p(tabs[1][1]), C.c_int(tabs[1][0].size),
+                              C.c_int(int(fn_type[y] == abi.OMCGPU_FN_POLYNOMIAL)), p(y_d), C.c_int(y_d.size),
+                              C.c_int(int(model["prod_emission"][prod])), C.c_double(float(model["prod_decay_rate"][prod])))
+        assert rc == 0, L.ref_geom_error()
+    return True
+
+
+@needs_ref
+def test_inelastic_scattering_and_fission_emission_equal_reference():
+    """inelastic_scatter and sample_fission_neutron of the reference's src/physics.cpp (compiled
+    unmodified) on every inelastic and fission reaction of the synthetic library: outgoing
+    energy, direction, lab cosine, weight (yield), delayed group, emission time and the seed
+    afterwards are identical to the oracle's restatement -- Nuclide::nu total / delayed, the
+    precursor-group walk, ReactionProduct::sample, CM -> LAB, rotate_angle"""
+    import ctypes as C
+    model, box, of, libx = cases.build_ce(n_grid=500)
+    L = C.CDLL(ref_geometry.LIB)
+    L.ref_geom_error.restype = C.c_char_p
+    o = Oracle(model); o.load()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    g = np.random.default_rng(29)
+    n = 8000
+    n_inel = n_fis = n_delayed = 0
+    par = np.asarray(model["prod_par"]).reshape(-1, 2)
+    for nuc in range(int(model["n_nuclides"])):
+        r0, r1 = int(model["nuc_rx_ofs"][nuc]), int(model["nuc_rx_ofs"][nuc + 1])
+        fis = r0 + int(model["nuc_fission_rx"][nuc]) if int(model["nuc_fissionable"][nuc]) else -1
+        for rx in range(r0, r1):
+            is_fis = rx == fis
+            if not is_fis and not int(model["rx_inelastic"][rx]):
+                continue
+            if not _reaction_into_reference(L, model, nuc, rx, is_fis):
+                continue
+            prod0 = int(model["rx_prod_ofs"][rx])
+            n = 60000 if is_fis else 8000          # enough histories for a few hundred delayed neutrons
+            lo = max(par[prod0, 0] * 1.0001, 1e-3) + 1.0 if not is_fis else 1e-4
+            E = np.ascontiguousarray(np.exp(g.uniform(np.log(lo), np.log(1.9e7), n)))
+            u = g.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
+            u = np.ascontiguousarray(u)
+            seeds = g.integers(1, 2**63, n, dtype=np.uint64)
+            res = []
+            if is_fis:
+                for fn, head in ((L.ref_rx_fission_neutron, ()), (o.lib.orc_fission_neutron, (C.c_int(nuc), C.c_int(rx)))):
+                    Eo = np.zeros(n); uo = np.zeros((n, 3)); grp = np.zeros(n, np.int32); t = np.zeros(n)
+                    so = np.zeros(n, np.uint64)
+                    rc = fn(*head, C.c_int64(n), p(E), p(u), p(seeds), p(Eo), p(uo), p(grp), p(t), p(so))
+                    assert rc == 0, L.ref_geom_error()
+                    res.append((Eo, uo, grp, t, so))
+                n_fis += 1
+                n_delayed += int((res[0][2] > 0).sum())
+            else:
+                for fn, head in ((L.ref_rx_inelastic, ()), (o.lib.orc_inelastic_scatter, (C.c_int(nuc), C.c_int(rx)))):
+                    Eo = np.zeros(n); uo = np.zeros((n, 3)); mu = np.zeros(n); w = np.zeros(n); so = np.zeros(n, np.uint64)
+                    rc = fn(*head, C.c_int64(n), p(E), p(u), p(seeds), p(Eo), p(uo), p(mu), p(w), p(so))
+                    assert rc == 0, L.ref_geom_error()
+                    res.append((Eo, uo, mu, w, so))
+                n_inel += 1
+            for a, b in zip(res[0], res[1]):
+                assert np.array_equal(a, b), (nuc, rx, is_fis)
+    assert n_inel > 0 and n_fis > 0 and n_delayed > 50, (n_inel, n_fis, n_delayed)
+    print(f"reactions compared: {n_inel} inelastic, {n_fis} fission ({n_delayed} delayed neutrons)")
