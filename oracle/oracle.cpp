@@ -2344,6 +2344,51 @@ int orc_elastic_scatter(int nuc, double kT, int64_t n, const double* E, const do
   return 0;
 }
 
+// collision (src/physics.cpp:43-168) of n fresh neutrons of weight wgt0 in the loaded CE model; fission sites of
+// collision k are site_*[site_ofs[k] .. site_ofs[k+1])
+int64_t orc_collision(int64_t n, const int32_t* material, const double* E, const double* uvw,
+  const uint64_t* seed_in, double k_eff, double wgt0, double* E_out, double* uvw_out, double* wgt_out,
+  double* kabs_out, uint64_t* seed_out, int64_t* site_ofs, double* site_E, double* site_u, int32_t* site_group,
+  double* site_time, int64_t site_cap)
+{
+  RS.keff = k_eff;
+  RS.fission_capacity = 64;
+  int64_t total = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    Particle p;
+    p.E = E[k];
+    p.wgt = wgt0;
+    p.u() = {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]};
+    p.stream = 0;
+    p.seeds[0] = seed_in[k];
+    p.material = material[k];
+    RS.fission_bank.clear();
+    ce_calculate_xs(p);
+    collision_ce(p);
+    E_out[k] = p.E;
+    uvw_out[3 * k] = p.u().x;
+    uvw_out[3 * k + 1] = p.u().y;
+    uvw_out[3 * k + 2] = p.u().z;
+    wgt_out[k] = p.wgt;
+    kabs_out[k] = p.k_abs;
+    seed_out[k] = p.seeds[0];
+    site_ofs[k] = total;
+    if (total + (int64_t)RS.fission_bank.size() > site_cap)
+      return -1;
+    for (const auto& s : RS.fission_bank) {
+      site_E[total] = s.E;
+      site_u[3 * total] = s.u[0];
+      site_u[3 * total + 1] = s.u[1];
+      site_u[3 * total + 2] = s.u[2];
+      site_group[total] = s.delayed_group;
+      site_time[total] = s.time;
+      ++total;
+    }
+  }
+  site_ofs[n] = total;
+  return total;
+}
+
 // inelastic_scatter (src/physics.cpp:1119-1167) through reaction `rx` (global index) of nuclide `nuc`
 int orc_inelastic_scatter(int nuc, int rx, int64_t n, const double* E, const double* uvw,
   const uint64_t* seed_in, double* E_out, double* uvw_out, double* mu_out, double* wgt_out, uint64_t* seed_out)

@@ -195,11 +195,6 @@ std::tuple<double, double, double> WindowedMultipole::evaluate(double, double) c
 void ThermalScattering::calculate_xs(double, double, int*, double*, double*, uint64_t*) const { unreachable("sab"); }
 PhotonInteraction::PhotonInteraction(hid_t) { unreachable("PhotonInteraction"); }
 PhotonInteraction::~PhotonInteraction() {}
-Reaction::Reaction(hid_t, const vector<int>&, std::string) { unreachable("Reaction"); }
-double Reaction::collapse_rate(int64_t, span<const double>, span<const double>, const vector<double>&) const
-{
-  unreachable("collapse_rate");
-}
 namespace mpi {
 bool master {true};
 int rank {0};
@@ -214,11 +209,7 @@ bool photon_transport = false;
 int verbosity = 0;
 }
 
-// ---- filler for src/physics.cpp (compiled for sample_cxs_target_velocity; the collision
-//      chain itself needs fully built nuclides / materials and is not driven here) ----------
-double Reaction::xs(const NuclideMicroXS&) const { unreachable("Reaction::xs"); }
 // ---- filler for src/reaction_product.cpp / src/chain.cpp (compiled for ReactionProduct::sample; their HDF5 / XML readers are not driven) ----
-int reaction_type(std::string) { unreachable("reaction_type"); }
 ParticleType str_to_particle_type(std::string) { unreachable("str_to_particle_type"); }
 void ThermalData::sample(const NuclideMicroXS&, double, double*, double*, uint64_t*) { unreachable("ThermalData"); }
 void PhotonInteraction::compton_scatter(double, bool, double*, double*, int*, uint64_t*) const { unreachable("photon"); }
@@ -232,8 +223,6 @@ void Particle::write_restart() const {}
 void apply_weight_windows(Particle&) {}
 void ifp(const Particle&, int64_t) {}
 Direction isotropic_direction(uint64_t*) { unreachable("isotropic_direction"); }
-std::string reaction_name(int) { return ""; }
-void russian_roulette(Particle&, double) { unreachable("russian_roulette"); }
 double ufs_get_weight(const Particle&) { return 1.0; }
 namespace simulation {
 SharedArray<SourceSite> fission_bank;
@@ -997,7 +986,7 @@ int ref_rx_product(int i, int law, double par0, double par1, const double* x0, c
       fill_tab(&e->b_, x1, y1, n1);
       e->u_ = par0;
       uae->energy_.reset(e);
-    } else {
+    } else if (law != 0) { // 0: elastic, kinematics only (elastic_scatter reads the angle part alone)
       throw std::runtime_error("unknown energy law");
     }
     prod.distribution_.push_back(unique_ptr<AngleEnergy>(uae));
@@ -1061,6 +1050,173 @@ int ref_rx_fission_neutron(int64_t n, const double* E, const double* uvw, const 
     return -1;
   }
   return 0;
+}
+
+} // extern "C"
+
+// =============================================================================
+// The whole neutron collision, collision() of src/physics.cpp:43-168 -> sample_neutron_reaction
+// (:93-168): sample_nuclide, sample_fission + create_fission_sites, absorption, scatter
+// (elastic / inelastic channel walk over Reaction::xs of src/reaction.cpp), on hand-made
+// nuclides (ref_xs_load + the calls below) and hand-made materials.  The per-nuclide cache the
+// collision reads is filled by Nuclide::calculate_xs, the macroscopic total summed as
+// Material::calculate_neutron_xs does (src/material.cpp:829-901).
+// =============================================================================
+namespace {
+std::vector<Material*>& ref_materials()
+{ // model::materials is a vector of unique_ptr<Material>: same layout as a vector of plain pointers
+  return *reinterpret_cast<std::vector<Material*>*>(filler__ZN6openmc5model9materialsE);
+}
+} // namespace
+
+extern "C" {
+
+int ref_nuc_physics(int nuc, double awr, int n_precursor, int total_nu_is_polynomial, const double* total_nu,
+  int n_total_nu)
+{
+  Nuclide& n = *data::nuclides[nuc];
+  n.awr_ = awr;
+  n.n_precursor_ = n_precursor;
+  if (n_total_nu > 0)
+    n.total_nu_.reset(make_fn(total_nu_is_polynomial, total_nu, n_total_nu));
+  return 0;
+}
+
+// appends a reaction to nuclide `nuc` (the first one must be elastic) and makes it the one
+// ref_rx_product fills; xs = values from grid index `threshold` on
+int ref_nuc_reaction(int nuc, int mt, int scatter_in_cm, int inelastic, int is_fission, int threshold,
+  const double* xs, int64_t n_xs, int n_products)
+{
+  try {
+    Nuclide& n = *data::nuclides[nuc];
+    g_rx = static_cast<Reaction*>(::operator new(sizeof(Reaction)));
+    std::memset(static_cast<void*>(g_rx), 0, sizeof(Reaction));
+    g_rx->mt_ = mt;
+    g_rx->scatter_in_cm_ = scatter_in_cm != 0;
+    g_rx->xs_.emplace_back();
+    g_rx->xs_[0].threshold = threshold;
+    g_rx->xs_[0].value.assign(xs, xs + n_xs);
+    g_n_prod = n_products;
+    g_prod = static_cast<ReactionProduct*>(::operator new(sizeof(ReactionProduct) * std::max(n_products, 1)));
+    std::memset(static_cast<void*>(g_prod), 0, sizeof(ReactionProduct) * std::max(n_products, 1));
+    ReactionProduct* three[3] = {g_prod, g_prod + n_products, g_prod + n_products};
+    std::memcpy(static_cast<void*>(&g_rx->products_), three, sizeof(three));
+    if (inelastic)
+      n.index_inelastic_scatter_.push_back(n.reactions_.size());
+    if (is_fission)
+      n.fission_rx_.push_back(g_rx);
+    n.reactions_.emplace_back(g_rx);
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+int ref_materials_load(int n_mat, const int32_t* ofs, const int32_t* nuclide, const double* density)
+{
+  try {
+    auto& mats = ref_materials();
+    mats.clear(); // hand-made objects, never destroyed
+    for (int m = 0; m < n_mat; ++m) {
+      auto* mat = static_cast<Material*>(::operator new(sizeof(Material)));
+      std::memset(static_cast<void*>(mat), 0, sizeof(Material));
+      const int n = ofs[m + 1] - ofs[m];
+      mat->nuclide_.assign(nuclide + ofs[m], nuclide + ofs[m + 1]);
+      new (&mat->atom_density_) xt::xtensor<double, 1>(std::array<size_t, 1> {(size_t)n});
+      for (int i = 0; i < n; ++i)
+        mat->atom_density_(i) = density[ofs[m] + i];
+      mats.push_back(mat);
+    }
+    settings::run_mode = RunMode::EIGENVALUE;
+    settings::survival_biasing = false;
+    settings::create_delayed_neutrons = true;
+    settings::energy_cutoff[0] = 0.0;
+    if (model::n_coord_levels < 1)
+      model::n_coord_levels = 1;
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
+int ref_collision_settings(int survival_biasing, double weight_cutoff, double weight_survive)
+{
+  settings::survival_biasing = survival_biasing != 0;
+  settings::survival_normalization = false;
+  settings::weight_cutoff = weight_cutoff;
+  settings::weight_survive = weight_survive;
+  return 0;
+}
+
+// n collisions, each of a fresh neutron of weight wgt0; fission sites of collision k are
+// site_*[site_ofs[k] .. site_ofs[k+1])
+int64_t ref_collision(int64_t n, const int32_t* material, const double* E, const double* uvw,
+  const uint64_t* seed_in, double k_eff, double wgt0, double* E_out, double* uvw_out, double* wgt_out, double* kabs_out,
+  int32_t* nuclide_out, int32_t* mt_out, uint64_t* seed_out, int64_t* site_ofs, double* site_E,
+  double* site_u, int32_t* site_group, double* site_time, int64_t site_cap)
+{
+  try {
+    simulation::keff = k_eff;
+    simulation::fission_bank.reserve(64);
+    int64_t total = 0;
+    Particle p;
+    p.stream() = STREAM_TRACKING;
+    for (int64_t k = 0; k < n; ++k) {
+      p.E() = E[k];
+      p.E_last() = E[k];
+      p.wgt() = wgt0;
+      p.wgt_born() = 1.0;
+      p.time() = 0.0;
+      p.u() = {uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]};
+      p.seeds(STREAM_TRACKING) = seed_in[k];
+      p.material() = material[k];
+      p.fission() = false;
+      p.n_progeny() = 0;
+      p.keff_tally_absorption() = 0.0;
+      p.event_mt() = 0;
+      simulation::fission_bank.resize(0);
+      const Material& mat = *ref_materials()[material[k]];
+      const int i_log_union = std::log(p.E() / data::energy_min[0]) / simulation::log_spacing;
+      double total_xs = 0.0;
+      for (size_t i = 0; i < mat.nuclide_.size(); ++i) {
+        const int i_nuc = mat.nuclide_[i];
+        data::nuclides[i_nuc]->calculate_xs(C_NONE, i_log_union, 0.0, p);
+        total_xs += mat.atom_density_(i) * p.neutron_xs(i_nuc).total;
+      }
+      p.macro_xs().total = total_xs;
+      collision(p);
+      E_out[k] = p.E();
+      uvw_out[3 * k] = p.u().x;
+      uvw_out[3 * k + 1] = p.u().y;
+      uvw_out[3 * k + 2] = p.u().z;
+      wgt_out[k] = p.wgt();
+      kabs_out[k] = p.keff_tally_absorption();
+      nuclide_out[k] = p.event_nuclide();
+      mt_out[k] = p.event_mt();
+      seed_out[k] = p.seeds(STREAM_TRACKING);
+      site_ofs[k] = total;
+      const int64_t ns = simulation::fission_bank.size();
+      if (total + ns > site_cap)
+        throw std::runtime_error("site capacity");
+      for (int64_t j = 0; j < ns; ++j) {
+        const SourceSite& s = simulation::fission_bank[j];
+        site_E[total] = s.E;
+        site_u[3 * total] = s.u.x;
+        site_u[3 * total + 1] = s.u.y;
+        site_u[3 * total + 2] = s.u.z;
+        site_group[total] = s.delayed_group;
+        site_time[total] = s.time;
+        ++total;
+      }
+    }
+    site_ofs[n] = total;
+    return total;
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
 }
 
 } // extern "C"
