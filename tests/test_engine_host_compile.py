@@ -142,3 +142,35 @@ def test_surface_zoo_generation_matches_oracle(emu_lib, case, threshold, monkeyp
         assert np.array_equal(fb[f], fb_o[f]), f
     np.testing.assert_allclose(out.global_tally[:], out_o.global_tally[:], rtol=1e-13)
     eng.finalize()
+
+
+@pytest.mark.parametrize("sweep", ["1", "2"])
+def test_ce_survival_biasing_generation_matches_oracle(emu_lib, sweep, monkeypatch):
+    """CE pincell with survival biasing (implicit absorption + russian roulette in collision_ce,
+    src/physics.cpp:638-651, 152-167): the engine sources bank the oracle's fission sites and
+    score the same tallies -- the oracle's collision is itself held to the reference's
+    collision() with survival biasing (test_whole_collision_equals_reference)"""
+    monkeypatch.setenv("OMCGPU_SWEEP", sweep)
+    model, box, of, libx = cases.build_ce(n_grid=500)
+    model.struct.survival_biasing = 1             # (cached model: put it back)
+    try:
+        o = Oracle(model)
+        n = 1500
+        src = o.sample_initial_source(n, box, of)
+        eng = lib.Engine(emu_lib)
+        eng.init(model, 0, 4096)
+        gi = eng.gen_in(n, 0, 0, 1.0, True)
+        fb, out = eng.transport_generation(gi, src)
+        fb_o, out_o = o.transport_generation(gi, src)
+    finally:
+        model.struct.survival_biasing = 0
+    assert out.n_lost == 0 and out_o.n_lost == 0
+    assert out.n_fission == out_o.n_fission and out.n_events == out_o.n_events
+    assert out.n_crossings == out_o.n_crossings and out.n_collisions == out_o.n_collisions
+    for f in ("r", "u", "E", "time", "wgt", "delayed_group", "parent_id", "progeny_id"):
+        assert np.array_equal(fb[f], fb_o[f]), f
+    np.testing.assert_allclose(out.global_tally[:], out_o.global_tally[:], rtol=1e-12)
+    m = int(model["tally_result_ofs"][1])
+    v = np.zeros(m); eng.tally_results(0, v)
+    np.testing.assert_allclose(v, o.tally_results(0, m), rtol=1e-11, atol=1e-300)
+    eng.finalize()

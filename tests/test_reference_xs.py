@@ -334,7 +334,6 @@ def test_whole_collision_equals_reference(survival):
     import ctypes as C
     from openmc_b200 import _abi as abi
     model, box, of, libx = cases.build_ce(n_grid=500)
-    model.struct.survival_biasing = survival
     wgt0 = 0.3 if survival else 1.0
     ref = ref_geometry.ReferenceXS(model)
     L = ref.lib
@@ -378,22 +377,26 @@ def test_whole_collision_equals_reference(survival):
     seeds = g.integers(1, 2**63, n, dtype=np.uint64)
     cap = 8 * n
     res = []
-    for which in ("ref", "oracle"):
-        Eo = np.zeros(n); uo = np.zeros((n, 3)); w = np.zeros(n); ka = np.zeros(n); so = np.zeros(n, np.uint64)
-        ofs = np.zeros(n + 1, np.int64); sE = np.zeros(cap); su = np.zeros((cap, 3)); sg = np.zeros(cap, np.int32)
-        st = np.zeros(cap)
-        if which == "ref":
-            inuc = np.zeros(n, np.int32); mt = np.zeros(n, np.int32)
-            L.ref_collision.restype = C.c_int64
-            tot = L.ref_collision(C.c_int64(n), p(mat), p(E), p(u), p(seeds), C.c_double(1.1), C.c_double(wgt0), p(Eo), p(uo), p(w), p(ka),
-                                  p(inuc), p(mt), p(so), p(ofs), p(sE), p(su), p(sg), p(st), C.c_int64(cap))
-            assert tot >= 0, L.ref_geom_error()
-        else:
-            o.lib.orc_collision.restype = C.c_int64
-            tot = o.lib.orc_collision(C.c_int64(n), p(mat), p(E), p(u), p(seeds), C.c_double(1.1), C.c_double(wgt0), p(Eo), p(uo), p(w),
-                                      p(ka), p(so), p(ofs), p(sE), p(su), p(sg), p(st), C.c_int64(cap))
-            assert tot >= 0
-        res.append((Eo, uo, w, ka, so, ofs, sE[:tot], su[:tot], sg[:tot], st[:tot]))
+    model.struct.survival_biasing = survival      # the oracle reads the live struct; the model is cached
+    try:
+        for which in ("ref", "oracle"):
+            Eo = np.zeros(n); uo = np.zeros((n, 3)); w = np.zeros(n); ka = np.zeros(n); so = np.zeros(n, np.uint64)
+            ofs = np.zeros(n + 1, np.int64); sE = np.zeros(cap); su = np.zeros((cap, 3)); sg = np.zeros(cap, np.int32)
+            st = np.zeros(cap)
+            if which == "ref":
+                inuc = np.zeros(n, np.int32); mt = np.zeros(n, np.int32)
+                L.ref_collision.restype = C.c_int64
+                tot = L.ref_collision(C.c_int64(n), p(mat), p(E), p(u), p(seeds), C.c_double(1.1), C.c_double(wgt0), p(Eo), p(uo), p(w), p(ka),
+                                      p(inuc), p(mt), p(so), p(ofs), p(sE), p(su), p(sg), p(st), C.c_int64(cap))
+                assert tot >= 0, L.ref_geom_error()
+            else:
+                o.lib.orc_collision.restype = C.c_int64
+                tot = o.lib.orc_collision(C.c_int64(n), p(mat), p(E), p(u), p(seeds), C.c_double(1.1), C.c_double(wgt0), p(Eo), p(uo), p(w),
+                                          p(ka), p(so), p(ofs), p(sE), p(su), p(sg), p(st), C.c_int64(cap))
+                assert tot >= 0
+            res.append((Eo, uo, w, ka, so, ofs, sE[:tot], su[:tot], sg[:tot], st[:tot]))
+    finally:
+        model.struct.survival_biasing = 0         # ... by cases.build_ce: put it back
     assert L.ref_materials_load(C.c_int(0), p(m_ofs), p(m_nuc), p(m_rho)) == 0   # leave the library as found
     L.ref_collision_settings(C.c_int(0), C.c_double(0.25), C.c_double(1.0))
     names = "E u wgt k_abs seed site_ofs site_E site_u site_group site_time".split()
