@@ -28,7 +28,8 @@ def build(force=False):
     have_ref = os.path.isdir("/root/reference/src")
     shim = os.path.join(HERE, "ref_geom_shim.cpp")
     ref_stale = have_ref and (not os.path.exists(REF_LIB) or not os.path.exists(REF_GEOM_LIB)
-                              or os.path.getmtime(REF_GEOM_LIB) < os.path.getmtime(shim))
+                              or os.path.getmtime(REF_GEOM_LIB) < os.path.getmtime(shim)
+                              or os.path.getmtime(REF_GEOM_LIB) < os.path.getmtime(os.path.join(HERE, "Makefile")))
     if force or stale or ref_stale:
         subprocess.check_call(["make", "-s", "-C", HERE])
 
