@@ -225,3 +225,137 @@ class ReferenceMesh:
         if tot < 0:
             raise RuntimeError(self.lib.ref_geom_error().decode() or "capacity")
         return ofs, bins[:tot], lengths[:tot]
+
+
+def products_into_reference(L, model, rx, allow_no_law=False):
+    """fills the products of the library's current hand-made Reaction from reaction `rx`
+    (global index) of the model; False when a law's parameter is not a table"""
+    from openmc_b200 import _abi as abi
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    fn_ofs = np.asarray(model["fn_ofs"]); fn_type = np.asarray(model["fn_type"]); data = np.asarray(model["fn_data"])
+    elaw = np.asarray(model["prod_elaw"]); par = np.asarray(model["prod_par"]).reshape(-1, 2)
+    pfn = np.asarray(model["prod_fn"]).reshape(-1, 2)
+    fn = lambda f: np.ascontiguousarray(data[fn_ofs[f]:fn_ofs[f + 1]])
+    p0, p1 = int(model["rx_prod_ofs"][rx]), int(model["rx_prod_ofs"][rx + 1])
+    for i, prod in enumerate(range(p0, p1)):
+        law = int(elaw[prod])
+        if law == abi.OMCGPU_ELAW_NONE and not allow_no_law:
+            return False
+        tabs = []
+        for k in range(2 if law == abi.OMCGPU_ELAW_WATT else (0 if law in (abi.OMCGPU_ELAW_LEVEL, abi.OMCGPU_ELAW_NONE) else 1)):
+            f = int(pfn[prod, k])
+            if fn_type[f] != abi.OMCGPU_FN_TABULATED1D:
+                return False
+            d = fn(f)
+            tabs.append((np.ascontiguousarray(d[:d.size // 2]), np.ascontiguousarray(d[d.size // 2:])))
+        while len(tabs) < 2:
+            tabs.append((np.zeros(1), np.zeros(1)))
+        y = int(model["prod_yield_fn"][prod]); y_d = fn(y)
+        rc = L.ref_rx_product(C.c_int(i), C.c_int(law), C.c_double(par[prod, 0]), C.c_double(par[prod, 1]),
+                              p(tabs[0][0]), p(tabs[0][1]), C.c_int(tabs[0][0].size),
+                              p(tabs[1][0]), p(tabs[1][1]), C.c_int(tabs[1][0].size),
+                              C.c_int(int(fn_type[y] == abi.OMCGPU_FN_POLYNOMIAL)), p(y_d), C.c_int(y_d.size),
+                              C.c_int(int(model["prod_emission"][prod])), C.c_double(float(model["prod_decay_rate"][prod])))
+        assert rc == 0, L.ref_geom_error()
+    return True
+
+
+COLLISION_FIELDS = "E u wgt k_abs seed site_ofs site_E site_u site_group site_time".split()
+
+
+def collision_probes(ref, n, seed):
+    """(material, energy, direction, seed) of n neutrons about to collide"""
+    g = np.random.default_rng(seed)
+    E = ref.in_range(np.exp(g.uniform(np.log(1e-4), np.log(1.9e7), n)))
+    n = E.size
+    mat = np.ascontiguousarray(g.integers(0, int(ref.model["n_materials"]), n), np.int32)
+    u = g.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
+    return mat, E, np.ascontiguousarray(u), g.integers(1, 2**63, n, dtype=np.uint64)
+
+
+def _collision_buffers(n):
+    cap = 8 * n
+    return dict(E=np.zeros(n), u=np.zeros((n, 3)), wgt=np.zeros(n), k_abs=np.zeros(n), seed=np.zeros(n, np.uint64),
+                site_ofs=np.zeros(n + 1, np.int64), site_E=np.zeros(cap), site_u=np.zeros((cap, 3)),
+                site_group=np.zeros(cap, np.int32), site_time=np.zeros(cap)), cap
+
+
+def _trim_sites(b, tot):
+    for k in ("site_E", "site_u", "site_group", "site_time"):
+        b[k] = b[k][:tot]
+    return b
+
+
+def oracle_collisions(o, mat, E, u, seeds, k_eff, wgt0):
+    """the oracle's collision_ce on the same neutrons (oracle/oracle.cpp: orc_collision)"""
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = E.size
+    b, cap = _collision_buffers(n)
+    o.lib.orc_collision.restype = C.c_int64
+    tot = o.lib.orc_collision(C.c_int64(n), p(mat), p(E), p(u), p(seeds), C.c_double(k_eff), C.c_double(wgt0),
+                              p(b["E"]), p(b["u"]), p(b["wgt"]), p(b["k_abs"]), p(b["seed"]), p(b["site_ofs"]),
+                              p(b["site_E"]), p(b["site_u"]), p(b["site_group"]), p(b["site_time"]), C.c_int64(cap))
+    assert tot >= 0
+    return _trim_sites(b, tot)
+
+
+def _load_collision_physics(self, survival=0):
+    """hand-made Reaction / ReactionProduct / Material objects of the reference library that
+    carry the model's reactions, products and compositions (after ref_xs_load)"""
+    from openmc_b200 import _abi as abi
+    model, L = self.model, self.lib
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    fn_ofs = np.asarray(model["fn_ofs"]); fn_type = np.asarray(model["fn_type"]); data = np.asarray(model["fn_data"])
+    rx_xs_ofs = np.asarray(model["rx_xs_ofs"]); rx_xs = np.asarray(model["rx_xs"])
+    for nuc in range(int(model["n_nuclides"])):
+        fissionable = int(model["nuc_fissionable"][nuc])
+        tn = int(model["nuc_total_nu_fn"][nuc]) if fissionable else -1
+        tn_d = np.ascontiguousarray(data[fn_ofs[tn]:fn_ofs[tn + 1]]) if tn >= 0 else np.zeros(1)
+        assert L.ref_nuc_physics(C.c_int(nuc), C.c_double(float(model["nuc_awr"][nuc])),
+                                 C.c_int(int(model["nuc_n_precursor"][nuc])),
+                                 C.c_int(int(tn >= 0 and fn_type[tn] == abi.OMCGPU_FN_POLYNOMIAL)), p(tn_d),
+                                 C.c_int(tn_d.size if tn >= 0 else 0)) == 0
+        r0, r1 = int(model["nuc_rx_ofs"][nuc]), int(model["nuc_rx_ofs"][nuc + 1])
+        fis = r0 + int(model["nuc_fission_rx"][nuc]) if fissionable else -1
+        for rx in range(r0, r1):
+            v = np.ascontiguousarray(rx_xs[rx_xs_ofs[rx]:rx_xs_ofs[rx + 1]])
+            n_prod = int(model["rx_prod_ofs"][rx + 1]) - int(model["rx_prod_ofs"][rx])
+            rc = L.ref_nuc_reaction(C.c_int(nuc), C.c_int(int(model["rx_mt"][rx])), C.c_int(int(model["rx_scatter_in_cm"][rx])),
+                                    C.c_int(int(model["rx_inelastic"][rx])), C.c_int(int(rx == fis)),
+                                    C.c_int(int(model["rx_threshold"][rx])), p(v), C.c_int64(v.size), C.c_int(n_prod))
+            assert rc == 0, L.ref_geom_error()
+            assert products_into_reference(L, model, rx, allow_no_law=True), (nuc, rx)
+    self._m = (np.ascontiguousarray(model["mat_nuc_ofs"], np.int32), np.ascontiguousarray(model["mat_nuclide"], np.int32),
+               np.ascontiguousarray(model["mat_atom_density"], np.float64))
+    assert L.ref_materials_load(C.c_int(int(model["n_materials"])), *[p(a) for a in self._m]) == 0, L.ref_geom_error()
+    L.ref_collision_settings(C.c_int(int(survival)), C.c_double(float(model["weight_cutoff"])),
+                             C.c_double(float(model["weight_survive"])))
+
+
+def _unload_collision_physics(self):
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    if getattr(self, "_m", None) is not None:
+        self.lib.ref_materials_load(C.c_int(0), *[p(a) for a in self._m])     # leave the library as found
+    self.lib.ref_collision_settings(C.c_int(0), C.c_double(0.25), C.c_double(1.0))
+
+
+def _collisions(self, mat, E, u, seeds, k_eff, wgt0):
+    """the reference's collision() (src/physics.cpp:43-168) on n neutrons; adds the sampled
+    nuclide and MT to the fields of COLLISION_FIELDS"""
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = E.size
+    b, cap = _collision_buffers(n)
+    b["nuclide"] = np.zeros(n, np.int32); b["mt"] = np.zeros(n, np.int32)
+    self.lib.ref_collision.restype = C.c_int64
+    tot = self.lib.ref_collision(C.c_int64(n), p(mat), p(E), p(u), p(seeds), C.c_double(k_eff), C.c_double(wgt0),
+                                 p(b["E"]), p(b["u"]), p(b["wgt"]), p(b["k_abs"]), p(b["nuclide"]), p(b["mt"]),
+                                 p(b["seed"]), p(b["site_ofs"]), p(b["site_E"]), p(b["site_u"]), p(b["site_group"]),
+                                 p(b["site_time"]), C.c_int64(cap))
+    if tot < 0:
+        raise RuntimeError(self.lib.ref_geom_error().decode())
+    return _trim_sites(b, tot)
+
+
+ReferenceXS.load_collision_physics = _load_collision_physics
+ReferenceXS.unload_collision_physics = _unload_collision_physics
+ReferenceXS.collisions = _collisions

@@ -53,6 +53,22 @@ def test_committed_reference_vectors_are_reproduced_by_the_oracle():
         assert np.array_equal(ig_o[:, :n_nuc], v[f"ig{mat}"]) and np.array_equal(xs_o, v[f"xs{mat}"])
 
 
+def test_committed_reference_collisions_are_reproduced_by_the_oracle():
+    """tests/golden/refcoll_ce.npz (written by the reference's own collision(),
+    make_reference_collisions.py) without the reference tree -- this one travels to the GPU box:
+    the oracle leaves every neutron as the reference did, analog and with survival biasing"""
+    model = cases.load_model_npz(os.path.join(GOLDEN, "ce_model.npz"))
+    v = np.load(os.path.join(GOLDEN, "refcoll_ce.npz"))
+    mat, E, u, seeds = (np.ascontiguousarray(v[k]) for k in ("material", "E_in", "u_in", "seed_in"))
+    for tag, survival in (("a", 0), ("s", 1)):
+        model.struct.survival_biasing = survival
+        o = Oracle(model); o.load()
+        q = ref_geometry.oracle_collisions(o, mat, E, u, seeds, float(v["k_eff"]), float(v[f"{tag}_wgt0"]))
+        for name in ref_geometry.COLLISION_FIELDS:
+            assert np.array_equal(q[name], v[f"{tag}_{name}"]), (tag, name)
+        assert int(v[f"{tag}_site_ofs"][-1]) > 50
+
+
 @pytest.mark.gpu
 def test_gpu_lookup_equals_reference_vectors(gpu_engine):
     model, v = _fixture()
@@ -209,40 +225,6 @@ def test_elastic_scattering_equals_reference():
     # (afterwards the reference library holds the one hand-made nuclide; ReferenceXS reloads its own)
 
 
-def _products_into_reference(L, model, rx, allow_no_law=False):
-    """fills the products of the library's current hand-made Reaction from reaction `rx`
-    (global index) of the model; False when a law's parameter is not a table"""
-    import ctypes as C
-    from openmc_b200 import _abi as abi
-    p = lambda a: a.ctypes.data_as(C.c_void_p)
-    fn_ofs = np.asarray(model["fn_ofs"]); fn_type = np.asarray(model["fn_type"]); data = np.asarray(model["fn_data"])
-    elaw = np.asarray(model["prod_elaw"]); par = np.asarray(model["prod_par"]).reshape(-1, 2)
-    pfn = np.asarray(model["prod_fn"]).reshape(-1, 2)
-    fn = lambda f: np.ascontiguousarray(data[fn_ofs[f]:fn_ofs[f + 1]])
-    p0, p1 = int(model["rx_prod_ofs"][rx]), int(model["rx_prod_ofs"][rx + 1])
-    for i, prod in enumerate(range(p0, p1)):
-        law = int(elaw[prod])
-        if law == abi.OMCGPU_ELAW_NONE and not allow_no_law:
-            return False
-        tabs = []
-        for k in range(2 if law == abi.OMCGPU_ELAW_WATT else (0 if law in (abi.OMCGPU_ELAW_LEVEL, abi.OMCGPU_ELAW_NONE) else 1)):
-            f = int(pfn[prod, k])
-            if fn_type[f] != abi.OMCGPU_FN_TABULATED1D:
-                return False
-            d = fn(f)
-            tabs.append((np.ascontiguousarray(d[:d.size // 2]), np.ascontiguousarray(d[d.size // 2:])))
-        while len(tabs) < 2:
-            tabs.append((np.zeros(1), np.zeros(1)))
-        y = int(model["prod_yield_fn"][prod]); y_d = fn(y)
-        rc = L.ref_rx_product(C.c_int(i), C.c_int(law), C.c_double(par[prod, 0]), C.c_double(par[prod, 1]),
-                              p(tabs[0][0]), p(tabs[0][1]), C.c_int(tabs[0][0].size),
-                              p(tabs[1][0]), p(tabs[1][1]), C.c_int(tabs[1][0].size),
-                              C.c_int(int(fn_type[y] == abi.OMCGPU_FN_POLYNOMIAL)), p(y_d), C.c_int(y_d.size),
-                              C.c_int(int(model["prod_emission"][prod])), C.c_double(float(model["prod_decay_rate"][prod])))
-        assert rc == 0, L.ref_geom_error()
-    return True
-
-
 def _reaction_into_reference(L, model, nuc, rx, fissionable):
     """hand the products of reaction `rx` (global index) of nuclide `nuc` to the reference
     library's hand-made Reaction; returns False when a law's parameter is not a table"""
@@ -261,7 +243,7 @@ def _reaction_into_reference(L, model, nuc, rx, fissionable):
                         C.c_int(int(tn >= 0 and fn_type[tn] == abi.OMCGPU_FN_POLYNOMIAL)), p(tn_d),
                         C.c_int(tn_d.size if tn >= 0 else 0), C.c_int(p1 - p0), C.c_double(float(model["energy_max"])))
     assert rc == 0, L.ref_geom_error()
-    return _products_into_reference(L, model, rx)
+    return ref_geometry.products_into_reference(L, model, rx)
 
 
 @needs_ref
@@ -331,84 +313,30 @@ def test_whole_collision_equals_reference(survival):
     (count, energy, direction, delayed group, emission time) -- every material, 1e-4 eV to 19 MeV;
     analog absorption, and survival biasing with russian_roulette (src/physics_common.cpp) on
     neutrons that start just above the weight cutoff"""
-    import ctypes as C
-    from openmc_b200 import _abi as abi
     model, box, of, libx = cases.build_ce(n_grid=500)
     wgt0 = 0.3 if survival else 1.0
     ref = ref_geometry.ReferenceXS(model)
-    L = ref.lib
     o = Oracle(model); o.load()
-    p = lambda a: a.ctypes.data_as(C.c_void_p)
-    fn_ofs = np.asarray(model["fn_ofs"]); fn_type = np.asarray(model["fn_type"]); data = np.asarray(model["fn_data"])
-    rx_xs_ofs = np.asarray(model["rx_xs_ofs"]); rx_xs = np.asarray(model["rx_xs"])
-    for nuc in range(int(model["n_nuclides"])):
-        fissionable = int(model["nuc_fissionable"][nuc])
-        tn = int(model["nuc_total_nu_fn"][nuc]) if fissionable else -1
-        tn_d = np.ascontiguousarray(data[fn_ofs[tn]:fn_ofs[tn + 1]]) if tn >= 0 else np.zeros(1)
-        assert L.ref_nuc_physics(C.c_int(nuc), C.c_double(float(model["nuc_awr"][nuc])),
-                                 C.c_int(int(model["nuc_n_precursor"][nuc])),
-                                 C.c_int(int(tn >= 0 and fn_type[tn] == abi.OMCGPU_FN_POLYNOMIAL)), p(tn_d),
-                                 C.c_int(tn_d.size if tn >= 0 else 0)) == 0
-        r0, r1 = int(model["nuc_rx_ofs"][nuc]), int(model["nuc_rx_ofs"][nuc + 1])
-        fis = r0 + int(model["nuc_fission_rx"][nuc]) if fissionable else -1
-        for rx in range(r0, r1):
-            v = np.ascontiguousarray(rx_xs[rx_xs_ofs[rx]:rx_xs_ofs[rx + 1]])
-            n_prod = int(model["rx_prod_ofs"][rx + 1]) - int(model["rx_prod_ofs"][rx])
-            rc = L.ref_nuc_reaction(C.c_int(nuc), C.c_int(int(model["rx_mt"][rx])), C.c_int(int(model["rx_scatter_in_cm"][rx])),
-                                    C.c_int(int(model["rx_inelastic"][rx])), C.c_int(int(rx == fis)),
-                                    C.c_int(int(model["rx_threshold"][rx])), p(v), C.c_int64(v.size), C.c_int(n_prod))
-            assert rc == 0, L.ref_geom_error()
-            assert _products_into_reference(L, model, rx, allow_no_law=True), (nuc, rx)
-    m_ofs = np.ascontiguousarray(model["mat_nuc_ofs"], np.int32)
-    m_nuc = np.ascontiguousarray(model["mat_nuclide"], np.int32)
-    m_rho = np.ascontiguousarray(model["mat_atom_density"], np.float64)
-    n_mat = int(model["n_materials"])
-    assert L.ref_materials_load(C.c_int(n_mat), p(m_ofs), p(m_nuc), p(m_rho)) == 0, L.ref_geom_error()
-    L.ref_collision_settings(C.c_int(survival), C.c_double(float(model["weight_cutoff"])),
-                             C.c_double(float(model["weight_survive"])))
-
-    g = np.random.default_rng(31)
-    n = 60000
-    E = ref.in_range(np.exp(g.uniform(np.log(1e-4), np.log(1.9e7), n)))
+    mat, E, u, seeds = ref_geometry.collision_probes(ref, 60000, seed=31)
     n = E.size
-    mat = np.ascontiguousarray(g.integers(0, n_mat, n), np.int32)
-    u = g.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
-    u = np.ascontiguousarray(u)
-    seeds = g.integers(1, 2**63, n, dtype=np.uint64)
-    cap = 8 * n
-    res = []
     model.struct.survival_biasing = survival      # the oracle reads the live struct; the model is cached
     try:
-        for which in ("ref", "oracle"):
-            Eo = np.zeros(n); uo = np.zeros((n, 3)); w = np.zeros(n); ka = np.zeros(n); so = np.zeros(n, np.uint64)
-            ofs = np.zeros(n + 1, np.int64); sE = np.zeros(cap); su = np.zeros((cap, 3)); sg = np.zeros(cap, np.int32)
-            st = np.zeros(cap)
-            if which == "ref":
-                inuc = np.zeros(n, np.int32); mt = np.zeros(n, np.int32)
-                L.ref_collision.restype = C.c_int64
-                tot = L.ref_collision(C.c_int64(n), p(mat), p(E), p(u), p(seeds), C.c_double(1.1), C.c_double(wgt0), p(Eo), p(uo), p(w), p(ka),
-                                      p(inuc), p(mt), p(so), p(ofs), p(sE), p(su), p(sg), p(st), C.c_int64(cap))
-                assert tot >= 0, L.ref_geom_error()
-            else:
-                o.lib.orc_collision.restype = C.c_int64
-                tot = o.lib.orc_collision(C.c_int64(n), p(mat), p(E), p(u), p(seeds), C.c_double(1.1), C.c_double(wgt0), p(Eo), p(uo), p(w),
-                                          p(ka), p(so), p(ofs), p(sE), p(su), p(sg), p(st), C.c_int64(cap))
-                assert tot >= 0
-            res.append((Eo, uo, w, ka, so, ofs, sE[:tot], su[:tot], sg[:tot], st[:tot]))
+        ref.load_collision_physics(survival)
+        r = ref.collisions(mat, E, u, seeds, 1.1, wgt0)
+        q = ref_geometry.oracle_collisions(o, mat, E, u, seeds, 1.1, wgt0)
     finally:
         model.struct.survival_biasing = 0         # ... by cases.build_ce: put it back
-    assert L.ref_materials_load(C.c_int(0), p(m_ofs), p(m_nuc), p(m_rho)) == 0   # leave the library as found
-    L.ref_collision_settings(C.c_int(0), C.c_double(0.25), C.c_double(1.0))
-    names = "E u wgt k_abs seed site_ofs site_E site_u site_group site_time".split()
-    for name, a, b in zip(names, res[0], res[1]):
-        assert np.array_equal(a, b), name
+        ref.unload_collision_physics()
+    for name in ref_geometry.COLLISION_FIELDS:
+        assert np.array_equal(r[name], q[name]), name
     # every channel was exercised
-    absorbed = int((res[0][2] == 0).sum()); n_sites = int(res[0][5][-1])
-    elastic = int((mt == 2).sum()); inelastic = int(((mt != 2) & (mt != 18) & (res[0][2] > 0)).sum())
+    mt, inuc = r["mt"], r["nuclide"]
+    absorbed = int((r["wgt"] == 0).sum()); n_sites = int(r["site_ofs"][-1])
+    elastic = int((mt == 2).sum()); inelastic = int(((mt != 2) & (mt != 18) & (r["wgt"] > 0)).sum())
     print(f"collisions: {n}, absorbed {absorbed}, fission sites {n_sites}, elastic {elastic}, inelastic {inelastic}, "
           f"nuclides hit {np.unique(inuc).size}")
     assert absorbed > 100 and n_sites > 100 and elastic > 1000 and inelastic > 100
     if survival:
-        rouletted_up = int((res[0][2] == float(model["weight_survive"])).sum())
+        rouletted_up = int((r["wgt"] == float(model["weight_survive"])).sum())
         assert rouletted_up > 100, rouletted_up
     assert np.unique(inuc).size == int(model["n_nuclides"])
