@@ -3183,3 +3183,72 @@ int omcgpu_prn(const uint64_t* seed, int64_t n_seeds, int32_t count, double* out
 }
 
 } // extern "C"
+
+#ifdef OMC_EMU
+// TEST-ONLY, host compile only (tests/_emu; not declared in include/omcgpu.h, absent from
+// libomcgpu.so): one collision_ce per neutron in a plain loop, so that the CPU tier can hold the
+// DEVICE function to the vectors the reference's own collision() wrote
+// (tests/golden/refcoll_ce.npz).  Fission sites of collision k: site_*[site_ofs[k] .. site_ofs[k+1]).
+extern "C" int64_t emu_collide_ce(int64_t n, const int32_t* material, const double* E, const double* uvw,
+  const uint64_t* seed_in, double k_eff, double wgt0, double* E_out, double* uvw_out, double* wgt_out,
+  double* kabs_out, uint64_t* seed_out, int64_t* site_ofs, double* site_E, double* site_u,
+  int32_t* site_group, double* site_time, int64_t site_cap)
+{
+  using namespace omc;
+  if (!G.ready)
+    return -1;
+  const int64_t cap = 64;
+  std::vector<double> c[9];
+  for (auto& v : c)
+    v.assign(cap, 0.0);
+  std::vector<int32_t> dg(cap, 0);
+  std::vector<int64_t> pid(cap, 0), prog(cap, 0);
+  Bank fb;
+  fb.cap = cap;
+  fb.x = c[0].data(); fb.y = c[1].data(); fb.z = c[2].data();
+  fb.u = c[3].data(); fb.v = c[4].data(); fb.w = c[5].data();
+  fb.E = c[6].data(); fb.time = c[7].data(); fb.wgt = c[8].data();
+  fb.delayed_group = dg.data(); fb.parent_id = pid.data(); fb.progeny_id = prog.data();
+  int32_t n_fission = 0;
+  GenCtx gc {};
+  gc.keff = k_eff;
+  gc.n_fission = &n_fission;
+  gc.fission_cap = cap;
+  int64_t total = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    Collider p {};
+    p.r = v3(0., 0., 0.);
+    p.u = v3(uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]);
+    p.E = E[k];
+    p.wgt = wgt0;
+    p.material = material[k];
+    p.seed = seed_in[k];
+    p.id = k;
+    double t, a, f, nf;
+    ce_macro_xs<false>(p.material, p.E, t, a, f, nf, nullptr, 0);
+    p.xs_total = t; p.xs_absorption = a; p.xs_nu_fission = nf;
+    n_fission = 0;
+    bool no_nuclide = false;
+    collision_ce<false>(p, gc, fb, no_nuclide);
+    if (no_nuclide)
+      return -2;
+    E_out[k] = p.E;
+    uvw_out[3 * k] = p.u.x; uvw_out[3 * k + 1] = p.u.y; uvw_out[3 * k + 2] = p.u.z;
+    wgt_out[k] = p.wgt;
+    kabs_out[k] = p.k_abs;
+    seed_out[k] = p.seed;
+    site_ofs[k] = total;
+    if (total + n_fission > site_cap || n_fission > cap)
+      return -3;
+    for (int j = 0; j < n_fission; ++j) {
+      site_E[total] = fb.E[j];
+      site_u[3 * total] = fb.u[j]; site_u[3 * total + 1] = fb.v[j]; site_u[3 * total + 2] = fb.w[j];
+      site_group[total] = fb.delayed_group[j];
+      site_time[total] = fb.time[j];
+      ++total;
+    }
+  }
+  site_ofs[n] = total;
+  return total;
+}
+#endif
