@@ -350,6 +350,7 @@ typedef struct omcgpu_gen_in {
 typedef struct omcgpu_gen_out {
   int64_t n_fission;          /* sites banked (fission bank already sorted by parent/progeny) */
   int64_t n_lost;             /* lost particles                                          */
+  int64_t n_bank_full;        /* histories that found the fission bank full (sites dropped: the reference's warning, src/physics.cpp:236) */
   int64_t n_events;           /* total particle events processed                         */
   int64_t n_xs_lookups;       /* items processed by the calculate-xs kernel              */
   int64_t n_collisions;
@@ -459,6 +460,18 @@ int omcgpu_find_cell(const double* xyz, const double* uvw, int64_t n,
   int32_t* cell, int32_t* instance, int32_t* material, int32_t* n_coord);
 int omcgpu_distance_to_boundary(const double* xyz, const double* uvw, int64_t n,
   double* distance, int32_t* surface, int32_t* level, int32_t* lattice_trans);
+
+/* Collision probe: collision() (src/physics.cpp:43-168; MG: src/physics_mg.cpp:26-60) on n
+ * independent neutrons of weight `wgt` at the origin -- the device function of the collision
+ * kernels on its own, for parity against vectors written by the reference's collision().
+ * Neutron k: material[k], E[k] (MG: group), direction uvw[3k..], RNG state seed[k]; out: energy
+ * (group), direction, weight, k-absorption score, RNG state, n_sites[k] banked fission sites;
+ * the sites of all neutrons in (neutron, progeny) order in sites[0 .. *n_sites_total) with
+ * parent_id = k + 1.  n <= max_particles. */
+int omcgpu_collide(int64_t n, const int32_t* material, const double* E, const double* uvw,
+  const uint64_t* seed, double keff, double wgt, double* E_out, double* uvw_out, double* wgt_out,
+  double* k_abs_out, uint64_t* seed_out, int32_t* n_sites, omcgpu_site* sites,
+  int64_t site_capacity, int64_t* n_sites_total);
 
 /* RNG probes (src/random_lcg.cpp): out[i] = future_seed(n[i], seed[i]);
  * prn stream: out[i*count + j] = j-th prn of seed[i]. */

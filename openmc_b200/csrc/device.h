@@ -1455,6 +1455,13 @@ OMC_HD void bank_store(const Bank& fb, int64_t slot, V3 r, V3 u, double E, doubl
   fb.progeny_id[slot] = progeny_id;
 }
 
+// The shared fission bank is full (the reference's warning "Additional fission sites created in
+// this generation will not be banked"): counted, reported in omcgpu_gen_out.n_fission_dropped.
+OMC_HD void fission_bank_full(const GenCtx& gc)
+{
+  atomic_add_i32(gc.n_bank_full, 1);
+}
+
 // =============================================================================
 // Collision: multigroup -- src/physics_mg.cpp:26-259
 // =============================================================================
@@ -1505,10 +1512,12 @@ OMC_HD void collision_mg(Collider& p, int ba, const GenCtx& gc, const Bank& fb)
           t -= log(prn(p.seed)) / decay_rate;
         }
         const int64_t slot = (int64_t)base + k;
-        if (slot < gc.fission_cap) {
-          bank_store(fb, slot, p.r, su, (double)gout, t, 1.0, dg + 1, p.id, p.n_progeny);
-          p.n_progeny++;
+        if (slot >= gc.fission_cap) { // bank full: the reference warns and leaves the loop
+          fission_bank_full(gc);      // (thread_safe_append == -1, src/physics_mg.cpp:186-200)
+          break;
         }
+        bank_store(fb, slot, p.r, su, (double)gout, t, 1.0, dg + 1, p.id, p.n_progeny);
+        p.n_progeny++;
       }
     }
   }
@@ -1619,10 +1628,12 @@ OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no
         }
         const V3 su = rotate_angle(p.u, mu, p.seed);
         const int64_t slot = (int64_t)base + k;
-        if (slot < gc.fission_cap) {
-          bank_store(fb, slot, p.r, su, E_out, t, 1.0, group, p.id, p.n_progeny);
-          p.n_progeny++;
+        if (slot >= gc.fission_cap) { // bank full: warn + break, src/physics.cpp:233-247
+          fission_bank_full(gc);
+          break;
         }
+        bank_store(fb, slot, p.r, su, E_out, t, 1.0, group, p.id, p.n_progeny);
+        p.n_progeny++;
       }
     }
   }

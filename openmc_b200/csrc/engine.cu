@@ -1284,6 +1284,71 @@ OMC_D void body_probe_xs(int64_t tid, const XsArgs& a)
 OMC_KERNEL_MB(k_probe_xs, XsArgs, body_probe_xs<false>, 2)
 OMC_KERNEL_MB(k_probe_xs_b, XsArgs, body_probe_xs<true>, 2)
 
+// collision() of src/physics.cpp:43-168 (CE) / src/physics_mg.cpp:26-60 (MG) on n independent
+// neutrons -- the device function the collision kernels call, exposed on its own so that it can
+// be held to vectors written by the reference's collision() (tests/golden/refcoll_ce.npz)
+struct CollideArgs {
+  PState ps;
+  GenCtx gc;
+  Bank fb;
+  int64_t n;
+  const int32_t* material;
+  const double* E;
+  const double* uvw;
+  const uint64_t* seed;
+  double wgt;
+  double* E_out;
+  double* uvw_out;
+  double* wgt_out;
+  double* k_abs_out;
+  uint64_t* seed_out;
+};
+OMC_D void body_probe_collide(int64_t tid, const CollideArgs& a)
+{
+  if (tid >= a.n)
+    return;
+  Collider p;
+  p.r = v3(0., 0., 0.);
+  p.u = v3(a.uvw[3 * tid], a.uvw[3 * tid + 1], a.uvw[3 * tid + 2]);
+  p.E = a.E[tid];
+  p.wgt = a.wgt;
+  p.time = 0.0;
+  p.k_abs = 0.0;
+  p.g = 0;
+  p.material = a.material[tid];
+  p.seed = a.seed[tid];
+  p.n_progeny = 0;
+  p.id = tid + 1;
+  if (DM.run_CE) {
+    double t, ab, f, nf;
+    ce_macro_xs<false>(p.material, p.E, t, ab, f, nf, nullptr, 0);
+    p.xs_total = t;
+    p.xs_absorption = ab;
+    p.xs_nu_fission = nf;
+    bool no_nuclide = false;
+    collision_ce<false>(p, a.gc, a.fb, no_nuclide);
+    if (no_nuclide)
+      atomic_add_i32(a.gc.n_lost, 1);
+  } else {
+    const int G_ = DM.mg_n_groups;
+    p.g = (int)a.E[tid];
+    const int ba = mg_ba(p.material, 0, mg_angle_index(p.material, p.u));
+    p.xs_total = ld(DM.mg_total + ba * G_ + p.g);
+    p.xs_absorption = ld(DM.mg_absorption + ba * G_ + p.g);
+    p.xs_nu_fission = ld(DM.mgm_fissionable + p.material) ? ld(DM.mg_nu_fission + ba * G_ + p.g) : 0.;
+    collision_mg(p, ba, a.gc, a.fb);
+  }
+  a.E_out[tid] = DM.run_CE ? p.E : (double)p.g;
+  a.uvw_out[3 * tid] = p.u.x;
+  a.uvw_out[3 * tid + 1] = p.u.y;
+  a.uvw_out[3 * tid + 2] = p.u.z;
+  a.wgt_out[tid] = p.wgt;
+  a.k_abs_out[tid] = p.k_abs;
+  a.seed_out[tid] = p.seed;
+  a.ps.n_progeny[tid] = p.n_progeny;
+}
+OMC_KERNEL(k_probe_collide, CollideArgs, body_probe_collide)
+
 struct GeoArgs {
   PState ps;
   const double* xyz;
@@ -1379,7 +1444,7 @@ static int fail(int code, const char* fmt, const char* detail = "")
   } while (0)
 
 constexpr int RING = 32;              // sweeps whose counters stay readable
-constexpr int RING_OFS = 8;           // d_counts: [0] alive after k_init, [4] fission sites, [5] lost, [6] tail flight log
+constexpr int RING_OFS = 8;           // d_counts: [0] alive after k_init, [4] fission sites, [5] lost, [6] tail flight log, [7] bank-full hits
 constexpr int N_COUNTS = RING_OFS + 4 * RING;
 
 struct Engine {
@@ -1413,6 +1478,7 @@ struct Engine {
   omcgpu_site* h_aos = nullptr;  // pinned staging
   double* d_tally = nullptr;
   int64_t n_tally = 0;
+  std::vector<int64_t> tally_ofs; // host copy of tally_result_ofs
   int tally_replicas = 1;       // copies of the VALUE arrays k_score spreads its REDs over
   int64_t tally_stride = 0;
   cudaStream_t stream = 0;
@@ -1769,6 +1835,7 @@ static int upload_model(const omcgpu_model* m)
   UP(filter_idata, n_fdat);
   UP(filter_ddata, n_fdat);
   G.n_tally = nt ? m->tally_result_ofs[nt] : 0;
+  G.tally_ofs.assign(m->tally_result_ofs, m->tally_result_ofs + (nt ? nt + 1 : 0));
   UP(tally_n_filters, nt);
   UP(tally_filters, (size_t)nt * OMCGPU_MAX_FILTERS);
   UP(tally_strides, (size_t)nt * OMCGPU_MAX_FILTERS);
@@ -1813,6 +1880,38 @@ static int check_supported(const omcgpu_model* m)
     for (int p = 0; p < m->n_products; ++p)
       if (m->prod_elaw[p] < 0 || m->prod_elaw[p] > OMCGPU_ELAW_WATT)
         return fail(OMCGPU_E_UNSUPPORTED, "secondary energy law not supported on the device%s");
+    // inelastic_scatter creates yield - 1 secondary neutrons when a product's yield is an integer
+    // >= 2, e.g. (n,2n) (src/physics.cpp:1158-1162); the device keeps no secondary bank, so a
+    // yield function with a flat piece at such a value is refused instead of silently
+    // transporting one neutron of unchanged weight
+    for (int r = 0; r < m->n_reactions; ++r) {
+      if (!m->rx_inelastic[r] || m->rx_prod_ofs[r + 1] <= m->rx_prod_ofs[r])
+        continue;
+      const int fn = m->prod_yield_fn[m->rx_prod_ofs[r]];
+      if (fn < 0 || fn >= m->n_functions)
+        return fail(OMCGPU_E_DATA, "reaction product without a yield function%s");
+      const double* d = m->fn_data + m->fn_ofs[fn];
+      const int n = m->fn_ofs[fn + 1] - m->fn_ofs[fn];
+      auto creates_secondaries = [](double y) { return y >= 2.0 && std::floor(y) == y; };
+      bool bad = false;
+      if (m->fn_type[fn] == OMCGPU_FN_POLYNOMIAL) {
+        bool constant = true;
+        for (int k = 1; k < n; ++k)
+          constant = constant && d[k] == 0.0;
+        bad = n >= 1 && constant && creates_secondaries(d[0]);
+      } else {
+        const int np = n / 2;
+        const double* y = d + np;
+        bad = np == 1 && creates_secondaries(y[0]);
+        for (int k = 0; k + 1 < np; ++k)
+          bad = bad || (y[k] == y[k + 1] && creates_secondaries(y[k]));
+        bad = bad || (np >= 1 && (creates_secondaries(y[0]) || creates_secondaries(y[np - 1]))); // flat extrapolation
+      }
+      if (bad)
+        return fail(OMCGPU_E_UNSUPPORTED,
+          "a scattering reaction has an integer neutron yield >= 2 (secondary neutrons, src/physics.cpp:1158): "
+          "not supported on the device%s");
+    }
   }
   return 0;
 }
@@ -1835,6 +1934,7 @@ static EvArgs make_args(const omcgpu_gen_in* in)
   }
   a.gc.n_fission = G.d_counts + 4;
   a.gc.n_lost = G.d_counts + 5;
+  a.gc.n_bank_full = G.d_counts + 7;
   a.gc.counters = G.d_counters;
   a.gc.tally_values = G.d_tally;
   a.gc.tally_replicas = G.tally_replicas;
@@ -2344,6 +2444,7 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
   G.n_fis = std::min<int64_t>(G.h_counts[4], G.fis_cap);
   out->n_fission = G.n_fis;
   out->n_lost = G.h_counts[5];
+  out->n_bank_full = G.h_counts[7];
   out->n_xs_lookups = n_xs + (int64_t)G.h_counters[1];
   out->n_collisions = n_coll + (int64_t)G.h_counters[2];
   out->n_crossings = n_cross + (int64_t)G.h_counters[3];
@@ -2395,30 +2496,35 @@ int omcgpu_finalize(void)
     cudaFreeHost(G.h_partial);
   if (G.h_aos)
     cudaFreeHost(G.h_aos);
-  if (G.ev0) {
-    cudaEventDestroy(G.ev0);
-    cudaEventDestroy(G.ev1);
+  {
+    auto drop = [](cudaEvent_t e) {
+      if (e)
+        cudaEventDestroy(e);
+    };
+    drop(G.ev0);
+    drop(G.ev1);
     for (int k = 0; k < RING; ++k) {
-      cudaEventDestroy(G.evx0[k]);
-      cudaEventDestroy(G.evx1[k]);
+      drop(G.evx0[k]);
+      drop(G.evx1[k]);
     }
-    cudaEventDestroy(G.evp0);
-    cudaEventDestroy(G.evp1);
-    cudaEventDestroy(G.e_adv);
-    cudaEventDestroy(G.e_surf);
-    cudaEventDestroy(G.e_coll);
-    cudaEventDestroy(G.e_score[0]);
-    cudaEventDestroy(G.e_score[1]);
+    drop(G.evp0);
+    drop(G.evp1);
+    drop(G.e_adv);
+    drop(G.e_surf);
+    drop(G.e_coll);
+    drop(G.e_score[0]);
+    drop(G.e_score[1]);
   }
-  if (G.ready) {
-    cudaStreamDestroy(G.stream);
-    cudaStreamDestroy(G.s_score);
-    cudaStreamDestroy(G.s_surf);
-    cudaStreamDestroy(G.s_coll);
-  }
+  // streams and events are tracked one by one (not through G.ready): an omcgpu_init that
+  // failed half way must not leak what it had created
+  for (cudaStream_t st : {G.stream, G.s_score, G.s_surf, G.s_coll})
+    if (st)
+      cudaStreamDestroy(st);
   G = Engine();
   return 0;
 }
+
+static int init_impl(const omcgpu_model* model, int device, int64_t max_particles);
 
 int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
 {
@@ -2426,6 +2532,18 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
     return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_init: bad arguments%s");
   if (G.ready)
     omcgpu_finalize();
+  const int rc = init_impl(model, device, max_particles);
+  if (rc) { // release whatever the failed attempt had allocated; the error text survives
+    char keep[sizeof(g_err)];
+    std::memcpy(keep, g_err, sizeof(keep));
+    omcgpu_finalize();
+    std::memcpy(g_err, keep, sizeof(keep));
+  }
+  return rc;
+}
+
+static int init_impl(const omcgpu_model* model, int device, int64_t max_particles)
+{
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
     return fail(OMCGPU_E_CUDA, "no CUDA device available: the device path has no CPU fallback%s");
@@ -2573,8 +2691,9 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles)
   }
   // A rank's comb may select more sites than its share of the next generation (they
   // travel to their owners afterwards, src/eigenvalue.cpp:186-348): the source bank
-  // and the gather list hold up to 25 % + 1024 more than max_particles.
-  const int64_t src_cap = cap + cap / 4 + 1024;
+  // and the gather list hold 3 x max_particles sites, like the reference's temp_sites
+  // (src/eigenvalue.cpp:135).
+  const int64_t src_cap = 3 * cap;
   rc = rc ? rc : alloc_bank(G.src, src_cap);
   rc = rc ? rc : alloc_bank(G.fis, G.fis_cap);
   rc = rc ? rc : alloc_bank(G.fis_sorted, G.fis_cap);
@@ -2925,7 +3044,7 @@ int omcgpu_comb_fission_bank(int64_t start, int64_t total, int64_t n_particles, 
   int32_t* idx = reinterpret_cast<int32_t*>(G.h_aos);
   int64_t count = 0;
   if (omcgpu_comb_indices(start, G.n_fis, total, n_particles, seed_id, master_seed, stride, idx, G.src.cap, &count))
-    return fail(OMCGPU_E_OUT_OF_BOUNDS, "comb selects more sites than the source bank holds (1.25 max_particles + 1024)%s");
+    return fail(OMCGPU_E_OUT_OF_BOUNDS, "comb selects more sites than the source bank holds (3 max_particles)%s");
   if (count > 0) {
     CUDA_OK(cudaMemcpyAsync(G.d_gather, idx, count * sizeof(int32_t), cudaMemcpyHostToDevice, G.stream));
     BankArgs b;
@@ -2970,8 +3089,7 @@ int omcgpu_tally_results(int32_t tally, double* value, int64_t n)
 {
   if (!G.ready || tally < 0 || tally >= G.hm.n_tallies)
     return fail(OMCGPU_E_OUT_OF_BOUNDS, "omcgpu_tally_results: bad tally index%s");
-  std::vector<int64_t> ofs(G.hm.n_tallies + 1);
-  CUDA_OK(cudaMemcpy(ofs.data(), G.hm.tally_result_ofs, ofs.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  const std::vector<int64_t>& ofs = G.tally_ofs;
   const int64_t len = ofs[tally + 1] - ofs[tally];
   if (n != len)
     return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_tally_results: size mismatch%s");
@@ -2982,13 +3100,18 @@ int omcgpu_tally_results(int32_t tally, double* value, int64_t n)
     f.stride = G.tally_stride;
     f.replicas = G.tally_replicas;
     OMC_LAUNCH(k_fold_tally, len, G.stream, f);
-    CUDA_OK(cudaStreamSynchronize(G.stream));
   }
-  std::vector<double> tmp(len);
-  CUDA_OK(cudaMemcpy(tmp.data(), G.d_tally + ofs[tally], len * sizeof(double), cudaMemcpyDeviceToHost));
-  CUDA_OK(cudaMemset(G.d_tally + ofs[tally], 0, len * sizeof(double)));
-  for (int64_t i = 0; i < len; ++i)
-    value[i] += tmp[i];
+  // through the page-locked staging area, in pieces, all on the engine's stream
+  double* stage = reinterpret_cast<double*>(G.h_aos);
+  const int64_t piece = std::max<int64_t>(1, (int64_t)(G.fis_cap * sizeof(omcgpu_site) / sizeof(double)));
+  for (int64_t done = 0; done < len; done += piece) {
+    const int64_t m = std::min<int64_t>(piece, len - done);
+    CUDA_OK(cudaMemcpyAsync(stage, G.d_tally + ofs[tally] + done, m * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+    CUDA_OK(cudaMemsetAsync(G.d_tally + ofs[tally] + done, 0, m * sizeof(double), G.stream));
+    CUDA_OK(cudaStreamSynchronize(G.stream));
+    for (int64_t i = 0; i < m; ++i)
+      value[done + i] += stage[i];
+  }
   return 0;
 }
 
@@ -3061,6 +3184,83 @@ int omcgpu_calculate_xs_device(const double* E, const int32_t* material, int64_t
   return 0;
 }
 
+int omcgpu_collide(int64_t n, const int32_t* material, const double* E, const double* uvw,
+  const uint64_t* seed, double keff, double wgt, double* E_out, double* uvw_out, double* wgt_out,
+  double* k_abs_out, uint64_t* seed_out, int32_t* n_sites, omcgpu_site* sites, int64_t site_capacity,
+  int64_t* n_sites_total)
+{
+  if (!G.ready)
+    return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  if (n <= 0 || n > G.cap)
+    return fail(OMCGPU_E_OUT_OF_BOUNDS, "omcgpu_collide: n exceeds max_particles%s");
+  std::vector<void*> tmp;
+  int rc = 0;
+  auto dalloc = [&](size_t bytes, const void* from) -> void* {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      rc = fail(OMCGPU_E_ALLOCATE, "omcgpu_collide: cudaMalloc failed%s");
+      return nullptr;
+    }
+    tmp.push_back(p);
+    if (from && cudaMemcpy(p, from, bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+      rc = fail(OMCGPU_E_CUDA, "omcgpu_collide: H2D copy failed%s");
+    return p;
+  };
+  CollideArgs a;
+  std::memset(&a, 0, sizeof(a));
+  omcgpu_gen_in in;
+  std::memset(&in, 0, sizeof(in));
+  in.n_particles = n;
+  in.keff = keff;
+  const EvArgs ev = make_args(&in);
+  a.ps = G.ps;
+  a.gc = ev.gc;
+  a.fb = G.fis;
+  a.n = n;
+  a.wgt = wgt;
+  a.material = (const int32_t*)dalloc(n * 4, material);
+  a.E = (const double*)dalloc(n * 8, E);
+  a.uvw = (const double*)dalloc(n * 24, uvw);
+  a.seed = (const uint64_t*)dalloc(n * 8, seed);
+  a.E_out = (double*)dalloc(n * 8, nullptr);
+  a.uvw_out = (double*)dalloc(n * 24, nullptr);
+  a.wgt_out = (double*)dalloc(n * 8, nullptr);
+  a.k_abs_out = (double*)dalloc(n * 8, nullptr);
+  a.seed_out = (uint64_t*)dalloc(n * 8, nullptr);
+  auto done = [&](int code) {
+    for (void* p : tmp)
+      cudaFree(p);
+    return code;
+  };
+  if (rc)
+    return done(rc);
+  cudaMemsetAsync(G.d_counts, 0, N_COUNTS * sizeof(int32_t), G.stream);
+  OMC_LAUNCH(k_probe_collide, n, G.stream, a);
+  if (read_counts())
+    return done(OMCGPU_E_CUDA);
+  if (G.h_counts[5] > 0)
+    return done(fail(OMCGPU_E_PHYSICS, "omcgpu_collide: a neutron found no nuclide to collide with%s"));
+  if (G.h_counts[4] > G.fis_cap || G.h_counts[4] > site_capacity)
+    return done(fail(OMCGPU_E_OUT_OF_BOUNDS, "omcgpu_collide: more fission sites than the bank / caller's buffer holds%s"));
+  G.n_fis = G.h_counts[4];
+  if (sort_fission_bank(n, 0))
+    return done(OMCGPU_E_CUDA);
+  cudaMemcpyAsync(E_out, a.E_out, n * 8, cudaMemcpyDeviceToHost, G.stream);
+  cudaMemcpyAsync(uvw_out, a.uvw_out, n * 24, cudaMemcpyDeviceToHost, G.stream);
+  cudaMemcpyAsync(wgt_out, a.wgt_out, n * 8, cudaMemcpyDeviceToHost, G.stream);
+  cudaMemcpyAsync(k_abs_out, a.k_abs_out, n * 8, cudaMemcpyDeviceToHost, G.stream);
+  cudaMemcpyAsync(seed_out, a.seed_out, n * 8, cudaMemcpyDeviceToHost, G.stream);
+  cudaMemcpyAsync(n_sites, G.ps.n_progeny, n * 4, cudaMemcpyDeviceToHost, G.stream);
+  if (n_sites_total)
+    *n_sites_total = G.n_fis;
+  rc = G.n_fis > 0 ? fetch_bank(G.fis_sorted, sites, G.n_fis) : 0;
+  cudaStreamSynchronize(G.stream);
+  cudaError_t e = cudaGetLastError();
+  if (!rc && e != cudaSuccess)
+    rc = fail(OMCGPU_E_CUDA, "kernel failure: %s", cudaGetErrorString(e));
+  return done(rc);
+}
+
 static int geom_probe(const double* xyz, const double* uvw, int64_t n, int32_t* cell,
   int32_t* instance, int32_t* material, int32_t* n_coord, double* distance, int32_t* surface,
   int32_t* level, int32_t* lattice_trans)
@@ -3072,11 +3272,19 @@ static int geom_probe(const double* xyz, const double* uvw, int64_t n, int32_t* 
   a.ps = G.ps;
   a.n = n;
   std::vector<void*> tmp;
+  bool alloc_failed = false;
   auto dalloc = [&](size_t bytes) {
     void* p = nullptr;
-    cudaMalloc(&p, bytes);
-    tmp.push_back(p);
+    if (cudaMalloc(&p, bytes) != cudaSuccess)
+      alloc_failed = true;
+    else
+      tmp.push_back(p);
     return p;
+  };
+  auto release = [&]() {
+    for (void* p : tmp)
+      cudaFree(p);
+    tmp.clear();
   };
   for (int64_t done = 0; done < n; done += G.cap) {
     const int64_t m = std::min<int64_t>(G.cap, n - done);
@@ -3102,6 +3310,11 @@ static int geom_probe(const double* xyz, const double* uvw, int64_t n, int32_t* 
       a.level = (int32_t*)dalloc(m * 4);
       a.lat_trans = (int32_t*)dalloc(m * 12);
     }
+    if (alloc_failed) {
+      release();
+      cudaGetLastError();
+      return fail(OMCGPU_E_ALLOCATE, "geometry probe: cudaMalloc failed%s");
+    }
     OMC_LAUNCH(k_probe_geom, m, G.stream, a);
     cudaStreamSynchronize(G.stream);
     if (cell) {
@@ -3116,9 +3329,7 @@ static int geom_probe(const double* xyz, const double* uvw, int64_t n, int32_t* 
       cudaMemcpy(level + done, a.level, m * 4, cudaMemcpyDeviceToHost);
       cudaMemcpy(lattice_trans + 3 * done, a.lat_trans, m * 12, cudaMemcpyDeviceToHost);
     }
-    for (void* p : tmp)
-      cudaFree(p);
-    tmp.clear();
+    release();
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
@@ -3183,72 +3394,3 @@ int omcgpu_prn(const uint64_t* seed, int64_t n_seeds, int32_t count, double* out
 }
 
 } // extern "C"
-
-#ifdef OMC_EMU
-// TEST-ONLY, host compile only (tests/_emu; not declared in include/omcgpu.h, absent from
-// libomcgpu.so): one collision_ce per neutron in a plain loop, so that the CPU tier can hold the
-// DEVICE function to the vectors the reference's own collision() wrote
-// (tests/golden/refcoll_ce.npz).  Fission sites of collision k: site_*[site_ofs[k] .. site_ofs[k+1]).
-extern "C" int64_t emu_collide_ce(int64_t n, const int32_t* material, const double* E, const double* uvw,
-  const uint64_t* seed_in, double k_eff, double wgt0, double* E_out, double* uvw_out, double* wgt_out,
-  double* kabs_out, uint64_t* seed_out, int64_t* site_ofs, double* site_E, double* site_u,
-  int32_t* site_group, double* site_time, int64_t site_cap)
-{
-  using namespace omc;
-  if (!G.ready)
-    return -1;
-  const int64_t cap = 64;
-  std::vector<double> c[9];
-  for (auto& v : c)
-    v.assign(cap, 0.0);
-  std::vector<int32_t> dg(cap, 0);
-  std::vector<int64_t> pid(cap, 0), prog(cap, 0);
-  Bank fb;
-  fb.cap = cap;
-  fb.x = c[0].data(); fb.y = c[1].data(); fb.z = c[2].data();
-  fb.u = c[3].data(); fb.v = c[4].data(); fb.w = c[5].data();
-  fb.E = c[6].data(); fb.time = c[7].data(); fb.wgt = c[8].data();
-  fb.delayed_group = dg.data(); fb.parent_id = pid.data(); fb.progeny_id = prog.data();
-  int32_t n_fission = 0;
-  GenCtx gc {};
-  gc.keff = k_eff;
-  gc.n_fission = &n_fission;
-  gc.fission_cap = cap;
-  int64_t total = 0;
-  for (int64_t k = 0; k < n; ++k) {
-    Collider p {};
-    p.r = v3(0., 0., 0.);
-    p.u = v3(uvw[3 * k], uvw[3 * k + 1], uvw[3 * k + 2]);
-    p.E = E[k];
-    p.wgt = wgt0;
-    p.material = material[k];
-    p.seed = seed_in[k];
-    p.id = k;
-    double t, a, f, nf;
-    ce_macro_xs<false>(p.material, p.E, t, a, f, nf, nullptr, 0);
-    p.xs_total = t; p.xs_absorption = a; p.xs_nu_fission = nf;
-    n_fission = 0;
-    bool no_nuclide = false;
-    collision_ce<false>(p, gc, fb, no_nuclide);
-    if (no_nuclide)
-      return -2;
-    E_out[k] = p.E;
-    uvw_out[3 * k] = p.u.x; uvw_out[3 * k + 1] = p.u.y; uvw_out[3 * k + 2] = p.u.z;
-    wgt_out[k] = p.wgt;
-    kabs_out[k] = p.k_abs;
-    seed_out[k] = p.seed;
-    site_ofs[k] = total;
-    if (total + n_fission > site_cap || n_fission > cap)
-      return -3;
-    for (int j = 0; j < n_fission; ++j) {
-      site_E[total] = fb.E[j];
-      site_u[3 * total] = fb.u[j]; site_u[3 * total + 1] = fb.v[j]; site_u[3 * total + 2] = fb.w[j];
-      site_group[total] = fb.delayed_group[j];
-      site_time[total] = fb.time[j];
-      ++total;
-    }
-  }
-  site_ofs[n] = total;
-  return total;
-}
-#endif

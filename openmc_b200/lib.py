@@ -203,6 +203,28 @@ class Engine:
             _p(s, C.c_int32), _p(lv, C.c_int32), _p(lt, C.c_int32)))
         return d, s, lv, lt
 
+    def collide(self, material, E, uvw, seed, keff, wgt):
+        """omcgpu_collide: the collision kernels' device function on independent neutrons.
+        -> dict(E, u, wgt, k_abs, seed, n_sites, sites[(neutron, progeny) order])"""
+        material = np.ascontiguousarray(material, np.int32)
+        E = np.ascontiguousarray(E, np.float64)
+        uvw = np.ascontiguousarray(uvw, np.float64)
+        seed = np.ascontiguousarray(seed, np.uint64)
+        n = E.size
+        out = dict(E=np.zeros(n), u=np.zeros((n, 3)), wgt=np.zeros(n), k_abs=np.zeros(n),
+                   seed=np.zeros(n, np.uint64), n_sites=np.zeros(n, np.int32))
+        cap = 3 * self.max_particles
+        sites = np.zeros(cap, abi.site_dtype)
+        tot = C.c_int64(0)
+        self._check(self.lib.omcgpu_collide(
+            C.c_int64(n), _p(material, C.c_int32), _p(E, C.c_double), _p(uvw, C.c_double),
+            _p(seed, C.c_uint64), C.c_double(keff), C.c_double(wgt), _p(out["E"], C.c_double),
+            _p(out["u"], C.c_double), _p(out["wgt"], C.c_double), _p(out["k_abs"], C.c_double),
+            _p(out["seed"], C.c_uint64), _p(out["n_sites"], C.c_int32), sites.ctypes.data_as(C.c_void_p),
+            C.c_int64(cap), C.byref(tot)))
+        out["sites"] = sites[:tot.value]
+        return out
+
     def future_seed(self, n, seed):
         n = np.ascontiguousarray(n, np.uint64); seed = np.ascontiguousarray(seed, np.uint64)
         out = np.zeros_like(n)
@@ -395,6 +417,10 @@ class Simulation:
                 self.source_bank = np.ascontiguousarray(self.fission_bank[idx])
             return
         self.comm.synchronize_bank(self, seed_id, n_fission)
+        if not self.resident:
+            # the exchange leaves the new source in the DEVICE bank; the host bank is what the
+            # next generation uploads (transport_generation), so it has to follow
+            self.source_bank = np.ascontiguousarray(self.engine.get_source_bank(self.work))
 
     def _calculate_average_keff(self, og, gen, active):
         """src/eigenvalue.cpp:367-418"""

@@ -58,33 +58,33 @@ def test_eigenvalue_matches_oracle(emu_lib):
     sim.simulation_finalize()
 
 
-def test_device_collision_equals_reference_vectors(emu_lib):
-    """the DEVICE function collision_ce (csrc/device.h, host-compiled; the emu-only doorway
-    emu_collide_ce runs it once per neutron) against tests/golden/refcoll_ce.npz -- what the
-    reference's own collision() (src/physics.cpp compiled unmodified, make_reference_collisions.py)
-    left of the same neutrons: energy, direction, weight, k-absorption score, seed and banked
-    fission sites bit for bit, analog absorption and survival biasing"""
-    import ctypes as C
+def check_collide_against_reference_vectors(make_engine):
+    """the DEVICE function collision_ce (csrc/device.h) through the C ABI (omcgpu_collide) against
+    tests/golden/refcoll_ce.npz -- what the reference's own collision() (src/physics.cpp compiled
+    unmodified, tests/golden/make_reference_collisions.py) left of the same neutrons: energy,
+    direction, weight, k-absorption score, seed and banked fission sites bit for bit, analog
+    absorption and survival biasing"""
     import os
-    import ref_geometry
     golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     model = cases.load_model_npz(os.path.join(golden, "ce_model.npz"))
     v = np.load(os.path.join(golden, "refcoll_ce.npz"))
     mat, E, u, seeds = (np.ascontiguousarray(v[k]) for k in ("material", "E_in", "u_in", "seed_in"))
-    p = lambda a: a.ctypes.data_as(C.c_void_p)
     n = E.size
     for tag, survival in (("a", 0), ("s", 1)):
         model.struct.survival_biasing = survival
-        eng = lib.Engine(emu_lib)
-        eng.init(model, 0, 1024)
-        b, cap = ref_geometry._collision_buffers(n)
-        eng.lib.emu_collide_ce.restype = C.c_int64
-        tot = eng.lib.emu_collide_ce(C.c_int64(n), p(mat), p(E), p(u), p(seeds), C.c_double(float(v["k_eff"])),
-                                     C.c_double(float(v[f"{tag}_wgt0"])), p(b["E"]), p(b["u"]), p(b["wgt"]),
-                                     p(b["k_abs"]), p(b["seed"]), p(b["site_ofs"]), p(b["site_E"]), p(b["site_u"]),
-                                     p(b["site_group"]), p(b["site_time"]), C.c_int64(cap))
+        eng = make_engine()
+        eng.init(model, 0, max(n, 1024))
+        r = eng.collide(mat, E, u, seeds, float(v["k_eff"]), float(v[f"{tag}_wgt0"]))
         eng.finalize()
-        assert tot >= 0, tot
-        b = ref_geometry._trim_sites(b, tot)
-        for name in ref_geometry.COLLISION_FIELDS:
-            assert np.array_equal(b[name], v[f"{tag}_{name}"]), (tag, name)
+        got = dict(E=r["E"], u=r["u"], wgt=r["wgt"], k_abs=r["k_abs"], seed=r["seed"],
+                   site_ofs=np.concatenate([[0], np.cumsum(r["n_sites"])]).astype(np.int64),
+                   site_E=r["sites"]["E"], site_u=r["sites"]["u"],
+                   site_group=r["sites"]["delayed_group"], site_time=r["sites"]["time"])
+        # the sorted bank lists the sites of neutron k (parent_id k + 1) in progeny order
+        assert np.array_equal(r["sites"]["parent_id"], np.repeat(np.arange(1, n + 1), r["n_sites"]))
+        for name in got:
+            assert np.array_equal(got[name], v[f"{tag}_{name}"]), (tag, name)
+
+
+def test_device_collision_equals_reference_vectors(emu_lib):
+    check_collide_against_reference_vectors(lambda: lib.Engine(emu_lib))

@@ -97,3 +97,50 @@ def test_host_bank_is_authoritative_between_generations(emu_lib):
     assert out_b.n_fission == out_o.n_fission and out_b.n_events == out_o.n_events
     assert out_b.n_events < out_a.n_events
     eng.finalize()
+
+
+def test_integer_yield_secondaries_are_refused(emu_lib):
+    """an inelastic product whose yield is an integer >= 2 makes the reference bank yield - 1
+    secondary neutrons (src/physics.cpp:1158-1162); the device has no secondary bank and must
+    refuse the model instead of transporting one neutron of unchanged weight"""
+    model, box, of, _ = cases.build_ce()
+    rx = int(np.flatnonzero(np.asarray(model["rx_inelastic"]))[0])
+    fn = int(model["prod_yield_fn"][int(model["rx_prod_ofs"][rx])])
+    o0 = int(model["fn_ofs"][fn])
+    assert int(model["fn_type"][fn]) == abi.OMCGPU_FN_POLYNOMIAL and int(model["fn_ofs"][fn + 1]) - o0 == 1
+    keep = float(model["fn_data"][o0])
+    eng = lib.Engine(emu_lib)
+    try:
+        model["fn_data"][o0] = 2.0
+        with pytest.raises(lib.OmcGpuError) as e:
+            eng.init(model, 0, 100)
+        assert _code(e) == abi.OMCGPU_E_UNSUPPORTED and "yield" in str(e.value)
+        model["fn_data"][o0] = 1.5          # a non-integer yield only scales the weight: accepted
+        eng.init(model, 0, 100)
+        eng.finalize()
+    finally:
+        model["fn_data"][o0] = keep
+
+
+def test_full_fission_bank_stops_banking_like_the_reference(emu_lib, monkeypatch):
+    """fission bank full: the reference warns, takes the progeny counter back and leaves the site
+    loop (src/physics.cpp:233-247) -- no further random numbers are drawn for sites that cannot
+    be stored.  The oracle does the same; with a bank of 3 * 40 sites and k_eff = 0.02 both must
+    bank the same sites, and the count of histories that hit the full bank is reported.  (Which
+    sites fit depends on the order of the collisions -- "results may be non-deterministic" says the
+    reference -- so the histories run one after the other here, as in the oracle.)"""
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", "1000000")
+    model, box, of = cases.build("mg_legendre")
+    o = Oracle(model)
+    n = 40
+    src = o.sample_initial_source(n, box, of)
+    eng = lib.Engine(emu_lib)
+    eng.init(model, 0, n)
+    gi = eng.gen_in(n, 0, 0, 0.02, False)
+    fb, out = eng.transport_generation(gi, src)
+    fb_o, out_o = o.transport_generation(gi, src, 3 * n)
+    assert out.n_fission == 3 * n == out_o.n_fission and out.n_bank_full > 0
+    for f in ("E", "parent_id", "progeny_id", "delayed_group"):
+        assert np.array_equal(fb[f], fb_o[f]), f
+    assert out.n_events == out_o.n_events
+    eng.finalize()

@@ -100,3 +100,45 @@ def test_full_size_next_generation_equals_host_comb(gpu_engine, full, monkeypatc
     gpu_engine.finalize()
     assert out2.n_fission == out.n_fission
     assert bank.tobytes() == want.tobytes()
+
+
+# ------------------------------------------------------------------------------
+# BASELINE.json's full sizes BY VALUE.  Histories are independent (ids and seeds are
+# global, src/simulation.cpp:592,613-616), so the oracle transports a 20 000-history
+# slice of the very same 10^6-history generation with id_offset = the slice's start,
+# and the sites those parents banked must be the ones the GPU banked for them.
+# ------------------------------------------------------------------------------
+def test_full_size_generation_by_value(gpu_engine, full, monkeypatch):
+    """config C2 at BASELINE size (100 000-point grids, 10^6 histories, tallies active): the
+    fission sites of a 20 000-history slice equal the oracle's, parent by parent"""
+    from oracle.binding import Oracle
+    model, src = full
+    fb, out, _ = _generation(gpu_engine, model, src, {}, monkeypatch)
+    o = Oracle(model)
+    lo, n = 437_000, 20_000
+    gi = lib.Engine.gen_in(None, n, lo, 0, 1.0, True)
+    fb_o, out_o = o.transport_generation(gi, np.ascontiguousarray(src[lo:lo + n]))
+    assert out_o.n_lost == 0
+    import cases
+    same, close = cases.bank_parity(fb, fb_o, lo, lo + n)
+    print(f"parents with identical site counts {same:.5f}, sites equal {close:.5f}")
+
+
+def test_full_size_many_nuclide_lookup_by_value(gpu_engine):
+    """config C5 at BASELINE size (300-nuclide fuel x 100 000 points, 1.8 GB of tables):
+    grid indices bit-exact and macroscopic cross sections <= 1e-12 for every material"""
+    import cases
+    from oracle.binding import Oracle
+    m, libx, box, of = examples.pwr_core_ce(n_grid=100_000, n_fuel_nuclides=300)
+    model = nuclide.build_ce_model(m, libx)
+    o = Oracle(model)
+    n_nuc = np.diff(np.asarray(model["mat_nuc_ofs"]))
+    gpu_engine.init(model, 0, 1024)
+    E = cases.xs_probe_energies(model, None, 20000)
+    for mat in (int(np.argmax(n_nuc)), int(np.argmin(n_nuc)), int(model["n_materials"]) - 1):
+        mats = np.full(E.size, mat, np.int32)
+        xs_g, ig_g = gpu_engine.calculate_xs(E, mats, int(n_nuc[mat]))
+        xs_o, ig_o = o.calculate_xs(E, mats, int(n_nuc[mat]))
+        assert np.array_equal(ig_g, ig_o)
+        np.testing.assert_allclose(xs_g, xs_o, rtol=1e-12, atol=0)
+    gpu_engine.finalize()

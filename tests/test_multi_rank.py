@@ -25,7 +25,7 @@ def _free_port():
     return p
 
 
-def _run(name, emu_path, comm):
+def _run(name, emu_path, comm, resident=True):
     import cases
     from openmc_b200 import lib
     from oracle.binding import Oracle
@@ -35,7 +35,8 @@ def _run(name, emu_path, comm):
     # this rank's share of the global source bank (calculate_work, src/simulation.cpp:657-680)
     lo = sum(N // size + (1 if r < N % size else 0) for r in range(rank))
     hi = lo + N // size + (1 if rank < N % size else 0)
-    sim = lib.Simulation(lib.Engine(emu_path), model, N, BATCHES, INACTIVE, full[lo:hi], comm=comm)
+    sim = lib.Simulation(lib.Engine(emu_path), model, N, BATCHES, INACTIVE, full[lo:hi], comm=comm,
+                         resident=resident)
     k = sim.run()
     bank = sim.get_source_bank()
     tallies = [t[:, :, 1].copy() for t in sim.tally_results]
@@ -44,7 +45,7 @@ def _run(name, emu_path, comm):
     return dict(k=k, kgen=kgen, bank=bank, lo=lo, tallies=tallies)
 
 
-def _worker(rank, size, port, name, emu_path, out_dir):
+def _worker(rank, size, port, name, emu_path, out_dir, resident=True):
     for p in (ROOT, os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -53,7 +54,7 @@ def _worker(rank, size, port, name, emu_path, out_dir):
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=size)
     from openmc_b200.comm import TorchComm
-    r = _run(name, emu_path, TorchComm(on_gpu=False))
+    r = _run(name, emu_path, TorchComm(on_gpu=False), resident)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), k=np.array(r["k"]), kgen=np.array(r["kgen"]),
              bank=r["bank"], lo=r["lo"], **{f"t{i}": t for i, t in enumerate(r["tallies"])})
     dist.destroy_process_group()
@@ -78,3 +79,18 @@ def test_ranks_equal_one_rank(emu_lib, name, size, tmp_path):
         assert np.array_equal(bank[f], single["bank"][f]), f
     for i, t in enumerate(single["tallies"]):
         np.testing.assert_allclose(r0[f"t{i}"], t, rtol=1e-10, atol=1e-300)
+
+
+def test_host_bank_path_with_ranks(emu_lib, tmp_path):
+    """Simulation(resident=False) uploads the HOST source bank every generation: with ranks the
+    exchanged bank has to come back to the host, or every generation restarts from the initial
+    source (round-1 advisor finding)"""
+    single = _run("mg_legendre", emu_lib, None)
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, "mg_legendre", emu_lib, str(tmp_path), False), nprocs=2, join=True)
+    ranks = [np.load(tmp_path / f"rank{r}.npz") for r in range(2)]
+    for r in ranks:
+        np.testing.assert_allclose(r["kgen"], single["kgen"], rtol=1e-12)
+    bank = np.concatenate([r["bank"] for r in ranks])
+    for f in ("r", "u", "E", "parent_id", "progeny_id"):
+        assert np.array_equal(bank[f], single["bank"][f]), f
