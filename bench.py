@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=160_000, help="histories of the cpu_baseline sample (~25 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the C5 / C1 / C3 / C4 sub-lines (N = 1 runs of the default workload add them)")
     return ap.parse_args()
 
 
@@ -147,33 +149,122 @@ def cpu_baseline(args, src, n_sample, cores):
 
 
 # ------------------------------------------------------------------------------
-def main():
-    args = parse()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+# byte model of SURVEY.md section 8(d) (the figure `roofline.achieved` is built on)
+# ------------------------------------------------------------------------------
+def bytes_xs(n_nuclides_total, n_lookups):
+    """B_macro(n) = 60 + 116 n per macro lookup actually evaluated"""
+    return 60.0 * n_lookups + 116.0 * n_nuclides_total
 
-    if args.impl == "reference":
-        return reference_arm(args, rank, world)
 
+def state_bytes(levels):
+    """per-event particle-state traffic (SoA, `levels` coordinate levels)"""
+    L1 = max(levels, 1) - 1
+    return {"advance": (200 + 72 * L1) + (150 + 48 * L1), "cross_surface": 160 + 120, "collide": 140 + 120}
+
+
+RED_PEAK = 210e9   # measured L2 RED.F64 rate on this GPU (profiles/r13_red_peak.txt), adds per second
+
+
+def kernel_rooflines(model, steps_stats, count_stats, peak, fused=True):
+    """Per in-loop kernel: algorithmic bytes (section 8(d) model) of ALL its launches in the timed
+    steps / the sum of their durations (CUDA events on the kernel's own stream).  The lookup
+    statistics (share of events whose lookup is evaluated, nuclides per lookup) and the RED count
+    come from one extra, untimed generation run with the engine's counters on."""
+    L = int(model["n_coord_levels"])
+    sb = state_bytes(L)
+    st, cs = steps_stats, count_stats
+    out = {}
+
+    def entry(name, items, ms, launches, bytes_total, extra=None):
+        if ms <= 0 or items <= 0:
+            return
+        e = {"items": int(items), "launches": int(launches), "ms_total": ms,
+             "avg_launch_ms": ms / max(launches, 1),
+             "algorithmic_bytes_per_item": bytes_total / items,
+             "achieved": bytes_total / (ms * 1e-3) / 1e9, "unit": "GB/s", "peak": peak}
+        e["frac"] = e["achieved"] / peak
+        e["items_per_s"] = items / (ms * 1e-3)
+        if extra:
+            e.update(extra)
+        out[name] = e
+
+    # crossing kernel: cross_surface + [lookup] + advance per item (dead particles make no flight;
+    # they are a few per cent and are charged the full event)
+    sfx = "_xa" if fused else ""
+    for k, (name, ev, items, ms, nl) in enumerate((
+            ("k_surface" + sfx, "cross_surface", st["n_items_surface"], st["ms_surface"], st["n_launch_surface"]),
+            ("k_collide" + sfx, "collide", st["n_items_collide"], st["ms_collide"], st["n_launch_collide"]))):
+        c_items = max(cs["n_items_surface"] if k == 0 else cs["n_items_collide"], 1)
+        if fused:
+            lookups_per_item = cs["lookups_done"][k] / c_items
+            nuc_per_item = cs["nuclide_lookups"][k] / c_items
+            b = items * (sb[ev] + sb["advance"] + 120.0) + bytes_xs(nuc_per_item * items, lookups_per_item * items)
+            extra = {"lookups_per_item": lookups_per_item,
+                     "nuclides_per_lookup": cs["nuclide_lookups"][k] / max(cs["lookups_done"][k], 1),
+                     "model": f"{ev} {sb[ev]} B + advance {sb['advance']} B + flight record 120 B + "
+                              "(60 + 116 n) B per lookup evaluated"}
+        else:       # merged sweep: the event alone (lookup and flight are kernels of their own)
+            b = items * float(sb[ev])
+            extra = {"model": f"{ev} {sb[ev]} B"}
+        if k == 1:   # banked fission sites: 104 B each
+            b += 104.0 * st["n_fission"]
+        entry(name, items, ms, nl, b, extra)
+    flights = st["n_items_surface"] + st["n_items_collide"] + st["n_first_flights"]
+    c_flights = max(cs["n_items_surface"] + cs["n_items_collide"] + cs["n_first_flights"], 1)
+    red_per_flight = cs["n_red"] / c_flights
+    if st["ms_score"] > 0:
+        reds = red_per_flight * flights
+        entry("k_score", flights, st["ms_score"], st["n_launch_score"], flights * 120.0 + 8.0 * reds,
+              {"red_per_item": red_per_flight, "red_per_s": reds / (st["ms_score"] * 1e-3),
+               "red_frac_of_measured_peak": reds / (st["ms_score"] * 1e-3) / RED_PEAK,
+               "model": "flight record 120 B + 8 B per RED.F64 (bin, score); bound is the L2 atomic rate "
+                        f"({RED_PEAK / 1e9:.0f} G/s measured, profiles/r13_red_peak.txt), not HBM"})
+    if st.get("ms_xs_kernel", 0) > 0 and cs["lookups_done"][2] > 0:      # stand-alone lookup kernel (merged sweep)
+        items = st["n_xs_kernel_items"]
+        per_item_l = cs["lookups_done"][2] / max(cs["n_xs_kernel_items"], 1)
+        per_item_n = cs["nuclide_lookups"][2] / max(cs["n_xs_kernel_items"], 1)
+        entry("k_xs", items, st["ms_xs_kernel"], st["n_launch_xs"], bytes_xs(per_item_n * items, per_item_l * items),
+              {"lookups_per_item": per_item_l, "nuclide_lookups_per_s": per_item_n * items / (st["ms_xs_kernel"] * 1e-3),
+               "nuclides_per_lookup": cs["nuclide_lookups"][2] / max(cs["lookups_done"][2], 1),
+               "model": "(60 + 116 n) B per lookup evaluated"})
+    return out
+
+
+_STAT_KEYS = ("ms_transport", "ms_xs", "ms_surface", "ms_collide", "ms_score", "n_launch_surface",
+              "n_launch_collide", "n_launch_score", "n_items_surface", "n_items_collide", "n_events",
+              "n_xs_lookups", "n_collisions", "n_crossings", "n_lost", "n_fission", "n_red")
+
+
+def _accumulate(acc, out, n_first):
+    for k in _STAT_KEYS:
+        acc[k] = acc.get(k, 0) + getattr(out, k)
+    acc["n_first_flights"] = acc.get("n_first_flights", 0) + n_first
+    for name in ("lookups_done", "nuclide_lookups"):
+        v = acc.setdefault(name, [0, 0, 0])
+        for k in range(3):
+            v[k] += getattr(out, name)[k]
+    return acc
+
+
+def load_traffic(workload_key):
+    """DRAM bytes per list item of each in-loop kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by profiles/ncu_traffic.py from the .ncu-rep of this command)"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload_key)
+    except Exception:
+        return None
+
+
+def measure(args, workload_key, n_local, steps, warmup, rank, local_rank, world, comm, with_e2e, peak, peaks):
+    """one workload on this rank's GPU: resident loop (`value`), host-buffer loop (`e2e`), per-kernel rooflines"""
     import torch
     import torch.distributed as dist
     from openmc_b200 import lib, source
-    from openmc_b200.csrc import build as build_ext
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    comm = None
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        from openmc_b200.comm import TorchComm
-        comm = TorchComm(on_gpu=True)
-    build_ext.build()
-    model, box, of, workload = build_workload(args)
+    wargs = argparse.Namespace(**vars(args))
+    wargs.workload = workload_key
+    model, box, of, workload = build_workload(wargs)
     eng = lib.Engine()
-    n_local = args.particles
     n_global = n_local * world
     eng.init(model, local_rank, n_local)
     work_lo = rank * n_local
@@ -186,39 +277,55 @@ def main():
             torch.cuda.synchronize()
 
     # ---- resident loop ("value"): source bank stays in HBM between generations
-    sim = lib.Simulation(eng, model, n_global, args.warmup + args.steps, args.warmup, src,
+    sim = lib.Simulation(eng, model, n_global, warmup + steps + 1, warmup, src,
                          device=local_rank, resident=True, comm=comm)
     sim.engine.init = lambda *a, **k: None          # engine already initialised above
     sim.simulation_init()
     eng.set_source_bank(src)
-    for _ in range(args.warmup):
+    acc = {}
+    sim.on_generation = lambda out: _accumulate(acc, out, n_local)
+    for _ in range(warmup):
         sim.next_batch()
+    acc.clear()
     st0 = dict(sim.stats)
     l0 = eng.kernel_launches
     clocks = ClockSampler(local_rank)
     clocks.start()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         sim.next_batch()
     barrier()
     dt = time.perf_counter() - t0
     clk = clocks.stop()
     launches = eng.kernel_launches - l0
-    st = {k: sim.stats[k] - st0[k] for k in st0}
+    st = dict(acc)
+    st["ms_xs_kernel"] = st["ms_xs"] if eng.sweep_kind == 0 else 0.0
+    # one more, untimed generation with the engine's counters on (lookup statistics, RED count)
+    acc.clear()
+    eng.set_option("count_lookups", 1)
+    sim.next_batch()
+    eng.set_option("count_lookups", 0)
+    cs = dict(acc)
+    sim.on_generation = None
+    if eng.sweep_kind == 0:    # merged sweep: every alive history is an item of the lookup kernel
+        st["n_xs_kernel_items"] = st["n_xs_lookups"]; st["n_launch_xs"] = st["n_launch_surface"]
+        cs["n_xs_kernel_items"] = cs["n_xs_lookups"]
     if world > 1:
-        t = torch.tensor([dt, st["ms_transport"], st["ms_xs"]], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dt, st["ms_transport"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, st["ms_transport"], st["ms_xs"] = (float(x) for x in t)
-        c = torch.tensor([st["n_xs_lookups"], st["n_events"], launches], dtype=torch.float64, device="cuda")
+        dt, st["ms_transport"] = (float(x) for x in t)
+        c = torch.tensor([st["n_events"], launches], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        st["n_xs_lookups"], st["n_events"], launches = (int(x) for x in c)
-    value = n_global * args.steps / dt
+        n_events_all, launches = (int(x) for x in c)
+    else:
+        n_events_all = st["n_events"]
+    value = n_global * steps / dt
     k_res = sim.keff_combined()
 
     # ---- end to end through host buffers ("e2e"): the reference-facing call
     e2e = None
-    if not args.no_e2e:
+    if with_e2e:
         # The reference-facing calls on HOST buffers: libopenmc's simulation::source_bank
         # (page-locked once, as allocate_banks would) goes H2D, the generation runs, and
         # the NEXT source bank comes back D2H.  N = 1: omcgpu_next_generation (device sort
@@ -232,7 +339,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         keff = sim.keff
-        for s in range(args.steps):
+        for s in range(steps):
             gi = eng.gen_in(n_local, work_lo, (gen0 + s) * n_global, keff, True)
             h2d += bank.nbytes
             if world == 1:
@@ -254,67 +361,142 @@ def main():
             t = torch.tensor([dt_e], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt_e = float(t[0])
-        e2e = {"value": n_global * args.steps / dt_e, "unit": "particles/s",
-               "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
+        e2e = {"value": n_global * steps / dt_e, "unit": "particles/s",
+               "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps,
                "note": ("omcgpu_next_generation on the page-locked host SourceSite bank: H2D source, event "
                         "loop, device sort + comb, D2H next source" if world == 1 else
                         "per rank: H2D of the page-locked host source bank, event loop, device comb + NCCL "
                         "exchange of the sites that change owner, D2H of the next source bank")}
 
-    # ---- roofline of the dominant kernel (k_xs) from live CUDA-event timings
+    # ---- rooflines of the in-loop kernels from the live CUDA-event timings
+    kernels = kernel_rooflines(model, st, cs, peak, eng.fused_lookup)
+    traffic = load_traffic(workload_key) or {}
+    for name, e in kernels.items():
+        t = traffic.get(name)
+        e["traffic"] = (t["dram_bytes_per_item"] * e["items"] / e["launches"]) if t else None
+        if t:
+            e["ncu"] = {k: t[k] for k in t if k != "dram_bytes_per_item"}
+            e["traffic_over_algorithmic"] = t["dram_bytes_per_item"] / e["algorithmic_bytes_per_item"]
+    roof = None
+    if kernels:
+        dom = max(kernels, key=lambda k: kernels[k]["ms_total"])
+        # the headline object describes the event kernel that takes the most device time; k_score is
+        # bound by L2 atomics (see its red_frac_of_measured_peak), the event kernels by HBM gathers
+        ev_k = [k for k in kernels if k != "k_score"]
+        head = max(ev_k, key=lambda k: kernels[k]["ms_total"]) if ev_k else dom
+        e = kernels[head]
+        roof = {"bound": "hbm", "kernel": head, "achieved": e["achieved"],
+                "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "unit": "GB/s", "frac": e["frac"], "traffic": e["traffic"],
+                "algorithmic_bytes_per_launch": e["algorithmic_bytes_per_item"] * e["items"] / e["launches"],
+                "avg_launch_ms": e["avg_launch_ms"],
+                "how": "algorithmic bytes (SURVEY 8(d) model: per-event state bytes + (60 + 116 n) per lookup "
+                       "evaluated) of all launches of the kernel in the timed steps / the sum of their "
+                       "durations, CUDA events on the kernel's own stream",
+                "largest_kernel_by_time": dom, "kernels": kernels,
+                "step_check_GBps": sum(k["achieved"] * k["ms_total"] for k in kernels.values()) /
+                max(st["ms_transport"], 1e-9)}
+        if bool(model["run_CE"]) and workload_key == args.workload and world == 1:
+            roof["lookup_probe_L2_resident" if workload_key == "pincell_ce" else "lookup_probe"] = \
+                xs_probe(eng, model, min(n_local, 1_000_000), peak, box)
+    res = {"workload": workload, "value": value, "ms_per_step": 1e3 * dt / steps,
+           "device_ms_per_step": st["ms_transport"] / steps, "n_local": n_local, "n_global": n_global,
+           "events_per_particle": n_events_all / (n_global * steps), "k_combined": [k_res[0], k_res[1]],
+           "n_lost": st["n_lost"], "gpu_launches": launches, "clocks": clk, "e2e": e2e, "roofline": roof,
+           "sweep_mode": {2: "paired lists, lookup + flight fused into the crossing / collision kernels",
+                          1: "merged alive list, one lookup + flight kernel",
+                          0: "merged alive list, stand-alone lookup kernel over the (material, energy)-sorted list"
+                          }[eng.sweep_kind],
+           "src": src}
+    eng.finalize()
+    return res
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from openmc_b200.csrc import build as build_ext
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from openmc_b200.comm import TorchComm
+        comm = TorchComm(on_gpu=True)
+    build_ext.build()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    n_nuc = np.diff(np.asarray(model["mat_nuc_ofs"]))
-    roof = None
-    if bool(model["run_CE"]) and st["ms_xs"] > 0:
-        # algorithmic bytes per item: 60 + 88 * n_nuclides(material); the
-        # per-material item counts come from the lookup micro-benchmark below
-        roof = xs_roofline(eng, model, min(n_local, 1_000_000), peak, peaks, box, args.workload)
-        roof["in_loop"] = {"what": "device time of the event kernels that contain the lookup (k_xs_advance; "
-                                   "k_surface_xa + k_collide_xa in sweep mode 2), all generations timed",
-                           "ms_total": st["ms_xs"],
-                           "share_of_transport": st["ms_xs"] / max(st["ms_transport"], 1e-9),
-                           "lookups": st["n_xs_lookups"]}
+
+    r = measure(args, args.workload, args.particles, args.steps, args.warmup, rank, local_rank, world, comm,
+                not args.no_e2e, peak, peaks)
+
+    # ---- the other configurations of BASELINE.json (N = 1 only): C5 is the only one whose tables
+    # (1.8 GB) do not fit L2, i.e. the HBM-gather case of north_star
+    others = {}
+    if world == 1 and not args.no_other_configs and args.workload == "pincell_ce":
+        for key, tag, n_part in (("pwr_core_ce", "C5", 400_000), ("pincell_mg", "C1", 2_000_000),
+                                 ("assembly_ce", "C3", 2_000_000), ("c5g7_core", "C4", 2_000_000)):
+            try:
+                o = measure(args, key, n_part, 3, 3, rank, local_rank, world, None, False, peak, peaks)
+                o.pop("src")
+                others[tag] = {k: o[k] for k in ("workload", "value", "ms_per_step", "device_ms_per_step", "n_local",
+                                                 "events_per_particle", "k_combined", "n_lost", "sweep_mode",
+                                                 "roofline")}
+                others[tag]["unit"] = "particles/s"
+                others[tag]["steps"], others[tag]["warmup"] = 3, 3
+            except Exception as exc:     # a sub-line must not take the bench line down
+                others[tag] = {"error": repr(exc)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        cpu = cpu_baseline(args, src, args.cpu_sample, cores)
+        cpu = cpu_baseline(args, r["src"], args.cpu_sample, cores)
 
     if rank == 0:
         line = {
-            "metric": "particles/sec (active)", "value": value, "unit": "particles/s",
+            "metric": "particles/sec (active)", "value": r["value"], "unit": "particles/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "particles_per_generation_per_gpu": n_local,
-                       "global_particles_per_generation": n_global,
+            "config": {"workload": r["workload"], "particles_per_generation_per_gpu": r["n_local"],
+                       "global_particles_per_generation": r["n_global"],
                        "l2": "working set (cross-section tables + particle state + flight records, > 0.4 GB "
                              "at 1e6 histories) exceeds L2; no flush",
                        "tallies": "the config's tallies, active (C2: 100x100 mesh {flux,fission,nu-fission} "
                                   "+ 500-bin spectrum)",
-                       "parallelism": f"particles split over {world} GPU(s), replicated data"},
-            "device_ms_per_step": st["ms_transport"] / args.steps,
-            "events_per_particle": st["n_events"] / (n_global * args.steps),
-            "xs_lookups_per_s": st["n_xs_lookups"] / (st["ms_xs"] * 1e-3) if st["ms_xs"] > 0 else None,
-            "k_combined": [k_res[0], k_res[1]], "n_lost": st["n_lost"],
-            "gpu_launches": launches, "clocks": clk, "e2e": e2e, "roofline": roof,
-            "cpu_baseline": cpu,
+                       "parallelism": f"particles split over {world} GPU(s), replicated data",
+                       "sweep_mode": r["sweep_mode"]},
+            "device_ms_per_step": r["device_ms_per_step"],
+            "events_per_particle": r["events_per_particle"],
+            "k_combined": r["k_combined"], "n_lost": r["n_lost"],
+            "gpu_launches": r["gpu_launches"], "clocks": r["clocks"], "e2e": r["e2e"], "roofline": r["roofline"],
+            "cpu_baseline": cpu, "other_configs": others or None,
         }
         print(json.dumps(line))
-    eng.finalize()
     if world > 1:
         dist.destroy_process_group()
 
 
-def xs_roofline(eng, model, n, peak, peaks, box, args_workload="pincell_ce"):
-    """macro-xs lookup kernel alone on a device-resident work list (E log-uniform over
-    the library's range, materials by their volume fractions inside the source box --
-    found with the device find_cell probe on uniform points): achieved algorithmic GB/s."""
+def xs_probe(eng, model, n, peak, box):
+    """macro-xs lookup kernel ALONE on a device-resident work list (E log-uniform over the
+    library's range, materials by their volume fractions inside the source box -- found with
+    the device find_cell probe on uniform points).  A secondary entry: on C2 its 48 MB of tables
+    sit in L2 (DRAM traffic far below the algorithmic bytes), so this is L2 gather throughput."""
     import ctypes as C
     import torch
     g = np.random.default_rng(7)
@@ -326,7 +508,7 @@ def xs_roofline(eng, model, n, peak, peaks, box, args_workload="pincell_ce"):
     good = mat[mat >= 0]
     mat = np.where(mat >= 0, mat, good[0] if good.size else 0).astype(np.int32)
     n_nuc = np.diff(np.asarray(model["mat_nuc_ofs"]))
-    alg_bytes = float(np.sum(60 + 88 * n_nuc[mat]))
+    alg_bytes = float(np.sum(60 + 116 * n_nuc[mat]))
     dE = torch.from_numpy(E).cuda()
     dm = torch.from_numpy(mat).cuda()
     out = torch.empty((n, 4), dtype=torch.float64, device="cuda")
@@ -340,22 +522,11 @@ def xs_roofline(eng, model, n, peak, peaks, box, args_workload="pincell_ce"):
             best.append(ms.value)
     t = float(np.mean(best)) * 1e-3
     achieved = alg_bytes / t / 1e9
-    # DRAM bytes of one such launch from the committed `ncu --set full` capture of this very
-    # command (profiles/traffic.json, written from profiles/*_probe_xs_ncu.txt); None if absent
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        ent = tj.get(args_workload)
-        if ent and int(ent.get("lookups", 0)) == int(n):
-            traffic = float(ent["dram_bytes_per_launch"])
-    except Exception:
-        pass
-    return {"bound": "hbm", "kernel": "k_probe_xs (macro-xs lookup, same device function as k_xs)",
-            "achieved": achieved, "peak": peak,
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    return {"kernel": "k_probe_xs (macro-xs lookup alone, unsorted random energies)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": t * 1e3,
-            "lookups_per_s": n / t, "nuclide_lookups_per_s": float(np.sum(n_nuc[mat])) / t}
+            "lookups_per_s": n / t, "nuclide_lookups_per_s": float(np.sum(n_nuc[mat])) / t,
+            "model": "(60 + 116 n) B per lookup"}
 
 
 def reference_arm(args, rank, world):

@@ -359,6 +359,19 @@ typedef struct omcgpu_gen_out {
   double total_weight;        /* sum of source weights                                   */
   double ms_transport;        /* device time of the event loop (CUDA events)             */
   double ms_xs;               /* device time spent in the calculate-xs kernel            */
+  double ms_surface;          /* sum of the launch durations of the crossing kernel (CUDA events on its stream) */
+  double ms_collide;          /* the same for the collision kernel                       */
+  double ms_score;            /* the same for the tally-scoring kernel                   */
+  int64_t n_launch_surface;   /* launches behind ms_surface                              */
+  int64_t n_launch_collide;
+  int64_t n_launch_score;
+  int64_t n_items_surface;    /* list items the crossing kernel processed (sweeps, without the tail) */
+  int64_t n_items_collide;    /* the same for the collision kernel                       */
+  /* with omcgpu_set_option("count_lookups", 1) -- [0] crossing kernel, [1] collision kernel,
+   * [2] elsewhere (first flight, tail, stand-alone lookup kernel): */
+  int64_t lookups_done[3];    /* macro-xs lookups actually evaluated (material / temperature changed) */
+  int64_t nuclide_lookups[3]; /* sum over those of the material's nuclide count          */
+  int64_t n_red;              /* RED.F64 issued by the scoring kernel's mesh ray trace   */
 } omcgpu_gen_out;
 
 /* ------------------------------------------------------------------------- */
@@ -375,6 +388,19 @@ int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles);
 
 /* Release everything (replaces free_event_queues, src/finalize.cpp:57-59). */
 int omcgpu_finalize(void);
+
+/* Run-time knobs of an initialised engine (they survive until omcgpu_finalize):
+ *   "count_lookups"  1: fill omcgpu_gen_out.n_lookups_done / n_nuclide_lookups (costs atomics)
+ *   "tail_threshold" histories alive below which the generation is finished by the tail kernel
+ *   "sync_every"     sweeps the host lets run between two counter read-backs
+ *   "score_part"     mesh cells per part of a flight in the scoring kernel */
+int omcgpu_set_option(const char* name, int64_t value);
+
+/* How omcgpu_init arranged the event loop for this model: 2 = paired lists, crossing / collision
+ * kernels that also do the lookup and the flight; 1 = merged alive list with one lookup + flight
+ * kernel; 0 = merged alive list with the lookup as its own kernel over the (material, energy)-
+ * sorted work list (many-nuclide models); -1 before omcgpu_init. */
+int omcgpu_sweep_kind(void);
 
 /* Last error text (like openmc_err_msg, src/error.cpp:33). */
 const char* omcgpu_last_error(void);

@@ -179,7 +179,8 @@ struct GenCtx {
   int32_t* n_fission;  // fission bank fill
   int32_t* n_lost;
   int32_t* n_bank_full; // histories that found the fission bank full
-  unsigned long long* counters; // [0] events [1] xs lookups [2] collisions [3] crossings
+  unsigned long long* counters; // [0] events [1] xs lookups [2] collisions [3] crossings [4] lookups evaluated [5] their nuclides
+  int32_t count_lookups;       // fill counters [4], [5]
   double* tally_values;
   int64_t tally_replica_stride; // doubles between two replicas of the VALUE arrays (k_score spreads its REDs)
   int32_t tally_replicas;

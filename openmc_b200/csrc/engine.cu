@@ -22,6 +22,7 @@
 
 #if OMC_CUDA
 #include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/discard_iterator.h>
@@ -244,8 +245,29 @@ OMC_D bool ev_init(const PState& ps, const GenCtx& gc, const Bank& src, int64_t 
 }
 
 // Particle::event_calculate_xs, src/particle.cpp:160-230 (locate done at birth)
+// d_counters: [0] events [1] lookups [2] collisions [3] crossings (the tail kernel's share);
+// pairs {lookups evaluated, their nuclides} per kernel kind; REDs issued by the scoring kernel
+constexpr int CNT_SURFACE = 4, CNT_COLLIDE = 6, CNT_OTHER = 8, CNT_RED = 10, N_COUNTERS = 12;
+
+// lookups actually evaluated and their nuclide count (omcgpu_set_option("count_lookups", 1):
+// bench.py's byte model needs the mean number of nuclides per lookup; off in timed generations)
+OMC_D void count_lookup(unsigned long long* counters, int n_nuc)
+{
+#if OMC_CUDA
+  cg::coalesced_group g = cg::coalesced_threads();
+  const unsigned long long tot = cg::reduce(g, (unsigned long long)n_nuc, cg::plus<unsigned long long>());
+  if (g.thread_rank() == 0) {
+    atomicAdd(counters, (unsigned long long)g.size());
+    atomicAdd(counters + 1, tot);
+  }
+#else
+  counters[0] += 1;
+  counters[1] += (unsigned long long)n_nuc;
+#endif
+}
+
 template<bool BX = false>
-OMC_D void ev_xs(const PState& ps, int64_t i, int batch_min = OMC_XS_BATCH_MIN)
+OMC_D void ev_xs(const PState& ps, int64_t i, int batch_min = OMC_XS_BATCH_MIN, unsigned long long* count = nullptr)
 {
   const int m = ps.material[i];
   if (m == MATERIAL_VOID) {
@@ -259,6 +281,8 @@ OMC_D void ev_xs(const PState& ps, int64_t i, int batch_min = OMC_XS_BATCH_MIN)
     if (m != ps.material_last[i] || ps.sqrtkT[i] != ps.sqrtkT_last[i]) {
       double t, a, f, nf;
       ce_macro_xs<BX>(m, ps.E[i], t, a, f, nf, nullptr, 0, batch_min);
+      if (count)
+        count_lookup(count, ld(DM.mat_nuc_ofs + m + 1) - ld(DM.mat_nuc_ofs + m));
       ps.xs_total[i] = t;
       ps.xs_absorption[i] = a;
       ps.xs_fission[i] = f;
@@ -621,7 +645,7 @@ OMC_D void body_xs(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
     return;
-  ev_xs<BX>(a.ps, a.q_in.idx[tid], a.xs_batch_min);
+  ev_xs<BX>(a.ps, a.q_in.idx[tid], a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_OTHER : nullptr);
 }
 OMC_KERNEL_MB(k_xs, EvArgs, body_xs<false>, 2)
 OMC_KERNEL_MB(k_xs_b, EvArgs, body_xs<true>, 2)
@@ -672,7 +696,7 @@ OMC_D void body_xs_advance(int64_t tid, const EvArgs& a)
     return;
   const int32_t i = a.q_in.idx[tid];
   prefetch_particle(a.ps, i, false);
-  ev_xs<BX>(a.ps, i, a.xs_batch_min);
+  ev_xs<BX>(a.ps, i, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_OTHER : nullptr);
   advance_and_route(tid, a, i);
 }
 OMC_KERNEL_MB(k_xs_advance, EvArgs, body_xs_advance<false>, XA_MINBLOCKS)
@@ -693,7 +717,7 @@ OMC_D void body_surface_xa(int64_t tid, const EvArgs& a)
   const int32_t i = a.q_in.idx[tid];
   prefetch_particle(a.ps, i, false);
   if (ev_surface(a.ps, a.gc, i)) {
-    ev_xs<BX>(a.ps, i, a.xs_batch_min);
+    ev_xs<BX>(a.ps, i, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_SURFACE : nullptr);
     advance_and_route(tid, a, i);
   } else {
     no_flight(a, tid);
@@ -712,7 +736,7 @@ OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
   const int32_t i = a.q_in.idx[tid];
   prefetch_particle(a.ps, i, true);
   if (ev_collide<BX>(a.ps, a.gc, a.fb, i)) {
-    ev_xs<BX>(a.ps, i, a.xs_batch_min);
+    ev_xs<BX>(a.ps, i, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_COLLIDE : nullptr);
     advance_and_route(tid, a, i);
   } else {
     no_flight(a, tid);
@@ -746,18 +770,21 @@ struct PartEmit {
   double* r0;     // results + base * ns: the part's row of bin 0
   int bin_stride; // doubles between two mesh bins = mesh_stride * ns
   double val[NS];
+  unsigned n_red = 0; // REDs issued through this functor (reported when count_lookups is on)
   OMC_D void set(double* results, int64_t base, int mesh_stride, int ns)
   {
     r0 = results + base * ns;
     bin_stride = mesh_stride * ns;
   }
-  OMC_D void operator()(int bin, double w) const
+  OMC_D void operator()(int bin, double w)
   {
     double* r = r0 + (int64_t)bin * bin_stride; // one wide multiply-add per mesh cell
 #pragma unroll
     for (int s = 0; s < NS; ++s) // compile-time indices keep val in registers
-      if (val[s] != 0.0)
+      if (val[s] != 0.0) {
         atomic_add_f64(r + s, val[s] * w);
+        ++n_red;
+      }
   }
 };
 
@@ -911,7 +938,7 @@ __device__ __noinline__ int score_lane(int64_t j, int buf, int t, double* values
 // the lanes of a warp trace the parts of the warp's 32 flights round-robin
 template<int NS>
 __device__ __forceinline__ void score_parts(int mesh, int mesh_stride, int ns, double* results, int n_parts,
-  int lane, const int* incl, const double (*sd)[32], const int64_t* sbase)
+  int lane, const int* incl, const double (*sd)[32], const int64_t* sbase, unsigned long long* red_counter)
 {
   PartEmit<NS> em;
   for (int item = lane; item < n_parts; item += 32) {
@@ -930,6 +957,8 @@ __device__ __forceinline__ void score_parts(int mesh, int mesh_stride, int ns, d
     em.set(results, sbase[o], mesh_stride, ns);
     mesh_march(mesh, pr0, pu, ptotal, part_bound(c, onc, ptotal), part_bound(c + 1, onc, ptotal), em);
   }
+  if (red_counter && em.n_red)
+    atomicAdd(red_counter, (unsigned long long)em.n_red);
 }
 
 __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, EvArgs a)
@@ -944,6 +973,7 @@ __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, 
   // it (measured, profiles/r13_red_peak.txt: 143 G RED/s into 30 000 doubles, 210 G/s into
   // >= 300 000), so every block adds into its own replica; omcgpu_tally_results folds them.
   double* values = a.gc.tally_values + (int64_t)(blockIdx.x % a.gc.tally_replicas) * a.gc.tally_replica_stride;
+  unsigned long long* red_counter = a.gc.count_lookups ? a.gc.counters + CNT_RED : nullptr;
   // grid-stride over blocks of flights: with a capped grid (G.score_ctas) the kernel
   // occupies only part of every SM for the whole sweep, so that its RED traffic
   // shares the SM with the latency-bound event kernels of the next sweep
@@ -974,11 +1004,11 @@ __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, 
     double* results = values + ld(DM.tally_result_ofs + t);
     // warp-uniform: a property of the tally
     if (ns == 1)
-      score_parts<1>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp]);
+      score_parts<1>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp], red_counter);
     else if (ns <= 3)
-      score_parts<3>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp]);
+      score_parts<3>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp], red_counter);
     else
-      score_parts<SCORE_NVAL>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp]);
+      score_parts<SCORE_NVAL>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp], red_counter);
   }
   __syncwarp(); // the staging area is reused by the next block of flights
   }
@@ -1067,7 +1097,7 @@ OMC_D void body_tail(int64_t tid, const EvArgs& a)
   int next = a.first_event; // what the histories of this list are waiting for
   for (;;) {
     if (next == NEXT_NONE) {
-      ev_xs<true>(a.ps, i, a.xs_batch_min); // few long-running threads: chain length, not registers, matters
+      ev_xs<true>(a.ps, i, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_OTHER : nullptr); // few long-running threads: chain length, not registers, matters
       ++n_xs;
       next = ev_advance(a.ps, a.gc, a.fl, i, SLOT_LOG);
     }
@@ -1464,7 +1494,8 @@ struct Engine {
   Queue q[4];
   Queue q_alive;              // sweep mode 2: histories alive after k_init
   int32_t* d_counts = nullptr;   // [0..3] queue counts, [4] n_fission, [5] n_lost
-  unsigned long long* d_counters = nullptr; // [4]
+  unsigned long long* d_counters = nullptr; // [8]: events, xs, collisions, crossings (tail), lookups done, nuclide lookups
+  bool count_lookups = false;
   int32_t* h_counts = nullptr;   // pinned
   unsigned long long* h_counters = nullptr;
   int32_t* d_offs = nullptr;     // progeny scan
@@ -1484,6 +1515,8 @@ struct Engine {
   cudaStream_t stream = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evx0[RING] = {}, evx1[RING] = {}, evp0 = nullptr, evp1 = nullptr;
+  // per-kernel device times of a sweep, each on the stream its kernel runs on: [0] crossing, [1] collision, [2] scoring
+  cudaEvent_t evk0[4][RING] = {}, evk1[4][RING] = {}; // [3]: scoring of the collision list's flights
   bool fuse_xs = true;          // k_xs + k_advance as one kernel (ms_xs then covers both)
   bool sort_xs = false;         // sweep mode 1, unfused: k_xs runs over the list sorted by (material, energy)
   bool sort_coll = false;       // OMCGPU_SORT_COLL=1: k_collide in that order too (measured on C5: 211 vs 202 ms, off)
@@ -1504,6 +1537,8 @@ struct Engine {
   int64_t tail_threshold = 16384;
   int score_part = 16;          // measured: 4 / 8 / 16 -> 138.9 / 131.9 / 131.3 ms (profiles/r11_matrix.log)
   int64_t id_offset_last = 0;
+  FILE* trace = nullptr;        // OMCGPU_TRACE=<file>: one line per sweep {generation, sweep, collisions, crossings}
+  int64_t generation_no = 0;
 };
 static Engine G;
 static bool batch_xs_enabled()
@@ -1936,6 +1971,7 @@ static EvArgs make_args(const omcgpu_gen_in* in)
   a.gc.n_lost = G.d_counts + 5;
   a.gc.n_bank_full = G.d_counts + 7;
   a.gc.counters = G.d_counters;
+  a.gc.count_lookups = G.count_lookups ? 1 : 0;
   a.gc.tally_values = G.d_tally;
   a.gc.tally_replicas = G.tally_replicas;
   a.gc.tally_replica_stride = G.tally_stride;
@@ -1979,7 +2015,42 @@ static int sort_fission_bank(int64_t n, int64_t id_offset)
 struct SweepStats {
   int64_t n_xs = 0, n_coll = 0, n_cross = 0;
   double ms_xs = 0.0;
+  double ms_kernel[3] = {0.0, 0.0, 0.0}; // crossing, collision, scoring kernels (sum of launch durations)
+  int64_t n_launch[3] = {0, 0, 0};
+  // scoring runs two sweeps behind the event kernels on its own stream: its event pairs (ring
+  // slot = launch number % RING) are read only once the main stream is known to have waited for them
+  int64_t score_issued = 0, score_read = 0;
+  int score_pairs = 2; // event pairs per scoring launch number (paired mode: one per list)
 };
+// adds the elapsed times of ring slot `ev` (kernels that did not launch recorded no pair)
+static void drain_score_times(SweepStats& st, int64_t upto)
+{
+  for (; st.score_read < upto && st.score_read < st.score_issued; ++st.score_read) {
+    const int ev = (int)(st.score_read % RING);
+    for (int k = 2; k < 4; ++k) {
+      float ms = 0.f;
+      if (k == 3 && (st.score_read == 0 || st.score_pairs < 2))
+        continue; // the first flight (and the merged sweep) has one scoring launch
+      if (cudaEventElapsedTime(&ms, G.evk0[k][ev], G.evk1[k][ev]) == cudaSuccess) {
+        st.ms_kernel[2] += ms;
+        ++st.n_launch[2];
+      } else {
+        cudaGetLastError();
+      }
+    }
+  }
+}
+static void add_kernel_times(SweepStats& st, int ev, const bool* used)
+{
+  for (int k = 0; k < 3; ++k)
+    if (used[k]) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, G.evk0[k][ev], G.evk1[k][ev]) == cudaSuccess) {
+        st.ms_kernel[k] += ms;
+        ++st.n_launch[k];
+      }
+    }
+}
 
 // Order-preserving list build: the histories flagged 1 in ps.next_ev go to `coll`,
 // those flagged 2 to `surf`, both in ascending particle index, and the two counts
@@ -2054,6 +2125,7 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
   // always finds its input count in device memory, launched over the last count
   // the host knows (counts never grow within a generation).
   int cur = 0;
+  st.score_pairs = 1;
   a.q_a = G.q[cur];
   a.q_a.count = G.d_counts + 0;
   OMC_LAUNCH(k_init, n, G.stream, a);
@@ -2095,8 +2167,8 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     a.n_flights = alive_count;
     if (score && score_pending[buf] && G.overlap) // records of sweep-2 must have been consumed
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_score[buf], 0));
-    CUDA_OK(cudaEventRecord(G.evx0[ev], G.stream));
     if (G.fuse_xs) {
+      CUDA_OK(cudaEventRecord(G.evx0[ev], G.stream));
       LAUNCH_XS(k_xs_advance, n_alive, G.stream, a);
       CUDA_OK(cudaEventRecord(G.evx1[ev], G.stream));
     } else {
@@ -2106,8 +2178,10 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
           return rc;
         EvArgs ax = a; // the same histories, in (material, energy) order
         ax.q_in.idx = G.d_vals_out;
+        CUDA_OK(cudaEventRecord(G.evx0[ev], G.stream)); // ms_xs: the lookup kernel alone
         LAUNCH_XS(k_xs, n_alive, G.stream, ax);
       } else {
+        CUDA_OK(cudaEventRecord(G.evx0[ev], G.stream));
         LAUNCH_XS(k_xs, n_alive, G.stream, a);
       }
       CUDA_OK(cudaEventRecord(G.evx1[ev], G.stream));
@@ -2128,7 +2202,10 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     if (score && !score_in_order) {
       if (G.overlap)
         CUDA_OK(cudaStreamWaitEvent(st_score, G.e_adv, 0));
+      CUDA_OK(cudaEventRecord(G.evk0[2][ev], st_score));
       LAUNCH_SCORE(n_alive, st_score, a);
+      CUDA_OK(cudaEventRecord(G.evk1[2][ev], st_score));
+      st.score_issued = sweep + 1;
       if (G.overlap) {
         CUDA_OK(cudaEventRecord(G.e_score[buf], st_score));
         score_pending[buf] = true;
@@ -2140,7 +2217,9 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     a.q_a.count = slot + 2;
     if (G.overlap)
       CUDA_OK(cudaStreamWaitEvent(st_surf, G.e_adv, 0));
+    CUDA_OK(cudaEventRecord(G.evk0[0][ev], st_surf));
     OMC_LAUNCH(k_surface, n_alive, st_surf, a);
+    CUDA_OK(cudaEventRecord(G.evk1[0][ev], st_surf));
     a.q_in = G.q[2];
     a.q_in.count = slot + 0;
     if (G.overlap) {
@@ -2155,10 +2234,13 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
         return rc;
       EvArgs ac = a;
       ac.q_in.idx = G.d_vals_out;
+      CUDA_OK(cudaEventRecord(G.evk0[1][ev], st_coll));
       LAUNCH_XS(k_collide, n_alive, st_coll, ac);
     } else {
+      CUDA_OK(cudaEventRecord(G.evk0[1][ev], st_coll));
       LAUNCH_XS(k_collide, n_alive, st_coll, a);
     }
+    CUDA_OK(cudaEventRecord(G.evk1[1][ev], st_coll));
     if (G.overlap) {
       CUDA_OK(cudaEventRecord(G.e_coll, st_coll));
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_surf, 0));
@@ -2182,12 +2264,17 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
         float ms = 0.f;
         cudaEventElapsedTime(&ms, G.evx0[synced % RING], G.evx1[synced % RING]);
         ms_xs += ms;
+        {
+          const bool used[3] = {true, true, false};
+          add_kernel_times(st, (int)(synced % RING), used);
+        }
         n_xs += n_in_first;
         n_coll += h[0];
         n_cross += h[1];
         n_in_first = h[2];
       }
       n_alive = n_in_first;
+      drain_score_times(st, G.overlap ? sweep - 2 : sweep);
     }
   }
   if (synced < sweep) { // cannot happen with the loop above, kept for safety
@@ -2269,7 +2356,10 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       CUDA_OK(cudaEventRecord(G.e_adv, G.stream));
       CUDA_OK(cudaStreamWaitEvent(st_score, G.e_adv, 0));
     }
+    CUDA_OK(cudaEventRecord(G.evk0[2][0], st_score));
     LAUNCH_SCORE(n_alive0, st_score, a);
+    CUDA_OK(cudaEventRecord(G.evk1[2][0], st_score));
+    st.score_issued = 1;
     if (G.overlap) {
       CUDA_OK(cudaEventRecord(G.e_score[0], st_score));
       score_pending[0] = true;
@@ -2310,7 +2400,9 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     a.fl_buf = 0 * 2 + po;
     if (G.overlap)
       CUDA_OK(cudaStreamWaitEvent(st_surf, G.e_adv, 0));
+    CUDA_OK(cudaEventRecord(G.evk0[0][ev], st_surf));
     LAUNCH_XS(k_surface_xa, n_alive, st_surf, a);
+    CUDA_OK(cudaEventRecord(G.evk1[0][ev], st_surf));
     if (G.overlap)
       CUDA_OK(cudaEventRecord(G.e_surf, st_surf));
     // collisions
@@ -2320,7 +2412,9 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     a.fl_buf = 1 * 2 + po;
     if (G.overlap)
       CUDA_OK(cudaStreamWaitEvent(st_coll, G.e_adv, 0));
+    CUDA_OK(cudaEventRecord(G.evk0[1][ev], st_coll));
     LAUNCH_XS(k_collide_xa, n_alive, st_coll, a);
+    CUDA_OK(cudaEventRecord(G.evk1[1][ev], st_coll));
     if (G.overlap) {
       CUDA_OK(cudaEventRecord(G.e_coll, st_coll));
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_surf, 0));
@@ -2339,13 +2433,18 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       a.fl = G.fl[0 * 2 + po];
       a.fl_buf = 0 * 2 + po;
       a.n_flights = in_slot + 1;
+      CUDA_OK(cudaEventRecord(G.evk0[2][ev], st_score));
       LAUNCH_SCORE(n_alive, st_score, a);
+      CUDA_OK(cudaEventRecord(G.evk1[2][ev], st_score));
       if (G.overlap)
         CUDA_OK(cudaStreamWaitEvent(st_score, G.e_coll, 0));
       a.fl = G.fl[1 * 2 + po];
       a.fl_buf = 1 * 2 + po;
       a.n_flights = in_slot + 0;
+      CUDA_OK(cudaEventRecord(G.evk0[3][ev], st_score));
       LAUNCH_SCORE(n_alive, st_score, a);
+      CUDA_OK(cudaEventRecord(G.evk1[3][ev], st_score));
+      st.score_issued = sweep + 2; // launch numbers 0 (first flight) .. sweep + 1
       if (G.overlap) {
         CUDA_OK(cudaEventRecord(G.e_score[po], st_score));
         score_pending[po] = true;
@@ -2364,11 +2463,19 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
         float ms = 0.f;
         cudaEventElapsedTime(&ms, G.evx0[(known + 1) % RING], G.evx1[(known + 1) % RING]);
         st.ms_xs += ms;
+        {
+          const bool used[3] = {true, true, false};
+          add_kernel_times(st, (int)((known + 1) % RING), used);
+        }
         st.n_coll += hin[0];
         st.n_cross += hin[1];
+        if (G.trace)
+          std::fprintf(G.trace, "%lld %lld %d %d\n", (long long)G.generation_no, (long long)known, hin[0], hin[1]);
         st.n_xs += (int64_t)hout[0] + hout[1];
         n_alive = (int64_t)hout[0] + hout[1];
       }
+      // the main stream waited for scoring launch (sweep - 2) before it issued sweep - 1
+      drain_score_times(st, G.overlap ? sweep - 2 : sweep + 1);
     }
   }
   for (int b = 0; b < 2; ++b)
@@ -2408,10 +2515,11 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
     return fail(OMCGPU_E_OUT_OF_BOUNDS, "n_particles exceeds the source bank / capacity%s");
   std::memset(out, 0, sizeof(*out));
   CUDA_OK(cudaMemsetAsync(G.d_counts, 0, N_COUNTS * sizeof(int32_t), G.stream));
-  CUDA_OK(cudaMemsetAsync(G.d_counters, 0, 4 * sizeof(unsigned long long), G.stream));
+  CUDA_OK(cudaMemsetAsync(G.d_counters, 0, N_COUNTERS * sizeof(unsigned long long), G.stream));
   CUDA_OK(cudaEventRecord(G.ev0, G.stream));
   EvArgs a = make_args(in);
   SweepStats st;
+  ++G.generation_no;
   int rc = G.sweep_mode == 2 ? run_sweeps_paired(a, in, n, st) : run_sweeps_merged(a, in, n, st);
   if (rc)
     return rc;
@@ -2428,7 +2536,7 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
   OMC_LAUNCH(k_reduce, used_chunks, G.stream, r);
   CUDA_OK(cudaMemcpyAsync(G.h_partial, G.d_partial, used_chunks * 6 * sizeof(double),
     cudaMemcpyDeviceToHost, G.stream));
-  CUDA_OK(cudaMemcpyAsync(G.h_counters, G.d_counters, 4 * sizeof(unsigned long long),
+  CUDA_OK(cudaMemcpyAsync(G.h_counters, G.d_counters, N_COUNTERS * sizeof(unsigned long long),
     cudaMemcpyDeviceToHost, G.stream));
   rc = read_counts();
   if (rc)
@@ -2445,6 +2553,20 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
   out->n_fission = G.n_fis;
   out->n_lost = G.h_counts[5];
   out->n_bank_full = G.h_counts[7];
+  drain_score_times(st, st.score_issued); // the stream sync above covers every scoring launch
+  out->ms_surface = st.ms_kernel[0];
+  out->ms_collide = st.ms_kernel[1];
+  out->ms_score = st.ms_kernel[2];
+  out->n_launch_surface = st.n_launch[0];
+  out->n_launch_collide = st.n_launch[1];
+  out->n_launch_score = st.n_launch[2];
+  for (int k = 0; k < 3; ++k) {
+    out->lookups_done[k] = (int64_t)G.h_counters[CNT_SURFACE + 2 * k];
+    out->nuclide_lookups[k] = (int64_t)G.h_counters[CNT_SURFACE + 2 * k + 1];
+  }
+  out->n_red = (int64_t)G.h_counters[CNT_RED];
+  out->n_items_surface = st.n_cross;
+  out->n_items_collide = st.n_coll;
   out->n_xs_lookups = n_xs + (int64_t)G.h_counters[1];
   out->n_collisions = n_coll + (int64_t)G.h_counters[2];
   out->n_crossings = n_cross + (int64_t)G.h_counters[3];
@@ -2483,6 +2605,31 @@ int64_t omcgpu_kernel_launches(void)
   return g_launches;
 }
 
+int omcgpu_sweep_kind(void)
+{
+  if (!G.ready)
+    return -1;
+  return G.sweep_mode == 2 ? 2 : (G.fuse_xs ? 1 : 0);
+}
+
+int omcgpu_set_option(const char* name, int64_t value)
+{
+  if (!name)
+    return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_set_option: no name%s");
+  const std::string k(name);
+  if (k == "count_lookups")
+    G.count_lookups = value != 0;
+  else if (k == "tail_threshold")
+    G.tail_threshold = value;
+  else if (k == "sync_every")
+    G.sync_every = std::min<int64_t>(std::max<int64_t>(1, value), RING / 2);
+  else if (k == "score_part")
+    G.score_part = (int)std::max<int64_t>(1, value);
+  else
+    return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_set_option: unknown option %s", name);
+  return 0;
+}
+
 int omcgpu_finalize(void)
 {
   for (void* p : G.dev_allocs)
@@ -2506,6 +2653,10 @@ int omcgpu_finalize(void)
     for (int k = 0; k < RING; ++k) {
       drop(G.evx0[k]);
       drop(G.evx1[k]);
+      for (int j = 0; j < 4; ++j) {
+        drop(G.evk0[j][k]);
+        drop(G.evk1[j][k]);
+      }
     }
     drop(G.evp0);
     drop(G.evp1);
@@ -2520,6 +2671,8 @@ int omcgpu_finalize(void)
   for (cudaStream_t st : {G.stream, G.s_score, G.s_surf, G.s_coll})
     if (st)
       cudaStreamDestroy(st);
+  if (G.trace)
+    std::fclose(G.trace);
   G = Engine();
   return 0;
 }
@@ -2649,6 +2802,8 @@ static int init_impl(const omcgpu_model* model, int device, int64_t max_particle
 #endif
   if (const char* t = std::getenv("OMCGPU_TAIL_THRESHOLD"))
     G.tail_threshold = std::atoll(t);
+  if (const char* t = std::getenv("OMCGPU_TRACE"))
+    G.trace = std::fopen(t, "a");
   if (const char* t = std::getenv("OMCGPU_SCORE_PART"))
     G.score_part = std::max(1, std::atoi(t));
   const int64_t cap = max_particles;
@@ -2698,7 +2853,7 @@ static int init_impl(const omcgpu_model* model, int device, int64_t max_particle
   rc = rc ? rc : alloc_bank(G.fis, G.fis_cap);
   rc = rc ? rc : alloc_bank(G.fis_sorted, G.fis_cap);
   rc = rc ? rc : dev_alloc(&G.d_counts, N_COUNTS);
-  rc = rc ? rc : dev_alloc(&G.d_counters, 4);
+  rc = rc ? rc : dev_alloc(&G.d_counters, N_COUNTERS);
   for (int k = 0; k < 4; ++k) {
     rc = rc ? rc : dev_alloc(&G.q[k].idx, cap);
     G.q[k].count = G.d_counts + k;
@@ -2789,7 +2944,7 @@ static int init_impl(const omcgpu_model* model, int device, int64_t max_particle
   CUDA_OK(cudaMemcpyToSymbol(c_fl, G.fl, 4 * sizeof(Flights)));
 #endif
   CUDA_OK(cudaMallocHost((void**)&G.h_counts, N_COUNTS * sizeof(int32_t)));
-  CUDA_OK(cudaMallocHost((void**)&G.h_counters, 4 * sizeof(unsigned long long)));
+  CUDA_OK(cudaMallocHost((void**)&G.h_counters, N_COUNTERS * sizeof(unsigned long long)));
   CUDA_OK(cudaMallocHost((void**)&G.h_partial, G.n_chunks * 6 * sizeof(double)));
   CUDA_OK(cudaMallocHost((void**)&G.h_aos, G.fis_cap * sizeof(omcgpu_site)));
   CUDA_OK(cudaEventCreate(&G.ev0));
@@ -2797,6 +2952,10 @@ static int init_impl(const omcgpu_model* model, int device, int64_t max_particle
   for (int k = 0; k < RING; ++k) {
     CUDA_OK(cudaEventCreate(&G.evx0[k]));
     CUDA_OK(cudaEventCreate(&G.evx1[k]));
+    for (int j = 0; j < 4; ++j) {
+      CUDA_OK(cudaEventCreate(&G.evk0[j][k]));
+      CUDA_OK(cudaEventCreate(&G.evk1[j][k]));
+    }
   }
   CUDA_OK(cudaEventCreate(&G.evp0));
   CUDA_OK(cudaEventCreate(&G.evp1));

@@ -73,6 +73,20 @@ class Engine:
     def finalize(self):
         self._check(self.lib.omcgpu_finalize())
 
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.omcgpu_set_option(name.encode(), C.c_int64(value)))
+
+    @property
+    def sweep_kind(self) -> int:
+        """2: paired sweep, lookup + flight inside the crossing / collision kernels; 1: merged
+        sweep with one lookup + flight kernel; 0: merged sweep with the stand-alone lookup kernel
+        over the sorted list (many-nuclide models)"""
+        return int(self.lib.omcgpu_sweep_kind())
+
+    @property
+    def fused_lookup(self) -> bool:
+        return self.sweep_kind == 2
+
     # -- banks -------------------------------------------------------------------
     def set_source_bank(self, bank: np.ndarray):
         bank = np.ascontiguousarray(bank, dtype=abi.site_dtype)
@@ -382,6 +396,8 @@ class Simulation:
                 out = self.engine.run_generation(gi)
             else:
                 self.fission_bank, out = self.engine.transport_generation(gi, self.source_bank)
+            if getattr(self, "on_generation", None):
+                self.on_generation(out)
             st = self.stats
             st["ms_transport"] += out.ms_transport; st["ms_xs"] += out.ms_xs
             st["n_events"] += out.n_events; st["n_xs_lookups"] += out.n_xs_lookups
