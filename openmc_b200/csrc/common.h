@@ -103,6 +103,11 @@ struct Col {
 
 struct PState {
   int64_t cap; // stride between coordinate levels = particles allocated
+  // A PState may also describe ONE particle staged in thread-local memory (the tail kernel keeps
+  // the history it runs to completion there: cap = 1, index 0): `id_shift` is then the particle's
+  // index in the generation, so that ids and seeds stay global
+  int64_t id_shift;
+  int32_t is_local;
   // group A[level]: position + which cell / lattice the level is in
   Col<double, 4> rx, ry, rz;
   Col<int32_t, 8> cell, lattice;

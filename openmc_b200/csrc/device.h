@@ -8,6 +8,8 @@
 #pragma once
 
 #include "common.h"
+#include <cstddef>
+#include <cstring>
 
 namespace omc {
 
@@ -526,6 +528,129 @@ OMC_HD void reset_level(const PState& ps, int64_t i, int lvl)
 }
 
 // =============================================================================
+// One particle's state staged in thread-local memory, laid out as the sector groups of PState so
+// that the very same event functions run on it: a "local view" is a PState whose columns point at
+// the thread's copy (index 0).  Re-reads of a field an earlier event of the kernel wrote are then
+// L1 hits of the thread's own local memory instead of round trips to L2 for gathered global
+// sectors.  NL > 0: everything staged, NL coordinate levels (the tail kernel keeps a history here
+// from take-over to death).  NL == 0: only the groups P1 P2 P4 P5 (128 bytes); coordinate levels
+// and the k accumulators stay in the global columns, pre-offset to the particle.
+// =============================================================================
+template<int NL>
+struct LevelStore {
+  alignas(32) double gA[NL][4];
+  alignas(32) double gB[NL][4];
+  alignas(16) int32_t gC[NL][4];
+  alignas(32) double p3[4];
+};
+template<>
+struct LevelStore<0> {};
+template<int NL>
+struct LocalParticle : LevelStore<NL> {
+  alignas(32) double p1[4], p2[4];
+  alignas(32) int32_t p4[8];
+  alignas(32) double p5[4];
+  int32_t n_progeny;
+  uint8_t next_ev;
+};
+template<int NL>
+OMC_HD PState local_view(LocalParticle<NL>& lp, const PState& g, int64_t index)
+{
+  PState ps;
+  ps.id_shift = index;
+  ps.is_local = NL + 1;
+#define D_(col, base, slot) ps.col.p = reinterpret_cast<double*>(base) + (slot)
+#define I_(col, base, slot) ps.col.p = reinterpret_cast<int32_t*>(base) + (slot)
+  if constexpr (NL > 0) {
+    ps.cap = 1;
+    D_(rx, lp.gA, 0); D_(ry, lp.gA, 1); D_(rz, lp.gA, 2); I_(cell, lp.gA, 6); I_(lattice, lp.gA, 7);
+    D_(ux, lp.gB, 0); D_(uy, lp.gB, 1); D_(uz, lp.gB, 2); I_(universe, lp.gB, 6);
+    I_(lat_x, lp.gC, 0); I_(lat_y, lp.gC, 1); I_(lat_z, lp.gC, 2);
+    D_(k_abs, lp.p3, 0); D_(k_col, lp.p3, 1); D_(k_trk, lp.p3, 2); D_(k_leak, lp.p3, 3);
+    ps.n_progeny = &lp.n_progeny;
+  } else { // global columns, pre-offset so that index 0 is this particle
+    ps.cap = g.cap;
+    ps.rx.p = &g.rx[index]; ps.ry.p = &g.ry[index]; ps.rz.p = &g.rz[index];
+    ps.cell.p = &g.cell[index]; ps.lattice.p = &g.lattice[index];
+    ps.ux.p = &g.ux[index]; ps.uy.p = &g.uy[index]; ps.uz.p = &g.uz[index]; ps.universe.p = &g.universe[index];
+    ps.lat_x.p = &g.lat_x[index]; ps.lat_y.p = &g.lat_y[index]; ps.lat_z.p = &g.lat_z[index];
+    ps.k_abs.p = &g.k_abs[index]; ps.k_col.p = &g.k_col[index]; ps.k_trk.p = &g.k_trk[index];
+    ps.k_leak.p = &g.k_leak[index];
+    ps.n_progeny = g.n_progeny + index;
+  }
+  D_(E, lp.p1, 0); D_(wgt, lp.p1, 1); D_(time, lp.p1, 2);
+  ps.seed.p = reinterpret_cast<uint64_t*>(lp.p1) + 3;
+  D_(xs_total, lp.p2, 0); D_(xs_absorption, lp.p2, 1); D_(xs_fission, lp.p2, 2); D_(xs_nu_fission, lp.p2, 3);
+  I_(n_coord, lp.p4, 0); I_(surface, lp.p4, 1); I_(material, lp.p4, 2); I_(material_last, lp.p4, 3);
+  I_(cell_instance, lp.p4, 4); I_(cell_last0, lp.p4, 5); I_(g, lp.p4, 6); I_(n_event, lp.p4, 7);
+  D_(sqrtkT, lp.p5, 0); D_(sqrtkT_last, lp.p5, 1);
+  I_(b_surface, lp.p5, 4); I_(b_level_trans, lp.p5, 5); I_(g_last, lp.p5, 6);
+#undef D_
+#undef I_
+  ps.next_ev = &lp.next_ev;
+  return ps;
+}
+// whole sector groups, 16 bytes at a time
+OMC_HD void copy_group(void* dst, const void* src, int bytes)
+{
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  for (int k = 0; k < bytes / 16; ++k)
+    reinterpret_cast<int4*>(dst)[k] = reinterpret_cast<const int4*>(src)[k];
+#else
+  std::memcpy(dst, src, (size_t)bytes);
+#endif
+}
+template<int NL>
+OMC_HD void load_local(const PState& g, int64_t i, LocalParticle<NL>& lp)
+{
+  if constexpr (NL > 0) {
+    const int L = DM.n_coord_levels < NL ? DM.n_coord_levels : NL;
+    for (int l = 0; l < L; ++l) {
+      copy_group(lp.gA[l], &g.rx[(int64_t)l * g.cap + i], 32);
+      copy_group(lp.gB[l], &g.ux[(int64_t)l * g.cap + i], 32);
+      copy_group(lp.gC[l], &g.lat_x[(int64_t)l * g.cap + i], 16);
+    }
+    copy_group(lp.p3, &g.k_abs[i], 32);
+    lp.n_progeny = g.n_progeny[i];
+  }
+  copy_group(lp.p1, &g.E[i], 32);
+  copy_group(lp.p2, &g.xs_total[i], 32);
+  copy_group(lp.p4, &g.n_coord[i], 32);
+  copy_group(lp.p5, &g.sqrtkT[i], 32);
+  lp.next_ev = 0;
+}
+// every staged group back to the global columns (whole sectors: no partial-sector writes)
+template<int NL>
+OMC_HD void store_local_all(const PState& g, int64_t i, const LocalParticle<NL>& lp)
+{
+  if constexpr (NL > 0) {
+    const int L = DM.n_coord_levels < NL ? DM.n_coord_levels : NL;
+    for (int l = 0; l < L; ++l) {
+      copy_group(&g.rx[(int64_t)l * g.cap + i], lp.gA[l], 32);
+      copy_group(&g.ux[(int64_t)l * g.cap + i], lp.gB[l], 32);
+      copy_group(&g.lat_x[(int64_t)l * g.cap + i], lp.gC[l], 16);
+    }
+    copy_group(&g.k_abs[i], lp.p3, 32);
+    g.n_progeny[i] = lp.n_progeny;
+  }
+  copy_group(&g.E[i], lp.p1, 32);
+  copy_group(&g.xs_total[i], lp.p2, 32);
+  copy_group(&g.n_coord[i], lp.p4, 32);
+  copy_group(&g.sqrtkT[i], lp.p5, 32);
+}
+// what the rest of the generation reads of a finished history: the k / leakage accumulators and
+// the event count (k_reduce), the progeny count (fission-bank sort)
+template<int NL>
+OMC_HD void store_local_results(const PState& g, int64_t i, const LocalParticle<NL>& lp)
+{
+  static_assert(NL > 0, "the tail kernel stages everything");
+  copy_group(&g.k_abs[i], lp.p3, 32);
+  copy_group(&g.n_coord[i], lp.p4, 32);
+  copy_group(&g.E[i], lp.p1, 32); // (weight 0 = dead: what a later probe of the state expects)
+  g.n_progeny[i] = lp.n_progeny;
+}
+
+// =============================================================================
 // Locate -- src/geometry.cpp:66-98, 102-252, 256-297 ; src/universe.cpp:40-60
 // The walk keeps only the current level in registers and streams the deeper
 // levels straight into their SoA columns.  Neighbour lists only change the
@@ -675,12 +800,36 @@ __device__ __noinline__ bool find_cell_from_ool(int64_t i, int n_coord, int surf
   reset_deeper(c_ps, i, n_coord);
   return find_cell_inner(c_ps, i, n_coord - 1, surface);
 }
+// the same for a particle staged in thread-local memory: the view is rebuilt from the staging
+// area's address (so the caller's view never has to exist in memory)
+template<int NL>
+__device__ __noinline__ bool find_cell_from_local_ool(LocalParticle<NL>* lp, int64_t index, int n_coord, int surface)
+{
+  const PState ps = local_view(*lp, c_ps, index);
+  reset_deeper(ps, 0, n_coord);
+  return find_cell_inner(ps, 0, n_coord - 1, surface);
+}
+template<int NL>
+OMC_HD LocalParticle<NL>* staging_area(const PState& ps)
+{ // p1 is where the view's E column points
+  return reinterpret_cast<LocalParticle<NL>*>(reinterpret_cast<char*>(ps.E.p) - offsetof(LocalParticle<NL>, p1));
+}
 #endif
 OMC_HD bool find_cell_from(const PState& ps, int64_t i, int n_coord, int surface)
 {
 #if OMC_CUDA && defined(__CUDA_ARCH__)
-  (void)ps;
-  return find_cell_from_ool(i, n_coord, surface);
+  switch (ps.is_local) { // a compile-time constant wherever a view is built
+  case 0:
+    return find_cell_from_ool(i, n_coord, surface);
+  case 1:
+    return find_cell_from_local_ool<0>(staging_area<0>(ps), ps.id_shift, n_coord, surface);
+  case 2:
+    return find_cell_from_local_ool<1>(staging_area<1>(ps), ps.id_shift, n_coord, surface);
+  case 4:
+    return find_cell_from_local_ool<3>(staging_area<3>(ps), ps.id_shift, n_coord, surface);
+  default:
+    return find_cell_from_local_ool<OMCGPU_MAX_COORD>(staging_area<OMCGPU_MAX_COORD>(ps), ps.id_shift, n_coord, surface);
+  }
 #else
   reset_deeper(ps, i, n_coord);
   return find_cell_inner(ps, i, n_coord - 1, surface);

@@ -365,6 +365,10 @@ OMC_D int64_t flight_log_reserve(const Flights& fl)
 // (sweeps); slot == SLOT_LOG -- appended to the tail's flight log, scored by this
 // lane only if the log is full or a tally needs the particle's cells.
 constexpr int64_t SLOT_LOG = -1;
+// TAIL: the caller may pass SLOT_LOG (only the tail kernel does); the sweep kernels always own a
+// record slot, and their code then holds no out-of-line scoring call that would force a staged
+// particle's view into memory
+template<bool TAIL = false>
 OMC_D int ev_advance(const PState& ps, const GenCtx& gc, const Flights& fl, int64_t i, int64_t slot)
 {
   const int n_coord = ps.n_coord[i];
@@ -409,13 +413,13 @@ OMC_D int ev_advance(const PState& ps, const GenCtx& gc, const Flights& fl, int6
   const double wgt = ps.wgt[i];
   const double nu_fission = ps.xs_nu_fission[i];
   if (gc.tallies_active && DM.n_tallies > 0) {
-    int32_t pidx = (int32_t)i;
+    int32_t pidx = (int32_t)(ps.id_shift + i); // the particle's index in the generation
     if (slot == SLOT_LOG) {
       pidx = PIDX_LOGGED;
       if (!gc.tally_needs_cells)
         slot = flight_log_reserve(fl);
     }
-    if (slot >= 0) {
+    if (!TAIL || slot >= 0) {
       record_flight(fl, slot, ps, i, n_coord, r0, u0, E, distance, pidx);
     } else {
       ScoreCtx sc;
@@ -557,7 +561,7 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
   p.material = ps.material[i];
   p.seed = ps.seed[i];
   p.n_progeny = ps.n_progeny[i];
-  p.id = gc.id_offset + i + 1;
+  p.id = gc.id_offset + ps.id_shift + i + 1;
   p.xs_total = ps.xs_total[i];
   p.xs_absorption = ps.xs_absorption[i];
   p.xs_nu_fission = ps.xs_nu_fission[i];
@@ -677,6 +681,24 @@ OMC_D void advance_and_route(int64_t tid, const EvArgs& a, int32_t i)
     no_flight(a, tid);
 }
 
+// the same with the particle staged in thread-local memory (`ps` = local view of particle i)
+OMC_D void advance_and_route_local(int64_t tid, const EvArgs& a, const PState& ps, int32_t i)
+{
+  const int next = ev_advance(ps, a.gc, a.fl, 0, tid);
+  if (a.ordered) {
+    a.ps.next_ev[i] = next == NEXT_COLLISION ? 1 : (next == NEXT_SURFACE ? 2 : 0);
+    if (next == NEXT_DEAD)
+      no_flight(a, tid);
+    return;
+  }
+  if (next == NEXT_COLLISION)
+    queue_append(a.q_a, i);
+  else if (next == NEXT_SURFACE)
+    queue_append(a.q_b, i);
+  else
+    no_flight(a, tid);
+}
+
 OMC_D void body_advance(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
@@ -746,6 +768,58 @@ OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
 }
 OMC_KERNEL_MB(k_collide_xa, EvArgs, body_collide_xa<false>, CX_MINBLOCKS)
 OMC_KERNEL_MB(k_collide_xa_b, EvArgs, body_collide_xa<true>, 2)
+
+// OMCGPU_LOCAL_STATE=1: the same two kernels with the particle staged in thread-local memory for
+// the duration of the kernel (all sector groups in with 16-byte loads, events on the local copy,
+// all groups out as whole sectors).  Fields an earlier event of the kernel wrote are then re-read
+// from the thread's own L1-resident local memory, not from the gathered global sectors.
+template<int NL>
+OMC_D void body_surface_xa_local(int64_t tid, const EvArgs& a)
+{
+  if (tid >= *a.q_in.count)
+    return;
+  const int32_t i = a.q_in.idx[tid];
+  LocalParticle<NL> lp;
+  load_local(a.ps, i, lp);
+  const PState ps = local_view(lp, a.ps, i);
+  if (ev_surface(ps, a.gc, 0)) {
+    ev_xs<false>(ps, 0, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_SURFACE : nullptr);
+    advance_and_route_local(tid, a, ps, i);
+  } else {
+    no_flight(a, tid);
+    if (a.ordered)
+      a.ps.next_ev[i] = 0;
+  }
+  store_local_all(a.ps, i, lp);
+}
+template<int NL>
+OMC_D void body_collide_xa_local(int64_t tid, const EvArgs& a)
+{
+  if (tid >= *a.q_in.count)
+    return;
+  const int32_t i = a.q_in.idx[tid];
+  LocalParticle<NL> lp;
+  load_local(a.ps, i, lp);
+  const PState ps = local_view(lp, a.ps, i);
+  if (ev_collide<false>(ps, a.gc, a.fb, 0)) {
+    ev_xs<false>(ps, 0, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_COLLIDE : nullptr);
+    advance_and_route_local(tid, a, ps, i);
+  } else {
+    no_flight(a, tid);
+    if (a.ordered)
+      a.ps.next_ev[i] = 0;
+  }
+  store_local_all(a.ps, i, lp);
+}
+#ifndef XL_MINBLOCKS
+#define XL_MINBLOCKS 3
+#endif
+OMC_KERNEL_MB(k_surface_xa_l0, EvArgs, body_surface_xa_local<0>, XA_MINBLOCKS) // P1 P2 P4 P5 staged, levels global
+OMC_KERNEL_MB(k_surface_xa_l1, EvArgs, body_surface_xa_local<1>, XL_MINBLOCKS) // everything staged, 1 level
+OMC_KERNEL_MB(k_surface_xa_l3, EvArgs, body_surface_xa_local<3>, XL_MINBLOCKS)
+OMC_KERNEL_MB(k_collide_xa_l0, EvArgs, body_collide_xa_local<0>, CX_MINBLOCKS)
+OMC_KERNEL_MB(k_collide_xa_l1, EvArgs, body_collide_xa_local<1>, XL_MINBLOCKS)
+OMC_KERNEL_MB(k_collide_xa_l3, EvArgs, body_collide_xa_local<3>, XL_MINBLOCKS)
 
 // -----------------------------------------------------------------------------
 // k_score -- tracklength tally scoring for the flights k_advance just recorded
@@ -1092,21 +1166,25 @@ OMC_D void body_tail(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
     return;
-  const int32_t i = a.q_in.idx[tid];
+  const int32_t i_global = a.q_in.idx[tid];
+  LocalParticle<OMCGPU_MAX_COORD> lp;
+  load_local(a.ps, i_global, lp);
+  const PState ps = local_view(lp, a.ps, i_global);
+  const int64_t i = 0;
   unsigned long long n_xs = 0, n_coll = 0, n_cross = 0;
   int next = a.first_event; // what the histories of this list are waiting for
   for (;;) {
     if (next == NEXT_NONE) {
-      ev_xs<true>(a.ps, i, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_OTHER : nullptr); // few long-running threads: chain length, not registers, matters
+      ev_xs<true>(ps, i, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_OTHER : nullptr); // few long-running threads: chain length, not registers, matters
       ++n_xs;
-      next = ev_advance(a.ps, a.gc, a.fl, i, SLOT_LOG);
+      next = ev_advance<true>(ps, a.gc, a.fl, i, SLOT_LOG);
     }
     bool alive;
     if (next == NEXT_COLLISION) {
-      alive = ev_collide<true>(a.ps, a.gc, a.fb, i);
+      alive = ev_collide<true>(ps, a.gc, a.fb, i);
       ++n_coll;
     } else if (next == NEXT_SURFACE) {
-      alive = ev_surface(a.ps, a.gc, i);
+      alive = ev_surface(ps, a.gc, i);
       ++n_cross;
     } else {
       break;
@@ -1115,6 +1193,7 @@ OMC_D void body_tail(int64_t tid, const EvArgs& a)
       break;
     next = NEXT_NONE;
   }
+  store_local_results(a.ps, i_global, lp);
   atomic_add_u64(a.gc.counters + 1, n_xs);
   atomic_add_u64(a.gc.counters + 2, n_coll);
   atomic_add_u64(a.gc.counters + 3, n_cross);
@@ -1496,6 +1575,7 @@ struct Engine {
   int32_t* d_counts = nullptr;   // [0..3] queue counts, [4] n_fission, [5] n_lost
   unsigned long long* d_counters = nullptr; // [8]: events, xs, collisions, crossings (tail), lookups done, nuclide lookups
   bool count_lookups = false;
+  int local_state = 0;          // OMCGPU_LOCAL_STATE: crossing / collision kernels stage the particle in local memory (1: all groups, 2: P1 P2 P4 P5)
   int32_t* h_counts = nullptr;   // pinned
   unsigned long long* h_counters = nullptr;
   int32_t* d_offs = nullptr;     // progeny scan
@@ -2401,7 +2481,16 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     if (G.overlap)
       CUDA_OK(cudaStreamWaitEvent(st_surf, G.e_adv, 0));
     CUDA_OK(cudaEventRecord(G.evk0[0][ev], st_surf));
-    LAUNCH_XS(k_surface_xa, n_alive, st_surf, a);
+    if (G.local_state && !G.batch_xs && G.hm.n_coord_levels <= 3) {
+      if (G.local_state == 2)
+        OMC_LAUNCH(k_surface_xa_l0, n_alive, st_surf, a);
+      else if (G.hm.n_coord_levels == 1)
+        OMC_LAUNCH(k_surface_xa_l1, n_alive, st_surf, a);
+      else
+        OMC_LAUNCH(k_surface_xa_l3, n_alive, st_surf, a);
+    } else {
+      LAUNCH_XS(k_surface_xa, n_alive, st_surf, a);
+    }
     CUDA_OK(cudaEventRecord(G.evk1[0][ev], st_surf));
     if (G.overlap)
       CUDA_OK(cudaEventRecord(G.e_surf, st_surf));
@@ -2413,7 +2502,16 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     if (G.overlap)
       CUDA_OK(cudaStreamWaitEvent(st_coll, G.e_adv, 0));
     CUDA_OK(cudaEventRecord(G.evk0[1][ev], st_coll));
-    LAUNCH_XS(k_collide_xa, n_alive, st_coll, a);
+    if (G.local_state && !G.batch_xs && G.hm.n_coord_levels <= 3) {
+      if (G.local_state == 2)
+        OMC_LAUNCH(k_collide_xa_l0, n_alive, st_coll, a);
+      else if (G.hm.n_coord_levels == 1)
+        OMC_LAUNCH(k_collide_xa_l1, n_alive, st_coll, a);
+      else
+        OMC_LAUNCH(k_collide_xa_l3, n_alive, st_coll, a);
+    } else {
+      LAUNCH_XS(k_collide_xa, n_alive, st_coll, a);
+    }
     CUDA_OK(cudaEventRecord(G.evk1[1][ev], st_coll));
     if (G.overlap) {
       CUDA_OK(cudaEventRecord(G.e_coll, st_coll));
@@ -2802,6 +2900,8 @@ static int init_impl(const omcgpu_model* model, int device, int64_t max_particle
 #endif
   if (const char* t = std::getenv("OMCGPU_TAIL_THRESHOLD"))
     G.tail_threshold = std::atoll(t);
+  if (const char* t = std::getenv("OMCGPU_LOCAL_STATE"))
+    G.local_state = std::atoi(t);
   if (const char* t = std::getenv("OMCGPU_TRACE"))
     G.trace = std::fopen(t, "a");
   if (const char* t = std::getenv("OMCGPU_SCORE_PART"))
@@ -2812,6 +2912,8 @@ static int init_impl(const omcgpu_model* model, int device, int64_t max_particle
   const int L = std::max(1, std::min<int>(model->n_coord_levels, OMCGPU_MAX_COORD));
   PState& ps = G.ps;
   ps.cap = cap;
+  ps.id_shift = 0;
+  ps.is_local = 0;
   {
     // sector groups (see PState): one allocation per group, fields at fixed slots
     char *gA = nullptr, *gB = nullptr, *gC = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr,
