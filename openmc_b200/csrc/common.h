@@ -108,6 +108,11 @@ struct PState {
   // index in the generation, so that ids and seeds stay global
   int64_t id_shift;
   int32_t is_local;
+  // many-nuclide materials: running sums of rho_k sigma_t,k after every XS_PREFIX_STRIDE nuclides,
+  // written by the macro lookup and read by the nuclide-sampling walk of the collision, which
+  // then starts at the right block instead of at nuclide 0 (n_prefix = 0: not kept)
+  int32_t n_prefix;
+  double* xs_prefix; // [cap][n_prefix], always a global column
   // group A[level]: position + which cell / lattice the level is in
   Col<double, 4> rx, ry, rz;
   Col<int32_t, 8> cell, lattice;
@@ -139,6 +144,8 @@ struct PState {
 // k_advance at the flight's position in the work list (coalesced) and by the
 // tail kernel through an atomic append; consumed by k_score.  Self-contained,
 // so scoring does not depend on particle state that later events overwrite.
+constexpr int XS_PREFIX_STRIDE = 32;
+
 struct Flights {
   int64_t cap;
   double *x, *y, *z;       // start point (r_last of include/openmc/particle_data.h)
@@ -166,7 +173,8 @@ struct Bank {
 // include/openmc/shared_array.h:71-89).
 struct Queue {
   int32_t* idx;
-  int32_t* count; // device counter
+  int32_t* count;      // device counter
+  const int32_t* base; // keyed lists: both kinds share one sorted array, this list starts at *base (null: 0)
 };
 
 // Per-generation constants + counters visible to every kernel.

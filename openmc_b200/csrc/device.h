@@ -559,6 +559,8 @@ OMC_HD PState local_view(LocalParticle<NL>& lp, const PState& g, int64_t index)
   PState ps;
   ps.id_shift = index;
   ps.is_local = NL + 1;
+  ps.n_prefix = g.n_prefix;
+  ps.xs_prefix = g.xs_prefix;
 #define D_(col, base, slot) ps.col.p = reinterpret_cast<double*>(base) + (slot)
 #define I_(col, base, slot) ps.col.p = reinterpret_cast<int32_t*>(base) + (slot)
   if constexpr (NL > 0) {
@@ -1226,8 +1228,9 @@ OMC_HD double ce_reaction_xs(int rx, const MicroXS& micro)
 #endif
 template<int NB>
 OMC_HD void ce_macro_xs_batch(int k0, int k1, int j_fine, double E, double& t, double& a, double& f,
-  double& nf, int32_t* i_grid_out, int max_nuc)
+  double& nf, int32_t* i_grid_out, int max_nuc, double* prefix_out)
 {
+  static_assert(XS_PREFIX_STRIDE % NB == 0, "a prefix boundary must fall between two batches");
   for (int kb = k0; kb < k1; kb += NB) {
     int nuc[NB], n_grid[NB], lo[NB], len[NB], ig[NB];
     const double* energy[NB];
@@ -1321,6 +1324,10 @@ OMC_HD void ce_macro_xs_batch(int k0, int k1, int j_fine, double E, double& t, d
       if (i_grid_out && (kb + j - k0) < max_nuc)
         i_grid_out[kb + j - k0] = ig[j];
     }
+    // running total after nuclides 0 .. 32 b + 31 of the material: exactly the partial sum the
+    // sampling walk of sample_nuclide (src/physics.cpp:494-518) holds at that point
+    if (prefix_out && (kb + NB - k0) % XS_PREFIX_STRIDE == 0)
+      prefix_out[(kb + NB - k0) / XS_PREFIX_STRIDE - 1] = t;
   }
 }
 
@@ -1414,13 +1421,16 @@ OMC_HD void ce_total_xs_batch(int kb, int k1, int j_fine, double E, double* sig_
 // budget covers the lockstep walk); the host picks the kernel flavour per model.
 template<bool BX>
 OMC_HD void ce_macro_xs(int m, double E, double& t, double& a, double& f, double& nf,
-  int32_t* i_grid_out, int max_nuc, int batch_min = OMC_XS_BATCH_MIN)
+  int32_t* i_grid_out, int max_nuc, int batch_min = OMC_XS_BATCH_MIN, double* prefix_out = nullptr)
 {
   t = a = f = nf = 0.0;
   const int j_fine = ce_fine_index(E);
   const int k0 = ld(DM.mat_nuc_ofs + m), k1 = ld(DM.mat_nuc_ofs + m + 1);
   if (BX && k1 - k0 >= batch_min) {
-    ce_macro_xs_batch<OMC_XS_BATCH>(k0, k1, j_fine, E, t, a, f, nf, i_grid_out, max_nuc);
+    // (a material walked one nuclide at a time has fewer than OMC_XS_BATCH_MIN <= XS_PREFIX_STRIDE
+    // nuclides when prefixes are kept: it has no prefix entry and its collisions walk from 0)
+    ce_macro_xs_batch<OMC_XS_BATCH>(k0, k1, j_fine, E, t, a, f, nf, i_grid_out, max_nuc,
+      k1 - k0 >= 2 * XS_PREFIX_STRIDE ? prefix_out : nullptr);
     return;
   }
   for (int k = k0; k < k1; ++k) {
@@ -1700,7 +1710,8 @@ OMC_HD void collision_mg(Collider& p, int ba, const GenCtx& gc, const Bank& fb)
 // device recomputes the few entries it needs -- same numbers, no cache.
 // =============================================================================
 template<bool BX = false>
-OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no_nuclide)
+OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no_nuclide,
+  const double* prefix = nullptr)
 {
   no_nuclide = false;
   const int m = p.material;
@@ -1713,7 +1724,21 @@ OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no
   if (BX && k1 - k0 >= OMC_XS_BATCH_MIN) {
     // many-nuclide material: the totals come in lockstep batches, the walk itself keeps
     // the reference's order (same partial sums, same nuclide chosen)
-    for (int kb = k0; kb < k1 && nuc < 0; kb += OMC_XS_BATCH) {
+    int kb0 = k0;
+    if (prefix && k1 - k0 >= 2 * XS_PREFIX_STRIDE) {
+      // the macro lookup left the walk's partial sum after every 32 nuclides: skip the blocks
+      // whose partial sum is still below the cutoff (same comparison as the walk's own test, so
+      // the nuclide found is the one the walk from 0 finds)
+      const int nb = (k1 - k0) / XS_PREFIX_STRIDE;
+      int b = 0;
+      while (b < nb && !(prefix[b] >= cutoff))
+        ++b;
+      if (b > 0) {
+        prob = prefix[b - 1];
+        kb0 = k0 + b * XS_PREFIX_STRIDE;
+      }
+    }
+    for (int kb = kb0; kb < k1 && nuc < 0; kb += OMC_XS_BATCH) {
       double sig_t[OMC_XS_BATCH];
       ce_total_xs_batch<OMC_XS_BATCH>(kb, k1, i_log, p.E, sig_t);
 #pragma unroll

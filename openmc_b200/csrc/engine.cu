@@ -62,6 +62,39 @@ static int64_t g_launches = 0;
       body(tid, a); \
   }
 #define OMC_KERNEL(name, ArgT, body) OMC_KERNEL_MB(name, ArgT, body, 1)
+// The same body behind a persistent grid whose warps fetch the next 32 list positions from a device
+// cursor (a.cursor, zero at launch) until the list is exhausted.  With one block per 256 positions a
+// block keeps its registers and warp slots until its slowest warp is done -- the event kernels'
+// lanes differ by an order of magnitude in work (cell search, rejection loops), and ncu showed 46 %
+// of the warp slots occupied; here a warp that is done simply takes the next chunk.
+#define OMC_KERNEL_DYN(name, ArgT, body, MINBLOCKS) \
+  __global__ void __launch_bounds__(BLOCK, MINBLOCKS) name(int64_t n_ub, ArgT a) \
+  { \
+    const int lane = threadIdx.x & 31; \
+    int64_t cnt = *a.q_in.count; \
+    cnt = cnt < n_ub ? cnt : n_ub; \
+    for (;;) { \
+      int base = 0; \
+      if (lane == 0) \
+        base = atomicAdd(a.cursor, 32); \
+      base = __shfl_sync(0xffffffffu, base, 0); \
+      if (base >= cnt) \
+        break; \
+      if (base + lane < cnt) \
+        body((int64_t)base + lane, a); \
+      __syncwarp(); \
+    } \
+  }
+#define OMC_LAUNCH_DYN(name, n_ub, stream, args, ctas_per_sm) \
+  do { \
+    if ((n_ub) > 0) { \
+      unsigned grid_ = (unsigned)(((n_ub) + BLOCK - 1) / BLOCK); \
+      const unsigned cap_ = (unsigned)(dyn_grid_sms() * (ctas_per_sm)); \
+      name<<<grid_ < cap_ ? grid_ : cap_, BLOCK, 0, stream>>>((int64_t)(n_ub), args); \
+      ++g_launches; \
+    } \
+  } while (0)
+static int dyn_grid_sms();
 #define OMC_LAUNCH(name, n_ub, stream, args) \
   do { \
     if ((n_ub) > 0) { \
@@ -71,6 +104,8 @@ static int64_t g_launches = 0;
   } while (0)
 #else
 #define OMC_KERNEL_MB(name, ArgT, body, MINBLOCKS) OMC_KERNEL(name, ArgT, body)
+#define OMC_KERNEL_DYN(name, ArgT, body, MINBLOCKS) OMC_KERNEL(name, ArgT, body)
+#define OMC_LAUNCH_DYN(name, n_ub, stream, args, ctas_per_sm) OMC_LAUNCH(name, n_ub, stream, args)
 #define OMC_KERNEL(name, ArgT, body) \
   void name(int64_t n_ub, ArgT a) \
   { \
@@ -102,9 +137,26 @@ static int64_t g_launches = 0;
     else \
       OMC_LAUNCH(name, n_ub, stream, args); \
   } while (0)
+// crossing / collision kernels of the paired sweep: the persistent, work-fetching flavour when
+// OMCGPU_DYNAMIC is on (and the model does not need the lockstep-lookup flavour)
+#define LAUNCH_XA(name, n_ub, stream, args) \
+  do { \
+    if (dynamic_enabled() && !batch_xs_enabled() && (int64_t)(n_ub) >= low_count_threshold()) { \
+      (args).xs_batch_min = OMC_XS_BATCH_MIN; \
+      OMC_LAUNCH_DYN(name##_dyn, n_ub, stream, args, XA_MINBLOCKS); \
+    } else { \
+      LAUNCH_XS(name, n_ub, stream, args); \
+    } \
+  } while (0)
+static bool dynamic_enabled();
 static bool batch_xs_enabled();
 static int64_t low_count_threshold();
 static int tail_batch_min();
+
+OMC_D int32_t list_item(const Queue& q, int64_t tid)
+{
+  return q.idx[(q.base ? *q.base : 0) + tid];
+}
 
 // warp-aggregated append (ballot + one atomic per warp), cf. north_star
 OMC_D void queue_append(const Queue& q, int32_t value)
@@ -180,6 +232,7 @@ struct EvArgs {
   int32_t first_event;      // k_tail: event the histories of q_in are waiting for (NEXT_NONE: a flight)
   int32_t xs_batch_min;     // lockstep kernels: nuclides in a material from which the lockstep walk is used
   int32_t ordered;          // survivors are flagged in ps.next_ev (lists built in index order) instead of appended
+  int32_t* cursor;          // work cursor of a persistent (work-fetching) launch, zero when the kernel starts
 };
 
 enum { NEXT_NONE = -2, NEXT_DEAD = -1, NEXT_COLLISION = 0, NEXT_SURFACE = 1 };
@@ -280,7 +333,8 @@ OMC_D void ev_xs(const PState& ps, int64_t i, int batch_min = OMC_XS_BATCH_MIN, 
   if (DM.run_CE) {
     if (m != ps.material_last[i] || ps.sqrtkT[i] != ps.sqrtkT_last[i]) {
       double t, a, f, nf;
-      ce_macro_xs<BX>(m, ps.E[i], t, a, f, nf, nullptr, 0, batch_min);
+      ce_macro_xs<BX>(m, ps.E[i], t, a, f, nf, nullptr, 0, batch_min,
+        ps.n_prefix ? ps.xs_prefix + (ps.id_shift + i) * ps.n_prefix : nullptr);
       if (count)
         count_lookup(count, ld(DM.mat_nuc_ofs + m + 1) - ld(DM.mat_nuc_ofs + m));
       ps.xs_total[i] = t;
@@ -368,8 +422,12 @@ constexpr int64_t SLOT_LOG = -1;
 // TAIL: the caller may pass SLOT_LOG (only the tail kernel does); the sweep kernels always own a
 // record slot, and their code then holds no out-of-line scoring call that would force a staged
 // particle's view into memory
+struct AdvanceOut { // what the keyed list build wants to know of the flight (registers, not re-read)
+  int material, b_surface, b_level_trans;
+};
 template<bool TAIL = false>
-OMC_D int ev_advance(const PState& ps, const GenCtx& gc, const Flights& fl, int64_t i, int64_t slot)
+OMC_D int ev_advance(const PState& ps, const GenCtx& gc, const Flights& fl, int64_t i, int64_t slot,
+  AdvanceOut* ao = nullptr)
 {
   const int n_coord = ps.n_coord[i];
   const int surface = ps.surface[i];
@@ -430,6 +488,11 @@ OMC_D int ev_advance(const PState& ps, const GenCtx& gc, const Flights& fl, int6
   ps.k_trk[i] += wgt * distance * nu_fission;
   ps.b_surface[i] = b.surface;
   ps.b_level_trans[i] = b.level | (b.trans << 8);
+  if (ao) {
+    ao->material = m;
+    ao->b_surface = b.surface;
+    ao->b_level_trans = b.level | (b.trans << 8);
+  }
   return (d_coll > b.distance) ? NEXT_SURFACE : NEXT_COLLISION;
 }
 
@@ -570,7 +633,7 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
   ps.surface[i] = SURFACE_NONE;
   if (DM.run_CE) {
     bool no_nuclide;
-    collision_ce<BX>(p, gc, fb, no_nuclide);
+    collision_ce<BX>(p, gc, fb, no_nuclide, ps.n_prefix ? ps.xs_prefix + (ps.id_shift + i) * ps.n_prefix : nullptr);
     if (no_nuclide)
       atomic_add_i32(gc.n_lost, 1);
     if (p.E < DM.energy_cutoff) // src/physics.cpp:67-71
@@ -629,7 +692,7 @@ OMC_D void body_xs_keys(int64_t tid, const KeyArgs& a)
   uint32_t key = 0xffffffffu;
   int32_t i = 0;
   if (tid < *a.q_in.count) {
-    i = a.q_in.idx[tid];
+    i = list_item(a.q_in, tid);
     const int m = a.ps.material[i];
     if (m >= 0 && DM.run_CE) {
       double u = log(a.ps.E[i] / DM.energy_min) * DM.fine_inv_spacing * 8.0; // 1/8 of a fine-hash bin
@@ -649,7 +712,7 @@ OMC_D void body_xs(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
     return;
-  ev_xs<BX>(a.ps, a.q_in.idx[tid], a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_OTHER : nullptr);
+  ev_xs<BX>(a.ps, list_item(a.q_in, tid), a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_OTHER : nullptr);
 }
 OMC_KERNEL_MB(k_xs, EvArgs, body_xs<false>, 2)
 OMC_KERNEL_MB(k_xs_b, EvArgs, body_xs<true>, 2)
@@ -662,31 +725,41 @@ OMC_D void no_flight(const EvArgs& a, int64_t tid)
     a.fl.pidx[tid] = PIDX_NO_FLIGHT;
 }
 
+// What the list build reads of a history after its flight.  ordered == 1: 1 collision, 2 crossing,
+// 0 dead (three-way partition in index order).  ordered == 2 (keyed lists): a class byte -- 0..31
+// the material a collision happens in, 32..254 what a crossing will do (the surface token it
+// crosses, or the level of a lattice step), 255 dead.  The lists are then stable-sorted by class
+// (index order inside a class), so that the lanes of a warp sample the same nuclides, cross the
+// same surface, meet the same boundary condition and search the same candidate cells.
+constexpr int FLAG_DEAD_KEYED = 255, FLAG_FIRST_CROSSING = 32;
+OMC_D uint8_t event_flag(int ordered, int next, const AdvanceOut& ao)
+{
+  if (ordered != 2)
+    return next == NEXT_COLLISION ? 1 : (next == NEXT_SURFACE ? 2 : 0);
+  if (next == NEXT_COLLISION) {
+    const int m = ao.material;
+    return (uint8_t)(m < 0 || m > 31 ? 31 : m);
+  }
+  if (next == NEXT_SURFACE) {
+    const int blt = ao.b_level_trans;
+    const int code = (blt >> 8) != TRANS_NONE ? (blt & 0xff) : 8 + ao.b_surface + DM.n_surfaces;
+    return (uint8_t)(FLAG_FIRST_CROSSING + (code < 222 ? code : 222));
+  }
+  return FLAG_DEAD_KEYED;
+}
+OMC_D uint8_t dead_flag(int ordered)
+{
+  return ordered == 2 ? FLAG_DEAD_KEYED : 0;
+}
+
 // flight of particle i recorded at work-list position tid, then routed to the
 // collision (q_a) or crossing (q_b) list
 OMC_D void advance_and_route(int64_t tid, const EvArgs& a, int32_t i)
 {
-  const int next = ev_advance(a.ps, a.gc, a.fl, i, tid);
+  AdvanceOut ao = {0, 0, 0};
+  const int next = ev_advance(a.ps, a.gc, a.fl, i, tid, &ao);
   if (a.ordered) {
-    a.ps.next_ev[i] = next == NEXT_COLLISION ? 1 : (next == NEXT_SURFACE ? 2 : 0);
-    if (next == NEXT_DEAD)
-      no_flight(a, tid);
-    return;
-  }
-  if (next == NEXT_COLLISION)
-    queue_append(a.q_a, i);
-  else if (next == NEXT_SURFACE)
-    queue_append(a.q_b, i);
-  else
-    no_flight(a, tid);
-}
-
-// the same with the particle staged in thread-local memory (`ps` = local view of particle i)
-OMC_D void advance_and_route_local(int64_t tid, const EvArgs& a, const PState& ps, int32_t i)
-{
-  const int next = ev_advance(ps, a.gc, a.fl, 0, tid);
-  if (a.ordered) {
-    a.ps.next_ev[i] = next == NEXT_COLLISION ? 1 : (next == NEXT_SURFACE ? 2 : 0);
+    a.ps.next_ev[i] = event_flag(a.ordered, next, ao);
     if (next == NEXT_DEAD)
       no_flight(a, tid);
     return;
@@ -703,7 +776,7 @@ OMC_D void body_advance(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
     return;
-  advance_and_route(tid, a, a.q_in.idx[tid]);
+  advance_and_route(tid, a, list_item(a.q_in, tid));
 }
 OMC_KERNEL(k_advance, EvArgs, body_advance)
 
@@ -716,7 +789,7 @@ OMC_D void body_xs_advance(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
     return;
-  const int32_t i = a.q_in.idx[tid];
+  const int32_t i = list_item(a.q_in, tid);
   prefetch_particle(a.ps, i, false);
   ev_xs<BX>(a.ps, i, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_OTHER : nullptr);
   advance_and_route(tid, a, i);
@@ -736,7 +809,7 @@ OMC_D void body_surface_xa(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
     return;
-  const int32_t i = a.q_in.idx[tid];
+  const int32_t i = list_item(a.q_in, tid);
   prefetch_particle(a.ps, i, false);
   if (ev_surface(a.ps, a.gc, i)) {
     ev_xs<BX>(a.ps, i, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_SURFACE : nullptr);
@@ -744,18 +817,19 @@ OMC_D void body_surface_xa(int64_t tid, const EvArgs& a)
   } else {
     no_flight(a, tid);
     if (a.ordered)
-      a.ps.next_ev[i] = 0;
+      a.ps.next_ev[i] = dead_flag(a.ordered);
   }
 }
 OMC_KERNEL_MB(k_surface_xa, EvArgs, body_surface_xa<false>, XA_MINBLOCKS)
 OMC_KERNEL_MB(k_surface_xa_b, EvArgs, body_surface_xa<true>, 2)
+OMC_KERNEL_DYN(k_surface_xa_dyn, EvArgs, body_surface_xa<false>, XA_MINBLOCKS)
 
 template<bool BX>
 OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
     return;
-  const int32_t i = a.q_in.idx[tid];
+  const int32_t i = list_item(a.q_in, tid);
   prefetch_particle(a.ps, i, true);
   if (ev_collide<BX>(a.ps, a.gc, a.fb, i)) {
     ev_xs<BX>(a.ps, i, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_COLLIDE : nullptr);
@@ -763,63 +837,13 @@ OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
   } else {
     no_flight(a, tid);
     if (a.ordered)
-      a.ps.next_ev[i] = 0;
+      a.ps.next_ev[i] = dead_flag(a.ordered);
   }
 }
 OMC_KERNEL_MB(k_collide_xa, EvArgs, body_collide_xa<false>, CX_MINBLOCKS)
 OMC_KERNEL_MB(k_collide_xa_b, EvArgs, body_collide_xa<true>, 2)
+OMC_KERNEL_DYN(k_collide_xa_dyn, EvArgs, body_collide_xa<false>, CX_MINBLOCKS)
 
-// OMCGPU_LOCAL_STATE=1: the same two kernels with the particle staged in thread-local memory for
-// the duration of the kernel (all sector groups in with 16-byte loads, events on the local copy,
-// all groups out as whole sectors).  Fields an earlier event of the kernel wrote are then re-read
-// from the thread's own L1-resident local memory, not from the gathered global sectors.
-template<int NL>
-OMC_D void body_surface_xa_local(int64_t tid, const EvArgs& a)
-{
-  if (tid >= *a.q_in.count)
-    return;
-  const int32_t i = a.q_in.idx[tid];
-  LocalParticle<NL> lp;
-  load_local(a.ps, i, lp);
-  const PState ps = local_view(lp, a.ps, i);
-  if (ev_surface(ps, a.gc, 0)) {
-    ev_xs<false>(ps, 0, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_SURFACE : nullptr);
-    advance_and_route_local(tid, a, ps, i);
-  } else {
-    no_flight(a, tid);
-    if (a.ordered)
-      a.ps.next_ev[i] = 0;
-  }
-  store_local_all(a.ps, i, lp);
-}
-template<int NL>
-OMC_D void body_collide_xa_local(int64_t tid, const EvArgs& a)
-{
-  if (tid >= *a.q_in.count)
-    return;
-  const int32_t i = a.q_in.idx[tid];
-  LocalParticle<NL> lp;
-  load_local(a.ps, i, lp);
-  const PState ps = local_view(lp, a.ps, i);
-  if (ev_collide<false>(ps, a.gc, a.fb, 0)) {
-    ev_xs<false>(ps, 0, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_COLLIDE : nullptr);
-    advance_and_route_local(tid, a, ps, i);
-  } else {
-    no_flight(a, tid);
-    if (a.ordered)
-      a.ps.next_ev[i] = 0;
-  }
-  store_local_all(a.ps, i, lp);
-}
-#ifndef XL_MINBLOCKS
-#define XL_MINBLOCKS 3
-#endif
-OMC_KERNEL_MB(k_surface_xa_l0, EvArgs, body_surface_xa_local<0>, XA_MINBLOCKS) // P1 P2 P4 P5 staged, levels global
-OMC_KERNEL_MB(k_surface_xa_l1, EvArgs, body_surface_xa_local<1>, XL_MINBLOCKS) // everything staged, 1 level
-OMC_KERNEL_MB(k_surface_xa_l3, EvArgs, body_surface_xa_local<3>, XL_MINBLOCKS)
-OMC_KERNEL_MB(k_collide_xa_l0, EvArgs, body_collide_xa_local<0>, CX_MINBLOCKS)
-OMC_KERNEL_MB(k_collide_xa_l1, EvArgs, body_collide_xa_local<1>, XL_MINBLOCKS)
-OMC_KERNEL_MB(k_collide_xa_l3, EvArgs, body_collide_xa_local<3>, XL_MINBLOCKS)
 
 // -----------------------------------------------------------------------------
 // k_score -- tracklength tally scoring for the flights k_advance just recorded
@@ -1051,8 +1075,20 @@ __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, 
   // grid-stride over blocks of flights: with a capped grid (G.score_ctas) the kernel
   // occupies only part of every SM for the whole sweep, so that its RED traffic
   // shares the SM with the latency-bound event kernels of the next sweep
-  for (int64_t base = (int64_t)blockIdx.x * BLOCK; base < n && base < n_ub; base += (int64_t)gridDim.x * BLOCK) {
-  const int64_t tid = base + threadIdx.x;
+  // a warp's 32 flights at a time: either a static block-strided walk, or (a.cursor: persistent
+  // grid) the next chunk fetched from a device cursor, so that no warp slot idles while another
+  // warp of its block traces long flights
+  int64_t wbase = (int64_t)blockIdx.x * BLOCK + 32 * warp;
+  for (;; wbase += (int64_t)gridDim.x * BLOCK) {
+  if (a.cursor) {
+    int fetched = 0;
+    if (lane == 0)
+      fetched = atomicAdd(a.cursor, 32);
+    wbase = __shfl_sync(0xffffffffu, fetched, 0);
+  }
+  if (wbase >= n || wbase >= n_ub)
+    break;
+  const int64_t tid = wbase + lane;
   const bool active = tid < n && a.fl.pidx[tid] != PIDX_NO_FLIGHT;
   for (int t = 0; t < DM.n_tallies; ++t) {
     __syncwarp(); // lanes leave the part loop of the previous tally at different times
@@ -1094,6 +1130,8 @@ static int g_score_grid_cap = 0; // 0: one block per BLOCK flights; else at most
       unsigned grid_ = (unsigned)(((n_ub) + BLOCK - 1) / BLOCK); \
       if (g_score_grid_cap > 0 && grid_ > (unsigned)g_score_grid_cap) \
         grid_ = (unsigned)g_score_grid_cap; \
+      if ((args).cursor && grid_ > (unsigned)(dyn_grid_sms() * SCORE_MINBLOCKS)) \
+        grid_ = (unsigned)(dyn_grid_sms() * SCORE_MINBLOCKS); \
       k_score<<<grid_, BLOCK, 0, stream>>>((int64_t)(n_ub), args); \
       ++g_launches; \
     } \
@@ -1132,7 +1170,7 @@ OMC_D void body_surface(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
     return;
-  const int32_t i = a.q_in.idx[tid];
+  const int32_t i = list_item(a.q_in, tid);
   prefetch_particle(a.ps, i, false);
   const bool alive = ev_surface(a.ps, a.gc, i);
   if (a.ordered)
@@ -1147,7 +1185,7 @@ OMC_D void body_collide(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
     return;
-  const int32_t i = a.q_in.idx[tid];
+  const int32_t i = list_item(a.q_in, tid);
   prefetch_particle(a.ps, i, true);
   const bool alive = ev_collide<BX>(a.ps, a.gc, a.fb, i);
   if (a.ordered)
@@ -1166,7 +1204,7 @@ OMC_D void body_tail(int64_t tid, const EvArgs& a)
 {
   if (tid >= *a.q_in.count)
     return;
-  const int32_t i_global = a.q_in.idx[tid];
+  const int32_t i_global = list_item(a.q_in, tid);
   LocalParticle<OMCGPU_MAX_COORD> lp;
   load_local(a.ps, i_global, lp);
   const PState ps = local_view(lp, a.ps, i_global);
@@ -1217,6 +1255,50 @@ constexpr int TAIL_BLOCK = 64;
     OMC_LAUNCH(k_tail, n_ub, stream, args); \
   } while (0)
 #endif
+
+// ---- keyed lists: where the collision classes end and the dead begin in the sorted flags ----
+struct BoundsArgs {
+  const uint8_t* keys; // sorted ascending
+  int64_t n;
+  int32_t* counts; // [0] collisions, [1] crossings
+};
+OMC_D int64_t first_not_below(const uint8_t* k, int64_t n, int v)
+{
+  int64_t lo = 0, len = n;
+  while (len > 0) {
+    const int64_t half = len >> 1;
+    if (k[lo + half] < v) {
+      lo += half + 1;
+      len -= half + 1;
+    } else {
+      len = half;
+    }
+  }
+  return lo;
+}
+OMC_D void body_bounds(int64_t tid, const BoundsArgs& a)
+{
+  if (tid == 0) {
+    const int64_t c = first_not_below(a.keys, a.n, FLAG_FIRST_CROSSING);
+    a.counts[0] = (int32_t)c;
+  } else if (tid == 1) {
+    const int64_t c = first_not_below(a.keys, a.n, FLAG_FIRST_CROSSING);
+    const int64_t d = first_not_below(a.keys, a.n, FLAG_DEAD_KEYED);
+    a.counts[1] = (int32_t)(d - c);
+  }
+}
+OMC_KERNEL(k_bounds, BoundsArgs, body_bounds)
+
+struct IotaArgs {
+  int32_t* v;
+  int64_t n;
+};
+OMC_D void body_iota(int64_t tid, const IotaArgs& a)
+{
+  if (tid < a.n)
+    a.v[tid] = (int32_t)tid;
+}
+OMC_KERNEL(k_iota, IotaArgs, body_iota)
 
 // ---- deterministic reduction of the per-particle accumulators ------------------
 // (event_death, src/particle.cpp:475-512: global_tally_* += ..., total_weight)
@@ -1554,7 +1636,9 @@ static int fail(int code, const char* fmt, const char* detail = "")
 
 constexpr int RING = 32;              // sweeps whose counters stay readable
 constexpr int RING_OFS = 8;           // d_counts: [0] alive after k_init, [4] fission sites, [5] lost, [6] tail flight log, [7] bank-full hits
-constexpr int N_COUNTS = RING_OFS + 4 * RING;
+constexpr int SLOT = 8;               // ints per ring slot: [0] collisions [1] crossings [2] next alive (merged sweep)
+                                      // [4] [5] work cursors of the crossing / collision kernel, [6] [7] of their scoring launches
+constexpr int N_COUNTS = RING_OFS + SLOT * RING;
 
 struct Engine {
   bool ready = false;
@@ -1575,7 +1659,6 @@ struct Engine {
   int32_t* d_counts = nullptr;   // [0..3] queue counts, [4] n_fission, [5] n_lost
   unsigned long long* d_counters = nullptr; // [8]: events, xs, collisions, crossings (tail), lookups done, nuclide lookups
   bool count_lookups = false;
-  int local_state = 0;          // OMCGPU_LOCAL_STATE: crossing / collision kernels stage the particle in local memory (1: all groups, 2: P1 P2 P4 P5)
   int32_t* h_counts = nullptr;   // pinned
   unsigned long long* h_counters = nullptr;
   int32_t* d_offs = nullptr;     // progeny scan
@@ -1605,6 +1688,13 @@ struct Engine {
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   bool ordered = true;          // sweep mode 2: lists rebuilt in particle-index order after every sweep
+  bool dynamic_score = false;   // OMCGPU_DYNAMIC_SCORE=1: the same for the scoring kernel
+  bool dynamic = false;         // OMCGPU_DYNAMIC=1: persistent crossing / collision kernels whose warps fetch work from a cursor
+  bool keyed = false;           // ... and stable-sorted by event class (material / surface crossed): OMCGPU_KEYED=1
+  uint8_t* d_key_out = nullptr;
+  int32_t* d_iota = nullptr;
+  void* d_ksort_tmp = nullptr;
+  size_t ksort_tmp_bytes = 0;
   void* d_part_tmp = nullptr;   // cub::DevicePartition scratch
   size_t part_tmp_bytes = 0;
   int64_t low_count = 0;        // OMCGPU_LOW_COUNT: below this many alive histories sweeps and tail use the lockstep
@@ -1624,6 +1714,14 @@ static Engine G;
 static bool batch_xs_enabled()
 {
   return G.batch_xs;
+}
+static bool dynamic_enabled()
+{
+  return G.dynamic;
+}
+static int dyn_grid_sms()
+{
+  return G.n_sm;
 }
 static int64_t low_count_threshold()
 {
@@ -2169,6 +2267,34 @@ static int build_lists(int64_t n, int32_t* coll, int32_t* surf, int32_t* counts,
   return 0;
 }
 
+// Keyed list build: one stable radix pass over the class bytes of all n histories (see
+// event_flag) leaves the collision list in list[0, counts[0]) and the crossing list behind it,
+// each sorted by class with ascending particle index inside a class; the dead sort to the end.
+static int build_lists_keyed(int64_t n, int32_t* list, int32_t* counts, cudaStream_t stream)
+{
+#if OMC_CUDA
+  size_t bytes = G.ksort_tmp_bytes;
+  CUDA_OK(cub::DeviceRadixSort::SortPairs(G.d_ksort_tmp, bytes, G.ps.next_ev, G.d_key_out, G.d_iota, list, (int)n,
+    0, 8, stream));
+  g_launches += 3;
+#else
+  (void)stream;
+  std::vector<int32_t> order((size_t)n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [](int32_t x, int32_t y) { return G.ps.next_ev[x] < G.ps.next_ev[y]; });
+  for (int64_t k = 0; k < n; ++k) {
+    list[k] = order[k];
+    G.d_key_out[k] = G.ps.next_ev[order[k]];
+  }
+#endif
+  BoundsArgs b;
+  b.keys = G.d_key_out;
+  b.n = n;
+  b.counts = counts;
+  OMC_LAUNCH(k_bounds, 2, stream, b);
+  return 0;
+}
+
 // work list `q` re-ordered by (material, energy) into G.d_vals_out (see body_xs_keys)
 static int sort_by_energy(const Queue& q, int64_t n_ub, cudaStream_t stream)
 {
@@ -2233,8 +2359,8 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
   while (n_alive > 0 && n_alive > G.tail_threshold) {
     const int nxt = 1 - cur;
     const int buf = (int)(sweep & 1);
-    int32_t* slot = G.d_counts + RING_OFS + 4 * (sweep % RING);
-    CUDA_OK(cudaMemsetAsync(slot, 0, 4 * sizeof(int32_t), G.stream));
+    int32_t* slot = G.d_counts + RING_OFS + SLOT * (sweep % RING);
+    CUDA_OK(cudaMemsetAsync(slot, 0, SLOT * sizeof(int32_t), G.stream));
     a.q_in = G.q[cur];
     a.q_in.count = alive_count;
     const int ev = (int)(sweep % RING);
@@ -2275,6 +2401,7 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     // cell / universe filters read the live coordinate levels: score before the
     // crossing and collision kernels may change them
     const bool score_in_order = score && G.tally_needs_cells;
+    a.cursor = nullptr;
     if (score_in_order)
       LAUNCH_SCORE(n_alive, G.stream, a);
     if (G.overlap)
@@ -2283,6 +2410,7 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       if (G.overlap)
         CUDA_OK(cudaStreamWaitEvent(st_score, G.e_adv, 0));
       CUDA_OK(cudaEventRecord(G.evk0[2][ev], st_score));
+      a.cursor = nullptr;
       LAUNCH_SCORE(n_alive, st_score, a);
       CUDA_OK(cudaEventRecord(G.evk1[2][ev], st_score));
       st.score_issued = sweep + 1;
@@ -2340,7 +2468,7 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       if (rc)
         return rc;
       for (; synced < sweep; ++synced) {
-        const int32_t* h = G.h_counts + RING_OFS + 4 * (synced % RING);
+        const int32_t* h = G.h_counts + RING_OFS + SLOT * (synced % RING);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, G.evx0[synced % RING], G.evx1[synced % RING]);
         ms_xs += ms;
@@ -2376,6 +2504,7 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       if (rc)
         return rc;
       a.n_flights = G.fl[0].count;
+      a.cursor = nullptr;
       LAUNCH_SCORE(std::min<int64_t>(G.h_counts[6], G.fl[0].cap), G.stream, a);
     }
   }
@@ -2395,7 +2524,7 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
 // s + 1 runs.
 static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, SweepStats& st)
 {
-  auto slot_of = [](int64_t g) { return G.d_counts + RING_OFS + 4 * (g % RING); };
+  auto slot_of = [](int64_t g) { return G.d_counts + RING_OFS + SLOT * (g % RING); };
   const bool score = in->tallies_active && G.hm.n_tallies > 0;
   cudaStream_t st_score = G.overlap ? G.s_score : G.stream;
   cudaStream_t st_surf = G.overlap ? G.s_surf : G.stream;
@@ -2410,7 +2539,7 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
   const int64_t n_alive0 = G.h_counts[0];
   st.n_xs = n_alive0;
   // first flight: generation-0 lists
-  CUDA_OK(cudaMemsetAsync(slot_of(0), 0, 4 * sizeof(int32_t), G.stream));
+  CUDA_OK(cudaMemsetAsync(slot_of(0), 0, SLOT * sizeof(int32_t), G.stream));
   a.q_in = G.q_alive;
   a.q_in.count = G.d_counts + 0;
   a.q_a = G.q[0];
@@ -2420,13 +2549,14 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
   a.fl = G.fl[0];
   a.fl_buf = 0;
   a.n_flights = G.d_counts + 0;
-  a.ordered = G.ordered ? 1 : 0;
+  a.ordered = G.ordered ? (G.keyed ? 2 : 1) : 0;
   if (G.ordered) // histories that never fly (zero weight, lost at birth) carry no flag
-    CUDA_OK(cudaMemsetAsync(G.ps.next_ev, 0, (size_t)n, G.stream));
+    CUDA_OK(cudaMemsetAsync(G.ps.next_ev, G.keyed ? FLAG_DEAD_KEYED : 0, (size_t)n, G.stream));
   CUDA_OK(cudaEventRecord(G.evx0[0], G.stream));
   LAUNCH_XS(k_xs_advance, n_alive0, G.stream, a);
   if (G.ordered) {
-    rc = build_lists(n, G.q[0].idx, G.q[2].idx, slot_of(0), G.stream);
+    rc = G.keyed ? build_lists_keyed(n, G.q[0].idx, slot_of(0), G.stream)
+                 : build_lists(n, G.q[0].idx, G.q[2].idx, slot_of(0), G.stream);
     if (rc)
       return rc;
   }
@@ -2437,6 +2567,7 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       CUDA_OK(cudaStreamWaitEvent(st_score, G.e_adv, 0));
     }
     CUDA_OK(cudaEventRecord(G.evk0[2][0], st_score));
+    a.cursor = nullptr;
     LAUNCH_SCORE(n_alive0, st_score, a);
     CUDA_OK(cudaEventRecord(G.evk1[2][0], st_score));
     st.score_issued = 1;
@@ -2463,7 +2594,7 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     const int ev = (int)((sweep + 1) % RING);
     int32_t* in_slot = slot_of(sweep);
     int32_t* out_slot = slot_of(sweep + 1);
-    CUDA_OK(cudaMemsetAsync(out_slot, 0, 4 * sizeof(int32_t), G.stream));
+    CUDA_OK(cudaMemsetAsync(out_slot, 0, SLOT * sizeof(int32_t), G.stream));
     if (score && score_pending[po] && G.overlap) // the records of sweep - 2 must have been consumed
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_score[po], 0));
     CUDA_OK(cudaEventRecord(G.evx0[ev], G.stream));
@@ -2473,45 +2604,31 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     a.q_a.count = out_slot + 0;
     a.q_b = G.q[2 + po];
     a.q_b.count = out_slot + 1;
-    // crossings
-    a.q_in = G.q[2 + pi];
+    // crossings (keyed lists: behind the collisions in the same sorted array)
+    a.q_in = G.q[G.keyed ? pi : 2 + pi];
     a.q_in.count = in_slot + 1;
+    a.q_in.base = G.keyed ? in_slot + 0 : nullptr;
     a.fl = G.fl[0 * 2 + po];
     a.fl_buf = 0 * 2 + po;
     if (G.overlap)
       CUDA_OK(cudaStreamWaitEvent(st_surf, G.e_adv, 0));
     CUDA_OK(cudaEventRecord(G.evk0[0][ev], st_surf));
-    if (G.local_state && !G.batch_xs && G.hm.n_coord_levels <= 3) {
-      if (G.local_state == 2)
-        OMC_LAUNCH(k_surface_xa_l0, n_alive, st_surf, a);
-      else if (G.hm.n_coord_levels == 1)
-        OMC_LAUNCH(k_surface_xa_l1, n_alive, st_surf, a);
-      else
-        OMC_LAUNCH(k_surface_xa_l3, n_alive, st_surf, a);
-    } else {
-      LAUNCH_XS(k_surface_xa, n_alive, st_surf, a);
-    }
+    a.cursor = in_slot + 4;
+    LAUNCH_XA(k_surface_xa, n_alive, st_surf, a);
     CUDA_OK(cudaEventRecord(G.evk1[0][ev], st_surf));
     if (G.overlap)
       CUDA_OK(cudaEventRecord(G.e_surf, st_surf));
     // collisions
     a.q_in = G.q[pi];
     a.q_in.count = in_slot + 0;
+    a.q_in.base = nullptr;
     a.fl = G.fl[1 * 2 + po];
     a.fl_buf = 1 * 2 + po;
     if (G.overlap)
       CUDA_OK(cudaStreamWaitEvent(st_coll, G.e_adv, 0));
     CUDA_OK(cudaEventRecord(G.evk0[1][ev], st_coll));
-    if (G.local_state && !G.batch_xs && G.hm.n_coord_levels <= 3) {
-      if (G.local_state == 2)
-        OMC_LAUNCH(k_collide_xa_l0, n_alive, st_coll, a);
-      else if (G.hm.n_coord_levels == 1)
-        OMC_LAUNCH(k_collide_xa_l1, n_alive, st_coll, a);
-      else
-        OMC_LAUNCH(k_collide_xa_l3, n_alive, st_coll, a);
-    } else {
-      LAUNCH_XS(k_collide_xa, n_alive, st_coll, a);
-    }
+    a.cursor = in_slot + 5;
+    LAUNCH_XA(k_collide_xa, n_alive, st_coll, a);
     CUDA_OK(cudaEventRecord(G.evk1[1][ev], st_coll));
     if (G.overlap) {
       CUDA_OK(cudaEventRecord(G.e_coll, st_coll));
@@ -2519,7 +2636,8 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       CUDA_OK(cudaStreamWaitEvent(G.stream, G.e_coll, 0));
     }
     if (G.ordered) {
-      rc = build_lists(n, G.q[po].idx, G.q[2 + po].idx, out_slot, G.stream);
+      rc = G.keyed ? build_lists_keyed(n, G.q[po].idx, out_slot, G.stream)
+                   : build_lists(n, G.q[po].idx, G.q[2 + po].idx, out_slot, G.stream);
       if (rc)
         return rc;
     }
@@ -2532,6 +2650,7 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       a.fl_buf = 0 * 2 + po;
       a.n_flights = in_slot + 1;
       CUDA_OK(cudaEventRecord(G.evk0[2][ev], st_score));
+      a.cursor = G.dynamic_score ? in_slot + 6 : nullptr;
       LAUNCH_SCORE(n_alive, st_score, a);
       CUDA_OK(cudaEventRecord(G.evk1[2][ev], st_score));
       if (G.overlap)
@@ -2540,6 +2659,7 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       a.fl_buf = 1 * 2 + po;
       a.n_flights = in_slot + 0;
       CUDA_OK(cudaEventRecord(G.evk0[3][ev], st_score));
+      a.cursor = G.dynamic_score ? in_slot + 7 : nullptr;
       LAUNCH_SCORE(n_alive, st_score, a);
       CUDA_OK(cudaEventRecord(G.evk1[3][ev], st_score));
       st.score_issued = sweep + 2; // launch numbers 0 (first flight) .. sweep + 1
@@ -2556,8 +2676,8 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       if (rc)
         return rc;
       for (; known < sweep; ++known) { // account for sweep `known`: consumed generation known, made known + 1
-        const int32_t* hin = G.h_counts + RING_OFS + 4 * (known % RING);
-        const int32_t* hout = G.h_counts + RING_OFS + 4 * ((known + 1) % RING);
+        const int32_t* hin = G.h_counts + RING_OFS + SLOT * (known % RING);
+        const int32_t* hout = G.h_counts + RING_OFS + SLOT * ((known + 1) % RING);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, G.evx0[(known + 1) % RING], G.evx1[(known + 1) % RING]);
         st.ms_xs += ms;
@@ -2586,10 +2706,12 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     a.fl_buf = 0;
     a.q_in = G.q[pi];
     a.q_in.count = in_slot + 0;
+    a.q_in.base = nullptr;
     a.first_event = NEXT_COLLISION;
     LAUNCH_TAIL(n_alive, G.stream, a);
-    a.q_in = G.q[2 + pi];
+    a.q_in = G.q[G.keyed ? pi : 2 + pi];
     a.q_in.count = in_slot + 1;
+    a.q_in.base = G.keyed ? in_slot + 0 : nullptr;
     a.first_event = NEXT_SURFACE;
     LAUNCH_TAIL(n_alive, G.stream, a);
     a.first_event = NEXT_NONE;
@@ -2598,6 +2720,7 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       if (rc)
         return rc;
       a.n_flights = G.fl[0].count;
+      a.cursor = nullptr;
       LAUNCH_SCORE(std::min<int64_t>(G.h_counts[6], G.fl[0].cap), G.stream, a);
     }
   }
@@ -2900,8 +3023,6 @@ static int init_impl(const omcgpu_model* model, int device, int64_t max_particle
 #endif
   if (const char* t = std::getenv("OMCGPU_TAIL_THRESHOLD"))
     G.tail_threshold = std::atoll(t);
-  if (const char* t = std::getenv("OMCGPU_LOCAL_STATE"))
-    G.local_state = std::atoi(t);
   if (const char* t = std::getenv("OMCGPU_TRACE"))
     G.trace = std::fopen(t, "a");
   if (const char* t = std::getenv("OMCGPU_SCORE_PART"))
@@ -2914,6 +3035,22 @@ static int init_impl(const omcgpu_model* model, int device, int64_t max_particle
   ps.cap = cap;
   ps.id_shift = 0;
   ps.is_local = 0;
+  ps.n_prefix = 0;
+  ps.xs_prefix = nullptr;
+  if (model->run_CE && G.batch_xs) {
+    int most = 0;
+    for (int m = 0; m < model->n_materials; ++m)
+      most = std::max(most, model->mat_nuc_ofs[m + 1] - model->mat_nuc_ofs[m]);
+    if (most >= 2 * XS_PREFIX_STRIDE) {
+      bool on = true;
+      if (const char* t = std::getenv("OMCGPU_XS_PREFIX"))
+        on = std::atoi(t) != 0;
+      if (on) {
+        ps.n_prefix = most / XS_PREFIX_STRIDE;
+        rc = rc ? rc : dev_alloc(&ps.xs_prefix, (size_t)cap * ps.n_prefix);
+      }
+    }
+  }
   {
     // sector groups (see PState): one allocation per group, fields at fixed slots
     char *gA = nullptr, *gB = nullptr, *gC = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr,
@@ -2975,6 +3112,31 @@ static int init_impl(const omcgpu_model* model, int device, int64_t max_particle
     rc = rc ? rc : dev_alloc(&stmp, G.sort_tmp_bytes + 16);
     G.d_sort_tmp = stmp;
 #endif
+  }
+  if (const char* t = std::getenv("OMCGPU_DYNAMIC"))
+    G.dynamic = std::atoi(t) != 0;
+  if (const char* t = std::getenv("OMCGPU_DYNAMIC_SCORE"))
+    G.dynamic_score = std::atoi(t) != 0;
+  if (const char* t = std::getenv("OMCGPU_KEYED"))
+    G.keyed = std::atoi(t) != 0;
+  if (G.keyed && (G.sweep_mode != 2 || !G.ordered))
+    G.keyed = false;
+  if (G.keyed) {
+    rc = rc ? rc : dev_alloc(&G.d_key_out, cap);
+    rc = rc ? rc : dev_alloc(&G.d_iota, cap);
+#if OMC_CUDA
+    G.ksort_tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, G.ksort_tmp_bytes, G.ps.next_ev, G.d_key_out, G.d_iota, G.d_iota, (int)cap, 0, 8);
+    char* ktmp = nullptr;
+    rc = rc ? rc : dev_alloc(&ktmp, G.ksort_tmp_bytes + 16);
+    G.d_ksort_tmp = ktmp;
+#endif
+    if (!rc) {
+      IotaArgs ia;
+      ia.v = G.d_iota;
+      ia.n = cap;
+      OMC_LAUNCH(k_iota, cap, G.stream, ia);
+    }
   }
   rc = rc ? rc : dev_alloc(&G.d_offs, cap + 1);
   rc = rc ? rc : dev_alloc(&G.d_gather, src_cap);

@@ -96,3 +96,30 @@ def test_many_nuclide_scheduling_variants_bank_the_same_sites(emu_lib, env, monk
     for f in ("r", "u", "E", "wgt", "parent_id", "progeny_id"):
         assert np.array_equal(fb[f], fb_o[f]), f
     eng.finalize()
+
+
+@pytest.mark.parametrize("env", [{}, {"OMCGPU_XS_PREFIX": "0"}, {"OMCGPU_SORT_XS": "0"}])
+def test_nuclide_sampling_from_block_prefix_sums(emu_lib, env, monkeypatch):
+    """a 100-nuclide fuel: the macro lookup leaves the running sum of rho sigma_t after every 32
+    nuclides in the particle's prefix row, and the collision's sample_nuclide walk
+    (src/physics.cpp:494-518) starts at the block the cutoff falls into -- the nuclide it finds,
+    hence every later event and the fission bank, are those of the walk from nuclide 0 (oracle)"""
+    from openmc_b200 import examples, nuclide
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", "64")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    m, libx, box, of = examples.pwr_core_ce(n_grid=300, n_fuel_nuclides=100, tallies=True)
+    model = nuclide.build_ce_model(m, libx)
+    o = Oracle(model)
+    n = 600
+    src = o.sample_initial_source(n, box, of)
+    eng = lib.Engine(emu_lib)
+    eng.init(model, 0, 1024)
+    gi = eng.gen_in(n, 0, 0, 1.0, True)
+    fb, out = eng.transport_generation(gi, src)
+    fb_o, out_o = o.transport_generation(gi, src)
+    assert out.n_lost == 0
+    assert out.n_fission == out_o.n_fission and out.n_events == out_o.n_events
+    for f in ("r", "u", "E", "wgt", "parent_id", "progeny_id"):
+        assert np.array_equal(fb[f], fb_o[f]), f
+    eng.finalize()
