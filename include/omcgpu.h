@@ -463,6 +463,57 @@ int omcgpu_comb_indices(int64_t start, int64_t n_local, int64_t total, int64_t n
 int omcgpu_bank_columns_device(int which, void** cols, int64_t* n, int64_t* capacity);
 int omcgpu_set_source_count(int64_t n);
 
+/* ------------------------------------------------------------------------- */
+/* Multi-GPU: one process per GPU of one box.  Geometry and data  */
+/* are replicated, particle ids and seeds are global, rank r owns the global     */
+/* source sites [work_index[r], work_index[r+1]) (calculate_work,                */
+/* src/simulation.cpp:657-680).  The transport is NCCL (bound at run time from   */
+/* libnccl.so.2) or three caller-supplied functions, e.g. a CUDA-aware MPI.      */
+/* ------------------------------------------------------------------------- */
+#define OMCGPU_COMM_ID_BYTES 128
+
+/* Rank 0: a fresh NCCL unique id (ncclGetUniqueId) to hand to every rank by any side channel
+ * (MPI_Bcast in libopenmc; a TCP store in bench.py). */
+int omcgpu_comm_unique_id(char* id);
+
+/* Join the communicator on the engine's device (after omcgpu_init); connects to every peer. */
+int omcgpu_comm_init(const char* id, int rank, int n_ranks);
+
+/* The same with a caller-supplied transport.  Buffers are DEVICE memory (the engine's stream is
+ * synchronised before a call); every function returns 0 on success.
+ *   allgather: every rank contributes n values, recv = [n_ranks][n]   (host memory)
+ *   sendrecv:  n_ops simultaneous transfers with peers, complete on return
+ *   allreduce: in-place sum of n doubles; root < 0: result on every rank, else on `root` only */
+typedef int (*omcgpu_allgather_i64_fn)(void* user, const int64_t* send, int32_t n, int64_t* recv);
+typedef int (*omcgpu_sendrecv_fn)(void* user, int32_t n_ops, const int32_t* peer, const int32_t* is_send,
+  void* const* buf, const int64_t* bytes);
+typedef int (*omcgpu_allreduce_f64_fn)(void* user, double* buf, int64_t n, int32_t root);
+int omcgpu_comm_init_custom(int rank, int n_ranks, omcgpu_allgather_i64_fn allgather,
+  omcgpu_sendrecv_fn sendrecv, omcgpu_allreduce_f64_fn allreduce, void* user);
+int omcgpu_comm_finalize(void);
+
+/* All-gather of n <= 4 int64 per rank (host values): also the barrier and the max-over-ranks
+ * timing of bench.py. */
+int omcgpu_comm_allgather_i64(const int64_t* send, int32_t n, int64_t* recv);
+int64_t omcgpu_comm_bytes_exchanged(void);
+
+/* synchronize_bank() (src/eigenvalue.cpp:86-365) over the ranks, on the device-resident banks left
+ * by omcgpu_run_generation: all-gather of the fission-bank sizes, the comb with the common seed
+ * (seed_id = simulation::total_gen + overall_generation()), all-gather of the sampled counts,
+ * transfer of contiguous column ranges to their owners, and -- in the same call -- the sum over
+ * the ranks of `globals` (the generation's k-collision / k-absorption / k-tracklength / leakage /
+ * total weight; MPI_Allreduce of src/eigenvalue.cpp:63; in place, on every rank).  On return the
+ * device source bank holds this rank's share of the next generation (*n_source sites) and, if
+ * source_bank != NULL, so does the host's simulation::source_bank.  A rank without fission sites
+ * or with an overflowing comb makes EVERY rank return the error. */
+int omcgpu_sync_bank(int64_t n_particles, const int64_t* work_index, int64_t seed_id,
+  int64_t master_seed, uint64_t stride, double* globals, int32_t n_globals,
+  omcgpu_site* source_bank, int64_t* n_source);
+
+/* reduce_tally_results() (src/tallies/tally.cpp:997-1025): device VALUE arrays of all tallies
+ * summed onto rank `root` and zeroed elsewhere; root < 0: the sum on every rank. */
+int omcgpu_reduce_tallies(int root);
+
 /* Tally VALUE buffers: add the device VALUE array of tally `t` into
  * value[n_filter_bins*n_scores] (host) and zero it on the device -- the hand-off
  * into results_(:,:,VALUE) before Tally::accumulate (src/tallies/tally.cpp:821-878). */

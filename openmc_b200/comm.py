@@ -22,10 +22,14 @@ from __future__ import annotations
 import ctypes as C
 
 import numpy as np
-import torch
-import torch.distributed as dist
 
-_COL_DTYPES = [torch.float64] * 9 + [torch.int32, torch.int64, torch.int64]
+try:  # only TorchComm / GlooTransport (host-side plumbing of the CPU tests) need torch
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = dist = None
+
+_COL_DTYPES = ([torch.float64] * 9 + [torch.int32, torch.int64, torch.int64]) if torch else []
 
 
 class _CudaPtr:
@@ -145,3 +149,118 @@ class TorchComm:
         if self.on_gpu:
             torch.cuda.synchronize()
         eng.set_source_count(n_new)
+
+
+class NativeComm:
+    """The product's N > 1 path: everything inter-rank happens INSIDE libomcgpu.so
+    (omcgpu_sync_bank / omcgpu_reduce_tallies over NCCL, include/omcgpu.h); this class only
+    carries rank / size and the one-off distribution of the NCCL unique id.  The communicator
+    lives on the engine's device, so it joins in ``attach`` -- which ``Simulation.simulation_init``
+    calls right after ``omcgpu_init``.
+
+    ``NativeComm.over_nccl(rank, size, store)``: rank 0 makes the id, `store` (anything with
+    set / get, e.g. torch.distributed.TCPStore -- a plain TCP key-value store, no process group)
+    hands it to the others.  ``NativeComm.over_callbacks(transport)`` plugs a caller-supplied
+    transport (GlooTransport below in the CPU tests)."""
+    native = True
+
+    def __init__(self, rank, size, connect):
+        self.rank, self.size, self._connect, self.engine = rank, size, connect, None
+
+    @classmethod
+    def over_nccl(cls, rank, size, store, key="omcgpu_nccl_id"):
+        def connect(engine):
+            if rank == 0:
+                uid = engine.comm_unique_id()
+                store.set(key, uid)
+            else:
+                uid = bytes(store.get(key))
+            engine.comm_init(uid, rank, size)
+        return cls(rank, size, connect)
+
+    @classmethod
+    def over_callbacks(cls, transport):
+        def connect(engine):
+            engine.comm_init_custom(transport.rank, transport.size, transport.allgather_cb,
+                                    transport.sendrecv_cb, transport.allreduce_cb)
+        c = cls(transport.rank, transport.size, connect)
+        c.transport = transport
+        return c
+
+    def attach(self, engine):
+        if self.engine is not engine:
+            self._connect(engine)
+            self.engine = engine
+
+    def sync_bank(self, sim, seed_id, globals_, host_bank=None):
+        g, n = self.engine.sync_bank(sim.n_particles, sim.work_index, seed_id, globals_, sim.seed,
+                                     sim.stride, host_bank)
+        assert n == sim.work, (n, sim.work)
+        return g
+
+    def barrier(self):
+        self.engine.comm_allgather([0], self.size)
+
+    def max_over_ranks(self, x: float) -> float:
+        """(integers on the wire: nanoseconds for a time)"""
+        return float(self.engine.comm_allgather([int(round(x * 1e9))], self.size).max()) * 1e-9
+
+    def sum_over_ranks(self, x: int) -> int:
+        return int(self.engine.comm_allgather([int(x)], self.size).sum())
+
+
+class GlooTransport:
+    """omcgpu_comm_init_custom callbacks over torch.distributed (gloo) for the CPU test tier,
+    where "device" buffers of the host-compiled engine are host memory: the library's own
+    synchronize_bank code (csrc/comm.h) then runs across processes without a GPU."""
+
+    def __init__(self):
+        self.rank, self.size = dist.get_rank(), dist.get_world_size()
+        AG = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int64))
+        SR = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                         C.POINTER(C.c_void_p), C.POINTER(C.c_int64))
+        AR = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int64, C.c_int32)
+        self.allgather_cb = AG(self._allgather)
+        self.sendrecv_cb = SR(self._sendrecv)
+        self.allreduce_cb = AR(self._allreduce)
+
+    def _allgather(self, user, send, n, recv):
+        try:
+            t = torch.tensor([send[k] for k in range(n)], dtype=torch.int64)
+            out = [torch.zeros_like(t) for _ in range(self.size)]
+            dist.all_gather(out, t)
+            for r in range(self.size):
+                for k in range(n):
+                    recv[r * n + k] = int(out[r][k])
+            return 0
+        except Exception:
+            return 1
+
+    def _sendrecv(self, user, n_ops, peer, is_send, buf, nbytes):
+        try:
+            ops, keep = [], []
+            for k in range(n_ops):
+                if nbytes[k] == 0:
+                    continue
+                arr = np.ctypeslib.as_array(C.cast(buf[k], C.POINTER(C.c_uint8)), shape=(nbytes[k],))
+                t = torch.from_numpy(arr)
+                keep.append(t)
+                ops.append(dist.P2POp(dist.isend if is_send[k] else dist.irecv, t, int(peer[k])))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            return 0
+        except Exception:
+            return 1
+
+    def _allreduce(self, user, buf, n, root):
+        try:
+            arr = np.ctypeslib.as_array(buf, shape=(n,))
+            t = torch.from_numpy(arr)
+            if root < 0:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            else:
+                dist.reduce(t, root, op=dist.ReduceOp.SUM)
+            return 0
+        except Exception:
+            return 1

@@ -15,10 +15,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libomcgpu.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.h", "device.h", "cuda_emu.h", os.path.join("..", "..", "include", "omcgpu.h")]
+HEADERS = ["common.h", "device.h", "comm.h", "cuda_emu.h", os.path.join("..", "..", "include", "omcgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
-              "-Xptxas", "-v"]
+              "-Xptxas", "-v", "-I/usr/include", "-ldl"]
 
 
 def stale():

@@ -1894,9 +1894,13 @@ OMC_D void atomic_add_f64(double* addr, double val)
 #endif
 }
 
-OMC_D void tally_add(double* addr, double val)
+OMC_D void tally_add(double* addr, double val, bool few_bins = true)
 {
 #if OMC_CUDA && defined(__CUDA_ARCH__)
+  if (!few_bins) { // hundreds of bins (energy spectra, meshes): lanes rarely agree, the vote only costs
+    atomic_add_f64(addr, val);
+    return;
+  }
   // Warp-aggregated when it pays: if every active lane scores the same bin (cell /
   // material tallies with few bins) the warp sums in registers and issues one RED.
   // Otherwise (energy spectra, meshes: lanes rarely agree) each lane issues its own
@@ -2123,89 +2127,89 @@ void mesh_march_exact(int m, V3 r0, V3 u, double total, double t0, double t1, Em
 #undef MESH_BIN
 }
 
-// The same ray trace as a DDA (Amanatides & Woo) for a part that starts INSIDE
-// the mesh -- the case of every flight when the mesh covers the geometry.  The
-// first crossing of each axis uses the reference's formula; the j-th one after it
-// is tmax0 + j * (w / |u|) instead of a fresh division, and a length fraction is
-// (length * 1/total).  Crossing distances therefore differ from the reference's
-// by a few ulp (never accumulating: j multiplies, it is not a running sum), i.e.
-// bin sequences are the same and segment lengths agree to ~1e-14 relative; tally
-// sums are not bit-reproducible in the reference either (atomic order).  A part
-// that starts outside the mesh takes the exact routine above.  A straight track
-// cannot re-enter a box mesh, so leaving it ends the part.
-template<class Emit>
-OMC_D void mesh_march(int m, V3 r0, V3 u, double total, double t0, double t1, Emit& emit)
+template<int ND, class Emit>
+OMC_D void mesh_march_nd(int m, V3 r0, V3 u, double total, double t0, double t1, Emit& emit)
 {
-  const int nd = ld(DM.mesh_ndim + m);
   const double ts = (t0 == 0.0) ? TINY_BIT : t0;
-  double tmax0[3], tdel[3];
-  int idx[3], left[3], stride[3];
+  double tnext[ND], tdel[ND]; // distance of the next crossing of axis k, distance between two of them
+  int left[ND], stride[ND];   // cells ahead before the mesh ends, bin increment of a step
   bool in_mesh = true;
   int bin = 0, cells = 1;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    tmax0[k] = INFTY;
+  for (int k = 0; k < ND; ++k) {
+    const double ll = ld(DM.mesh_lower_left + 3 * m + k), w = ld(DM.mesh_width + 3 * m + k);
+    const int shape = ld(DM.mesh_shape + 3 * m + k);
+    const double rk = comp(r0, k), uk = comp(u, k);
+    const int idx = mesh_index(rk + ts * uk, ll, w);
+    in_mesh = in_mesh && idx >= 1 && idx <= shape;
+    const bool pos = uk > 0;
+    tnext[k] = INFTY;
     tdel[k] = 0.0;
-    idx[k] = 1;
-    left[k] = 0;
-    stride[k] = 0;
-    if (k < nd) {
-      const double ll = ld(DM.mesh_lower_left + 3 * m + k), w = ld(DM.mesh_width + 3 * m + k);
-      const int shape = ld(DM.mesh_shape + 3 * m + k);
-      const double rk = comp(r0, k), uk = comp(u, k);
-      idx[k] = mesh_index(rk + ts * uk, ll, w);
-      in_mesh = in_mesh && idx[k] >= 1 && idx[k] <= shape;
-      const bool pos = uk > 0;
-      if (!(fabs(uk) < FP_PRECISION)) {
-        tmax0[k] = ((ll + (pos ? idx[k] : idx[k] - 1) * w) - rk) / uk;
-        tdel[k] = w / fabs(uk);
-      }
-      left[k] = pos ? shape - idx[k] : idx[k] - 1; // cells ahead before the mesh ends
-      stride[k] = pos ? cells : -cells;
-      bin += (idx[k] - 1) * cells;
-      cells *= shape;
+    if (!(fabs(uk) < FP_PRECISION)) {
+      tnext[k] = ((ll + (pos ? idx : idx - 1) * w) - rk) / uk; // the reference's formula for the first crossing
+      tdel[k] = w / fabs(uk);
     }
+    left[k] = pos ? shape - idx : idx - 1;
+    stride[k] = pos ? cells : -cells;
+    bin += (idx - 1) * cells;
+    cells *= shape;
   }
   if (!in_mesh || total < 2 * TINY_BIT) {
     mesh_march_exact(m, r0, u, total, t0, t1, emit);
     return;
   }
   const double inv_total = 1.0 / total;
-  double t_0 = tmax0[0], t_1 = tmax0[1], t_2 = tmax0[2];
-  int j0 = 0, j1 = 0, j2 = 0;
   double traveled = t0;
   for (int guard = 0; guard < 1000000; ++guard) {
+    // nearest crossing; ties go to the lower axis as in the reference's loop
     int k = 0;
-    double dk = t_0;
-    if (t_1 < dk) {
+    double dk = tnext[0];
+    if (ND > 1 && tnext[1] < dk) {
       k = 1;
-      dk = t_1;
+      dk = tnext[1];
     }
-    if (t_2 < dk) {
+    if (ND > 2 && tnext[2] < dk) {
       k = 2;
-      dk = t_2;
+      dk = tnext[2];
     }
     emit(bin, ((dk < t1 ? dk : t1) - traveled) * inv_total);
     traveled = dk;
     if (traveled >= t1)
       break;
-    // step across the nearest edge without branching on the axis (the lanes of a warp
-    // cross different axes: an if / else chain would run the three bodies one after
-    // another)
-    const bool k0 = k == 0, k1 = k == 1;
-    int jk = k0 ? j0 : (k1 ? j1 : j2);
-    if (jk == (k0 ? left[0] : (k1 ? left[1] : left[2])))
-      break;
-    ++jk;
-    bin += k0 ? stride[0] : (k1 ? stride[1] : stride[2]);
-    const double tn = (k0 ? tmax0[0] : (k1 ? tmax0[1] : tmax0[2])) + jk * (k0 ? tdel[0] : (k1 ? tdel[1] : tdel[2]));
-    j0 = k0 ? jk : j0;
-    j1 = k1 ? jk : j1;
-    j2 = (k0 || k1) ? j2 : jk;
-    t_0 = k0 ? tn : t_0;
-    t_1 = k1 ? tn : t_1;
-    t_2 = (k0 || k1) ? t_2 : tn;
+    // step across that edge without branching on the axis (the lanes of a warp cross different
+    // axes: an if / else chain would run the bodies one after another)
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+      const bool ka = k == a;
+      if (ka && left[a] == 0) // the mesh ends here (a straight track cannot re-enter a box)
+        return;
+      left[a] -= ka ? 1 : 0;
+      bin += ka ? stride[a] : 0;
+      tnext[a] += ka ? tdel[a] : 0.0;
+    }
   }
+}
+
+// The same ray trace as a DDA (Amanatides & Woo) for a part that starts INSIDE
+// the mesh -- the case of every flight when the mesh covers the geometry.  The
+// first crossing of each axis uses the reference's formula; every later one adds w / |u|
+// instead of a fresh division, and a length fraction is (length * 1/total).  Crossing
+// distances therefore differ from the reference's by rounding (a few ulp per cell crossed,
+// over at most the cells of ONE part, since every part starts afresh from its own position),
+// i.e. bin sequences are the same and segment lengths agree to ~1e-14 relative; tally sums are
+// not bit-reproducible in the reference either (atomic order).  A part that starts outside the
+// mesh takes the exact routine above.  Compiled per mesh dimension: a 2-D mesh (configs C1-C4)
+// carries no third axis through the loop.
+template<class Emit>
+OMC_D void mesh_march(int m, V3 r0, V3 u, double total, double t0, double t1, Emit& emit)
+{
+  const int nd = ld(DM.mesh_ndim + m);
+  if (nd == 2)
+    mesh_march_nd<2>(m, r0, u, total, t0, t1, emit);
+  else if (nd == 3)
+    mesh_march_nd<3>(m, r0, u, total, t0, t1, emit);
+  else
+    mesh_march_nd<1>(m, r0, u, total, t0, t1, emit);
 }
 
 // Number of mesh cells the track r0 -> r1 visits (exact for a track inside the
@@ -2305,7 +2309,9 @@ OMC_D void tally_emit(const TallyEval& te, int t, int mesh_bin, double mesh_w, c
 {
   const int ns = ld(DM.tally_n_scores + t);
   const int32_t* scores = DM.tally_scores + OMCGPU_MAX_SCORES * t;
-  double* results = values + ld(DM.tally_result_ofs + t);
+  const int64_t r_ofs = ld(DM.tally_result_ofs + t);
+  double* results = values + r_ofs;
+  const bool few_bins = ld(DM.tally_result_ofs + t + 1) - r_ofs <= 64 * ns; // warp-aggregate only small tallies
   // cartesian product over the non-mesh filters (at most MAX_COORD^2 combos; 1 in practice)
   int n0 = 1, n1 = 1, n2 = 1;
   if (te.nf > 0)
@@ -2328,7 +2334,7 @@ OMC_D void tally_emit(const TallyEval& te, int t, int mesh_bin, double mesh_w, c
           bool skip;
           const double score = score_value(ld(scores + s), sc, skip);
           if (!skip)
-            tally_add(results + index * ns + s, score * mesh_w);
+            tally_add(results + index * ns + s, score * mesh_w, few_bins);
         }
       }
 }

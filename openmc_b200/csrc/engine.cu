@@ -868,7 +868,6 @@ struct PartEmit {
   double* r0;     // results + base * ns: the part's row of bin 0
   int bin_stride; // doubles between two mesh bins = mesh_stride * ns
   double val[NS];
-  unsigned n_red = 0; // REDs issued through this functor (reported when count_lookups is on)
   OMC_D void set(double* results, int64_t base, int mesh_stride, int ns)
   {
     r0 = results + base * ns;
@@ -879,10 +878,8 @@ struct PartEmit {
     double* r = r0 + (int64_t)bin * bin_stride; // one wide multiply-add per mesh cell
 #pragma unroll
     for (int s = 0; s < NS; ++s) // compile-time indices keep val in registers
-      if (val[s] != 0.0) {
+      if (val[s] != 0.0)
         atomic_add_f64(r + s, val[s] * w);
-        ++n_red;
-      }
   }
 };
 
@@ -939,7 +936,7 @@ OMC_D Flight load_flight(const Flights& fl, int64_t j)
 // scores tallies without a mesh filter at once, and returns the number of parts
 // the mesh ray trace is cut into (0: nothing to trace cooperatively)
 OMC_D int score_prepare(const PState& ps, const Flight& f, int t, double* values, int score_part,
-  int64_t& base, double* val)
+  int64_t& base, double* val, unsigned long long* red_counter = nullptr)
 {
   TallyEval te;
   const int64_t i = f.pidx; // cell / universe filters read the particle's coordinate levels
@@ -984,6 +981,16 @@ OMC_D int score_prepare(const PState& ps, const Flight& f, int t, double* values
     return 1;
   const V3 r1 = v3(f.r0.x + f.total * f.u.x, f.r0.y + f.total * f.u.y, f.r0.z + f.total * f.u.z);
   const int cells = mesh_cells_visited(te.mesh, f.r0, r1, f.u);
+  if (red_counter) { // cells x scores that add something: the REDs this flight issues (exact inside the mesh)
+    int nnz = 0;
+    for (int s = 0; s < SCORE_NVAL; ++s)
+      nnz += val[s] != 0.0 ? 1 : 0;
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+    atomicAdd(red_counter, (unsigned long long)(cells * nnz));
+#else
+    *red_counter += (unsigned long long)(cells * nnz);
+#endif
+  }
   const int nc = (cells + score_part - 1) / score_part;
   return nc < 1 ? 1 : nc;
 }
@@ -1011,12 +1018,12 @@ OMC_HD void tally_mesh_info(int t, int& mesh, int& mesh_stride)
 __constant__ Flights c_fl[4]; // [list kind][parity]: k_score(sweep s) overlaps the event kernels of sweep s+1
 
 __device__ __noinline__ int score_lane(int64_t j, int buf, int t, double* values, int score_part,
-  double* sd, int64_t* sbase)
+  double* sd, int64_t* sbase, unsigned long long* red_counter)
 {
   const Flight f = load_flight(c_fl[buf], j);
   double val[SCORE_NVAL];
   int64_t base = 0;
-  const int nc = score_prepare(c_ps, f, t, values, score_part, base, val);
+  const int nc = score_prepare(c_ps, f, t, values, score_part, base, val, red_counter);
   if (nc > 0) {
     sd[0 * 32] = f.r0.x;
     sd[1 * 32] = f.r0.y;
@@ -1036,7 +1043,7 @@ __device__ __noinline__ int score_lane(int64_t j, int buf, int t, double* values
 // the lanes of a warp trace the parts of the warp's 32 flights round-robin
 template<int NS>
 __device__ __forceinline__ void score_parts(int mesh, int mesh_stride, int ns, double* results, int n_parts,
-  int lane, const int* incl, const double (*sd)[32], const int64_t* sbase, unsigned long long* red_counter)
+  int lane, const int* incl, const double (*sd)[32], const int64_t* sbase)
 {
   PartEmit<NS> em;
   for (int item = lane; item < n_parts; item += 32) {
@@ -1055,8 +1062,6 @@ __device__ __forceinline__ void score_parts(int mesh, int mesh_stride, int ns, d
     em.set(results, sbase[o], mesh_stride, ns);
     mesh_march(mesh, pr0, pu, ptotal, part_bound(c, onc, ptotal), part_bound(c + 1, onc, ptotal), em);
   }
-  if (red_counter && em.n_red)
-    atomicAdd(red_counter, (unsigned long long)em.n_red);
 }
 
 __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, EvArgs a)
@@ -1094,7 +1099,7 @@ __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, 
     __syncwarp(); // lanes leave the part loop of the previous tally at different times
     int nc = 0;
     if (active) // loads the flight, evaluates the filters, publishes r0/u/total/val/base
-      nc = score_lane(tid, a.fl_buf, t, values, a.gc.score_part, &s_d[warp][0][lane], &s_base[warp][lane]);
+      nc = score_lane(tid, a.fl_buf, t, values, a.gc.score_part, &s_d[warp][0][lane], &s_base[warp][lane], red_counter);
     int mesh, mesh_stride;
     tally_mesh_info(t, mesh, mesh_stride);
     if (mesh < 0)
@@ -1114,11 +1119,11 @@ __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, 
     double* results = values + ld(DM.tally_result_ofs + t);
     // warp-uniform: a property of the tally
     if (ns == 1)
-      score_parts<1>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp], red_counter);
+      score_parts<1>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp]);
     else if (ns <= 3)
-      score_parts<3>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp], red_counter);
+      score_parts<3>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp]);
     else
-      score_parts<SCORE_NVAL>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp], red_counter);
+      score_parts<SCORE_NVAL>(mesh, mesh_stride, ns, results, n_parts, lane, s_incl[warp], s_d[warp], s_base[warp]);
   }
   __syncwarp(); // the staging area is reused by the next block of flights
   }
@@ -2851,8 +2856,11 @@ int omcgpu_set_option(const char* name, int64_t value)
   return 0;
 }
 
+int omcgpu_comm_finalize(void);
+
 int omcgpu_finalize(void)
 {
+  omcgpu_comm_finalize(); // its staging buffers live in this engine's allocation list
   for (void* p : G.dev_allocs)
     cudaFree(p);
   G.dev_allocs.clear();
@@ -3816,4 +3824,8 @@ int omcgpu_prn(const uint64_t* seed, int64_t n_seeds, int32_t count, double* out
   return rng_probe(nullptr, seed, n_seeds, count, nullptr, out);
 }
 
+int omcgpu_comm_allgather_i64(const int64_t* send, int32_t n, int64_t* recv);
+
 } // extern "C"
+
+#include "comm.h"

@@ -173,6 +173,47 @@ class Engine:
     def set_source_count(self, n: int):
         self._check(self.lib.omcgpu_set_source_count(C.c_int64(n)))
 
+    # -- multi-GPU (include/omcgpu.h: omcgpu_comm_*, omcgpu_sync_bank, omcgpu_reduce_tallies) ----
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(abi.OMCGPU_COMM_ID_BYTES)
+        self._check(self.lib.omcgpu_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, n_ranks: int):
+        assert len(uid) == abi.OMCGPU_COMM_ID_BYTES
+        self._check(self.lib.omcgpu_comm_init(C.c_char_p(uid), C.c_int(rank), C.c_int(n_ranks)))
+
+    def comm_init_custom(self, rank, n_ranks, allgather, sendrecv, allreduce):
+        """callbacks are ctypes function objects (kept alive here)"""
+        self._comm_callbacks = (allgather, sendrecv, allreduce)
+        self._check(self.lib.omcgpu_comm_init_custom(C.c_int(rank), C.c_int(n_ranks), allgather, sendrecv,
+                                                     allreduce, None))
+
+    def comm_finalize(self):
+        self._check(self.lib.omcgpu_comm_finalize())
+
+    def comm_allgather(self, values, n_ranks):
+        send = np.ascontiguousarray(values, np.int64)
+        recv = np.zeros((n_ranks, send.size), np.int64)
+        self._check(self.lib.omcgpu_comm_allgather_i64(_p(send, C.c_int64), C.c_int32(send.size),
+                                                       _p(recv, C.c_int64)))
+        return recv
+
+    def sync_bank(self, n_particles, work_index, seed_id, globals_, master_seed=DEFAULT_SEED,
+                  stride=DEFAULT_STRIDE, host_bank: np.ndarray | None = None):
+        """synchronize_bank over the ranks + the sum of `globals_`; -> (reduced globals, n_source)"""
+        wi = np.ascontiguousarray(work_index, np.int64)
+        g = np.ascontiguousarray(globals_, np.float64).copy()
+        n = C.c_int64(0)
+        hb = host_bank.ctypes.data_as(C.c_void_p) if host_bank is not None else None
+        self._check(self.lib.omcgpu_sync_bank(C.c_int64(n_particles), _p(wi, C.c_int64), C.c_int64(seed_id),
+                                              C.c_int64(master_seed), C.c_uint64(stride), _p(g, C.c_double),
+                                              C.c_int32(g.size), hb, C.byref(n)))
+        return g, n.value
+
+    def reduce_tallies(self, root: int = -1):
+        self._check(self.lib.omcgpu_reduce_tallies(C.c_int(root)))
+
     # -- tallies -----------------------------------------------------------------
     def tally_results(self, tally: int, value: np.ndarray):
         """value += device VALUE array of `tally`; zeroes the device array."""
@@ -354,6 +395,8 @@ class Simulation:
     # -- openmc_simulation_init, src/simulation.cpp:75-167 -----------------------
     def simulation_init(self):
         self.engine.init(self.model, self.device, max(self.work, 1))   # work_per_rank, as allocate_banks
+        if self.comm is not None and hasattr(self.comm, "attach"):
+            self.comm.attach(self.engine)      # the communicator lives on the engine's device
         self.source_bank = self._initial_source.copy()
         self.engine.set_source_bank(self.source_bank)
         self.current_batch = 0
@@ -406,11 +449,17 @@ class Simulation:
             if active:
                 st["active_ms"] += out.ms_transport; st["active_particles"] += self.work
             g = np.array(out.global_tally[:] + [out.total_weight])
-            if self.comm:                        # MPI_Allreduce / MPI_Reduce of globals
-                g = self.comm.allreduce_sum(g)
-            total_weight += g[4]
-            self.gt[:, 0] += g[:4]               # finalize_generation :524-533
-            self._synchronize_bank(og, out.n_fission)
+            if self.comm is not None and getattr(self.comm, "native", False):
+                # one library call: the comb + exchange of synchronize_bank AND the sum of the globals
+                g = self.comm.sync_bank(self, self.total_gen + og, g)
+                total_weight += g[4]
+                self.gt[:, 0] += g[:4]
+            else:
+                if self.comm:                    # MPI_Allreduce / MPI_Reduce of globals
+                    g = self.comm.allreduce_sum(g)
+                total_weight += g[4]
+                self.gt[:, 0] += g[:4]           # finalize_generation :524-533
+                self._synchronize_bank(og, out.n_fission)
             # calculate_generation_keff, src/eigenvalue.cpp:50-84
             keff_generation = self.gt[abi.OMCGPU_K_TRACKLENGTH, 0] - keff_generation
             self.k_generation.append(keff_generation / self.n_particles)
@@ -470,10 +519,13 @@ class Simulation:
         if active and self.tally_results:
             norm = 1.0 / (float(self.n_particles) * self.gen_per_batch)
             self.tally_n_realizations += 1
+            native = self.comm is not None and getattr(self.comm, "native", False)
+            if native:
+                self.engine.reduce_tallies(-1)             # reduce_tally_results :997-1057, on the device
             for t, res in enumerate(self.tally_results):
                 value = np.zeros(res.shape[0] * res.shape[1])
                 self.engine.tally_results(t, value)        # hand-off into results_(:,:,VALUE)
-                if self.comm:
+                if self.comm and not native:
                     value = self.comm.allreduce_sum(value)  # reduce_tally_results :997-1057
                 val = value.reshape(res.shape[:2]) * norm
                 res[:, :, 1] += val

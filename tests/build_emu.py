@@ -19,7 +19,7 @@ LIB = os.path.join(OUT_DIR, "libomcgpu_emu.so")
 
 def build(force=False):
     os.makedirs(OUT_DIR, exist_ok=True)
-    deps = [os.path.join(CSRC, f) for f in ("engine.cu", "device.h", "common.h", "cuda_emu.h")]
+    deps = [os.path.join(CSRC, f) for f in ("engine.cu", "device.h", "common.h", "comm.h", "cuda_emu.h")]
     deps.append(os.path.join(ROOT, "include", "omcgpu.h"))
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) < os.path.getmtime(LIB) for d in deps):
         return LIB

@@ -31,11 +31,20 @@ def _run(name, emu_path, comm, resident=True):
     from oracle.binding import Oracle
     model, box, of = cases.build(name)
     full = Oracle(model).sample_initial_source(N, box, of)
-    rank, size = (comm.rank, comm.size) if comm else (0, 1)
+    if comm == "native":
+        import torch.distributed as dist
+        rank, size = dist.get_rank(), dist.get_world_size()
+    else:
+        rank, size = (comm.rank, comm.size) if comm else (0, 1)
     # this rank's share of the global source bank (calculate_work, src/simulation.cpp:657-680)
     lo = sum(N // size + (1 if r < N % size else 0) for r in range(rank))
     hi = lo + N // size + (1 if rank < N % size else 0)
-    sim = lib.Simulation(lib.Engine(emu_path), model, N, BATCHES, INACTIVE, full[lo:hi], comm=comm,
+    eng = lib.Engine(emu_path)
+    if comm == "native":
+        # the library's own synchronize_bank (csrc/comm.h) over a caller-supplied transport
+        from openmc_b200.comm import GlooTransport, NativeComm
+        comm = NativeComm.over_callbacks(GlooTransport())
+    sim = lib.Simulation(eng, model, N, BATCHES, INACTIVE, full[lo:hi], comm=comm,
                          resident=resident)
     k = sim.run()
     bank = sim.get_source_bank()
@@ -45,7 +54,7 @@ def _run(name, emu_path, comm, resident=True):
     return dict(k=k, kgen=kgen, bank=bank, lo=lo, tallies=tallies)
 
 
-def _worker(rank, size, port, name, emu_path, out_dir, resident=True):
+def _worker(rank, size, port, name, emu_path, out_dir, resident=True, native=False):
     for p in (ROOT, os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -54,7 +63,7 @@ def _worker(rank, size, port, name, emu_path, out_dir, resident=True):
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=size)
     from openmc_b200.comm import TorchComm
-    r = _run(name, emu_path, TorchComm(on_gpu=False), resident)
+    r = _run(name, emu_path, "native" if native else TorchComm(on_gpu=False), resident)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), k=np.array(r["k"]), kgen=np.array(r["kgen"]),
              bank=r["bank"], lo=r["lo"], **{f"t{i}": t for i, t in enumerate(r["tallies"])})
     dist.destroy_process_group()
@@ -94,3 +103,21 @@ def test_host_bank_path_with_ranks(emu_lib, tmp_path):
     bank = np.concatenate([r["bank"] for r in ranks])
     for f in ("r", "u", "E", "parent_id", "progeny_id"):
         assert np.array_equal(bank[f], single["bank"][f]), f
+
+
+@pytest.mark.parametrize("name,size", [("mg_legendre", 2), ("mg_temperature_multi", 2), ("mg_legendre", 4)])
+def test_native_sync_bank_equals_one_rank(emu_lib, name, size, tmp_path):
+    """the same bar for the product's path: omcgpu_sync_bank / omcgpu_reduce_tallies inside the
+    library (csrc/comm.h), here over omcgpu_comm_init_custom with gloo callbacks"""
+    single = _run(name, emu_lib, None)
+    port = _free_port()
+    mp.spawn(_worker, args=(size, port, name, emu_lib, str(tmp_path), True, True), nprocs=size, join=True)
+    ranks = [np.load(tmp_path / f"rank{r}.npz") for r in range(size)]
+    for r in ranks:
+        np.testing.assert_allclose(r["kgen"], single["kgen"], rtol=1e-12)
+    np.testing.assert_allclose(ranks[0]["k"], single["k"], rtol=1e-9)
+    bank = np.concatenate([r["bank"] for r in ranks])
+    for f in ("r", "u", "E", "wgt", "delayed_group", "parent_id", "progeny_id"):
+        assert np.array_equal(bank[f], single["bank"][f]), f
+    for i, t in enumerate(single["tallies"]):
+        np.testing.assert_allclose(ranks[0][f"t{i}"], t, rtol=1e-10, atol=1e-300)
