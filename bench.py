@@ -258,7 +258,6 @@ def load_traffic(workload_key):
 def measure(args, workload_key, n_local, steps, warmup, rank, local_rank, world, comm, with_e2e, peak, peaks):
     """one workload on this rank's GPU: resident loop (`value`), host-buffer loop (`e2e`), per-kernel rooflines"""
     import torch
-    import torch.distributed as dist
     from openmc_b200 import lib, source
 
     wargs = argparse.Namespace(**vars(args))
@@ -273,7 +272,7 @@ def measure(args, workload_key, n_local, steps, warmup, rank, local_rank, world,
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            comm.barrier()          # the library's own all-gather over NCCL
             torch.cuda.synchronize()
 
     # ---- resident loop ("value"): source bank stays in HBM between generations
@@ -312,12 +311,10 @@ def measure(args, workload_key, n_local, steps, warmup, rank, local_rank, world,
         st["n_xs_kernel_items"] = st["n_xs_lookups"]; st["n_launch_xs"] = st["n_launch_surface"]
         cs["n_xs_kernel_items"] = cs["n_xs_lookups"]
     if world > 1:
-        t = torch.tensor([dt, st["ms_transport"]], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, st["ms_transport"] = (float(x) for x in t)
-        c = torch.tensor([st["n_events"], launches], dtype=torch.float64, device="cuda")
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        n_events_all, launches = (int(x) for x in c)
+        dt = comm.max_over_ranks(dt)
+        st["ms_transport"] = comm.max_over_ranks(st["ms_transport"] * 1e-3) * 1e3
+        n_events_all = comm.sum_over_ranks(st["n_events"])
+        launches = comm.sum_over_ranks(launches)
     else:
         n_events_all = st["n_events"]
     value = n_global * steps / dt
@@ -348,9 +345,10 @@ def measure(args, workload_key, n_local, steps, warmup, rank, local_rank, world,
             else:
                 eng.set_source_bank(bank)
                 out = eng.run_generation(gi)
-                g = comm.allreduce_sum(np.array(out.global_tally[:] + [out.total_weight]))
-                comm.synchronize_bank(sim, gen0 + s + 1, out.n_fission)
-                eng.get_source_bank(n_local, out=bank)
+                # omcgpu_sync_bank: comb + NCCL exchange + sum of the globals + the D2H mirror of
+                # the new source into the host bank, one library call
+                g = comm.sync_bank(sim, gen0 + s + 1, np.array(out.global_tally[:] + [out.total_weight]),
+                                   host_bank=bank)
                 k_gen = g[2] / n_global
             d2h += bank.nbytes + 96
             keff = k_gen
@@ -358,15 +356,14 @@ def measure(args, workload_key, n_local, steps, warmup, rank, local_rank, world,
         dt_e = time.perf_counter() - t0
         eng.host_unregister(bank)
         if world > 1:
-            t = torch.tensor([dt_e], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt_e = float(t[0])
+            dt_e = comm.max_over_ranks(dt_e)
         e2e = {"value": n_global * steps / dt_e, "unit": "particles/s",
                "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps,
                "note": ("omcgpu_next_generation on the page-locked host SourceSite bank: H2D source, event "
                         "loop, device sort + comb, D2H next source" if world == 1 else
-                        "per rank: H2D of the page-locked host source bank, event loop, device comb + NCCL "
-                        "exchange of the sites that change owner, D2H of the next source bank")}
+                        "per rank: H2D of the page-locked host source bank (omcgpu_set_source_bank), event loop "
+                        "(omcgpu_run_generation), omcgpu_sync_bank = device comb + NCCL exchange of the column "
+                        "ranges that change owner + NCCL sum of the globals + D2H of the next source bank")}
 
     # ---- rooflines of the in-loop kernels from the live CUDA-event timings
     kernels = kernel_rooflines(model, st, cs, peak, eng.fused_lookup)
@@ -422,7 +419,6 @@ def main():
         return reference_arm(args, rank, world)
 
     import torch
-    import torch.distributed as dist
     from openmc_b200.csrc import build as build_ext
 
     if not torch.cuda.is_available():
@@ -430,11 +426,22 @@ def main():
     torch.cuda.set_device(local_rank)
     comm = None
     if world > 1:
+        # one process per GPU; every inter-rank step is the library's own (NCCL behind the C ABI,
+        # csrc/comm.h).  torch only lends its rendezvous key-value store (plain TCP, no process
+        # group) to hand the NCCL unique id from rank 0 to the others.
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        from openmc_b200.comm import TorchComm
-        comm = TorchComm(on_gpu=True)
-    build_ext.build()
+        pin_to_gpu_numa_node(local_rank)
+        from torch.distributed import rendezvous
+        from openmc_b200.comm import NativeComm
+        store, _, _ = next(rendezvous("env://", rank, world))
+        comm = NativeComm.over_nccl(rank, world, store)
+    if rank == 0:
+        build_ext.build()
+    if world > 1:               # the other ranks load the library only once rank 0 has (re)built it
+        if rank == 0:
+            store.set("omcgpu_built", b"1")
+        else:
+            store.get("omcgpu_built")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -488,8 +495,29 @@ def main():
             "cpu_baseline": cpu, "other_configs": others or None,
         }
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def pin_to_gpu_numa_node(index):
+    """best effort: run this process (and first-touch its page-locked banks) on the CPU cores of
+    the NUMA node the GPU hangs off -- the host-buffer leg moves 0.8 GB per generation per GPU"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
 
 
 def xs_probe(eng, model, n, peak, box):
