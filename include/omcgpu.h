@@ -107,6 +107,12 @@ extern "C" {
 #define OMCGPU_FILTER_CELL      2
 #define OMCGPU_FILTER_MATERIAL  3
 #define OMCGPU_FILTER_UNIVERSE  4
+#define OMCGPU_FILTER_DISTRIBCELL 5 /* filter_idata = { cell index }; bins = instances of that cell
+                                     (src/tallies/filter_distribcell.cpp:40-63) */
+/* TallyEstimator, include/openmc/constants.h:299 */
+#define OMCGPU_ESTIMATOR_ANALOG      0 /* refused by omcgpu_init */
+#define OMCGPU_ESTIMATOR_TRACKLENGTH 1
+#define OMCGPU_ESTIMATOR_COLLISION   2
 #define OMCGPU_SCORE_FLUX        0
 #define OMCGPU_SCORE_TOTAL       1
 #define OMCGPU_SCORE_ABSORPTION  2
@@ -310,7 +316,7 @@ typedef struct omcgpu_model {
   const double* sc_mu;            /* mu grids (tabular: order pts, histogram: order+1) */
   const double* sc_dmu;           /* [n_ba]                                            */
 
-  /* ---- tallies (tracklength estimator; src/tallies/) ---------------------- */
+  /* ---- tallies (tracklength and collision estimators; src/tallies/) --------- */
   int32_t n_meshes;
   const int32_t* mesh_ndim;       /* [n_meshes]                                        */
   const int32_t* mesh_shape;      /* [n_meshes][3]                                     */
@@ -325,6 +331,8 @@ typedef struct omcgpu_model {
   const int32_t* filter_idata;    /* cell/material/universe: map[index] -> bin or -1   */
   const double* filter_ddata;     /* energy: bin edges                                 */
   int32_t n_tallies;
+  int32_t n_collision_tallies;    /* derived by omcgpu_init (ignored on input): tallies with the collision estimator */
+  const int32_t* tally_estimator; /* [n_tallies] OMCGPU_ESTIMATOR_* (Tally::estimator_)       */
   const int32_t* tally_n_filters; /* [n_tallies]                                       */
   const int32_t* tally_filters;   /* [n_tallies][OMCGPU_MAX_FILTERS]                   */
   const int32_t* tally_strides;   /* [n_tallies][OMCGPU_MAX_FILTERS]                   */

@@ -2243,9 +2243,58 @@ struct TallyEval {
   int stride[OMCGPU_MAX_FILTERS];
 };
 
-// returns false when some filter of tally t has no matching bin
+// StructuredMesh::get_bin, src/mesh.cpp:874-929: bin of a point, -1 outside the mesh
+OMC_HD int mesh_get_bin(int m, V3 r)
+{
+  const int nd = ld(DM.mesh_ndim + m);
+  int bin = 0, cells = 1;
+  for (int k = 0; k < nd; ++k) {
+    const int shape = ld(DM.mesh_shape + 3 * m + k);
+    const int idx = mesh_index(comp(r, k), ld(DM.mesh_lower_left + 3 * m + k), ld(DM.mesh_width + 3 * m + k));
+    if (idx < 1 || idx > shape)
+      return -1;
+    bin += (idx - 1) * cells;
+    cells *= shape;
+  }
+  return bin;
+}
+
+// DistribcellFilter::get_all_bins, src/tallies/filter_distribcell.cpp:40-63: the instance of
+// `cell` the particle is in, or -1
+OMC_HD int distribcell_bin(const PState& ps, int64_t i, int n_coord, int cell)
+{
+  const int map = ld(DM.cell_distribcell_index + cell);
+  int offset = 0;
+  for (int l = 0; l < n_coord; ++l) {
+    const int c = LV(cell, l);
+    const int type = ld(DM.cell_type + c);
+    if (type == OMCGPU_FILL_UNIVERSE) {
+      offset += ld(DM.cell_offset + ld(DM.cell_offset_ofs + c) + map);
+    } else if (type == OMCGPU_FILL_LATTICE) {
+      const int lat = LV(lattice, l + 1);
+      LatIdx li;
+      li.x = LV(lat_x, l + 1);
+      li.y = LV(lat_y, l + 1);
+      li.z = LV(lat_z, l + 1);
+      if (lat_valid(lat, li)) {
+        const int32_t* n = DM.lat_shape + 3 * lat;
+        offset += ld(DM.lat_offsets + ld(DM.lat_offset_ofs + lat) + ld(n) * ld(n + 1) * ld(n + 2) * map +
+                     lat_flat(lat, li)) +
+                  ld(DM.cell_offset + ld(DM.cell_offset_ofs + c) + map);
+      }
+    }
+    if (c == cell)
+      return offset;
+  }
+  return -1;
+}
+
+// returns false when some filter of tally t has no matching bin.  `r_point` non-null: the tally
+// is scored at a point with the collision estimator (the mesh filter matches the bin of the
+// point, MeshFilter::get_all_bins src/tallies/filter_mesh.cpp:61-66; sc.g is then the
+// pre-collision group, EnergyFilter::get_all_bins src/tallies/filter_energy.cpp:62-67)
 OMC_HD bool tally_prepare(const PState& ps, int64_t i, int n_coord, int t, double E_last,
-  const ScoreCtx& sc, TallyEval& te)
+  const ScoreCtx& sc, TallyEval& te, const V3* r_point = nullptr)
 {
   const int G = DM.mg_n_groups;
   te.nf = ld(DM.tally_n_filters + t);
@@ -2258,9 +2307,15 @@ OMC_HD bool tally_prepare(const PState& ps, int64_t i, int n_coord, int t, doubl
     const int o = ld(DM.filter_data_ofs + f);
     switch (ld(DM.filter_type + f)) {
     case OMCGPU_FILTER_MESH:
-      te.mesh_pos = k;
-      te.mesh = ld(DM.filter_mesh + f);
-      te.nb[k] = 1;
+      if (r_point) {
+        const int b = mesh_get_bin(ld(DM.filter_mesh + f), *r_point);
+        if (b >= 0)
+          te.bins[k][te.nb[k]++] = b;
+      } else {
+        te.mesh_pos = k;
+        te.mesh = ld(DM.filter_mesh + f);
+        te.nb[k] = 1;
+      }
       break;
     case OMCGPU_FILTER_ENERGY: {
       const int nbin = ld(DM.filter_n_bins + f);
@@ -2290,6 +2345,12 @@ OMC_HD bool tally_prepare(const PState& ps, int64_t i, int n_coord, int t, doubl
           te.bins[k][te.nb[k]++] = b;
       }
       break;
+    case OMCGPU_FILTER_DISTRIBCELL: {
+      const int b = distribcell_bin(ps, i, n_coord, ld(DM.filter_idata + o));
+      if (b >= 0)
+        te.bins[k][te.nb[k]++] = b;
+      break;
+    }
     default: // universe
       for (int l = 0; l < n_coord; ++l) {
         const int b = ld(DM.filter_idata + o + LV(universe, l));
@@ -2361,6 +2422,8 @@ OMC_OOL void score_tracklength(const PState& ps, int64_t i, int n_coord, V3 r0, 
   double E_last, const ScoreCtx& sc, double* values)
 {
   for (int t = 0; t < DM.n_tallies; ++t) {
+    if (ld(DM.tally_estimator + t) != OMCGPU_ESTIMATOR_TRACKLENGTH)
+      continue;
     TallyEval te;
     if (!tally_prepare(ps, i, n_coord, t, E_last, sc, te))
       continue;
@@ -2380,4 +2443,23 @@ OMC_OOL void score_tracklength(const PState& ps, int64_t i, int n_coord, V3 r0, 
   }
 }
 
+// score_collision_tally, src/tallies/tally_scoring.cpp:2543-2620: the tallies with the collision
+// estimator, at the point of a collision.  sc carries flux = wgt_last / Sigma_t and the
+// PRE-collision macroscopic cross sections, group and (MG) angle block; E_last the pre-collision
+// energy -- nothing a score of score_general_ce_nonanalog / score_general_mg reads changes in the
+// collision, so the collision kernel scores before it calls collision().
+OMC_OOL void score_collision(const PState& ps, int64_t i, int n_coord, V3 r, double E_last, const ScoreCtx& sc,
+  double* values)
+{
+  for (int t = 0; t < DM.n_tallies; ++t) {
+    if (ld(DM.tally_estimator + t) != OMCGPU_ESTIMATOR_COLLISION)
+      continue;
+    TallyEval te;
+    if (!tally_prepare(ps, i, n_coord, t, E_last, sc, te, &r))
+      continue;
+    tally_emit(te, t, 0, 1.0, sc, values);
+  }
+}
+
 } // namespace omc
+

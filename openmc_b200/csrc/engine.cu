@@ -610,6 +610,16 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
   return ev_revive(ps, i);
 }
 
+// the replica of the tally VALUE arrays this block adds into (see k_score)
+OMC_D double* score_values(const GenCtx& gc)
+{
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  return gc.tally_values + (int64_t)(blockIdx.x % gc.tally_replicas) * gc.tally_replica_stride;
+#else
+  return gc.tally_values;
+#endif
+}
+
 // Particle::event_collide, src/particle.cpp:331-415
 template<bool BX = false>
 OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_t i)
@@ -631,6 +641,22 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
   p.k_abs = ps.k_abs[i];
   ps.k_col[i] += p.wgt * p.xs_nu_fission / p.xs_total;
   ps.surface[i] = SURFACE_NONE;
+  if (gc.tallies_active && DM.n_collision_tallies > 0) {
+    ScoreCtx sc;
+    const int n_coord = ps.n_coord[i];
+    sc.flux = p.wgt / p.xs_total; // wgt_last / Sigma_t, src/tallies/tally_scoring.cpp:2546-2549
+    sc.xs_total = p.xs_total;
+    sc.xs_absorption = p.xs_absorption;
+    sc.xs_fission = ps.xs_fission[i];
+    sc.xs_nu_fission = p.xs_nu_fission;
+    sc.material = p.material;
+    sc.g = p.g;
+    sc.mg_ba = 0;
+    if (!DM.run_CE && p.material >= 0)
+      sc.mg_ba = mg_ba(p.material, mg_temperature_index(p.material, ps.sqrtkT[i]),
+        mg_angle_index(p.material, get_u(ps, i, n_coord - 1)));
+    score_collision(ps, i, n_coord, p.r, p.E, sc, score_values(gc));
+  }
   if (DM.run_CE) {
     bool no_nuclide;
     collision_ce<BX>(p, gc, fb, no_nuclide, ps.n_prefix ? ps.xs_prefix + (ps.id_shift + i) * ps.n_prefix : nullptr);
@@ -938,6 +964,8 @@ OMC_D Flight load_flight(const Flights& fl, int64_t j)
 OMC_D int score_prepare(const PState& ps, const Flight& f, int t, double* values, int score_part,
   int64_t& base, double* val, unsigned long long* red_counter = nullptr)
 {
+  if (ld(DM.tally_estimator + t) != OMCGPU_ESTIMATOR_TRACKLENGTH)
+    return 0; // collision-estimator tallies are scored by the collision kernel
   TallyEval te;
   const int64_t i = f.pidx; // cell / universe filters read the particle's coordinate levels
   const int n_coord = f.pidx >= 0 ? ps.n_coord[i] : 0;
@@ -2052,6 +2080,10 @@ static int upload_model(const omcgpu_model* m)
   UP(filter_data_ofs, nfl + 1);
   UP(filter_idata, n_fdat);
   UP(filter_ddata, n_fdat);
+  h.n_collision_tallies = 0;
+  for (int t = 0; t < nt; ++t)
+    h.n_collision_tallies += m->tally_estimator[t] == OMCGPU_ESTIMATOR_COLLISION ? 1 : 0;
+  UP(tally_estimator, nt);
   G.n_tally = nt ? m->tally_result_ofs[nt] : 0;
   G.tally_ofs.assign(m->tally_result_ofs, m->tally_result_ofs + (nt ? nt + 1 : 0));
   UP(tally_n_filters, nt);
@@ -2087,6 +2119,8 @@ static int check_supported(const omcgpu_model* m)
   for (int t = 0; t < m->n_tallies; ++t) {
     if (m->tally_n_filters[t] > OMCGPU_MAX_FILTERS || m->tally_n_scores[t] > OMCGPU_MAX_SCORES)
       return fail(OMCGPU_E_UNSUPPORTED, "tally has too many filters or scores%s");
+    if (m->tally_estimator[t] != OMCGPU_ESTIMATOR_TRACKLENGTH && m->tally_estimator[t] != OMCGPU_ESTIMATOR_COLLISION)
+      return fail(OMCGPU_E_UNSUPPORTED, "analog tally estimator (src/tallies/tally_scoring.cpp:2314-2414) not supported on the device%s");
     int n_mesh = 0;
     for (int k = 0; k < m->tally_n_filters[t]; ++k)
       if (m->filter_type[m->tally_filters[t * OMCGPU_MAX_FILTERS + k]] == OMCGPU_FILTER_MESH)
@@ -3202,7 +3236,8 @@ static int init_impl(const omcgpu_model* model, int device, int64_t max_particle
       return rc;
     G.tally_needs_cells = false;
     for (int f = 0; f < model->n_filters; ++f)
-      if (model->filter_type[f] == OMCGPU_FILTER_CELL || model->filter_type[f] == OMCGPU_FILTER_UNIVERSE)
+      if (model->filter_type[f] == OMCGPU_FILTER_CELL || model->filter_type[f] == OMCGPU_FILTER_UNIVERSE ||
+          model->filter_type[f] == OMCGPU_FILTER_DISTRIBCELL)
         G.tally_needs_cells = true;
   }
 #if OMC_CUDA

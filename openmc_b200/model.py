@@ -103,8 +103,8 @@ class Mesh:
 @dataclass
 class Filter:
     id: int
-    type: str                          # 'mesh' 'energy' 'cell' 'material' 'universe'
-    bins: object                       # mesh id | energy edges | list of ids
+    type: str                          # 'mesh' 'energy' 'cell' 'material' 'universe' 'distribcell'
+    bins: object                       # mesh id | energy edges | list of ids | [cell id]
 
 
 @dataclass
@@ -112,6 +112,7 @@ class Tally:
     id: int
     filters: list                      # filter ids
     scores: list                       # names
+    estimator: str = "tracklength"     # 'tracklength' | 'collision' (Tally::estimator_)
 
 
 # ----------------------------------------------------------------------------
@@ -527,10 +528,92 @@ class Model:
         v["n_coord_levels"] = depth(roots[0])
         if v["n_coord_levels"] > abi.OMCGPU_MAX_COORD:
             raise ValueError("geometry nests deeper than OMCGPU_MAX_COORD")
+        self._prepare_distribcell(v)
         return v
+
+    def _prepare_distribcell(self, v):
+        """prepare_distribcell + count_universe_instances, src/geometry_aux.cpp:327-500,
+        src/lattice.cpp:106-129: distribcell maps for the cells named by DistribcellFilters
+        (and, with settings['material_cell_offsets'], for every material cell), cell / lattice
+        offset tables, instances per cell."""
+        nc, nu, nl = v["n_cells"], v["n_universes"], v["n_lattices"]
+        ctype, cfill = v["cell_type"], v["cell_fill"]
+        uofs, ucells = v["univ_cell_ofs"], v["univ_cells"]
+        lofs, lun = v["lat_univ_ofs"], v["lat_universes"]
+
+        def cells_of(u):
+            return ucells[uofs[u]:uofs[u + 1]]
+
+        def count(search, target, memo):       # count_universe_instances :462-500
+            if search == target:
+                return 1
+            if search in memo:
+                return memo[search]
+            n = 0
+            for c in cells_of(search):
+                if ctype[c] == abi.OMCGPU_FILL_UNIVERSE:
+                    n += count(int(cfill[c]), target, memo)
+                elif ctype[c] == abi.OMCGPU_FILL_LATTICE:
+                    l = int(cfill[c])
+                    for u in lun[lofs[l]:lofs[l + 1]]:
+                        n += count(int(u), target, memo)
+            memo[search] = n
+            return n
+
+        root = v["root_universe"]
+        univ_instances = [count(root, u, {}) for u in range(nu)]
+        self._n_instances = [univ_instances[v["cell_universe"][c]] for c in range(nc)]
+
+        targets = {self._c_index[f.bins[0]] for f in self.filters if f.type == "distribcell"}
+        if self.settings.get("material_cell_offsets"):
+            targets |= {c for c in range(nc) if ctype[c] == abi.OMCGPU_FILL_MATERIAL}
+        dindex = np.full(nc, -1, np.int32)
+        target_univs = []
+        for u in range(nu):
+            for c in cells_of(u):
+                if int(c) in targets:
+                    if u not in target_univs:
+                        target_univs.append(u)
+                    dindex[c] = target_univs.index(u)
+        n_maps = len(target_univs)
+        v["cell_distribcell_index"] = dindex
+        if n_maps == 0:
+            return
+        # offset tables
+        cofs = [0]
+        for c in range(nc):
+            cofs.append(cofs[-1] + (n_maps if ctype[c] != abi.OMCGPU_FILL_MATERIAL else 0))
+        coff = np.full(max(cofs[-1], 1), -1, np.int32)
+        lat_size = [int(lofs[l + 1] - lofs[l]) for l in range(nl)]
+        loofs = [0]
+        for l in range(nl):
+            loofs.append(loofs[-1] + n_maps * lat_size[l])
+        loff = np.full(max(loofs[-1], 1), -1, np.int32)
+        for mp, tu in enumerate(target_univs):
+            memo = {}
+            for u in range(nu):
+                offset = 0
+                for c in cells_of(u):
+                    if ctype[c] == abi.OMCGPU_FILL_UNIVERSE:
+                        coff[cofs[c] + mp] = offset
+                        offset += count(int(cfill[c]), tu, memo)
+                    elif ctype[c] == abi.OMCGPU_FILL_LATTICE:
+                        coff[cofs[c] + mp] = offset
+                        l = int(cfill[c])
+                        o = 0                   # Lattice::fill_offset_table
+                        for k, uu in enumerate(lun[lofs[l]:lofs[l + 1]]):
+                            loff[loofs[l] + mp * lat_size[l] + k] = o
+                            o += count(int(uu), tu, memo)
+                        offset += o
+        v["cell_offset_ofs"] = np.array(cofs, np.int32)
+        v["cell_offset"] = coff
+        v["lat_offset_ofs"] = np.array(loofs + [loofs[-1]] * (max(nl, 1) + 1 - len(loofs)), np.int32)
+        v["lat_offsets"] = loff
 
     def flatten_tallies(self, n_groups=0, group_edges=None) -> dict:
         v = {}
+        if not hasattr(self, "_n_instances"):
+            self.flatten_geometry()
         nm = len(self.meshes)
         mnd = np.zeros(max(nm, 1), np.int32); msh = np.ones((max(nm, 1), 3), np.int32)
         mll = np.zeros((max(nm, 1), 3)); mw = np.ones((max(nm, 1), 3))
@@ -563,6 +646,12 @@ class Model:
                 # EnergyFilter::set_bins: matches the transport group structure?
                 if group_edges is not None and len(edges) == n_groups + 1:
                     fmg[i] = int(all(e == g for e, g in zip(edges, sorted(group_edges))))
+            elif f.type == "distribcell":
+                # DistribcellFilter::set_cell: one bin per instance of the cell
+                ftype[i] = abi.OMCGPU_FILTER_DISTRIBCELL
+                (cid,) = f.bins
+                fnb[i] = int(self._n_instances[self._c_index[cid]])
+                fi += [self._c_index[cid]]; fd += [0.0]
             else:
                 kind = {"cell": (abi.OMCGPU_FILTER_CELL, self._c_index, len(self.cells)),
                         "material": (abi.OMCGPU_FILTER_MATERIAL, self._m_index, len(self.materials)),
@@ -583,7 +672,10 @@ class Model:
         tst = np.zeros((max(nt, 1), abi.OMCGPU_MAX_FILTERS), np.int32)
         tns = np.zeros(max(nt, 1), np.int32); tsc = np.zeros((max(nt, 1), abi.OMCGPU_MAX_SCORES), np.int32)
         tofs = [0]
+        test = np.full(max(nt, 1), abi.OMCGPU_ESTIMATOR_TRACKLENGTH, np.int32)
         for i, t in enumerate(self.tallies):
+            test[i] = {"tracklength": abi.OMCGPU_ESTIMATOR_TRACKLENGTH, "collision": abi.OMCGPU_ESTIMATOR_COLLISION,
+                       "analog": abi.OMCGPU_ESTIMATOR_ANALOG}[t.estimator]
             tnf[i] = len(t.filters)
             stride = 1
             for k in range(len(t.filters) - 1, -1, -1):   # src/tallies/tally.cpp:503-516
@@ -594,7 +686,7 @@ class Model:
             tns[i] = len(t.scores)
             tsc[i, :len(t.scores)] = [_SCORES[s] for s in t.scores]
             tofs.append(tofs[-1] + stride * len(t.scores))
-        v.update(n_tallies=nt, tally_n_filters=tnf, tally_filters=tf, tally_strides=tst,
+        v.update(n_tallies=nt, tally_estimator=test, tally_n_filters=tnf, tally_filters=tf, tally_strides=tst,
                  tally_n_scores=tns, tally_scores=tsc, tally_result_ofs=np.array(tofs, np.int64))
         return v
 
@@ -609,6 +701,8 @@ class Model:
                 nb *= int(np.prod(m.dimension))
             elif f.type == "energy":
                 nb *= len(f.bins) - 1
+            elif f.type == "distribcell":
+                nb *= int(self._n_instances[self._c_index[f.bins[0]]])
             else:
                 nb *= len(f.bins)
         return nb, len(t.scores)

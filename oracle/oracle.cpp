@@ -213,6 +213,7 @@ struct Particle {
   double mu {0};
   double time {0};
   Vec3 r_last {0, 0, 0}, u_last {0, 0, 0};
+  Vec3 u_last_local {0, 0, 0}; // direction at the lowest level before the collision (MG angle index of a collision-estimator score)
   uint64_t seeds[4];
   int stream {STREAM_TRACKING};
   int64_t id {0};
@@ -245,6 +246,7 @@ struct RunState {
   double keff {1.0};
   int64_t work_index {0};
   bool tallies_active {false};
+  int n_collision_tallies {0};
   std::vector<omcgpu_site> fission_bank;
   int64_t fission_capacity {0};
   std::vector<int64_t> progeny_per_particle;
@@ -1664,7 +1666,10 @@ void mesh_bins_crossed(int m, Vec3 r0, Vec3 r1, Vec3 u, Match& match)
   }
 }
 
-void filter_get_all_bins(int f, Particle& p, Match& match)
+// `tracklength`: the estimator of the tally being scored (MeshFilter::get_all_bins and
+// EnergyFilter::get_all_bins differ for the collision estimator: src/tallies/filter_mesh.cpp:61-69,
+// src/tallies/filter_energy.cpp:62-67)
+void filter_get_all_bins(int f, Particle& p, Match& match, bool tracklength = true)
 {
   match.bins.clear();
   match.weights.clear();
@@ -1672,12 +1677,22 @@ void filter_get_all_bins(int f, Particle& p, Match& match)
   const double* ddata = M->filter_ddata + M->filter_data_ofs[f];
   switch (M->filter_type[f]) {
   case OMCGPU_FILTER_MESH:
-    mesh_bins_crossed(M->filter_mesh[f], p.r_last, p.r(), p.u(), match);
+    if (tracklength) {
+      mesh_bins_crossed(M->filter_mesh[f], p.r_last, p.r(), p.u(), match);
+    } else { // StructuredMesh::get_bin(r), src/mesh.cpp:874-929
+      int ijk[3] = {0, 0, 0};
+      bool in_mesh;
+      mesh_get_indices(M->filter_mesh[f], p.r(), ijk, in_mesh);
+      if (in_mesh) {
+        match.bins.push_back(mesh_bin_from_indices(M->filter_mesh[f], ijk));
+        match.weights.push_back(1.0);
+      }
+    }
     break;
   case OMCGPU_FILTER_ENERGY: {
     int nb = M->filter_n_bins[f];
     if (!M->run_CE && M->filter_matches_groups[f]) {
-      match.bins.push_back(M->mg_n_groups - p.g - 1);
+      match.bins.push_back(M->mg_n_groups - (tracklength ? p.g : p.g_last) - 1);
       match.weights.push_back(1.0);
     } else {
       double E = p.E_last;
@@ -1712,6 +1727,31 @@ void filter_get_all_bins(int f, Particle& p, Match& match)
       }
     }
     break;
+  case OMCGPU_FILTER_DISTRIBCELL: { // DistribcellFilter::get_all_bins, src/tallies/filter_distribcell.cpp:40-63
+    const int cell = idata[0];
+    const int map = M->cell_distribcell_index[cell];
+    int offset = 0;
+    for (int i = 0; i < p.n_coord; i++) {
+      const int c = p.coord[i].cell;
+      if (M->cell_type[c] == OMCGPU_FILL_UNIVERSE) {
+        offset += M->cell_offset[M->cell_offset_ofs[c] + map];
+      } else if (M->cell_type[c] == OMCGPU_FILL_LATTICE) {
+        const int lat = p.coord[i + 1].lattice;
+        const int* li = p.coord[i + 1].lat_idx;
+        const int32_t* n = M->lat_shape + 3 * lat;
+        if (li[0] >= 0 && li[0] < n[0] && li[1] >= 0 && li[1] < n[1] && li[2] >= 0 && li[2] < n[2])
+          offset += M->lat_offsets[M->lat_offset_ofs[lat] + n[0] * n[1] * n[2] * map +
+                                   n[0] * n[1] * li[2] + n[0] * li[1] + li[0]] +
+                    M->cell_offset[M->cell_offset_ofs[c] + map];
+      }
+      if (cell == c) {
+        match.bins.push_back(offset);
+        match.weights.push_back(1.0);
+        break;
+      }
+    }
+    break;
+  }
   }
 }
 
@@ -1726,13 +1766,26 @@ double mg_scatter_xs(int ba, int g)
   return M->sc_scattxs[ba * G + g] / ip;
 }
 
+// score_tracklength_tally_general / score_collision_tally, src/tallies/tally_scoring.cpp:2416-2490,
+// 2543-2620: the same filter / score machinery for the tallies of one estimator
+void score_tallies(Particle& p, double flux, int estimator);
 void score_tracklength_tally(Particle& p, double distance)
 {
-  double flux = p.wgt * distance;
+  score_tallies(p, p.wgt * distance, OMCGPU_ESTIMATOR_TRACKLENGTH);
+}
+void score_collision_tally(Particle& p)
+{ // flux = wgt_last / Sigma_t (:2546-2549); called after the collision, which leaves macro_xs alone
+  score_tallies(p, p.wgt_last / p.xs_total, OMCGPU_ESTIMATOR_COLLISION);
+}
+void score_tallies(Particle& p, double flux, int estimator)
+{
+  const bool tracklength = estimator == OMCGPU_ESTIMATOR_TRACKLENGTH;
   int G = M->mg_n_groups;
   std::vector<Match> matches(M->n_filters);
   std::vector<char> present(M->n_filters, 0);
   for (int t = 0; t < M->n_tallies; ++t) {
+    if (M->tally_estimator[t] != estimator)
+      continue;
     int nf = M->tally_n_filters[t];
     const int32_t* filt = M->tally_filters + OMCGPU_MAX_FILTERS * t;
     const int32_t* strides = M->tally_strides + OMCGPU_MAX_FILTERS * t;
@@ -1740,7 +1793,7 @@ void score_tracklength_tally(Particle& p, double distance)
     for (int i = 0; i < nf; ++i) {
       int f = filt[i];
       if (!present[f]) {
-        filter_get_all_bins(f, p, matches[f]);
+        filter_get_all_bins(f, p, matches[f], tracklength);
         present[f] = 1;
       }
       if (matches[f].bins.empty()) {
@@ -1792,7 +1845,11 @@ void score_tracklength_tally(Particle& p, double distance)
           }
         } else { // score_general_mg :1622-1990 (tracklength branch, i_nuclide = -1)
           int m = p.material;
-          int ba = (m >= 0) ? mg_ba(m, p.mg_t, mg_angle_index(m, p.u_local())) : 0;
+          // tracklength: no collision happened, g and the local direction are current; collision
+          // estimator: the pre-collision group and direction (:1632-1663 -- whether the particle
+          // scattered or not, that is what p_g / p_u resolve to)
+          const int p_g = tracklength ? p.g : p.g_last;
+          int ba = (m >= 0) ? mg_ba(m, p.mg_t, mg_angle_index(m, tracklength ? p.u_local() : p.u_last_local)) : 0;
           switch (scores[s]) {
           case OMCGPU_SCORE_FLUX:
             score = flux;
@@ -1804,14 +1861,14 @@ void score_tracklength_tally(Particle& p, double distance)
             score = p.xs_absorption * flux;
             break;
           case OMCGPU_SCORE_SCATTER:
-            score = (m >= 0) ? flux * mg_scatter_xs(ba, p.g) : 0.0;
+            score = (m >= 0) ? flux * mg_scatter_xs(ba, p_g) : 0.0;
             break;
           case OMCGPU_SCORE_FISSION:
-            score = (m >= 0 && M->mgm_fissionable[m]) ? flux * M->mg_fission[ba * G + p.g] : flux * 0.;
+            score = (m >= 0 && M->mgm_fissionable[m]) ? flux * M->mg_fission[ba * G + p_g] : flux * 0.;
             break;
           case OMCGPU_SCORE_NU_FISSION:
             score =
-              (m >= 0 && M->mgm_fissionable[m]) ? flux * M->mg_nu_fission[ba * G + p.g] : flux * 0.;
+              (m >= 0 && M->mgm_fissionable[m]) ? flux * M->mg_nu_fission[ba * G + p_g] : flux * 0.;
             break;
           }
         }
@@ -2026,6 +2083,7 @@ void event_collide(Particle& p)
 {
   p.k_col += p.wgt * p.xs_nu_fission / p.xs_total;
   p.surface = SURFACE_NONE;
+  p.u_last_local = p.u_local();
   if (M->run_CE) {
     collision_ce(p);
     if (p.E < M->energy_cutoff) // src/physics.cpp:67-71
@@ -2034,6 +2092,8 @@ void event_collide(Particle& p)
     collision_mg(p);
   }
   RS.n_coll++;
+  if (RS.tallies_active && RS.n_collision_tallies > 0) // src/particle.cpp:362-363
+    score_collision_tally(p);
   p.fission = false;
   p.material_last = C_NONE;
   for (int j = 0; j < p.n_coord - 1; ++j) { // src/particle.cpp:396-406
@@ -2109,6 +2169,9 @@ void transport_generation(const omcgpu_gen_in& in, const omcgpu_site* source_ban
   RS.keff = in.keff;
   RS.work_index = in.id_offset;
   RS.tallies_active = in.tallies_active != 0;
+  RS.n_collision_tallies = 0;
+  for (int t = 0; t < M->n_tallies; ++t)
+    RS.n_collision_tallies += M->tally_estimator[t] == OMCGPU_ESTIMATOR_COLLISION ? 1 : 0;
   RS.fission_bank.clear();
   RS.fission_capacity = fission_capacity;
   RS.progeny_per_particle.assign(in.n_particles, 0);

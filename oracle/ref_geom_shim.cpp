@@ -311,6 +311,22 @@ const char* ref_geom_error(void)
   return g_msg;
 }
 
+// prepare_distribcell (src/geometry_aux.cpp:327-446) with settings::material_cell_offsets on:
+// every material cell gets a distribcell map, and exhaustive_find_cell then reports the real
+// cell instance (src/geometry.cpp:66-98) -- the reference's own offset tables against the
+// flattener's (openmc_b200/model.py _prepare_distribcell).
+int ref_geom_prepare_distribcell(void)
+{
+  try {
+    settings::material_cell_offsets = true;
+    prepare_distribcell(nullptr);
+  } catch (const std::exception& e) {
+    std::snprintf(g_msg, sizeof(g_msg), "%s", e.what());
+    return -1;
+  }
+  return 0;
+}
+
 // Parse a geometry.xml text with the reference's readers and finalize the geometry
 // (read_geometry_xml + finalize_geometry, src/geometry_aux.cpp:55-84, 268-281).
 // material_ids: the ids the cells may name, mapped to 0..n-1 in this order.

@@ -99,6 +99,8 @@ def load_model_npz(path):
     nc = int(vals["n_cells"])
     vals.setdefault("cell_rotated", np.zeros(nc, np.int32))
     vals.setdefault("cell_rotation", np.zeros(9 * nc))
+    # per-tally estimator added later: the fixtures' tallies are tracklength tallies
+    vals.setdefault("tally_estimator", np.full(max(int(vals["n_tallies"]), 1), abi.OMCGPU_ESTIMATOR_TRACKLENGTH, np.int32))
     return abi.ModelHandle(vals)
 
 
