@@ -352,7 +352,10 @@ typedef struct omcgpu_gen_in {
   uint64_t stride;            /* openmc_get_stride()                                     */
   double keff;                /* simulation::keff                                        */
   int32_t tallies_active;     /* score user tallies this generation                      */
-  int32_t reserved;
+  int32_t source_bank_clean;  /* 1: the host has not touched simulation::source_bank since the library wrote it
+                                 (omcgpu_next_generation / omcgpu_sync_bank): the device-resident copy is current and the
+                                 upload is skipped.  0: the host bank is authoritative (Python may edit it between batches,
+                                 tests/unit_tests/test_lib.py:451-455) and is uploaded. */
 } omcgpu_gen_in;
 
 typedef struct omcgpu_gen_out {
@@ -393,6 +396,14 @@ typedef struct omcgpu_gen_out {
  * present and OMCGPU_E_UNSUPPORTED if the model needs a feature the device path
  * refuses -- there is no CPU fallback. */
 int omcgpu_init(const omcgpu_model* model, int device, int64_t max_particles);
+
+/* Re-upload mutable properties of an initialised engine from the (re-flattened) host model: what
+ * openmc_cell_set_temperature (include/openmc/capi.h:30) and openmc_material_set_densities /
+ * openmc_material_set_density (:98) change between batches.  Array shapes must equal those given to
+ * omcgpu_init; anything else needs a new omcgpu_init. */
+#define OMCGPU_UPDATE_CELL_TEMPERATURES  1  /* cell_sqrtkT                         */
+#define OMCGPU_UPDATE_MATERIAL_DENSITIES 2  /* mat_atom_density                    */
+int omcgpu_update(const omcgpu_model* model, uint32_t what);
 
 /* Release everything (replaces free_event_queues, src/finalize.cpp:57-59). */
 int omcgpu_finalize(void);

@@ -1706,6 +1706,7 @@ struct Engine {
   double* d_tally = nullptr;
   int64_t n_tally = 0;
   std::vector<int64_t> tally_ofs; // host copy of tally_result_ofs
+  int n_cell_sqrtkT = 0, n_mat_nuclides = 0; // array lengths omcgpu_update checks
   int tally_replicas = 1;       // copies of the VALUE arrays k_score spreads its REDs over
   int64_t tally_stride = 0;
   cudaStream_t stream = 0;
@@ -1872,6 +1873,7 @@ static int upload_model(const omcgpu_model* m)
   UP(cell_material, n_cmat);
   UP(cell_sqrtkT_ofs, nc + 1);
   UP(cell_sqrtkT, n_ckt);
+  G.n_cell_sqrtkT = n_ckt;
   UP(cell_translation, (size_t)nc * 3);
   UP(cell_rotated, nc);
   UP(cell_rotation, (size_t)nc * 9);
@@ -1923,6 +1925,7 @@ static int upload_model(const omcgpu_model* m)
   UP(mat_nuc_ofs, nm + 1);
   UP(mat_nuclide, n_mn);
   UP(mat_atom_density, n_mn);
+  G.n_mat_nuclides = n_mn;
   if (h.run_CE) {
     const int nn = h.n_nuclides;
     const int64_t n_pts = m->nuc_grid_ofs[nn];
@@ -2865,6 +2868,34 @@ int64_t omcgpu_kernel_launches(void)
   return g_launches;
 }
 
+int omcgpu_update(const omcgpu_model* model, uint32_t what)
+{
+  if (!G.ready)
+    return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  if (!model)
+    return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_update: no model%s");
+  const omcgpu_model& h = G.hm; // scalars + device pointers of the model in use
+  if (model->n_cells != h.n_cells || model->n_materials != h.n_materials)
+    return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_update: the model's shape differs from the one given to omcgpu_init%s");
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  if (what & OMCGPU_UPDATE_CELL_TEMPERATURES) {
+    const int n = h.n_cells ? model->cell_sqrtkT_ofs[h.n_cells] : 0;
+    if (n != G.n_cell_sqrtkT)
+      return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_update: number of cell temperatures changed%s");
+    CUDA_OK(cudaMemcpy(const_cast<double*>(h.cell_sqrtkT), model->cell_sqrtkT, n * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  if (what & OMCGPU_UPDATE_MATERIAL_DENSITIES) {
+    const int n = h.n_materials ? model->mat_nuc_ofs[h.n_materials] : 0;
+    if (n != G.n_mat_nuclides)
+      return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_update: number of material nuclides changed%s");
+    CUDA_OK(cudaMemcpy(const_cast<double*>(h.mat_atom_density), model->mat_atom_density, n * sizeof(double),
+      cudaMemcpyHostToDevice));
+  }
+  if (what & ~(OMCGPU_UPDATE_CELL_TEMPERATURES | OMCGPU_UPDATE_MATERIAL_DENSITIES))
+    return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_update: unknown property%s");
+  return 0;
+}
+
 int omcgpu_sweep_kind(void)
 {
   if (!G.ready)
@@ -3394,10 +3425,21 @@ int omcgpu_run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
   return run_generation(in, out);
 }
 
+// host bank -> device unless the caller vouches that the device copy is current
+static int upload_source(const omcgpu_gen_in* in, const omcgpu_site* source_bank)
+{
+  if (in->source_bank_clean) {
+    if (in->n_particles > G.n_src)
+      return fail(OMCGPU_E_OUT_OF_BOUNDS, "source_bank_clean: the device bank holds fewer sites than n_particles%s");
+    return 0;
+  }
+  return set_source_bank_async(source_bank, in->n_particles);
+}
+
 int omcgpu_transport_generation(const omcgpu_gen_in* in, const omcgpu_site* source_bank,
   omcgpu_site* fission_bank, int64_t fission_capacity, omcgpu_gen_out* out)
 {
-  int rc = set_source_bank_async(source_bank, in->n_particles);
+  int rc = upload_source(in, source_bank);
   if (rc)
     return rc;
   rc = run_generation(in, out);
@@ -3415,7 +3457,7 @@ int omcgpu_comb_fission_bank(int64_t start, int64_t total, int64_t n_particles, 
 int omcgpu_next_generation(const omcgpu_gen_in* in, omcgpu_site* source_bank, int64_t seed_id,
   omcgpu_gen_out* out)
 {
-  int rc = set_source_bank_async(source_bank, in->n_particles);
+  int rc = upload_source(in, source_bank);
   if (rc)
     return rc;
   rc = run_generation(in, out);

@@ -108,9 +108,14 @@ class Engine:
         return bank[:n.value]
 
     def gen_in(self, n, id_offset, particle_seed_base, keff, tallies_active,
-               master_seed=DEFAULT_SEED, stride=DEFAULT_STRIDE) -> abi.GenIn:
+               master_seed=DEFAULT_SEED, stride=DEFAULT_STRIDE, source_bank_clean=False) -> abi.GenIn:
         return abi.GenIn(n, id_offset, particle_seed_base, master_seed, stride, keff,
-                         int(tallies_active), 0)
+                         int(tallies_active), int(source_bank_clean))
+
+    def update(self, model: abi.ModelHandle, what: int):
+        """omcgpu_update: re-upload cell temperatures / material densities of `model`"""
+        self._check(self.lib.omcgpu_update(model.byref(), C.c_uint32(what)))
+        self.model = model
 
     def run_generation(self, gen_in: abi.GenIn) -> abi.GenOut:
         out = abi.GenOut()

@@ -2814,7 +2814,7 @@ int orc_run_eigenvalue(const orc_settings* st, omcgpu_site* source_bank, orc_res
       in.stride = st->stride;
       in.keff = keff;
       in.tallies_active = active ? 1 : 0;
-      in.reserved = 0;
+      in.source_bank_clean = 0;
       transport_generation(in, source_bank, 3 * N);
       total_weight += RS.total_weight;
       ev += RS.n_events;

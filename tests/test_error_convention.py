@@ -144,3 +144,80 @@ def test_full_fission_bank_stops_banking_like_the_reference(emu_lib, monkeypatch
         assert np.array_equal(fb[f], fb_o[f]), f
     assert out.n_events == out_o.n_events
     eng.finalize()
+
+
+def test_update_reuploads_temperatures_and_densities(emu_lib):
+    """omcgpu_update: what openmc_cell_set_temperature / openmc_material_set_densities change
+    between batches (include/openmc/capi.h:30,98) reaches the device without a new omcgpu_init:
+    a generation after the update equals the oracle's on the edited model"""
+    model, box, of = cases.build("mg_temperature_multi")    # two cells at different temperatures
+    o = Oracle(model)
+    n = 600
+    src = o.sample_initial_source(n, box, of)
+    # (the two temperature blocks of the regression case's UO2 carry the same numbers: make the
+    # hotter block absorb 5 % more, so that a cell's temperature shows in the transport)
+    G = int(model["mg_n_groups"])
+    ba_hot = int(model["blk_ang_ofs"][int(model["mgm_blk_ofs"][0]) + int(np.argmax(model["mgm_kTs"][:2]))])
+    keep_abs = model["mg_absorption"].copy(); keep_tot = model["mg_total"].copy()
+    model["mg_total"][ba_hot * G:(ba_hot + 1) * G] += 0.05 * keep_abs[ba_hot * G:(ba_hot + 1) * G]
+    model["mg_absorption"][ba_hot * G:(ba_hot + 1) * G] *= 1.05
+    eng = lib.Engine(emu_lib)
+    eng.init(model, 0, n)
+    gi = eng.gen_in(n, 0, 0, 1.0, False)
+    _, out0 = eng.transport_generation(gi, src)
+    keep = model["cell_sqrtkT"].copy()
+    try:
+        model["cell_sqrtkT"][:] = keep.max()                # every cell at the hotter temperature
+        eng.update(model, abi.OMCGPU_UPDATE_CELL_TEMPERATURES)
+        _, out1 = eng.transport_generation(gi, src)
+        _, out_o = Oracle(model).transport_generation(gi, src)
+        assert out1.n_fission == out_o.n_fission and out1.n_events == out_o.n_events
+        assert out1.n_events != out0.n_events              # the temperatures do matter in this model
+        with pytest.raises(lib.OmcGpuError) as e:
+            eng.update(model, 64)
+        assert _code(e) == abi.OMCGPU_E_INVALID_ARGUMENT
+    finally:
+        model["cell_sqrtkT"][:] = keep
+        model["mg_absorption"][:] = keep_abs
+        model["mg_total"][:] = keep_tot
+    eng.finalize()
+    # densities, on a continuous-energy model
+    model, box, of, _ = cases.build_ce()
+    src = Oracle(model).sample_initial_source(n, box, of)
+    eng.init(model, 0, n)
+    keep = model["mat_atom_density"].copy()
+    try:
+        model["mat_atom_density"][:] = keep * 0.9
+        eng.update(model, abi.OMCGPU_UPDATE_MATERIAL_DENSITIES)
+        fb, out1 = eng.transport_generation(gi, src)
+        fb_o, out_o = Oracle(model).transport_generation(gi, src)
+        assert out1.n_fission == out_o.n_fission and out1.n_events == out_o.n_events
+        assert np.array_equal(fb["E"], fb_o["E"])
+    finally:
+        model["mat_atom_density"][:] = keep
+    eng.finalize()
+
+
+def test_clean_source_bank_skips_the_upload(emu_lib):
+    """gen_in.source_bank_clean = 1: the host vouches that it has not touched its bank since the
+    library wrote it; the device-resident bank is used and the host buffer is not read"""
+    model, box, of = cases.build("mg_legendre")
+    o = Oracle(model)
+    n = 400
+    bank = np.ascontiguousarray(o.sample_initial_source(n, box, of))
+    eng = lib.Engine(emu_lib)
+    eng.init(model, 0, n)
+    out_a = eng.next_generation(eng.gen_in(n, 0, 0, 1.0, False), bank, 1)     # uploads, leaves the next source on both sides
+    after = bank.copy()
+    bank["wgt"][:] = 0.0                                                        # garbage the host copy ...
+    out_b = eng.next_generation(eng.gen_in(n, 0, n, 1.0, False, source_bank_clean=True), bank, 2)
+    ref = after.copy()
+    out_c = o_next = None
+    eng2 = lib.Engine(emu_lib)       # the same second generation from the intact host copy
+    eng.finalize()
+    eng2.init(model, 0, n)
+    out_c = eng2.next_generation(eng2.gen_in(n, 0, n, 1.0, False), ref, 2)
+    assert out_b.total_weight == n == out_c.total_weight                        # ... it was not read
+    assert out_b.n_fission == out_c.n_fission and out_b.n_events == out_c.n_events
+    assert np.array_equal(bank["E"], ref["E"])
+    eng2.finalize()
