@@ -620,10 +620,37 @@ OMC_D double* score_values(const GenCtx& gc)
 #endif
 }
 
+// Tallies with the collision estimator, scored by the collision kernel before collision()
+// (score_collision_tally, src/tallies/tally_scoring.cpp:2543-2620).  Out of line and fed from the
+// particle's columns, not from ev_collide's registers: models without such tallies (the default
+// estimator is tracklength) pay one uniform branch.
+OMC_OOL void ev_collide_score(const PState& ps, const GenCtx& gc, int64_t i)
+{
+  ScoreCtx sc;
+  const int n_coord = ps.n_coord[i];
+  const int material = ps.material[i];
+  sc.xs_total = ps.xs_total[i];
+  sc.flux = ps.wgt[i] / sc.xs_total; // wgt_last / Sigma_t, src/tallies/tally_scoring.cpp:2546-2549
+  sc.xs_absorption = ps.xs_absorption[i];
+  sc.xs_fission = ps.xs_fission[i];
+  sc.xs_nu_fission = ps.xs_nu_fission[i];
+  sc.material = material;
+  sc.g = ps.g[i];
+  sc.mg_ba = 0;
+  if (!DM.run_CE && material >= 0)
+    sc.mg_ba = mg_ba(material, mg_temperature_index(material, ps.sqrtkT[i]),
+      mg_angle_index(material, get_u(ps, i, n_coord - 1)));
+  score_collision(ps, i, n_coord, get_r(ps, i, 0), ps.E[i], sc, score_values(gc));
+}
+
 // Particle::event_collide, src/particle.cpp:331-415
-template<bool BX = false>
+// SCORE: score the collision-estimator tallies here (the tail kernel); the list kernels leave
+// that to k_collision_score, launched ahead of them only when the model has such tallies
+template<bool BX = false, bool SCORE = true>
 OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_t i)
 {
+  if (SCORE && gc.tallies_active && DM.n_collision_tallies > 0)
+    ev_collide_score(ps, gc, i);
   Collider p;
   p.r = get_r(ps, i, 0);
   p.u = get_u(ps, i, 0);
@@ -641,22 +668,6 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
   p.k_abs = ps.k_abs[i];
   ps.k_col[i] += p.wgt * p.xs_nu_fission / p.xs_total;
   ps.surface[i] = SURFACE_NONE;
-  if (gc.tallies_active && DM.n_collision_tallies > 0) {
-    ScoreCtx sc;
-    const int n_coord = ps.n_coord[i];
-    sc.flux = p.wgt / p.xs_total; // wgt_last / Sigma_t, src/tallies/tally_scoring.cpp:2546-2549
-    sc.xs_total = p.xs_total;
-    sc.xs_absorption = p.xs_absorption;
-    sc.xs_fission = ps.xs_fission[i];
-    sc.xs_nu_fission = p.xs_nu_fission;
-    sc.material = p.material;
-    sc.g = p.g;
-    sc.mg_ba = 0;
-    if (!DM.run_CE && p.material >= 0)
-      sc.mg_ba = mg_ba(p.material, mg_temperature_index(p.material, ps.sqrtkT[i]),
-        mg_angle_index(p.material, get_u(ps, i, n_coord - 1)));
-    score_collision(ps, i, n_coord, p.r, p.E, sc, score_values(gc));
-  }
   if (DM.run_CE) {
     bool no_nuclide;
     collision_ce<BX>(p, gc, fb, no_nuclide, ps.n_prefix ? ps.xs_prefix + (ps.id_shift + i) * ps.n_prefix : nullptr);
@@ -850,6 +861,22 @@ OMC_KERNEL_MB(k_surface_xa, EvArgs, body_surface_xa<false>, XA_MINBLOCKS)
 OMC_KERNEL_MB(k_surface_xa_b, EvArgs, body_surface_xa<true>, 2)
 OMC_KERNEL_DYN(k_surface_xa_dyn, EvArgs, body_surface_xa<false>, XA_MINBLOCKS)
 
+// collision-estimator tallies of the particles on a collision list, before the collision kernel
+// changes them (launched only for models that have such tallies: the collision kernels themselves
+// carry none of the scoring code)
+OMC_D void body_collision_score(int64_t tid, const EvArgs& a)
+{
+  if (tid >= *a.q_in.count)
+    return;
+  ev_collide_score(a.ps, a.gc, list_item(a.q_in, tid));
+}
+OMC_KERNEL(k_collision_score, EvArgs, body_collision_score)
+#define LAUNCH_COLLISION_SCORE(n_ub, stream, args) \
+  do { \
+    if (G.n_collision_tallies > 0 && (args).gc.tallies_active) \
+      OMC_LAUNCH(k_collision_score, n_ub, stream, args); \
+  } while (0)
+
 template<bool BX>
 OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
 {
@@ -857,7 +884,7 @@ OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
     return;
   const int32_t i = list_item(a.q_in, tid);
   prefetch_particle(a.ps, i, true);
-  if (ev_collide<BX>(a.ps, a.gc, a.fb, i)) {
+  if (ev_collide<BX, false>(a.ps, a.gc, a.fb, i)) {
     ev_xs<BX>(a.ps, i, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_COLLIDE : nullptr);
     advance_and_route(tid, a, i);
   } else {
@@ -1220,7 +1247,7 @@ OMC_D void body_collide(int64_t tid, const EvArgs& a)
     return;
   const int32_t i = list_item(a.q_in, tid);
   prefetch_particle(a.ps, i, true);
-  const bool alive = ev_collide<BX>(a.ps, a.gc, a.fb, i);
+  const bool alive = ev_collide<BX, false>(a.ps, a.gc, a.fb, i);
   if (a.ordered)
     a.ps.next_ev[i] = alive ? 3 : 0;
   else if (alive)
@@ -1707,6 +1734,7 @@ struct Engine {
   int64_t n_tally = 0;
   std::vector<int64_t> tally_ofs; // host copy of tally_result_ofs
   int n_cell_sqrtkT = 0, n_mat_nuclides = 0; // array lengths omcgpu_update checks
+  int n_collision_tallies = 0;
   int tally_replicas = 1;       // copies of the VALUE arrays k_score spreads its REDs over
   int64_t tally_stride = 0;
   cudaStream_t stream = 0;
@@ -2086,6 +2114,7 @@ static int upload_model(const omcgpu_model* m)
   h.n_collision_tallies = 0;
   for (int t = 0; t < nt; ++t)
     h.n_collision_tallies += m->tally_estimator[t] == OMCGPU_ESTIMATOR_COLLISION ? 1 : 0;
+  G.n_collision_tallies = h.n_collision_tallies;
   UP(tally_estimator, nt);
   G.n_tally = nt ? m->tally_result_ofs[nt] : 0;
   G.tally_ofs.assign(m->tally_result_ofs, m->tally_result_ofs + (nt ? nt + 1 : 0));
@@ -2485,9 +2514,11 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       EvArgs ac = a;
       ac.q_in.idx = G.d_vals_out;
       CUDA_OK(cudaEventRecord(G.evk0[1][ev], st_coll));
+      LAUNCH_COLLISION_SCORE(n_alive, st_coll, ac);
       LAUNCH_XS(k_collide, n_alive, st_coll, ac);
     } else {
       CUDA_OK(cudaEventRecord(G.evk0[1][ev], st_coll));
+      LAUNCH_COLLISION_SCORE(n_alive, st_coll, a);
       LAUNCH_XS(k_collide, n_alive, st_coll, a);
     }
     CUDA_OK(cudaEventRecord(G.evk1[1][ev], st_coll));
@@ -2670,6 +2701,7 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       CUDA_OK(cudaStreamWaitEvent(st_coll, G.e_adv, 0));
     CUDA_OK(cudaEventRecord(G.evk0[1][ev], st_coll));
     a.cursor = in_slot + 5;
+    LAUNCH_COLLISION_SCORE(n_alive, st_coll, a);
     LAUNCH_XA(k_collide_xa, n_alive, st_coll, a);
     CUDA_OK(cudaEventRecord(G.evk1[1][ev], st_coll));
     if (G.overlap) {
