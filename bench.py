@@ -3,7 +3,7 @@
 active-batch particles/s; macro-xs lookups/s).
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path)
-    python bench.py --impl reference --gpus N --steps K ...  # CPU oracle on the host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own binary on the host cores
 
 A "step" is ONE active generation of the workload: initialise n histories from
 the source bank, run the event loop to completion with the tallies active, sort
@@ -46,11 +46,23 @@ def parse():
                     help="pincell_ce = config C2 (the bench line); the others are C1, C3, C4, C5")
     ap.add_argument("--n-fuel-nuclides", type=int, default=300, help="pwr_core_ce: nuclides in the fuel")
     ap.add_argument("--cpu-sample", type=int, default=160_000, help="histories of the cpu_baseline sample (~25 s of CPU work)")
+    ap.add_argument("--ref-particles", type=int, default=0,
+                    help="histories per batch of the reference binary's runs (default 2500 per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the C5 / C1 / C3 / C4 sub-lines (N = 1 runs of the default workload add them)")
     return ap.parse_args()
+
+
+def build_workload_description(args):
+    w = args.workload
+    name = {"pincell_ce": f"UO2 pincell CE, synthetic library 10 nuclides x {args.n_grid} pts (config C2)",
+            "assembly_ce": f"17x17 assembly CE, synthetic library x {args.n_grid} pts, pin-wise mesh tally (config C3)",
+            "pwr_core_ce": f"Hoogenboom-Martin full core CE, {args.n_fuel_nuclides}-nuclide fuel x {args.n_grid} pts (config C5)",
+            "c5g7_core": "C5G7-style 2-D core MG, 510x510 mesh tally (config C4)",
+            "pincell_mg": "pincell_multigroup 7-group C5G7 (config C1)"}[w]
+    return None, None, None, name
 
 
 def build_workload(args):
@@ -472,7 +484,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        cpu = cpu_baseline(args, r["src"], args.cpu_sample, cores)
+        if reference_binary_available():
+            cpu = reference_binary_baseline(args, args.ref_particles or 2500 * cores, 2, 1, cores)
+        else:
+            cpu = cpu_baseline(args, r["src"], args.cpu_sample, cores)
 
     if rank == 0:
         line = {
@@ -557,30 +572,91 @@ def xs_probe(eng, model, n, peak, box):
             "model": "(60 + 116 n) B per lookup"}
 
 
+def reference_binary_available():
+    from oracle import refrun
+    return refrun.available()
+
+
+def reference_binary_baseline(args, n_per_batch, active, inactive, threads, modes=("history", "event")):
+    """time the UNMODIFIED reference (oracle/_ref/openmc: every translation unit of libopenmc compiled
+    from /root/reference with OpenMP, against oracle/h5shim) on the workload: XML inputs + the synthetic
+    library written by oracle/refrun.py, `inactive` + `active` batches of n_per_batch histories, all
+    host threads, history-based and --event.  The rate is the reference's own "Calculation Rate
+    (active)" line (src/output.cpp:457-497)."""
+    import shutil
+    import tempfile
+    from openmc_b200 import examples
+    from oracle import refrun
+    w = args.workload
+    d = tempfile.mkdtemp(prefix="omc_ref_")
+    try:
+        if w in ("pincell_ce", "assembly_ce", "pwr_core_ce"):
+            if w == "pincell_ce":
+                m, libx, box, of = examples.pincell_ce(n_grid=args.n_grid)
+            elif w == "assembly_ce":
+                m, libx, box, of = examples.assembly_ce(n_grid=args.n_grid)
+            else:
+                m, libx, box, of = examples.pwr_core_ce(n_grid=args.n_grid, n_fuel_nuclides=args.n_fuel_nuclides)
+            refrun.write_ce_library(os.path.join(d, "data"), libx)
+            xs, ce = "data/cross_sections.xml", True
+        else:
+            m, libx, box, of = examples.c5g7_core() if w == "c5g7_core" else examples.pincell_multigroup()
+            refrun.write_mgxs_library(os.path.join(d, "mgxs.h5"), libx)
+            xs, ce = "mgxs.h5", False
+        with open(os.path.join(d, "model.xml"), "w") as f:
+            f.write(refrun.model_xml(m, xs, n_per_batch, inactive + active, inactive, box, of, run_CE=ce,
+                                     extra={"output": "<summary>false</summary><tallies>false</tallies>"}))
+        res = {}
+        for mode in modes:
+            t0 = time.perf_counter()
+            r = refrun.run(d, threads=threads, event=(mode == "event"))
+            if r["returncode"] != 0:
+                raise RuntimeError("reference run failed: " + (r["stdout"][-400:] + r["stderr"][-400:]))
+            res[mode] = {"particles_per_s": r["rates"]["active"], "inactive_particles_per_s": r["rates"].get("inactive"),
+                         "active_s": r["times"].get("Time in active batches"), "wall_s": time.perf_counter() - t0}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    best = max(res, key=lambda k: res[k]["particles_per_s"])
+    return {"value": res[best]["particles_per_s"], "unit": "particles/s", "cores": threads, "kind": "reference",
+            "mode": best, "history": res.get("history"), "event": res.get("event"),
+            "sample": f"the reference's own openmc binary (unmodified sources, OpenMP, CMake-Release flags -O3 -DNDEBUG), {threads} threads: "
+                      f"{inactive} inactive + {active} active batches of {n_per_batch} histories of the same "
+                      f"workload (XML + synthetic library), tallies active in the active batches; value = its "
+                      f"'Calculation Rate (active)' in the faster of history-based and --event mode"}
+
+
 def reference_arm(args, rank, world):
-    """--impl reference: the CPU restatement (oracle) on all host cores; the
-    reference itself needs HDF5 + cmake and cannot be built here."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores --
+    oracle/_ref/openmc (the unmodified reference built against oracle/h5shim) when it is there,
+    else the oracle port."""
     if rank != 0:
         return
-    from oracle.binding import Oracle
-    model, box, of, workload = build_workload(args)
-    o = Oracle(model)
     cores = os.cpu_count() or 1
-    n = args.cpu_sample
-    src = o.sample_initial_source(n, box, of)
-    vals = []
-    for s in range(args.warmup + args.steps):
-        r = cpu_baseline(args, src, n, cores)
-        if s >= args.warmup:
-            vals.append(r)
-    v = float(np.mean([r["value"] for r in vals]))
+    _, _, _, workload = build_workload_description(args)
+    if reference_binary_available():
+        n = args.ref_particles or 2500 * cores
+        cpu = reference_binary_baseline(args, n, args.steps, args.warmup, cores)
+        v = cpu["value"]
+    else:
+        from oracle.binding import Oracle
+        model, box, of, workload = build_workload(args)
+        o = Oracle(model)
+        n = args.cpu_sample
+        src = o.sample_initial_source(n, box, of)
+        vals = []
+        for s in range(args.warmup + args.steps):
+            r = cpu_baseline(args, src, n, cores)
+            if s >= args.warmup:
+                vals.append(r)
+        v = float(np.mean([r["value"] for r in vals]))
+        cpu = {"value": v, "unit": "particles/s", "cores": vals[0]["cores"], "kind": "port",
+               "sample": vals[0]["sample"]}
     line = {"impl": "reference", "metric": "particles/sec (active)", "value": v,
             "unit": "particles/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * n / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "particles_per_step": n},
-            "cpu_baseline": {"value": v, "unit": "particles/s", "cores": vals[0]["cores"],
-                             "kind": "port", "sample": vals[0]["sample"]},
+            "cpu_baseline": cpu,
             "e2e": {"value": v, "unit": "particles/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -27,7 +27,10 @@ def build(force=False):
              or os.path.getmtime(LIB) < os.path.getmtime(hdr))
     have_ref = os.path.isdir("/root/reference/src")
     shim = os.path.join(HERE, "ref_geom_shim.cpp")
+    full = os.path.join(HERE, "_ref", "openmc")
+    h5shim = os.path.join(HERE, "h5shim", "h5shim.cpp")
     ref_stale = have_ref and (not os.path.exists(REF_LIB) or not os.path.exists(REF_GEOM_LIB)
+                              or not os.path.exists(full) or os.path.getmtime(full) < os.path.getmtime(h5shim)
                               or os.path.getmtime(REF_GEOM_LIB) < os.path.getmtime(shim)
                               or os.path.getmtime(REF_GEOM_LIB) < os.path.getmtime(os.path.join(HERE, "Makefile")))
     if force or stale or ref_stale:

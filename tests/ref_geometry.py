@@ -12,62 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "oracle", "_ref", "libref_geom.so")
 
 
-def _fmt(x):
-    return " ".join(repr(float(v)) for v in x)
-
-
-LATTICE_ID_BASE = 100000   # universes and lattices share one id space in geometry.xml
-                           # (a cell's fill is looked up as a universe first, src/geometry_aux.cpp:
-                           # 90-106); this repo's description refers to lattices by object
-
-
-def geometry_xml(m) -> str:
-    out = ["<?xml version='1.0' encoding='utf-8'?>", "<geometry>"]
-    for s in m.surfaces:
-        bc = "" if s.boundary in ("transmission", None) else f' boundary="{s.boundary}"'
-        if getattr(s, "periodic_surface_id", None) is not None:
-            bc += f' periodic_surface_id="{s.periodic_surface_id}"'
-        out.append(f'  <surface id="{s.id}" type="{s.kind}" coeffs="{_fmt(s.coeffs)}"{bc}/>')
-    for c in m.cells:
-        a = [f'id="{c.id}"', f'universe="{c.universe}"']
-        if c.fill_type == "material":
-            a.append('material="void"' if c.fill is None else f'material="{c.fill.id}"')
-        elif c.fill_type == "universe":
-            a.append(f'fill="{c.fill}"')
-        else:
-            a.append(f'fill="{LATTICE_ID_BASE + c.fill.id}"')
-        if c.region:
-            a.append(f'region="{c.region}"')
-        if any(float(t) != 0.0 for t in c.translation):
-            a.append(f'translation="{_fmt(c.translation)}"')
-        if getattr(c, "rotation", None) is not None:
-            a.append(f'rotation="{_fmt(c.rotation)}"')
-        out.append("  <cell " + " ".join(a) + "/>")
-    for l in m.lattices:
-        arr = np.asarray(l.universes)
-        if arr.ndim == 2:
-            ny, nx = arr.shape
-            dim = f"{nx} {ny}"
-            nd = 2
-            slabs = [arr]
-        else:
-            nz, ny, nx = arr.shape
-            dim = f"{nx} {ny} {nz}"
-            nd = 3
-            slabs = list(arr)
-        out.append(f'  <lattice id="{LATTICE_ID_BASE + l.id}">')
-        out.append(f"    <pitch>{_fmt(l.pitch[:nd])}</pitch>")
-        out.append(f"    <dimension>{dim}</dimension>")
-        out.append(f"    <lower_left>{_fmt(l.lower_left[:nd])}</lower_left>")
-        if l.outer is not None:
-            out.append(f"    <outer>{l.outer}</outer>")
-        rows = []
-        for slab in slabs:
-            rows += [" ".join(str(int(u)) for u in row) for row in slab]
-        out.append("    <universes>\n" + "\n".join(rows) + "\n    </universes>")
-        out.append("  </lattice>")
-    out.append("</geometry>")
-    return "\n".join(out)
+from oracle.refrun import LATTICE_ID_BASE, geometry_xml  # noqa: E402,F401  (the emitter lives with the other XML writers)
 
 
 class ReferenceGeometry:
