@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--n-fuel-nuclides", type=int, default=300, help="pwr_core_ce: nuclides in the fuel")
     ap.add_argument("--cpu-sample", type=int, default=160_000, help="histories of the cpu_baseline sample (~25 s of CPU work)")
     ap.add_argument("--ref-particles", type=int, default=0,
-                    help="histories per batch of the reference binary's runs (default 2500 per host thread)")
+                    help="histories per batch of the reference binary's runs (default 10000 per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true",
@@ -485,7 +485,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         if reference_binary_available():
-            cpu = reference_binary_baseline(args, args.ref_particles or 2500 * cores, 2, 1, cores)
+            cpu = reference_binary_baseline(args, args.ref_particles or 10000 * cores, 2, 1, cores)
         else:
             cpu = cpu_baseline(args, r["src"], args.cpu_sample, cores)
 
@@ -634,7 +634,7 @@ def reference_arm(args, rank, world):
     cores = os.cpu_count() or 1
     _, _, _, workload = build_workload_description(args)
     if reference_binary_available():
-        n = args.ref_particles or 2500 * cores
+        n = args.ref_particles or 10000 * cores
         cpu = reference_binary_baseline(args, n, args.steps, args.warmup, cores)
         v = cpu["value"]
     else:
