@@ -489,6 +489,13 @@ def main():
         else:
             cpu = cpu_baseline(args, r["src"], args.cpu_sample, cores)
 
+    dropin = None
+    if rank == 0 and world == 1 and not args.no_e2e and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "openmc_gpu")):
+        try:
+            dropin = dropin_rate(args, args.particles, 3, 2, os.cpu_count() or 1)
+        except Exception as exc:
+            dropin = {"error": repr(exc)[:300]}
+
     if rank == 0:
         line = {
             "metric": "particles/sec (active)", "value": r["value"], "unit": "particles/s",
@@ -507,7 +514,7 @@ def main():
             "events_per_particle": r["events_per_particle"],
             "k_combined": r["k_combined"], "n_lost": r["n_lost"],
             "gpu_launches": r["gpu_launches"], "clocks": r["clocks"], "e2e": r["e2e"], "roofline": r["roofline"],
-            "cpu_baseline": cpu, "other_configs": others or None,
+            "cpu_baseline": cpu, "other_configs": others or None, "dropin": dropin,
         }
         print(json.dumps(line))
 
@@ -577,7 +584,25 @@ def reference_binary_available():
     return refrun.available()
 
 
-def reference_binary_baseline(args, n_per_batch, active, inactive, threads, modes=("history", "event")):
+def dropin_rate(args, n_per_batch, active, inactive, threads):
+    """the user-visible drop-in: the reference's own binary with the three hooks compiled in
+    (oracle/_ref/openmc_gpu = unmodified libopenmc sources + openmc_b200/host), OPENMC_GPU=1, in a
+    directory with model.xml + the data library; the rate is the line its own output prints.  Host
+    side per generation as in libopenmc: sort_fission_bank, synchronize_bank (serial comb),
+    k statistics, tally accumulation."""
+    r = reference_binary_baseline(args, n_per_batch, active, inactive, threads, modes=("history",),
+                                  binary="openmc_gpu", env={"OPENMC_GPU": "1", "OMCGPU_LIB": os.path.join(
+                                      ROOT, "openmc_b200", "csrc", "libomcgpu.so")})
+    h = r["history"]
+    return {"value": h["particles_per_s"], "unit": "particles/s", "inactive_particles_per_s": h["inactive_particles_per_s"],
+            "active_s": h["active_s"], "wall_s": h["wall_s"], "particles_per_generation": n_per_batch,
+            "batches": [inactive, active],
+            "what": "OPENMC_GPU=1 oracle/_ref/openmc_gpu (the reference's binary + hooks) on model.xml: its own "
+                    "'Calculation Rate (active)'; host side (bank sort / comb, statistics, statepoint) is libopenmc's"}
+
+
+def reference_binary_baseline(args, n_per_batch, active, inactive, threads, modes=("history", "event"),
+                              binary="openmc", env=None):
     """time the UNMODIFIED reference (oracle/_ref/openmc: every translation unit of libopenmc compiled
     from /root/reference with OpenMP, against oracle/h5shim) on the workload: XML inputs + the synthetic
     library written by oracle/refrun.py, `inactive` + `active` batches of n_per_batch histories, all
@@ -609,7 +634,17 @@ def reference_binary_baseline(args, n_per_batch, active, inactive, threads, mode
         res = {}
         for mode in modes:
             t0 = time.perf_counter()
-            r = refrun.run(d, threads=threads, event=(mode == "event"))
+            saved = {k: os.environ.get(k) for k in (env or {})}
+            os.environ.update(env or {})
+            try:
+                r = refrun.run(d, threads=threads, event=(mode == "event"),
+                               binary=os.path.join(ROOT, "oracle", "_ref", binary))
+            finally:
+                for k, v in saved.items():
+                    if v is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v
             if r["returncode"] != 0:
                 raise RuntimeError("reference run failed: " + (r["stdout"][-400:] + r["stderr"][-400:]))
             res[mode] = {"particles_per_s": r["rates"]["active"], "inactive_particles_per_s": r["rates"].get("inactive"),

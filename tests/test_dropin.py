@@ -1,0 +1,229 @@
+"""The drop-in itself: the reference's OWN library and binary -- XML input, data
+loading, source sampling, synchronize_bank, k statistics, tally accumulation, statepoint
+writing, all unmodified -- with the three hook edits of openmc_b200/host/apply_hooks.py and the
+host side of the B200 path (openmc_b200/host/omcgpu_host.cpp) compiled in
+(oracle/_ref/libopenmc_gpu.so, oracle/_ref/openmc_gpu; recipe oracle/Makefile).
+
+* the C++ flattener (model:: / data:: -> omcgpu_model) gives, field by field, the arrays this
+  repo's Python flattener derives from the same description;
+* `OPENMC_GPU=1 openmc_gpu` writes the statepoint `openmc` writes: here, on the CPU tier, the
+  device library is the TEST-ONLY host compile of the engine sources (tests/_emu, the same
+  event loop and device functions with glibc's libm), so k of every generation and the source
+  bank are bit-identical and tallies agree to summation order;
+* with OPENMC_GPU unset the patched binary is the reference;
+* a model the device path refuses ends in the reference's fatal_error, not in a CPU fallback.
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import cases
+import reference_runs as rr
+from openmc_b200 import _abi as abi
+from openmc_b200 import mgxs, nuclide
+from oracle import refrun
+from oracle.binding import build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GPU_BINARY = os.path.join(ROOT, "oracle", "_ref", "openmc_gpu")
+GPU_LIB = os.path.join(ROOT, "oracle", "_ref", "libopenmc_gpu.so")
+
+
+@pytest.fixture(scope="module")
+def dropin(emu_lib):
+    if os.path.isdir("/root/reference/src"):
+        build()
+    if not os.path.exists(GPU_BINARY):
+        pytest.skip("oracle/_ref/openmc_gpu not built (no /root/reference on this box)")
+    return emu_lib
+
+
+def _inputs(name):
+    m, lib, model, box, of, ce = rr.build(name)
+    particles, batches, inactive = rr.RUNS[name]
+    d = tempfile.mkdtemp(prefix="omc_dropin_")
+    rr.write_inputs(d, m, lib, box, of, ce, particles, batches, inactive)
+    return d
+
+
+def _run(d, engine_lib, gpu=True, threads=1):
+    env = dict(os.environ)
+    env.pop("OPENMC_GPU", None)
+    if gpu:
+        env["OPENMC_GPU"] = "1"
+        env["OMCGPU_LIB"] = engine_lib
+    for f in os.listdir(d):
+        if f.startswith("statepoint"):
+            os.remove(os.path.join(d, f))
+    res = subprocess.run([GPU_BINARY, "-s", str(threads)], cwd=d, capture_output=True, text=True, env=env, timeout=1200)
+    return res
+
+
+@pytest.mark.parametrize("name", list(rr.RUNS))
+def test_dropin_binary_equals_the_reference_binary(dropin, name):
+    d = _inputs(name)
+    try:
+        res = _run(d, dropin)
+        assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+        sp = [f for f in os.listdir(d) if f.startswith("statepoint")]
+        from oracle import omh5
+        got = rr.digest({"statepoint": omh5.File(os.path.join(d, sorted(sp)[-1]))})
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    ref = dict(np.load(rr.GOLDEN % name))     # what the unmodified binary writes (checked current elsewhere)
+    assert np.array_equal(got["k_generation"], ref["k_generation"])
+    assert np.array_equal(got["k_combined"], ref["k_combined"])
+    assert np.array_equal(got["global_tallies"], ref["global_tallies"])
+    for k in ("bank_r", "bank_u", "bank_E", "bank_wgt", "bank_delayed_group"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert got["tally_sum"].size == ref["tally_sum"].size
+    if ref["tally_sum"].size:
+        np.testing.assert_allclose(got["tally_sum"], ref["tally_sum"], rtol=1e-11, atol=1e-14 * ref["tally_sum"].max())
+        np.testing.assert_allclose(got["tally_sum_sq"], ref["tally_sum_sq"], rtol=1e-11,
+                                   atol=1e-14 * ref["tally_sum_sq"].max())
+
+
+def test_switch_off_is_the_reference(dropin):
+    d = _inputs("pincell_mg")
+    try:
+        res = _run(d, dropin, gpu=False)
+        assert res.returncode == 0, res.stderr[-1500:]
+        from oracle import omh5
+        sp = sorted(f for f in os.listdir(d) if f.startswith("statepoint"))[-1]
+        got = rr.digest({"statepoint": omh5.File(os.path.join(d, sp))})
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    ref = dict(np.load(rr.GOLDEN % "pincell_mg"))
+    for k in ref:
+        assert np.array_equal(got[k], ref[k]), k
+
+
+def test_refused_model_is_a_fatal_error(dropin):
+    """a white boundary condition: the device path refuses it, the run ends with the reference's
+    ' ERROR: ' convention (src/error.cpp:113-140) instead of silently using the CPU"""
+    m, lib, model, box, of, ce = rr.build("pincell_mg")
+    import copy
+    m2 = copy.deepcopy(m)
+    next(s for s in m2.surfaces if s.boundary == "reflective").boundary = "white"
+    d = tempfile.mkdtemp(prefix="omc_dropin_")
+    try:
+        rr.write_inputs(d, m2, lib, box, of, ce, 200, 3, 1)
+        res = _run(d, dropin)
+        assert res.returncode != 0
+        assert "ERROR" in res.stderr and "not supported by the device path" in res.stderr.replace("\n", " ").replace("  ", " ")
+        assert _run(d, dropin, gpu=False).returncode == 0      # the reference itself runs the model
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# C++ flattener == Python flattener, field by field
+# ---------------------------------------------------------------------------------------------
+def _region_truth(tokens, senses):
+    """evaluate an infix region expression (surface tokens +-(index+1), OMCGPU_OP_*) for one
+    assignment of surface senses"""
+    LP, RP, CO, IN, UN = (abi.OMCGPU_OP_LEFT_PAREN, abi.OMCGPU_OP_RIGHT_PAREN, abi.OMCGPU_OP_COMPLEMENT,
+                          abi.OMCGPU_OP_INTERSECTION, abi.OMCGPU_OP_UNION)
+    pos = 0
+
+    def primary():
+        nonlocal pos
+        t = int(tokens[pos]); pos += 1
+        if t == CO:
+            return not primary()
+        if t == LP:
+            v = union()
+            pos += 1
+            return v
+        return senses[abs(t) - 1] == (t > 0)
+
+    def inter():
+        nonlocal pos
+        v = primary()
+        while pos < len(tokens) and (tokens[pos] == IN or tokens[pos] not in (RP, UN)):
+            if tokens[pos] == IN:
+                pos += 1
+            v = primary() and v
+        return v
+
+    def union():
+        nonlocal pos
+        v = inter()
+        while pos < len(tokens) and tokens[pos] == UN:
+            pos += 1
+            v = inter() or v
+        return v
+    return union() if len(tokens) else True
+
+
+def _regions_equivalent(tok_a, ofs_a, tok_b, ofs_b, n_surfaces, seed=5):
+    """the reference keeps the user's parentheses (and those of a complement), this repo's Python
+    tokenizer normalises them away: the cells must be the same Boolean functions of the senses"""
+    g = np.random.default_rng(seed)
+    for c in range(len(ofs_a) - 1):
+        a, b = tok_a[ofs_a[c]:ofs_a[c + 1]], tok_b[ofs_b[c]:ofs_b[c + 1]]
+        if np.array_equal(a, b):
+            continue
+        for _ in range(512):
+            senses = g.integers(0, 2, n_surfaces).astype(bool)
+            if _region_truth(list(a), senses) != _region_truth(list(b), senses):
+                return False
+    return True
+
+
+SKIP = {"hash_edge", "tok_cell_ofs", "tok_cells", "fine_window", "n_fine_bins", "fine_inv_spacing", "reserved_ce",
+        "n_collision_tallies"}       # derived by omcgpu_init, ignored on input
+
+
+@pytest.mark.parametrize("name", list(rr.RUNS))
+def test_cpp_flattener_equals_python_flattener(dropin, name):
+    m, lib, model, box, of, ce = rr.build(name)
+    import copy
+    m2 = copy.deepcopy(m)
+    m2.settings["material_cell_offsets"] = True      # the reference's default (src/settings.cpp)
+    py = nuclide.build_ce_model(m2, lib) if ce else mgxs.build_mg_model(m2, lib)
+    d = _inputs(name)
+    try:
+        out = os.path.join(d, "flat.npz")
+        res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "flatten_worker.py"), GPU_LIB, out],
+                             cwd=d, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout[-800:] + res.stderr[-1500:]
+        cpp = dict(np.load(out))
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    assert "__error__" not in cpp, cpp.get("__error__")
+    checked = 0
+    for fname, (dt, is_ptr) in abi.model_field_types().items():
+        if fname in SKIP:
+            continue
+        if not ce and (fname.startswith(("nuc_", "rx_", "prod_", "fn_")) or fname in (
+                "n_nuclides", "n_log_bins", "log_spacing", "n_reactions", "n_products", "n_functions")):
+            continue
+        if ce and fname.startswith(("mg", "sc_", "blk_")):
+            continue
+        if not is_ptr:
+            a, b = cpp[fname].item(), py[fname]
+            assert a == b or (isinstance(b, float) and abs(a - b) <= 1e-15 * abs(b)), (fname, a, b)
+        else:
+            a, b = cpp[fname], py.arrays[fname]
+            if fname in ("region_tokens", "cell_region_ofs"):
+                assert _regions_equivalent(cpp["region_tokens"], cpp["cell_region_ofs"], py.arrays["region_tokens"],
+                                           py.arrays["cell_region_ofs"], int(cpp["n_surfaces"]))
+                checked += 1
+                continue
+            # the Python side pads empty arrays with one zero
+            if a.size == 0:
+                assert b.size <= 1, fname
+                continue
+            assert a.size == b.size, (fname, a.size, b.size)
+            if dt == np.float64:
+                np.testing.assert_allclose(a, b, rtol=1e-15, atol=0, err_msg=fname)
+            else:
+                assert np.array_equal(a, b), fname
+        checked += 1
+    assert checked > 60
