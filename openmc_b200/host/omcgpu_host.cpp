@@ -8,9 +8,11 @@
 //                            /root/reference/src/simulation.cpp:99-105
 //   transport_generation()   one generation on the device in place of transport_event_based()
 //                            / transport_history_based(), src/simulation.cpp:255-259; leaves the
-//                            host exactly what event_death() (src/particle.cpp:475-512) and the
-//                            tally scoring leave: global_tally_*, progeny_per_particle, the
-//                            fission bank, results_(:,:,VALUE), n_lost_particles
+//                            host what event_death() (src/particle.cpp:475-512), the tally scoring
+//                            and sort_fission_bank() + synchronize_bank() leave: global_tally_*,
+//                            results_(:,:,VALUE), n_lost_particles, the NEXT simulation::source_bank
+//   bank_synchronized()      tells finalize_generation() (src/simulation.cpp:546-552) that the bank
+//                            sort and the comb were done on the device
 //   simulation_finalize()    omcgpu_finalize, next to free_event_queues(), src/finalize.cpp:57-59
 //
 // The device library is loaded with dlopen (OMCGPU_LIB, default libomcgpu.so next to this
@@ -874,7 +876,7 @@ struct Api {
   int (*init)(const omcgpu_model*, int, int64_t) = nullptr;
   int (*finalize)() = nullptr;
   const char* (*last_error)() = nullptr;
-  int (*transport_generation)(const omcgpu_gen_in*, const omcgpu_site*, omcgpu_site*, int64_t, omcgpu_gen_out*) = nullptr;
+  int (*next_generation)(const omcgpu_gen_in*, omcgpu_site*, int64_t, omcgpu_gen_out*) = nullptr;
   int (*tally_results)(int32_t, double*, int64_t) = nullptr;
   int (*host_register)(void*, int64_t) = nullptr;
   int (*host_unregister)(void*) = nullptr;
@@ -912,7 +914,7 @@ void load_library()
   bind(api.init, "omcgpu_init");
   bind(api.finalize, "omcgpu_finalize");
   bind(api.last_error, "omcgpu_last_error");
-  bind(api.transport_generation, "omcgpu_transport_generation");
+  bind(api.next_generation, "omcgpu_next_generation");
   bind(api.tally_results, "omcgpu_tally_results");
   bind(api.host_register, "omcgpu_host_register");
   bind(api.host_unregister, "omcgpu_host_unregister");
@@ -951,7 +953,6 @@ void simulation_init()
   // the banks were allocated by allocate_banks() just above the hook: page-lock them so that the
   // per-generation copies are DMA transfers straight from / into them
   api.host_register(simulation::source_bank.data(), simulation::source_bank.size() * sizeof(SourceSite));
-  api.host_register(simulation::fission_bank.data(), simulation::fission_bank.capacity() * sizeof(SourceSite));
   g_ready = true;
 }
 
@@ -970,10 +971,12 @@ void transport_generation()
   in.tallies_active = model::active_tallies.empty() ? 0 : 1;
   in.source_bank_clean = 0; // the host bank is authoritative (ownership)
   omcgpu_gen_out out {};
-  const int64_t cap = simulation::fission_bank.capacity();
-  check(api.transport_generation(&in, reinterpret_cast<const omcgpu_site*>(simulation::source_bank.data()),
-          reinterpret_cast<omcgpu_site*>(simulation::fission_bank.data()), cap, &out),
-    "omcgpu_transport_generation");
+  // event loop, fission-bank sort (src/bank.cpp:76-134) and the sampling half of synchronize_bank
+  // (src/eigenvalue.cpp:152-178, same seed: total_gen + overall_generation()) on the device; the NEXT
+  // source bank comes back into simulation::source_bank
+  check(api.next_generation(&in, reinterpret_cast<omcgpu_site*>(simulation::source_bank.data()),
+          simulation::total_gen + overall_generation(), &out),
+    "omcgpu_next_generation");
 
   // what event_death() leaves (src/particle.cpp:475-512)
   global_tally_collision += out.global_tally[OMCGPU_K_COLLISION];
@@ -984,10 +987,8 @@ void transport_generation()
   simulation::n_lost_particles += out.n_lost;
   if (out.n_bank_full > 0)
     warning("The shared fission bank is full. Additional fission sites created in this generation will not be banked.");
-  simulation::fission_bank.resize(out.n_fission);
-  std::fill(simulation::progeny_per_particle.begin(), simulation::progeny_per_particle.end(), 0);
-  for (int64_t k = 0; k < out.n_fission; ++k) // the bank arrives sorted: sort_fission_bank() keeps it as it is
-    ++simulation::progeny_per_particle[simulation::fission_bank[k].parent_id - 1 - in.id_offset];
+  if (out.n_fission == 0)
+    fatal_error("No fission sites banked on MPI rank " + std::to_string(mpi::rank)); // src/eigenvalue.cpp:121-124
 
   // tally VALUE arrays -> results_(:, :, VALUE), the hand-off before Tally::accumulate
   if (in.tallies_active) {
@@ -1005,12 +1006,16 @@ void transport_generation()
   }
 }
 
+bool bank_synchronized()
+{
+  return enabled() && g_ready;
+}
+
 void simulation_finalize()
 {
   if (!g_ready)
     return;
   api.host_unregister(simulation::source_bank.data());
-  api.host_unregister(simulation::fission_bank.data());
   api.finalize();
   g_ready = false;
   g_flat.reset();

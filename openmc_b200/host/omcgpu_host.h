@@ -1,6 +1,6 @@
 // omcgpu_host.h -- libopenmc-side hooks of the B200 transport path (see omcgpu_host.cpp).
 //
-// Three call sites of libopenmc change (apply_hooks.py makes exactly these edits; INTEGRATION.md
+// Four call sites of libopenmc change (apply_hooks.py makes exactly these edits; INTEGRATION.md
 // shows them as a diff):
 //
 //   src/simulation.cpp:99-105   openmc_simulation_init():  `if (settings::event_based) init_event_queues(...)`
@@ -8,6 +8,8 @@
 //   src/simulation.cpp:255-259  openmc_next_batch():        `if (settings::event_based) transport_event_based();
 //                               else transport_history_based();`
 //                               -> `if (gpu::enabled()) gpu::transport_generation(); else if (...)`
+//   src/simulation.cpp:546-552  finalize_generation():      `sort_fission_bank(); synchronize_bank();`
+//                               -> `if (!gpu::bank_synchronized()) { ... }` (the device sorted and combed the bank)
 //   src/finalize.cpp:57-59      free_memory():              `gpu::simulation_finalize();` next to free_event_queues()
 //
 // Everything else of libopenmc -- XML input, data loading, source sampling, synchronize_bank, k statistics,
@@ -27,6 +29,8 @@ bool enabled();
 const omcgpu_model* flatten_model();
 void simulation_init();
 void transport_generation();
+//! true: sort_fission_bank() / synchronize_bank() of this generation were done on the device
+bool bank_synchronized();
 void simulation_finalize();
 
 } // namespace gpu
