@@ -230,7 +230,16 @@ typedef struct omcgpu_model {
   const double* mat_atom_density; /* atom/b-cm                                         */
 
   /* ---- continuous-energy nuclides: data::nuclides (src/nuclide.cpp) ------- */
-  int32_t n_nuclides;
+  /* A "table" is one nuclide at one loaded temperature (Nuclide::kTs_[t], grid_[t], xs_[t],
+   * Reaction::xs_[t]); every nuc_* / rx_* array below has one entry per TABLE.  With one
+   * temperature per nuclide (n_nuclide_temps == 0) tables and nuclides coincide and
+   * mat_nuclide holds table indices.  Otherwise mat_nuclide holds nuclide indices d and the
+   * tables of nuclide d are nuct_ofs[d] .. nuct_ofs[d+1]-1 in ascending kT; a lookup takes
+   * the one nearest to the cell's kT (TemperatureMethod::NEAREST, src/nuclide.cpp:682-691;
+   * stochastic interpolation is refused). */
+  int32_t n_nuclide_temps;        /* 0, or the number of distinct nuclides               */
+  const int32_t* nuct_ofs;        /* [n_nuclide_temps+1] into the tables                  */
+  int32_t n_nuclides;             /* number of tables                                    */
   int32_t n_log_bins;             /* settings::n_log_bins (8000)                       */
   double log_spacing;             /* simulation::log_spacing                           */
   const double* hash_edge;        /* [n_log_bins+2] smallest E whose host-libm hash bin is k */
@@ -242,7 +251,7 @@ typedef struct omcgpu_model {
   double fine_inv_spacing;        /* n_fine_bins / log(energy_max / energy_min)       */
   const int32_t* fine_window;     /* [n_fine_bins][n_nuclides][2]                      */
   const double* nuc_awr;          /* [n_nuclides]                                      */
-  const double* nuc_kT;           /* [n_nuclides] kT of the single loaded temperature  */
+  const double* nuc_kT;           /* [n_nuclides] kT of the table                      */
   const int32_t* nuc_fissionable; /* [n_nuclides]                                      */
   const int64_t* nuc_grid_ofs;    /* [n_nuclides+1] into nuc_energy / nuc_xs           */
   const double* nuc_energy;       /* concatenated energy grids                         */
@@ -412,7 +421,9 @@ int omcgpu_finalize(void);
  *   "count_lookups"  1: fill omcgpu_gen_out.n_lookups_done / n_nuclide_lookups (costs atomics)
  *   "tail_threshold" histories alive below which the generation is finished by the tail kernel
  *   "sync_every"     sweeps the host lets run between two counter read-backs
- *   "score_part"     mesh cells per part of a flight in the scoring kernel */
+ *   "score_part"     mesh cells per part of a flight in the scoring kernel
+ *   "probe_kT_neV"   cell temperature (kT in 1e-9 eV) the stand-alone lookup / collision probes use to
+ *                    pick a nuclide's temperature table */
 int omcgpu_set_option(const char* name, int64_t value);
 
 /* How omcgpu_init arranged the event loop for this model: 2 = paired lists, crossing / collision

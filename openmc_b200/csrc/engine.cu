@@ -333,7 +333,8 @@ OMC_D void ev_xs(const PState& ps, int64_t i, int batch_min = OMC_XS_BATCH_MIN, 
   if (DM.run_CE) {
     if (m != ps.material_last[i] || ps.sqrtkT[i] != ps.sqrtkT_last[i]) {
       double t, a, f, nf;
-      ce_macro_xs<BX>(m, ps.E[i], t, a, f, nf, nullptr, 0, batch_min,
+      const double sq = ps.sqrtkT[i];
+      ce_macro_xs<BX>(m, ps.E[i], sq * sq, t, a, f, nf, nullptr, 0, batch_min,
         ps.n_prefix ? ps.xs_prefix + (ps.id_shift + i) * ps.n_prefix : nullptr);
       if (count)
         count_lookup(count, ld(DM.mat_nuc_ofs + m + 1) - ld(DM.mat_nuc_ofs + m));
@@ -666,6 +667,10 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
   p.xs_absorption = ps.xs_absorption[i];
   p.xs_nu_fission = ps.xs_nu_fission[i];
   p.k_abs = ps.k_abs[i];
+  {
+    const double sq = ps.sqrtkT[i];
+    p.kT = sq * sq;
+  }
   ps.k_col[i] += p.wgt * p.xs_nu_fission / p.xs_total;
   ps.surface[i] = SURFACE_NONE;
   if (DM.run_CE) {
@@ -1503,6 +1508,7 @@ struct XsArgs {
   int32_t* i_grid;
   int32_t max_nuc;
   int32_t xs_batch_min;
+  double kT; // temperature of the probe lookups (omcgpu_set_probe_temperature)
 };
 template<bool BX>
 OMC_D void body_probe_xs(int64_t tid, const XsArgs& a)
@@ -1512,7 +1518,7 @@ OMC_D void body_probe_xs(int64_t tid, const XsArgs& a)
   const int m = a.material[tid];
   double t = 0, ab = 0, f = 0, nf = 0;
   if (DM.run_CE) {
-    ce_macro_xs<BX>(m, a.E[tid], t, ab, f, nf, a.i_grid ? a.i_grid + tid * a.max_nuc : nullptr,
+    ce_macro_xs<BX>(m, a.E[tid], a.kT, t, ab, f, nf, a.i_grid ? a.i_grid + tid * a.max_nuc : nullptr,
       a.max_nuc, a.xs_batch_min);
   } else {
     const int G = DM.mg_n_groups;
@@ -1548,6 +1554,7 @@ struct CollideArgs {
   const double* uvw;
   const uint64_t* seed;
   double wgt;
+  double kT;
   double* E_out;
   double* uvw_out;
   double* wgt_out;
@@ -1572,7 +1579,8 @@ OMC_D void body_probe_collide(int64_t tid, const CollideArgs& a)
   p.id = tid + 1;
   if (DM.run_CE) {
     double t, ab, f, nf;
-    ce_macro_xs<false>(p.material, p.E, t, ab, f, nf, nullptr, 0);
+    p.kT = a.kT;
+    ce_macro_xs<false>(p.material, p.E, p.kT, t, ab, f, nf, nullptr, 0);
     p.xs_total = t;
     p.xs_absorption = ab;
     p.xs_nu_fission = nf;
@@ -1767,6 +1775,7 @@ struct Engine {
   int n_sm = 148;
   int64_t sync_every = 8;       // sweeps the host lets run between two counter read-backs
   int64_t tail_threshold = 16384;
+  double probe_kT = 0.0;
   int score_part = 16;          // measured: 4 / 8 / 16 -> 138.9 / 131.9 / 131.3 ms (profiles/r11_matrix.log)
   int64_t id_offset_last = 0;
   FILE* trace = nullptr;        // OMCGPU_TRACE=<file>: one line per sweep {generation, sweep, collisions, crossings}
@@ -1965,6 +1974,7 @@ static int upload_model(const omcgpu_model* m)
     edge[h.n_log_bins + 1] = INFINITY;
     h.hash_edge = edge.data();
     UP(hash_edge, h.n_log_bins + 2);
+    UP(nuct_ofs, h.n_nuclide_temps ? h.n_nuclide_temps + 1 : 0);
     UP(nuc_awr, nn);
     UP(nuc_kT, nn);
     UP(nuc_fissionable, nn);
@@ -2948,6 +2958,8 @@ int omcgpu_set_option(const char* name, int64_t value)
     G.sync_every = std::min<int64_t>(std::max<int64_t>(1, value), RING / 2);
   else if (k == "score_part")
     G.score_part = (int)std::max<int64_t>(1, value);
+  else if (k == "probe_kT_neV") // cell temperature of the stand-alone lookup / collision probes, in 1e-9 eV
+    G.probe_kT = 1e-9 * (double)value;
   else
     return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_set_option: unknown option %s", name);
   return 0;
@@ -3690,7 +3702,7 @@ int omcgpu_calculate_xs(const double* E, const int32_t* material, int64_t n, dou
   CUDA_OK(cudaMemcpy(dE, E, n * sizeof(double), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(dm, material, n * sizeof(int32_t), cudaMemcpyHostToDevice));
   XsArgs a;
-  a.E = dE; a.material = dm; a.n = n; a.out = dout; a.i_grid = dig; a.max_nuc = max_nuc;
+  a.E = dE; a.material = dm; a.n = n; a.out = dout; a.i_grid = dig; a.max_nuc = max_nuc; a.kT = G.probe_kT;
   LAUNCH_XS(k_probe_xs, n, G.stream, a);
   CUDA_OK(cudaStreamSynchronize(G.stream));
   CUDA_OK(cudaMemcpy(out, dout, n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
@@ -3711,7 +3723,7 @@ int omcgpu_calculate_xs_device(const double* E, const int32_t* material, int64_t
   if (!G.ready)
     return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
   XsArgs a;
-  a.E = E; a.material = material; a.n = n; a.out = out; a.i_grid = nullptr; a.max_nuc = 0;
+  a.E = E; a.material = material; a.n = n; a.out = out; a.i_grid = nullptr; a.max_nuc = 0; a.kT = G.probe_kT;
   CUDA_OK(cudaEventRecord(G.evp0, G.stream));
   LAUNCH_XS(k_probe_xs, n, G.stream, a);
   CUDA_OK(cudaEventRecord(G.evp1, G.stream));
@@ -3758,6 +3770,7 @@ int omcgpu_collide(int64_t n, const int32_t* material, const double* E, const do
   a.fb = G.fis;
   a.n = n;
   a.wgt = wgt;
+  a.kT = G.probe_kT;
   a.material = (const int32_t*)dalloc(n * 4, material);
   a.E = (const double*)dalloc(n * 8, E);
   a.uvw = (const double*)dalloc(n * 24, uvw);

@@ -296,11 +296,13 @@ def pincell_multigroup(mesh_dim=100, energy_bins=500):
 # ----------------------------------------------------------------------------
 # Config C2: UO2 pincell, continuous energy, synthetic library
 # ----------------------------------------------------------------------------
-def pincell_ce(n_grid=100000, mesh_dim=100, energy_bins=500, tallies=True, library=None):
+def pincell_ce(n_grid=100000, mesh_dim=100, energy_bins=500, tallies=True, library=None, temperatures=None):
     """examples/pincell/build_xml.py:11-120 geometry/settings (fuel, gap, clad,
     borated water in a reflective 1.25984 cm box; 100x100 mesh {flux, fission,
     nu-fission} + 500-bin flux spectrum) with the 10-nuclide synthetic library of
-    openmc_b200.nuclide (no S(a,b), one temperature)."""
+    openmc_b200.nuclide (no S(a,b)).  `temperatures` = (library temperatures [K], cell temperatures
+    [K] of fuel, gap, clad, water): a library with several tables per nuclide and cells that pick
+    among them (nearest temperature, the reference's default method)."""
     from . import nuclide as nd
     m = Model()
     uo2 = m.material(name="UO2 fuel at 2.4% wt enrichment", units="g/cm3", density=10.29769,
@@ -322,17 +324,19 @@ def pincell_ce(n_grid=100000, mesh_dim=100, energy_bins=500, tallies=True, libra
     x1 = m.surface("x-plane", [pitch / 2], "reflective").id
     y0 = m.surface("y-plane", [-pitch / 2], "reflective").id
     y1 = m.surface("y-plane", [pitch / 2], "reflective").id
-    m.cell(region=f"-{s_fo}", fill=uo2)
-    m.cell(region=f"{s_fo} -{s_ci}", fill=helium)
-    m.cell(region=f"{s_ci} -{s_co}", fill=zirc)
-    m.cell(region=f"{s_co} {x0} -{x1} {y0} -{y1}", fill=water)
+    cT = temperatures[1] if temperatures else (None, None, None, None)
+    m.cell(region=f"-{s_fo}", fill=uo2, temperature=cT[0])
+    m.cell(region=f"{s_fo} -{s_ci}", fill=helium, temperature=cT[1])
+    m.cell(region=f"{s_ci} -{s_co}", fill=zirc, temperature=cT[2])
+    m.cell(region=f"{s_co} {x0} -{x1} {y0} -{y1}", fill=water, temperature=cT[3])
     if tallies:
         m.meshes = [Mesh(1, [mesh_dim, mesh_dim], [-pitch / 2, -pitch / 2], [pitch / 2, pitch / 2])]
         edges = np.logspace(np.log10(1e-5), np.log10(20.0e6), energy_bins + 1)
         m.filters = [Filter(1, "mesh", 1), Filter(2, "energy", list(edges))]
         m.tallies = [Tally(1, [1], ["flux", "fission", "nu-fission"]), Tally(2, [2], ["flux"])]
     if library is None:
-        library = nd.synthetic_library(nd.PINCELL_NUCLIDES, n_grid)
+        library = nd.synthetic_library(nd.PINCELL_NUCLIDES, n_grid,
+                                       temperatures=temperatures[0] if temperatures else None)
     box = [-pitch / 2, -pitch / 2, -1, pitch / 2, pitch / 2, 1]
     return m, library, box, True
 

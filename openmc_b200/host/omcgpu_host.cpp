@@ -436,104 +436,117 @@ void flatten_nuclides(Flat& F)
 {
   auto& m = F.m;
   const int nn = data::nuclides.size();
-  m.n_nuclides = nn;
   m.n_log_bins = settings::n_log_bins;
   m.log_spacing = simulation::log_spacing;
   m.energy_min = data::energy_min[0];
   m.energy_max = data::energy_max[0];
   if (settings::temperature_multipole || settings::res_scat_on)
     unsupported("windowed multipole / resonance scattering");
-  DV awr(nn), kT(nn), energy, xs, rx_xs, rx_q, p_decay, p_par;
-  IV fissionable(nn), gidx, rx_ofs {0}, fis_rx(nn, -1), n_prec(nn), tot_nu(nn, -1), rx_mt, rx_cm, rx_inel, rx_thr, rx_pofs {0},
-    p_em, p_yield, p_law, p_fn;
+  // A TABLE is one nuclide at one loaded temperature (kTs_[t], grid_[t], xs_[t], Reaction::xs_[t]);
+  // every nuc_* / rx_* array has one entry per table, nuclide-major, ascending kT
+  bool multi = false;
+  for (int i = 0; i < nn; ++i)
+    multi = multi || data::nuclides[i]->kTs_.size() != 1;
+  if (multi && settings::temperature_method != TemperatureMethod::NEAREST)
+    unsupported("temperature interpolation between the tables of a nuclide (only the nearest-temperature method)");
+  DV awr, kT, energy, xs, rx_xs, rx_q, p_decay, p_par;
+  IV tab_ofs {0}, fissionable, gidx, rx_ofs {0}, fis_rx, n_prec, tot_nu, rx_mt, rx_cm, rx_inel, rx_thr, rx_pofs {0}, p_em,
+    p_yield, p_law, p_fn;
   LV gofs {0}, rx_xofs {0};
   Functions fn;
   for (int i = 0; i < nn; ++i) {
     const Nuclide& nuc = *data::nuclides[i];
-    if (nuc.kTs_.size() != 1)
-      unsupported(fmt::format("nuclide {} at more than one temperature", nuc.name_));
     if (nuc.urr_present_ && settings::urr_ptables_on)
       unsupported(fmt::format("the unresolved-resonance probability tables of {}", nuc.name_));
     if (nuc.multipole_)
       unsupported("windowed multipole data");
-    awr[i] = nuc.awr_;
-    kT[i] = nuc.kTs_[0];
-    fissionable[i] = nuc.fissionable_ ? 1 : 0;
-    const auto& grid = nuc.grid_[0];
-    const auto& tab = nuc.xs_[0];
-    const size_t n = grid.energy.size();
-    energy.insert(energy.end(), grid.energy.begin(), grid.energy.end());
-    for (size_t k = 0; k < n; ++k)
-      for (int x = 0; x < 4; ++x) // total, absorption, fission, nu-fission (photon production dropped)
-        xs.push_back(tab(k, x));
-    gidx.insert(gidx.end(), grid.grid_index.begin(), grid.grid_index.end());
-    if ((int)grid.grid_index.size() != settings::n_log_bins + 1)
-      unsupported("a log-hash table whose size is not n_log_bins + 1");
-    gofs.push_back(energy.size());
-    n_prec[i] = nuc.n_precursor_;
-    tot_nu[i] = fn.add(nuc.total_nu_.get());
-    const int r0 = rx_mt.size();
-    for (size_t r = 0; r < nuc.reactions_.size(); ++r) {
-      const Reaction& rx = *nuc.reactions_[r];
-      if (rx.redundant_)
-        unsupported(fmt::format("the redundant reaction MT {} of {}", rx.mt_, nuc.name_));
-      if (!nuc.fission_rx_.empty() && nuc.fission_rx_[0] == &rx)
-        fis_rx[i] = r;
-      rx_mt.push_back(rx.mt_);
-      rx_cm.push_back(rx.scatter_in_cm_ ? 1 : 0);
-      rx_inel.push_back(std::find(nuc.index_inelastic_scatter_.begin(), nuc.index_inelastic_scatter_.end(), (int)r) !=
-                            nuc.index_inelastic_scatter_.end()
-                          ? 1
-                          : 0);
-      rx_thr.push_back(rx.xs_[0].threshold);
-      rx_xs.insert(rx_xs.end(), rx.xs_[0].value.begin(), rx.xs_[0].value.end());
-      rx_xofs.push_back(rx_xs.size());
-      rx_q.push_back(rx.q_value_);
-      for (const auto& p : rx.products_) {
-        if (p.particle_ != ParticleType::neutron)
-          continue; // photon production: photon transport is refused above
-        p_em.push_back(p.emission_mode_ == ReactionProduct::EmissionMode::prompt    ? 0
-                       : p.emission_mode_ == ReactionProduct::EmissionMode::delayed ? 1
-                                                                                    : 2);
-        // decay_rate_ is read (and meaningful) for delayed emission only, src/reaction_product.cpp:43-52
-        p_decay.push_back(p.emission_mode_ == ReactionProduct::EmissionMode::delayed ? p.decay_rate_ : 0.0);
-        p_yield.push_back(fn.add(p.yield_.get()));
-        if (p.distribution_.size() != 1)
-          unsupported(fmt::format("a product of {} MT {} with several distributions", nuc.name_, rx.mt_));
-        auto d = dynamic_cast<const UncorrelatedAngleEnergy*>(p.distribution_[0].get());
-        if (!d)
-          unsupported(fmt::format("the correlated angle-energy distribution of {} MT {}", nuc.name_, rx.mt_));
-        if (!d->angle_.empty())
-          unsupported(fmt::format("the anisotropic angular distribution of {} MT {}", nuc.name_, rx.mt_));
-        const EnergyDistribution* e = d->energy_.get();
-        int law = OMCGPU_ELAW_NONE, f0 = -1, f1 = -1;
-        double par0 = 0.0, par1 = 0.0;
-        if (!e) {
-          if (rx.mt_ != ELASTIC)
-            unsupported(fmt::format("{} MT {} without an energy distribution", nuc.name_, rx.mt_));
-        } else if (auto l = dynamic_cast<const LevelInelastic*>(e)) {
-          law = OMCGPU_ELAW_LEVEL; par0 = l->threshold_; par1 = l->mass_ratio_;
-        } else if (auto l = dynamic_cast<const MaxwellEnergy*>(e)) {
-          law = OMCGPU_ELAW_MAXWELL; par0 = l->u_; f0 = fn.add(&l->theta_);
-        } else if (auto l = dynamic_cast<const Evaporation*>(e)) {
-          law = OMCGPU_ELAW_EVAPORATION; par0 = l->u_; f0 = fn.add(&l->theta_);
-        } else if (auto l = dynamic_cast<const WattEnergy*>(e)) {
-          law = OMCGPU_ELAW_WATT; par0 = l->u_; f0 = fn.add(&l->a_); f1 = fn.add(&l->b_);
-        } else {
-          unsupported(fmt::format("the energy distribution of {} MT {} (continuous tabular / discrete photon)", nuc.name_, rx.mt_));
+    for (size_t it = 0; it < nuc.kTs_.size(); ++it) {
+      awr.push_back(nuc.awr_);
+      kT.push_back(nuc.kTs_[it]);
+      fissionable.push_back(nuc.fissionable_ ? 1 : 0);
+      const auto& grid = nuc.grid_[it];
+      const auto& tab = nuc.xs_[it];
+      const size_t n = grid.energy.size();
+      energy.insert(energy.end(), grid.energy.begin(), grid.energy.end());
+      for (size_t k = 0; k < n; ++k)
+        for (int x = 0; x < 4; ++x) // total, absorption, fission, nu-fission (photon production dropped)
+          xs.push_back(tab(k, x));
+      gidx.insert(gidx.end(), grid.grid_index.begin(), grid.grid_index.end());
+      if ((int)grid.grid_index.size() != settings::n_log_bins + 1)
+        unsupported("a log-hash table whose size is not n_log_bins + 1");
+      gofs.push_back(energy.size());
+      n_prec.push_back(nuc.n_precursor_);
+      tot_nu.push_back(fn.add(nuc.total_nu_.get()));
+      fis_rx.push_back(-1);
+      const int r0 = rx_mt.size();
+      for (size_t r = 0; r < nuc.reactions_.size(); ++r) {
+        const Reaction& rx = *nuc.reactions_[r];
+        if (rx.redundant_)
+          unsupported(fmt::format("the redundant reaction MT {} of {}", rx.mt_, nuc.name_));
+        if (!nuc.fission_rx_.empty() && nuc.fission_rx_[0] == &rx)
+          fis_rx.back() = r;
+        rx_mt.push_back(rx.mt_);
+        rx_cm.push_back(rx.scatter_in_cm_ ? 1 : 0);
+        rx_inel.push_back(std::find(nuc.index_inelastic_scatter_.begin(), nuc.index_inelastic_scatter_.end(), (int)r) !=
+                              nuc.index_inelastic_scatter_.end()
+                            ? 1
+                            : 0);
+        rx_thr.push_back(rx.xs_[it].threshold);
+        rx_xs.insert(rx_xs.end(), rx.xs_[it].value.begin(), rx.xs_[it].value.end());
+        rx_xofs.push_back(rx_xs.size());
+        rx_q.push_back(rx.q_value_);
+        for (const auto& p : rx.products_) {
+          if (p.particle_ != ParticleType::neutron)
+            continue; // photon production: photon transport is refused above
+          p_em.push_back(p.emission_mode_ == ReactionProduct::EmissionMode::prompt    ? 0
+                         : p.emission_mode_ == ReactionProduct::EmissionMode::delayed ? 1
+                                                                                      : 2);
+          // decay_rate_ is read (and meaningful) for delayed emission only, src/reaction_product.cpp:43-52
+          p_decay.push_back(p.emission_mode_ == ReactionProduct::EmissionMode::delayed ? p.decay_rate_ : 0.0);
+          p_yield.push_back(fn.add(p.yield_.get()));
+          if (p.distribution_.size() != 1)
+            unsupported(fmt::format("a product of {} MT {} with several distributions", nuc.name_, rx.mt_));
+          auto d = dynamic_cast<const UncorrelatedAngleEnergy*>(p.distribution_[0].get());
+          if (!d)
+            unsupported(fmt::format("the correlated angle-energy distribution of {} MT {}", nuc.name_, rx.mt_));
+          if (!d->angle_.empty())
+            unsupported(fmt::format("the anisotropic angular distribution of {} MT {}", nuc.name_, rx.mt_));
+          const EnergyDistribution* e = d->energy_.get();
+          int law = OMCGPU_ELAW_NONE, f0 = -1, f1 = -1;
+          double par0 = 0.0, par1 = 0.0;
+          if (!e) {
+            if (rx.mt_ != ELASTIC)
+              unsupported(fmt::format("{} MT {} without an energy distribution", nuc.name_, rx.mt_));
+          } else if (auto l = dynamic_cast<const LevelInelastic*>(e)) {
+            law = OMCGPU_ELAW_LEVEL; par0 = l->threshold_; par1 = l->mass_ratio_;
+          } else if (auto l = dynamic_cast<const MaxwellEnergy*>(e)) {
+            law = OMCGPU_ELAW_MAXWELL; par0 = l->u_; f0 = fn.add(&l->theta_);
+          } else if (auto l = dynamic_cast<const Evaporation*>(e)) {
+            law = OMCGPU_ELAW_EVAPORATION; par0 = l->u_; f0 = fn.add(&l->theta_);
+          } else if (auto l = dynamic_cast<const WattEnergy*>(e)) {
+            law = OMCGPU_ELAW_WATT; par0 = l->u_; f0 = fn.add(&l->a_); f1 = fn.add(&l->b_);
+          } else {
+            unsupported(fmt::format("the energy distribution of {} MT {} (continuous tabular / discrete photon)", nuc.name_, rx.mt_));
+          }
+          p_law.push_back(law);
+          p_par.push_back(par0);
+          p_par.push_back(par1);
+          p_fn.push_back(f0);
+          p_fn.push_back(f1);
         }
-        p_law.push_back(law);
-        p_par.push_back(par0);
-        p_par.push_back(par1);
-        p_fn.push_back(f0);
-        p_fn.push_back(f1);
+        rx_pofs.push_back(p_em.size());
       }
-      rx_pofs.push_back(p_em.size());
+      if (rx_mt.size() == (size_t)r0 || rx_mt[r0] != ELASTIC)
+        unsupported(fmt::format("{}: elastic scattering is not the first reaction", nuc.name_));
+      rx_ofs.push_back(rx_mt.size());
     }
-    if (rx_mt.size() == (size_t)r0 || rx_mt[r0] != ELASTIC)
-      unsupported(fmt::format("{}: elastic scattering is not the first reaction", nuc.name_));
-    rx_ofs.push_back(rx_mt.size());
+    tab_ofs.push_back(kT.size());
   }
+  m.n_nuclides = kT.size();
+  m.n_nuclide_temps = multi ? nn : 0;
+  if (!multi)
+    tab_ofs.assign(1, 0);
+  KEEP(nuct_ofs, tab_ofs);
   KEEP(nuc_awr, awr);
   KEEP(nuc_kT, kT);
   KEEP(nuc_fissionable, fissionable);

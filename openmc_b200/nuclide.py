@@ -123,6 +123,10 @@ def synthetic_nuclide(name, Z, A, n_grid=100000, fissionable=False, inelastic=Fa
     lo, hi = (1.0, 3.0e4) if heavy else (1.0e4, 5.0e6)
     E_r = np.sort(np.exp(rng.uniform(np.log(lo), np.log(hi), n_res)))
     gam = E_r * rng.uniform(2e-4, 3e-3, n_res) + 0.03
+    # crude Doppler broadening: resonances widen (and their peaks drop) with sqrt(T / 294 K); the
+    # grid clusters follow the widths, so every temperature has its own energy grid
+    broaden = math.sqrt(temperature / 294.0)
+    gam = gam * broaden
     # grid: 60 % log-uniform + 40 % clustered on the resonances, plus exact end points
     n_smooth = int(0.6 * n_grid)
     g_smooth = np.exp(np.linspace(np.log(E_LOW), np.log(E_HIGH), n_smooth))
@@ -142,7 +146,7 @@ def synthetic_nuclide(name, Z, A, n_grid=100000, fissionable=False, inelastic=Fa
         out = np.zeros_like(energy)
         if scale == 0.0:
             return out
-        peaks = scale * rng.lognormal(0.0, 0.8, n_res) * 100.0 / np.sqrt(np.maximum(E_r, 1.0))
+        peaks = scale * rng.lognormal(0.0, 0.8, n_res) * 100.0 / np.sqrt(np.maximum(E_r, 1.0)) / broaden
         for k in range(n_res):
             i0 = np.searchsorted(energy, E_r[k] - 400 * gam[k])
             i1 = np.searchsorted(energy, E_r[k] + 400 * gam[k])
@@ -185,9 +189,53 @@ def synthetic_nuclide(name, Z, A, n_grid=100000, fissionable=False, inelastic=Fa
     return Nuclide(name, Z, A, awr, temperature * K_BOLTZMANN, energy, rx, total_nu)
 
 
-def synthetic_library(names_ZA, n_grid=100000, **kw):
-    """names_ZA: [(name, Z, A, fissionable, inelastic, delayed)]"""
+def synthetic_library(names_ZA, n_grid=100000, temperatures=None, **kw):
+    """names_ZA: [(name, Z, A, fissionable, inelastic, delayed)].  With `temperatures` (K) every
+    entry is a LIST of tables, one per temperature in ascending order (an OpenMC nuclide file with
+    several kTs / energy / reaction_xxx/<T>K groups)."""
+    if temperatures:
+        return {n: [synthetic_nuclide(n, Z, A, n_grid, f, i, d, temperature=T) for T in sorted(temperatures)]
+                for n, Z, A, f, i, d in names_ZA}
     return {n: synthetic_nuclide(n, Z, A, n_grid, f, i, d, **kw) for n, Z, A, f, i, d in names_ZA}
+
+
+def tables_of(entry):
+    """library entry -> list of per-temperature tables (ascending kT)"""
+    return list(entry) if isinstance(entry, (list, tuple)) else [entry]
+
+
+def nuclide_temperatures(model: Model, names):
+    """temperatures [K] every nuclide is needed at: get_temperatures, src/cross_sections.cpp --
+    every material cell contributes its temperature(s) to the nuclides of its material, in cell order"""
+    need = {n: [] for n in names}
+    for c in model.cells:
+        if c.fill_type != "material" or c.fill is None:
+            continue
+        T = c.temperature
+        if T is None and c.fill.temperature is not None:
+            T = c.fill.temperature
+        if T is None:
+            T = 293.6
+        sq = math.sqrt(K_BOLTZMANN * T)
+        T = sq * sq / K_BOLTZMANN                       # as the reference recovers it from sqrtkT_
+        for n, _ in c.fill.components:
+            if T not in need[n]:
+                need[n].append(T)
+    return need
+
+
+def temperatures_to_read(tables, desired, tolerance):
+    """Nuclide::Nuclide, TemperatureMethod::NEAREST (src/nuclide.cpp:84-165): indices of the
+    library tables loaded for the desired temperatures, ascending"""
+    avail = [float(round(t.kT / K_BOLTZMANN)) for t in tables]
+    read = []
+    for T in desired:
+        best = min(range(len(avail)), key=lambda i: (abs(avail[i] - T), i))
+        if abs(avail[best] - T) >= tolerance:
+            raise ValueError(f"library does not contain cross sections at or near {T} K")
+        if best not in read:
+            read.append(best)
+    return sorted(read, key=lambda i: avail[i])
 
 
 PINCELL_NUCLIDES = [
@@ -228,8 +276,17 @@ def build_ce_fields(model: Model, library: dict) -> dict:
         for n, _ in m.components:
             if n not in names:
                 names.append(n)
-    nucs = [library[n] for n in names]
-    index = {n: i for i, n in enumerate(names)}
+    need = nuclide_temperatures(model, names)
+    tol = float(st.get("temperature_tolerance", 10.0))
+    nucs = []            # the TABLES (nuclide x loaded temperature), nuclide-major, ascending kT
+    tab_ofs = [0]
+    for n in names:
+        tabs = tables_of(library[n])
+        for k in temperatures_to_read(tabs, need[n], tol):
+            nucs.append(tabs[k])
+        tab_ofs.append(len(nucs))
+    multi = len(nucs) != len(names)
+    index = {n: i for i, n in enumerate(names)}       # mat_nuclide: nuclide index (== table index if not multi)
     M = int(st["n_log_bins"])
     # data::energy_min/max = intersection over nuclides (src/simulation.cpp:682-696)
     e_min = max(float(n.energy[0]) for n in nucs)
@@ -241,7 +298,8 @@ def build_ce_fields(model: Model, library: dict) -> dict:
     umesh = np.array(umesh)
 
     v = dict(n_nuclides=len(nucs), n_log_bins=M, log_spacing=spacing, energy_min=e_min,
-             energy_max=e_max)
+             energy_max=e_max, n_nuclide_temps=len(names) if multi else 0,
+             nuct_ofs=np.array(tab_ofs if multi else [0], np.int32))
     grid_ofs = [0]; energy = []; xs = []; gidx = []
     rx_ofs = [0]; fis_rx = []; n_prec = []; tot_nu = []
     rx_mt = []; rx_cm = []; rx_inel = []; rx_thr = []; rx_xs_ofs = [0]; rx_xs = []; rx_q = []
@@ -328,12 +386,12 @@ def build_ce_fields(model: Model, library: dict) -> dict:
     # materials
     mofs = [0]; mnuc = []; mden = []; mfis = []
     for m in model.materials:
-        awr = [library[n].awr for n, _ in m.components]
+        awr = [tables_of(library[n])[0].awr for n, _ in m.components]
         dens = normalize_density(m, awr)
         mnuc += [index[n] for n, _ in m.components]
         mden += dens
         mofs.append(len(mnuc))
-        mfis.append(int(any(library[n].fissionable for n, _ in m.components)))
+        mfis.append(int(any(tables_of(library[n])[0].fissionable for n, _ in m.components)))
     v.update(n_materials=len(model.materials),
              mat_id=np.array([m.id for m in model.materials], np.int32),
              mat_fissionable=np.array(mfis, np.int32), mat_nuc_ofs=np.array(mofs, np.int32),

@@ -1240,6 +1240,25 @@ double ce_reaction_xs(int rx, const MicroXS& micro)
          micro.interp_factor * v[micro.index_grid - thr + 1];
 }
 
+// temperature pick of Nuclide::calculate_xs, TemperatureMethod::NEAREST (src/nuclide.cpp:682-691):
+// the table of material entry d (one nuclide at one loaded temperature) nearest to the cell's kT
+int nuc_table(int d, double sqrtkT)
+{
+  if (M->n_nuclide_temps == 0)
+    return d;
+  const double kT = sqrtkT * sqrtkT;
+  int i_temp = M->nuct_ofs[d];
+  double max_diff = INFINITY;
+  for (int t = M->nuct_ofs[d]; t < M->nuct_ofs[d + 1]; ++t) {
+    const double diff = std::abs(M->nuc_kT[t] - kT);
+    if (diff < max_diff) {
+      i_temp = t;
+      max_diff = diff;
+    }
+  }
+  return i_temp;
+}
+
 void ce_calculate_xs(Particle& p, int32_t* i_grid_out = nullptr, int max_nuc = 0)
 {
   p.xs_total = p.xs_absorption = p.xs_fission = p.xs_nu_fission = 0.0;
@@ -1247,7 +1266,7 @@ void ce_calculate_xs(Particle& p, int32_t* i_grid_out = nullptr, int max_nuc = 0
   int m = p.material;
   for (int k = M->mat_nuc_ofs[m]; k < M->mat_nuc_ofs[m + 1]; ++k) {
     MicroXS micro;
-    ce_micro_xs(M->mat_nuclide[k], i_log, p.E, micro);
+    ce_micro_xs(nuc_table(M->mat_nuclide[k], p.sqrtkT), i_log, p.E, micro);
     double atom_density = M->mat_atom_density[k];
     p.xs_total += atom_density * micro.total;
     p.xs_absorption += atom_density * micro.absorption;
@@ -1495,10 +1514,11 @@ void collision_ce(Particle& p)
   int i_nuclide = -1;
   MicroXS micro;
   for (int k = M->mat_nuc_ofs[m]; k < M->mat_nuc_ofs[m + 1]; ++k) {
-    ce_micro_xs(M->mat_nuclide[k], i_log, p.E, micro);
+    const int table = nuc_table(M->mat_nuclide[k], p.sqrtkT);
+    ce_micro_xs(table, i_log, p.E, micro);
     prob += M->mat_atom_density[k] * micro.total;
     if (prob >= cutoff) {
-      i_nuclide = M->mat_nuclide[k];
+      i_nuclide = table; // every nuc_* / rx_* array is indexed by table
       break;
     }
   }

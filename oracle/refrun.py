@@ -231,11 +231,14 @@ def _write_function(group, name, fn):
 _ELAW = {1: "level", 2: "maxwell", 3: "evaporation", 4: "watt"}   # OMCGPU_ELAW_* (include/omcgpu.h:94-98)
 
 
-def write_nuclide(path, nuc):
-    """one synthetic nuclide (openmc_b200.nuclide.Nuclide) -> <path> in the layout of
-    IncidentNeutron.export_to_hdf5 (openmc/data/neutron.py:354-431)"""
-    T = int(round(nuc.kT / K_BOLTZMANN))
-    label = f"{T}K"
+def write_nuclide(path, entry):
+    """one synthetic nuclide (openmc_b200.nuclide.Nuclide, or a list of them = the same nuclide
+    at several temperatures) -> <path> in the layout of IncidentNeutron.export_to_hdf5
+    (openmc/data/neutron.py:354-431): kTs/<T>K, energy/<T>K, reactions/reaction_<mt>/<T>K/xs;
+    products and distributions are temperature independent (taken from the first table)"""
+    tables = list(entry) if isinstance(entry, (list, tuple)) else [entry]
+    nuc = tables[0]
+    labels = ["%dK" % int(round(t.kT / K_BOLTZMANN)) for t in tables]
     with omh5.File(path, "w") as f:
         f.attrs["filetype"] = b"data_neutron"
         f.attrs["version"] = np.array([3, 0], np.int32)      # HDF5_VERSION, include/openmc/constants.h:25
@@ -244,18 +247,22 @@ def write_nuclide(path, nuc):
         g.attrs["A"] = np.int32(nuc.A)
         g.attrs["metastable"] = np.int32(0)
         g.attrs["atomic_weight_ratio"] = float(nuc.awr)
-        g.create_dataset(f"kTs/{label}", data=float(nuc.kT))
-        g.create_dataset(f"energy/{label}", data=np.asarray(nuc.energy, float))
+        for t, label in zip(tables, labels):
+            g.create_dataset(f"kTs/{label}", data=float(t.kT))
+            g.create_dataset(f"energy/{label}", data=np.asarray(t.energy, float))
         rxs = g.create_group("reactions")
-        for r in nuc.reactions:
+        for ir, r in enumerate(nuc.reactions):
             rg = rxs.create_group("reaction_%03d" % r.mt)
             rg.attrs["mt"] = np.int32(r.mt)
             rg.attrs["label"] = ("MT%d" % r.mt).encode()
             rg.attrs["Q_value"] = float(r.q_value)
             rg.attrs["center_of_mass"] = np.int32(1 if r.scatter_in_cm else 0)
             rg.attrs["redundant"] = np.int32(0)
-            d = rg.create_dataset(f"{label}/xs", data=np.asarray(r.xs, float))
-            d.attrs["threshold_idx"] = np.int32(r.threshold)
+            for t, label in zip(tables, labels):
+                rt = t.reactions[ir]
+                assert rt.mt == r.mt
+                d = rg.create_dataset(f"{label}/xs", data=np.asarray(rt.xs, float))
+                d.attrs["threshold_idx"] = np.int32(rt.threshold)
             for k, p in enumerate(r.products):
                 pg = rg.create_group(f"product_{k}")
                 pg.attrs["particle"] = b"neutron"

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "oracle", "_ref", "libref_geom.so")
 
 
-from oracle.refrun import LATTICE_ID_BASE, geometry_xml  # noqa: E402,F401  (the emitter lives with the other XML writers)
+from oracle.refrun import LATTICE_ID_BASE, _fmt, geometry_xml  # noqa: E402,F401  (the emitters live with the other XML writers)
 
 
 class ReferenceGeometry:

@@ -15,6 +15,7 @@ from openmc_b200.model import Filter, Tally
 # name -> (particles, batches, inactive)
 RUNS = {
     "pincell_ce": (1000, 10, 5),          # C2, small grids, mesh x energy tallies + collision estimator
+    "pincell_ce_temperatures": (1000, 8, 3),   # library at 294 / 600 / 900 K, cells at 880 / 620 / 600 / 575 K
     "assembly_ce": (1000, 8, 3),          # C3, lattice, distribcell + collision-estimator tallies
     "pincell_mg": (1000, 8, 3),           # C1
     "c5g7_core": (1000, 8, 3),            # C4, lattice of lattices, mesh tally
@@ -36,6 +37,11 @@ def build(name):
         m.filters.append(Filter(nf + 1, "material", [mat.id for mat in m.materials]))
         m.tallies.append(Tally(nt + 1, [nf + 1], ["flux", "total", "absorption", "fission", "nu-fission", "scatter"],
                                estimator="collision"))
+        ce = True
+    elif name == "pincell_ce_temperatures":
+        m, lib, box, of = examples.pincell_ce(n_grid=3000, mesh_dim=6, energy_bins=12, tallies=True,
+                                               temperatures=((294.0, 600.0, 900.0), (880.0, 620.0, 600.0, 575.0)))
+        m.settings["temperature_tolerance"] = 50.0
         ce = True
     elif name == "assembly_ce":
         m, lib, box, of = examples.assembly_ce(n_grid=2000)

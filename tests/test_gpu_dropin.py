@@ -48,7 +48,7 @@ def test_dropin_multigroup(gpu_engine, name):
         np.testing.assert_allclose(got["tally_sum"], ref["tally_sum"], rtol=1e-6, atol=1e-9 * ref["tally_sum"].max())
 
 
-@pytest.mark.parametrize("name", ["pincell_ce", "assembly_ce"])
+@pytest.mark.parametrize("name", ["pincell_ce", "pincell_ce_temperatures", "assembly_ce"])
 def test_dropin_continuous_energy(gpu_engine, name):
     got, n = _run(name, gpu_engine)
     ref = dict(np.load(rr.GOLDEN % name))

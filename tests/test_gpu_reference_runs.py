@@ -24,7 +24,7 @@ from oracle.binding import Oracle
 pytestmark = pytest.mark.gpu
 
 MG = ["pincell_mg", "c5g7_core", "surface_zoo", "rotated_fills", "periodic_box"]
-CE = ["pincell_ce", "assembly_ce", "pwr_core_ce"]
+CE = ["pincell_ce", "pincell_ce_temperatures", "assembly_ce", "pwr_core_ce"]
 
 
 def _run(gpu_engine, name):
