@@ -32,6 +32,57 @@ OMC_HD T ld(const T* p)
 #endif
 }
 
+// ---- CSG tables staged in shared memory ---------------------------------------------------------
+// Surfaces, region tokens, cells, universes' cell lists, half-space candidate lists and lattices
+// are uploaded into ONE block of device memory (the geometry blob: a few KB for the configurations
+// of BASELINE.json).  Kernels that walk the geometry are launched with the blob's size (up to a
+// budget) as dynamic shared memory and copy it there once per block (stage_geometry); every read
+// of a geometry table then goes through gld(): an address inside the staged part of the blob is
+// served from the block's copy, anything else (a model larger than the budget, a kernel launched
+// without dynamic shared memory) from global memory.  The event kernels stream ~1 KB of particle
+// state per event through L1, which keeps evicting the geometry lines every lane needs again a
+// moment later; the block's copy cannot be evicted.
+#if OMC_CUDA
+__constant__ const char* c_geo_blob;
+#if defined(__CUDA_ARCH__)
+extern __shared__ __align__(16) unsigned char g_geo_smem[];
+OMC_HD uint32_t geo_staged_bytes()
+{
+  uint32_t r;
+  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(r));
+  return r;
+}
+#endif
+#endif
+template<class T>
+OMC_HD T gld(const T* p)
+{
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  const uint64_t off = (uint64_t)(reinterpret_cast<const char*>(p) - c_geo_blob);
+  if (off < (uint64_t)geo_staged_bytes())
+    return *reinterpret_cast<const T*>(g_geo_smem + off);
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+#if OMC_CUDA
+// every thread of the block, before any of them leaves the kernel
+OMC_HD void stage_geometry()
+{
+#if defined(__CUDA_ARCH__)
+  const uint32_t nb = geo_staged_bytes();
+  if (nb) {
+    const uint4* src = reinterpret_cast<const uint4*>(c_geo_blob);
+    uint4* dst = reinterpret_cast<uint4*>(g_geo_smem);
+    for (uint32_t k = threadIdx.x; k < (nb >> 4); k += blockDim.x)
+      dst[k] = __ldg(src + k);
+    __syncthreads();
+  }
+#endif
+}
+#endif
+
 // =============================================================================
 // RNG -- src/random_lcg.cpp:11-13 (constants), 32-44 (prn), 91-120 (future_seed)
 // =============================================================================
@@ -138,8 +189,8 @@ OMC_HD double watt_spectrum(double a, double b, uint64_t& seed)
 OMC_HD double surf_evaluate(int s, V3 r)
 {
   const double* c = DM.surf_coef + OMCGPU_SURF_NCOEF * s;
-  const double c0 = ld(c), c1 = ld(c + 1), c2 = ld(c + 2), c3 = ld(c + 3);
-  switch (ld(DM.surf_type + s)) {
+  const double c0 = gld(c), c1 = gld(c + 1), c2 = gld(c + 2), c3 = gld(c + 3);
+  switch (gld(DM.surf_type + s)) {
   case OMCGPU_SURF_XPLANE:
     return r.x - c0;
   case OMCGPU_SURF_YPLANE:
@@ -182,7 +233,7 @@ OMC_HD double surf_evaluate(int s, V3 r)
 OMC_HD V3 surf_normal(int s, V3 r)
 {
   const double* c = DM.surf_coef + OMCGPU_SURF_NCOEF * s;
-  switch (ld(DM.surf_type + s)) {
+  switch (gld(DM.surf_type + s)) {
   case OMCGPU_SURF_XPLANE:
     return v3(1., 0., 0.);
   case OMCGPU_SURF_YPLANE:
@@ -190,21 +241,21 @@ OMC_HD V3 surf_normal(int s, V3 r)
   case OMCGPU_SURF_ZPLANE:
     return v3(0., 0., 1.);
   case OMCGPU_SURF_PLANE:
-    return v3(ld(c), ld(c + 1), ld(c + 2));
+    return v3(gld(c), gld(c + 1), gld(c + 2));
   case OMCGPU_SURF_XCYLINDER:
-    return v3(0.0, 2.0 * (r.y - ld(c)), 2.0 * (r.z - ld(c + 1)));
+    return v3(0.0, 2.0 * (r.y - gld(c)), 2.0 * (r.z - gld(c + 1)));
   case OMCGPU_SURF_YCYLINDER:
-    return v3(2.0 * (r.x - ld(c)), 0.0, 2.0 * (r.z - ld(c + 1)));
+    return v3(2.0 * (r.x - gld(c)), 0.0, 2.0 * (r.z - gld(c + 1)));
   case OMCGPU_SURF_ZCYLINDER:
-    return v3(2.0 * (r.x - ld(c)), 2.0 * (r.y - ld(c + 1)), 0.0);
+    return v3(2.0 * (r.x - gld(c)), 2.0 * (r.y - gld(c + 1)), 0.0);
   case OMCGPU_SURF_SPHERE:
-    return v3(2.0 * (r.x - ld(c)), 2.0 * (r.y - ld(c + 1)), 2.0 * (r.z - ld(c + 2)));
+    return v3(2.0 * (r.x - gld(c)), 2.0 * (r.y - gld(c + 1)), 2.0 * (r.z - gld(c + 2)));
   case OMCGPU_SURF_XCONE: // axis_aligned_cone_normal, src/surface.cpp:747-756
-    return v3(-2.0 * ld(c + 3) * (r.x - ld(c)), 2.0 * (r.y - ld(c + 1)), 2.0 * (r.z - ld(c + 2)));
+    return v3(-2.0 * gld(c + 3) * (r.x - gld(c)), 2.0 * (r.y - gld(c + 1)), 2.0 * (r.z - gld(c + 2)));
   case OMCGPU_SURF_YCONE:
-    return v3(2.0 * (r.x - ld(c)), -2.0 * ld(c + 3) * (r.y - ld(c + 1)), 2.0 * (r.z - ld(c + 2)));
+    return v3(2.0 * (r.x - gld(c)), -2.0 * gld(c + 3) * (r.y - gld(c + 1)), 2.0 * (r.z - gld(c + 2)));
   default:
-    return v3(2.0 * (r.x - ld(c)), 2.0 * (r.y - ld(c + 1)), -2.0 * ld(c + 3) * (r.z - ld(c + 2)));
+    return v3(2.0 * (r.x - gld(c)), 2.0 * (r.y - gld(c + 1)), -2.0 * gld(c + 3) * (r.z - gld(c + 2)));
   }
 }
 
@@ -289,8 +340,8 @@ OMC_HD double cone_distance(double r1, double r2, double r3, double u1, double u
 OMC_HD double surf_distance(int s, V3 r, V3 u, bool coincident)
 {
   const double* c = DM.surf_coef + OMCGPU_SURF_NCOEF * s;
-  const double c0 = ld(c), c1 = ld(c + 1), c2 = ld(c + 2), c3 = ld(c + 3);
-  switch (ld(DM.surf_type + s)) {
+  const double c0 = gld(c), c1 = gld(c + 1), c2 = gld(c + 2), c3 = gld(c + 3);
+  switch (gld(DM.surf_type + s)) {
   case OMCGPU_SURF_XPLANE:
     return plane_distance(c0 - r.x, u.x, coincident);
   case OMCGPU_SURF_YPLANE:
@@ -332,11 +383,11 @@ OMC_HD double surf_distance(int s, V3 r, V3 u, bool coincident)
 // =============================================================================
 OMC_HD bool cell_contains(int c, V3 r, V3 u, int on_surface)
 {
-  const int t0 = ld(DM.cell_region_ofs + c), t1 = ld(DM.cell_region_ofs + c + 1);
+  const int t0 = gld(DM.cell_region_ofs + c), t1 = gld(DM.cell_region_ofs + c + 1);
   const int32_t* tok = DM.region_tokens;
-  if (ld(DM.cell_simple + c)) {
+  if (gld(DM.cell_simple + c)) {
     for (int it = t0; it < t1; ++it) {
-      const int32_t token = ld(tok + it);
+      const int32_t token = gld(tok + it);
       if (token == on_surface)
         continue;
       if (-token == on_surface)
@@ -349,7 +400,7 @@ OMC_HD bool cell_contains(int c, V3 r, V3 u, int on_surface)
   bool in_cell = true;
   int total_depth = 0;
   for (int it = t0; it < t1; ++it) {
-    const int32_t token = ld(tok + it);
+    const int32_t token = gld(tok + it);
     if (token < OP_UNION) {
       if (token == on_surface)
         in_cell = true;
@@ -364,7 +415,7 @@ OMC_HD bool cell_contains(int c, V3 r, V3 u, int on_surface)
       int depth = 1;
       do {
         ++it;
-        const int32_t next_token = ld(tok + it);
+        const int32_t next_token = gld(tok + it);
         if (next_token > OP_COMPLEMENT)
           depth += (next_token == OP_RIGHT_PAREN) ? -1 : 1;
       } while (depth > 0);
@@ -381,10 +432,10 @@ OMC_HD void cell_distance(int c, V3 r, V3 u, int on_surface, double& min_dist, i
 {
   min_dist = INFTY;
   i_surf = 2147483647;
-  const int t0 = ld(DM.cell_region_ofs + c), t1 = ld(DM.cell_region_ofs + c + 1);
+  const int t0 = gld(DM.cell_region_ofs + c), t1 = gld(DM.cell_region_ofs + c + 1);
   const int abs_on = abs(on_surface);
   for (int it = t0; it < t1; ++it) {
-    const int32_t token = ld(DM.region_tokens + it);
+    const int32_t token = gld(DM.region_tokens + it);
     if (token >= OP_UNION)
       continue;
     const double d = surf_distance(abs(token) - 1, r, u, abs(token) == abs_on);
@@ -404,8 +455,8 @@ OMC_HD void cell_distance(int c, V3 r, V3 u, int on_surface, double& min_dist, i
 OMC_HD V3 cell_rotate(int c, V3 v)
 {
   const double* m = DM.cell_rotation + 9 * c;
-  return v3(v.x * ld(m) + v.y * ld(m + 1) + v.z * ld(m + 2), v.x * ld(m + 3) + v.y * ld(m + 4) + v.z * ld(m + 5),
-    v.x * ld(m + 6) + v.y * ld(m + 7) + v.z * ld(m + 8));
+  return v3(v.x * gld(m) + v.y * gld(m + 1) + v.z * gld(m + 2), v.x * gld(m + 3) + v.y * gld(m + 4) + v.z * gld(m + 5),
+    v.x * gld(m + 6) + v.y * gld(m + 7) + v.z * gld(m + 8));
 }
 
 struct LatIdx {
@@ -415,17 +466,17 @@ struct LatIdx {
 OMC_HD bool lat_valid(int l, LatIdx i)
 {
   const int32_t* n = DM.lat_shape + 3 * l;
-  return i.x >= 0 && i.x < ld(n) && i.y >= 0 && i.y < ld(n + 1) && i.z >= 0 && i.z < ld(n + 2);
+  return i.x >= 0 && i.x < gld(n) && i.y >= 0 && i.y < gld(n + 1) && i.z >= 0 && i.z < gld(n + 2);
 }
 OMC_HD int lat_flat(int l, LatIdx i)
 {
   const int32_t* n = DM.lat_shape + 3 * l;
-  const int nx = ld(n), ny = ld(n + 1);
+  const int nx = gld(n), ny = gld(n + 1);
   return nx * ny * i.z + nx * i.y + i.x;
 }
 OMC_HD int lat_universe(int l, LatIdx i)
 {
-  return ld(DM.lat_universes + ld(DM.lat_univ_ofs + l) + lat_flat(l, i));
+  return gld(DM.lat_universes + gld(DM.lat_univ_ofs + l) + lat_flat(l, i));
 }
 OMC_HD int lat_axis_index(double r, double ll, double pitch, double u)
 {
@@ -440,19 +491,19 @@ OMC_HD LatIdx lat_get_indices(int l, V3 r, V3 u)
   const double* ll = DM.lat_lower_left + 3 * l;
   const double* p = DM.lat_pitch + 3 * l;
   LatIdx i;
-  i.x = lat_axis_index(r.x, ld(ll), ld(p), u.x);
-  i.y = lat_axis_index(r.y, ld(ll + 1), ld(p + 1), u.y);
-  i.z = ld(DM.lat_is3d + l) ? lat_axis_index(r.z, ld(ll + 2), ld(p + 2), u.z) : 0;
+  i.x = lat_axis_index(r.x, gld(ll), gld(p), u.x);
+  i.y = lat_axis_index(r.y, gld(ll + 1), gld(p + 1), u.y);
+  i.z = gld(DM.lat_is3d + l) ? lat_axis_index(r.z, gld(ll + 2), gld(p + 2), u.z) : 0;
   return i;
 }
 OMC_HD V3 lat_local_position(int l, V3 r, LatIdx i)
 {
   const double* ll = DM.lat_lower_left + 3 * l;
   const double* p = DM.lat_pitch + 3 * l;
-  r.x -= (ld(ll) + (i.x + 0.5) * ld(p));
-  r.y -= (ld(ll + 1) + (i.y + 0.5) * ld(p + 1));
-  if (ld(DM.lat_is3d + l))
-    r.z -= (ld(ll + 2) + (i.z + 0.5) * ld(p + 2));
+  r.x -= (gld(ll) + (i.x + 0.5) * gld(p));
+  r.y -= (gld(ll + 1) + (i.y + 0.5) * gld(p + 1));
+  if (gld(DM.lat_is3d + l))
+    r.z -= (gld(ll + 2) + (i.z + 0.5) * gld(p + 2));
   return r;
 }
 // returns distance; translation packed as (tx+1) | (ty+1)<<2 | (tz+1)<<4
@@ -464,8 +515,8 @@ constexpr int TRANS_NONE = 1 | (1 << 2) | (1 << 4);
 OMC_HD double lat_distance(int l, V3 r, V3 u, int& trans)
 {
   const double* p = DM.lat_pitch + 3 * l;
-  const double x0 = copysign(0.5 * ld(p), u.x);
-  const double y0 = copysign(0.5 * ld(p + 1), u.y);
+  const double x0 = copysign(0.5 * gld(p), u.x);
+  const double y0 = copysign(0.5 * gld(p + 1), u.y);
   double d = INFTY;
   trans = TRANS_NONE;
   if ((fabs(r.x - x0) > FP_PRECISION) && u.x != 0) {
@@ -479,8 +530,8 @@ OMC_HD double lat_distance(int l, V3 r, V3 u, int& trans)
       trans = pack_trans(0, u.y > 0 ? 1 : -1, 0);
     }
   }
-  if (ld(DM.lat_is3d + l)) {
-    const double z0 = copysign(0.5 * ld(p + 2), u.z);
+  if (gld(DM.lat_is3d + l)) {
+    const double z0 = copysign(0.5 * gld(p + 2), u.z);
     if ((fabs(r.z - z0) > FP_PRECISION) && u.z != 0) {
       const double this_d = (z0 - r.z) / u.z;
       if (this_d < d) {
@@ -661,17 +712,17 @@ OMC_HD void store_local_results(const PState& g, int64_t i, const LocalParticle<
 OMC_HD int cell_instance_at_level(const PState& ps, int64_t i, int level)
 {
   const int c = LV(cell, level);
-  const int map = ld(DM.cell_distribcell_index + c);
+  const int map = gld(DM.cell_distribcell_index + c);
   if (map == C_NONE)
     return C_NONE;
   int instance = 0;
   for (int k = 0; k < level; k++) {
     const int c_k = LV(cell, k);
-    const int type = ld(DM.cell_type + c_k);
+    const int type = gld(DM.cell_type + c_k);
     if (type == OMCGPU_FILL_UNIVERSE) {
-      instance += ld(DM.cell_offset + ld(DM.cell_offset_ofs + c_k) + map);
+      instance += gld(DM.cell_offset + gld(DM.cell_offset_ofs + c_k) + map);
     } else if (type == OMCGPU_FILL_LATTICE) {
-      instance += ld(DM.cell_offset + ld(DM.cell_offset_ofs + c_k) + map);
+      instance += gld(DM.cell_offset + gld(DM.cell_offset_ofs + c_k) + map);
       const int lat = LV(lattice, k + 1);
       LatIdx li;
       li.x = LV(lat_x, k + 1);
@@ -679,8 +730,8 @@ OMC_HD int cell_instance_at_level(const PState& ps, int64_t i, int level)
       li.z = LV(lat_z, k + 1);
       if (lat_valid(lat, li)) {
         const int32_t* n = DM.lat_shape + 3 * lat;
-        instance += ld(DM.lat_offsets + ld(DM.lat_offset_ofs + lat) +
-                       ld(n) * ld(n + 1) * ld(n + 2) * map + lat_flat(lat, li));
+        instance += gld(DM.lat_offsets + gld(DM.lat_offset_ofs + lat) +
+                       gld(n) * gld(n + 1) * gld(n + 2) * map + lat_flat(lat, li));
       }
     }
   }
@@ -703,10 +754,10 @@ OMC_HD bool find_cell_inner(const PState& ps, int64_t i, int lvl, int surface)
       // (cells of a valid model do not overlap): search those cells of this
       // universe first -- same result as the full list, far fewer candidates
       const int slot = 2 * (abs(surface) - 1) + (surface > 0 ? 1 : 0);
-      const int k1 = ld(DM.tok_cell_ofs + slot + 1);
-      for (int k = ld(DM.tok_cell_ofs + slot); k < k1; ++k) {
-        const int c = ld(DM.tok_cells + k);
-        if (ld(DM.cell_universe + c) == univ && cell_contains(c, r, u, surface)) {
+      const int k1 = gld(DM.tok_cell_ofs + slot + 1);
+      for (int k = gld(DM.tok_cell_ofs + slot); k < k1; ++k) {
+        const int c = gld(DM.tok_cells + k);
+        if (gld(DM.cell_universe + c) == univ && cell_contains(c, r, u, surface)) {
           found = c;
           break;
         }
@@ -714,9 +765,9 @@ OMC_HD bool find_cell_inner(const PState& ps, int64_t i, int lvl, int surface)
       crossed = false;
     }
     if (found == C_NONE) { // Universe::find_cell
-      const int k1 = ld(DM.univ_cell_ofs + univ + 1);
-      for (int k = ld(DM.univ_cell_ofs + univ); k < k1; ++k) {
-        const int c = ld(DM.univ_cells + k);
+      const int k1 = gld(DM.univ_cell_ofs + univ + 1);
+      for (int k = gld(DM.univ_cell_ofs + univ); k < k1; ++k) {
+        const int c = gld(DM.univ_cells + k);
         if (cell_contains(c, r, u, surface)) {
           found = c;
           break;
@@ -728,19 +779,19 @@ OMC_HD bool find_cell_inner(const PState& ps, int64_t i, int lvl, int surface)
       return false;
     }
     LV(cell, lvl) = found;
-    const int type = ld(DM.cell_type + found);
+    const int type = gld(DM.cell_type + found);
     if (type == OMCGPU_FILL_MATERIAL) {
       ps.n_coord[i] = lvl + 1;
       int inst = 0;
-      if (ld(DM.cell_distribcell_index + found) >= 0)
+      if (gld(DM.cell_distribcell_index + found) >= 0)
         inst = cell_instance_at_level(ps, i, lvl);
       ps.cell_instance[i] = inst;
-      const int m0 = ld(DM.cell_mat_ofs + found), m1 = ld(DM.cell_mat_ofs + found + 1);
-      const int t0 = ld(DM.cell_sqrtkT_ofs + found), t1 = ld(DM.cell_sqrtkT_ofs + found + 1);
+      const int m0 = gld(DM.cell_mat_ofs + found), m1 = gld(DM.cell_mat_ofs + found + 1);
+      const int t0 = gld(DM.cell_sqrtkT_ofs + found), t1 = gld(DM.cell_sqrtkT_ofs + found + 1);
       ps.material_last[i] = ps.material[i];
-      ps.material[i] = ld(DM.cell_material + m0 + ((m1 - m0) > 1 ? inst : 0));
+      ps.material[i] = gld(DM.cell_material + m0 + ((m1 - m0) > 1 ? inst : 0));
       ps.sqrtkT_last[i] = ps.sqrtkT[i];
-      ps.sqrtkT[i] = ld(DM.cell_sqrtkT + t0 + ((t1 - t0) > 1 ? inst : 0));
+      ps.sqrtkT[i] = gld(DM.cell_sqrtkT + t0 + ((t1 - t0) > 1 ? inst : 0));
       return true;
     }
     if (lvl + 1 >= OMCGPU_MAX_COORD) {
@@ -748,15 +799,15 @@ OMC_HD bool find_cell_inner(const PState& ps, int64_t i, int lvl, int surface)
       return false;
     }
     const double* t = DM.cell_translation + 3 * found;
-    r.x -= ld(t);
-    r.y -= ld(t + 1);
-    r.z -= ld(t + 2);
-    if (ld(DM.cell_rotated + found)) { // LocalCoord::rotate, src/geometry.cpp:200-203, 219-222
+    r.x -= gld(t);
+    r.y -= gld(t + 1);
+    r.z -= gld(t + 2);
+    if (gld(DM.cell_rotated + found)) { // LocalCoord::rotate, src/geometry.cpp:200-203, 219-222
       r = cell_rotate(found, r);
       u = cell_rotate(found, u);
     }
     const int nl = lvl + 1;
-    const int fill = ld(DM.cell_fill + found);
+    const int fill = gld(DM.cell_fill + found);
     if (type == OMCGPU_FILL_UNIVERSE) {
       univ = fill;
       // lattice column of the new level stays C_NONE (levels were reset)
@@ -770,7 +821,7 @@ OMC_HD bool find_cell_inner(const PState& ps, int64_t i, int lvl, int surface)
       if (lat_valid(fill, li)) {
         univ = lat_universe(fill, li);
       } else {
-        univ = ld(DM.lat_outer + fill);
+        univ = gld(DM.lat_outer + fill);
         if (univ == C_NONE) {
           ps.n_coord[i] = nl;
           return false;
@@ -882,7 +933,7 @@ OMC_HD Boundary distance_to_boundary(const PState& ps, int64_t i, int n_coord, i
     if (d_surf < d_lat - FP_COINCIDENT) {
       if (d == inf_d() || (d - d_surf) / d >= FP_REL_PRECISION) {
         info.distance = d_surf;
-        if (ld(DM.cell_simple + c) || d_surf == INFTY) {
+        if (gld(DM.cell_simple + c) || d_surf == INFTY) {
           info.surface = level_surf_cross;
         } else {
           const V3 r_hit = v3(r.x + d_surf * u.x, r.y + d_surf * u.y, r.z + d_surf * u.z);
@@ -2285,13 +2336,13 @@ OMC_HD int mesh_get_bin(int m, V3 r)
 // `cell` the particle is in, or -1
 OMC_HD int distribcell_bin(const PState& ps, int64_t i, int n_coord, int cell)
 {
-  const int map = ld(DM.cell_distribcell_index + cell);
+  const int map = gld(DM.cell_distribcell_index + cell);
   int offset = 0;
   for (int l = 0; l < n_coord; ++l) {
     const int c = LV(cell, l);
-    const int type = ld(DM.cell_type + c);
+    const int type = gld(DM.cell_type + c);
     if (type == OMCGPU_FILL_UNIVERSE) {
-      offset += ld(DM.cell_offset + ld(DM.cell_offset_ofs + c) + map);
+      offset += gld(DM.cell_offset + gld(DM.cell_offset_ofs + c) + map);
     } else if (type == OMCGPU_FILL_LATTICE) {
       const int lat = LV(lattice, l + 1);
       LatIdx li;
@@ -2300,9 +2351,9 @@ OMC_HD int distribcell_bin(const PState& ps, int64_t i, int n_coord, int cell)
       li.z = LV(lat_z, l + 1);
       if (lat_valid(lat, li)) {
         const int32_t* n = DM.lat_shape + 3 * lat;
-        offset += ld(DM.lat_offsets + ld(DM.lat_offset_ofs + lat) + ld(n) * ld(n + 1) * ld(n + 2) * map +
+        offset += gld(DM.lat_offsets + gld(DM.lat_offset_ofs + lat) + gld(n) * gld(n + 1) * gld(n + 2) * map +
                      lat_flat(lat, li)) +
-                  ld(DM.cell_offset + ld(DM.cell_offset_ofs + c) + map);
+                  gld(DM.cell_offset + gld(DM.cell_offset_ofs + c) + map);
       }
     }
     if (c == cell)

@@ -54,22 +54,37 @@ constexpr int BLOCK = OMC_BLOCK;
 static int64_t g_launches = 0;
 
 #if OMC_CUDA
+// name##_geo: the kernel walks the CSG tables and is launched with the staged part of the geometry
+// blob as dynamic shared memory (device.h, stage_geometry / gld)
 #define OMC_KERNEL_MB(name, ArgT, body, MINBLOCKS) \
+  constexpr bool name##_geo = false; \
   __global__ void __launch_bounds__(BLOCK, MINBLOCKS) name(int64_t n_ub, ArgT a) \
   { \
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; \
     if (tid < n_ub) \
       body(tid, a); \
   }
+#define OMC_KERNEL_MB_GEO(name, ArgT, body, MINBLOCKS) \
+  constexpr bool name##_geo = true; \
+  __global__ void __launch_bounds__(BLOCK, MINBLOCKS) name(int64_t n_ub, ArgT a) \
+  { \
+    stage_geometry(); \
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; \
+    if (tid < n_ub) \
+      body(tid, a); \
+  }
 #define OMC_KERNEL(name, ArgT, body) OMC_KERNEL_MB(name, ArgT, body, 1)
+#define OMC_KERNEL_GEO(name, ArgT, body) OMC_KERNEL_MB_GEO(name, ArgT, body, 1)
 // The same body behind a persistent grid whose warps fetch the next 32 list positions from a device
 // cursor (a.cursor, zero at launch) until the list is exhausted.  With one block per 256 positions a
 // block keeps its registers and warp slots until its slowest warp is done -- the event kernels'
 // lanes differ by an order of magnitude in work (cell search, rejection loops), and ncu showed 46 %
 // of the warp slots occupied; here a warp that is done simply takes the next chunk.
 #define OMC_KERNEL_DYN(name, ArgT, body, MINBLOCKS) \
+  constexpr bool name##_geo = true; \
   __global__ void __launch_bounds__(BLOCK, MINBLOCKS) name(int64_t n_ub, ArgT a) \
   { \
+    stage_geometry(); \
     const int lane = threadIdx.x & 31; \
     int64_t cnt = *a.q_in.count; \
     cnt = cnt < n_ub ? cnt : n_ub; \
@@ -90,20 +105,24 @@ static int64_t g_launches = 0;
     if ((n_ub) > 0) { \
       unsigned grid_ = (unsigned)(((n_ub) + BLOCK - 1) / BLOCK); \
       const unsigned cap_ = (unsigned)(dyn_grid_sms() * (ctas_per_sm)); \
-      name<<<grid_ < cap_ ? grid_ : cap_, BLOCK, 0, stream>>>((int64_t)(n_ub), args); \
+      name<<<grid_ < cap_ ? grid_ : cap_, BLOCK, name##_geo ? geo_smem_bytes() : 0, stream>>>((int64_t)(n_ub), args); \
       ++g_launches; \
     } \
   } while (0)
 static int dyn_grid_sms();
+static unsigned geo_smem_bytes();
 #define OMC_LAUNCH(name, n_ub, stream, args) \
   do { \
     if ((n_ub) > 0) { \
-      name<<<(unsigned)(((n_ub) + BLOCK - 1) / BLOCK), BLOCK, 0, stream>>>((int64_t)(n_ub), args); \
+      name<<<(unsigned)(((n_ub) + BLOCK - 1) / BLOCK), BLOCK, name##_geo ? geo_smem_bytes() : 0, stream>>>((int64_t)(n_ub), \
+        args); \
       ++g_launches; \
     } \
   } while (0)
 #else
 #define OMC_KERNEL_MB(name, ArgT, body, MINBLOCKS) OMC_KERNEL(name, ArgT, body)
+#define OMC_KERNEL_MB_GEO(name, ArgT, body, MINBLOCKS) OMC_KERNEL(name, ArgT, body)
+#define OMC_KERNEL_GEO(name, ArgT, body) OMC_KERNEL(name, ArgT, body)
 #define OMC_KERNEL_DYN(name, ArgT, body, MINBLOCKS) OMC_KERNEL(name, ArgT, body)
 #define OMC_LAUNCH_DYN(name, n_ub, stream, args, ctas_per_sm) OMC_LAUNCH(name, n_ub, stream, args)
 #define OMC_KERNEL(name, ArgT, body) \
@@ -533,10 +552,10 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
     V3 r = get_r(ps, i, lvl - 1);
     const int c_up = LV(cell, lvl - 1);
     const double* t = DM.cell_translation + 3 * c_up;
-    r.x -= ld(t);
-    r.y -= ld(t + 1);
-    r.z -= ld(t + 2);
-    if (ld(DM.cell_rotated + c_up)) // src/geometry.cpp:324-326
+    r.x -= gld(t);
+    r.y -= gld(t + 1);
+    r.z -= gld(t + 2);
+    if (gld(DM.cell_rotated + c_up)) // src/geometry.cpp:324-326
       r = cell_rotate(c_up, r);
     set_r(ps, i, lvl, lat_local_position(lat, r, li));
     bool found = false;
@@ -552,7 +571,7 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
     }
   } else {
     const int s = abs(surface) - 1;
-    const int bc = ld(DM.surf_bc + s);
+    const int bc = gld(DM.surf_bc + s);
     if (bc == OMCGPU_BC_VACUUM) {
       ps.k_leak[i] += ps.wgt[i];
       ps.wgt[i] = 0.0;
@@ -563,10 +582,10 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
         mark_lost(ps, gc, i);
       } else {
         const double* t = DM.surf_periodic_shift + 3 * s;
-        LV(rx, 0) += ld(t);
-        LV(ry, 0) += ld(t + 1);
-        LV(rz, 0) += ld(t + 2);
-        const int partner = ld(DM.surf_periodic + s) + 1;
+        LV(rx, 0) += gld(t);
+        LV(ry, 0) += gld(t + 1);
+        LV(rz, 0) += gld(t + 2);
+        const int partner = gld(DM.surf_periodic + s) + 1;
         surface = surface > 0 ? partner : -partner;
         ps.surface[i] = surface;
         if (!find_cell_from(ps, i, 1, surface))
@@ -693,7 +712,7 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
     set_u(ps, i, 0, ul);
     for (int l = 1; l < n_coord; ++l) {
       const int c_up = LV(cell, l - 1);
-      if (ld(DM.cell_rotated + c_up))
+      if (gld(DM.cell_rotated + c_up))
         ul = cell_rotate(c_up, ul);
       set_u(ps, i, l, ul);
     }
@@ -716,7 +735,7 @@ OMC_D void body_init(int64_t tid, const EvArgs& a)
   if (ev_init(a.ps, a.gc, a.src, tid))
     queue_append(a.q_a, (int32_t)tid);
 }
-OMC_KERNEL(k_init, EvArgs, body_init)
+OMC_KERNEL_GEO(k_init, EvArgs, body_init)
 
 // Sort key of a calculate-xs work item: (material, lethargy) -- particles of one material
 // with neighbouring energies sit next to each other in the sorted list, so a warp's
@@ -820,7 +839,7 @@ OMC_D void body_advance(int64_t tid, const EvArgs& a)
     return;
   advance_and_route(tid, a, list_item(a.q_in, tid));
 }
-OMC_KERNEL(k_advance, EvArgs, body_advance)
+OMC_KERNEL_GEO(k_advance, EvArgs, body_advance)
 
 // calculate-xs and advance events of the same work list in one pass: every
 // alive particle goes through both in every sweep, so unless the xs list is to be
@@ -836,8 +855,8 @@ OMC_D void body_xs_advance(int64_t tid, const EvArgs& a)
   ev_xs<BX>(a.ps, i, a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_OTHER : nullptr);
   advance_and_route(tid, a, i);
 }
-OMC_KERNEL_MB(k_xs_advance, EvArgs, body_xs_advance<false>, XA_MINBLOCKS)
-OMC_KERNEL_MB(k_xs_advance_b, EvArgs, body_xs_advance<true>, 2)
+OMC_KERNEL_MB_GEO(k_xs_advance, EvArgs, body_xs_advance<false>, XA_MINBLOCKS)
+OMC_KERNEL_MB_GEO(k_xs_advance_b, EvArgs, body_xs_advance<true>, 2)
 
 // Sweep mode 2 (run_sweeps_paired): a crossing or a collision is always followed,
 // for the survivor, by a cross-section lookup and a flight.  One kernel per list
@@ -862,8 +881,8 @@ OMC_D void body_surface_xa(int64_t tid, const EvArgs& a)
       a.ps.next_ev[i] = dead_flag(a.ordered);
   }
 }
-OMC_KERNEL_MB(k_surface_xa, EvArgs, body_surface_xa<false>, XA_MINBLOCKS)
-OMC_KERNEL_MB(k_surface_xa_b, EvArgs, body_surface_xa<true>, 2)
+OMC_KERNEL_MB_GEO(k_surface_xa, EvArgs, body_surface_xa<false>, XA_MINBLOCKS)
+OMC_KERNEL_MB_GEO(k_surface_xa_b, EvArgs, body_surface_xa<true>, 2)
 OMC_KERNEL_DYN(k_surface_xa_dyn, EvArgs, body_surface_xa<false>, XA_MINBLOCKS)
 
 // collision-estimator tallies of the particles on a collision list, before the collision kernel
@@ -898,8 +917,8 @@ OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
       a.ps.next_ev[i] = dead_flag(a.ordered);
   }
 }
-OMC_KERNEL_MB(k_collide_xa, EvArgs, body_collide_xa<false>, CX_MINBLOCKS)
-OMC_KERNEL_MB(k_collide_xa_b, EvArgs, body_collide_xa<true>, 2)
+OMC_KERNEL_MB_GEO(k_collide_xa, EvArgs, body_collide_xa<false>, CX_MINBLOCKS)
+OMC_KERNEL_MB_GEO(k_collide_xa_b, EvArgs, body_collide_xa<true>, 2)
 OMC_KERNEL_DYN(k_collide_xa_dyn, EvArgs, body_collide_xa<false>, CX_MINBLOCKS)
 
 
@@ -1243,7 +1262,7 @@ OMC_D void body_surface(int64_t tid, const EvArgs& a)
   else if (alive)
     queue_append(a.q_a, i);
 }
-OMC_KERNEL(k_surface, EvArgs, body_surface)
+OMC_KERNEL_GEO(k_surface, EvArgs, body_surface)
 
 template<bool BX>
 OMC_D void body_collide(int64_t tid, const EvArgs& a)
@@ -1258,8 +1277,8 @@ OMC_D void body_collide(int64_t tid, const EvArgs& a)
   else if (alive)
     queue_append(a.q_a, i);
 }
-OMC_KERNEL_MB(k_collide, EvArgs, body_collide<false>, CX_MINBLOCKS)
-OMC_KERNEL_MB(k_collide_b, EvArgs, body_collide<true>, 2)
+OMC_KERNEL_MB_GEO(k_collide, EvArgs, body_collide<false>, CX_MINBLOCKS)
+OMC_KERNEL_MB_GEO(k_collide_b, EvArgs, body_collide<true>, 2)
 
 // The tail of a generation (few particles left, launch-latency bound): one
 // thread runs the remaining events of one history to completion with the very
@@ -1301,7 +1320,7 @@ OMC_D void body_tail(int64_t tid, const EvArgs& a)
   atomic_add_u64(a.gc.counters + 2, n_coll);
   atomic_add_u64(a.gc.counters + 3, n_cross);
 }
-OMC_KERNEL(k_tail, EvArgs, body_tail)
+OMC_KERNEL_GEO(k_tail, EvArgs, body_tail)
 // few, long-running threads: small blocks spread them over all SMs
 constexpr int TAIL_BLOCK = 64;
 #if OMC_CUDA
@@ -1309,7 +1328,8 @@ constexpr int TAIL_BLOCK = 64;
   do { \
     (args).xs_batch_min = tail_batch_min(); \
     if ((n_ub) > 0) { \
-      k_tail<<<(unsigned)(((n_ub) + TAIL_BLOCK - 1) / TAIL_BLOCK), TAIL_BLOCK, 0, stream>>>((int64_t)(n_ub), args); \
+      k_tail<<<(unsigned)(((n_ub) + TAIL_BLOCK - 1) / TAIL_BLOCK), TAIL_BLOCK, geo_smem_bytes(), stream>>>((int64_t)(n_ub), \
+        args); \
       ++g_launches; \
     } \
   } while (0)
@@ -1523,7 +1543,7 @@ OMC_D void body_probe_xs(int64_t tid, const XsArgs& a)
   } else {
     const int G = DM.mg_n_groups;
     const int g = (int)a.E[tid];
-    const int ba = mg_ba(m, mg_temperature_index(m, ld(DM.cell_sqrtkT)), 0);
+    const int ba = mg_ba(m, mg_temperature_index(m, gld(DM.cell_sqrtkT)), 0);
     t = ld(DM.mg_total + ba * G + g);
     ab = ld(DM.mg_absorption + ba * G + g);
     nf = ld(DM.mgm_fissionable + m) ? ld(DM.mg_nu_fission + ba * G + g) : 0.;
@@ -1660,7 +1680,7 @@ OMC_D void body_probe_geom(int64_t tid, const GeoArgs& a)
     }
   }
 }
-OMC_KERNEL(k_probe_geom, GeoArgs, body_probe_geom)
+OMC_KERNEL_GEO(k_probe_geom, GeoArgs, body_probe_geom)
 
 struct RngArgs {
   const uint64_t* n;
@@ -1743,6 +1763,9 @@ struct Engine {
   std::vector<int64_t> tally_ofs; // host copy of tally_result_ofs
   int n_cell_sqrtkT = 0, n_mat_nuclides = 0; // array lengths omcgpu_update checks
   int n_collision_tallies = 0;
+  const char* geo_blob = nullptr; // CSG tables in one block (device.h, gld)
+  size_t geo_bytes = 0;
+  unsigned geo_smem = 0;        // bytes of it the geometry kernels stage in shared memory
   int tally_replicas = 1;       // copies of the VALUE arrays k_score spreads its REDs over
   int64_t tally_stride = 0;
   cudaStream_t stream = 0;
@@ -1782,6 +1805,10 @@ struct Engine {
   int64_t generation_no = 0;
 };
 static Engine G;
+static unsigned geo_smem_bytes()
+{
+  return G.geo_smem;
+}
 static bool batch_xs_enabled()
 {
   return G.batch_xs;
@@ -1807,14 +1834,14 @@ static int tail_batch_min()
 // allocation so that ONE access-policy window can ask L2 to keep them resident while
 // particle state and flight records stream through (OMCGPU_L2_PERSIST=1).
 static char* g_arena = nullptr;
-static size_t g_arena_size = 0, g_arena_used = 0;
+static size_t g_arena_size = 0, g_arena_used = 0, g_arena_align = 256;
 static bool g_arena_on = false;
 
 template<class T>
 static int dev_alloc(T** p, size_t count)
 {
   if (g_arena_on) {
-    const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) / 256 * 256;
+    const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + g_arena_align - 1) / g_arena_align * g_arena_align;
     if (g_arena_used + bytes <= g_arena_size) {
       *p = reinterpret_cast<T*>(g_arena + g_arena_used);
       cudaMemset(*p, 0, bytes);
@@ -1889,6 +1916,20 @@ static int upload_model(const omcgpu_model* m)
   const int nm = h.n_materials;
   int rc = 0;
 #define UP(field, count) rc = rc ? rc : upload(&h.field, (size_t)(count))
+  // the CSG tables go into one block, hottest first: the kernels that walk the geometry stage its
+  // first OMCGPU_GEO_SMEM bytes (default 24 KB, 0 = off) in shared memory (device.h, gld)
+  {
+    g_arena_size = 1 << 20; // tables beyond this fall back to their own allocations (read from global memory)
+    g_arena_used = 0;
+    g_arena_align = 16;
+    void* q = nullptr;
+    if (cudaMalloc(&q, g_arena_size) != cudaSuccess)
+      return fail(OMCGPU_E_ALLOCATE, "cudaMalloc of the geometry block failed%s");
+    G.dev_allocs.push_back(q);
+    g_arena = static_cast<char*>(q);
+    g_arena_on = true;
+    G.geo_blob = g_arena;
+  }
   UP(surf_type, ns);
   UP(surf_bc, ns);
   UP(surf_periodic, ns);
@@ -1956,6 +1997,18 @@ static int upload_model(const omcgpu_model* m)
   UP(lat_universes, n_lu);
   UP(lat_offset_ofs, nl + 1);
   UP(lat_offsets, n_lo);
+  {
+    g_arena_on = false;
+    g_arena_align = 256;
+    G.geo_bytes = g_arena_used;
+    size_t budget = 24576;
+    if (const char* t = std::getenv("OMCGPU_GEO_SMEM"))
+      budget = (size_t)std::max(0, std::atoi(t));
+    G.geo_smem = (unsigned)(std::min(G.geo_bytes, budget) / 16 * 16);
+#if OMC_CUDA
+    CUDA_OK(cudaMemcpyToSymbol(c_geo_blob, &G.geo_blob, sizeof(char*)));
+#endif
+  }
   const int n_mn = nm ? m->mat_nuc_ofs[nm] : 0;
   UP(mat_id, nm);
   UP(mat_fissionable, nm);
