@@ -464,6 +464,20 @@ def main():
     r = measure(args, args.workload, args.particles, args.steps, args.warmup, rank, local_rank, world, comm,
                 not args.no_e2e, peak, peaks)
 
+    # ---- strong-scaling point (N > 1): the SAME global generation as the N = 1 line (--particles
+    # histories in total, --particles / N per GPU) through the same NCCL path
+    strong = None
+    if world > 1 and not args.no_other_configs:
+        try:
+            o = measure(args, args.workload, max(args.particles // world, 1), 3, 3, rank, local_rank, world, comm,
+                        False, peak, peaks)
+            strong = {"value": o["value"], "unit": "particles/s", "ms_per_step": o["ms_per_step"],
+                      "device_ms_per_step": o["device_ms_per_step"], "global_particles_per_generation": o["n_global"],
+                      "particles_per_generation_per_gpu": o["n_local"], "steps": 3, "warmup": 3,
+                      "note": "fixed total work: the N = 1 generation split over N GPUs"}
+        except Exception as exc:
+            strong = {"error": repr(exc)[:300]}
+
     # ---- the other configurations of BASELINE.json (N = 1 only): C5 is the only one whose tables
     # (1.8 GB) do not fit L2, i.e. the HBM-gather case of north_star
     others = {}
@@ -514,7 +528,7 @@ def main():
             "events_per_particle": r["events_per_particle"],
             "k_combined": r["k_combined"], "n_lost": r["n_lost"],
             "gpu_launches": r["gpu_launches"], "clocks": r["clocks"], "e2e": r["e2e"], "roofline": r["roofline"],
-            "cpu_baseline": cpu, "other_configs": others or None, "dropin": dropin,
+            "cpu_baseline": cpu, "other_configs": others or None, "dropin": dropin, "strong_scaling": strong,
         }
         print(json.dumps(line))
 

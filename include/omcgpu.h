@@ -72,6 +72,7 @@ extern "C" {
 #define OMCGPU_BC_VACUUM      1
 #define OMCGPU_BC_REFLECTIVE  2
 #define OMCGPU_BC_PERIODIC    3   /* translational, between two planes (src/boundary_condition.cpp:66-155) */
+#define OMCGPU_BC_WHITE       4   /* cosine-distributed diffuse reflection (WhiteBC :53-62, Surface::diffuse_reflect src/surface.cpp:142-161) */
 
 /* cell fill: include/openmc/cell.h Fill enum */
 #define OMCGPU_FILL_MATERIAL  0

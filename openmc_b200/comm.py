@@ -169,12 +169,16 @@ class NativeComm:
 
     @classmethod
     def over_nccl(cls, rank, size, store, key="omcgpu_nccl_id"):
+        joined = [0]      # a communicator per engine: every attach publishes its id under its own key
+
         def connect(engine):
+            k = "%s_%d" % (key, joined[0])
+            joined[0] += 1
             if rank == 0:
                 uid = engine.comm_unique_id()
-                store.set(key, uid)
+                store.set(k, uid)
             else:
-                uid = bytes(store.get(key))
+                uid = bytes(store.get(k))
             engine.comm_init(uid, rank, size)
         return cls(rank, size, connect)
 

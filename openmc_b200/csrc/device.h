@@ -57,7 +57,17 @@ OMC_HD uint32_t geo_staged_bytes()
 template<class T>
 OMC_HD T gld(const T* p)
 {
-#if OMC_CUDA && defined(__CUDA_ARCH__)
+#if OMC_CUDA && defined(__CUDA_ARCH__) && defined(OMC_GEO_ALWAYS)
+  // measurement build: the geometry pointers of c_dm are offsets into the staged block
+  return *reinterpret_cast<const T*>(g_geo_smem + (uint32_t)reinterpret_cast<uintptr_t>(p));
+#elif OMC_CUDA && defined(__CUDA_ARCH__) && defined(OMC_GEO_NEVER)
+  return __ldg(p);
+#elif OMC_CUDA && defined(__CUDA_ARCH__) && defined(OMC_GEO_GENERIC)
+  // the geometry pointers of c_dm are offsets into the block; one generic base per kernel: the
+  // block's shared-memory copy when the launch staged it, else the block itself in global memory
+  const char* base = geo_staged_bytes() ? reinterpret_cast<const char*>(g_geo_smem) : c_geo_blob;
+  return *reinterpret_cast<const T*>(base + reinterpret_cast<uintptr_t>(p));
+#elif OMC_CUDA && defined(__CUDA_ARCH__)
   const uint64_t off = (uint64_t)(reinterpret_cast<const char*>(p) - c_geo_blob);
   if (off < (uint64_t)geo_staged_bytes())
     return *reinterpret_cast<const T*>(g_geo_smem + off);
@@ -375,6 +385,19 @@ OMC_HD double surf_distance(int s, V3 r, V3 u, bool coincident)
   default:
     return cone_distance(r.z - c2, r.x - c0, r.y - c1, u.z, u.x, u.y, c3, coincident);
   }
+}
+
+// Surface::diffuse_reflect, src/surface.cpp:142-161: cosine-distributed direction about the
+// surface normal n (not normalised on entry), on the side the particle came from
+OMC_OOL V3 diffuse_reflect(V3 n, V3 u, uint64_t& seed)
+{
+  const double nn = sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
+  n = v3(n.x / nn, n.y / nn, n.z / nn);
+  const double projection = dot(n, u);
+  const double mu = (projection >= 0.0) ? -sqrt(prn(seed)) : sqrt(prn(seed));
+  V3 d = rotate_angle(n, mu, seed);
+  const double dn = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+  return v3(d.x / dn, d.y / dn, d.z / dn);
 }
 
 // =============================================================================

@@ -591,17 +591,21 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
         if (!find_cell_from(ps, i, 1, surface))
           mark_lost(ps, gc, i);
       }
-    } else if (bc == OMCGPU_BC_REFLECTIVE) {
+    } else if (bc == OMCGPU_BC_REFLECTIVE || bc == OMCGPU_BC_WHITE) {
       if (n_coord != 1) {
         mark_lost(ps, gc, i);
       } else {
         const V3 r = get_r(ps, i, 0);
         V3 u = get_u(ps, i, 0);
         V3 n = surf_normal(s, r); // Position::reflect, include/openmc/position.h:207-213
-        const double projection = dot(n, u);
-        const double magnitude = dot(n, n);
-        const double f = 2.0 * projection / magnitude;
-        u = v3(u.x - n.x * f, u.y - n.y * f, u.z - n.z * f);
+        if (bc == OMCGPU_BC_WHITE) {
+          u = diffuse_reflect(n, u, ps.seed[i]); // WhiteBC::handle_particle, src/boundary_condition.cpp:53-62
+        } else {
+          const double projection = dot(n, u);
+          const double magnitude = dot(n, n);
+          const double f = 2.0 * projection / magnitude;
+          u = v3(u.x - n.x * f, u.y - n.y * f, u.z - n.z * f);
+        }
         const double nrm = sqrt(u.x * u.x + u.y * u.y + u.z * u.z);
         u = v3(u.x / nrm, u.y / nrm, u.z / nrm);
         set_u(ps, i, 0, u);
@@ -2191,7 +2195,33 @@ static int upload_model(const omcgpu_model* m)
   if (rc)
     return rc;
 #if OMC_CUDA
+#if defined(OMC_GEO_ALWAYS) || defined(OMC_GEO_GENERIC)
+  { // (device.h, gld): geometry pointers become offsets into the geometry block
+#if defined(OMC_GEO_ALWAYS)
+    if (G.geo_smem < G.geo_bytes)
+      return fail(OMCGPU_E_UNSUPPORTED, "OMC_GEO_ALWAYS build: the geometry block does not fit the shared-memory budget%s");
+#else
+    if (G.geo_smem < G.geo_bytes)
+      G.geo_smem = 0; // all or nothing: a block larger than the budget is read from global memory
+    if (G.geo_bytes >= g_arena_size)
+      return fail(OMCGPU_E_UNSUPPORTED, "geometry tables larger than the geometry block (1 MB)%s");
+#endif
+    omcgpu_model hd = h;
+#define REBASE(field) hd.field = reinterpret_cast<decltype(hd.field)>(reinterpret_cast<const char*>(h.field) - G.geo_blob)
+    REBASE(surf_type); REBASE(surf_bc); REBASE(surf_periodic); REBASE(surf_periodic_shift); REBASE(surf_id);
+    REBASE(surf_coef); REBASE(cell_id); REBASE(cell_type); REBASE(cell_universe); REBASE(cell_fill);
+    REBASE(cell_simple); REBASE(cell_region_ofs); REBASE(region_tokens); REBASE(cell_mat_ofs); REBASE(cell_material);
+    REBASE(cell_sqrtkT_ofs); REBASE(cell_sqrtkT); REBASE(cell_translation); REBASE(cell_rotated); REBASE(cell_rotation);
+    REBASE(cell_distribcell_index); REBASE(cell_offset_ofs); REBASE(cell_offset); REBASE(univ_cell_ofs);
+    REBASE(univ_cells); REBASE(tok_cell_ofs); REBASE(tok_cells); REBASE(lat_shape); REBASE(lat_is3d); REBASE(lat_outer);
+    REBASE(lat_pitch); REBASE(lat_lower_left); REBASE(lat_univ_ofs); REBASE(lat_universes); REBASE(lat_offset_ofs);
+    REBASE(lat_offsets);
+#undef REBASE
+    CUDA_OK(cudaMemcpyToSymbol(c_dm, &hd, sizeof(omcgpu_model)));
+  }
+#else
   CUDA_OK(cudaMemcpyToSymbol(c_dm, &h, sizeof(omcgpu_model)));
+#endif
 #else
   c_dm = h;
 #endif
@@ -2205,7 +2235,7 @@ static int check_supported(const omcgpu_model* m)
   for (int s = 0; s < m->n_surfaces; ++s) {
     if (m->surf_type[s] < 0 || m->surf_type[s] > OMCGPU_SURF_ZCONE)
       return fail(OMCGPU_E_UNSUPPORTED, "surface type not supported on the device%s");
-    if (m->surf_bc[s] < 0 || m->surf_bc[s] > OMCGPU_BC_PERIODIC)
+    if (m->surf_bc[s] < 0 || m->surf_bc[s] > OMCGPU_BC_WHITE)
       return fail(OMCGPU_E_UNSUPPORTED, "boundary condition not supported on the device%s");
     if (m->surf_bc[s] == OMCGPU_BC_PERIODIC &&
         (m->surf_type[s] > OMCGPU_SURF_PLANE || m->surf_periodic[s] < 0 || m->surf_periodic[s] >= m->n_surfaces))

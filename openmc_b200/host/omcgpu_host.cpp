@@ -218,6 +218,8 @@ void flatten_surfaces(Flat& F)
       bc[i] = OMCGPU_BC_VACUUM;
     } else if (dynamic_cast<const ReflectiveBC*>(b)) {
       bc[i] = OMCGPU_BC_REFLECTIVE;
+    } else if (dynamic_cast<const WhiteBC*>(b)) {
+      bc[i] = OMCGPU_BC_WHITE;
     } else if (auto p = dynamic_cast<const TranslationalPeriodicBC*>(b)) {
       // handle_particle (src/boundary_condition.cpp:101-127): + translation_ when the first
       // surface of the pair is struck, - translation_ on the second
@@ -227,7 +229,7 @@ void flatten_surfaces(Flat& F)
       for (int k = 0; k < 3; ++k)
         shift[3 * i + k] = first ? p->translation_[k] : -p->translation_[k];
     } else {
-      unsupported(fmt::format("the boundary condition of surface {} (white / rotational periodic)", s->id_));
+      unsupported(fmt::format("the boundary condition of surface {} (rotational periodic)", s->id_));
     }
   }
   F.m.n_surfaces = ns;

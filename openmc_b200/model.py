@@ -40,7 +40,8 @@ _SURF_KINDS = {
     "z-cone": (abi.OMCGPU_SURF_ZCONE, 4),
 }
 _BCS = {"transmission": abi.OMCGPU_BC_NONE, "vacuum": abi.OMCGPU_BC_VACUUM,
-        "reflective": abi.OMCGPU_BC_REFLECTIVE, "periodic": abi.OMCGPU_BC_PERIODIC}
+        "reflective": abi.OMCGPU_BC_REFLECTIVE, "periodic": abi.OMCGPU_BC_PERIODIC,
+        "white": abi.OMCGPU_BC_WHITE}
 _SCORES = {"flux": abi.OMCGPU_SCORE_FLUX, "total": abi.OMCGPU_SCORE_TOTAL,
            "absorption": abi.OMCGPU_SCORE_ABSORPTION, "fission": abi.OMCGPU_SCORE_FISSION,
            "nu-fission": abi.OMCGPU_SCORE_NU_FISSION, "scatter": abi.OMCGPU_SCORE_SCATTER}

@@ -2047,13 +2047,21 @@ void cross_surface(Particle& p)
       mark_as_lost(p, "Couldn't find particle after hitting periodic boundary");
     return;
   }
-  if (bc == OMCGPU_BC_REFLECTIVE) { // ReflectiveBC + cross_reflective_bc :657-710
+  if (bc == OMCGPU_BC_REFLECTIVE || bc == OMCGPU_BC_WHITE) { // ReflectiveBC / WhiteBC + cross_reflective_bc :657-710
     Vec3 n = surf_normal(s, p.r());
     Vec3 u = p.u();
-    const double projection = dot(n, u);
-    const double magnitude = dot(n, n);
-    n = n * (2.0 * projection / magnitude);
-    u = u - n;
+    if (bc == OMCGPU_BC_WHITE) { // Surface::diffuse_reflect, src/surface.cpp:142-161
+      n = n / norm(n);
+      const double projection = dot(n, u);
+      const double mu = (projection >= 0.0) ? -std::sqrt(prn(p.current_seed())) : std::sqrt(prn(p.current_seed()));
+      u = rotate_angle(n, mu, nullptr, p.current_seed());
+      u = u / norm(u);
+    } else {
+      const double projection = dot(n, u);
+      const double magnitude = dot(n, n);
+      n = n * (2.0 * projection / magnitude);
+      u = u - n;
+    }
     u = u / norm(u);
     if (p.n_coord != 1) {
       mark_as_lost(p, "Cannot reflect particle off surface in a lower universe.");

@@ -23,6 +23,7 @@ RUNS = {
     "surface_zoo": (1000, 6, 2),          # every surface kind, union / complement regions
     "rotated_fills": (1000, 6, 2),
     "periodic_box": (1000, 6, 2),
+    "white_pincell": (1000, 6, 2),         # C1 pin cell with white (diffuse) boundaries
 }
 _CACHE = {}
 
@@ -60,6 +61,12 @@ def build(name):
         ce = False
     elif name == "c5g7_core":
         m, lib, box, of = examples.c5g7_core(mesh_dim=51)
+        ce = False
+    elif name == "white_pincell":
+        m, lib, box, of = examples.pincell_multigroup(mesh_dim=6, energy_bins=8)
+        for s in m.surfaces:
+            if s.boundary == "reflective":
+                s.boundary = "white"
         ce = False
     else:
         m, lib, box, of = getattr(examples, name)()

@@ -104,15 +104,16 @@ def test_switch_off_is_the_reference(dropin):
 
 
 def test_refused_model_is_a_fatal_error(dropin):
-    """a white boundary condition: the device path refuses it, the run ends with the reference's
+    """a boundary with an albedo: the device path refuses it, the run ends with the reference's
     ' ERROR: ' convention (src/error.cpp:113-140) instead of silently using the CPU"""
     m, lib, model, box, of, ce = rr.build("pincell_mg")
-    import copy
-    m2 = copy.deepcopy(m)
-    next(s for s in m2.surfaces if s.boundary == "reflective").boundary = "white"
     d = tempfile.mkdtemp(prefix="omc_dropin_")
     try:
-        rr.write_inputs(d, m2, lib, box, of, ce, 200, 3, 1)
+        rr.write_inputs(d, m, lib, box, of, ce, 200, 3, 1)
+        path = os.path.join(d, "model.xml")
+        xml = open(path).read()
+        assert 'boundary="reflective"' in xml
+        open(path, "w").write(xml.replace('boundary="reflective"', 'boundary="reflective" albedo="0.9"', 1))
         res = _run(d, dropin)
         assert res.returncode != 0
         assert "ERROR" in res.stderr and "not supported by the device path" in res.stderr.replace("\n", " ").replace("  ", " ")
