@@ -65,7 +65,8 @@ extern "C" {
 #define OMCGPU_SURF_XCONE     8   /* coef: x0 y0 z0 r^2  (src/surface.cpp:688-742) */
 #define OMCGPU_SURF_YCONE     9
 #define OMCGPU_SURF_ZCONE     10
-#define OMCGPU_SURF_NCOEF     4   /* doubles stored per surface */
+#define OMCGPU_SURF_QUADRIC   11  /* coef: A B C D E F G H J K  (src/surface.cpp:855-949) */
+#define OMCGPU_SURF_NCOEF     10  /* doubles stored per surface */
 
 /* boundary conditions: src/boundary_condition.cpp:18-62 */
 #define OMCGPU_BC_NONE        0   /* transmission */

@@ -34,14 +34,16 @@ OMC_HD T ld(const T* p)
 
 // ---- CSG tables staged in shared memory ---------------------------------------------------------
 // Surfaces, region tokens, cells, universes' cell lists, half-space candidate lists and lattices
-// are uploaded into ONE block of device memory (the geometry blob: a few KB for the configurations
-// of BASELINE.json).  Kernels that walk the geometry are launched with the blob's size (up to a
-// budget) as dynamic shared memory and copy it there once per block (stage_geometry); every read
-// of a geometry table then goes through gld(): an address inside the staged part of the blob is
-// served from the block's copy, anything else (a model larger than the budget, a kernel launched
-// without dynamic shared memory) from global memory.  The event kernels stream ~1 KB of particle
-// state per event through L1, which keeps evicting the geometry lines every lane needs again a
-// moment later; the block's copy cannot be evicted.
+// are uploaded into ONE block of device memory (the geometry block: a few KB for the configurations
+// of BASELINE.json), and the geometry pointers of c_dm hold OFFSETS into it.  Kernels that walk the
+// geometry are launched with the block's size as dynamic shared memory and copy it there once per
+// thread block (stage_geometry); every read of a geometry table goes through gld(): base + offset,
+// where the base is the thread block's shared-memory copy when the launch staged one, else the
+// block itself in global memory (a geometry larger than the budget OMCGPU_GEO_SMEM, kernels
+// launched without dynamic shared memory such as k_score).  One generic base, no per-access test.
+// Measured (profiles/r52-r54, README): C2 unchanged, C3 / C4 1-3 % slower than plain __ldg loads,
+// an LDS-only build (no global fallback, -DOMC_GEO_ALWAYS) 1-2 % faster: the geometry tables are
+// L1 hits either way and not what bounds the event kernels.
 #if OMC_CUDA
 __constant__ const char* c_geo_blob;
 #if defined(__CUDA_ARCH__)
@@ -58,20 +60,13 @@ template<class T>
 OMC_HD T gld(const T* p)
 {
 #if OMC_CUDA && defined(__CUDA_ARCH__) && defined(OMC_GEO_ALWAYS)
-  // measurement build: the geometry pointers of c_dm are offsets into the staged block
+  // measurement build: shared memory only (omcgpu_init refuses geometries beyond the budget)
   return *reinterpret_cast<const T*>(g_geo_smem + (uint32_t)reinterpret_cast<uintptr_t>(p));
 #elif OMC_CUDA && defined(__CUDA_ARCH__) && defined(OMC_GEO_NEVER)
-  return __ldg(p);
-#elif OMC_CUDA && defined(__CUDA_ARCH__) && defined(OMC_GEO_GENERIC)
-  // the geometry pointers of c_dm are offsets into the block; one generic base per kernel: the
-  // block's shared-memory copy when the launch staged it, else the block itself in global memory
+  return __ldg(p); // measurement build: real pointers, global memory only
+#elif OMC_CUDA && defined(__CUDA_ARCH__)
   const char* base = geo_staged_bytes() ? reinterpret_cast<const char*>(g_geo_smem) : c_geo_blob;
   return *reinterpret_cast<const T*>(base + reinterpret_cast<uintptr_t>(p));
-#elif OMC_CUDA && defined(__CUDA_ARCH__)
-  const uint64_t off = (uint64_t)(reinterpret_cast<const char*>(p) - c_geo_blob);
-  if (off < (uint64_t)geo_staged_bytes())
-    return *reinterpret_cast<const T*>(g_geo_smem + off);
-  return __ldg(p);
 #else
   return *p;
 #endif
@@ -196,6 +191,58 @@ OMC_HD double watt_spectrum(double a, double b, uint64_t& seed)
 // =============================================================================
 // Surfaces -- src/surface.cpp:116-130, 207-220, 354-375, 399-456, 598-648
 // =============================================================================
+// General quadric A x^2 + B y^2 + C z^2 + D xy + E yz + F xz + G x + H y + J z + K = 0,
+// src/surface.cpp:861-868 (evaluate), 870-939 (distance), 941-949 (normal); out of line: rare
+OMC_OOL double general_quadric_evaluate(const double* c, V3 r)
+{
+  const double A = gld(c), B = gld(c + 1), C = gld(c + 2), D = gld(c + 3), E = gld(c + 4), F = gld(c + 5),
+               G = gld(c + 6), H = gld(c + 7), J = gld(c + 8), K = gld(c + 9);
+  const double x = r.x, y = r.y, z = r.z;
+  return x * (A * x + D * y + G) + y * (B * y + E * z + H) + z * (C * z + F * x + J) + K;
+}
+OMC_OOL double general_quadric_distance(const double* c, V3 r, V3 ang, bool coincident)
+{
+  const double A = gld(c), B = gld(c + 1), C = gld(c + 2), D = gld(c + 3), E = gld(c + 4), F = gld(c + 5),
+               G = gld(c + 6), H = gld(c + 7), J = gld(c + 8), K = gld(c + 9);
+  const double x = r.x, y = r.y, z = r.z, u = ang.x, v = ang.y, w = ang.z;
+  const double a = A * u * u + B * v * v + C * w * w + D * u * v + E * v * w + F * u * w;
+  const double k = A * u * x + B * v * y + C * w * z +
+                   0.5 * (D * (u * y + v * x) + E * (v * z + w * y) + F * (w * x + u * z) + G * u + H * v + J * w);
+  const double cc = A * x * x + B * y * y + C * z * z + D * x * y + E * y * z + F * x * z + G * x + H * y + J * z + K;
+  double quad = k * k - a * cc;
+  double d;
+  if (quad < 0.0) {
+    return INFTY;
+  } else if (coincident || fabs(cc) < FP_COINCIDENT) {
+    if (a == 0.0)
+      d = INFTY;
+    else if (k >= 0.0)
+      d = (-k - sqrt(quad)) / a;
+    else
+      d = (-k + sqrt(quad)) / a;
+  } else if (a == 0.0) {
+    d = -0.5 * cc / k;
+  } else {
+    quad = sqrt(quad);
+    d = (-k - quad) / a;
+    const double b = (-k + quad) / a;
+    if (d < 0.0) {
+      if (b > 0.0)
+        d = b;
+    } else if (b > 0.0 && b < d) {
+      d = b;
+    }
+  }
+  return d <= 0.0 ? INFTY : d;
+}
+OMC_OOL V3 general_quadric_normal(const double* c, V3 r)
+{
+  const double A = gld(c), B = gld(c + 1), C = gld(c + 2), D = gld(c + 3), E = gld(c + 4), F = gld(c + 5),
+               G = gld(c + 6), H = gld(c + 7), J = gld(c + 8);
+  return v3(2.0 * A * r.x + D * r.y + F * r.z + G, 2.0 * B * r.y + D * r.x + E * r.z + H,
+    2.0 * C * r.z + E * r.y + F * r.x + J);
+}
+
 OMC_HD double surf_evaluate(int s, V3 r)
 {
   const double* c = DM.surf_coef + OMCGPU_SURF_NCOEF * s;
@@ -233,6 +280,8 @@ OMC_HD double surf_evaluate(int s, V3 r)
     const double r1 = r.y - c1, r2 = r.x - c0, r3 = r.z - c2;
     return r2 * r2 + r3 * r3 - c3 * r1 * r1;
   }
+  case OMCGPU_SURF_QUADRIC:
+    return general_quadric_evaluate(c, r);
   default: { // z-cone
     const double r1 = r.z - c2, r2 = r.x - c0, r3 = r.y - c1;
     return r2 * r2 + r3 * r3 - c3 * r1 * r1;
@@ -264,6 +313,8 @@ OMC_HD V3 surf_normal(int s, V3 r)
     return v3(-2.0 * gld(c + 3) * (r.x - gld(c)), 2.0 * (r.y - gld(c + 1)), 2.0 * (r.z - gld(c + 2)));
   case OMCGPU_SURF_YCONE:
     return v3(2.0 * (r.x - gld(c)), -2.0 * gld(c + 3) * (r.y - gld(c + 1)), 2.0 * (r.z - gld(c + 2)));
+  case OMCGPU_SURF_QUADRIC:
+    return general_quadric_normal(c, r);
   default:
     return v3(2.0 * (r.x - gld(c)), 2.0 * (r.y - gld(c + 1)), -2.0 * gld(c + 3) * (r.z - gld(c + 2)));
   }
@@ -382,6 +433,8 @@ OMC_HD double surf_distance(int s, V3 r, V3 u, bool coincident)
     return cone_distance(r.x - c0, r.y - c1, r.z - c2, u.x, u.y, u.z, c3, coincident);
   case OMCGPU_SURF_YCONE:
     return cone_distance(r.y - c1, r.x - c0, r.z - c2, u.y, u.x, u.z, c3, coincident);
+  case OMCGPU_SURF_QUADRIC:
+    return general_quadric_distance(c, r, u, coincident);
   default:
     return cone_distance(r.z - c2, r.x - c0, r.y - c1, u.z, u.x, u.y, c3, coincident);
   }

@@ -1770,6 +1770,7 @@ struct Engine {
   const char* geo_blob = nullptr; // CSG tables in one block (device.h, gld)
   size_t geo_bytes = 0;
   unsigned geo_smem = 0;        // bytes of it the geometry kernels stage in shared memory
+  bool geo_spilled = false;     // a geometry table did not fit the block (sizing bug)
   int tally_replicas = 1;       // copies of the VALUE arrays k_score spreads its REDs over
   int64_t tally_stride = 0;
   cudaStream_t stream = 0;
@@ -1839,7 +1840,7 @@ static int tail_batch_min()
 // particle state and flight records stream through (OMCGPU_L2_PERSIST=1).
 static char* g_arena = nullptr;
 static size_t g_arena_size = 0, g_arena_used = 0, g_arena_align = 256;
-static bool g_arena_on = false;
+static bool g_arena_on = false, g_arena_spilled = false;
 
 template<class T>
 static int dev_alloc(T** p, size_t count)
@@ -1852,6 +1853,7 @@ static int dev_alloc(T** p, size_t count)
       g_arena_used += bytes;
       return 0;
     }
+    g_arena_spilled = true;
   }
   void* q = nullptr;
   cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
@@ -1923,7 +1925,16 @@ static int upload_model(const omcgpu_model* m)
   // the CSG tables go into one block, hottest first: the kernels that walk the geometry stage its
   // first OMCGPU_GEO_SMEM bytes (default 24 KB, 0 = off) in shared memory (device.h, gld)
   {
-    g_arena_size = 1 << 20; // tables beyond this fall back to their own allocations (read from global memory)
+    // upper bound of the geometry tables uploaded between here and lat_offsets (16-byte slots)
+    const size_t n_tok_ = nc ? m->cell_region_ofs[nc] : 0, n_cm_ = nc ? m->cell_mat_ofs[nc] : 0,
+                 n_kt_ = nc ? m->cell_sqrtkT_ofs[nc] : 0, n_co_ = nc ? m->cell_offset_ofs[nc] : 0,
+                 n_uc_ = nu ? m->univ_cell_ofs[nu] : 0, n_lu_ = nl ? m->lat_univ_ofs[nl] : 0,
+                 n_lo_ = nl ? m->lat_offset_ofs[nl] : 0;
+    g_arena_size = 40 * 16 + (size_t)ns * (4 * 4 + 8 * 3 + 8 * OMCGPU_SURF_NCOEF + 2 * 4) +
+                   (size_t)nc * (4 * 12 + 8 * 12) + 4 * (n_tok_ + n_cm_ + n_co_ + n_uc_ + n_lu_ + n_lo_) + 8 * n_kt_ +
+                   4 * (2 * (size_t)ns + 1) + 8 * n_tok_ + /* half-space candidate lists: <= 2 entries per token */
+                   (size_t)nu * 4 + (size_t)nl * (4 * 8 + 8 * 6) + 4096;
+    g_arena_size = (g_arena_size + 255) / 256 * 256;
     g_arena_used = 0;
     g_arena_align = 16;
     void* q = nullptr;
@@ -1932,6 +1943,7 @@ static int upload_model(const omcgpu_model* m)
     G.dev_allocs.push_back(q);
     g_arena = static_cast<char*>(q);
     g_arena_on = true;
+    g_arena_spilled = false;
     G.geo_blob = g_arena;
   }
   UP(surf_type, ns);
@@ -2005,6 +2017,7 @@ static int upload_model(const omcgpu_model* m)
     g_arena_on = false;
     g_arena_align = 256;
     G.geo_bytes = g_arena_used;
+    G.geo_spilled = g_arena_spilled;
     size_t budget = 24576;
     if (const char* t = std::getenv("OMCGPU_GEO_SMEM"))
       budget = (size_t)std::max(0, std::atoi(t));
@@ -2195,7 +2208,7 @@ static int upload_model(const omcgpu_model* m)
   if (rc)
     return rc;
 #if OMC_CUDA
-#if defined(OMC_GEO_ALWAYS) || defined(OMC_GEO_GENERIC)
+#if !defined(OMC_GEO_NEVER)
   { // (device.h, gld): geometry pointers become offsets into the geometry block
 #if defined(OMC_GEO_ALWAYS)
     if (G.geo_smem < G.geo_bytes)
@@ -2203,8 +2216,8 @@ static int upload_model(const omcgpu_model* m)
 #else
     if (G.geo_smem < G.geo_bytes)
       G.geo_smem = 0; // all or nothing: a block larger than the budget is read from global memory
-    if (G.geo_bytes >= g_arena_size)
-      return fail(OMCGPU_E_UNSUPPORTED, "geometry tables larger than the geometry block (1 MB)%s");
+    if (G.geo_spilled)
+      return fail(OMCGPU_E_ALLOCATE, "internal: the geometry block was sized too small%s");
 #endif
     omcgpu_model hd = h;
 #define REBASE(field) hd.field = reinterpret_cast<decltype(hd.field)>(reinterpret_cast<const char*>(h.field) - G.geo_blob)
@@ -2233,7 +2246,7 @@ static int check_supported(const omcgpu_model* m)
   if (m->n_coord_levels > OMCGPU_MAX_COORD)
     return fail(OMCGPU_E_UNSUPPORTED, "geometry nests deeper than OMCGPU_MAX_COORD%s");
   for (int s = 0; s < m->n_surfaces; ++s) {
-    if (m->surf_type[s] < 0 || m->surf_type[s] > OMCGPU_SURF_ZCONE)
+    if (m->surf_type[s] < 0 || m->surf_type[s] > OMCGPU_SURF_QUADRIC)
       return fail(OMCGPU_E_UNSUPPORTED, "surface type not supported on the device%s");
     if (m->surf_bc[s] < 0 || m->surf_bc[s] > OMCGPU_BC_WHITE)
       return fail(OMCGPU_E_UNSUPPORTED, "boundary condition not supported on the device%s");

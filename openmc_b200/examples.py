@@ -227,6 +227,28 @@ def surface_zoo():
     return m, c5g7_library(False), box, False
 
 
+def quadric_pin():
+    """a fuel region bounded by general quadrics (src/surface.cpp:855-949): a tilted elliptic
+    cylinder (xy cross term), cut by a paraboloid-like sheet, in a reflective box of water"""
+    m = Model()
+    fuel = m.material(name="UO2 fuel", macroscopic="UO2", units="macro", density=1.0)
+    water = m.material(name="Water", macroscopic="LWTR", units="macro", density=1.0)
+    # x^2/0.45^2 + y^2/0.3^2 + 0.8 xy - 1 = 0
+    q1 = m.surface("quadric", [1 / 0.45 ** 2, 1 / 0.3 ** 2, 0.0, 0.8, 0.0, 0.0, 0.0, 0.0, 0.0, -1.0]).id
+    # z = 0.6 (x^2 + y^2) + 0.1 x - 0.4   ->   0.6 x^2 + 0.6 y^2 + 0.1 x - z - 0.4 = 0
+    q2 = m.surface("quadric", [0.6, 0.6, 0.0, 0.0, 0.0, 0.0, 0.1, 0.0, -1.0, -0.4]).id
+    x0 = m.surface("x-plane", [-0.63], "reflective").id
+    x1 = m.surface("x-plane", [0.63], "reflective").id
+    y0 = m.surface("y-plane", [-0.63], "reflective").id
+    y1 = m.surface("y-plane", [0.63], "reflective").id
+    z0 = m.surface("z-plane", [-1.0], "reflective").id
+    z1 = m.surface("z-plane", [1.0], "reflective").id
+    box = f"{x0} -{x1} {y0} -{y1} {z0} -{z1}"
+    m.cell(region=f"-{q1} -{q2} {z0} -{z1}", fill=fuel)
+    m.cell(region=f"({q1} | {q2}) {box}", fill=water)
+    return m, c5g7_library(False), [-0.63, -0.63, -1.0, 0.63, 0.63, 1.0], True
+
+
 def periodic_box():
     """Fuel pin in a box with translational periodic boundaries in x (paired by id), in y
     (general planes with a non-unit normal; the two unpaired periodic surfaces pair up,

@@ -206,8 +206,13 @@ void flatten_surfaces(Flat& F)
       type[i] = OMCGPU_SURF_YCONE; c[0] = p->x0_; c[1] = p->y0_; c[2] = p->z0_; c[3] = p->radius_sq_;
     } else if (auto p = dynamic_cast<const SurfaceZCone*>(s)) {
       type[i] = OMCGPU_SURF_ZCONE; c[0] = p->x0_; c[1] = p->y0_; c[2] = p->z0_; c[3] = p->radius_sq_;
+    } else if (auto p = dynamic_cast<const SurfaceQuadric*>(s)) {
+      type[i] = OMCGPU_SURF_QUADRIC;
+      const double q[10] = {p->A_, p->B_, p->C_, p->D_, p->E_, p->F_, p->G_, p->H_, p->J_, p->K_};
+      for (int k = 0; k < 10; ++k)
+        c[k] = q[k];
     } else {
-      unsupported(fmt::format("surface {} (general quadric / torus / DAGMC)", s->id_));
+      unsupported(fmt::format("surface {} (torus / DAGMC)", s->id_));
     }
     const BoundaryCondition* b = s->bc_.get();
     if (!b) {

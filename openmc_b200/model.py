@@ -37,7 +37,7 @@ _SURF_KINDS = {
     "x-cylinder": (abi.OMCGPU_SURF_XCYLINDER, 3), "y-cylinder": (abi.OMCGPU_SURF_YCYLINDER, 3),
     "z-cylinder": (abi.OMCGPU_SURF_ZCYLINDER, 3), "sphere": (abi.OMCGPU_SURF_SPHERE, 4),
     "x-cone": (abi.OMCGPU_SURF_XCONE, 4), "y-cone": (abi.OMCGPU_SURF_YCONE, 4),
-    "z-cone": (abi.OMCGPU_SURF_ZCONE, 4),
+    "z-cone": (abi.OMCGPU_SURF_ZCONE, 4), "quadric": (abi.OMCGPU_SURF_QUADRIC, 10),
 }
 _BCS = {"transmission": abi.OMCGPU_BC_NONE, "vacuum": abi.OMCGPU_BC_VACUUM,
         "reflective": abi.OMCGPU_BC_REFLECTIVE, "periodic": abi.OMCGPU_BC_PERIODIC,

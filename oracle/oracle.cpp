@@ -311,6 +311,10 @@ double surf_evaluate(int s, Vec3 r)
     const double r1 = r.z - c[2], r2 = r.x - c[0], r3 = r.y - c[1];
     return r2 * r2 + r3 * r3 - c[3] * r1 * r1;
   }
+  case OMCGPU_SURF_QUADRIC: { // SurfaceQuadric::evaluate, src/surface.cpp:861-868
+    const double x = r.x, y = r.y, z = r.z;
+    return x * (c[0] * x + c[3] * y + c[6]) + y * (c[1] * y + c[4] * z + c[7]) + z * (c[2] * z + c[5] * x + c[8]) + c[9];
+  }
   }
   return 0.0;
 }
@@ -342,6 +346,9 @@ Vec3 surf_normal(int s, Vec3 r)
     return {2.0 * (r.x - c[0]), -2.0 * c[3] * (r.y - c[1]), 2.0 * (r.z - c[2])};
   case OMCGPU_SURF_ZCONE:
     return {2.0 * (r.x - c[0]), 2.0 * (r.y - c[1]), -2.0 * c[3] * (r.z - c[2])};
+  case OMCGPU_SURF_QUADRIC: // SurfaceQuadric::normal, src/surface.cpp:941-949
+    return {2.0 * c[0] * r.x + c[3] * r.y + c[5] * r.z + c[6], 2.0 * c[1] * r.y + c[3] * r.x + c[4] * r.z + c[7],
+      2.0 * c[2] * r.z + c[4] * r.y + c[5] * r.x + c[8]};
   }
   return {0, 0, 0};
 }
@@ -481,6 +488,39 @@ double surf_distance(int s, Vec3 r, Vec3 u, bool coincident)
     return cone_axis_distance(r.y - c[1], r.x - c[0], r.z - c[2], u.y, u.x, u.z, c[3], coincident);
   case OMCGPU_SURF_ZCONE:
     return cone_axis_distance(r.z - c[2], r.x - c[0], r.y - c[1], u.z, u.x, u.y, c[3], coincident);
+  case OMCGPU_SURF_QUADRIC: { // SurfaceQuadric::distance, src/surface.cpp:870-939
+    const double A = c[0], B = c[1], C = c[2], D = c[3], E = c[4], F = c[5], G = c[6], H = c[7], J = c[8], K = c[9];
+    const double x = r.x, y = r.y, z = r.z, uu = u.x, v = u.y, w = u.z;
+    const double a = A * uu * uu + B * v * v + C * w * w + D * uu * v + E * v * w + F * uu * w;
+    const double k = A * uu * x + B * v * y + C * w * z +
+                     0.5 * (D * (uu * y + v * x) + E * (v * z + w * y) + F * (w * x + uu * z) + G * uu + H * v + J * w);
+    const double cc = A * x * x + B * y * y + C * z * z + D * x * y + E * y * z + F * x * z + G * x + H * y + J * z + K;
+    double quad = k * k - a * cc;
+    double d;
+    if (quad < 0.0) {
+      return INFTY;
+    } else if (coincident || std::abs(cc) < FP_COINCIDENT) {
+      if (a == 0.0)
+        d = INFTY;
+      else if (k >= 0.0)
+        d = (-k - std::sqrt(quad)) / a;
+      else
+        d = (-k + std::sqrt(quad)) / a;
+    } else if (a == 0.0) {
+      d = -0.5 * cc / k;
+    } else {
+      quad = std::sqrt(quad);
+      d = (-k - quad) / a;
+      const double b = (-k + quad) / a;
+      if (d < 0.0) {
+        if (b > 0.0)
+          d = b;
+      } else if (b > 0.0 && b < d) {
+        d = b;
+      }
+    }
+    return d <= 0.0 ? INFTY : d;
+  }
   }
   return INFTY;
 }

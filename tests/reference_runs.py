@@ -24,6 +24,7 @@ RUNS = {
     "rotated_fills": (1000, 6, 2),
     "periodic_box": (1000, 6, 2),
     "white_pincell": (1000, 6, 2),         # C1 pin cell with white (diffuse) boundaries
+    "quadric_pin": (1000, 6, 2),           # general quadric surfaces
 }
 _CACHE = {}
 
