@@ -1,14 +1,15 @@
 #!/usr/bin/env python
-"""profiles/traffic.json from `ncu --set full` captures of bench.py's in-loop kernels.
+"""profiles/traffic.json from an `ncu --set full` capture of bench.py's in-loop kernels.
 
-    python profiles/ncu_traffic.py <workload> <report.ncu-rep> <trace file> <first launch skipped (-s)> [digest name]
+    python profiles/ncu_traffic.py <workload> <report.ncu-rep> <trace file> <generation> <sweep> [digest name]
 
-The capture is taken with `-k regex:'k_surface_xa|k_collide_xa|k_score' -s S -c C` while the engine
-writes OMCGPU_TRACE (one line per sweep: generation, sweep, collisions, crossings).  Launches of the
-three kernels come in a fixed order per sweep (crossing, collision, score of the crossing list's
-flights, score of the collision list's flights -- the scoring pair of a sweep runs during the next
-one), so the S-th matching launch is mapped to its list length through the trace, and DRAM bytes
-are reported PER LIST ITEM; bench.py scales them to its average launch.
+The capture holds the four launches of ONE sweep of the paired event loop (k_surface_xa,
+k_collide_xa and the two k_score launches that score the PREVIOUS sweep's flights), taken with
+`-k regex:'k_surface_xa|k_collide_xa|k_score' -s S -c 4`, S computed from the launch list so that it
+is the first launch of sweep <sweep> of generation <generation> (profiles/exp_r56.sh).  The engine
+writes OMCGPU_TRACE (one line per sweep: generation, sweep, collisions, crossings), so the list
+length of every captured launch is known and DRAM bytes are reported PER LIST ITEM; bench.py scales
+them to its average launch (`roofline.kernels.*.traffic`).
 """
 import csv
 import io
@@ -21,56 +22,74 @@ import sys
 def rows_of(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr, data = rows[0], rows[2:]
-    return hdr, data
+    return rows[0], rows[2:]
+
+
+def num(x):
+    return float(x.replace(",", ""))
 
 
 def main():
-    workload, rep, trace = sys.argv[1], sys.argv[2], sys.argv[3]
-    source = sys.argv[4] if len(sys.argv) > 4 else os.path.basename(rep)
+    workload, rep, trace, gen, sweep = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5])
+    source = sys.argv[6] if len(sys.argv) > 6 else os.path.basename(rep)
     hdr, data = rows_of(rep)
     col = {h: i for i, h in enumerate(hdr)}
-    sweeps = [tuple(int(x) for x in ln.split()) for ln in open(trace) if ln.strip()]
-    out = {}
+    counts = {}
+    for ln in open(trace):
+        p = ln.split()
+        if len(p) >= 4:
+            counts[(int(p[0]), int(p[1]))] = (int(p[2]), int(p[3]))     # collisions, crossings
+    n_coll, n_surf = counts[(gen, sweep)]
+    p_coll, p_surf = counts[(gen, sweep - 1)]
+    result = {}
+    scores = []
     for d in data:
         name = d[col["Kernel Name"]]
-        key = next((k for k in ("k_surface_xa", "k_collide_xa", "k_score", "k_xs", "k_collide", "k_surface")
-                    if k in name), None)
-        if key is None:
-            continue
-        grid = int(d[col["launch__grid_size"]].replace(",", ""))
-        rd = float(d[col["dram__bytes_read.sum"]].replace(",", ""))
-        wr = float(d[col["dram__bytes_write.sum"]].replace(",", ""))
-        unit_r = 1.0
-        e = out.setdefault(key, {"launches": []})
-        e["launches"].append({
-            "grid": grid, "dram_bytes": (rd + wr) * unit_r,
-            "duration_us": float(d[col["gpu__time_duration.sum"]].replace(",", "")),
-            "l2_hit_pct": float(d[col["lts__t_sector_hit_rate.pct"]].replace(",", "")),
-            "lanes_active": float(d[col["smsp__thread_inst_executed_per_inst_executed.ratio"]].replace(",", "")),
-            "dram_pct_of_peak": float(d[col["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]].replace(",", "")),
-            "long_scoreboard_per_issue": float(
-                d[col["smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]].replace(",", "")),
-        })
-    # list items of a captured launch: every kernel is launched over the host's last-known upper
-    # bound (grid * 256) but processes the device count; the trace gives the counts of the sweeps
-    # of that generation -- the captured launch is matched by the closest upper bound
-    result = {}
-    for key, e in out.items():
-        best = e["launches"][len(e["launches"]) // 2]
-        result[key] = dict(best)
-        result[key]["source"] = source
+        e = {"grid": int(num(d[col["launch__grid_size"]])),
+             "dram_bytes": num(d[col["dram__bytes_read.sum"]]) + num(d[col["dram__bytes_write.sum"]]),
+             "duration_us": num(d[col["gpu__time_duration.sum"]]),
+             "l2_hit_pct": num(d[col["lts__t_sector_hit_rate.pct"]]),
+             "l1_hit_pct": num(d[col["l1tex__t_sector_hit_rate.pct"]]),
+             "lanes_active": num(d[col["smsp__thread_inst_executed_per_inst_executed.ratio"]]),
+             "dram_pct_of_peak": num(d[col["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]]),
+             "warps_active_pct": num(d[col["sm__warps_active.avg.pct_of_peak_sustained_active"]]),
+             "issue_active_pct": num(d[col["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
+             "long_scoreboard_per_issue": num(
+                 d[col["smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]]),
+             "source": source, "generation": gen, "sweep": sweep}
+        if "k_surface_xa" in name:
+            e["items"] = n_surf
+            result["k_surface_xa"] = e
+        elif "k_collide_xa" in name:
+            e["items"] = n_coll
+            result["k_collide_xa"] = e
+        elif "k_score" in name:
+            scores.append(e)
+    if scores:       # the larger launch scores the crossing list's flights, the other the collision list's
+        scores.sort(key=lambda e: -e["duration_us"])
+        scores[0]["items"] = p_surf
+        if len(scores) > 1:
+            scores[1]["items"] = p_coll
+        tot = {"dram_bytes": sum(s["dram_bytes"] for s in scores), "items": sum(s["items"] for s in scores),
+               "duration_us": sum(s["duration_us"] for s in scores), "l2_hit_pct": scores[0]["l2_hit_pct"],
+               "lanes_active": scores[0]["lanes_active"], "source": source, "generation": gen, "sweep": sweep - 1,
+               "launches": scores}
+        result["k_score"] = tot
+    for e in result.values():
+        e["dram_bytes_per_item"] = e["dram_bytes"] / max(e["items"], 1)
     json_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")
     try:
         allj = json.load(open(json_path))
     except Exception:
         allj = {}
-    allj[workload] = result
-    allj["_comment"] = ("per kernel: one mid-generation launch from an ncu --set full capture of bench.py; "
-                        "`items` (list length of that launch) is filled in from the OMCGPU_TRACE file by hand / by "
-                        "exp scripts; dram_bytes_per_item = dram_bytes / items")
+    probe = allj.get(workload, {}) if isinstance(allj.get(workload), dict) else {}
+    keep = {k: v for k, v in probe.items() if k in ("lookups", "dram_bytes_per_launch", "source")}
+    allj[workload] = dict(result, **({"k_probe_xs": keep} if keep else {}))
+    allj["_comment"] = ("per in-loop kernel: one mid-generation launch from an `ncu --set full` capture of bench.py "
+                        "(profiles/exp_r56.sh); items = list length of that launch from the engine's sweep trace; "
+                        "dram_bytes_per_item = (dram__bytes_read.sum + dram__bytes_write.sum) / items")
     json.dump(allj, open(json_path, "w"), indent=1)
-    print(json.dumps(result, indent=1))
+    print(json.dumps({k: {kk: vv for kk, vv in v.items() if kk != "launches"} for k, v in result.items()}, indent=1))
 
 
 if __name__ == "__main__":
