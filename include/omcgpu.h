@@ -72,7 +72,8 @@ extern "C" {
 #define OMCGPU_BC_NONE        0   /* transmission */
 #define OMCGPU_BC_VACUUM      1
 #define OMCGPU_BC_REFLECTIVE  2
-#define OMCGPU_BC_PERIODIC    3   /* translational, between two planes (src/boundary_condition.cpp:66-155) */
+#define OMCGPU_BC_PERIODIC    3   /* translational between two parallel planes (src/boundary_condition.cpp:66-155), or rotational
+                                   about x / y / z between two planes through the origin (:161-287): surf_periodic_axis */
 #define OMCGPU_BC_WHITE       4   /* cosine-distributed diffuse reflection (WhiteBC :53-62, Surface::diffuse_reflect src/surface.cpp:142-161) */
 
 /* cell fill: include/openmc/cell.h Fill enum */
@@ -176,7 +177,9 @@ typedef struct omcgpu_model {
   const int32_t* surf_type;       /* [n_surfaces] OMCGPU_SURF_*                        */
   const int32_t* surf_bc;         /* [n_surfaces] OMCGPU_BC_*                          */
   const int32_t* surf_periodic;   /* [n_surfaces] partner surface of a periodic BC, else -1 */
-  const double* surf_periodic_shift; /* [n_surfaces][3] added to r when this periodic surface is struck */
+  const double* surf_periodic_shift; /* [n_surfaces][3] translational: added to r when this periodic surface is struck;
+                                        rotational: { cos(theta), sin(theta), 0 } of the rotation applied to r and u */
+  const int32_t* surf_periodic_axis; /* [n_surfaces] -1 translational, else 0 / 1 / 2 = rotation about x / y / z */
   const int32_t* surf_id;         /* [n_surfaces] user ids (messages only)             */
   const double* surf_coef;        /* [n_surfaces][OMCGPU_SURF_NCOEF]                   */
 

@@ -280,8 +280,10 @@ OMC_HD double surf_evaluate(int s, V3 r)
     const double r1 = r.y - c1, r2 = r.x - c0, r3 = r.z - c2;
     return r2 * r2 + r3 * r3 - c3 * r1 * r1;
   }
+#ifndef OMC_NO_QUADRIC /* measurement build */
   case OMCGPU_SURF_QUADRIC:
     return general_quadric_evaluate(c, r);
+#endif
   default: { // z-cone
     const double r1 = r.z - c2, r2 = r.x - c0, r3 = r.y - c1;
     return r2 * r2 + r3 * r3 - c3 * r1 * r1;
@@ -313,8 +315,10 @@ OMC_HD V3 surf_normal(int s, V3 r)
     return v3(-2.0 * gld(c + 3) * (r.x - gld(c)), 2.0 * (r.y - gld(c + 1)), 2.0 * (r.z - gld(c + 2)));
   case OMCGPU_SURF_YCONE:
     return v3(2.0 * (r.x - gld(c)), -2.0 * gld(c + 3) * (r.y - gld(c + 1)), 2.0 * (r.z - gld(c + 2)));
+#ifndef OMC_NO_QUADRIC /* measurement build */
   case OMCGPU_SURF_QUADRIC:
     return general_quadric_normal(c, r);
+#endif
   default:
     return v3(2.0 * (r.x - gld(c)), 2.0 * (r.y - gld(c + 1)), -2.0 * gld(c + 3) * (r.z - gld(c + 2)));
   }
@@ -433,8 +437,10 @@ OMC_HD double surf_distance(int s, V3 r, V3 u, bool coincident)
     return cone_distance(r.x - c0, r.y - c1, r.z - c2, u.x, u.y, u.z, c3, coincident);
   case OMCGPU_SURF_YCONE:
     return cone_distance(r.y - c1, r.x - c0, r.z - c2, u.y, u.x, u.z, c3, coincident);
+#ifndef OMC_NO_QUADRIC /* measurement build */
   case OMCGPU_SURF_QUADRIC:
     return general_quadric_distance(c, r, u, coincident);
+#endif
   default:
     return cone_distance(r.z - c2, r.x - c0, r.y - c1, u.z, u.x, u.y, c3, coincident);
   }
@@ -1348,6 +1354,9 @@ OMC_HD double ce_reaction_xs(int rx, const MicroXS& micro)
 // temperature per nuclide (n_nuclide_temps == 0) keep table indices in mat_nuclide: one uniform branch.
 OMC_HD int nuc_table(int d, double kT)
 {
+#ifdef OMC_SINGLE_T /* measurement build */
+  return d;
+#endif
   if (DM.n_nuclide_temps == 0)
     return d;
   const int t0 = ld(DM.nuct_ofs + d), t1 = ld(DM.nuct_ofs + d + 1);

@@ -582,11 +582,25 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
         mark_lost(ps, gc, i);
       } else {
         const double* t = DM.surf_periodic_shift + 3 * s;
-        LV(rx, 0) += gld(t);
-        LV(ry, 0) += gld(t + 1);
-        LV(rz, 0) += gld(t + 2);
+        const int axis = gld(DM.surf_periodic_axis + s);
+        if (axis < 0) {
+          LV(rx, 0) += gld(t);
+          LV(ry, 0) += gld(t + 1);
+          LV(rz, 0) += gld(t + 2);
+        } else { // RotationalPeriodicBC::handle_particle, src/boundary_condition.cpp:242-287
+          const double c = gld(t), sn = gld(t + 1);
+          double r[3] = {LV(rx, 0), LV(ry, 0), LV(rz, 0)}, u[3] = {LV(ux, 0), LV(uy, 0), LV(uz, 0)};
+          const int a1 = axis == 0 ? 1 : 0, a2 = axis == 2 ? 1 : 2; // x: (y, z)  y: (x, z)  z: (x, y)
+          const double r1 = c * r[a1] - sn * r[a2], r2 = sn * r[a1] + c * r[a2];
+          const double u1 = c * u[a1] - sn * u[a2], u2 = sn * u[a1] + c * u[a2];
+          r[a1] = r1; r[a2] = r2; u[a1] = u1; u[a2] = u2;
+          LV(rx, 0) = r[0]; LV(ry, 0) = r[1]; LV(rz, 0) = r[2];
+          LV(ux, 0) = u[0]; LV(uy, 0) = u[1]; LV(uz, 0) = u[2];
+        }
         const int partner = gld(DM.surf_periodic + s) + 1;
-        surface = surface > 0 ? partner : -partner;
+        // translational: same side of the partner; rotational: the other side (both normals of a
+        // rotational pair point into the geometry), src/boundary_condition.cpp:137-143, 252-258
+        surface = (surface > 0) == (axis < 0) ? partner : -partner;
         ps.surface[i] = surface;
         if (!find_cell_from(ps, i, 1, surface))
           mark_lost(ps, gc, i);
@@ -690,10 +704,14 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
   p.xs_absorption = ps.xs_absorption[i];
   p.xs_nu_fission = ps.xs_nu_fission[i];
   p.k_abs = ps.k_abs[i];
+#ifdef OMC_SINGLE_T /* measurement build */
+  p.kT = 0.0;
+#else
   {
     const double sq = ps.sqrtkT[i];
     p.kT = sq * sq;
   }
+#endif
   ps.k_col[i] += p.wgt * p.xs_nu_fission / p.xs_total;
   ps.surface[i] = SURFACE_NONE;
   if (DM.run_CE) {
@@ -1930,7 +1948,7 @@ static int upload_model(const omcgpu_model* m)
                  n_kt_ = nc ? m->cell_sqrtkT_ofs[nc] : 0, n_co_ = nc ? m->cell_offset_ofs[nc] : 0,
                  n_uc_ = nu ? m->univ_cell_ofs[nu] : 0, n_lu_ = nl ? m->lat_univ_ofs[nl] : 0,
                  n_lo_ = nl ? m->lat_offset_ofs[nl] : 0;
-    g_arena_size = 40 * 16 + (size_t)ns * (4 * 4 + 8 * 3 + 8 * OMCGPU_SURF_NCOEF + 2 * 4) +
+    g_arena_size = 40 * 16 + (size_t)ns * (4 * 5 + 8 * 3 + 8 * OMCGPU_SURF_NCOEF + 2 * 4) +
                    (size_t)nc * (4 * 12 + 8 * 12) + 4 * (n_tok_ + n_cm_ + n_co_ + n_uc_ + n_lu_ + n_lo_) + 8 * n_kt_ +
                    4 * (2 * (size_t)ns + 1) + 8 * n_tok_ + /* half-space candidate lists: <= 2 entries per token */
                    (size_t)nu * 4 + (size_t)nl * (4 * 8 + 8 * 6) + 4096;
@@ -1950,6 +1968,7 @@ static int upload_model(const omcgpu_model* m)
   UP(surf_bc, ns);
   UP(surf_periodic, ns);
   UP(surf_periodic_shift, (size_t)ns * 3);
+  UP(surf_periodic_axis, ns);
   UP(surf_id, ns);
   UP(surf_coef, (size_t)ns * OMCGPU_SURF_NCOEF);
   const int n_tok = nc ? m->cell_region_ofs[nc] : 0;
@@ -2221,7 +2240,7 @@ static int upload_model(const omcgpu_model* m)
 #endif
     omcgpu_model hd = h;
 #define REBASE(field) hd.field = reinterpret_cast<decltype(hd.field)>(reinterpret_cast<const char*>(h.field) - G.geo_blob)
-    REBASE(surf_type); REBASE(surf_bc); REBASE(surf_periodic); REBASE(surf_periodic_shift); REBASE(surf_id);
+    REBASE(surf_type); REBASE(surf_bc); REBASE(surf_periodic); REBASE(surf_periodic_shift); REBASE(surf_periodic_axis); REBASE(surf_id);
     REBASE(surf_coef); REBASE(cell_id); REBASE(cell_type); REBASE(cell_universe); REBASE(cell_fill);
     REBASE(cell_simple); REBASE(cell_region_ofs); REBASE(region_tokens); REBASE(cell_mat_ofs); REBASE(cell_material);
     REBASE(cell_sqrtkT_ofs); REBASE(cell_sqrtkT); REBASE(cell_translation); REBASE(cell_rotated); REBASE(cell_rotation);
@@ -2251,8 +2270,9 @@ static int check_supported(const omcgpu_model* m)
     if (m->surf_bc[s] < 0 || m->surf_bc[s] > OMCGPU_BC_WHITE)
       return fail(OMCGPU_E_UNSUPPORTED, "boundary condition not supported on the device%s");
     if (m->surf_bc[s] == OMCGPU_BC_PERIODIC &&
-        (m->surf_type[s] > OMCGPU_SURF_PLANE || m->surf_periodic[s] < 0 || m->surf_periodic[s] >= m->n_surfaces))
-      return fail(OMCGPU_E_UNSUPPORTED, "periodic boundary: only translational, between two planes%s");
+        (m->surf_type[s] > OMCGPU_SURF_PLANE || m->surf_periodic[s] < 0 || m->surf_periodic[s] >= m->n_surfaces ||
+          m->surf_periodic_axis[s] < -1 || m->surf_periodic_axis[s] > 2))
+      return fail(OMCGPU_E_UNSUPPORTED, "periodic boundary: only between two planes%s");
   }
   for (int t = 0; t < m->n_tallies; ++t) {
     if (m->tally_n_filters[t] > OMCGPU_MAX_FILTERS || m->tally_n_scores[t] > OMCGPU_MAX_SCORES)

@@ -227,6 +227,30 @@ def surface_zoo():
     return m, c5g7_library(False), box, False
 
 
+def rotational_wedge():
+    """a 90-degree wedge of a fuel pin in water with ROTATIONAL periodic boundaries on its two flat
+    sides (RotationalPeriodicBC about z, src/boundary_condition.cpp:161-287), reflective outside"""
+    m = Model()
+    fuel = m.material(name="UO2 fuel", macroscopic="UO2", units="macro", density=1.0)
+    water = m.material(name="Water", macroscopic="LWTR", units="macro", density=1.0)
+    cyl = m.surface("z-cylinder", [0.0, 0.0, 0.45]).id
+    out = m.surface("z-cylinder", [0.0, 0.0, 1.1], "reflective").id
+    # the planes' normals point INTO the wedge x > 0, y > 0
+    px = m.surface("plane", [1.0, 0.0, 0.0, 0.0], "periodic", id=None).id      # x = 0, normal +x
+    py = m.surface("plane", [0.0, 1.0, 0.0, 0.0], "periodic").id               # y = 0, normal +y
+    for sfc in m.surfaces:
+        if sfc.id == px:
+            sfc.periodic_surface_id = py
+        elif sfc.id == py:
+            sfc.periodic_surface_id = px
+    z0 = m.surface("z-plane", [-1.0], "reflective").id
+    z1 = m.surface("z-plane", [1.0], "reflective").id
+    wedge = f"{px} {py} {z0} -{z1}"
+    m.cell(region=f"-{cyl} {wedge}", fill=fuel)
+    m.cell(region=f"{cyl} -{out} {wedge}", fill=water)
+    return m, c5g7_library(False), [0.0, 0.0, -1.0, 0.7, 0.7, 1.0], True
+
+
 def quadric_pin():
     """a fuel region bounded by general quadrics (src/surface.cpp:855-949): a tilted elliptic
     cylinder (xy cross term), cut by a paraboloid-like sheet, in a reflective box of water"""

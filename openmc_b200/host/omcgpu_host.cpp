@@ -178,7 +178,7 @@ void flatten_settings(Flat& F)
 void flatten_surfaces(Flat& F)
 {
   const int ns = model::surfaces.size();
-  IV type(ns), bc(ns), partner(ns, -1), id(ns);
+  IV type(ns), bc(ns), partner(ns, -1), id(ns), paxis(ns, -1);
   DV coef((size_t)ns * OMCGPU_SURF_NCOEF, 0.0), shift((size_t)ns * 3, 0.0);
   for (int i = 0; i < ns; ++i) {
     const Surface* s = model::surfaces[i].get();
@@ -233,8 +233,18 @@ void flatten_surfaces(Flat& F)
       partner[i] = first ? p->j_surf_ : p->i_surf_;
       for (int k = 0; k < 3; ++k)
         shift[3 * i + k] = first ? p->translation_[k] : -p->translation_[k];
+    } else if (auto p = dynamic_cast<const RotationalPeriodicBC*>(b)) {
+      // handle_particle (src/boundary_condition.cpp:242-287): rotation by +angle_ when the first surface of
+      // the pair is struck, -angle_ on the second; cos / sin taken here with the host's libm, as there
+      bc[i] = OMCGPU_BC_PERIODIC;
+      const bool first = p->i_surf_ == i;
+      partner[i] = first ? p->j_surf_ : p->i_surf_;
+      const double theta = first ? p->angle_ : -p->angle_;
+      shift[3 * i + 0] = std::cos(theta);
+      shift[3 * i + 1] = std::sin(theta);
+      paxis[i] = p->zero_axis_idx_;
     } else {
-      unsupported(fmt::format("the boundary condition of surface {} (rotational periodic)", s->id_));
+      unsupported(fmt::format("the boundary condition of surface {}", s->id_));
     }
   }
   F.m.n_surfaces = ns;
@@ -242,6 +252,7 @@ void flatten_surfaces(Flat& F)
   KEEP(surf_bc, bc);
   KEEP(surf_periodic, partner);
   KEEP(surf_periodic_shift, shift);
+  KEEP(surf_periodic_axis, paxis);
   KEEP(surf_id, id);
   KEEP(surf_coef, coef);
 }

@@ -329,6 +329,7 @@ class Model:
         ns = len(self.surfaces)
         partner = np.full(max(ns, 1), -1, np.int32)
         shift = np.zeros((max(ns, 1), 3))
+        axis = np.full(max(ns, 1), -1, np.int32)
         per = [s for s in self.surfaces if s.boundary == "periodic"]
         pairs = set()
         loose = []
@@ -369,13 +370,30 @@ class Model:
         for lo, hi in sorted(pairs):
             i, j = s_index[lo], s_index[hi]
             p1, p2 = plane(self.surfaces[i]), plane(self.surfaces[j])
+            n1 = np.array(p1[:3]) / math.sqrt(sum(c * c for c in p1[:3]))
+            n2 = np.array(p2[:3]) / math.sqrt(sum(c * c for c in p2[:3]))
+            if not abs(1.0 - float(n1 @ n2)) < 1e-14:
+                # RotationalPeriodicBC (src/surface.cpp:1336-1373, src/boundary_condition.cpp:161-240): the
+                # common zero component of the two normals is the axis; angle = (atan2 of the second normal
+                # + pi) - atan2 of the first, in the (independent, dependent) plane of that axis
+                zero = next((k for k in range(3) if abs(n1[k]) <= 1e-14 and abs(n2[k]) <= 1e-14), None)
+                if zero is None or abs(p1[3]) > 1e-12 or abs(p2[3]) > 1e-12:
+                    raise ValueError("rotational periodic BCs need two planes through the origin with a common zero normal component")
+                a1, a2 = (1, 2) if zero == 0 else ((0, 2) if zero == 1 else (0, 1))
+                m1, m2 = p1[:3], p2[:3]          # normal({0,0,0}) of the planes, not normalised
+                angle = (math.atan2(m2[a2], m2[a1]) + math.pi) - math.atan2(m1[a2], m1[a1])
+                partner[i], partner[j] = j, i
+                axis[i] = axis[j] = zero
+                shift[i] = [math.cos(angle), math.sin(angle), 0.0]
+                shift[j] = [math.cos(-angle), math.sin(-angle), 0.0]
+                continue
             u = p1[:3]
             d1, d2 = signed_distance(p1, u), signed_distance(p2, u)
             t = [u[k] * (d2 - d1) for k in range(3)]
             partner[i], partner[j] = j, i
             shift[i] = t
             shift[j] = [-x for x in t]
-        return partner, shift
+        return partner, shift, axis
 
     # -- flattening --------------------------------------------------------------
     def flatten_geometry(self) -> dict:
@@ -392,9 +410,9 @@ class Model:
             stype[i] = kind
             coef[i, :nco] = s.coeffs
             sbc[i] = _BCS[s.boundary]
-        partner, shift = self._periodic_pairs({s.id: i for i, s in enumerate(self.surfaces)})
+        partner, shift, paxis = self._periodic_pairs({s.id: i for i, s in enumerate(self.surfaces)})
         v.update(n_surfaces=ns, surf_type=stype, surf_bc=sbc, surf_coef=coef, surf_periodic=partner,
-                 surf_periodic_shift=shift,
+                 surf_periodic_shift=shift, surf_periodic_axis=paxis,
                  surf_id=np.array([s.id for s in self.surfaces] or [0], np.int32))
 
         # universes: ids in order of first appearance (cells' universe attribute,

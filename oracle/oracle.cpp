@@ -2077,11 +2077,25 @@ void cross_surface(Particle& p)
       return;
     }
     const double* t = M->surf_periodic_shift + 3 * s;
-    p.r().x += t[0];
-    p.r().y += t[1];
-    p.r().z += t[2];
+    const int axis = M->surf_periodic_axis[s];
+    if (axis < 0) {
+      p.r().x += t[0];
+      p.r().y += t[1];
+      p.r().z += t[2];
+    } else { // RotationalPeriodicBC::handle_particle, src/boundary_condition.cpp:242-287
+      const double c = t[0], sn = t[1];
+      double r[3] = {p.r().x, p.r().y, p.r().z}, u[3] = {p.u().x, p.u().y, p.u().z};
+      const int a1 = axis == 0 ? 1 : 0, a2 = axis == 2 ? 1 : 2;
+      const double r1 = c * r[a1] - sn * r[a2], r2 = sn * r[a1] + c * r[a2];
+      const double u1 = c * u[a1] - sn * u[a2], u2 = sn * u[a1] + c * u[a2];
+      r[a1] = r1; r[a2] = r2; u[a1] = u1; u[a2] = u2;
+      p.r() = {r[0], r[1], r[2]};
+      p.u() = {u[0], u[1], u[2]};
+    }
     const int partner = M->surf_periodic[s] + 1;
-    p.surface = p.surface > 0 ? partner : -partner;
+    // translational: same side of the partner (:137-143); rotational: the other side (:252-258) -- the
+    // normals of a rotational pair both point into the geometry
+    p.surface = (p.surface > 0) == (axis < 0) ? partner : -partner;
     p.n_coord = 1;
     if (!neighbor_list_find_cell(p))
       mark_as_lost(p, "Couldn't find particle after hitting periodic boundary");

@@ -25,6 +25,7 @@ RUNS = {
     "periodic_box": (1000, 6, 2),
     "white_pincell": (1000, 6, 2),         # C1 pin cell with white (diffuse) boundaries
     "quadric_pin": (1000, 6, 2),           # general quadric surfaces
+    "rotational_wedge": (1000, 6, 2),      # rotational periodic boundaries
 }
 _CACHE = {}
 

@@ -23,7 +23,7 @@ from oracle.binding import Oracle
 
 pytestmark = pytest.mark.gpu
 
-MG = ["pincell_mg", "c5g7_core", "surface_zoo", "rotated_fills", "periodic_box", "white_pincell", "quadric_pin"]
+MG = ["pincell_mg", "c5g7_core", "surface_zoo", "rotated_fills", "periodic_box", "white_pincell", "quadric_pin", "rotational_wedge"]
 CE = ["pincell_ce", "pincell_ce_temperatures", "assembly_ce", "pwr_core_ce"]
 
 
