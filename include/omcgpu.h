@@ -233,6 +233,8 @@ typedef struct omcgpu_model {
   const int32_t* mat_nuc_ofs;     /* [n_materials+1]                                   */
   const int32_t* mat_nuclide;     /* nuclide index                                     */
   const double* mat_atom_density; /* atom/b-cm                                         */
+  const int32_t* mat_base;        /* derived by omcgpu_init (ignored on input): NULL, or for a model with several
+                                     temperatures per nuclide the model material each device material was derived from */
 
   /* ---- continuous-energy nuclides: data::nuclides (src/nuclide.cpp) ------- */
   /* A "table" is one nuclide at one loaded temperature (Nuclide::kTs_[t], grid_[t], xs_[t],
@@ -241,7 +243,8 @@ typedef struct omcgpu_model {
    * mat_nuclide holds table indices.  Otherwise mat_nuclide holds nuclide indices d and the
    * tables of nuclide d are nuct_ofs[d] .. nuct_ofs[d+1]-1 in ascending kT; a lookup takes
    * the one nearest to the cell's kT (TemperatureMethod::NEAREST, src/nuclide.cpp:682-691;
-   * stochastic interpolation is refused). */
+   * stochastic interpolation is refused).  omcgpu_init resolves that choice once per
+   * (material, cell temperature) pair into derived materials, so the kernels pay nothing. */
   int32_t n_nuclide_temps;        /* 0, or the number of distinct nuclides               */
   const int32_t* nuct_ofs;        /* [n_nuclide_temps+1] into the tables                  */
   int32_t n_nuclides;             /* number of tables                                    */

@@ -1348,30 +1348,11 @@ OMC_HD double ce_reaction_xs(int rx, const MicroXS& micro)
   return (1.0 - micro.interp_factor) * ld(v) + micro.interp_factor * ld(v + 1);
 }
 
-// The table (nuclide at one loaded temperature) a lookup of material entry `d` uses at the cell's
-// kT: Nuclide::calculate_xs, TemperatureMethod::NEAREST (src/nuclide.cpp:682-691) -- the loaded
-// temperature with the smallest |kTs_[t] - kT|, the first of equals.  Libraries with one
-// temperature per nuclide (n_nuclide_temps == 0) keep table indices in mat_nuclide: one uniform branch.
-OMC_HD int nuc_table(int d, double kT)
-{
-#ifdef OMC_SINGLE_T /* measurement build */
-  return d;
-#endif
-  if (DM.n_nuclide_temps == 0)
-    return d;
-  const int t0 = ld(DM.nuct_ofs + d), t1 = ld(DM.nuct_ofs + d + 1);
-  int best = t0;
-  double max_diff = INFINITY;
-  for (int t = t0; t < t1; ++t) {
-    const double diff = fabs(ld(DM.nuc_kT + t) - kT);
-    if (diff < max_diff) {
-      best = t;
-      max_diff = diff;
-    }
-  }
-  return best;
-}
-
+// Several temperatures per nuclide (TemperatureMethod::NEAREST, src/nuclide.cpp:682-691): every
+// nuc_* / rx_* array is indexed by TABLE = nuclide at one loaded temperature, and omcgpu_init
+// resolves "the table nearest to the cell's kT" once per (material, cell temperature) pair into
+// derived materials whose entries are table indices (engine.cu, expand_temperatures) -- the
+// lookup and collision code below never sees a temperature.
 // Materials with many nuclides (depleted fuel, config C5: ~300): NB nuclides walk the
 // lookup chain (window -> probes -> bracketing energies -> two xs rows) in lockstep, so
 // that the loads of one stage are independent and overlap; the partial sums are added
@@ -1384,7 +1365,7 @@ OMC_HD int nuc_table(int d, double kT)
 #define OMC_XS_BATCH_MIN 16 /* nuclides in the material from which the lockstep walk is used */
 #endif
 template<int NB>
-OMC_HD void ce_macro_xs_batch(int k0, int k1, int j_fine, double E, double kT, double& t, double& a, double& f,
+OMC_HD void ce_macro_xs_batch(int k0, int k1, int j_fine, double E, double& t, double& a, double& f,
   double& nf, int32_t* i_grid_out, int max_nuc, double* prefix_out)
 {
   static_assert(XS_PREFIX_STRIDE % NB == 0, "a prefix boundary must fall between two batches");
@@ -1394,7 +1375,7 @@ OMC_HD void ce_macro_xs_batch(int k0, int k1, int j_fine, double E, double kT, d
     int64_t g0[NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j)
-      nuc[j] = nuc_table(ld(DM.mat_nuclide + (kb + j < k1 ? kb + j : k1 - 1)), kT);
+      nuc[j] = ld(DM.mat_nuclide + (kb + j < k1 ? kb + j : k1 - 1));
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       g0[j] = ld(DM.nuc_grid_ofs + nuc[j]);
@@ -1497,14 +1478,14 @@ OMC_HD void ce_macro_xs_batch(int k0, int k1, int j_fine, double E, double kT, d
 // (src/physics.cpp:494-518) over a many-nuclide material needs up to n of them in a row.
 // sig_t[j] is bit-identical to ce_micro_xs(...).total.
 template<int NB>
-OMC_HD void ce_total_xs_batch(int kb, int k1, int j_fine, double E, double kT, double* sig_t)
+OMC_HD void ce_total_xs_batch(int kb, int k1, int j_fine, double E, double* sig_t)
 {
   int nuc[NB], n_grid[NB], lo[NB], len[NB], ig[NB];
   const double* energy[NB];
   int64_t g0[NB];
 #pragma unroll
   for (int j = 0; j < NB; ++j)
-    nuc[j] = nuc_table(ld(DM.mat_nuclide + (kb + j < k1 ? kb + j : k1 - 1)), kT);
+    nuc[j] = ld(DM.mat_nuclide + (kb + j < k1 ? kb + j : k1 - 1));
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
     g0[j] = ld(DM.nuc_grid_ofs + nuc[j]);
@@ -1577,7 +1558,7 @@ OMC_HD void ce_total_xs_batch(int kb, int k1, int j_fine, double E, double kT, d
 // BX: the kernel was compiled for models with many-nuclide materials (its register
 // budget covers the lockstep walk); the host picks the kernel flavour per model.
 template<bool BX>
-OMC_HD void ce_macro_xs(int m, double E, double kT, double& t, double& a, double& f, double& nf,
+OMC_HD void ce_macro_xs(int m, double E, double& t, double& a, double& f, double& nf,
   int32_t* i_grid_out, int max_nuc, int batch_min = OMC_XS_BATCH_MIN, double* prefix_out = nullptr)
 {
   t = a = f = nf = 0.0;
@@ -1586,13 +1567,13 @@ OMC_HD void ce_macro_xs(int m, double E, double kT, double& t, double& a, double
   if (BX && k1 - k0 >= batch_min) {
     // (a material walked one nuclide at a time has fewer than OMC_XS_BATCH_MIN <= XS_PREFIX_STRIDE
     // nuclides when prefixes are kept: it has no prefix entry and its collisions walk from 0)
-    ce_macro_xs_batch<OMC_XS_BATCH>(k0, k1, j_fine, E, kT, t, a, f, nf, i_grid_out, max_nuc,
+    ce_macro_xs_batch<OMC_XS_BATCH>(k0, k1, j_fine, E, t, a, f, nf, i_grid_out, max_nuc,
       k1 - k0 >= 2 * XS_PREFIX_STRIDE ? prefix_out : nullptr);
     return;
   }
   for (int k = k0; k < k1; ++k) {
     MicroXS micro;
-    ce_micro_xs(nuc_table(ld(DM.mat_nuclide + k), kT), j_fine, E, micro);
+    ce_micro_xs(ld(DM.mat_nuclide + k), j_fine, E, micro);
     const double rho = ld(DM.mat_atom_density + k);
     t += rho * micro.total;
     a += rho * micro.absorption;
@@ -1789,7 +1770,6 @@ struct Collider { // registers of the colliding particle
   int n_progeny;
   int64_t id;
   double xs_total, xs_absorption, xs_nu_fission;
-  double kT; // of the cell: picks the nuclides' temperature tables (CE)
 };
 
 OMC_HD void russian_roulette(Collider& p, double weight_survive)
@@ -1898,21 +1878,21 @@ OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no
     }
     for (int kb = kb0; kb < k1 && nuc < 0; kb += OMC_XS_BATCH) {
       double sig_t[OMC_XS_BATCH];
-      ce_total_xs_batch<OMC_XS_BATCH>(kb, k1, i_log, p.E, p.kT, sig_t);
+      ce_total_xs_batch<OMC_XS_BATCH>(kb, k1, i_log, p.E, sig_t);
 #pragma unroll
       for (int j = 0; j < OMC_XS_BATCH; ++j) {
         if (nuc >= 0 || kb + j >= k1)
           continue;
         prob += ld(DM.mat_atom_density + kb + j) * sig_t[j];
         if (prob >= cutoff)
-          nuc = nuc_table(ld(DM.mat_nuclide + kb + j), p.kT);
+          nuc = ld(DM.mat_nuclide + kb + j);
       }
     }
     if (nuc >= 0)
       ce_micro_xs(nuc, i_log, p.E, micro);
   } else {
     for (int k = k0; k < k1; ++k) {
-      const int cand = nuc_table(ld(DM.mat_nuclide + k), p.kT);
+      const int cand = ld(DM.mat_nuclide + k);
       ce_micro_xs(cand, i_log, p.E, micro);
       prob += ld(DM.mat_atom_density + k) * micro.total;
       if (prob >= cutoff) {
@@ -2498,7 +2478,8 @@ OMC_HD bool tally_prepare(const PState& ps, int64_t i, int n_coord, int t, doubl
       break;
     case OMCGPU_FILTER_MATERIAL:
       if (sc.material >= 0) {
-        const int b = ld(DM.filter_idata + o + sc.material);
+        // (derived materials of a multi-temperature model map back to the model's material)
+        const int b = ld(DM.filter_idata + o + (DM.mat_base ? ld(DM.mat_base + sc.material) : sc.material));
         if (b >= 0)
           te.bins[k][te.nb[k]++] = b;
       }

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -352,8 +353,7 @@ OMC_D void ev_xs(const PState& ps, int64_t i, int batch_min = OMC_XS_BATCH_MIN, 
   if (DM.run_CE) {
     if (m != ps.material_last[i] || ps.sqrtkT[i] != ps.sqrtkT_last[i]) {
       double t, a, f, nf;
-      const double sq = ps.sqrtkT[i];
-      ce_macro_xs<BX>(m, ps.E[i], sq * sq, t, a, f, nf, nullptr, 0, batch_min,
+      ce_macro_xs<BX>(m, ps.E[i], t, a, f, nf, nullptr, 0, batch_min,
         ps.n_prefix ? ps.xs_prefix + (ps.id_shift + i) * ps.n_prefix : nullptr);
       if (count)
         count_lookup(count, ld(DM.mat_nuc_ofs + m + 1) - ld(DM.mat_nuc_ofs + m));
@@ -704,14 +704,6 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
   p.xs_absorption = ps.xs_absorption[i];
   p.xs_nu_fission = ps.xs_nu_fission[i];
   p.k_abs = ps.k_abs[i];
-#ifdef OMC_SINGLE_T /* measurement build */
-  p.kT = 0.0;
-#else
-  {
-    const double sq = ps.sqrtkT[i];
-    p.kT = sq * sq;
-  }
-#endif
   ps.k_col[i] += p.wgt * p.xs_nu_fission / p.xs_total;
   ps.surface[i] = SURFACE_NONE;
   if (DM.run_CE) {
@@ -1550,7 +1542,6 @@ struct XsArgs {
   int32_t* i_grid;
   int32_t max_nuc;
   int32_t xs_batch_min;
-  double kT; // temperature of the probe lookups (omcgpu_set_probe_temperature)
 };
 template<bool BX>
 OMC_D void body_probe_xs(int64_t tid, const XsArgs& a)
@@ -1560,7 +1551,7 @@ OMC_D void body_probe_xs(int64_t tid, const XsArgs& a)
   const int m = a.material[tid];
   double t = 0, ab = 0, f = 0, nf = 0;
   if (DM.run_CE) {
-    ce_macro_xs<BX>(m, a.E[tid], a.kT, t, ab, f, nf, a.i_grid ? a.i_grid + tid * a.max_nuc : nullptr,
+    ce_macro_xs<BX>(m, a.E[tid], t, ab, f, nf, a.i_grid ? a.i_grid + tid * a.max_nuc : nullptr,
       a.max_nuc, a.xs_batch_min);
   } else {
     const int G = DM.mg_n_groups;
@@ -1596,7 +1587,6 @@ struct CollideArgs {
   const double* uvw;
   const uint64_t* seed;
   double wgt;
-  double kT;
   double* E_out;
   double* uvw_out;
   double* wgt_out;
@@ -1621,8 +1611,7 @@ OMC_D void body_probe_collide(int64_t tid, const CollideArgs& a)
   p.id = tid + 1;
   if (DM.run_CE) {
     double t, ab, f, nf;
-    p.kT = a.kT;
-    ce_macro_xs<false>(p.material, p.E, p.kT, t, ab, f, nf, nullptr, 0);
+    ce_macro_xs<false>(p.material, p.E, t, ab, f, nf, nullptr, 0);
     p.xs_total = t;
     p.xs_absorption = ab;
     p.xs_nu_fission = nf;
@@ -1785,6 +1774,10 @@ struct Engine {
   std::vector<int64_t> tally_ofs; // host copy of tally_result_ofs
   int n_cell_sqrtkT = 0, n_mat_nuclides = 0; // array lengths omcgpu_update checks
   int n_collision_tallies = 0;
+  // several temperatures per nuclide: device materials are (model material, cell sqrt(kT)) pairs
+  int n_base_materials = 0;
+  std::vector<int32_t> mat_base;    // [device material] -> model material (empty: identity)
+  std::vector<double> mat_sqrtkT;   // [device material] the cell temperature it was resolved for
   const char* geo_blob = nullptr; // CSG tables in one block (device.h, gld)
   size_t geo_bytes = 0;
   unsigned geo_smem = 0;        // bytes of it the geometry kernels stage in shared memory
@@ -1932,10 +1925,92 @@ static double hash_edge_for(int k, double e_min, double spacing)
   return E;
 }
 
+// Several temperatures per nuclide (TemperatureMethod::NEAREST, src/nuclide.cpp:682-691): the table
+// a lookup uses depends on the nuclide and on the cell's kT only, so it is resolved HERE, once per
+// (material, cell temperature) pair: every such pair becomes a device material whose entries are
+// table indices, and the cells point at those.  The kernels then run exactly the one-temperature
+// code (no per-lookup temperature search, no kT in the collision registers).
+struct TemperatureExpansion {
+  std::vector<int32_t> cell_mat_ofs, cell_material, mat_id, mat_fissionable, mat_nuc_ofs, mat_nuclide, mat_base;
+  std::vector<double> mat_atom_density, mat_sqrtkT;
+};
+static int nearest_table(const omcgpu_model* m, int d, double kT)
+{
+  int best = m->nuct_ofs[d];
+  double max_diff = INFINITY;
+  for (int t = m->nuct_ofs[d]; t < m->nuct_ofs[d + 1]; ++t) {
+    const double diff = std::fabs(m->nuc_kT[t] - kT);
+    if (diff < max_diff) {
+      best = t;
+      max_diff = diff;
+    }
+  }
+  return best;
+}
+static void expand_temperatures(const omcgpu_model* m, TemperatureExpansion& X)
+{
+  std::map<std::pair<int32_t, double>, int32_t> derived;
+  X.cell_mat_ofs.push_back(0);
+  for (int c = 0; c < m->n_cells; ++c) {
+    const int m0 = m->cell_mat_ofs[c], nmat = m->cell_mat_ofs[c + 1] - m0;
+    const int k0 = m->cell_sqrtkT_ofs[c], nkt = m->cell_sqrtkT_ofs[c + 1] - k0;
+    const int n = nmat == 0 ? 0 : std::max(nmat, std::max(nkt, 1));
+    for (int k = 0; k < n; ++k) {
+      const int32_t mat = m->cell_material[m0 + (nmat > 1 ? k : 0)];
+      if (mat < 0) {
+        X.cell_material.push_back(mat);
+        continue;
+      }
+      const double sq = nkt > 0 ? m->cell_sqrtkT[k0 + (nkt > 1 ? k : 0)] : 0.0;
+      auto it = derived.find({mat, sq});
+      if (it == derived.end()) {
+        it = derived.emplace(std::make_pair(mat, sq), (int32_t)X.mat_base.size()).first;
+        X.mat_base.push_back(mat);
+        X.mat_sqrtkT.push_back(sq);
+      }
+      X.cell_material.push_back(it->second);
+    }
+    X.cell_mat_ofs.push_back((int32_t)X.cell_material.size());
+  }
+  X.mat_nuc_ofs.push_back(0);
+  for (size_t d = 0; d < X.mat_base.size(); ++d) {
+    const int b = X.mat_base[d];
+    const double kT = X.mat_sqrtkT[d] * X.mat_sqrtkT[d];
+    X.mat_id.push_back(m->mat_id[b]);
+    X.mat_fissionable.push_back(m->mat_fissionable[b]);
+    for (int k = m->mat_nuc_ofs[b]; k < m->mat_nuc_ofs[b + 1]; ++k) {
+      X.mat_nuclide.push_back(nearest_table(m, m->mat_nuclide[k], kT));
+      X.mat_atom_density.push_back(m->mat_atom_density[k]);
+    }
+    X.mat_nuc_ofs.push_back((int32_t)X.mat_nuclide.size());
+  }
+}
+
 static int upload_model(const omcgpu_model* m)
 {
   G.hm = *m;
   omcgpu_model& h = G.hm;
+  TemperatureExpansion X;
+  G.n_base_materials = m->n_materials;
+  G.mat_base.clear();
+  G.mat_sqrtkT.clear();
+  h.mat_base = nullptr;
+  if (h.run_CE && m->n_nuclide_temps > 0) {
+    expand_temperatures(m, X);
+    h.n_materials = (int32_t)X.mat_base.size();
+    h.cell_mat_ofs = X.cell_mat_ofs.data();
+    h.cell_material = X.cell_material.data();
+    h.mat_id = X.mat_id.data();
+    h.mat_fissionable = X.mat_fissionable.data();
+    h.mat_nuc_ofs = X.mat_nuc_ofs.data();
+    h.mat_nuclide = X.mat_nuclide.data();
+    h.mat_atom_density = X.mat_atom_density.data();
+    h.mat_base = X.mat_base.data();
+    h.n_nuclide_temps = 0; // the device sees resolved tables only
+    h.nuct_ofs = nullptr;
+    G.mat_base = X.mat_base;
+    G.mat_sqrtkT = X.mat_sqrtkT;
+  }
   const int ns = h.n_surfaces, nc = h.n_cells, nu = h.n_universes, nl = h.n_lattices;
   const int nm = h.n_materials;
   int rc = 0;
@@ -1944,7 +2019,7 @@ static int upload_model(const omcgpu_model* m)
   // first OMCGPU_GEO_SMEM bytes (default 24 KB, 0 = off) in shared memory (device.h, gld)
   {
     // upper bound of the geometry tables uploaded between here and lat_offsets (16-byte slots)
-    const size_t n_tok_ = nc ? m->cell_region_ofs[nc] : 0, n_cm_ = nc ? m->cell_mat_ofs[nc] : 0,
+    const size_t n_tok_ = nc ? m->cell_region_ofs[nc] : 0, n_cm_ = nc ? h.cell_mat_ofs[nc] : 0,
                  n_kt_ = nc ? m->cell_sqrtkT_ofs[nc] : 0, n_co_ = nc ? m->cell_offset_ofs[nc] : 0,
                  n_uc_ = nu ? m->univ_cell_ofs[nu] : 0, n_lu_ = nl ? m->lat_univ_ofs[nl] : 0,
                  n_lo_ = nl ? m->lat_offset_ofs[nl] : 0;
@@ -1972,7 +2047,7 @@ static int upload_model(const omcgpu_model* m)
   UP(surf_id, ns);
   UP(surf_coef, (size_t)ns * OMCGPU_SURF_NCOEF);
   const int n_tok = nc ? m->cell_region_ofs[nc] : 0;
-  const int n_cmat = nc ? m->cell_mat_ofs[nc] : 0;
+  const int n_cmat = nc ? h.cell_mat_ofs[nc] : 0;
   const int n_ckt = nc ? m->cell_sqrtkT_ofs[nc] : 0;
   const int n_coff = nc ? m->cell_offset_ofs[nc] : 0;
   UP(cell_id, nc);
@@ -2045,7 +2120,9 @@ static int upload_model(const omcgpu_model* m)
     CUDA_OK(cudaMemcpyToSymbol(c_geo_blob, &G.geo_blob, sizeof(char*)));
 #endif
   }
-  const int n_mn = nm ? m->mat_nuc_ofs[nm] : 0;
+  const int n_mn = nm ? h.mat_nuc_ofs[nm] : 0;
+  if (h.mat_base)
+    UP(mat_base, nm);
   UP(mat_id, nm);
   UP(mat_fissionable, nm);
   UP(mat_nuc_ofs, nm + 1);
@@ -2063,7 +2140,6 @@ static int upload_model(const omcgpu_model* m)
     edge[h.n_log_bins + 1] = INFINITY;
     h.hash_edge = edge.data();
     UP(hash_edge, h.n_log_bins + 2);
-    UP(nuct_ofs, h.n_nuclide_temps ? h.n_nuclide_temps + 1 : 0);
     UP(nuc_awr, nn);
     UP(nuc_kT, nn);
     UP(nuc_fissionable, nn);
@@ -3033,9 +3109,30 @@ int omcgpu_update(const omcgpu_model* model, uint32_t what)
   if (!model)
     return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_update: no model%s");
   const omcgpu_model& h = G.hm; // scalars + device pointers of the model in use
-  if (model->n_cells != h.n_cells || model->n_materials != h.n_materials)
+  if (model->n_cells != h.n_cells || model->n_materials != G.n_base_materials)
     return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_update: the model's shape differs from the one given to omcgpu_init%s");
   CUDA_OK(cudaStreamSynchronize(G.stream));
+  if (!G.mat_base.empty()) {
+    // several temperatures per nuclide: the device materials are (material, cell temperature) pairs
+    if (what & OMCGPU_UPDATE_CELL_TEMPERATURES)
+      return fail(OMCGPU_E_UNSUPPORTED, "omcgpu_update: cell temperatures of a model with several temperatures per "
+                                        "nuclide select other tables: call omcgpu_init again%s");
+    if (what & OMCGPU_UPDATE_MATERIAL_DENSITIES) {
+      std::vector<double> dens;
+      for (size_t d = 0; d < G.mat_base.size(); ++d) {
+        const int b = G.mat_base[d];
+        for (int k = model->mat_nuc_ofs[b]; k < model->mat_nuc_ofs[b + 1]; ++k)
+          dens.push_back(model->mat_atom_density[k]);
+      }
+      if ((int)dens.size() != G.n_mat_nuclides)
+        return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_update: number of material nuclides changed%s");
+      CUDA_OK(cudaMemcpy(const_cast<double*>(h.mat_atom_density), dens.data(), dens.size() * sizeof(double),
+        cudaMemcpyHostToDevice));
+    }
+    if (what & ~(OMCGPU_UPDATE_CELL_TEMPERATURES | OMCGPU_UPDATE_MATERIAL_DENSITIES))
+      return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_update: unknown property%s");
+    return 0;
+  }
   if (what & OMCGPU_UPDATE_CELL_TEMPERATURES) {
     const int n = h.n_cells ? model->cell_sqrtkT_ofs[h.n_cells] : 0;
     if (n != G.n_cell_sqrtkT)
@@ -3043,7 +3140,7 @@ int omcgpu_update(const omcgpu_model* model, uint32_t what)
     CUDA_OK(cudaMemcpy(const_cast<double*>(h.cell_sqrtkT), model->cell_sqrtkT, n * sizeof(double), cudaMemcpyHostToDevice));
   }
   if (what & OMCGPU_UPDATE_MATERIAL_DENSITIES) {
-    const int n = h.n_materials ? model->mat_nuc_ofs[h.n_materials] : 0;
+    const int n = G.n_base_materials ? model->mat_nuc_ofs[G.n_base_materials] : 0;
     if (n != G.n_mat_nuclides)
       return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_update: number of material nuclides changed%s");
     CUDA_OK(cudaMemcpy(const_cast<double*>(h.mat_atom_density), model->mat_atom_density, n * sizeof(double),
@@ -3801,11 +3898,41 @@ int omcgpu_tally_values_device(double** values, int64_t* n)
   return 0;
 }
 
+// The probes take MODEL material indices; with several temperatures per nuclide the device
+// materials are (material, cell temperature) pairs: take the pair of that material whose
+// temperature is nearest to the probe temperature ("probe_kT_neV")
+static std::vector<int32_t> device_materials(const int32_t* material, int64_t n)
+{
+  std::vector<int32_t> out(material, material + n);
+  if (G.mat_base.empty())
+    return out;
+  for (int64_t k = 0; k < n; ++k) {
+    int best = -1;
+    double max_diff = INFINITY;
+    for (size_t d = 0; d < G.mat_base.size(); ++d) {
+      if (G.mat_base[d] != material[k])
+        continue;
+      const double diff = std::fabs(G.mat_sqrtkT[d] * G.mat_sqrtkT[d] - G.probe_kT);
+      if (diff < max_diff) {
+        best = (int)d;
+        max_diff = diff;
+      }
+    }
+    out[k] = best;
+  }
+  return out;
+}
+
 int omcgpu_calculate_xs(const double* E, const int32_t* material, int64_t n, double* out,
   int32_t* i_grid, int32_t max_nuc)
 {
   if (!G.ready)
     return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  const std::vector<int32_t> dmat = device_materials(material, n);
+  for (int64_t k = 0; k < n; ++k)
+    if (dmat[k] < 0 || dmat[k] >= G.hm.n_materials)
+      return fail(OMCGPU_E_OUT_OF_BOUNDS, "omcgpu_calculate_xs: material index out of range%s");
+  material = dmat.data();
   double *dE = nullptr, *dout = nullptr;
   int32_t *dm = nullptr, *dig = nullptr;
   CUDA_OK(cudaMalloc((void**)&dE, n * sizeof(double)));
@@ -3818,7 +3945,7 @@ int omcgpu_calculate_xs(const double* E, const int32_t* material, int64_t n, dou
   CUDA_OK(cudaMemcpy(dE, E, n * sizeof(double), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(dm, material, n * sizeof(int32_t), cudaMemcpyHostToDevice));
   XsArgs a;
-  a.E = dE; a.material = dm; a.n = n; a.out = dout; a.i_grid = dig; a.max_nuc = max_nuc; a.kT = G.probe_kT;
+  a.E = dE; a.material = dm; a.n = n; a.out = dout; a.i_grid = dig; a.max_nuc = max_nuc;
   LAUNCH_XS(k_probe_xs, n, G.stream, a);
   CUDA_OK(cudaStreamSynchronize(G.stream));
   CUDA_OK(cudaMemcpy(out, dout, n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
@@ -3839,7 +3966,7 @@ int omcgpu_calculate_xs_device(const double* E, const int32_t* material, int64_t
   if (!G.ready)
     return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
   XsArgs a;
-  a.E = E; a.material = material; a.n = n; a.out = out; a.i_grid = nullptr; a.max_nuc = 0; a.kT = G.probe_kT;
+  a.E = E; a.material = material; a.n = n; a.out = out; a.i_grid = nullptr; a.max_nuc = 0;
   CUDA_OK(cudaEventRecord(G.evp0, G.stream));
   LAUNCH_XS(k_probe_xs, n, G.stream, a);
   CUDA_OK(cudaEventRecord(G.evp1, G.stream));
@@ -3886,8 +4013,8 @@ int omcgpu_collide(int64_t n, const int32_t* material, const double* E, const do
   a.fb = G.fis;
   a.n = n;
   a.wgt = wgt;
-  a.kT = G.probe_kT;
-  a.material = (const int32_t*)dalloc(n * 4, material);
+  const std::vector<int32_t> dmat = device_materials(material, n);
+  a.material = (const int32_t*)dalloc(n * 4, dmat.data());
   a.E = (const double*)dalloc(n * 8, E);
   a.uvw = (const double*)dalloc(n * 24, uvw);
   a.seed = (const uint64_t*)dalloc(n * 8, seed);
@@ -3990,6 +4117,10 @@ static int geom_probe(const double* xyz, const double* uvw, int64_t n, int32_t* 
       cudaMemcpy(cell + done, a.cell, m * 4, cudaMemcpyDeviceToHost);
       cudaMemcpy(instance + done, a.instance, m * 4, cudaMemcpyDeviceToHost);
       cudaMemcpy(material + done, a.material, m * 4, cudaMemcpyDeviceToHost);
+      if (!G.mat_base.empty()) // device materials -> the model's materials
+        for (int64_t k = done; k < done + m; ++k)
+          if (material[k] >= 0)
+            material[k] = G.mat_base[material[k]];
       cudaMemcpy(n_coord + done, a.n_coord, m * 4, cudaMemcpyDeviceToHost);
     }
     if (distance) {
