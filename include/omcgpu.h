@@ -65,8 +65,8 @@ extern "C" {
 #define OMCGPU_SURF_XCONE     8   /* coef: x0 y0 z0 r^2  (src/surface.cpp:688-742) */
 #define OMCGPU_SURF_YCONE     9
 #define OMCGPU_SURF_ZCONE     10
-#define OMCGPU_SURF_QUADRIC   11  /* coef: A B C D E F G H J K  (src/surface.cpp:855-949) */
-#define OMCGPU_SURF_NCOEF     10  /* doubles stored per surface */
+#define OMCGPU_SURF_QUADRIC   11  /* coef: row index into quad_coef = A B C D E F G H J K  (src/surface.cpp:855-949) */
+#define OMCGPU_SURF_NCOEF     4   /* doubles stored per surface */
 
 /* boundary conditions: src/boundary_condition.cpp:18-62 */
 #define OMCGPU_BC_NONE        0   /* transmission */
@@ -182,6 +182,8 @@ typedef struct omcgpu_model {
   const int32_t* surf_periodic_axis; /* [n_surfaces] -1 translational, else 0 / 1 / 2 = rotation about x / y / z */
   const int32_t* surf_id;         /* [n_surfaces] user ids (messages only)             */
   const double* surf_coef;        /* [n_surfaces][OMCGPU_SURF_NCOEF]                   */
+  int32_t n_quadrics;             /* general quadrics among the surfaces               */
+  const double* quad_coef;        /* [n_quadrics][10]: kept apart so that the common surfaces stay 32 bytes */
 
   /* ---- cells: model::cells (include/openmc/cell.h:339-375) ---------------- */
   int32_t n_cells;

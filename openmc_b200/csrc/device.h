@@ -193,15 +193,17 @@ OMC_HD double watt_spectrum(double a, double b, uint64_t& seed)
 // =============================================================================
 // General quadric A x^2 + B y^2 + C z^2 + D xy + E yz + F xz + G x + H y + J z + K = 0,
 // src/surface.cpp:861-868 (evaluate), 870-939 (distance), 941-949 (normal); out of line: rare
-OMC_OOL double general_quadric_evaluate(const double* c, V3 r)
+OMC_OOL double general_quadric_evaluate(const double* c4, V3 r)
 {
+  const double* c = DM.quad_coef + 10 * (int)gld(c4);
   const double A = gld(c), B = gld(c + 1), C = gld(c + 2), D = gld(c + 3), E = gld(c + 4), F = gld(c + 5),
                G = gld(c + 6), H = gld(c + 7), J = gld(c + 8), K = gld(c + 9);
   const double x = r.x, y = r.y, z = r.z;
   return x * (A * x + D * y + G) + y * (B * y + E * z + H) + z * (C * z + F * x + J) + K;
 }
-OMC_OOL double general_quadric_distance(const double* c, V3 r, V3 ang, bool coincident)
+OMC_OOL double general_quadric_distance(const double* c4, V3 r, V3 ang, bool coincident)
 {
+  const double* c = DM.quad_coef + 10 * (int)gld(c4);
   const double A = gld(c), B = gld(c + 1), C = gld(c + 2), D = gld(c + 3), E = gld(c + 4), F = gld(c + 5),
                G = gld(c + 6), H = gld(c + 7), J = gld(c + 8), K = gld(c + 9);
   const double x = r.x, y = r.y, z = r.z, u = ang.x, v = ang.y, w = ang.z;
@@ -235,8 +237,9 @@ OMC_OOL double general_quadric_distance(const double* c, V3 r, V3 ang, bool coin
   }
   return d <= 0.0 ? INFTY : d;
 }
-OMC_OOL V3 general_quadric_normal(const double* c, V3 r)
+OMC_OOL V3 general_quadric_normal(const double* c4, V3 r)
 {
+  const double* c = DM.quad_coef + 10 * (int)gld(c4);
   const double A = gld(c), B = gld(c + 1), C = gld(c + 2), D = gld(c + 3), E = gld(c + 4), F = gld(c + 5),
                G = gld(c + 6), H = gld(c + 7), J = gld(c + 8);
   return v3(2.0 * A * r.x + D * r.y + F * r.z + G, 2.0 * B * r.y + D * r.x + E * r.z + H,

@@ -526,6 +526,37 @@ OMC_D bool ev_revive(const PState& ps, int64_t i)
   return ps.wgt[i] != 0.0;
 }
 
+// Rare boundary conditions, out of line so that the crossing kernel does not carry them.
+// RotationalPeriodicBC::handle_particle, src/boundary_condition.cpp:242-287: position and direction
+// rotated about x / y / z by the angle whose cosine and sine the flattener took with the host's libm
+OMC_OOL void rotate_periodic(const PState& ps, int64_t i, int s, int axis)
+{
+  const double* t = DM.surf_periodic_shift + 3 * s;
+  const double c = gld(t), sn = gld(t + 1);
+  const V3 r = get_r(ps, i, 0), u = get_u(ps, i, 0);
+  V3 nr = r, nu = u;
+  if (axis == 0) { // independent y, dependent z
+    nr.y = c * r.y - sn * r.z; nr.z = sn * r.y + c * r.z;
+    nu.y = c * u.y - sn * u.z; nu.z = sn * u.y + c * u.z;
+  } else if (axis == 1) { // independent x, dependent z (the reference's left-handed convention for y)
+    nr.x = c * r.x - sn * r.z; nr.z = sn * r.x + c * r.z;
+    nu.x = c * u.x - sn * u.z; nu.z = sn * u.x + c * u.z;
+  } else { // independent x, dependent y
+    nr.x = c * r.x - sn * r.y; nr.y = sn * r.x + c * r.y;
+    nu.x = c * u.x - sn * u.y; nu.y = sn * u.x + c * u.y;
+  }
+  LV(rx, 0) = nr.x; LV(ry, 0) = nr.y; LV(rz, 0) = nr.z;
+  set_u(ps, i, 0, nu);
+}
+// WhiteBC::handle_particle, src/boundary_condition.cpp:53-62
+OMC_OOL void white_reflect(const PState& ps, int64_t i, int s)
+{
+  const V3 r = get_r(ps, i, 0);
+  V3 u = diffuse_reflect(surf_normal(s, r), get_u(ps, i, 0), ps.seed[i]);
+  const double nrm = sqrt(u.x * u.x + u.y * u.y + u.z * u.z);
+  set_u(ps, i, 0, v3(u.x / nrm, u.y / nrm, u.z / nrm));
+}
+
 // Particle::event_cross_surface + cross_surface + BCs + cross_lattice:
 // src/particle.cpp:288-329, 549-710 ; src/geometry.cpp:301-357 ;
 // src/boundary_condition.cpp:18-47
@@ -581,21 +612,14 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
       if (n_coord != 1) {
         mark_lost(ps, gc, i);
       } else {
-        const double* t = DM.surf_periodic_shift + 3 * s;
         const int axis = gld(DM.surf_periodic_axis + s);
         if (axis < 0) {
+          const double* t = DM.surf_periodic_shift + 3 * s;
           LV(rx, 0) += gld(t);
           LV(ry, 0) += gld(t + 1);
           LV(rz, 0) += gld(t + 2);
-        } else { // RotationalPeriodicBC::handle_particle, src/boundary_condition.cpp:242-287
-          const double c = gld(t), sn = gld(t + 1);
-          double r[3] = {LV(rx, 0), LV(ry, 0), LV(rz, 0)}, u[3] = {LV(ux, 0), LV(uy, 0), LV(uz, 0)};
-          const int a1 = axis == 0 ? 1 : 0, a2 = axis == 2 ? 1 : 2; // x: (y, z)  y: (x, z)  z: (x, y)
-          const double r1 = c * r[a1] - sn * r[a2], r2 = sn * r[a1] + c * r[a2];
-          const double u1 = c * u[a1] - sn * u[a2], u2 = sn * u[a1] + c * u[a2];
-          r[a1] = r1; r[a2] = r2; u[a1] = u1; u[a2] = u2;
-          LV(rx, 0) = r[0]; LV(ry, 0) = r[1]; LV(rz, 0) = r[2];
-          LV(ux, 0) = u[0]; LV(uy, 0) = u[1]; LV(uz, 0) = u[2];
+        } else {
+          rotate_periodic(ps, i, s, axis);
         }
         const int partner = gld(DM.surf_periodic + s) + 1;
         // translational: same side of the partner; rotational: the other side (both normals of a
@@ -609,20 +633,20 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
       if (n_coord != 1) {
         mark_lost(ps, gc, i);
       } else {
-        const V3 r = get_r(ps, i, 0);
-        V3 u = get_u(ps, i, 0);
-        V3 n = surf_normal(s, r); // Position::reflect, include/openmc/position.h:207-213
         if (bc == OMCGPU_BC_WHITE) {
-          u = diffuse_reflect(n, u, ps.seed[i]); // WhiteBC::handle_particle, src/boundary_condition.cpp:53-62
+          white_reflect(ps, i, s);
         } else {
+          const V3 r = get_r(ps, i, 0);
+          V3 u = get_u(ps, i, 0);
+          V3 n = surf_normal(s, r); // Position::reflect, include/openmc/position.h:207-213
           const double projection = dot(n, u);
           const double magnitude = dot(n, n);
           const double f = 2.0 * projection / magnitude;
           u = v3(u.x - n.x * f, u.y - n.y * f, u.z - n.z * f);
+          const double nrm = sqrt(u.x * u.x + u.y * u.y + u.z * u.z);
+          u = v3(u.x / nrm, u.y / nrm, u.z / nrm);
+          set_u(ps, i, 0, u);
         }
-        const double nrm = sqrt(u.x * u.x + u.y * u.y + u.z * u.z);
-        u = v3(u.x / nrm, u.y / nrm, u.z / nrm);
-        set_u(ps, i, 0, u);
         surface = -surface;
         ps.surface[i] = surface;
         if (!find_cell_from(ps, i, 1, surface))
@@ -2023,7 +2047,7 @@ static int upload_model(const omcgpu_model* m)
                  n_kt_ = nc ? m->cell_sqrtkT_ofs[nc] : 0, n_co_ = nc ? m->cell_offset_ofs[nc] : 0,
                  n_uc_ = nu ? m->univ_cell_ofs[nu] : 0, n_lu_ = nl ? m->lat_univ_ofs[nl] : 0,
                  n_lo_ = nl ? m->lat_offset_ofs[nl] : 0;
-    g_arena_size = 40 * 16 + (size_t)ns * (4 * 5 + 8 * 3 + 8 * OMCGPU_SURF_NCOEF + 2 * 4) +
+    g_arena_size = 40 * 16 + (size_t)ns * (4 * 5 + 8 * 3 + 8 * OMCGPU_SURF_NCOEF + 2 * 4) + 80 * (size_t)h.n_quadrics +
                    (size_t)nc * (4 * 12 + 8 * 12) + 4 * (n_tok_ + n_cm_ + n_co_ + n_uc_ + n_lu_ + n_lo_) + 8 * n_kt_ +
                    4 * (2 * (size_t)ns + 1) + 8 * n_tok_ + /* half-space candidate lists: <= 2 entries per token */
                    (size_t)nu * 4 + (size_t)nl * (4 * 8 + 8 * 6) + 4096;
@@ -2046,6 +2070,7 @@ static int upload_model(const omcgpu_model* m)
   UP(surf_periodic_axis, ns);
   UP(surf_id, ns);
   UP(surf_coef, (size_t)ns * OMCGPU_SURF_NCOEF);
+  UP(quad_coef, (size_t)h.n_quadrics * 10);
   const int n_tok = nc ? m->cell_region_ofs[nc] : 0;
   const int n_cmat = nc ? h.cell_mat_ofs[nc] : 0;
   const int n_ckt = nc ? m->cell_sqrtkT_ofs[nc] : 0;
@@ -2317,7 +2342,7 @@ static int upload_model(const omcgpu_model* m)
     omcgpu_model hd = h;
 #define REBASE(field) hd.field = reinterpret_cast<decltype(hd.field)>(reinterpret_cast<const char*>(h.field) - G.geo_blob)
     REBASE(surf_type); REBASE(surf_bc); REBASE(surf_periodic); REBASE(surf_periodic_shift); REBASE(surf_periodic_axis); REBASE(surf_id);
-    REBASE(surf_coef); REBASE(cell_id); REBASE(cell_type); REBASE(cell_universe); REBASE(cell_fill);
+    REBASE(surf_coef); REBASE(quad_coef); REBASE(cell_id); REBASE(cell_type); REBASE(cell_universe); REBASE(cell_fill);
     REBASE(cell_simple); REBASE(cell_region_ofs); REBASE(region_tokens); REBASE(cell_mat_ofs); REBASE(cell_material);
     REBASE(cell_sqrtkT_ofs); REBASE(cell_sqrtkT); REBASE(cell_translation); REBASE(cell_rotated); REBASE(cell_rotation);
     REBASE(cell_distribcell_index); REBASE(cell_offset_ofs); REBASE(cell_offset); REBASE(univ_cell_ofs);

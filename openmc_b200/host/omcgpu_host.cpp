@@ -179,7 +179,7 @@ void flatten_surfaces(Flat& F)
 {
   const int ns = model::surfaces.size();
   IV type(ns), bc(ns), partner(ns, -1), id(ns), paxis(ns, -1);
-  DV coef((size_t)ns * OMCGPU_SURF_NCOEF, 0.0), shift((size_t)ns * 3, 0.0);
+  DV coef((size_t)ns * OMCGPU_SURF_NCOEF, 0.0), shift((size_t)ns * 3, 0.0), quads;
   for (int i = 0; i < ns; ++i) {
     const Surface* s = model::surfaces[i].get();
     double* c = coef.data() + (size_t)i * OMCGPU_SURF_NCOEF;
@@ -208,9 +208,9 @@ void flatten_surfaces(Flat& F)
       type[i] = OMCGPU_SURF_ZCONE; c[0] = p->x0_; c[1] = p->y0_; c[2] = p->z0_; c[3] = p->radius_sq_;
     } else if (auto p = dynamic_cast<const SurfaceQuadric*>(s)) {
       type[i] = OMCGPU_SURF_QUADRIC;
+      c[0] = quads.size() / 10; // row of the side table
       const double q[10] = {p->A_, p->B_, p->C_, p->D_, p->E_, p->F_, p->G_, p->H_, p->J_, p->K_};
-      for (int k = 0; k < 10; ++k)
-        c[k] = q[k];
+      quads.insert(quads.end(), q, q + 10);
     } else {
       unsupported(fmt::format("surface {} (torus / DAGMC)", s->id_));
     }
@@ -255,6 +255,8 @@ void flatten_surfaces(Flat& F)
   KEEP(surf_periodic_axis, paxis);
   KEEP(surf_id, id);
   KEEP(surf_coef, coef);
+  F.m.n_quadrics = quads.size() / 10;
+  KEEP(quad_coef, quads);
 }
 
 //------------------------------------------------------------------------------

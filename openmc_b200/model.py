@@ -37,7 +37,7 @@ _SURF_KINDS = {
     "x-cylinder": (abi.OMCGPU_SURF_XCYLINDER, 3), "y-cylinder": (abi.OMCGPU_SURF_YCYLINDER, 3),
     "z-cylinder": (abi.OMCGPU_SURF_ZCYLINDER, 3), "sphere": (abi.OMCGPU_SURF_SPHERE, 4),
     "x-cone": (abi.OMCGPU_SURF_XCONE, 4), "y-cone": (abi.OMCGPU_SURF_YCONE, 4),
-    "z-cone": (abi.OMCGPU_SURF_ZCONE, 4), "quadric": (abi.OMCGPU_SURF_QUADRIC, 10),
+    "z-cone": (abi.OMCGPU_SURF_ZCONE, 4), "quadric": (abi.OMCGPU_SURF_QUADRIC, 10),   # 10 coefficients in quad_coef
 }
 _BCS = {"transmission": abi.OMCGPU_BC_NONE, "vacuum": abi.OMCGPU_BC_VACUUM,
         "reflective": abi.OMCGPU_BC_REFLECTIVE, "periodic": abi.OMCGPU_BC_PERIODIC,
@@ -403,15 +403,21 @@ class Model:
         coef = np.zeros((max(ns, 1), abi.OMCGPU_SURF_NCOEF))
         stype = np.zeros(max(ns, 1), np.int32)
         sbc = np.zeros(max(ns, 1), np.int32)
+        quads = []
         for i, s in enumerate(self.surfaces):
             kind, nco = _SURF_KINDS[s.kind]
             if len(s.coeffs) != nco:
                 raise ValueError(f"surface {s.id}: {s.kind} needs {nco} coefficients")
             stype[i] = kind
-            coef[i, :nco] = s.coeffs
+            if kind == abi.OMCGPU_SURF_QUADRIC:       # row of the side table
+                coef[i, 0] = len(quads)
+                quads.append([float(x) for x in s.coeffs])
+            else:
+                coef[i, :nco] = s.coeffs
             sbc[i] = _BCS[s.boundary]
         partner, shift, paxis = self._periodic_pairs({s.id: i for i, s in enumerate(self.surfaces)})
-        v.update(n_surfaces=ns, surf_type=stype, surf_bc=sbc, surf_coef=coef, surf_periodic=partner,
+        v.update(n_surfaces=ns, surf_type=stype, surf_bc=sbc, surf_coef=coef, n_quadrics=len(quads),
+                 quad_coef=np.array(quads or [[0.0]]).reshape(-1), surf_periodic=partner,
                  surf_periodic_shift=shift, surf_periodic_axis=paxis,
                  surf_id=np.array([s.id for s in self.surfaces] or [0], np.int32))
 

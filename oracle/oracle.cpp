@@ -312,6 +312,7 @@ double surf_evaluate(int s, Vec3 r)
     return r2 * r2 + r3 * r3 - c[3] * r1 * r1;
   }
   case OMCGPU_SURF_QUADRIC: { // SurfaceQuadric::evaluate, src/surface.cpp:861-868
+    c = M->quad_coef + 10 * (int)c[0];
     const double x = r.x, y = r.y, z = r.z;
     return x * (c[0] * x + c[3] * y + c[6]) + y * (c[1] * y + c[4] * z + c[7]) + z * (c[2] * z + c[5] * x + c[8]) + c[9];
   }
@@ -347,6 +348,7 @@ Vec3 surf_normal(int s, Vec3 r)
   case OMCGPU_SURF_ZCONE:
     return {2.0 * (r.x - c[0]), 2.0 * (r.y - c[1]), -2.0 * c[3] * (r.z - c[2])};
   case OMCGPU_SURF_QUADRIC: // SurfaceQuadric::normal, src/surface.cpp:941-949
+    c = M->quad_coef + 10 * (int)c[0];
     return {2.0 * c[0] * r.x + c[3] * r.y + c[5] * r.z + c[6], 2.0 * c[1] * r.y + c[3] * r.x + c[4] * r.z + c[7],
       2.0 * c[2] * r.z + c[4] * r.y + c[5] * r.x + c[8]};
   }
@@ -489,6 +491,7 @@ double surf_distance(int s, Vec3 r, Vec3 u, bool coincident)
   case OMCGPU_SURF_ZCONE:
     return cone_axis_distance(r.z - c[2], r.x - c[0], r.y - c[1], u.z, u.x, u.y, c[3], coincident);
   case OMCGPU_SURF_QUADRIC: { // SurfaceQuadric::distance, src/surface.cpp:870-939
+    c = M->quad_coef + 10 * (int)c[0];
     const double A = c[0], B = c[1], C = c[2], D = c[3], E = c[4], F = c[5], G = c[6], H = c[7], J = c[8], K = c[9];
     const double x = r.x, y = r.y, z = r.z, uu = u.x, v = u.y, w = u.z;
     const double a = A * uu * uu + B * v * v + C * w * w + D * uu * v + E * v * w + F * uu * w;

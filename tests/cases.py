@@ -99,12 +99,6 @@ def load_model_npz(path):
     nc = int(vals["n_cells"])
     vals.setdefault("cell_rotated", np.zeros(nc, np.int32))
     vals.setdefault("cell_rotation", np.zeros(9 * nc))
-    # fixtures written when a surface kept 4 coefficients (general quadrics keep 10)
-    ns = int(vals["n_surfaces"])
-    if vals["surf_coef"].size == 4 * max(ns, 1) and abi.OMCGPU_SURF_NCOEF != 4:
-        wide = np.zeros((max(ns, 1), abi.OMCGPU_SURF_NCOEF))
-        wide[:, :4] = np.asarray(vals["surf_coef"]).reshape(-1, 4)
-        vals["surf_coef"] = wide
     # per-tally estimator added later: the fixtures' tallies are tracklength tallies
     vals.setdefault("tally_estimator", np.full(max(int(vals["n_tallies"]), 1), abi.OMCGPU_ESTIMATOR_TRACKLENGTH, np.int32))
     return abi.ModelHandle(vals)
