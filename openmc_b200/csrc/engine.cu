@@ -526,35 +526,46 @@ OMC_D bool ev_revive(const PState& ps, int64_t i)
   return ps.wgt[i] != 0.0;
 }
 
-// Rare boundary conditions, out of line so that the crossing kernel does not carry them.
+// Rare boundary conditions, out of line so that the crossing kernel does not carry them.  They take
+// and return VALUES: a `const PState&` argument would make the caller keep a 1 KB copy of the column
+// pointers in its stack frame (measured: +30 % on the crossing kernel, profiles/r59).
+struct PosDir {
+  V3 r, u;
+};
 // RotationalPeriodicBC::handle_particle, src/boundary_condition.cpp:242-287: position and direction
 // rotated about x / y / z by the angle whose cosine and sine the flattener took with the host's libm
-OMC_OOL void rotate_periodic(const PState& ps, int64_t i, int s, int axis)
+OMC_OOL PosDir rotate_periodic(V3 r, V3 u, int s, int axis)
 {
   const double* t = DM.surf_periodic_shift + 3 * s;
   const double c = gld(t), sn = gld(t + 1);
-  const V3 r = get_r(ps, i, 0), u = get_u(ps, i, 0);
-  V3 nr = r, nu = u;
+  PosDir o;
+  o.r = r;
+  o.u = u;
   if (axis == 0) { // independent y, dependent z
-    nr.y = c * r.y - sn * r.z; nr.z = sn * r.y + c * r.z;
-    nu.y = c * u.y - sn * u.z; nu.z = sn * u.y + c * u.z;
-  } else if (axis == 1) { // independent x, dependent z (the reference's left-handed convention for y)
-    nr.x = c * r.x - sn * r.z; nr.z = sn * r.x + c * r.z;
-    nu.x = c * u.x - sn * u.z; nu.z = sn * u.x + c * u.z;
+    o.r.y = c * r.y - sn * r.z; o.r.z = sn * r.y + c * r.z;
+    o.u.y = c * u.y - sn * u.z; o.u.z = sn * u.y + c * u.z;
+  } else if (axis == 1) { // independent x, dependent z (the reference's convention for y)
+    o.r.x = c * r.x - sn * r.z; o.r.z = sn * r.x + c * r.z;
+    o.u.x = c * u.x - sn * u.z; o.u.z = sn * u.x + c * u.z;
   } else { // independent x, dependent y
-    nr.x = c * r.x - sn * r.y; nr.y = sn * r.x + c * r.y;
-    nu.x = c * u.x - sn * u.y; nu.y = sn * u.x + c * u.y;
+    o.r.x = c * r.x - sn * r.y; o.r.y = sn * r.x + c * r.y;
+    o.u.x = c * u.x - sn * u.y; o.u.y = sn * u.x + c * u.y;
   }
-  LV(rx, 0) = nr.x; LV(ry, 0) = nr.y; LV(rz, 0) = nr.z;
-  set_u(ps, i, 0, nu);
+  return o;
 }
-// WhiteBC::handle_particle, src/boundary_condition.cpp:53-62
-OMC_OOL void white_reflect(const PState& ps, int64_t i, int s)
+// WhiteBC::handle_particle, src/boundary_condition.cpp:53-62 -> new direction, advanced seed
+struct DirSeed {
+  V3 u;
+  uint64_t seed;
+};
+OMC_OOL DirSeed white_reflect(V3 r, V3 u, uint64_t seed, int s)
 {
-  const V3 r = get_r(ps, i, 0);
-  V3 u = diffuse_reflect(surf_normal(s, r), get_u(ps, i, 0), ps.seed[i]);
-  const double nrm = sqrt(u.x * u.x + u.y * u.y + u.z * u.z);
-  set_u(ps, i, 0, v3(u.x / nrm, u.y / nrm, u.z / nrm));
+  DirSeed o;
+  o.seed = seed;
+  const V3 d = diffuse_reflect(surf_normal(s, r), u, o.seed);
+  const double nrm = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+  o.u = v3(d.x / nrm, d.y / nrm, d.z / nrm);
+  return o;
 }
 
 // Particle::event_cross_surface + cross_surface + BCs + cross_lattice:
@@ -619,7 +630,11 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
           LV(ry, 0) += gld(t + 1);
           LV(rz, 0) += gld(t + 2);
         } else {
-          rotate_periodic(ps, i, s, axis);
+          const PosDir o = rotate_periodic(get_r(ps, i, 0), get_u(ps, i, 0), s, axis);
+          LV(rx, 0) = o.r.x;
+          LV(ry, 0) = o.r.y;
+          LV(rz, 0) = o.r.z;
+          set_u(ps, i, 0, o.u);
         }
         const int partner = gld(DM.surf_periodic + s) + 1;
         // translational: same side of the partner; rotational: the other side (both normals of a
@@ -634,7 +649,9 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
         mark_lost(ps, gc, i);
       } else {
         if (bc == OMCGPU_BC_WHITE) {
-          white_reflect(ps, i, s);
+          const DirSeed o = white_reflect(get_r(ps, i, 0), get_u(ps, i, 0), ps.seed[i], s);
+          ps.seed[i] = o.seed;
+          set_u(ps, i, 0, o.u);
         } else {
           const V3 r = get_r(ps, i, 0);
           V3 u = get_u(ps, i, 0);
