@@ -2353,6 +2353,151 @@ OMC_D void mesh_march(int m, V3 r0, V3 u, double total, double t0, double t1, Em
     mesh_march_nd<1>(m, r0, u, total, t0, t1, emit);
 }
 
+// -----------------------------------------------------------------------------
+// The same DDA with the per-FLIGHT constants taken out (k_score, second version).  A flight's own
+// lane computes them once -- the only divisions of the ray trace: first crossing of every axis (the
+// reference's formula), distance between crossings w / |u| and its inverse -- and publishes them;
+// any lane can then start ANY part [ta, tb] of the flight with a multiply per axis
+// (mesh_part_begin: crossings of axis k before ta = floor((ta - tnext0) |u| / w) + 1), so parts
+// can be a few cells short and the lanes of a warp stay in step.  Crossing distances inside a part
+// are tnext0 + n tdel followed by additions of tdel: as in mesh_march_nd they differ from the
+// reference's per-crossing quotient by rounding only, the bins are the same, and a piece that
+// straddles a cut is emitted as two pieces of the same bin.
+// -----------------------------------------------------------------------------
+constexpr int MESH_RAY_AXES = 3;
+struct MeshRay {
+  double tnext0[MESH_RAY_AXES], tdel[MESH_RAY_AXES], inv_tdel[MESH_RAY_AXES];
+  int left[MESH_RAY_AXES], stride[MESH_RAY_AXES]; // cells ahead before the mesh ends, bin increment of a step
+  int bin0;
+};
+
+// false: the flight starts outside the mesh (the exact routine traces it).  Axes the mesh does not
+// have are never crossed (tnext0 = INFTY).
+OMC_HD bool mesh_ray_setup(int m, V3 r0, V3 u, MeshRay& ray)
+{
+  const int nd = ld(DM.mesh_ndim + m);
+  bool in_mesh = true;
+  int bin = 0, cells = 1;
+#pragma unroll
+  for (int k = 0; k < MESH_RAY_AXES; ++k) {
+    ray.tnext0[k] = INFTY;
+    ray.tdel[k] = 0.0;
+    ray.inv_tdel[k] = 0.0;
+    ray.left[k] = 0;
+    ray.stride[k] = 0;
+    if (k < nd) {
+      const double ll = ld(DM.mesh_lower_left + 3 * m + k), w = ld(DM.mesh_width + 3 * m + k);
+      const int shape = ld(DM.mesh_shape + 3 * m + k);
+      const double rk = comp(r0, k), uk = comp(u, k);
+      const int idx = mesh_index(rk + TINY_BIT * uk, ll, w);
+      in_mesh = in_mesh && idx >= 1 && idx <= shape;
+      const bool pos = uk > 0;
+      if (!(fabs(uk) < FP_PRECISION)) {
+        ray.tnext0[k] = ((ll + (pos ? idx : idx - 1) * w) - rk) / uk; // the reference's formula for the first crossing
+        ray.tdel[k] = w / fabs(uk);
+        ray.inv_tdel[k] = fabs(uk) / w;
+      }
+      ray.left[k] = pos ? shape - idx : idx - 1;
+      ray.stride[k] = pos ? cells : -cells;
+      bin += (idx - 1) * cells;
+      cells *= shape;
+    }
+  }
+  ray.bin0 = bin;
+  return in_mesh;
+}
+
+// crossings of one axis strictly before distance t, at most left + 1 (= the ray has left the mesh);
+// tn: distance of the first crossing at or after t
+OMC_HD int mesh_ray_crossed(double tnext0, double tdel, double inv_tdel, int left, double t, double& tn)
+{
+  int n = 0;
+  tn = tnext0;
+  if (t > tnext0) {
+    const double q = (t - tnext0) * inv_tdel;
+    n = q >= (double)left + 1.0 ? left + 1 : (int)q + 1;
+    tn = tnext0 + n * tdel;
+    if (tn < t) { // the quotient was rounded down across an integer
+      ++n;
+      tn += tdel;
+    }
+  }
+  return n;
+}
+
+// mesh cells the flight visits inside the mesh (to balance the parts)
+OMC_HD int mesh_ray_cells(const MeshRay& ray, double total)
+{
+  int n = 1;
+#pragma unroll
+  for (int k = 0; k < MESH_RAY_AXES; ++k) {
+    double tn;
+    const int c = mesh_ray_crossed(ray.tnext0[k], ray.tdel[k], ray.inv_tdel[k], ray.left[k], total, tn);
+    n += c > ray.left[k] ? ray.left[k] : c;
+  }
+  return n;
+}
+
+// the part [ta, tb] of a flight that starts inside the mesh: emit(bin, fraction of total).
+// RAY: anything with the members of MeshRay read as ray.member(k) -- registers on the host,
+// the warp's staging area in k_score
+template<int ND, bool LENGTHS = false, class Ray, class Emit>
+OMC_D void mesh_part_march(const Ray& ray, double ta, double tb, double inv_total, Emit& emit)
+{ // LENGTHS: emit(bin, length) -- the caller has folded 1 / total into its scores
+  double tnext[ND], tdel[ND];
+  int left[ND], stride[ND];
+  int bin = ray.bin0();
+#pragma unroll
+  for (int k = 0; k < ND; ++k) {
+    tdel[k] = ray.tdel(k);
+    stride[k] = ray.stride(k);
+    const int l = ray.left(k);
+    const int n = mesh_ray_crossed(ray.tnext0(k), tdel[k], ray.inv_tdel(k), l, ta, tnext[k]);
+    if (n > l)
+      return; // the flight left the mesh before this part
+    left[k] = l - n;
+    bin += n * stride[k];
+  }
+  double traveled = ta;
+#pragma unroll 1
+  for (;;) { // ends: every crossing distance grows by tdel > 0, an axis that is never crossed sits at INFTY
+    int k = 0;
+    double dk = tnext[0];
+    if (ND > 1 && tnext[1] < dk) {
+      k = 1;
+      dk = tnext[1];
+    }
+    if (ND > 2 && tnext[2] < dk) {
+      k = 2;
+      dk = tnext[2];
+    }
+    const double len = (dk < tb ? dk : tb) - traveled;
+    emit(bin, LENGTHS ? len : len * inv_total);
+    traveled = dk;
+    if (traveled >= tb)
+      break;
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+      const bool ka = k == a;
+      if (ka && left[a] == 0)
+        return;
+      left[a] -= ka ? 1 : 0;
+      bin += ka ? stride[a] : 0;
+      tnext[a] += ka ? tdel[a] : 0.0;
+    }
+  }
+}
+
+struct MeshRayRegs { // Ray view of a MeshRay in registers (host compile, single-lane paths)
+  const MeshRay* r;
+  OMC_HD double tnext0(int k) const { return r->tnext0[k]; }
+  OMC_HD double tdel(int k) const { return r->tdel[k]; }
+  OMC_HD double inv_tdel(int k) const { return r->inv_tdel[k]; }
+  OMC_HD int left(int k) const { return r->left[k]; }
+  OMC_HD int stride(int k) const { return r->stride[k]; }
+  OMC_HD int bin0() const { return r->bin0; }
+};
+
 // Number of mesh cells the track r0 -> r1 visits (exact for a track inside the
 // mesh, an estimate otherwise) -- only used to balance work between lanes.
 OMC_HD int mesh_cells_visited(int m, V3 r0, V3 r1, V3 u)

@@ -1129,6 +1129,91 @@ OMC_D int score_prepare(const PState& ps, const Flight& f, int t, double* values
   return nc < 1 ? 1 : nc;
 }
 
+// The same preparation for the second version of k_score: the lane also computes the per-flight
+// constants of the mesh ray trace (mesh_ray_setup: the only divisions of the trace), so that the
+// parts can be started by any lane without a division.  Flights the DDA does not cover (they
+// start outside the mesh, or are shorter than 2 TINY_BIT) are traced here by their own lane
+// with the reference's loop.  Returns the number of parts; dpart = length of a part.
+OMC_D int score_prepare2(const PState& ps, const Flight& f, int t, double* values, int score_part,
+  int64_t& base, double* val, MeshRay& ray, double& dpart, unsigned long long* red_counter = nullptr)
+{
+  if (ld(DM.tally_estimator + t) != OMCGPU_ESTIMATOR_TRACKLENGTH)
+    return 0; // collision-estimator tallies are scored by the collision kernel
+  TallyEval te;
+  const int64_t i = f.pidx; // cell / universe filters read the particle's coordinate levels
+  const int n_coord = f.pidx >= 0 ? ps.n_coord[i] : 0;
+  if (!tally_prepare(ps, i, n_coord, t, f.E, f.sc, te))
+    return 0;
+  if (te.mesh_pos < 0) {
+    tally_emit(te, t, 0, 1.0, f.sc, values);
+    return 0;
+  }
+  if (f.total == 0.0)
+    return 0;
+  bool simple = true;
+  base = 0;
+  for (int k = 0; k < te.nf; ++k) {
+    if (k == te.mesh_pos)
+      continue;
+    if (te.nb[k] != 1)
+      simple = false;
+    base += (int64_t)te.bins[k][0] * te.stride[k];
+  }
+  if (!simple) { // several matches per filter: this lane traces the whole flight
+    score_mesh_generic(te, t, f.sc, values, f.r0, f.u, f.total);
+    return 0;
+  }
+  const int ns = ld(DM.tally_n_scores + t);
+  bool any = false;
+#pragma unroll
+  for (int s = 0; s < SCORE_NVAL; ++s) {
+    val[s] = 0.0;
+    if (s < ns) {
+      bool skip;
+      const double v = score_value(ld(DM.tally_scores + OMCGPU_MAX_SCORES * t + s), f.sc, skip);
+      if (!skip)
+        val[s] = v;
+      any = any || val[s] != 0.0;
+    }
+  }
+  if (!any)
+    return 0;
+  if (f.total < 2 * TINY_BIT || !mesh_ray_setup(te.mesh, f.r0, f.u, ray)) {
+    PartEmit<SCORE_NVAL> em;
+#pragma unroll
+    for (int s = 0; s < SCORE_NVAL; ++s)
+      em.val[s] = val[s];
+    em.set(values + ld(DM.tally_result_ofs + t), base, te.stride[te.mesh_pos], ns);
+    mesh_march_exact(te.mesh, f.r0, f.u, f.total, 0.0, f.total, em);
+    return 0;
+  }
+  const int cells = mesh_ray_cells(ray, f.total);
+  if (red_counter) { // cells x scores that add something: the REDs this flight issues
+    int nnz = 0;
+    for (int s = 0; s < SCORE_NVAL; ++s)
+      nnz += val[s] != 0.0 ? 1 : 0;
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+    atomicAdd(red_counter, (unsigned long long)(cells * nnz));
+#else
+    *red_counter += (unsigned long long)(cells * nnz);
+#endif
+  }
+  int nc = (cells + score_part - 1) / score_part;
+  nc = nc < 1 ? 1 : nc;
+  dpart = f.total / nc;
+  return nc;
+}
+
+// part c of nc: [c dpart, (c + 1) dpart], the last one ends at total exactly
+OMC_HD double part_begin(int c, double dpart)
+{
+  return c * dpart;
+}
+OMC_HD double part_end(int c, int nc, double dpart, double total)
+{
+  return c + 1 >= nc ? total : (c + 1) * dpart;
+}
+
 // position of the mesh filter and its stride are properties of the tally
 OMC_HD void tally_mesh_info(int t, int& mesh, int& mesh_stride)
 {
@@ -1262,7 +1347,164 @@ __global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score(int64_t n_ub, 
   __syncwarp(); // the staging area is reused by the next block of flights
   }
 }
+// ---- second version: per-flight ray constants in the staging area, short parts, lanes in step ------
+// staging area of one warp, one column per lane (= per flight)
+constexpr int SD_TNEXT0 = 0, SD_TDEL = 3, SD_INV_TDEL = 6, SD_TOTAL = 9, SD_INV_TOTAL = 10, SD_DPART = 11,
+              SD_VAL = 12, SD_N = SD_VAL + SCORE_NVAL;
+constexpr int SI_LEFT = 0, SI_STRIDE = 3, SI_BIN0 = 6, SI_N = 7;
+__device__ __noinline__ int score_lane2(int64_t j, int buf, int t, double* values, int score_part,
+  double* sd, int* si, int64_t* sbase, unsigned long long* red_counter)
+{
+  const Flight f = load_flight(c_fl[buf], j);
+  double val[SCORE_NVAL];
+  int64_t base = 0;
+  MeshRay ray;
+  double dpart = 0.0;
+  const int nc = score_prepare2(c_ps, f, t, values, score_part, base, val, ray, dpart, red_counter);
+  if (nc > 0) {
+#pragma unroll
+    for (int k = 0; k < MESH_RAY_AXES; ++k) {
+      sd[(SD_TNEXT0 + k) * 32] = ray.tnext0[k];
+      sd[(SD_TDEL + k) * 32] = ray.tdel[k];
+      sd[(SD_INV_TDEL + k) * 32] = ray.inv_tdel[k];
+      si[(SI_LEFT + k) * 32] = ray.left[k];
+      si[(SI_STRIDE + k) * 32] = ray.stride[k];
+    }
+    si[SI_BIN0 * 32] = ray.bin0;
+    sd[SD_TOTAL * 32] = f.total;
+    sd[SD_INV_TOTAL * 32] = 1.0 / f.total;
+    sd[SD_DPART * 32] = dpart;
+#pragma unroll
+    for (int s = 0; s < SCORE_NVAL; ++s)
+      sd[(SD_VAL + s) * 32] = val[s];
+    *sbase = base;
+  }
+  return nc;
+}
+
+// the lanes of a warp trace the parts of the warp's 32 flights in rounds of 32 parts: every lane
+// starts its part (multiplies only), then all lanes step through their few cells together
+// (out of line, one function per variant: the hot loops get the kernel's whole register budget
+// instead of sharing it with everything k_score2 keeps live -- inlined, they reloaded spilled
+// values from local memory in every DDA step, profiles/r64)
+constexpr int SCORE_WARPS = BLOCK / 32;
+__shared__ double s2_d[SCORE_WARPS][SD_N][32];
+__shared__ int s2_i[SCORE_WARPS][SI_N][32];
+__shared__ int64_t s2_base[SCORE_WARPS][32];
+__shared__ int s2_incl[SCORE_WARPS][32];
+struct MeshRayStaged { // Ray view (mesh_part_march) of column o of the warp's staging area
+  int warp, o;
+  __device__ __forceinline__ double tnext0(int k) const { return s2_d[warp][SD_TNEXT0 + k][o]; }
+  __device__ __forceinline__ double tdel(int k) const { return s2_d[warp][SD_TDEL + k][o]; }
+  __device__ __forceinline__ double inv_tdel(int k) const { return s2_d[warp][SD_INV_TDEL + k][o]; }
+  __device__ __forceinline__ int left(int k) const { return s2_i[warp][SI_LEFT + k][o]; }
+  __device__ __forceinline__ int stride(int k) const { return s2_i[warp][SI_STRIDE + k][o]; }
+  __device__ __forceinline__ int bin0() const { return s2_i[warp][SI_BIN0][o]; }
+};
+template<int NS, int ND>
+__device__ __noinline__ void score_parts2(int mesh_stride, int ns, double* results, int n_parts)
+{
+  const int warp = threadIdx.x >> 5;
+  PartEmit<NS> em;
+  const int n_round = (n_parts + 31) & ~31;
+  for (int item = threadIdx.x & 31; item < n_round; item += 32) {
+    const bool have = item < n_parts;
+    MeshRayStaged ray;
+    ray.warp = warp;
+    ray.o = 0;
+    double ta = 0.0, tb = 0.0;
+    if (have) {
+      const int* incl = s2_incl[warp];
+      int o = 0; // owner: first lane whose inclusive count exceeds item
+      for (int step = 16; step > 0; step >>= 1)
+        if (incl[o + step - 1] <= item)
+          o += step;
+      const int before = o > 0 ? incl[o - 1] : 0;
+      const int c = item - before;
+      const int onc = incl[o] - before;
+      const double dpart = s2_d[warp][SD_DPART][o];
+      ta = part_begin(c, dpart);
+      tb = part_end(c, onc, dpart, s2_d[warp][SD_TOTAL][o]);
+      const double inv_total = s2_d[warp][SD_INV_TOTAL][o];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) // score per unit length: the march emits lengths
+        em.val[s] = s2_d[warp][SD_VAL + s][o] * inv_total;
+      em.set(results, s2_base[warp][o], mesh_stride, ns);
+      ray.o = o;
+    }
+    __syncwarp();
+    if (have)
+      mesh_part_march<ND, true>(ray, ta, tb, 1.0, em);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK, SCORE_MINBLOCKS) k_score2(int64_t n_ub, EvArgs a)
+{
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n = *a.n_flights < a.fl.cap ? *a.n_flights : a.fl.cap;
+  double* values = a.gc.tally_values + (int64_t)(blockIdx.x % a.gc.tally_replicas) * a.gc.tally_replica_stride;
+  unsigned long long* red_counter = a.gc.count_lookups ? a.gc.counters + CNT_RED : nullptr;
+  int64_t wbase = (int64_t)blockIdx.x * BLOCK + 32 * warp;
+  for (;; wbase += (int64_t)gridDim.x * BLOCK) {
+    if (a.cursor) {
+      int fetched = 0;
+      if (lane == 0)
+        fetched = atomicAdd(a.cursor, 32);
+      wbase = __shfl_sync(0xffffffffu, fetched, 0);
+    }
+    if (wbase >= n || wbase >= n_ub)
+      break;
+    const int64_t tid = wbase + lane;
+    const bool active = tid < n && a.fl.pidx[tid] != PIDX_NO_FLIGHT;
+    for (int t = 0; t < DM.n_tallies; ++t) {
+      __syncwarp();
+      int nc = 0;
+      if (active)
+        nc = score_lane2(tid, a.fl_buf, t, values, a.gc.score_part, &s2_d[warp][0][lane], &s2_i[warp][0][lane],
+          &s2_base[warp][lane], red_counter);
+      int mesh, mesh_stride;
+      tally_mesh_info(t, mesh, mesh_stride);
+      if (mesh < 0)
+        continue; // warp-uniform: a property of the tally
+      int incl = nc; // inclusive warp scan of the part counts
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+          incl += v;
+      }
+      const int n_parts = __shfl_sync(0xffffffffu, incl, 31);
+      if (n_parts == 0)
+        continue;
+      s2_incl[warp][lane] = incl;
+      __syncwarp();
+      const int ns = ld(DM.tally_n_scores + t);
+      const bool d2 = ld(DM.mesh_ndim + mesh) == 2; // 1-D meshes take the 3-axis loop (absent axes are never crossed)
+      double* results = values + ld(DM.tally_result_ofs + t);
+#define SCORE_PARTS2(NS_) \
+  do { \
+    if (d2) \
+      score_parts2<NS_, 2>(mesh_stride, ns, results, n_parts); \
+    else \
+      score_parts2<NS_, 3>(mesh_stride, ns, results, n_parts); \
+  } while (0)
+      if (ns == 1)
+        SCORE_PARTS2(1);
+      else if (ns <= 3)
+        SCORE_PARTS2(3);
+      else
+        SCORE_PARTS2(SCORE_NVAL);
+#undef SCORE_PARTS2
+    }
+    __syncwarp(); // the staging area is reused by the next block of flights
+  }
+}
+
+#ifndef SCORE_PART_V2
+#define SCORE_PART_V2 6 /* mesh cells per part, k_score2 */
+#endif
 static int g_score_grid_cap = 0; // 0: one block per BLOCK flights; else at most this many blocks
+static int g_score_version = 1;  // OMCGPU_SCORE_VERSION=2: k_score2 (measured slower, profiles/README.md r63-r65)
 #define LAUNCH_SCORE(n_ub, stream, args) \
   do { \
     if ((n_ub) > 0) { \
@@ -1271,12 +1513,20 @@ static int g_score_grid_cap = 0; // 0: one block per BLOCK flights; else at most
         grid_ = (unsigned)g_score_grid_cap; \
       if ((args).cursor && grid_ > (unsigned)(dyn_grid_sms() * SCORE_MINBLOCKS)) \
         grid_ = (unsigned)(dyn_grid_sms() * SCORE_MINBLOCKS); \
-      k_score<<<grid_, BLOCK, 0, stream>>>((int64_t)(n_ub), args); \
+      if (g_score_version == 1) \
+        k_score<<<grid_, BLOCK, 0, stream>>>((int64_t)(n_ub), args); \
+      else \
+        k_score2<<<grid_, BLOCK, 0, stream>>>((int64_t)(n_ub), args); \
       ++g_launches; \
     } \
   } while (0)
 #else
 // host compile (tests only): same preparation, same parts, traced one after another
+#ifndef SCORE_PART_V2
+#define SCORE_PART_V2 6
+#endif
+static int g_score_version_host = 1;
+#define g_score_version g_score_version_host
 void k_score(int64_t n_ub, EvArgs a)
 {
   const int64_t n = *a.n_flights < a.fl.cap ? *a.n_flights : a.fl.cap;
@@ -1287,12 +1537,31 @@ void k_score(int64_t n_ub, EvArgs a)
     for (int t = 0; t < DM.n_tallies; ++t) {
       PartEmit<SCORE_NVAL> em;
       int64_t base = 0;
-      const int nc = score_prepare(a.ps, f, t, a.gc.tally_values, a.gc.score_part, base, em.val);
       int mesh, mesh_stride;
       tally_mesh_info(t, mesh, mesh_stride);
+      if (g_score_version_host == 1) {
+        const int nc = score_prepare(a.ps, f, t, a.gc.tally_values, a.gc.score_part, base, em.val);
+        em.set(a.gc.tally_values + DM.tally_result_ofs[t], base, mesh_stride, DM.tally_n_scores[t]);
+        for (int c = 0; c < nc; ++c)
+          mesh_march(mesh, f.r0, f.u, f.total, part_bound(c, nc, f.total), part_bound(c + 1, nc, f.total), em);
+        continue;
+      }
+      // the arithmetic of k_score2: ray constants once per flight, parts started without a division
+      MeshRay ray;
+      double dpart = 0.0;
+      const int nc = score_prepare2(a.ps, f, t, a.gc.tally_values, a.gc.score_part, base, em.val, ray, dpart);
+      if (nc == 0)
+        continue;
       em.set(a.gc.tally_values + DM.tally_result_ofs[t], base, mesh_stride, DM.tally_n_scores[t]);
-      for (int c = 0; c < nc; ++c)
-        mesh_march(mesh, f.r0, f.u, f.total, part_bound(c, nc, f.total), part_bound(c + 1, nc, f.total), em);
+      MeshRayRegs view;
+      view.r = &ray;
+      const double inv_total = 1.0 / f.total;
+      for (int c = 0; c < nc; ++c) {
+        if (DM.mesh_ndim[mesh] == 2)
+          mesh_part_march<2>(view, part_begin(c, dpart), part_end(c, nc, dpart, f.total), inv_total, em);
+        else
+          mesh_part_march<3>(view, part_begin(c, dpart), part_end(c, nc, dpart, f.total), inv_total, em);
+      }
     }
   }
 }
@@ -3213,6 +3482,8 @@ int omcgpu_set_option(const char* name, int64_t value)
     G.sync_every = std::min<int64_t>(std::max<int64_t>(1, value), RING / 2);
   else if (k == "score_part")
     G.score_part = (int)std::max<int64_t>(1, value);
+  else if (k == "score_version")
+    g_score_version = value == 2 ? 2 : 1;
   else if (k == "probe_kT_neV") // cell temperature of the stand-alone lookup / collision probes, in 1e-9 eV
     G.probe_kT = 1e-9 * (double)value;
   else
@@ -3397,6 +3668,9 @@ static int init_impl(const omcgpu_model* model, int device, int64_t max_particle
     G.tail_threshold = std::atoll(t);
   if (const char* t = std::getenv("OMCGPU_TRACE"))
     G.trace = std::fopen(t, "a");
+  if (const char* t = std::getenv("OMCGPU_SCORE_VERSION"))
+    g_score_version = std::atoi(t) == 2 ? 2 : 1;
+  G.score_part = g_score_version == 1 ? 16 : SCORE_PART_V2;
   if (const char* t = std::getenv("OMCGPU_SCORE_PART"))
     G.score_part = std::max(1, std::atoi(t));
   const int64_t cap = max_particles;

@@ -31,9 +31,12 @@ def test_golden_through_engine(emu_lib, name, threshold, sweep, monkeypatch):
     sim.simulation_finalize()
 
 
-def test_host_buffer_generation_matches_oracle(emu_lib, monkeypatch):
-    """omcgpu_transport_generation == oracle generation: identical sorted fission bank."""
+@pytest.mark.parametrize("score_version", [1, 2])
+def test_host_buffer_generation_matches_oracle(emu_lib, monkeypatch, score_version):
+    """omcgpu_transport_generation == oracle generation: identical sorted fission bank.
+    score_version 2: the arithmetic of k_score2 (ray constants per flight, parts started by a multiply)."""
     monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", "0")
+    monkeypatch.setenv("OMCGPU_SCORE_VERSION", str(score_version))
     model, box, of = cases.build("mg_temperature_multi")
     o = Oracle(model)
     src = o.sample_initial_source(2000, box, of)

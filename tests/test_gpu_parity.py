@@ -116,6 +116,35 @@ def test_pincell_multigroup_generation_matches_oracle(gpu_engine, threshold, mon
     gpu_engine.finalize()
 
 
+def test_second_scoring_kernel_equals_the_first(gpu_engine, monkeypatch):
+    """k_score2 (OMCGPU_SCORE_VERSION=2: ray constants once per flight, short parts started by a
+    multiply, lanes in step) scores the same bins with the same lengths as k_score: every bin of
+    the C1 tallies to 1e-10 relative (the two differ by the rounding of the crossing distances)."""
+    from openmc_b200 import examples, mgxs
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", "2048")
+    m, libx, box, of = examples.pincell_multigroup()
+    model = mgxs.build_mg_model(m, libx)
+    n = 20000
+    src = Oracle(model).sample_initial_source(n, box, of)
+    res = {}
+    for version in ("1", "2"):
+        monkeypatch.setenv("OMCGPU_SCORE_VERSION", version)
+        gpu_engine.init(model, 0, n)
+        gi = gpu_engine.gen_in(n, 0, 0, 1.0, True)
+        fb, out = gpu_engine.transport_generation(gi, src)
+        tall = []
+        for t in range(int(model["n_tallies"])):
+            k = int(model["tally_result_ofs"][t + 1] - model["tally_result_ofs"][t])
+            v = np.zeros(k); gpu_engine.tally_results(t, v)
+            tall.append(v)
+        res[version] = (out.n_fission, out.n_events, tall)
+        gpu_engine.finalize()
+    assert res["1"][:2] == res["2"][:2]
+    for a, b in zip(res["1"][2], res["2"][2]):
+        assert a.sum() > 0
+        np.testing.assert_allclose(b, a, rtol=1e-10, atol=1e-12 * a.max())
+
+
 def test_device_collision_equals_reference_vectors_on_gpu(gpu_engine):
     """collision_ce ON THE DEVICE (omcgpu_collide) against tests/golden/refcoll_ce.npz, the
     vectors the reference's collision() wrote.  Integer results (seed = the number of random
