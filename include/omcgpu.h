@@ -113,7 +113,7 @@ extern "C" {
 #define OMCGPU_FILTER_DISTRIBCELL 5 /* filter_idata = { cell index }; bins = instances of that cell
                                      (src/tallies/filter_distribcell.cpp:40-63) */
 /* TallyEstimator, include/openmc/constants.h:299 */
-#define OMCGPU_ESTIMATOR_ANALOG      0 /* refused by omcgpu_init */
+#define OMCGPU_ESTIMATOR_ANALOG      0 /* scored after the collision from the collision records */
 #define OMCGPU_ESTIMATOR_TRACKLENGTH 1
 #define OMCGPU_ESTIMATOR_COLLISION   2
 #define OMCGPU_SCORE_FLUX        0

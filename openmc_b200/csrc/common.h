@@ -198,6 +198,16 @@ struct GenCtx {
   int64_t tally_replica_stride; // doubles between two replicas of the VALUE arrays (k_score spreads its REDs)
   int32_t tally_replicas;
   int64_t fission_cap;
+  // Collision records for the tallies scored AFTER a collision (analog estimator; collision
+  // estimator of multigroup runs with survival biasing): column k of particle idx is
+  // an_d[k * an_cap + idx] / an_i[k * an_cap + idx] (AN_* below).  Null when the model has no
+  // such tally -- the collision kernels then carry one uniform branch and no stores.
+  double* an_d;
+  int32_t* an_i;
+  int64_t an_cap;
 };
+enum { AN_RX, AN_RY, AN_RZ, AN_E_LAST, AN_WGT_LAST, AN_WGT_BANK, AN_MICRO_T, AN_MICRO_A, AN_MICRO_F, AN_MICRO_NF,
+  AN_XS_T, AN_XS_A, AN_XS_F, AN_XS_NF, AN_ND };
+enum { AN_SCATTER, AN_FISSION, AN_ALIVE, AN_G_LAST, AN_G_POST, AN_MATERIAL, AN_MG_BA, AN_NI };
 
 } // namespace omc

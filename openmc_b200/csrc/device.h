@@ -1792,6 +1792,24 @@ OMC_HD int fission_site_count(Collider& p, double nu_t)
   return nu;
 }
 
+// collision record of the particle the Collider came from (its index in the generation)
+OMC_HD int64_t an_index(const Collider& p, const GenCtx& gc)
+{
+  return p.id - gc.id_offset - 1;
+}
+OMC_HD bool an_on(const GenCtx& gc) // records are written only while tallies are active
+{
+  return gc.an_d != nullptr && gc.tallies_active;
+}
+OMC_HD void an_put(const GenCtx& gc, int64_t idx, int k, double v)
+{
+  gc.an_d[k * gc.an_cap + idx] = v;
+}
+OMC_HD void an_puti(const GenCtx& gc, int64_t idx, int k, int32_t v)
+{
+  gc.an_i[k * gc.an_cap + idx] = v;
+}
+
 OMC_HD void collision_mg(Collider& p, int ba, const GenCtx& gc, const Bank& fb)
 {
   const int G = DM.mg_n_groups;
@@ -1800,7 +1818,8 @@ OMC_HD void collision_mg(Collider& p, int ba, const GenCtx& gc, const Bank& fb)
     const int nu = fission_site_count(p, nu_t);
     if (nu > 0) {
       const int32_t base = atomic_add_i32(gc.n_fission, nu);
-      for (int k = 0; k < nu; ++k) {
+      int k = 0;
+      for (; k < nu; ++k) {
         const double mu = 2. * prn(p.seed) - 1.;
         const double phi = 2. * PI * prn(p.seed);
         const V3 su = v3(mu, sqrt(1. - mu * mu) * cos(phi), sqrt(1. - mu * mu) * sin(phi));
@@ -1819,6 +1838,10 @@ OMC_HD void collision_mg(Collider& p, int ba, const GenCtx& gc, const Bank& fb)
         bank_store(fb, slot, p.r, su, (double)gout, t, 1.0, dg + 1, p.id, p.n_progeny);
         p.n_progeny++;
       }
+      if (an_on(gc) && k > 0) { // p.fission(), p.wgt_bank() = sites stored / weight, src/physics_mg.cpp:223-233
+        an_puti(gc, an_index(p, gc), AN_FISSION, 1);
+        an_put(gc, an_index(p, gc), AN_WGT_BANK, (double)k);
+      }
     }
   }
   if (p.xs_absorption > 0.) { // absorption :239-259
@@ -1833,6 +1856,8 @@ OMC_HD void collision_mg(Collider& p, int ba, const GenCtx& gc, const Bank& fb)
   }
   if (p.wgt == 0.0)
     return;
+  if (an_on(gc))
+    an_puti(gc, an_index(p, gc), AN_SCATTER, 1); // p.event() = TallyEvent::SCATTER, :95
   int gout;
   double mu;
   mg_sample_scatter(ba, p.g, gout, mu, p.wgt, p.seed); // scatter :83-96
@@ -1909,6 +1934,13 @@ OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no
     p.wgt = 0.0;
     return;
   }
+  if (an_on(gc)) { // p.neutron_xs(p.event_nuclide()), read by the analog scores
+    const int64_t idx = an_index(p, gc);
+    an_put(gc, idx, AN_MICRO_T, micro.total);
+    an_put(gc, idx, AN_MICRO_A, micro.absorption);
+    an_put(gc, idx, AN_MICRO_F, micro.fission);
+    an_put(gc, idx, AN_MICRO_NF, micro.nu_fission);
+  }
   const int rx0 = ld(DM.nuc_rx_ofs + nuc);
   if (ld(DM.nuc_fissionable + nuc) && micro.fission > 0.0) { // create_fission_sites :170-285
     const int rx = rx0 + ld(DM.nuc_fission_rx + nuc);
@@ -1917,7 +1949,8 @@ OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no
     if (nu > 0) {
       const int32_t base = atomic_add_i32(gc.n_fission, nu);
       const int p0 = ld(DM.rx_prod_ofs + rx);
-      for (int k = 0; k < nu; ++k) { // sample_fission_neutron :1043-1117
+      int k = 0;
+      for (; k < nu; ++k) { // sample_fission_neutron :1043-1117
         const double nu_tot = ce_nu(nuc, p.E, 2);
         const double nu_d = ce_nu(nuc, p.E, 1);
         const double beta = nu_d / nu_tot;
@@ -1950,6 +1983,10 @@ OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no
         bank_store(fb, slot, p.r, su, E_out, t, 1.0, group, p.id, p.n_progeny);
         p.n_progeny++;
       }
+      if (an_on(gc) && k > 0) { // p.fission(), p.wgt_bank() = sites stored / weight, src/physics.cpp:268-281
+        an_puti(gc, an_index(p, gc), AN_FISSION, 1);
+        an_put(gc, an_index(p, gc), AN_WGT_BANK, (double)k);
+      }
     }
   }
   if (micro.absorption > 0.0) { // absorption :638-672
@@ -1965,6 +2002,8 @@ OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no
   if (p.wgt == 0.0)
     return;
   // scatter :674-752
+  if (an_on(gc))
+    an_puti(gc, an_index(p, gc), AN_SCATTER, 1); // p.event() = TallyEvent::SCATTER, :740
   const double cut = prn(p.seed) * (micro.total - micro.absorption);
   const double elastic = ce_reaction_xs(rx0, micro); // Nuclide::calculate_elastic_xs
   if (elastic > cut) {                                 // elastic_scatter :754-818
@@ -2652,7 +2691,9 @@ OMC_HD bool tally_prepare(const PState& ps, int64_t i, int n_coord, int t, doubl
   return true;
 }
 
-OMC_D void tally_emit(const TallyEval& te, int t, int mesh_bin, double mesh_w, const ScoreCtx& sc,
+// SCORE: (score code, skip&) -> value of the score for this event
+template<class Score>
+OMC_D void tally_emit_with(const TallyEval& te, int t, int mesh_bin, double mesh_w, const Score& score_of,
   double* values)
 {
   const int ns = ld(DM.tally_n_scores + t);
@@ -2680,12 +2721,104 @@ OMC_D void tally_emit(const TallyEval& te, int t, int mesh_bin, double mesh_w, c
           index += (int64_t)((te.mesh_pos == 2) ? mesh_bin : te.bins[2][c]) * te.stride[2];
         for (int s = 0; s < ns; ++s) {
           bool skip;
-          const double score = score_value(ld(scores + s), sc, skip);
+          const double score = score_of(ld(scores + s), skip);
           if (!skip)
             tally_add(results + index * ns + s, score * mesh_w, few_bins);
         }
       }
 }
+
+struct NonAnalogScore { // score_general_ce_nonanalog / score_general_mg (tracklength, collision)
+  const ScoreCtx* sc;
+  OMC_D double operator()(int score, bool& skip) const { return score_value(score, *sc, skip); }
+};
+OMC_D void tally_emit(const TallyEval& te, int t, int mesh_bin, double mesh_w, const ScoreCtx& sc,
+  double* values)
+{
+  NonAnalogScore f;
+  f.sc = &sc;
+  tally_emit_with(te, t, mesh_bin, mesh_w, f, values);
+}
+
+// score_general_ce_analog (src/tallies/tally_scoring.cpp:1116-1330) and the ANALOG branches of
+// score_general_mg (:1622-1990), i_nuclide = -1, flux = 1 (neutrons): the six scores of the path
+struct AnalogScore {
+  double wgt_last, wgt_bank, keff;
+  double xs_total, xs_absorption, xs_fission; // macroscopic, before the collision
+  double micro_t, micro_a, micro_f, micro_nf; // of the nuclide collided with (CE)
+  double mg_fis_over_abs, mg_nufis_over_abs;  // table values at (angle, temperature, p_g) (MG)
+  bool scatter, fission;                      // p.event() == SCATTER, p.fission()
+  OMC_D double operator()(int score, bool& skip) const
+  {
+    skip = false;
+    const bool sb = DM.survival_biasing != 0;
+    if (DM.run_CE) {
+      const double wgt_absorb = sb ? wgt_last * micro_a / micro_t : 0.0;
+      switch (score) {
+      case OMCGPU_SCORE_FLUX:
+        return 1.0 * wgt_last / xs_total;
+      case OMCGPU_SCORE_TOTAL:
+        return wgt_last * 1.0;
+      case OMCGPU_SCORE_SCATTER:
+        skip = !scatter;
+        return (wgt_last - wgt_absorb) * 1.0;
+      case OMCGPU_SCORE_ABSORPTION:
+        if (sb)
+          return wgt_absorb * 1.0;
+        skip = scatter;
+        return wgt_last * 1.0;
+      case OMCGPU_SCORE_FISSION:
+        if (xs_fission == 0) {
+          skip = true;
+          return 0.0;
+        }
+        if (sb)
+          return micro_t > 0 ? wgt_last * micro_f / micro_t * 1.0 : 0.;
+        skip = scatter;
+        return wgt_last * micro_f / micro_a * 1.0;
+      default: // nu-fission
+        if (xs_fission == 0) {
+          skip = true;
+          return 0.0;
+        }
+        if (sb)
+          return micro_t > 0 ? wgt_last * micro_nf / micro_t * 1.0 : 0.;
+        skip = !fission;
+        return keff * wgt_bank * 1.0;
+      }
+    }
+    const double wgt_absorb = sb ? wgt_last * xs_absorption / xs_total : 0.0;
+    switch (score) {
+    case OMCGPU_SCORE_FLUX:
+      return 1.0 * wgt_last / xs_total;
+    case OMCGPU_SCORE_TOTAL:
+      return 1.0 * wgt_last;
+    case OMCGPU_SCORE_SCATTER:
+      skip = !scatter;
+      return (wgt_last - wgt_absorb) * 1.0;
+    case OMCGPU_SCORE_ABSORPTION:
+      if (sb)
+        return wgt_absorb * 1.0;
+      skip = scatter;
+      return wgt_last * 1.0;
+    case OMCGPU_SCORE_FISSION: {
+      double s;
+      if (sb) {
+        s = wgt_absorb * 1.0;
+      } else {
+        skip = scatter;
+        s = wgt_last * 1.0;
+      }
+      return s * mg_fis_over_abs;
+    }
+    default: // nu-fission
+      if (sb)
+        return wgt_absorb * 1.0 * mg_nufis_over_abs;
+      skip = !fission;
+      return keff * wgt_bank * 1.0;
+    }
+  }
+};
 
 struct GenericEmit { // one lane scores its whole track: any filter combination
   const TallyEval* te;
@@ -2730,6 +2863,20 @@ OMC_OOL void score_tracklength(const PState& ps, int64_t i, int n_coord, V3 r0, 
   }
 }
 
+// which tallies are scored AFTER the collision from the collision record: the analog estimator,
+// and the collision estimator of multigroup runs with survival biasing (score_general_mg takes
+// the group from whether the particle is still alive after the roulette, :1632-1657)
+OMC_HD bool tally_scored_after_collision(int t)
+{
+  const int est = ld(DM.tally_estimator + t);
+  return est == OMCGPU_ESTIMATOR_ANALOG ||
+         (est == OMCGPU_ESTIMATOR_COLLISION && !DM.run_CE && DM.survival_biasing != 0);
+}
+OMC_HD bool tally_scored_before_collision(int t)
+{
+  return ld(DM.tally_estimator + t) == OMCGPU_ESTIMATOR_COLLISION && !tally_scored_after_collision(t);
+}
+
 // score_collision_tally, src/tallies/tally_scoring.cpp:2543-2620: the tallies with the collision
 // estimator, at the point of a collision.  sc carries flux = wgt_last / Sigma_t and the
 // PRE-collision macroscopic cross sections, group and (MG) angle block; E_last the pre-collision
@@ -2739,12 +2886,70 @@ OMC_OOL void score_collision(const PState& ps, int64_t i, int n_coord, V3 r, dou
   double* values)
 {
   for (int t = 0; t < DM.n_tallies; ++t) {
-    if (ld(DM.tally_estimator + t) != OMCGPU_ESTIMATOR_COLLISION)
+    if (!tally_scored_before_collision(t))
       continue;
     TallyEval te;
     if (!tally_prepare(ps, i, n_coord, t, E_last, sc, te, &r))
       continue;
     tally_emit(te, t, 0, 1.0, sc, values);
+  }
+}
+
+// score_analog_tally_ce / _mg (src/tallies/tally_scoring.cpp:2314-2414) and, for the case above,
+// score_collision_tally, from the record the collision left for particle idx
+OMC_OOL void score_after_collision(const PState& ps, int64_t i, int n_coord, const GenCtx& gc, int64_t idx,
+  double* values)
+{
+  const double* d = gc.an_d + idx;
+  const int32_t* n = gc.an_i + idx;
+  const int64_t cap = gc.an_cap;
+  const V3 r = v3(d[AN_RX * cap], d[AN_RY * cap], d[AN_RZ * cap]);
+  const double E_last = d[AN_E_LAST * cap];
+  const int g_last = n[AN_G_LAST * cap];
+  // the group of the scores: the new one when the roulette killed the particle after its scatter
+  const int p_g = (DM.survival_biasing && !n[AN_ALIVE * cap]) ? n[AN_G_POST * cap] : g_last;
+  ScoreCtx sc;
+  sc.xs_total = d[AN_XS_T * cap];
+  sc.xs_absorption = d[AN_XS_A * cap];
+  sc.xs_fission = d[AN_XS_F * cap];
+  sc.xs_nu_fission = d[AN_XS_NF * cap];
+  sc.flux = d[AN_WGT_LAST * cap] / sc.xs_total;
+  sc.material = n[AN_MATERIAL * cap];
+  sc.mg_ba = n[AN_MG_BA * cap];
+  AnalogScore an;
+  an.wgt_last = d[AN_WGT_LAST * cap];
+  an.wgt_bank = d[AN_WGT_BANK * cap];
+  an.keff = gc.keff;
+  an.xs_total = sc.xs_total;
+  an.xs_absorption = sc.xs_absorption;
+  an.xs_fission = sc.xs_fission;
+  an.micro_t = d[AN_MICRO_T * cap];
+  an.micro_a = d[AN_MICRO_A * cap];
+  an.micro_f = d[AN_MICRO_F * cap];
+  an.micro_nf = d[AN_MICRO_NF * cap];
+  an.scatter = n[AN_SCATTER * cap] != 0;
+  an.fission = n[AN_FISSION * cap] != 0;
+  an.mg_fis_over_abs = an.mg_nufis_over_abs = 0.0;
+  if (!DM.run_CE) {
+    const int G = DM.mg_n_groups;
+    const bool fis = ld(DM.mgm_fissionable + sc.material);
+    const double a = ld(DM.mg_absorption + sc.mg_ba * G + p_g);
+    an.mg_fis_over_abs = (fis ? ld(DM.mg_fission + sc.mg_ba * G + p_g) : 0.) / a;
+    an.mg_nufis_over_abs = (fis ? ld(DM.mg_nu_fission + sc.mg_ba * G + p_g) : 0.) / a;
+  }
+  for (int t = 0; t < DM.n_tallies; ++t) {
+    if (!tally_scored_after_collision(t))
+      continue;
+    TallyEval te;
+    sc.g = g_last; // the energy filter matches the group the particle collided in
+    if (!tally_prepare(ps, i, n_coord, t, E_last, sc, te, &r))
+      continue;
+    if (ld(DM.tally_estimator + t) == OMCGPU_ESTIMATOR_ANALOG) {
+      tally_emit_with(te, t, 0, 1.0, an, values);
+    } else {
+      sc.g = p_g;
+      tally_emit(te, t, 0, 1.0, sc, values);
+    }
   }
 }
 

@@ -747,6 +747,31 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
   p.k_abs = ps.k_abs[i];
   ps.k_col[i] += p.wgt * p.xs_nu_fission / p.xs_total;
   ps.surface[i] = SURFACE_NONE;
+  // tallies scored after the collision (analog estimator): the state before it goes into the
+  // particle's collision record, collision_ce / collision_mg add what happened
+  const bool record = an_on(gc);
+  const int64_t ridx = ps.id_shift + i;
+  if (record) {
+    an_put(gc, ridx, AN_RX, p.r.x);
+    an_put(gc, ridx, AN_RY, p.r.y);
+    an_put(gc, ridx, AN_RZ, p.r.z);
+    an_put(gc, ridx, AN_E_LAST, p.E);
+    an_put(gc, ridx, AN_WGT_LAST, p.wgt);
+    an_put(gc, ridx, AN_WGT_BANK, 0.0);
+    an_put(gc, ridx, AN_MICRO_T, 0.0);
+    an_put(gc, ridx, AN_MICRO_A, 0.0);
+    an_put(gc, ridx, AN_MICRO_F, 0.0);
+    an_put(gc, ridx, AN_MICRO_NF, 0.0);
+    an_put(gc, ridx, AN_XS_T, p.xs_total);
+    an_put(gc, ridx, AN_XS_A, p.xs_absorption);
+    an_put(gc, ridx, AN_XS_F, ps.xs_fission[i]);
+    an_put(gc, ridx, AN_XS_NF, p.xs_nu_fission);
+    an_puti(gc, ridx, AN_SCATTER, 0);
+    an_puti(gc, ridx, AN_FISSION, 0);
+    an_puti(gc, ridx, AN_G_LAST, p.g);
+    an_puti(gc, ridx, AN_MATERIAL, p.material);
+    an_puti(gc, ridx, AN_MG_BA, 0);
+  }
   if (DM.run_CE) {
     bool no_nuclide;
     collision_ce<BX>(p, gc, fb, no_nuclide, ps.n_prefix ? ps.xs_prefix + (ps.id_shift + i) * ps.n_prefix : nullptr);
@@ -758,7 +783,13 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
     const int n_coord = ps.n_coord[i];
     const int ba = mg_ba(p.material, mg_temperature_index(p.material, ps.sqrtkT[i]),
       mg_angle_index(p.material, get_u(ps, i, n_coord - 1)));
+    if (record)
+      an_puti(gc, ridx, AN_MG_BA, ba);
     collision_mg(p, ba, gc, fb);
+  }
+  if (record) {
+    an_puti(gc, ridx, AN_ALIVE, p.wgt != 0.0 ? 1 : 0);
+    an_puti(gc, ridx, AN_G_POST, p.g);
   }
   const int n_coord = ps.n_coord[i];
   { // directions of all levels follow level 0, through the rotations of rotated fills
@@ -779,6 +810,8 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
   ps.n_progeny[i] = p.n_progeny;
   ps.k_abs[i] = p.k_abs;
   ps.material_last[i] = C_NONE;
+  if (SCORE && record)
+    score_after_collision(ps, i, n_coord, gc, ridx, score_values(gc));
   return ev_revive(ps, i);
 }
 
@@ -954,6 +987,22 @@ OMC_KERNEL(k_collision_score, EvArgs, body_collision_score)
   do { \
     if (G.n_collision_tallies > 0 && (args).gc.tallies_active) \
       OMC_LAUNCH(k_collision_score, n_ub, stream, args); \
+  } while (0)
+
+// tallies scored AFTER the collision (analog estimator), from the records the collision kernel
+// left: launched behind it on the same stream, only for models that have such tallies
+OMC_D void body_after_collision_score(int64_t tid, const EvArgs& a)
+{
+  if (tid >= *a.q_in.count)
+    return;
+  const int32_t i = list_item(a.q_in, tid);
+  score_after_collision(a.ps, i, a.ps.n_coord[i], a.gc, a.ps.id_shift + i, score_values(a.gc));
+}
+OMC_KERNEL(k_after_collision_score, EvArgs, body_after_collision_score)
+#define LAUNCH_AFTER_COLLISION_SCORE(n_ub, stream, args) \
+  do { \
+    if (G.n_after_collision_tallies > 0 && (args).gc.tallies_active) \
+      OMC_LAUNCH(k_after_collision_score, n_ub, stream, args); \
   } while (0)
 
 template<bool BX>
@@ -2083,7 +2132,10 @@ struct Engine {
   int64_t n_tally = 0;
   std::vector<int64_t> tally_ofs; // host copy of tally_result_ofs
   int n_cell_sqrtkT = 0, n_mat_nuclides = 0; // array lengths omcgpu_update checks
-  int n_collision_tallies = 0;
+  int n_collision_tallies = 0;       // tallies scored before the collision (collision estimator)
+  int n_after_collision_tallies = 0; // ... after it, from the collision records (analog estimator)
+  double* d_an_d = nullptr;          // collision records, AN_ND / AN_NI columns of `cap` entries
+  int32_t* d_an_i = nullptr;
   // several temperatures per nuclide: device materials are (model material, cell sqrt(kT)) pairs
   int n_base_materials = 0;
   std::vector<int32_t> mat_base;    // [device material] -> model material (empty: identity)
@@ -2598,8 +2650,13 @@ static int upload_model(const omcgpu_model* m)
   UP(filter_idata, n_fdat);
   UP(filter_ddata, n_fdat);
   h.n_collision_tallies = 0;
-  for (int t = 0; t < nt; ++t)
-    h.n_collision_tallies += m->tally_estimator[t] == OMCGPU_ESTIMATOR_COLLISION ? 1 : 0;
+  G.n_after_collision_tallies = 0;
+  for (int t = 0; t < nt; ++t) { // (the same split as device.h tally_scored_after_collision)
+    const bool after = m->tally_estimator[t] == OMCGPU_ESTIMATOR_ANALOG ||
+                       (m->tally_estimator[t] == OMCGPU_ESTIMATOR_COLLISION && !m->run_CE && m->survival_biasing);
+    G.n_after_collision_tallies += after ? 1 : 0;
+    h.n_collision_tallies += m->tally_estimator[t] == OMCGPU_ESTIMATOR_COLLISION && !after ? 1 : 0;
+  }
   G.n_collision_tallies = h.n_collision_tallies;
   UP(tally_estimator, nt);
   G.n_tally = nt ? m->tally_result_ofs[nt] : 0;
@@ -2664,8 +2721,9 @@ static int check_supported(const omcgpu_model* m)
   for (int t = 0; t < m->n_tallies; ++t) {
     if (m->tally_n_filters[t] > OMCGPU_MAX_FILTERS || m->tally_n_scores[t] > OMCGPU_MAX_SCORES)
       return fail(OMCGPU_E_UNSUPPORTED, "tally has too many filters or scores%s");
-    if (m->tally_estimator[t] != OMCGPU_ESTIMATOR_TRACKLENGTH && m->tally_estimator[t] != OMCGPU_ESTIMATOR_COLLISION)
-      return fail(OMCGPU_E_UNSUPPORTED, "analog tally estimator (src/tallies/tally_scoring.cpp:2314-2414) not supported on the device%s");
+    if (m->tally_estimator[t] != OMCGPU_ESTIMATOR_TRACKLENGTH && m->tally_estimator[t] != OMCGPU_ESTIMATOR_COLLISION &&
+        m->tally_estimator[t] != OMCGPU_ESTIMATOR_ANALOG)
+      return fail(OMCGPU_E_UNSUPPORTED, "unknown tally estimator%s");
     int n_mesh = 0;
     for (int k = 0; k < m->tally_n_filters[t]; ++k)
       if (m->filter_type[m->tally_filters[t * OMCGPU_MAX_FILTERS + k]] == OMCGPU_FILTER_MESH)
@@ -2740,6 +2798,9 @@ static EvArgs make_args(const omcgpu_gen_in* in)
   a.gc.fission_cap = G.fis_cap;
   a.gc.score_part = G.score_part;
   a.gc.tally_needs_cells = G.tally_needs_cells ? 1 : 0;
+  a.gc.an_d = G.d_an_d;
+  a.gc.an_i = G.d_an_i;
+  a.gc.an_cap = G.cap;
   a.fl = G.fl[0];
   a.fl_buf = 0;
   a.first_event = NEXT_NONE;
@@ -3029,10 +3090,12 @@ static int run_sweeps_merged(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
       CUDA_OK(cudaEventRecord(G.evk0[1][ev], st_coll));
       LAUNCH_COLLISION_SCORE(n_alive, st_coll, ac);
       LAUNCH_XS(k_collide, n_alive, st_coll, ac);
+      LAUNCH_AFTER_COLLISION_SCORE(n_alive, st_coll, ac);
     } else {
       CUDA_OK(cudaEventRecord(G.evk0[1][ev], st_coll));
       LAUNCH_COLLISION_SCORE(n_alive, st_coll, a);
       LAUNCH_XS(k_collide, n_alive, st_coll, a);
+      LAUNCH_AFTER_COLLISION_SCORE(n_alive, st_coll, a);
     }
     CUDA_OK(cudaEventRecord(G.evk1[1][ev], st_coll));
     if (G.overlap) {
@@ -3216,6 +3279,7 @@ static int run_sweeps_paired(EvArgs& a, const omcgpu_gen_in* in, int64_t n, Swee
     a.cursor = in_slot + 5;
     LAUNCH_COLLISION_SCORE(n_alive, st_coll, a);
     LAUNCH_XA(k_collide_xa, n_alive, st_coll, a);
+    LAUNCH_AFTER_COLLISION_SCORE(n_alive, st_coll, a);
     CUDA_OK(cudaEventRecord(G.evk1[1][ev], st_coll));
     if (G.overlap) {
       CUDA_OK(cudaEventRecord(G.e_coll, st_coll));
@@ -3798,6 +3862,12 @@ static int init_impl(const omcgpu_model* model, int device, int64_t max_particle
     G.tally_stride = (G.n_tally + 15) / 16 * 16;
   }
   rc = rc ? rc : dev_alloc(&G.d_tally, (size_t)G.tally_stride * G.tally_replicas);
+  G.d_an_d = nullptr;
+  G.d_an_i = nullptr;
+  if (G.n_after_collision_tallies > 0) { // collision records for the tallies scored after a collision
+    rc = rc ? rc : dev_alloc(&G.d_an_d, (size_t)AN_ND * cap);
+    rc = rc ? rc : dev_alloc(&G.d_an_i, (size_t)AN_NI * cap);
+  }
   G.n_chunks = 4096;
   rc = rc ? rc : dev_alloc(&G.d_partial, G.n_chunks * 6);
   if (rc)

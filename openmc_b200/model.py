@@ -113,7 +113,7 @@ class Tally:
     id: int
     filters: list                      # filter ids
     scores: list                       # names
-    estimator: str = "tracklength"     # 'tracklength' | 'collision' (Tally::estimator_)
+    estimator: str = "tracklength"     # 'tracklength' | 'collision' | 'analog' (Tally::estimator_)
 
 
 # ----------------------------------------------------------------------------

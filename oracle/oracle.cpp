@@ -221,6 +221,10 @@ struct Particle {
   int64_t n_event {0};
   int n_collision {0};
   bool fission {false};
+  // what the analog estimator reads after a collision (src/tallies/tally_scoring.cpp:1116-1330, 1622-1990)
+  bool event_scatter {false};  // p.event() == TallyEvent::SCATTER
+  double wgt_bank {0};         // fission sites stored / weight (src/physics.cpp:280-281)
+  MicroXS event_micro {};      // p.neutron_xs(p.event_nuclide()) at the collision energy
   int delayed_group {0};
   int cell_born {C_NONE};
   double xs_total {0}, xs_absorption {0}, xs_fission {0}, xs_nu_fission {0};
@@ -247,6 +251,7 @@ struct RunState {
   int64_t work_index {0};
   bool tallies_active {false};
   int n_collision_tallies {0};
+  int n_analog_tallies {0};
   std::vector<omcgpu_site> fission_bank;
   int64_t fission_capacity {0};
   std::vector<int64_t> progeny_per_particle;
@@ -1164,8 +1169,11 @@ void mg_create_fission_sites(Particle& p)
     }
     p.delayed_group = dg + 1;
   }
-  if (n_sites_stored == 0)
+  if (n_sites_stored == 0) {
     p.fission = false;
+    return;
+  }
+  p.wgt_bank = n_sites_stored / weight; // src/physics_mg.cpp:232-233
 }
 
 void collision_mg(Particle& p)
@@ -1182,12 +1190,14 @@ void collision_mg(Particle& p)
       if (p.xs_absorption > prn(p.current_seed()) * p.xs_total) {
         p.k_abs += p.wgt * p.xs_nu_fission / p.xs_absorption;
         p.wgt = 0.0;
+        p.event_scatter = false; // TallyEvent::ABSORB, src/physics_mg.cpp:256
       }
     }
   }
   if (!p.alive())
     return;
   // scatter (src/physics_mg.cpp:83-96)
+  p.event_scatter = true;
   int ba = mg_ba(p.material, p.mg_t, p.mg_a);
   mg_sample_scatter(ba, p.g_last, p.g, p.mu, p.wgt, p.current_seed());
   p.u() = rotate_angle(p.u(), p.mu, nullptr, p.current_seed());
@@ -1467,8 +1477,11 @@ void ce_create_fission_sites(Particle& p, int i_nuclide, int rx, const MicroXS& 
       break;
     }
   }
-  if (n_sites_stored == 0)
+  if (n_sites_stored == 0) {
     p.fission = false;
+    return;
+  }
+  p.wgt_bank = n_sites_stored / weight; // src/physics.cpp:280-281
 }
 
 Vec3 sample_cxs_target_velocity(double awr, double E, Vec3 u, double kT, uint64_t* seed)
@@ -1569,6 +1582,7 @@ void collision_ce(Particle& p)
     mark_as_lost(p, "Did not sample any nuclide during collision.");
     return;
   }
+  p.event_micro = micro; // p.event_nuclide() = i_nuclide, :99
   int rx0 = M->nuc_rx_ofs[i_nuclide];
   if (M->nuc_fissionable[i_nuclide] && micro.fission > 0.0) {
     int rx = rx0 + M->nuc_fission_rx[i_nuclide]; // no partial fission reactions
@@ -1583,12 +1597,14 @@ void collision_ce(Particle& p)
       if (micro.absorption > prn(p.current_seed()) * micro.total) {
         p.k_abs += p.wgt * micro.nu_fission / micro.absorption;
         p.wgt = 0.0;
+        p.event_scatter = false; // TallyEvent::ABSORB, :666
       }
     }
   }
   if (!p.alive())
     return;
   // scatter (:674-752)
+  p.event_scatter = true; // :740
   {
     double cut = prn(p.current_seed()) * (micro.total - micro.absorption);
     micro.elastic = ce_reaction_xs(rx0, micro); // calculate_elastic_xs, src/nuclide.cpp:578-590
@@ -1840,9 +1856,14 @@ void score_collision_tally(Particle& p)
 { // flux = wgt_last / Sigma_t (:2546-2549); called after the collision, which leaves macro_xs alone
   score_tallies(p, p.wgt_last / p.xs_total, OMCGPU_ESTIMATOR_COLLISION);
 }
+void score_analog_tally(Particle& p)
+{ // score_analog_tally_ce / _mg, :2314-2414: flux = 1 for neutrons; after the collision
+  score_tallies(p, 1.0, OMCGPU_ESTIMATOR_ANALOG);
+}
 void score_tallies(Particle& p, double flux, int estimator)
 {
   const bool tracklength = estimator == OMCGPU_ESTIMATOR_TRACKLENGTH;
+  const bool analog = estimator == OMCGPU_ESTIMATOR_ANALOG;
   int G = M->mg_n_groups;
   std::vector<Match> matches(M->n_filters);
   std::vector<char> present(M->n_filters, 0);
@@ -1881,7 +1902,54 @@ void score_tallies(Particle& p, double flux, int estimator)
       for (int s = 0; s < ns; ++s) {
         double score = 0.0;
         bool skip = false;
-        if (M->run_CE) { // score_general_ce_nonanalog :578-700
+        if (M->run_CE && analog) { // score_general_ce_analog :1116-1330
+          const MicroXS& em = p.event_micro;
+          const double wgt_absorb = M->survival_biasing ? p.wgt_last * em.absorption / em.total : 0.0;
+          switch (scores[s]) {
+          case OMCGPU_SCORE_FLUX:
+            score = flux * p.wgt_last / p.xs_total;
+            break;
+          case OMCGPU_SCORE_TOTAL:
+            score = p.wgt_last * flux;
+            break;
+          case OMCGPU_SCORE_SCATTER:
+            if (!p.event_scatter)
+              skip = true;
+            score = (p.wgt_last - wgt_absorb) * flux;
+            break;
+          case OMCGPU_SCORE_ABSORPTION:
+            if (M->survival_biasing) {
+              score = wgt_absorb * flux;
+            } else {
+              if (p.event_scatter)
+                skip = true;
+              score = p.wgt_last * flux;
+            }
+            break;
+          case OMCGPU_SCORE_FISSION:
+            if (p.xs_fission == 0) {
+              skip = true;
+            } else if (M->survival_biasing) {
+              score = em.total > 0 ? p.wgt_last * em.fission / em.total * flux : 0.;
+            } else {
+              if (p.event_scatter)
+                skip = true;
+              score = p.wgt_last * em.fission / em.absorption * flux;
+            }
+            break;
+          case OMCGPU_SCORE_NU_FISSION:
+            if (p.xs_fission == 0) {
+              skip = true;
+            } else if (M->survival_biasing) {
+              score = em.total > 0 ? p.wgt_last * em.nu_fission / em.total * flux : 0.;
+            } else {
+              if (!p.fission)
+                skip = true;
+              score = RS.keff * p.wgt_bank * flux; // sites banked, weighted by 1 / keff
+            }
+            break;
+          }
+        } else if (M->run_CE) { // score_general_ce_nonanalog :578-700
           switch (scores[s]) {
           case OMCGPU_SCORE_FLUX:
             score = flux;
@@ -1906,12 +1974,64 @@ void score_tallies(Particle& p, double flux, int estimator)
             score = p.xs_nu_fission * flux;
             break;
           }
+        } else if (analog) { // score_general_mg :1622-1990, estimator_ == ANALOG, i_nuclide = -1
+          const int m = p.material;
+          const double wgt_absorb = M->survival_biasing ? p.wgt_last * p.xs_absorption / p.xs_total : 0.0;
+          // :1632-1657: with survival biasing a particle killed by the roulette after its scatter is
+          // scored with its NEW group; every other case resolves to the pre-collision group
+          const int p_g = (M->survival_biasing && !p.alive()) ? p.g : p.g_last;
+          const int ba = mg_ba(m, p.mg_t, mg_angle_index(m, p.u_last_local));
+          const bool fis = M->mgm_fissionable[m];
+          switch (scores[s]) {
+          case OMCGPU_SCORE_FLUX:
+            score = flux * p.wgt_last / p.xs_total;
+            break;
+          case OMCGPU_SCORE_TOTAL:
+            score = flux * p.wgt_last;
+            break;
+          case OMCGPU_SCORE_SCATTER:
+            if (!p.event_scatter)
+              skip = true;
+            score = (p.wgt_last - wgt_absorb) * flux;
+            break;
+          case OMCGPU_SCORE_ABSORPTION:
+            if (M->survival_biasing) {
+              score = wgt_absorb * flux;
+            } else {
+              if (p.event_scatter)
+                skip = true;
+              score = p.wgt_last * flux;
+            }
+            break;
+          case OMCGPU_SCORE_FISSION:
+            if (M->survival_biasing) {
+              score = wgt_absorb * flux;
+            } else {
+              if (p.event_scatter)
+                skip = true;
+              score = p.wgt_last * flux;
+            }
+            score *= (fis ? M->mg_fission[ba * G + p_g] : 0.) / M->mg_absorption[ba * G + p_g];
+            break;
+          case OMCGPU_SCORE_NU_FISSION:
+            if (M->survival_biasing) {
+              score = wgt_absorb * flux;
+              score *= (fis ? M->mg_nu_fission[ba * G + p_g] : 0.) / M->mg_absorption[ba * G + p_g];
+            } else {
+              if (!p.fission)
+                skip = true;
+              score = RS.keff * p.wgt_bank * flux;
+            }
+            break;
+          }
         } else { // score_general_mg :1622-1990 (tracklength branch, i_nuclide = -1)
           int m = p.material;
           // tracklength: no collision happened, g and the local direction are current; collision
           // estimator: the pre-collision group and direction (:1632-1663 -- whether the particle
           // scattered or not, that is what p_g / p_u resolve to)
-          const int p_g = tracklength ? p.g : p.g_last;
+          // (:1632-1657: with survival biasing a particle the roulette killed after its scatter is
+          // scored with its NEW group)
+          const int p_g = tracklength ? p.g : ((M->survival_biasing && !p.alive()) ? p.g : p.g_last);
           int ba = (m >= 0) ? mg_ba(m, p.mg_t, mg_angle_index(m, tracklength ? p.u_local() : p.u_last_local)) : 0;
           switch (scores[s]) {
           case OMCGPU_SCORE_FLUX:
@@ -2179,6 +2299,9 @@ void event_collide(Particle& p)
   RS.n_coll++;
   if (RS.tallies_active && RS.n_collision_tallies > 0) // src/particle.cpp:362-363
     score_collision_tally(p);
+  if (RS.tallies_active && RS.n_analog_tallies > 0) // :364-370
+    score_analog_tally(p);
+  p.wgt_bank = 0.0; // :379-385
   p.fission = false;
   p.material_last = C_NONE;
   for (int j = 0; j < p.n_coord - 1; ++j) { // src/particle.cpp:396-406
@@ -2255,8 +2378,11 @@ void transport_generation(const omcgpu_gen_in& in, const omcgpu_site* source_ban
   RS.work_index = in.id_offset;
   RS.tallies_active = in.tallies_active != 0;
   RS.n_collision_tallies = 0;
-  for (int t = 0; t < M->n_tallies; ++t)
+  RS.n_analog_tallies = 0;
+  for (int t = 0; t < M->n_tallies; ++t) {
     RS.n_collision_tallies += M->tally_estimator[t] == OMCGPU_ESTIMATOR_COLLISION ? 1 : 0;
+    RS.n_analog_tallies += M->tally_estimator[t] == OMCGPU_ESTIMATOR_ANALOG ? 1 : 0;
+  }
   RS.fission_bank.clear();
   RS.fission_capacity = fission_capacity;
   RS.progeny_per_particle.assign(in.n_particles, 0);

@@ -26,6 +26,10 @@ RUNS = {
     "white_pincell": (1000, 6, 2),         # C1 pin cell with white (diffuse) boundaries
     "quadric_pin": (1000, 6, 2),           # general quadric surfaces
     "rotational_wedge": (1000, 6, 2),      # rotational periodic boundaries
+    "pincell_ce_analog": (1000, 8, 3),     # analog estimator: material x energy and mesh tallies, all six scores
+    "pincell_ce_analog_survival": (1000, 8, 3),   # the same with survival biasing
+    "pincell_mg_analog": (1000, 8, 3),     # analog estimator, multigroup
+    "pincell_mg_analog_survival": (1000, 8, 3),
 }
 _CACHE = {}
 
@@ -41,6 +45,22 @@ def build(name):
         m.tallies.append(Tally(nt + 1, [nf + 1], ["flux", "total", "absorption", "fission", "nu-fission", "scatter"],
                                estimator="collision"))
         ce = True
+    elif name in ("pincell_ce_analog", "pincell_ce_analog_survival", "pincell_mg_analog", "pincell_mg_analog_survival"):
+        ce = "_ce_" in name
+        if ce:
+            m, lib, box, of = examples.pincell_ce(n_grid=3000, mesh_dim=6, energy_bins=10, tallies=True)
+        else:
+            m, lib, box, of = examples.pincell_multigroup(mesh_dim=6, energy_bins=8)
+        six = ["flux", "total", "scatter", "absorption", "fission", "nu-fission"]
+        nf, nt = len(m.filters), len(m.tallies)
+        mesh_f = next(f for f in m.filters if f.type == "mesh")
+        energy_f = next(f for f in m.filters if f.type == "energy")
+        m.filters.append(Filter(nf + 1, "material", [mat.id for mat in m.materials]))
+        m.tallies.append(Tally(nt + 1, [nf + 1, energy_f.id], six, estimator="analog"))
+        m.tallies.append(Tally(nt + 2, [mesh_f.id], ["flux", "nu-fission", "scatter"], estimator="analog"))
+        m.tallies.append(Tally(nt + 3, [nf + 1], six, estimator="collision"))
+        if name.endswith("_survival"):
+            m.settings["survival_biasing"] = 1
     elif name == "pincell_ce_temperatures":
         m, lib, box, of = examples.pincell_ce(n_grid=3000, mesh_dim=6, energy_bins=12, tallies=True,
                                                temperatures=((294.0, 600.0, 900.0), (880.0, 620.0, 600.0, 575.0)))

@@ -92,15 +92,27 @@ def test_collision_estimator_and_distribcell_mg(emu_lib, threshold, monkeypatch)
     _check_generation(lib.Engine(emu_lib), c5g7_with_estimators, 1500, 1e-11)
 
 
-def test_analog_estimator_is_refused(emu_lib):
-    import cases
-    from openmc_b200 import _abi as abi
-    model, box, of = cases.build("mg_temperature_multi")
-    model["tally_estimator"][0] = abi.OMCGPU_ESTIMATOR_ANALOG
-    eng = lib.Engine(emu_lib)
-    with pytest.raises(lib.OmcGpuError, match="analog"):
-        eng.init(model, 0, 100)
-    model["tally_estimator"][0] = abi.OMCGPU_ESTIMATOR_TRACKLENGTH
+def _analog_case(name):
+    """the analog-estimator cases of tests/reference_runs.py (on which the oracle equals the
+    reference's own binary bit for bit): analog material x energy and mesh tallies with all six
+    scores + a collision-estimator tally, CE / MG, with and without survival biasing"""
+    import reference_runs as rr
+    m, libx, model, box, of, ce = rr.build(name)
+    return model, box, of
+
+
+ANALOG = ["pincell_ce_analog", "pincell_ce_analog_survival", "pincell_mg_analog", "pincell_mg_analog_survival"]
+
+
+@pytest.mark.parametrize("sweep", ["1", "2"])
+@pytest.mark.parametrize("threshold", ["0", "100000"])
+@pytest.mark.parametrize("name", ANALOG)
+def test_analog_estimator(emu_lib, name, threshold, sweep, monkeypatch):
+    """score_analog_tally_ce / _mg (src/tallies/tally_scoring.cpp:2314-2414): scored after the
+    collision from the collision records (list kernels: k_after_collision_score; tail: in line)"""
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)
+    monkeypatch.setenv("OMCGPU_SWEEP", sweep)
+    _check_generation(lib.Engine(emu_lib), lambda: _analog_case(name), 1500, 1e-11)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference tree (container only)")
@@ -134,3 +146,13 @@ def test_collision_estimator_and_distribcell_on_gpu(gpu_engine, threshold, monke
     monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)
     _check_generation(gpu_engine, lambda: assembly_with_estimators(4000), 20000, None, exact_bank=False)
     _check_generation(gpu_engine, c5g7_with_estimators, 20000, None, exact_bank=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threshold", ["0", "2048"])
+@pytest.mark.parametrize("name", ANALOG)
+def test_analog_estimator_on_gpu(gpu_engine, name, threshold, monkeypatch):
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)
+    mg = "_mg_" in name
+    # multigroup: the same histories as the oracle (every bin to 1e-9); CE: a few flipped decisions
+    _check_generation(gpu_engine, lambda: _analog_case(name), 20000, 1e-9 if mg else None, exact_bank=mg)

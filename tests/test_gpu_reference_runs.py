@@ -23,8 +23,9 @@ from oracle.binding import Oracle
 
 pytestmark = pytest.mark.gpu
 
-MG = ["pincell_mg", "c5g7_core", "surface_zoo", "rotated_fills", "periodic_box", "white_pincell", "quadric_pin"]
-CE = ["pincell_ce", "pincell_ce_temperatures", "assembly_ce", "pwr_core_ce",
+MG = ["pincell_mg", "c5g7_core", "surface_zoo", "rotated_fills", "periodic_box", "white_pincell", "quadric_pin",
+      "pincell_mg_analog", "pincell_mg_analog_survival"]          # analog-estimator tallies
+CE = ["pincell_ce", "pincell_ce_temperatures", "assembly_ce", "pwr_core_ce", "pincell_ce_analog", "pincell_ce_analog_survival",
       # multigroup, but a last-ulp difference of CUDA's log() flips a history within five generations
       # (curved reflective boundary + rotated re-entry): the first four generations agree to 1e-6
       "rotational_wedge"]
