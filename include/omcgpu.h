@@ -477,6 +477,15 @@ int omcgpu_host_unregister(void* p);
 int omcgpu_set_source_bank(const omcgpu_site* source_bank, int64_t n);
 int omcgpu_get_source_bank(omcgpu_site* source_bank, int64_t n);
 int omcgpu_run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out);
+
+/* Particle::mark_as_lost (src/particle.cpp:762-785) prints a warning with the particle's id and
+ * writes a particle restart file per lost particle.  The device counts lost particles
+ * (omcgpu_gen_out.n_lost) and keeps the state of the first OMCGPU_MAX_LOST_RECORDS of the last
+ * generation: records[k] = {id, x, y, z, u, v, w, E} at the moment the particle was lost.
+ * Returns the number of records written (<= capacity), or a negative error code. */
+#define OMCGPU_LOST_RECORD 8
+#define OMCGPU_MAX_LOST_RECORDS 64
+int64_t omcgpu_lost_particles(double* records, int64_t capacity);
 int omcgpu_get_fission_bank(omcgpu_site* fission_bank, int64_t capacity, int64_t* n);
 
 /* Uniform-comb resampling of the (sorted, device-resident) fission bank into

@@ -205,6 +205,10 @@ struct GenCtx {
   double* an_d;
   int32_t* an_i;
   int64_t an_cap;
+  // the first lost_cap lost particles of the generation: [slot][OMCGPU_LOST_RECORD] =
+  // {id, x, y, z, u, v, w, E} (what Particle::mark_as_lost reports, src/particle.cpp:762-785)
+  double* lost_rec;
+  int32_t lost_cap;
 };
 enum { AN_RX, AN_RY, AN_RZ, AN_E_LAST, AN_WGT_LAST, AN_WGT_BANK, AN_MICRO_T, AN_MICRO_A, AN_MICRO_F, AN_MICRO_NF,
   AN_XS_T, AN_XS_A, AN_XS_F, AN_XS_NF, AN_ND };

@@ -259,10 +259,25 @@ enum { NEXT_NONE = -2, NEXT_DEAD = -1, NEXT_COLLISION = 0, NEXT_SURFACE = 1 };
 constexpr int32_t PIDX_LOGGED = -1;    // flight logged by the tail: no particle state to consult
 constexpr int32_t PIDX_NO_FLIGHT = -2; // work-list position whose history made no flight this sweep
 
+OMC_OOL void record_lost(const PState& ps, const GenCtx& gc, int64_t i, int32_t slot)
+{ // rare, out of line: what the host reports for the first lost particles of a generation
+  double* rec = gc.lost_rec + (int64_t)slot * OMCGPU_LOST_RECORD;
+  const V3 r = get_r(ps, i, 0), u = get_u(ps, i, 0);
+  rec[0] = (double)(gc.id_offset + ps.id_shift + i + 1);
+  rec[1] = r.x;
+  rec[2] = r.y;
+  rec[3] = r.z;
+  rec[4] = u.x;
+  rec[5] = u.y;
+  rec[6] = u.z;
+  rec[7] = ps.E[i];
+}
 OMC_D void mark_lost(const PState& ps, const GenCtx& gc, int64_t i)
-{ // Particle::mark_as_lost, src/particle.cpp:762-785 (count + kill)
+{ // Particle::mark_as_lost, src/particle.cpp:762-785 (count + kill; the warning is the host's)
+  const int32_t slot = atomic_add_i32(gc.n_lost, 1);
+  if (gc.lost_rec && slot < gc.lost_cap)
+    record_lost(ps, gc, i, slot);
   ps.wgt[i] = 0.0;
-  atomic_add_i32(gc.n_lost, 1);
 }
 
 // initialize_history + Particle::from_source + first locate
@@ -2134,6 +2149,8 @@ struct Engine {
   int n_cell_sqrtkT = 0, n_mat_nuclides = 0; // array lengths omcgpu_update checks
   int n_collision_tallies = 0;       // tallies scored before the collision (collision estimator)
   int n_after_collision_tallies = 0; // ... after it, from the collision records (analog estimator)
+  double* d_lost_rec = nullptr;      // state of the first lost particles of the generation (mark_lost)
+  int64_t n_lost_last = 0;           // lost particles of the last generation
   double* d_an_d = nullptr;          // collision records, AN_ND / AN_NI columns of `cap` entries
   int32_t* d_an_i = nullptr;
   // several temperatures per nuclide: device materials are (model material, cell sqrt(kT)) pairs
@@ -2801,6 +2818,8 @@ static EvArgs make_args(const omcgpu_gen_in* in)
   a.gc.an_d = G.d_an_d;
   a.gc.an_i = G.d_an_i;
   a.gc.an_cap = G.cap;
+  a.gc.lost_rec = G.d_lost_rec;
+  a.gc.lost_cap = OMCGPU_MAX_LOST_RECORDS;
   a.fl = G.fl[0];
   a.fl_buf = 0;
   a.first_event = NEXT_NONE;
@@ -3424,6 +3443,7 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
   G.n_fis = std::min<int64_t>(G.h_counts[4], G.fis_cap);
   out->n_fission = G.n_fis;
   out->n_lost = G.h_counts[5];
+  G.n_lost_last = out->n_lost;
   out->n_bank_full = G.h_counts[7];
   drain_score_times(st, st.score_issued); // the stream sync above covers every scoring launch
   out->ms_surface = st.ms_kernel[0];
@@ -3531,6 +3551,24 @@ int omcgpu_sweep_kind(void)
   if (!G.ready)
     return -1;
   return G.sweep_mode == 2 ? 2 : (G.fuse_xs ? 1 : 0);
+}
+
+int64_t omcgpu_lost_particles(double* records, int64_t capacity)
+{
+  if (!G.ready)
+    return -fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_lost_particles: library not initialised%s");
+  if (!records && capacity > 0)
+    return -fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_lost_particles: no buffer%s");
+  const int64_t n = std::max<int64_t>(0, std::min<int64_t>(std::min<int64_t>(G.n_lost_last, OMCGPU_MAX_LOST_RECORDS), capacity));
+  if (n > 0) {
+#if OMC_CUDA
+    if (cudaMemcpy(records, G.d_lost_rec, (size_t)n * OMCGPU_LOST_RECORD * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+      return -fail(OMCGPU_E_CUDA, "omcgpu_lost_particles: copy failed%s");
+#else
+    std::memcpy(records, G.d_lost_rec, (size_t)n * OMCGPU_LOST_RECORD * sizeof(double));
+#endif
+  }
+  return n;
 }
 
 int omcgpu_set_option(const char* name, int64_t value)
@@ -3862,6 +3900,7 @@ static int init_impl(const omcgpu_model* model, int device, int64_t max_particle
     G.tally_stride = (G.n_tally + 15) / 16 * 16;
   }
   rc = rc ? rc : dev_alloc(&G.d_tally, (size_t)G.tally_stride * G.tally_replicas);
+  rc = rc ? rc : dev_alloc(&G.d_lost_rec, (size_t)OMCGPU_MAX_LOST_RECORDS * OMCGPU_LOST_RECORD);
   G.d_an_d = nullptr;
   G.d_an_i = nullptr;
   if (G.n_after_collision_tallies > 0) { // collision records for the tallies scored after a collision

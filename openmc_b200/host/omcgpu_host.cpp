@@ -51,6 +51,7 @@
 
 #define private public
 #define protected public
+#include "openmc/timer.h" // Timer::elapsed_: the device's kernel times are added to the event timers
 #include "openmc/bank.h"
 #include "openmc/boundary_condition.h"
 #include "openmc/cell.h"
@@ -913,6 +914,7 @@ struct Api {
   int (*tally_results)(int32_t, double*, int64_t) = nullptr;
   int (*host_register)(void*, int64_t) = nullptr;
   int (*host_unregister)(void*) = nullptr;
+  int64_t (*lost_particles)(double*, int64_t) = nullptr;
 } api;
 bool g_ready = false;
 std::vector<double> g_values;
@@ -951,6 +953,7 @@ void load_library()
   bind(api.tally_results, "omcgpu_tally_results");
   bind(api.host_register, "omcgpu_host_register");
   bind(api.host_unregister, "omcgpu_host_unregister");
+  bind(api.lost_particles, "omcgpu_lost_particles");
 }
 
 void check(int rc, const char* what)
@@ -989,6 +992,37 @@ void simulation_init()
   g_ready = true;
 }
 
+// Particle::mark_as_lost (src/particle.cpp:762-785) for the particles the device lost in this
+// generation: the warning per particle (the device keeps the state of the first
+// OMCGPU_MAX_LOST_RECORDS), the count, and the reference's abort rule.  No particle restart files:
+// the history was not run on the host.
+static void report_lost_particles(const omcgpu_gen_out& out)
+{
+  double rec[OMCGPU_MAX_LOST_RECORDS][OMCGPU_LOST_RECORD];
+  const int64_t n = api.lost_particles(&rec[0][0], OMCGPU_MAX_LOST_RECORDS);
+  for (int64_t k = 0; k < n; ++k)
+    warning(fmt::format("Particle {} was lost on the device (no cell found) at r = ({}, {}, {}), "
+                        "u = ({}, {}, {}), E = {}",
+      (int64_t)rec[k][0], rec[k][1], rec[k][2], rec[k][3], rec[k][4], rec[k][5], rec[k][6], rec[k][7]));
+  if (out.n_lost > n)
+    warning(fmt::format("{} more particles were lost in this generation", out.n_lost - n));
+  simulation::n_lost_particles += out.n_lost;
+  const auto n_run = simulation::current_batch * settings::gen_per_batch * simulation::work_per_rank;
+  if (simulation::n_lost_particles >= settings::max_lost_particles &&
+      simulation::n_lost_particles >= settings::rel_max_lost_particles * n_run)
+    fatal_error("Maximum number of lost particles has been reached.");
+}
+
+// the device's per-kernel times go where print_runtime reads them (src/output.cpp:439-446, shown
+// for event-based runs): the crossing / collision kernels carry the lookup and the flight of the
+// following event (sweep mode 2), so "XS lookups" is the stand-alone lookup kernel only and
+// "Advancing" stays zero; tally scoring on the device is booked under "Particle death", the event
+// that hands the history's scores over
+static void add_seconds(Timer& t, double ms)
+{
+  t.elapsed_ += 1e-3 * ms;
+}
+
 void transport_generation()
 {
   if (!g_ready)
@@ -1017,7 +1051,12 @@ void transport_generation()
   global_tally_tracklength += out.global_tally[OMCGPU_K_TRACKLENGTH];
   global_tally_leakage += out.global_tally[OMCGPU_LEAKAGE];
   simulation::total_weight += out.total_weight;
-  simulation::n_lost_particles += out.n_lost;
+  if (out.n_lost > 0)
+    report_lost_particles(out);
+  add_seconds(simulation::time_event_calculate_xs, out.ms_xs);
+  add_seconds(simulation::time_event_surface_crossing, out.ms_surface);
+  add_seconds(simulation::time_event_collision, out.ms_collide);
+  add_seconds(simulation::time_event_death, out.ms_score);
   if (out.n_bank_full > 0)
     warning("The shared fission bank is full. Additional fission sites created in this generation will not be banked.");
   if (out.n_fission == 0)

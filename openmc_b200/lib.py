@@ -53,6 +53,7 @@ class Engine:
         self.lib = L = C.CDLL(path)
         L.omcgpu_last_error.restype = C.c_char_p
         L.omcgpu_kernel_launches.restype = C.c_int64
+        L.omcgpu_lost_particles.restype = C.c_int64
         self.model = None
 
     # -- helpers -----------------------------------------------------------------
@@ -72,6 +73,15 @@ class Engine:
 
     def finalize(self):
         self._check(self.lib.omcgpu_finalize())
+
+    def lost_particles(self, capacity: int = 64):
+        """{id, r, u, E} of the first lost particles of the last generation (what
+        Particle::mark_as_lost reports, src/particle.cpp:762-785) -> array [n][8]"""
+        rec = np.zeros((max(int(capacity), 1), 8))
+        n = int(self.lib.omcgpu_lost_particles(rec.ctypes.data_as(C.c_void_p), C.c_int64(capacity)))
+        if n < 0:
+            self._check(-n)
+        return rec[:n]
 
     def set_option(self, name: str, value: int):
         self._check(self.lib.omcgpu_set_option(name.encode(), C.c_int64(value)))

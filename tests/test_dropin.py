@@ -122,6 +122,52 @@ def test_refused_model_is_a_fatal_error(dropin):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def test_lost_particles_are_reported_like_the_reference(dropin):
+    """a pin cell whose moderator stops short of the boundary: the drop-in prints one warning per
+    lost particle (the device keeps the first 64 of a generation), counts them into
+    simulation::n_lost_particles and ends the run by the reference's rule
+    (src/particle.cpp:762-785) -- the reference itself aborts on the same model"""
+    m, lib, model, box, of, ce = rr.build("pincell_mg")
+    d = tempfile.mkdtemp(prefix="omc_dropin_")
+    try:
+        rr.write_inputs(d, m, lib, box, of, ce, 200, 3, 1)
+        path = os.path.join(d, "model.xml")
+        xml = open(path).read()
+        # the moderator cell loses its outer x boundary's neighbourhood: region ... -<x1> becomes ... -<xp>
+        import re
+        sid = max(int(i) for i in re.findall(r'<surface[^>]*\bid="(\d+)"', xml)) + 1
+        assert '<surface ' in xml
+        xml = xml.replace("<surface ", f'<surface id="{sid}" type="x-plane" coeffs="0.5"/>\n  <surface ', 1)
+        cells = re.findall(r'<cell [^>]*>', xml)
+        mod = cells[-1]
+        reg = re.search(r'region="([^"]*)"', mod).group(1)
+        xml = xml.replace(mod, mod.replace(f'region="{reg}"', f'region="{reg} -{sid}"'), 1)
+        open(path, "w").write(xml)
+        res = _run(d, dropin)
+        out = res.stdout + res.stderr
+        assert "was lost on the device" in out.replace("\n", " ").replace("  ", " "), out[-2000:]
+        assert "Maximum number of lost particles has been reached" in out.replace("\n", " ").replace("  ", " ")
+        assert res.returncode != 0
+        ref = _run(d, dropin, gpu=False)
+        assert ref.returncode != 0 and "Maximum number of lost particles" in (ref.stdout + ref.stderr).replace("\n", " ")
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def test_event_timers_are_fed_by_the_device(dropin):
+    """print_runtime (src/output.cpp:439-446) lists the event timers of an event-based run: in the
+    drop-in they carry the device's per-kernel times"""
+    d = _inputs("pincell_mg")
+    try:
+        env = dict(os.environ, OPENMC_GPU="1", OMCGPU_LIB=dropin)
+        res = subprocess.run([GPU_BINARY, "-s", "1", "-e"], cwd=d, capture_output=True, text=True, env=env, timeout=1200)
+        assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+        for line in ("Surface crossings", "Collisions", "Particle death"):
+            assert line in res.stdout
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 # ---------------------------------------------------------------------------------------------
 # C++ flattener == Python flattener, field by field
 # ---------------------------------------------------------------------------------------------

@@ -177,3 +177,37 @@ def test_ce_survival_biasing_generation_matches_oracle(emu_lib, sweep, monkeypat
     v = np.zeros(m); eng.tally_results(0, v)
     np.testing.assert_allclose(v, o.tally_results(0, m), rtol=1e-11, atol=1e-300)
     eng.finalize()
+
+
+def test_lost_particles_are_counted_and_recorded(emu_lib):
+    """Particle::mark_as_lost (src/particle.cpp:762-785): a pin cell whose moderator ends at x = 0.5
+    (nothing defined up to the reflective plane at 0.63) loses every particle that crosses that
+    plane -- same count as the oracle, and omcgpu_lost_particles returns {id, r, u, E} of the
+    first ones at the moment they were lost"""
+    from openmc_b200 import examples, mgxs
+    m, libx, box, of = examples.pincell_multigroup(mesh_dim=4, energy_bins=4)
+    xp = m.surface("x-plane", [0.5]).id
+    m.cells[-1].region += f" -{xp}"
+    model = mgxs.build_mg_model(m, libx)
+    o = Oracle(model)
+    n = 400
+    src = o.sample_initial_source(n, box, of)
+    eng = lib.Engine(emu_lib)
+    eng.init(model, 0, n)
+    gi = eng.gen_in(n, 0, 0, 1.0, False)
+    fb, out = eng.transport_generation(gi, src)
+    fb_o, out_o = o.transport_generation(gi, src)
+    assert out.n_lost == out_o.n_lost > 10
+    rec = eng.lost_particles()
+    assert rec.shape == (min(out.n_lost, 64), 8)
+    ids = rec[:, 0].astype(np.int64)
+    assert len(set(ids)) == len(ids) and ids.min() >= 1 and ids.max() <= n
+    # lost on the plane x = 0.5 moving outwards, or leaving the fuel (r = 0.54) beyond it
+    # (recorded after the last attempt: TINY_BIT = 1e-8 beyond the surface, src/particle.cpp:686-695)
+    on_plane = np.abs(rec[:, 1] - 0.5) < 2e-8
+    assert on_plane.sum() > 5 and np.all(rec[on_plane, 4] > 0)
+    np.testing.assert_allclose(np.hypot(rec[~on_plane, 1], rec[~on_plane, 2]), 0.54, atol=2e-8)
+    assert np.all(rec[:, 1] > 0.5 - 1e-9)
+    np.testing.assert_allclose(np.linalg.norm(rec[:, 4:7], axis=1), 1.0, rtol=1e-12)
+    assert rec[:3].shape == eng.lost_particles(3).shape
+    eng.finalize()
