@@ -112,6 +112,10 @@ extern "C" {
 #define OMCGPU_FILTER_UNIVERSE  4
 #define OMCGPU_FILTER_DISTRIBCELL 5 /* filter_idata = { cell index }; bins = instances of that cell
                                      (src/tallies/filter_distribcell.cpp:40-63) */
+/* LatticeType + HexLattice::Orientation, include/openmc/lattice.h */
+#define OMCGPU_LATTICE_RECT  0
+#define OMCGPU_LATTICE_HEX_Y 1
+#define OMCGPU_LATTICE_HEX_X 2
 /* TallyEstimator, include/openmc/constants.h:299 */
 #define OMCGPU_ESTIMATOR_ANALOG      0 /* scored after the collision from the collision records */
 #define OMCGPU_ESTIMATOR_TRACKLENGTH 1
@@ -220,6 +224,10 @@ typedef struct omcgpu_model {
   int32_t n_lattices;
   const int32_t* lat_shape;       /* [n_lattices][3]  n_cells_                         */
   const int32_t* lat_is3d;        /* [n_lattices]                                      */
+  const int32_t* lat_type;        /* [n_lattices] OMCGPU_LATTICE_*; hex (src/lattice.cpp:458-1009): lat_shape =
+                                     (2 n_rings - 1, 2 n_rings - 1, n_axial), lat_pitch = (radial, axial), lat_lower_left =
+                                     centre, lat_universes = the skewed square array with -1 outside the hexagon */
+  int32_t n_hex_lattices;         /* derived by omcgpu_init (ignored on input): lattices with lat_type != RECT */
   const int32_t* lat_outer;       /* [n_lattices] outer universe or -1                 */
   const double* lat_pitch;        /* [n_lattices][3]                                   */
   const double* lat_lower_left;   /* [n_lattices][3]                                   */

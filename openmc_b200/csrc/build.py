@@ -14,6 +14,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libomcgpu.so")
+# the same sources with the hexagonal-lattice dispatch compiled in (device.h, OMC_HEX_LATTICES): loaded
+# instead of LIB for models with hexagonal lattices (openmc_b200/lib.py, host/omcgpu_host.cpp)
+LIB_HEX = os.path.join(HERE, "libomcgpu_hex.so")
 SOURCES = ["engine.cu"]
 HEADERS = ["common.h", "device.h", "comm.h", "cuda_emu.h", os.path.join("..", "..", "include", "omcgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -22,9 +25,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 
 def stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(LIB_HEX):
         return True
-    t = os.path.getmtime(LIB)
+    t = min(os.path.getmtime(LIB), os.path.getmtime(LIB_HEX))
     return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SOURCES + HEADERS)
 
 
@@ -47,17 +50,24 @@ def build(force=False, verbose=False):
     if not (force or stale()):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + ["-o", LIB] + \
-          [os.path.join(HERE, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = os.path.join(HERE, "build.log")
-    with open(log, "w") as f:
-        f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed, see " + log)
-    if verbose:
-        print(res.stderr)
+    jobs = []
+    for out, extra, logname in ((LIB, [], "build.log"), (LIB_HEX, ["-DOMC_HEX_LATTICES=1"], "build_hex.log")):
+        cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + extra + ["-o", out] + \
+              [os.path.join(HERE, s) for s in SOURCES]
+        jobs.append((cmd, logname, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = None
+    for cmd, logname, proc in jobs:      # the two builds run side by side
+        text, _ = proc.communicate()
+        log = os.path.join(HERE, logname)
+        with open(log, "w") as f:
+            f.write(" ".join(cmd) + "\n" + text)
+        if proc.returncode != 0:
+            sys.stderr.write(text)
+            failed = log
+        elif verbose:
+            print(text)
+    if failed:
+        raise RuntimeError("nvcc failed, see " + failed)
     return LIB
 
 

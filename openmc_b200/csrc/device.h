@@ -548,10 +548,206 @@ struct LatIdx {
   int x, y, z;
 };
 
-OMC_HD bool lat_valid(int l, LatIdx i)
+// ---- hexagonal lattices, src/lattice.cpp:727-1007: rare, out of line; lat_shape = (2 n_rings - 1,
+// 2 n_rings - 1, n_axial), lat_pitch = (radial, axial), lat_lower_left = the centre ----------------
+// Compiled in only with -DOMC_HEX_LATTICES=1 (libomcgpu_hex.so; the loaders pick it for models with
+// hexagonal lattices): the dispatch in the lattice functions cost every event kernel 2-4 % in
+// registers and spills even for models without a lattice (profiles/r68-r69), so the default
+// build does not carry it and omcgpu_init refuses such models there, naming the other build.
+#ifndef OMC_HEX_LATTICES
+#define OMC_HEX_LATTICES 0
+#endif
+OMC_HD bool lat_is_hex(int l)
+{
+#if OMC_HEX_LATTICES
+  return DM.n_hex_lattices > 0 && gld(DM.lat_type + l) != OMCGPU_LATTICE_RECT;
+#else
+  (void)l;
+  return false;
+#endif
+}
+OMC_OOL bool hex_valid(int l, LatIdx i)
+{ // HexLattice::are_valid_indices :727-735
+  const int n_rings = (gld(DM.lat_shape + 3 * l) + 1) / 2;
+  return (i.x >= 0) && (i.y >= 0) && (i.z >= 0) && (i.x < 2 * n_rings - 1) && (i.y < 2 * n_rings - 1) &&
+         (i.x + i.y > n_rings - 2) && (i.x + i.y < 3 * n_rings - 2) && (i.z < gld(DM.lat_shape + 3 * l + 2));
+}
+OMC_OOL V3 hex_local_position(int l, V3 r, LatIdx i)
+{ // HexLattice::get_local_position :983-1007
+  const double* c = DM.lat_lower_left + 3 * l;
+  const double p0 = gld(DM.lat_pitch + 3 * l);
+  const int n_rings = (gld(DM.lat_shape + 3 * l) + 1) / 2;
+  if (gld(DM.lat_type + l) == OMCGPU_LATTICE_HEX_Y) {
+    r.x -= gld(c) + sqrt(3.0) / 2.0 * (i.x - n_rings + 1) * p0;
+    r.y -= (gld(c + 1) + (i.y - n_rings + 1) * p0 + (i.x - n_rings + 1) * p0 / 2.0);
+  } else {
+    r.x -= (gld(c) + (i.x - n_rings + 1) * p0 + (i.y - n_rings + 1) * p0 / 2.0);
+    r.y -= gld(c + 1) + sqrt(3.0) / 2.0 * (i.y - n_rings + 1) * p0;
+  }
+  if (gld(DM.lat_is3d + l)) {
+    const int n_axial = gld(DM.lat_shape + 3 * l + 2);
+    r.z -= gld(c + 2) - (0.5 * n_axial - i.z - 0.5) * gld(DM.lat_pitch + 3 * l + 1);
+  }
+  return r;
+}
+OMC_OOL LatIdx hex_get_indices(int l, V3 r, V3 u)
+{ // HexLattice::get_indices :879-973
+  const double* c = DM.lat_lower_left + 3 * l;
+  const double p0 = gld(DM.lat_pitch + 3 * l);
+  const int n_rings = (gld(DM.lat_shape + 3 * l) + 1) / 2;
+  const bool is_3d = gld(DM.lat_is3d + l);
+  V3 r_o = v3(r.x - gld(c), r.y - gld(c + 1), r.z);
+  if (is_3d)
+    r_o.z -= gld(c + 2);
+  LatIdx res;
+  res.z = 0;
+  if (is_3d) {
+    const int n_axial = gld(DM.lat_shape + 3 * l + 2);
+    const double iz_ = r_o.z / gld(DM.lat_pitch + 3 * l + 1) + 0.5 * n_axial;
+    const long long iz_close = llround(iz_);
+    if (fabs(iz_ - (double)iz_close) < FP_COINCIDENT)
+      res.z = (u.z > 0) ? (int)iz_close : (int)iz_close - 1;
+    else
+      res.z = (int)floor(iz_);
+  }
+  if (gld(DM.lat_type + l) == OMCGPU_LATTICE_HEX_Y) {
+    const double alpha = r_o.y - r_o.x / sqrt(3.0);
+    res.x = (int)floor(r_o.x / (0.5 * sqrt(3.0) * p0));
+    res.y = (int)floor(alpha / p0);
+  } else {
+    const double alpha = r_o.y - r_o.x * sqrt(3.0);
+    res.x = (int)floor(-alpha / (sqrt(3.0) * p0));
+    res.y = (int)floor(r_o.y / (0.5 * sqrt(3.0) * p0));
+  }
+  res.x += n_rings - 1;
+  res.y += n_rings - 1;
+  int i1_chg = 0, i2_chg = 0;
+  double d_min = INFTY, dp_min = INFTY;
+  for (int i = 0; i < 2; i++) {
+    for (int j = 0; j < 2; j++) {
+      LatIdx t;
+      t.x = res.x + j;
+      t.y = res.y + i;
+      t.z = 0;
+      V3 r_t = hex_local_position(l, r, t);
+      const double d = r_t.x * r_t.x + r_t.y * r_t.y;
+      const bool on_boundary = fabs(1.0 - d_min / d) < FP_COINCIDENT;
+      if (d < d_min || on_boundary) {
+        const double nrm = sqrt(d);
+        r_t = v3(r_t.x / nrm, r_t.y / nrm, r_t.z / nrm);
+        const double dp = u.x * r_t.x + u.y * r_t.y;
+        if (on_boundary && dp > dp_min)
+          continue;
+        d_min = d;
+        i1_chg = j;
+        i2_chg = i;
+        dp_min = dp;
+      }
+    }
+  }
+  res.x += i1_chg;
+  res.y += i2_chg;
+  return res;
+}
+OMC_HD int pack_trans(int tx, int ty, int tz);
+// HexLattice::distance :738-875: r is the position at the lattice's own level (z: the tile's), idx
+// the current tile -- distances are measured in the frames of the NEIGHBOUR tiles
+struct HexDist {
+  double d;
+  int trans;
+};
+OMC_HD HexDist hex_distance(int l, V3 r, V3 u, LatIdx idx)
+{
+  int trans;
+  const double p0 = gld(DM.lat_pitch + 3 * l);
+  const bool oy = gld(DM.lat_type + l) == OMCGPU_LATTICE_HEX_Y;
+  double beta_dir, gamma_dir, delta_dir;
+  if (oy) {
+    beta_dir = u.x * sqrt(3.0) / 2.0 + u.y / 2.0;
+    gamma_dir = u.x * sqrt(3.0) / 2.0 - u.y / 2.0;
+    delta_dir = u.y;
+  } else {
+    beta_dir = u.x;
+    gamma_dir = u.x / 2.0 - u.y * sqrt(3.0) / 2.0;
+    delta_dir = u.x / 2.0 + u.y * sqrt(3.0) / 2.0;
+  }
+  double d = INFTY;
+  trans = pack_trans(0, 0, 0);
+  LatIdx t = idx;
+  double edge = -copysign(0.5 * p0, beta_dir);
+  t.x = idx.x + (beta_dir > 0 ? 1 : -1);
+  V3 r_t = hex_local_position(l, r, t);
+  const double beta = oy ? r_t.x * sqrt(3.0) / 2.0 + r_t.y / 2.0 : r_t.x;
+  if ((fabs(beta - edge) > FP_PRECISION) && beta_dir != 0) {
+    d = (edge - beta) / beta_dir;
+    trans = pack_trans(beta_dir > 0 ? 1 : -1, 0, 0);
+  }
+  edge = -copysign(0.5 * p0, gamma_dir);
+  t.x = idx.x + (gamma_dir > 0 ? 1 : -1);
+  t.y = idx.y - (gamma_dir > 0 ? 1 : -1);
+  r_t = hex_local_position(l, r, t);
+  const double gamma = oy ? r_t.x * sqrt(3.0) / 2.0 - r_t.y / 2.0 : r_t.x / 2.0 - r_t.y * sqrt(3.0) / 2.0;
+  if ((fabs(gamma - edge) > FP_PRECISION) && gamma_dir != 0) {
+    const double this_d = (edge - gamma) / gamma_dir;
+    if (this_d < d) {
+      trans = pack_trans(gamma_dir > 0 ? 1 : -1, gamma_dir > 0 ? -1 : 1, 0);
+      d = this_d;
+    }
+  }
+  edge = -copysign(0.5 * p0, delta_dir);
+  t.x = idx.x;
+  t.y = idx.y + (delta_dir > 0 ? 1 : -1);
+  r_t = hex_local_position(l, r, t);
+  const double delta = oy ? r_t.y : r_t.x / 2.0 + r_t.y * sqrt(3.0) / 2.0;
+  if ((fabs(delta - edge) > FP_PRECISION) && delta_dir != 0) {
+    const double this_d = (edge - delta) / delta_dir;
+    if (this_d < d) {
+      trans = pack_trans(0, delta_dir > 0 ? 1 : -1, 0);
+      d = this_d;
+    }
+  }
+  if (gld(DM.lat_is3d + l)) {
+    const double z0 = copysign(0.5 * gld(DM.lat_pitch + 3 * l + 1), u.z);
+    if ((fabs(r.z - z0) > FP_PRECISION) && u.z != 0) {
+      const double this_d = (z0 - r.z) / u.z;
+      if (this_d < d) {
+        d = this_d;
+        trans = pack_trans(0, 0, u.z > 0 ? 1 : -1);
+      }
+    }
+  }
+  HexDist out;
+  out.d = d;
+  out.trans = trans;
+  return out;
+}
+OMC_HD V3 cell_rotate(int c, V3 v);
+// src/geometry.cpp:392-400: the distance is taken from the position at the lattice's OWN level --
+// the parent level's position through the fill cell's translation / rotation, z of the tile
+OMC_OOL HexDist hex_level_distance(int l, int c_up, V3 r_up, double z_local, V3 u, int ix, int iy, int iz)
+{
+  const double* t = DM.cell_translation + 3 * c_up;
+  V3 r_hex = v3(r_up.x - gld(t), r_up.y - gld(t + 1), r_up.z - gld(t + 2));
+  if (gld(DM.cell_rotated + c_up))
+    r_hex = cell_rotate(c_up, r_hex);
+  r_hex.z = z_local;
+  LatIdx li;
+  li.x = ix;
+  li.y = iy;
+  li.z = iz;
+  return hex_distance(l, r_hex, u, li);
+}
+
+OMC_HD bool rect_valid(int l, LatIdx i)
 {
   const int32_t* n = DM.lat_shape + 3 * l;
   return i.x >= 0 && i.x < gld(n) && i.y >= 0 && i.y < gld(n + 1) && i.z >= 0 && i.z < gld(n + 2);
+}
+OMC_HD bool lat_valid(int l, LatIdx i)
+{
+  if (lat_is_hex(l))
+    return hex_valid(l, i);
+  return rect_valid(l, i);
 }
 OMC_HD int lat_flat(int l, LatIdx i)
 {
@@ -573,6 +769,8 @@ OMC_HD int lat_axis_index(double r, double ll, double pitch, double u)
 }
 OMC_HD LatIdx lat_get_indices(int l, V3 r, V3 u)
 {
+  if (lat_is_hex(l))
+    return hex_get_indices(l, r, u);
   const double* ll = DM.lat_lower_left + 3 * l;
   const double* p = DM.lat_pitch + 3 * l;
   LatIdx i;
@@ -581,7 +779,14 @@ OMC_HD LatIdx lat_get_indices(int l, V3 r, V3 u)
   i.z = gld(DM.lat_is3d + l) ? lat_axis_index(r.z, gld(ll + 2), gld(p + 2), u.z) : 0;
   return i;
 }
+OMC_HD V3 rect_local_position(int l, V3 r, LatIdx i);
 OMC_HD V3 lat_local_position(int l, V3 r, LatIdx i)
+{
+  if (lat_is_hex(l))
+    return hex_local_position(l, r, i);
+  return rect_local_position(l, r, i);
+}
+OMC_HD V3 rect_local_position(int l, V3 r, LatIdx i)
 {
   const double* ll = DM.lat_lower_left + 3 * l;
   const double* p = DM.lat_pitch + 3 * l;
@@ -653,6 +858,69 @@ OMC_HD void set_u(const PState& ps, int64_t i, int lvl, V3 u)
   LV(uy, lvl) = u.y;
   LV(uz, lvl) = u.z;
 }
+// Hexagonal lattices at a particle's level l, for distance_to_boundary and cross_lattice.  For a
+// particle in the global columns (the list kernels) the out-of-line functions take (i, l) and read
+// the state through the constant-memory copy of the column pointers: the call sites hold two
+// integers, not twenty registers of arguments (measured: passing the values cost the event
+// kernels 2-4 %, profiles/r68).  A particle staged in thread-local memory (tail kernel) passes values.
+OMC_HD HexDist hex_distance_values(const PState& ps, int64_t i, int l)
+{
+  LatIdx li;
+  li.x = LV(lat_x, l);
+  li.y = LV(lat_y, l);
+  li.z = LV(lat_z, l);
+  return hex_level_distance(LV(lattice, l), LV(cell, l - 1), v3(LV(rx, l - 1), LV(ry, l - 1), LV(rz, l - 1)),
+    LV(rz, l), v3(LV(ux, l), LV(uy, l), LV(uz, l)), li.x, li.y, li.z);
+}
+// cross_lattice for a hex lattice: local position in the new tile; false when the tile is outside
+OMC_HD bool hex_cross_values(const PState& ps, int64_t i, int lvl)
+{
+  const int lat = LV(lattice, lvl);
+  LatIdx li;
+  li.x = LV(lat_x, lvl);
+  li.y = LV(lat_y, lvl);
+  li.z = LV(lat_z, lvl);
+  const int c_up = LV(cell, lvl - 1);
+  const double* t = DM.cell_translation + 3 * c_up;
+  V3 r = v3(LV(rx, lvl - 1) - gld(t), LV(ry, lvl - 1) - gld(t + 1), LV(rz, lvl - 1) - gld(t + 2));
+  if (gld(DM.cell_rotated + c_up))
+    r = cell_rotate(c_up, r);
+  r = hex_local_position(lat, r, li);
+  LV(rx, lvl) = r.x;
+  LV(ry, lvl) = r.y;
+  LV(rz, lvl) = r.z;
+  if (!hex_valid(lat, li))
+    return false;
+  LV(universe, lvl) = lat_universe(lat, li);
+  return true;
+}
+#if OMC_CUDA
+__device__ __noinline__ HexDist hex_distance_ool(int64_t i, int l)
+{
+  return hex_distance_values(c_ps, i, l);
+}
+__device__ __noinline__ bool hex_cross_ool(int64_t i, int lvl)
+{
+  return hex_cross_values(c_ps, i, lvl);
+}
+#endif
+OMC_HD HexDist hex_distance_at_level(const PState& ps, int64_t i, int l)
+{
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  if (ps.is_local == 0)
+    return hex_distance_ool(i, l);
+#endif
+  return hex_distance_values(ps, i, l);
+}
+OMC_HD bool hex_cross(const PState& ps, int64_t i, int lvl)
+{
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+  if (ps.is_local == 0)
+    return hex_cross_ool(i, lvl);
+#endif
+  return hex_cross_values(ps, i, lvl);
+}
+
 OMC_HD void reset_level(const PState& ps, int64_t i, int lvl)
 { // LocalCoord::reset, include/openmc/particle_data.h
   LV(cell, lvl) = C_NONE;
@@ -1010,7 +1278,13 @@ OMC_HD Boundary distance_to_boundary(const PState& ps, int64_t i, int n_coord, i
     cell_distance(c, r, u, surface, d_surf, level_surf_cross);
     const int lat = LV(lattice, l);
     if (lat != C_NONE) {
-      d_lat = lat_distance(lat, r, u, level_lat_trans);
+      if (lat_is_hex(lat)) { // out of line; the common path carries one uniform test
+        const HexDist hd = hex_distance_at_level(ps, i, l);
+        d_lat = hd.d;
+        level_lat_trans = hd.trans;
+      } else {
+        d_lat = lat_distance(lat, r, u, level_lat_trans);
+      }
       if (d_lat < 0)
         negative_lattice_distance = true;
     }

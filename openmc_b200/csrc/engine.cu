@@ -259,24 +259,30 @@ enum { NEXT_NONE = -2, NEXT_DEAD = -1, NEXT_COLLISION = 0, NEXT_SURFACE = 1 };
 constexpr int32_t PIDX_LOGGED = -1;    // flight logged by the tail: no particle state to consult
 constexpr int32_t PIDX_NO_FLIGHT = -2; // work-list position whose history made no flight this sweep
 
-OMC_OOL void record_lost(const PState& ps, const GenCtx& gc, int64_t i, int32_t slot)
-{ // rare, out of line: what the host reports for the first lost particles of a generation
-  double* rec = gc.lost_rec + (int64_t)slot * OMCGPU_LOST_RECORD;
-  const V3 r = get_r(ps, i, 0), u = get_u(ps, i, 0);
-  rec[0] = (double)(gc.id_offset + ps.id_shift + i + 1);
+// rare, out of line, VALUES only (an out-of-line helper that takes `const PState&` makes its
+// caller keep the 1 KB of column pointers in its stack frame: DESIGN.md, stack-frame pitfall --
+// measured again here, profiles/r67: 1272-byte frames, +50 % on every event kernel)
+OMC_OOL void record_lost(double* rec, int64_t id, V3 r, V3 u, double E)
+{
+  rec[0] = (double)id;
   rec[1] = r.x;
   rec[2] = r.y;
   rec[3] = r.z;
   rec[4] = u.x;
   rec[5] = u.y;
   rec[6] = u.z;
-  rec[7] = ps.E[i];
+  rec[7] = E;
 }
 OMC_D void mark_lost(const PState& ps, const GenCtx& gc, int64_t i)
 { // Particle::mark_as_lost, src/particle.cpp:762-785 (count + kill; the warning is the host's)
   const int32_t slot = atomic_add_i32(gc.n_lost, 1);
+#ifndef OMC_NO_LOST_REC /* measurement build */
   if (gc.lost_rec && slot < gc.lost_cap)
-    record_lost(ps, gc, i, slot);
+    record_lost(gc.lost_rec + (int64_t)slot * OMCGPU_LOST_RECORD, gc.id_offset + ps.id_shift + i + 1, get_r(ps, i, 0),
+      get_u(ps, i, 0), ps.E[i]);
+#else
+  (void)slot;
+#endif
   ps.wgt[i] = 0.0;
 }
 
@@ -606,19 +612,24 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
     LV(lat_x, lvl) = li.x;
     LV(lat_y, lvl) = li.y;
     LV(lat_z, lvl) = li.z;
-    V3 r = get_r(ps, i, lvl - 1);
-    const int c_up = LV(cell, lvl - 1);
-    const double* t = DM.cell_translation + 3 * c_up;
-    r.x -= gld(t);
-    r.y -= gld(t + 1);
-    r.z -= gld(t + 2);
-    if (gld(DM.cell_rotated + c_up)) // src/geometry.cpp:324-326
-      r = cell_rotate(c_up, r);
-    set_r(ps, i, lvl, lat_local_position(lat, r, li));
     bool found = false;
-    if (lat_valid(lat, li)) {
-      LV(universe, lvl) = lat_universe(lat, li);
-      found = find_cell_from(ps, i, n_coord, surface);
+    if (lat_is_hex(lat)) { // hexagonal lattice: out of line
+      if (hex_cross(ps, i, lvl))
+        found = find_cell_from(ps, i, n_coord, surface);
+    } else {
+      V3 r = get_r(ps, i, lvl - 1);
+      const int c_up = LV(cell, lvl - 1);
+      const double* t = DM.cell_translation + 3 * c_up;
+      r.x -= gld(t);
+      r.y -= gld(t + 1);
+      r.z -= gld(t + 2);
+      if (gld(DM.cell_rotated + c_up)) // src/geometry.cpp:324-326
+        r = cell_rotate(c_up, r);
+      set_r(ps, i, lvl, rect_local_position(lat, r, li));
+      if (rect_valid(lat, li)) {
+        LV(universe, lvl) = lat_universe(lat, li);
+        found = find_cell_from(ps, i, n_coord, surface);
+      }
     }
     if (!found) {
       ps.n_coord[i] = 1;
@@ -830,9 +841,19 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
   return ev_revive(ps, i);
 }
 
+// The particle columns a list kernel receives are the GLOBAL ones (EvArgs::ps.is_local == 0; the tail
+// kernel builds its thread-local views itself).  Telling the compiler lets it drop the
+// thread-local branches of find_cell_from / hex_cross / hex_distance_at_level from those kernels.
+#if OMC_CUDA && defined(__CUDA_ARCH__)
+#define ASSUME_GLOBAL_COLUMNS(a) __builtin_assume((a).ps.is_local == 0)
+#else
+#define ASSUME_GLOBAL_COLUMNS(a) ((void)0)
+#endif
+
 // ---- kernels -----------------------------------------------------------------
 OMC_D void body_init(int64_t tid, const EvArgs& a)
 {
+  ASSUME_GLOBAL_COLUMNS(a);
   if (tid >= a.gc.n)
     return;
   if (ev_init(a.ps, a.gc, a.src, tid))
@@ -874,6 +895,7 @@ OMC_KERNEL(k_xs_keys, KeyArgs, body_xs_keys)
 template<bool BX>
 OMC_D void body_xs(int64_t tid, const EvArgs& a)
 {
+  ASSUME_GLOBAL_COLUMNS(a);
   if (tid >= *a.q_in.count)
     return;
   ev_xs<BX>(a.ps, list_item(a.q_in, tid), a.xs_batch_min, a.gc.count_lookups ? a.gc.counters + CNT_OTHER : nullptr);
@@ -938,6 +960,7 @@ OMC_D void advance_and_route(int64_t tid, const EvArgs& a, int32_t i)
 
 OMC_D void body_advance(int64_t tid, const EvArgs& a)
 {
+  ASSUME_GLOBAL_COLUMNS(a);
   if (tid >= *a.q_in.count)
     return;
   advance_and_route(tid, a, list_item(a.q_in, tid));
@@ -951,6 +974,7 @@ OMC_KERNEL_GEO(k_advance, EvArgs, body_advance)
 template<bool BX>
 OMC_D void body_xs_advance(int64_t tid, const EvArgs& a)
 {
+  ASSUME_GLOBAL_COLUMNS(a);
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = list_item(a.q_in, tid);
@@ -971,6 +995,7 @@ OMC_KERNEL_MB_GEO(k_xs_advance_b, EvArgs, body_xs_advance<true>, 2)
 template<bool BX>
 OMC_D void body_surface_xa(int64_t tid, const EvArgs& a)
 {
+  ASSUME_GLOBAL_COLUMNS(a);
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = list_item(a.q_in, tid);
@@ -993,6 +1018,7 @@ OMC_KERNEL_DYN(k_surface_xa_dyn, EvArgs, body_surface_xa<false>, XA_MINBLOCKS)
 // carry none of the scoring code)
 OMC_D void body_collision_score(int64_t tid, const EvArgs& a)
 {
+  ASSUME_GLOBAL_COLUMNS(a);
   if (tid >= *a.q_in.count)
     return;
   ev_collide_score(a.ps, a.gc, list_item(a.q_in, tid));
@@ -1008,6 +1034,7 @@ OMC_KERNEL(k_collision_score, EvArgs, body_collision_score)
 // left: launched behind it on the same stream, only for models that have such tallies
 OMC_D void body_after_collision_score(int64_t tid, const EvArgs& a)
 {
+  ASSUME_GLOBAL_COLUMNS(a);
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = list_item(a.q_in, tid);
@@ -1023,6 +1050,7 @@ OMC_KERNEL(k_after_collision_score, EvArgs, body_after_collision_score)
 template<bool BX>
 OMC_D void body_collide_xa(int64_t tid, const EvArgs& a)
 {
+  ASSUME_GLOBAL_COLUMNS(a);
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = list_item(a.q_in, tid);
@@ -1640,6 +1668,7 @@ void k_score(int64_t n_ub, EvArgs a)
 
 OMC_D void body_surface(int64_t tid, const EvArgs& a)
 {
+  ASSUME_GLOBAL_COLUMNS(a);
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = list_item(a.q_in, tid);
@@ -1655,6 +1684,7 @@ OMC_KERNEL_GEO(k_surface, EvArgs, body_surface)
 template<bool BX>
 OMC_D void body_collide(int64_t tid, const EvArgs& a)
 {
+  ASSUME_GLOBAL_COLUMNS(a);
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = list_item(a.q_in, tid);
@@ -2405,7 +2435,7 @@ static int upload_model(const omcgpu_model* m)
     g_arena_size = 40 * 16 + (size_t)ns * (4 * 5 + 8 * 3 + 8 * OMCGPU_SURF_NCOEF + 2 * 4) + 80 * (size_t)h.n_quadrics +
                    (size_t)nc * (4 * 12 + 8 * 12) + 4 * (n_tok_ + n_cm_ + n_co_ + n_uc_ + n_lu_ + n_lo_) + 8 * n_kt_ +
                    4 * (2 * (size_t)ns + 1) + 8 * n_tok_ + /* half-space candidate lists: <= 2 entries per token */
-                   (size_t)nu * 4 + (size_t)nl * (4 * 8 + 8 * 6) + 4096;
+                   (size_t)nu * 4 + (size_t)nl * (4 * 9 + 8 * 6) + 4096;
     g_arena_size = (g_arena_size + 255) / 256 * 256;
     g_arena_used = 0;
     g_arena_align = 16;
@@ -2480,6 +2510,10 @@ static int upload_model(const omcgpu_model* m)
   const int n_lo = nl ? m->lat_offset_ofs[nl] : 0;
   UP(lat_shape, (size_t)nl * 3);
   UP(lat_is3d, nl);
+  UP(lat_type, nl);
+  h.n_hex_lattices = 0;
+  for (int l = 0; l < nl; ++l)
+    h.n_hex_lattices += m->lat_type[l] != OMCGPU_LATTICE_RECT ? 1 : 0;
   UP(lat_outer, nl);
   UP(lat_pitch, (size_t)nl * 3);
   UP(lat_lower_left, (size_t)nl * 3);
@@ -2706,7 +2740,7 @@ static int upload_model(const omcgpu_model* m)
     REBASE(cell_simple); REBASE(cell_region_ofs); REBASE(region_tokens); REBASE(cell_mat_ofs); REBASE(cell_material);
     REBASE(cell_sqrtkT_ofs); REBASE(cell_sqrtkT); REBASE(cell_translation); REBASE(cell_rotated); REBASE(cell_rotation);
     REBASE(cell_distribcell_index); REBASE(cell_offset_ofs); REBASE(cell_offset); REBASE(univ_cell_ofs);
-    REBASE(univ_cells); REBASE(tok_cell_ofs); REBASE(tok_cells); REBASE(lat_shape); REBASE(lat_is3d); REBASE(lat_outer);
+    REBASE(univ_cells); REBASE(tok_cell_ofs); REBASE(tok_cells); REBASE(lat_shape); REBASE(lat_is3d); REBASE(lat_type); REBASE(lat_outer);
     REBASE(lat_pitch); REBASE(lat_lower_left); REBASE(lat_univ_ofs); REBASE(lat_universes); REBASE(lat_offset_ofs);
     REBASE(lat_offsets);
 #undef REBASE
@@ -2735,6 +2769,12 @@ static int check_supported(const omcgpu_model* m)
           m->surf_periodic_axis[s] < -1 || m->surf_periodic_axis[s] > 2))
       return fail(OMCGPU_E_UNSUPPORTED, "periodic boundary: only between two planes%s");
   }
+#if !OMC_HEX_LATTICES
+  for (int l = 0; l < m->n_lattices; ++l)
+    if (m->lat_type[l] != OMCGPU_LATTICE_RECT)
+      return fail(OMCGPU_E_UNSUPPORTED, "hexagonal lattices (src/lattice.cpp:458-1009) are compiled into libomcgpu_hex.so "
+                                        "(-DOMC_HEX_LATTICES=1), not into this build: load that library%s");
+#endif
   for (int t = 0; t < m->n_tallies; ++t) {
     if (m->tally_n_filters[t] > OMCGPU_MAX_FILTERS || m->tally_n_scores[t] > OMCGPU_MAX_SCORES)
       return fail(OMCGPU_E_UNSUPPORTED, "tally has too many filters or scores%s");

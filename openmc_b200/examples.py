@@ -564,6 +564,64 @@ def c5g7_core(mesh_dim=510, tallies=True):
 
 
 # ----------------------------------------------------------------------------
+# hexagonal lattices (src/lattice.cpp:458-1009): a VVER-like bundle, multigroup
+# ----------------------------------------------------------------------------
+def hex_bundle(orientation="y", n_axial=None, n_rings=3, tallies=True):
+    """n_rings rings of pins on a hexagonal pitch (centre pin MOX, then UO2 with guide tubes at
+    three corners of the outer ring) in a vacuum cylinder; positions of the lattice outside the
+    cylinder's rings fall to the `outer` water universe.  n_axial: a three-dimensional lattice
+    (the axial levels alternate the centre pin)."""
+    from .model import HexLattice  # noqa: F401
+    m = Model()
+    names = ["UO2", "MOX70", "GT", "LWTR"]
+    mats = {n: m.material(name=n, macroscopic=n, units="macro", density=1.0) for n in names}
+    cyl = m.surface("z-cylinder", [0.0, 0.0, 0.45]).id
+    pin_u = {}
+    for k, n in enumerate(["UO2", "MOX70", "GT"]):
+        pin_u[n] = 10 + k
+        m.cell(region=f"-{cyl}", fill=mats[n], universe=10 + k)
+        m.cell(region=f"{cyl}", fill=mats["LWTR"], universe=10 + k)
+    u_water = 20
+    m.cell(region="", fill=mats["LWTR"], universe=u_water)
+    pitch = 1.275
+    n = 2 * n_rings - 1
+    nz = n_axial or 1
+    arr = np.full((nz, n, n), -1, dtype=np.int64)
+    for z in range(nz):
+        for i1 in range(n):
+            for i0 in range(n):
+                a, b = i0 - (n_rings - 1), i1 - (n_rings - 1)
+                if not (n_rings - 2 < i0 + i1 < 3 * n_rings - 2):
+                    continue
+                ring = max(abs(a), abs(b), abs(a + b))
+                u = pin_u["UO2"]
+                if ring == 0:
+                    u = pin_u["MOX70"] if z % 2 == 0 else pin_u["GT"]
+                elif ring == n_rings - 1 and (a, b) in ((n_rings - 1, 0), (0, -(n_rings - 1)), (-(n_rings - 1), n_rings - 1)):
+                    u = pin_u["GT"]
+                arr[z, i1, i0] = u
+    height = 4.0
+    lat = m.hex_lattice(n_rings=n_rings, pitch=(pitch,) if n_axial is None else (pitch, height / nz),
+                        center=(0.1, -0.05) if n_axial is None else (0.1, -0.05, 0.0),
+                        universes=arr, orientation=orientation, n_axial=n_axial, outer=u_water)
+    r_out = pitch * (n_rings - 0.3)
+    rc = m.surface("z-cylinder", [0.1, -0.05, r_out], "vacuum").id
+    z0 = m.surface("z-plane", [-height / 2], "reflective").id
+    z1 = m.surface("z-plane", [height / 2], "reflective").id
+    m.cell(region=f"-{rc} {z0} -{z1}", fill=lat, universe=0)
+    m.settings["legendre_to_tabular"] = True
+    if tallies:
+        half = r_out
+        m.meshes = [Mesh(1, [8, 8], [0.1 - half, -0.05 - half], [0.1 + half, -0.05 + half])]
+        fuel_cell = m.cells[0].id     # the fuel of the UO2 pin universe: one instance per UO2 position
+        m.filters = [Filter(1, "mesh", 1), Filter(2, "distribcell", [fuel_cell])]
+        m.tallies = [Tally(1, [1], ["flux", "fission"]), Tally(2, [2], ["flux", "nu-fission"])]
+    s = 0.6 * r_out
+    box = [0.1 - s, -0.05 - s, -height / 2, 0.1 + s, -0.05 + s, height / 2]
+    return m, c5g7_core_library(), box, True
+
+
+# ----------------------------------------------------------------------------
 # config C5: Hoogenboom-Martin full core (openmc/examples.py:94-439), continuous
 # energy, fuel expanded to a depleted-fuel-like set of synthetic nuclides
 # ----------------------------------------------------------------------------

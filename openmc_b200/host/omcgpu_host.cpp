@@ -362,27 +362,41 @@ void flatten_cells(Flat& F)
   const int nl1 = std::max(nl, 1);
   IV shape((size_t)nl1 * 3, 1), is3d(nl1, 0), outer(nl1, -1), lofs {0}, lun, loofs {0}, loff;
   DV pitch((size_t)nl1 * 3, 0.0), ll((size_t)nl1 * 3, 0.0);
+  IV ltype(nl1, OMCGPU_LATTICE_RECT);
   for (int l = 0; l < nl; ++l) {
-    auto r = dynamic_cast<const RectLattice*>(model::lattices[l].get());
-    if (!r)
-      unsupported(fmt::format("lattice {} (hexagonal)", model::lattices[l]->id_));
-    for (int k = 0; k < 3; ++k) {
-      shape[3 * l + k] = r->n_cells_[k];
-      pitch[3 * l + k] = r->pitch_[k];
-      ll[3 * l + k] = r->lower_left_[k];
+    const Lattice& base = *model::lattices[l];
+    if (auto h = dynamic_cast<const HexLattice*>(model::lattices[l].get())) {
+      // src/lattice.cpp:458-1009: the skewed square array as stored (C_NONE = -1 outside the hexagon)
+      ltype[l] = h->orientation_ == HexLattice::Orientation::y ? OMCGPU_LATTICE_HEX_Y : OMCGPU_LATTICE_HEX_X;
+      shape[3 * l + 0] = shape[3 * l + 1] = 2 * h->n_rings_ - 1;
+      shape[3 * l + 2] = h->n_axial_;
+      is3d[l] = h->is_3d_ ? 1 : 0;
+      pitch[3 * l + 0] = h->pitch_[0];
+      pitch[3 * l + 1] = h->is_3d_ ? h->pitch_[1] : 0.0;
+      ll[3 * l + 0] = h->center_[0];
+      ll[3 * l + 1] = h->center_[1];
+      ll[3 * l + 2] = h->is_3d_ ? h->center_[2] : 0.0;
+    } else if (auto r = dynamic_cast<const RectLattice*>(model::lattices[l].get())) {
+      for (int k = 0; k < 3; ++k) {
+        shape[3 * l + k] = r->n_cells_[k];
+        pitch[3 * l + k] = r->pitch_[k];
+        ll[3 * l + k] = r->lower_left_[k];
+      }
+      is3d[l] = r->is_3d_ ? 1 : 0;
+      if (!r->is_3d_) { // the reader leaves the z entries of a 2-D lattice unset
+        pitch[3 * l + 2] = 0.0;
+        ll[3 * l + 2] = 0.0;
+      }
+    } else {
+      unsupported(fmt::format("lattice {} (neither rectangular nor hexagonal)", base.id_));
     }
-    is3d[l] = r->is_3d_ ? 1 : 0;
-    if (!r->is_3d_) { // the reader leaves the z entries of a 2-D lattice unset
-      pitch[3 * l + 2] = 0.0;
-      ll[3 * l + 2] = 0.0;
-    }
-    outer[l] = r->outer_ == NO_OUTER_UNIVERSE ? -1 : r->outer_;
-    for (int32_t u : r->universes_)
+    outer[l] = base.outer_ == NO_OUTER_UNIVERSE ? -1 : base.outer_;
+    for (int32_t u : base.universes_)
       lun.push_back(u);
     lofs.push_back(lun.size());
     if (n_maps > 0)
-      for (size_t k = 0; k < (size_t)n_maps * r->universes_.size(); ++k)
-        loff.push_back(k < r->offsets_.size() ? r->offsets_[k] : -1);
+      for (size_t k = 0; k < (size_t)n_maps * base.universes_.size(); ++k)
+        loff.push_back(k < base.offsets_.size() ? base.offsets_[k] : -1);
     loofs.push_back(loff.size());
   }
   while ((int)loofs.size() < nl1 + 1)
@@ -390,6 +404,7 @@ void flatten_cells(Flat& F)
   F.m.n_lattices = nl;
   KEEP(lat_shape, shape);
   KEEP(lat_is3d, is3d);
+  KEEP(lat_type, ltype);
   KEEP(lat_outer, outer);
   KEEP(lat_pitch, pitch);
   KEEP(lat_lower_left, ll);
@@ -927,6 +942,8 @@ void bind(Fn& fn, const char* name)
     fatal_error(fmt::format("OPENMC_GPU: {} lacks the symbol {}", "libomcgpu", name));
 }
 
+bool g_hex_lattices = false; // the model has hexagonal lattices: the build that carries their code
+
 void load_library()
 {
   if (api.handle)
@@ -938,9 +955,9 @@ void load_library()
     Dl_info info;
     if (dladdr(reinterpret_cast<void*>(&load_library), &info) && info.dli_fname) {
       path = info.dli_fname;
-      path = path.substr(0, path.find_last_of('/') + 1) + "libomcgpu.so";
+      path = path.substr(0, path.find_last_of('/') + 1) + (g_hex_lattices ? "libomcgpu_hex.so" : "libomcgpu.so");
     } else {
-      path = "libomcgpu.so";
+      path = g_hex_lattices ? "libomcgpu_hex.so" : "libomcgpu.so";
     }
   }
   api.handle = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
@@ -975,6 +992,9 @@ bool enabled()
 
 void simulation_init()
 {
+  for (const auto& lat : model::lattices) // which build of the device library: see load_library
+    if (dynamic_cast<const HexLattice*>(lat.get()))
+      g_hex_lattices = true;
   load_library();
   const omcgpu_model* m;
   try {

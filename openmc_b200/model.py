@@ -94,6 +94,65 @@ class RectLattice:
 
 
 @dataclass
+class HexLattice:
+    """HexLattice of src/lattice.cpp:458-1009.  `universes` is the reference's own storage: the
+    skewed "square" array [n_axial][2 n_rings - 1][2 n_rings - 1] indexed [z][i_alpha][i_x]
+    (orientation y; [z][i_y][i_alpha] for x), flat index (2n-1)^2 z + (2n-1) i1 + i0
+    (get_flat_index :975-981), with -1 at the positions outside the hexagon
+    (are_valid_indices :727-735)."""
+    id: int
+    n_rings: int
+    pitch: Sequence[float]             # (radial,) or (radial, axial)
+    center: Sequence[float]            # (x, y) or (x, y, z)
+    universes: object
+    orientation: str = "y"
+    n_axial: Optional[int] = None      # None: two-dimensional
+    outer: Optional[int] = None
+
+    def valid(self, i0, i1):
+        n = self.n_rings
+        return 0 <= i0 < 2 * n - 1 and 0 <= i1 < 2 * n - 1 and n - 2 < i0 + i1 < 3 * n - 2
+
+    def input_order(self):
+        """(i1, i0) array positions in the order the <universes> text lists one axial level:
+        the index walks of fill_lattice_y / fill_lattice_x (src/lattice.cpp:548-685)"""
+        n = self.n_rings
+        seq = []
+        if self.orientation == "y":
+            i_x, i_a = 1, n - 1
+            for k in range(n - 1):                      # upper triangle
+                i_x -= 1
+                for j in range(k + 1):
+                    seq.append((i_a + n - 1, i_x + n - 1)); i_x += 2; i_a -= 1
+                i_x -= 2 * (k + 1); i_a += k + 1
+            for k in range(2 * n - 1):                  # middle
+                if k % 2 == 0:
+                    i_x -= 1
+                else:
+                    i_x += 1; i_a -= 1
+                for j in range(n - (k % 2)):
+                    seq.append((i_a + n - 1, i_x + n - 1)); i_x += 2; i_a -= 1
+                i_x -= 2 * (n - (k % 2)); i_a += n - (k % 2)
+            for k in range(n - 1):                      # lower triangle
+                i_x += 1; i_a -= 1
+                for j in range(n - k - 1):
+                    seq.append((i_a + n - 1, i_x + n - 1)); i_x += 2; i_a -= 1
+                i_x -= 2 * (n - k - 1); i_a += n - k - 1
+        else:
+            i_a, i_y = -(n - 1), n - 1
+            for k in range(n - 1):
+                for j in range(k + n):
+                    seq.append((i_y + n - 1, i_a + n - 1)); i_a += 1
+                i_a = -(n - 1); i_y -= 1
+            for k in range(n):
+                i_a = -(n - 1) + k
+                for j in range(2 * n - k - 1):
+                    seq.append((i_y + n - 1, i_a + n - 1)); i_a += 1
+                i_y -= 1
+        return seq
+
+
+@dataclass
 class Mesh:
     id: int
     dimension: Sequence[int]
@@ -306,7 +365,7 @@ class Model:
     def cell(self, **kw):
         kw.setdefault("id", len(self.cells) + 1)
         c = Cell(**kw)
-        if isinstance(c.fill, RectLattice):
+        if isinstance(c.fill, (RectLattice, HexLattice)):
             c.fill_type = "lattice"
         elif isinstance(c.fill, int):
             c.fill_type = "universe"
@@ -318,6 +377,12 @@ class Model:
     def lattice(self, **kw):
         kw.setdefault("id", len(self.lattices) + 1)
         l = RectLattice(**kw)
+        self.lattices.append(l)
+        return l
+
+    def hex_lattice(self, **kw):
+        kw.setdefault("id", len(self.lattices) + 1)
+        l = HexLattice(**kw)
         self.lattices.append(l)
         return l
 
@@ -435,7 +500,8 @@ class Model:
                 add_univ(c.fill)
         for l in self.lattices:
             for u in np.asarray(l.universes).reshape(-1):
-                add_univ(int(u))
+                if int(u) >= 0:                      # (hex lattices: -1 outside the hexagon)
+                    add_univ(int(u))
             if l.outer is not None:
                 add_univ(l.outer)
         u_index = {u: i for i, u in enumerate(univ_ids)}
@@ -500,7 +566,28 @@ class Model:
         louter = np.full(max(nl, 1), -1, np.int32)
         lpitch = np.zeros((max(nl, 1), 3)); lll = np.zeros((max(nl, 1), 3))
         lofs = [0]; lun = []
+        ltype = np.zeros(max(nl, 1), np.int32)
         for i, l in enumerate(self.lattices):
+            if isinstance(l, HexLattice):
+                n = 2 * l.n_rings - 1
+                arr = np.asarray(l.universes, dtype=np.int64).reshape(-1, n, n)
+                ltype[i] = abi.OMCGPU_LATTICE_HEX_Y if l.orientation == "y" else abi.OMCGPU_LATTICE_HEX_X
+                l3d[i] = int(l.n_axial is not None)
+                lshape[i] = (n, n, arr.shape[0])
+                lpitch[i, 0] = l.pitch[0]
+                if l3d[i]:
+                    lpitch[i, 1] = l.pitch[1]
+                lll[i, :len(l.center)] = l.center       # the lattice centre
+                if l.outer is not None:
+                    louter[i] = u_index[l.outer]
+                for z in range(arr.shape[0]):
+                    for i1 in range(n):
+                        for i0 in range(n):
+                            if l.valid(i0, i1) != (arr[z, i1, i0] >= 0):
+                                raise ValueError(f"hex lattice {l.id}: universes must be >= 0 exactly inside the hexagon")
+                lun += [u_index[int(u)] if u >= 0 else -1 for u in arr.reshape(-1)]
+                lofs.append(len(lun))
+                continue
             arr = np.asarray(l.universes)
             if arr.ndim == 2:
                 arr = arr[None]
@@ -517,7 +604,7 @@ class Model:
             flipped = arr[:, ::-1, :]
             lun += [u_index[int(u)] for u in flipped.reshape(-1)]
             lofs.append(len(lun))
-        v.update(n_lattices=nl, lat_shape=lshape, lat_is3d=l3d, lat_outer=louter, lat_pitch=lpitch,
+        v.update(n_lattices=nl, lat_shape=lshape, lat_is3d=l3d, lat_type=ltype, lat_outer=louter, lat_pitch=lpitch,
                  lat_lower_left=lll, lat_univ_ofs=np.array(lofs, np.int32),
                  lat_universes=np.array(lun or [0], np.int32),
                  lat_offset_ofs=np.zeros(max(nl, 1) + 1, np.int32),
@@ -529,7 +616,7 @@ class Model:
             if c.fill_type == "universe":
                 filled.add(c.fill)
         for l in self.lattices:
-            filled |= {int(u) for u in np.asarray(l.universes).reshape(-1)}
+            filled |= {int(u) for u in np.asarray(l.universes).reshape(-1) if int(u) >= 0}
             if l.outer is not None:
                 filled.add(l.outer)
         roots = [u for u in univ_ids if u not in filled]
@@ -545,7 +632,7 @@ class Model:
                 if c.fill_type == "universe":
                     d = max(d, 1 + depth(c.fill))
                 elif c.fill_type == "lattice":
-                    subs = {int(x) for x in np.asarray(c.fill.universes).reshape(-1)}
+                    subs = {int(x) for x in np.asarray(c.fill.universes).reshape(-1) if int(x) >= 0}
                     if c.fill.outer is not None:
                         subs.add(c.fill.outer)
                     d = max(d, 1 + max(depth(s) for s in subs))
@@ -581,7 +668,8 @@ class Model:
                 elif ctype[c] == abi.OMCGPU_FILL_LATTICE:
                     l = int(cfill[c])
                     for u in lun[lofs[l]:lofs[l + 1]]:
-                        n += count(int(u), target, memo)
+                        if u >= 0:                   # LatticeIter skips the empty positions of a hex lattice
+                            n += count(int(u), target, memo)
             memo[search] = n
             return n
 
@@ -627,6 +715,8 @@ class Model:
                         l = int(cfill[c])
                         o = 0                   # Lattice::fill_offset_table
                         for k, uu in enumerate(lun[lofs[l]:lofs[l + 1]]):
+                            if uu < 0:
+                                continue
                             loff[loofs[l] + mp * lat_size[l] + k] = o
                             o += count(int(uu), tu, memo)
                         offset += o

@@ -616,9 +616,18 @@ void cell_distance(int c, Vec3 r, Vec3 u, int on_surface, double& min_dist, int&
 // =============================================================================
 // Rectangular lattices -- src/lattice.cpp:243-248,252-306,310-342,352-377
 // =============================================================================
+bool lat_is_hex(int l)
+{
+  return M->lat_type[l] != OMCGPU_LATTICE_RECT;
+}
 bool lat_valid(int l, const int* i)
 {
   const int32_t* n = M->lat_shape + 3 * l;
+  if (lat_is_hex(l)) { // HexLattice::are_valid_indices, src/lattice.cpp:727-735
+    const int n_rings = (n[0] + 1) / 2;
+    return (i[0] >= 0) && (i[1] >= 0) && (i[2] >= 0) && (i[0] < 2 * n_rings - 1) && (i[1] < 2 * n_rings - 1) &&
+           (i[0] + i[1] > n_rings - 2) && (i[0] + i[1] < 3 * n_rings - 2) && (i[2] < n[2]);
+  }
   return i[0] >= 0 && i[0] < n[0] && i[1] >= 0 && i[1] < n[1] && i[2] >= 0 && i[2] < n[2];
 }
 int lat_flat(int l, const int* i)
@@ -639,8 +648,70 @@ bool coincident(double d1, double d2)
 {
   return std::abs(d1 - d2) < FP_COINCIDENT;
 }
+Vec3 lat_local_position(int l, Vec3 r, const int* i);
+// HexLattice::get_indices, src/lattice.cpp:879-973
+void hex_get_indices(int l, Vec3 r, Vec3 u, int* result)
+{
+  const double* center = M->lat_lower_left + 3 * l;
+  const double* pitch = M->lat_pitch + 3 * l;
+  const int n_rings = (M->lat_shape[3 * l] + 1) / 2;
+  const int n_axial = M->lat_shape[3 * l + 2];
+  const bool is_3d = M->lat_is3d[l];
+  Vec3 r_o {r.x - center[0], r.y - center[1], r.z};
+  if (is_3d)
+    r_o.z -= center[2];
+  result[2] = 0;
+  if (is_3d) {
+    double iz_ {r_o.z / pitch[1] + 0.5 * n_axial};
+    long iz_close {std::lround(iz_)};
+    if (coincident(iz_, iz_close))
+      result[2] = (u.z > 0) ? iz_close : iz_close - 1;
+    else
+      result[2] = std::floor(iz_);
+  }
+  if (M->lat_type[l] == OMCGPU_LATTICE_HEX_Y) {
+    double alpha = r_o.y - r_o.x / std::sqrt(3.0);
+    result[0] = std::floor(r_o.x / (0.5 * std::sqrt(3.0) * pitch[0]));
+    result[1] = std::floor(alpha / pitch[0]);
+  } else {
+    double alpha = r_o.y - r_o.x * std::sqrt(3.0);
+    result[0] = std::floor(-alpha / (std::sqrt(3.0) * pitch[0]));
+    result[1] = std::floor(r_o.y / (0.5 * std::sqrt(3.0) * pitch[0]));
+  }
+  result[0] += n_rings - 1;
+  result[1] += n_rings - 1;
+  int i1_chg = 0;
+  int i2_chg = 0;
+  double d_min {INFTY};
+  double dp_min {INFTY};
+  for (int i = 0; i < 2; i++) {
+    for (int j = 0; j < 2; j++) {
+      const int i_xyz[3] = {result[0] + j, result[1] + i, 0};
+      Vec3 r_t = lat_local_position(l, r, i_xyz);
+      double d = r_t.x * r_t.x + r_t.y * r_t.y;
+      bool on_boundary = coincident(1.0, d_min / d);
+      if (d < d_min || on_boundary) {
+        const double nrm = std::sqrt(d);
+        r_t = Vec3 {r_t.x / nrm, r_t.y / nrm, r_t.z / nrm};
+        double dp = u.x * r_t.x + u.y * r_t.y;
+        if (on_boundary && dp > dp_min)
+          continue;
+        d_min = d;
+        i1_chg = j;
+        i2_chg = i;
+        dp_min = dp;
+      }
+    }
+  }
+  result[0] += i1_chg;
+  result[1] += i2_chg;
+}
 void lat_get_indices(int l, Vec3 r, Vec3 u, int* result)
 {
+  if (lat_is_hex(l)) {
+    hex_get_indices(l, r, u, result);
+    return;
+  }
   const double* ll = M->lat_lower_left + 3 * l;
   const double* pitch = M->lat_pitch + 3 * l;
   double ix_ = (r.x - ll[0]) / pitch[0];
@@ -669,11 +740,107 @@ Vec3 lat_local_position(int l, Vec3 r, const int* i)
 {
   const double* ll = M->lat_lower_left + 3 * l;
   const double* pitch = M->lat_pitch + 3 * l;
+  if (lat_is_hex(l)) { // HexLattice::get_local_position, src/lattice.cpp:983-1007 (ll = the centre)
+    const int n_rings = (M->lat_shape[3 * l] + 1) / 2;
+    const int n_axial = M->lat_shape[3 * l + 2];
+    if (M->lat_type[l] == OMCGPU_LATTICE_HEX_Y) {
+      r.x -= ll[0] + std::sqrt(3.0) / 2.0 * (i[0] - n_rings + 1) * pitch[0];
+      r.y -= (ll[1] + (i[1] - n_rings + 1) * pitch[0] + (i[0] - n_rings + 1) * pitch[0] / 2.0);
+    } else {
+      r.x -= (ll[0] + (i[0] - n_rings + 1) * pitch[0] + (i[1] - n_rings + 1) * pitch[0] / 2.0);
+      r.y -= ll[1] + std::sqrt(3.0) / 2.0 * (i[1] - n_rings + 1) * pitch[0];
+    }
+    if (M->lat_is3d[l])
+      r.z -= ll[2] - (0.5 * n_axial - i[2] - 0.5) * pitch[1];
+    return r;
+  }
   r.x -= (ll[0] + (i[0] + 0.5) * pitch[0]);
   r.y -= (ll[1] + (i[1] + 0.5) * pitch[1]);
   if (M->lat_is3d[l])
     r.z -= (ll[2] + (i[2] + 0.5) * pitch[2]);
   return r;
+}
+// HexLattice::distance, src/lattice.cpp:738-875: r is the GLOBAL (lattice-level) position and
+// i_xyz the current indices -- the distances are taken relative to the NEIGHBOUR tiles
+double hex_distance(int l, Vec3 r, Vec3 u, const int* i_xyz, int* trans)
+{
+  const double* pitch = M->lat_pitch + 3 * l;
+  const bool oy = M->lat_type[l] == OMCGPU_LATTICE_HEX_Y;
+  double beta_dir, gamma_dir, delta_dir;
+  if (oy) {
+    beta_dir = u.x * std::sqrt(3.0) / 2.0 + u.y / 2.0;
+    gamma_dir = u.x * std::sqrt(3.0) / 2.0 - u.y / 2.0;
+    delta_dir = u.y;
+  } else {
+    beta_dir = u.x;
+    gamma_dir = u.x / 2.0 - u.y * std::sqrt(3.0) / 2.0;
+    delta_dir = u.x / 2.0 + u.y * std::sqrt(3.0) / 2.0;
+  }
+  double d {INFTY};
+  trans[0] = trans[1] = trans[2] = 0;
+  // beta direction
+  double edge = -std::copysign(0.5 * pitch[0], beta_dir);
+  Vec3 r_t;
+  {
+    const int s = beta_dir > 0 ? 1 : -1;
+    const int t[3] = {i_xyz[0] + s, i_xyz[1], i_xyz[2]};
+    r_t = lat_local_position(l, r, t);
+  }
+  double beta = oy ? r_t.x * std::sqrt(3.0) / 2.0 + r_t.y / 2.0 : r_t.x;
+  if ((std::abs(beta - edge) > FP_PRECISION) && beta_dir != 0) {
+    d = (edge - beta) / beta_dir;
+    trans[0] = beta_dir > 0 ? 1 : -1;
+    trans[1] = 0;
+    trans[2] = 0;
+  }
+  // gamma direction
+  edge = -std::copysign(0.5 * pitch[0], gamma_dir);
+  {
+    const int s = gamma_dir > 0 ? 1 : -1;
+    const int t[3] = {i_xyz[0] + s, i_xyz[1] - s, i_xyz[2]};
+    r_t = lat_local_position(l, r, t);
+  }
+  double gamma = oy ? r_t.x * std::sqrt(3.0) / 2.0 - r_t.y / 2.0 : r_t.x / 2.0 - r_t.y * std::sqrt(3.0) / 2.0;
+  if ((std::abs(gamma - edge) > FP_PRECISION) && gamma_dir != 0) {
+    double this_d = (edge - gamma) / gamma_dir;
+    if (this_d < d) {
+      trans[0] = gamma_dir > 0 ? 1 : -1;
+      trans[1] = gamma_dir > 0 ? -1 : 1;
+      trans[2] = 0;
+      d = this_d;
+    }
+  }
+  // delta direction
+  edge = -std::copysign(0.5 * pitch[0], delta_dir);
+  {
+    const int s = delta_dir > 0 ? 1 : -1;
+    const int t[3] = {i_xyz[0], i_xyz[1] + s, i_xyz[2]};
+    r_t = lat_local_position(l, r, t);
+  }
+  double delta = oy ? r_t.y : r_t.x / 2.0 + r_t.y * std::sqrt(3.0) / 2.0;
+  if ((std::abs(delta - edge) > FP_PRECISION) && delta_dir != 0) {
+    double this_d = (edge - delta) / delta_dir;
+    if (this_d < d) {
+      trans[0] = 0;
+      trans[1] = delta_dir > 0 ? 1 : -1;
+      trans[2] = 0;
+      d = this_d;
+    }
+  }
+  if (M->lat_is3d[l]) { // top and bottom; z is LOCAL to the tile here as in the reference (r.z of the argument)
+    double z = r.z;
+    double z0 {std::copysign(0.5 * pitch[1], u.z)};
+    if ((std::abs(z - z0) > FP_PRECISION) && u.z != 0) {
+      double this_d = (z0 - z) / u.z;
+      if (this_d < d) {
+        d = this_d;
+        trans[0] = 0;
+        trans[1] = 0;
+        trans[2] = u.z > 0 ? 1 : -1;
+      }
+    }
+  }
+  return d;
 }
 double lat_distance(int l, Vec3 r, Vec3 u, int* trans)
 {
@@ -891,7 +1058,20 @@ BoundaryInfo distance_to_boundary(Particle& p)
     int c = coord.cell;
     cell_distance(c, r, u, p.surface, d_surf, level_surf_cross);
     if (coord.lattice != C_NONE) {
-      d_lat = lat_distance(coord.lattice, r, u, level_lat_trans);
+      if (lat_is_hex(coord.lattice)) { // src/geometry.cpp:392-400: the position at the lattice's own level
+        const int c_above = p.coord[i - 1].cell;
+        const double* t = M->cell_translation + 3 * c_above;
+        Vec3 r_hex = p.coord[i - 1].r;
+        r_hex.x -= t[0];
+        r_hex.y -= t[1];
+        r_hex.z -= t[2];
+        if (M->cell_rotated[c_above])
+          r_hex = cell_rotate(c_above, r_hex);
+        r_hex.z = coord.r.z;
+        d_lat = hex_distance(coord.lattice, r_hex, u, coord.lat_idx, level_lat_trans);
+      } else {
+        d_lat = lat_distance(coord.lattice, r, u, level_lat_trans);
+      }
       if (d_lat < 0)
         mark_as_lost(p, "negative distance to a lattice boundary");
     }

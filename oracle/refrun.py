@@ -75,6 +75,21 @@ def geometry_elements(m) -> list:
             a.append(f'rotation="{_fmt(c.rotation)}"')
         out.append("  <cell " + " ".join(a) + "/>")
     for l in m.lattices:
+        if hasattr(l, "n_rings"):      # HexLattice: <universes> in the order fill_lattice_x / _y walk it
+            n = 2 * l.n_rings - 1
+            arr = np.asarray(l.universes, dtype=np.int64).reshape(-1, n, n)
+            out.append(f'  <hex_lattice id="{LATTICE_ID_BASE + l.id}" n_rings="{l.n_rings}"' +
+                       (f' n_axial="{l.n_axial}"' if l.n_axial is not None else "") +
+                       f' orientation="{l.orientation}">')
+            out.append(f"    <pitch>{_fmt(l.pitch)}</pitch>")
+            out.append(f"    <center>{_fmt(l.center)}</center>")
+            if l.outer is not None:
+                out.append(f"    <outer>{l.outer}</outer>")
+            order = l.input_order()
+            rows = [" ".join(str(int(arr[z, i1, i0])) for i1, i0 in order) for z in range(arr.shape[0])]
+            out.append("    <universes>\n" + "\n".join(rows) + "\n    </universes>")
+            out.append("  </hex_lattice>")
+            continue
         arr = np.asarray(l.universes)
         if arr.ndim == 2:
             ny, nx = arr.shape

@@ -30,6 +30,8 @@ RUNS = {
     "pincell_ce_analog_survival": (1000, 8, 3),   # the same with survival biasing
     "pincell_mg_analog": (1000, 8, 3),     # analog estimator, multigroup
     "pincell_mg_analog_survival": (1000, 8, 3),
+    "hex_bundle_y": (1000, 6, 2),          # hexagonal lattice, orientation y, mesh + distribcell tallies
+    "hex_bundle_x3d": (1000, 6, 2),        # orientation x, two axial levels
 }
 _CACHE = {}
 
@@ -61,6 +63,12 @@ def build(name):
         m.tallies.append(Tally(nt + 3, [nf + 1], six, estimator="collision"))
         if name.endswith("_survival"):
             m.settings["survival_biasing"] = 1
+    elif name == "hex_bundle_y":
+        m, lib, box, of = examples.hex_bundle("y")
+        ce = False
+    elif name == "hex_bundle_x3d":
+        m, lib, box, of = examples.hex_bundle("x", n_axial=2)
+        ce = False
     elif name == "pincell_ce_temperatures":
         m, lib, box, of = examples.pincell_ce(n_grid=3000, mesh_dim=6, energy_bins=12, tallies=True,
                                                temperatures=((294.0, 600.0, 900.0), (880.0, 620.0, 600.0, 575.0)))

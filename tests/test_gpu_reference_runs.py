@@ -24,7 +24,8 @@ from oracle.binding import Oracle
 pytestmark = pytest.mark.gpu
 
 MG = ["pincell_mg", "c5g7_core", "surface_zoo", "rotated_fills", "periodic_box", "white_pincell", "quadric_pin",
-      "pincell_mg_analog", "pincell_mg_analog_survival"]          # analog-estimator tallies
+      "pincell_mg_analog", "pincell_mg_analog_survival",          # analog-estimator tallies
+      "hex_bundle_y", "hex_bundle_x3d"]                           # hexagonal lattices
 CE = ["pincell_ce", "pincell_ce_temperatures", "assembly_ce", "pwr_core_ce", "pincell_ce_analog", "pincell_ce_analog_survival",
       # multigroup, but a last-ulp difference of CUDA's log() flips a history within five generations
       # (curved reflective boundary + rotated re-entry): the first four generations agree to 1e-6

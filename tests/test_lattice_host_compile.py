@@ -123,3 +123,41 @@ def test_nuclide_sampling_from_block_prefix_sums(emu_lib, env, monkeypatch):
     for f in ("r", "u", "E", "wgt", "parent_id", "progeny_id"):
         assert np.array_equal(fb[f], fb_o[f]), f
     eng.finalize()
+
+
+@pytest.mark.parametrize("sweep", ["1", "2"])
+@pytest.mark.parametrize("threshold", ["0", "100000"])
+@pytest.mark.parametrize("name", ["hex_bundle_y", "hex_bundle_x3d"])
+def test_hexagonal_lattices(emu_lib, name, threshold, sweep, monkeypatch):
+    """HexLattice (src/lattice.cpp:458-1009: get_indices, get_local_position, distance with the
+    neighbour-tile frames, are_valid_indices, the skewed square storage and its distribcell
+    offsets), both orientations, 2-D and 3-D: one generation of the engine sources equals the
+    oracle -- which equals the reference's own binary bit for bit on these two models
+    (tests/test_reference_end_to_end.py)"""
+    import reference_runs as rr
+    from openmc_b200 import lib
+    from oracle.binding import Oracle
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)
+    monkeypatch.setenv("OMCGPU_SWEEP", sweep)
+    m, libx, model, box, of, ce = rr.build(name)
+    o = Oracle(model)
+    n = 1500
+    src = o.sample_initial_source(n, box, of)
+    eng = lib.Engine(emu_lib)
+    eng.init(model, 0, n)
+    gi = eng.gen_in(n, 0, 0, 1.0, True)
+    fb, out = eng.transport_generation(gi, src)
+    fb_o, out_o = o.transport_generation(gi, src)
+    assert out.n_lost == 0 and out_o.n_lost == 0
+    assert out.n_fission == out_o.n_fission and out.n_events == out_o.n_events
+    assert out.n_crossings == out_o.n_crossings
+    for f in ("r", "u", "E", "parent_id", "progeny_id"):
+        assert np.array_equal(fb[f], fb_o[f]), f
+    np.testing.assert_allclose(out.global_tally[:], out_o.global_tally[:], rtol=1e-13)
+    for t in range(int(model["n_tallies"])):
+        k = int(model["tally_result_ofs"][t + 1] - model["tally_result_ofs"][t])
+        v = np.zeros(k); eng.tally_results(t, v)
+        vo = o.tally_results(t, k)
+        assert vo.sum() > 0
+        np.testing.assert_allclose(v, vo, rtol=1e-11, atol=1e-300)
+    eng.finalize()
