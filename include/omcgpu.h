@@ -202,6 +202,9 @@ typedef struct omcgpu_model {
   const int32_t* cell_material;   /* material index, -1 = MATERIAL_VOID                */
   const int32_t* cell_sqrtkT_ofs; /* [n_cells+1] into cell_sqrtkT                      */
   const double* cell_sqrtkT;      /* sqrt(k_B T) per instance (or 1 entry)             */
+  const int32_t* cell_density_ofs;/* [n_cells+1] into cell_density_mult                */
+  const double* cell_density_mult;/* Cell::density_mult_ (src/cell.cpp:104-111): density of the instance / the
+                                     material's density, per instance or 1 entry; {1.0} when the cell gives none */
   const double* cell_translation; /* [n_cells][3]                                      */
   const int32_t* cell_rotated;    /* [n_cells] fill cell has a rotation (Cell::rotation_ non-empty)   */
   const double* cell_rotation;    /* [n_cells][9] rotation matrix as Cell::set_rotation stores it (src/cell.cpp:48-90) */

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -2187,6 +2188,8 @@ struct Engine {
   int n_base_materials = 0;
   std::vector<int32_t> mat_base;    // [device material] -> model material (empty: identity)
   std::vector<double> mat_sqrtkT;   // [device material] the cell temperature it was resolved for
+  std::vector<double> mat_mult;     // [device material] the cell density multiplier folded into its atom densities
+  bool temps_expanded = false;      // the device materials were resolved per cell temperature (temperature tables)
   const char* geo_blob = nullptr; // CSG tables in one block (device.h, gld)
   size_t geo_bytes = 0;
   unsigned geo_smem = 0;        // bytes of it the geometry kernels stage in shared memory
@@ -2341,8 +2344,22 @@ static double hash_edge_for(int k, double e_min, double spacing)
 // code (no per-lookup temperature search, no kT in the collision registers).
 struct TemperatureExpansion {
   std::vector<int32_t> cell_mat_ofs, cell_material, mat_id, mat_fissionable, mat_nuc_ofs, mat_nuclide, mat_base;
-  std::vector<double> mat_atom_density, mat_sqrtkT;
+  std::vector<double> mat_atom_density, mat_sqrtkT, mat_mult;
 };
+// Cell density multipliers (Cell::density_mult, src/cell.cpp:104-111; Material::atom_density(i, rho),
+// include/openmc/material.h:104) are resolved the same way: a (material, multiplier) pair is a device
+// material whose atom densities are atom_density_(i) * multiplier -- the very product the reference
+// forms at every lookup -- so the kernels carry neither the multiplier nor its test
+// (src/particle.cpp:209: a change of multiplier is a change of device material).
+static bool has_density_multipliers(const omcgpu_model* m)
+{
+  if (!m->cell_density_ofs || !m->cell_density_mult)
+    return false;
+  for (int k = 0; k < m->cell_density_ofs[m->n_cells]; ++k)
+    if (m->cell_density_mult[k] != 1.0)
+      return true;
+  return false;
+}
 static int nearest_table(const omcgpu_model* m, int d, double kT)
 {
   int best = m->nuct_ofs[d];
@@ -2358,24 +2375,28 @@ static int nearest_table(const omcgpu_model* m, int d, double kT)
 }
 static void expand_temperatures(const omcgpu_model* m, TemperatureExpansion& X)
 {
-  std::map<std::pair<int32_t, double>, int32_t> derived;
+  std::map<std::tuple<int32_t, double, double>, int32_t> derived;
+  const bool temps = m->n_nuclide_temps > 0, dens = has_density_multipliers(m);
   X.cell_mat_ofs.push_back(0);
   for (int c = 0; c < m->n_cells; ++c) {
     const int m0 = m->cell_mat_ofs[c], nmat = m->cell_mat_ofs[c + 1] - m0;
-    const int k0 = m->cell_sqrtkT_ofs[c], nkt = m->cell_sqrtkT_ofs[c + 1] - k0;
-    const int n = nmat == 0 ? 0 : std::max(nmat, std::max(nkt, 1));
+    const int k0 = m->cell_sqrtkT_ofs[c], nkt = temps ? m->cell_sqrtkT_ofs[c + 1] - k0 : 0;
+    const int d0 = dens ? m->cell_density_ofs[c] : 0, nd = dens ? m->cell_density_ofs[c + 1] - d0 : 0;
+    const int n = nmat == 0 ? 0 : std::max(std::max(nmat, nd), std::max(nkt, 1));
     for (int k = 0; k < n; ++k) {
       const int32_t mat = m->cell_material[m0 + (nmat > 1 ? k : 0)];
       if (mat < 0) {
         X.cell_material.push_back(mat);
         continue;
       }
-      const double sq = nkt > 0 ? m->cell_sqrtkT[k0 + (nkt > 1 ? k : 0)] : 0.0;
-      auto it = derived.find({mat, sq});
+      const double sq = nkt > 0 ? m->cell_sqrtkT[k0 + (nkt > 1 ? k : 0)] : 0.0; // (the key of a model without temperature tables)
+      const double mult = nd > 0 ? m->cell_density_mult[d0 + (nd > 1 ? k : 0)] : 1.0;
+      auto it = derived.find({mat, sq, mult});
       if (it == derived.end()) {
-        it = derived.emplace(std::make_pair(mat, sq), (int32_t)X.mat_base.size()).first;
+        it = derived.emplace(std::make_tuple(mat, sq, mult), (int32_t)X.mat_base.size()).first;
         X.mat_base.push_back(mat);
         X.mat_sqrtkT.push_back(sq);
+        X.mat_mult.push_back(mult);
       }
       X.cell_material.push_back(it->second);
     }
@@ -2388,8 +2409,8 @@ static void expand_temperatures(const omcgpu_model* m, TemperatureExpansion& X)
     X.mat_id.push_back(m->mat_id[b]);
     X.mat_fissionable.push_back(m->mat_fissionable[b]);
     for (int k = m->mat_nuc_ofs[b]; k < m->mat_nuc_ofs[b + 1]; ++k) {
-      X.mat_nuclide.push_back(nearest_table(m, m->mat_nuclide[k], kT));
-      X.mat_atom_density.push_back(m->mat_atom_density[k]);
+      X.mat_nuclide.push_back(temps ? nearest_table(m, m->mat_nuclide[k], kT) : m->mat_nuclide[k]);
+      X.mat_atom_density.push_back(m->mat_atom_density[k] * X.mat_mult[d]); // atom_density_(i) * rho_multiplier
     }
     X.mat_nuc_ofs.push_back((int32_t)X.mat_nuclide.size());
   }
@@ -2404,7 +2425,11 @@ static int upload_model(const omcgpu_model* m)
   G.mat_base.clear();
   G.mat_sqrtkT.clear();
   h.mat_base = nullptr;
-  if (h.run_CE && m->n_nuclide_temps > 0) {
+  G.mat_mult.clear();
+  G.temps_expanded = h.run_CE && m->n_nuclide_temps > 0;
+  h.cell_density_ofs = nullptr; // host-side input only: folded into the device materials below
+  h.cell_density_mult = nullptr;
+  if (h.run_CE && (m->n_nuclide_temps > 0 || has_density_multipliers(m))) {
     expand_temperatures(m, X);
     h.n_materials = (int32_t)X.mat_base.size();
     h.cell_mat_ofs = X.cell_mat_ofs.data();
@@ -2419,6 +2444,7 @@ static int upload_model(const omcgpu_model* m)
     h.nuct_ofs = nullptr;
     G.mat_base = X.mat_base;
     G.mat_sqrtkT = X.mat_sqrtkT;
+    G.mat_mult = X.mat_mult;
   }
   const int ns = h.n_surfaces, nc = h.n_cells, nu = h.n_universes, nl = h.n_lattices;
   const int nm = h.n_materials;
@@ -2769,6 +2795,9 @@ static int check_supported(const omcgpu_model* m)
           m->surf_periodic_axis[s] < -1 || m->surf_periodic_axis[s] > 2))
       return fail(OMCGPU_E_UNSUPPORTED, "periodic boundary: only between two planes%s");
   }
+  if (!m->run_CE && has_density_multipliers(m))
+    return fail(OMCGPU_E_UNSUPPORTED, "cell density multipliers (src/cell.cpp:104-120) in a multigroup model are not "
+                                      "supported on the device (continuous-energy models: resolved at omcgpu_init)%s");
 #if !OMC_HEX_LATTICES
   for (int l = 0; l < m->n_lattices; ++l)
     if (m->lat_type[l] != OMCGPU_LATTICE_RECT)
@@ -3549,15 +3578,21 @@ int omcgpu_update(const omcgpu_model* model, uint32_t what)
   CUDA_OK(cudaStreamSynchronize(G.stream));
   if (!G.mat_base.empty()) {
     // several temperatures per nuclide: the device materials are (material, cell temperature) pairs
-    if (what & OMCGPU_UPDATE_CELL_TEMPERATURES)
+    if ((what & OMCGPU_UPDATE_CELL_TEMPERATURES) && G.temps_expanded)
       return fail(OMCGPU_E_UNSUPPORTED, "omcgpu_update: cell temperatures of a model with several temperatures per "
                                         "nuclide select other tables: call omcgpu_init again%s");
+    if (what & OMCGPU_UPDATE_CELL_TEMPERATURES) {
+      const int n = h.n_cells ? model->cell_sqrtkT_ofs[h.n_cells] : 0;
+      if (n != G.n_cell_sqrtkT)
+        return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_update: number of cell temperatures changed%s");
+      CUDA_OK(cudaMemcpy(const_cast<double*>(h.cell_sqrtkT), model->cell_sqrtkT, n * sizeof(double), cudaMemcpyHostToDevice));
+    }
     if (what & OMCGPU_UPDATE_MATERIAL_DENSITIES) {
       std::vector<double> dens;
       for (size_t d = 0; d < G.mat_base.size(); ++d) {
         const int b = G.mat_base[d];
         for (int k = model->mat_nuc_ofs[b]; k < model->mat_nuc_ofs[b + 1]; ++k)
-          dens.push_back(model->mat_atom_density[k]);
+          dens.push_back(model->mat_atom_density[k] * (d < G.mat_mult.size() ? G.mat_mult[d] : 1.0));
       }
       if ((int)dens.size() != G.n_mat_nuclides)
         return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_update: number of material nuclides changed%s");

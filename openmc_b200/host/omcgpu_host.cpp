@@ -267,7 +267,8 @@ void flatten_cells(Flat& F)
   const int nc = model::cells.size();
   IV id(nc), type(nc), univ(nc), fill(nc, -1), simple(nc), rofs {0}, rtok, mofs {0}, cmat, kofs {0}, rotated(nc, 0),
     dindex(nc, -1), oofs {0}, off;
-  DV ckt, trans((size_t)nc * 3, 0.0), rot((size_t)nc * 9, 0.0);
+  DV ckt, cden, trans((size_t)nc * 3, 0.0), rot((size_t)nc * 9, 0.0);
+  IV dofs {0};
   int n_maps = 0;
   for (int i = 0; i < nc; ++i)
     n_maps = std::max(n_maps, model::cells[i]->distribcell_index_ + 1);
@@ -298,9 +299,9 @@ void flatten_cells(Flat& F)
       for (int k = 0; k < 9; ++k)
         rot[9 * i + k] = c.rotation_[k];
     }
-    for (double d : c.density_mult_)
-      if (d != 1.0)
-        unsupported(fmt::format("the density multiplier of cell {}", c.id_));
+    for (double d : c.density_mult_) // {1.0} unless the cell gives densities (finalize_cell_densities)
+      cden.push_back(d);
+    dofs.push_back(cden.size());
     if (c.type_ == Fill::MATERIAL) {
       type[i] = OMCGPU_FILL_MATERIAL;
       for (int32_t mt : c.material_)
@@ -334,6 +335,8 @@ void flatten_cells(Flat& F)
   KEEP(cell_material, cmat);
   KEEP(cell_sqrtkT_ofs, kofs);
   KEEP(cell_sqrtkT, ckt);
+  KEEP(cell_density_ofs, dofs);
+  KEEP(cell_density_mult, cden);
   KEEP(cell_translation, trans);
   KEEP(cell_rotated, rotated);
   KEEP(cell_rotation, rot);

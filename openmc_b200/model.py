@@ -81,6 +81,7 @@ class Cell:
     temperature: Optional[float] = None
     translation: Sequence[float] = (0.0, 0.0, 0.0)
     rotation: Optional[Sequence[float]] = None   # (phi, theta, psi) in degrees, fill cells only
+    density: object = None             # g/cm3 of the cell (one value or one per instance): Cell::density_mult_
     fill_type: str = "material"        # 'material' | 'universe' | 'lattice'
 
 
@@ -549,6 +550,9 @@ class Model:
                  cell_region_ofs=np.array(rofs, np.int32), region_tokens=np.array(rtok or [0], np.int32),
                  cell_mat_ofs=np.array(mofs, np.int32), cell_material=np.array(cmat or [0], np.int32),
                  cell_sqrtkT_ofs=np.array(kofs, np.int32), cell_sqrtkT=np.array(ckt or [0.0]),
+                 # finalize_cell_densities (src/geometry_aux.cpp:197-211): {1.0} unless the cell gives
+                 # densities; those are divided by the material's density by the CE builder
+                 cell_density_ofs=np.arange(nc + 1, dtype=np.int32), cell_density_mult=np.ones(max(nc, 1)),
                  cell_translation=trans, cell_rotated=rotated, cell_rotation=rot,
                  cell_distribcell_index=np.full(nc, -1, np.int32),
                  cell_offset_ofs=np.zeros(nc + 1, np.int32), cell_offset=np.zeros(1, np.int32))

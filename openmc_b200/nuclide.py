@@ -27,6 +27,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _abi as abi
+from .model import MASS_NEUTRON, N_AVOGADRO
 from .model import K_BOLTZMANN, Model, normalize_density
 
 E_LOW, E_HIGH = 1.0e-5, 2.0e7
@@ -385,9 +386,14 @@ def build_ce_fields(model: Model, library: dict) -> dict:
 
     # materials
     mofs = [0]; mnuc = []; mden = []; mfis = []
+    gpcc = {}
     for m in model.materials:
         awr = [tables_of(library[n])[0].awr for n, _ in m.components]
         dens = normalize_density(m, awr)
+        g = 0.0        # Material::density_gpcc_, src/material.cpp:458-466
+        for d, a in zip(dens, awr):
+            g += d * a * MASS_NEUTRON / N_AVOGADRO
+        gpcc[m.id] = g
         mnuc += [index[n] for n, _ in m.components]
         mden += dens
         mofs.append(len(mnuc))
@@ -396,6 +402,18 @@ def build_ce_fields(model: Model, library: dict) -> dict:
              mat_id=np.array([m.id for m in model.materials], np.int32),
              mat_fissionable=np.array(mfis, np.int32), mat_nuc_ofs=np.array(mofs, np.int32),
              mat_nuclide=np.array(mnuc, np.int32), mat_atom_density=np.array(mden))
+    # cell densities -> multipliers (finalize_cell_densities, src/geometry_aux.cpp:197-211)
+    dofs = [0]; dmult = []
+    for c in model.cells:
+        if getattr(c, "density", None) is None:
+            dmult.append(1.0)
+        else:
+            if c.fill_type != "material" or c.fill is None:
+                raise ValueError(f"cell {c.id}: a density needs a (non-void) material")
+            rho = np.atleast_1d(np.asarray(c.density, float))
+            dmult += [float(r) / gpcc[c.fill.id] for r in rho]
+        dofs.append(len(dmult))
+    v.update(cell_density_ofs=np.array(dofs, np.int32), cell_density_mult=np.array(dmult or [1.0]))
     return v
 
 

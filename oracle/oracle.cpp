@@ -207,6 +207,7 @@ struct Particle {
   int surface {SURFACE_NONE};
   int material {C_NONE}, material_last {C_NONE};
   double sqrtkT {-1.0}, sqrtkT_last {0.0};
+  double density_mult {1.0}, density_mult_last {1.0}; // Cell::density_mult of the cell instance, src/geometry.cpp:180-181
   double E {0}, E_last {0};
   int g {0}, g_last {0};
   double wgt {1}, wgt_last {1}, wgt_born {1};
@@ -947,6 +948,10 @@ bool find_cell_inner(Particle& p)
       p.material = M->cell_material[M->cell_mat_ofs[i_cell] + (nmat > 1 ? p.cell_instance : 0)];
       p.sqrtkT_last = p.sqrtkT;
       p.sqrtkT = M->cell_sqrtkT[M->cell_sqrtkT_ofs[i_cell] + (nkt > 1 ? p.cell_instance : 0)];
+      // (a model description without the arrays -- older flattened fixtures -- has no multipliers)
+      const int nd = M->cell_density_ofs ? M->cell_density_ofs[i_cell + 1] - M->cell_density_ofs[i_cell] : 0;
+      p.density_mult_last = p.density_mult; // src/geometry.cpp:180-181, Cell::density_mult src/cell.cpp:104-111
+      p.density_mult = nd > 0 ? M->cell_density_mult[M->cell_density_ofs[i_cell] + (nd > 1 ? p.cell_instance : 0)] : 1.0;
       return true;
     }
     if (p.n_coord >= OMCGPU_MAX_COORD) {
@@ -1500,7 +1505,7 @@ void ce_calculate_xs(Particle& p, int32_t* i_grid_out = nullptr, int max_nuc = 0
   for (int k = M->mat_nuc_ofs[m]; k < M->mat_nuc_ofs[m + 1]; ++k) {
     MicroXS micro;
     ce_micro_xs(nuc_table(M->mat_nuclide[k], p.sqrtkT), i_log, p.E, micro);
-    double atom_density = M->mat_atom_density[k];
+    double atom_density = M->mat_atom_density[k] * p.density_mult; // Material::atom_density(i, rho_multiplier)
     p.xs_total += atom_density * micro.total;
     p.xs_absorption += atom_density * micro.absorption;
     p.xs_fission += atom_density * micro.fission;
@@ -1752,7 +1757,7 @@ void collision_ce(Particle& p)
   for (int k = M->mat_nuc_ofs[m]; k < M->mat_nuc_ofs[m + 1]; ++k) {
     const int table = nuc_table(M->mat_nuclide[k], p.sqrtkT);
     ce_micro_xs(table, i_log, p.E, micro);
-    prob += M->mat_atom_density[k] * micro.total;
+    prob += M->mat_atom_density[k] * p.density_mult * micro.total; // src/physics.cpp:507
     if (prob >= cutoff) {
       i_nuclide = table; // every nuc_* / rx_* array is indexed by table
       break;
@@ -2324,7 +2329,7 @@ void event_calculate_xs(Particle& p)
   RS.n_xs++;
   if (p.material != MATERIAL_VOID) {
     if (M->run_CE) {
-      if (p.material != p.material_last || p.sqrtkT != p.sqrtkT_last)
+      if (p.material != p.material_last || p.sqrtkT != p.sqrtkT_last || p.density_mult != p.density_mult_last)
         ce_calculate_xs(p);
     } else {
       mg_calculate_xs(p);

@@ -69,6 +69,8 @@ def geometry_elements(m) -> list:
             a.append(f'region="{c.region}"')
         if getattr(c, "temperature", None) is not None and c.fill_type == "material":
             a.append(f'temperature="{float(c.temperature)!r}"')
+        if getattr(c, "density", None) is not None:
+            a.append(f'density="{_fmt(np.atleast_1d(np.asarray(c.density, float)))}"')
         if any(float(t) != 0.0 for t in c.translation):
             a.append(f'translation="{_fmt(c.translation)}"')
         if getattr(c, "rotation", None) is not None:

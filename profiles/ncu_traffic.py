@@ -22,7 +22,11 @@ import sys
 def rows_of(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    return rows[0], rows[2:]
+    return rows[0], rows[1], rows[2:]
+
+
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6,
+        "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}
 
 
 def num(x):
@@ -32,8 +36,11 @@ def num(x):
 def main():
     workload, rep, trace, gen, sweep = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5])
     source = sys.argv[6] if len(sys.argv) > 6 else os.path.basename(rep)
-    hdr, data = rows_of(rep)
+    hdr, units, data = rows_of(rep)
     col = {h: i for i, h in enumerate(hdr)}
+
+    def scaled(d, name):       # ncu prints large counters in Kbyte / Mbyte / Gbyte, times in us / ms
+        return num(d[col[name]]) * UNIT.get(units[col[name]], 1.0)
     counts = {}
     for ln in open(trace):
         p = ln.split()
@@ -46,8 +53,8 @@ def main():
     for d in data:
         name = d[col["Kernel Name"]]
         e = {"grid": int(num(d[col["launch__grid_size"]])),
-             "dram_bytes": num(d[col["dram__bytes_read.sum"]]) + num(d[col["dram__bytes_write.sum"]]),
-             "duration_us": num(d[col["gpu__time_duration.sum"]]),
+             "dram_bytes": scaled(d, "dram__bytes_read.sum") + scaled(d, "dram__bytes_write.sum"),
+             "duration_us": scaled(d, "gpu__time_duration.sum"),
              "l2_hit_pct": num(d[col["lts__t_sector_hit_rate.pct"]]),
              "l1_hit_pct": num(d[col["l1tex__t_sector_hit_rate.pct"]]),
              "lanes_active": num(d[col["smsp__thread_inst_executed_per_inst_executed.ratio"]]),

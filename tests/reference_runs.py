@@ -32,6 +32,8 @@ RUNS = {
     "pincell_mg_analog_survival": (1000, 8, 3),
     "hex_bundle_y": (1000, 6, 2),          # hexagonal lattice, orientation y, mesh + distribcell tallies
     "hex_bundle_x3d": (1000, 6, 2),        # orientation x, two axial levels
+    "pincell_ce_density": (1000, 8, 3),    # cell densities (density multipliers) on the fuel rings and the moderator
+    "assembly_ce_density": (1000, 6, 2),   # one density per INSTANCE of the fuel cell (distribcell offsets)
 }
 _CACHE = {}
 
@@ -63,6 +65,23 @@ def build(name):
         m.tallies.append(Tally(nt + 3, [nf + 1], six, estimator="collision"))
         if name.endswith("_survival"):
             m.settings["survival_biasing"] = 1
+    elif name == "pincell_ce_density":
+        m, lib, box, of = examples.pincell_ce(n_grid=3000, mesh_dim=6, energy_bins=12, tallies=True,
+                                               temperatures=((294.0, 600.0, 900.0), (880.0, 620.0, 600.0, 575.0)))
+        m.settings["temperature_tolerance"] = 50.0
+        mats = [c for c in m.cells if c.fill_type == "material" and c.fill is not None]
+        mats[0].density = 9.3          # inner fuel ring: below the material's density
+        mats[1].density = 10.9         # outer ring: above
+        mats[-1].density = 0.66        # moderator
+        ce = True
+    elif name == "assembly_ce_density":
+        m, lib, box, of = examples.assembly_ce(n_grid=2000)
+        m.settings["material_cell_offsets"] = 1
+        fuel_cell = next(c for c in m.cells if c.fill_type == "material" and c.fill is not None
+                         and any(n == "U235" for n, _ in c.fill.components))
+        n_inst = 17 * 17 - 25
+        fuel_cell.density = list(10.0 + 0.4 * np.cos(0.37 * np.arange(n_inst)))
+        ce = True
     elif name == "hex_bundle_y":
         m, lib, box, of = examples.hex_bundle("y")
         ce = False

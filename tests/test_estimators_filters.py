@@ -156,3 +156,33 @@ def test_analog_estimator_on_gpu(gpu_engine, name, threshold, monkeypatch):
     mg = "_mg_" in name
     # multigroup: the same histories as the oracle (every bin to 1e-9); CE: a few flipped decisions
     _check_generation(gpu_engine, lambda: _analog_case(name), 20000, 1e-9 if mg else None, exact_bank=mg)
+
+
+@pytest.mark.parametrize("threshold", ["0", "100000"])
+@pytest.mark.parametrize("name", ["pincell_ce_density", "assembly_ce_density"])
+def test_cell_density_multipliers(emu_lib, name, threshold, monkeypatch):
+    """Cell::density_mult (src/cell.cpp:104-111) / Material::atom_density(i, rho): resolved at
+    omcgpu_init into (material, multiplier) device materials -- one density per cell (with several
+    temperatures per nuclide on top) and one per cell INSTANCE of a lattice; on both the oracle
+    equals the reference's binary bit for bit"""
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)
+    _check_generation(lib.Engine(emu_lib), lambda: _analog_case(name), 1500, 1e-11)
+
+
+def test_density_multipliers_of_a_multigroup_model_are_refused(emu_lib):
+    import reference_runs as rr
+    m, libx, model, box, of, ce = rr.build("pincell_mg")
+    model["cell_density_mult"][0] = 0.9          # (in place: the handle points at this array)
+    eng = lib.Engine(emu_lib)
+    try:
+        with pytest.raises(lib.OmcGpuError, match="density multipliers"):
+            eng.init(model, 0, 100)
+    finally:
+        model["cell_density_mult"][0] = 1.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["pincell_ce_density", "assembly_ce_density"])
+def test_cell_density_multipliers_on_gpu(gpu_engine, name, monkeypatch):
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", "2048")
+    _check_generation(gpu_engine, lambda: _analog_case(name), 20000, None, exact_bank=False)

@@ -27,6 +27,7 @@ MG = ["pincell_mg", "c5g7_core", "surface_zoo", "rotated_fills", "periodic_box",
       "pincell_mg_analog", "pincell_mg_analog_survival",          # analog-estimator tallies
       "hex_bundle_y", "hex_bundle_x3d"]                           # hexagonal lattices
 CE = ["pincell_ce", "pincell_ce_temperatures", "assembly_ce", "pwr_core_ce", "pincell_ce_analog", "pincell_ce_analog_survival",
+      "pincell_ce_density", "assembly_ce_density",                # cell density multipliers
       # multigroup, but a last-ulp difference of CUDA's log() flips a history within five generations
       # (curved reflective boundary + rotated re-entry): the first four generations agree to 1e-6
       "rotational_wedge"]
