@@ -497,6 +497,15 @@ int omcgpu_run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out);
 #define OMCGPU_LOST_RECORD 8
 #define OMCGPU_MAX_LOST_RECORDS 64
 int64_t omcgpu_lost_particles(double* records, int64_t capacity);
+
+/* The device library comes in two builds of the same sources (openmc_b200/csrc/build.py):
+ * libomcgpu.so, and libomcgpu_ext.so with the rarely needed features compiled in -- hexagonal
+ * lattices (src/lattice.cpp:458-1009) and secondary neutrons of reactions with an integer yield
+ * (src/physics.cpp:1158-1162, src/particle.cpp:417-473).  Compiled into every kernel, their
+ * dispatch costs 2-4 % even on models that use neither (profiles/r68-r70, r75), so the caller
+ * asks, before omcgpu_init, which build the model needs: 1 = libomcgpu_ext.so.  omcgpu_init of
+ * the other build refuses such a model by name.  Pure host code: no device is needed. */
+int omcgpu_needs_extended_build(const omcgpu_model* model);
 int omcgpu_get_fission_bank(omcgpu_site* fission_bank, int64_t capacity, int64_t* n);
 
 /* Uniform-comb resampling of the (sorted, device-resident) fission bank into

@@ -14,9 +14,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libomcgpu.so")
-# the same sources with the hexagonal-lattice dispatch compiled in (device.h, OMC_HEX_LATTICES): loaded
-# instead of LIB for models with hexagonal lattices (openmc_b200/lib.py, host/omcgpu_host.cpp)
-LIB_HEX = os.path.join(HERE, "libomcgpu_hex.so")
+# the same sources with the rarely needed features compiled in (device.h, OMC_EXTENDED: hexagonal lattices,
+# secondary neutrons of integer yields): loaded instead of LIB for the models omcgpu_needs_extended_build
+# names (openmc_b200/lib.py, host/omcgpu_host.cpp)
+LIB_EXT = os.path.join(HERE, "libomcgpu_ext.so")
 SOURCES = ["engine.cu"]
 HEADERS = ["common.h", "device.h", "comm.h", "cuda_emu.h", os.path.join("..", "..", "include", "omcgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -25,9 +26,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 
 def stale():
-    if not os.path.exists(LIB) or not os.path.exists(LIB_HEX):
+    if not os.path.exists(LIB) or not os.path.exists(LIB_EXT):
         return True
-    t = min(os.path.getmtime(LIB), os.path.getmtime(LIB_HEX))
+    t = min(os.path.getmtime(LIB), os.path.getmtime(LIB_EXT))
     return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SOURCES + HEADERS)
 
 
@@ -51,7 +52,7 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     jobs = []
-    for out, extra, logname in ((LIB, [], "build.log"), (LIB_HEX, ["-DOMC_HEX_LATTICES=1"], "build_hex.log")):
+    for out, extra, logname in ((LIB, [], "build.log"), (LIB_EXT, ["-DOMC_EXTENDED=1"], "build_ext.log")):
         cmd = [nvcc, "-ccbin", "/usr/bin/g++"] + NVCC_FLAGS + extra + ["-o", out] + \
               [os.path.join(HERE, s) for s in SOURCES]
         jobs.append((cmd, logname, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

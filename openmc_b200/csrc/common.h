@@ -209,7 +209,18 @@ struct GenCtx {
   // {id, x, y, z, u, v, w, E} (what Particle::mark_as_lost reports, src/particle.cpp:762-785)
   double* lost_rec;
   int32_t lost_cap;
+  // Secondary neutrons of reactions with an integer yield >= 2, e.g. (n,2n) (Particle::create_secondary
+  // src/particle.cpp:75-93, inelastic_scatter src/physics.cpp:1158-1162, event_revive_from_secondary
+  // src/particle.cpp:417-473): a pool of sites {x, y, z, u, v, w, E, wgt, time} handed out by an atomic
+  // counter, and one LIFO list per particle through sec_next.  Null when no reaction of the model can
+  // create them: the kernels then carry one uniform branch.
+  double* sec_site;
+  int32_t* sec_next;
+  int32_t* sec_head;  // [particles of the generation] first site of the particle's list, -1 = none
+  int32_t* sec_count; // [0] sites handed out  [1] sites that did not fit
+  int32_t sec_cap;
 };
+constexpr int SEC_ND = 9;
 enum { AN_RX, AN_RY, AN_RZ, AN_E_LAST, AN_WGT_LAST, AN_WGT_BANK, AN_MICRO_T, AN_MICRO_A, AN_MICRO_F, AN_MICRO_NF,
   AN_XS_T, AN_XS_A, AN_XS_F, AN_XS_NF, AN_ND };
 enum { AN_SCATTER, AN_FISSION, AN_ALIVE, AN_G_LAST, AN_G_POST, AN_MATERIAL, AN_MG_BA, AN_NI };

@@ -550,12 +550,18 @@ struct LatIdx {
 
 // ---- hexagonal lattices, src/lattice.cpp:727-1007: rare, out of line; lat_shape = (2 n_rings - 1,
 // 2 n_rings - 1, n_axial), lat_pitch = (radial, axial), lat_lower_left = the centre ----------------
-// Compiled in only with -DOMC_HEX_LATTICES=1 (libomcgpu_hex.so; the loaders pick it for models with
-// hexagonal lattices): the dispatch in the lattice functions cost every event kernel 2-4 % in
+// Compiled in only with -DOMC_EXTENDED=1 (libomcgpu_ext.so; the loaders pick it for models with
+// hexagonal lattices or secondary neutrons): the dispatch in the lattice functions cost every event kernel 2-4 % in
 // registers and spills even for models without a lattice (profiles/r68-r69), so the default
 // build does not carry it and omcgpu_init refuses such models there, naming the other build.
+#ifndef OMC_EXTENDED
+#define OMC_EXTENDED 0 /* 1: libomcgpu_ext.so, the build with the rarely needed features compiled in */
+#endif
 #ifndef OMC_HEX_LATTICES
-#define OMC_HEX_LATTICES 0
+#define OMC_HEX_LATTICES OMC_EXTENDED
+#endif
+#ifndef OMC_SECONDARIES
+#define OMC_SECONDARIES OMC_EXTENDED /* secondary neutrons of integer yields: create_secondary / ev_revive */
 #endif
 OMC_HD bool lat_is_hex(int l)
 {
@@ -2084,6 +2090,32 @@ OMC_HD void an_puti(const GenCtx& gc, int64_t idx, int k, int32_t v)
   gc.an_i[k * gc.an_cap + idx] = v;
 }
 
+// Particle::create_secondary, src/particle.cpp:75-93: the neutron as it leaves the reaction, put on
+// the particle's list; it is transported when the particle itself is dead (ev_revive)
+OMC_HD void create_secondary(const Collider& p, const GenCtx& gc)
+{
+  if (p.E < DM.energy_cutoff)
+    return;
+  const int32_t slot = atomic_add_i32(gc.sec_count, 1);
+  if (slot >= gc.sec_cap) { // the host fails the generation: nothing is dropped silently
+    atomic_add_i32(gc.sec_count + 1, 1);
+    return;
+  }
+  double* s = gc.sec_site + (int64_t)slot * SEC_ND;
+  s[0] = p.r.x;
+  s[1] = p.r.y;
+  s[2] = p.r.z;
+  s[3] = p.u.x;
+  s[4] = p.u.y;
+  s[5] = p.u.z;
+  s[6] = p.E;
+  s[7] = p.wgt;
+  s[8] = p.time;
+  const int64_t idx = an_index(p, gc);
+  gc.sec_next[slot] = gc.sec_head[idx];
+  gc.sec_head[idx] = slot;
+}
+
 OMC_HD void collision_mg(Collider& p, int ba, const GenCtx& gc, const Bank& fb)
 {
   const int G = DM.mg_n_groups;
@@ -2324,8 +2356,16 @@ OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no
     p.E = E;
     p.u = rotate_angle(p.u, mu, p.seed);
     const double yield = eval_function(ld(DM.prod_yield_fn + prod), E_in);
-    if (!(floor(yield) == yield && yield > 0))
+    if (floor(yield) == yield && yield > 0) {
+      // an integral yield creates exactly yield - 1 secondary neutrons (src/physics.cpp:1158-1162)
+#if OMC_SECONDARIES
+      if (gc.sec_site != nullptr)
+        for (int k = 0; k < (int)round(yield) - 1; ++k)
+          create_secondary(p, gc);
+#endif
+    } else {
       p.wgt *= yield;
+    }
   }
   if (DM.survival_biasing && p.wgt < DM.weight_cutoff)
     russian_roulette(p, DM.weight_survive);

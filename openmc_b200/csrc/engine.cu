@@ -316,6 +316,8 @@ OMC_D bool ev_init(const PState& ps, const GenCtx& gc, const Bank& src, int64_t 
   }
   ps.n_progeny[i] = 0;
   ps.n_event[i] = 0;
+  if (gc.sec_head != nullptr)
+    gc.sec_head[ps.id_shift + i] = -1;
   ps.k_abs[i] = 0.0;
   ps.k_col[i] = 0.0;
   ps.k_trk[i] = 0.0;
@@ -538,14 +540,53 @@ OMC_D int ev_advance(const PState& ps, const GenCtx& gc, const Flights& fl, int6
   return (d_coll > b.distance) ? NEXT_SURFACE : NEXT_COLLISION;
 }
 
-// Particle::event_revive_from_secondary, src/particle.cpp:417-425 (no secondaries)
-OMC_D bool ev_revive(const PState& ps, int64_t i)
+// Particle::event_revive_from_secondary, src/particle.cpp:417-473: a dead particle with secondary
+// neutrons on its list becomes the last one created (Particle::from_source on the site: the random
+// number streams, the id, the progeny counter and the k accumulators carry on)
+OMC_D bool ev_revive(const PState& ps, const GenCtx& gc, int64_t i)
 {
   const int n_event = ps.n_event[i] + 1;
   ps.n_event[i] = n_event;
   if (n_event == DM.max_particle_events)
     ps.wgt[i] = 0.0;
-  return ps.wgt[i] != 0.0;
+  if (ps.wgt[i] != 0.0)
+    return true;
+#if !OMC_SECONDARIES
+  (void)gc;
+  return false;
+#else
+  if (gc.sec_site == nullptr) // uniform: no reaction of the model creates secondaries
+    return false;
+  const int64_t idx = ps.id_shift + i;
+  for (;;) {
+    const int32_t slot = gc.sec_head[idx];
+    if (slot < 0)
+      return false;
+    gc.sec_head[idx] = gc.sec_next[slot];
+    atomic_add_u64(gc.counters, (unsigned long long)ps.n_event[i]); // the dead particle's events (counters[0])
+    const double* s = gc.sec_site + (int64_t)slot * SEC_ND;
+    const int L = DM.n_coord_levels < OMCGPU_MAX_COORD ? DM.n_coord_levels : OMCGPU_MAX_COORD;
+    for (int l = 0; l < L; ++l)
+      reset_level(ps, i, l);
+    set_r(ps, i, 0, v3(s[0], s[1], s[2]));
+    set_u(ps, i, 0, v3(s[3], s[4], s[5]));
+    ps.n_coord[i] = 1;
+    ps.surface[i] = SURFACE_NONE;
+    ps.material[i] = C_NONE;
+    ps.material_last[i] = C_NONE;
+    ps.cell_instance[i] = 0;
+    ps.E[i] = s[6];
+    ps.g[i] = 0;
+    ps.wgt[i] = s[7];
+    ps.time[i] = s[8];
+    ps.n_event[i] = 0;
+    if (find_cell_from_root(ps, i, SURFACE_NONE)) {
+      ps.cell_last0[i] = LV(cell, 0);
+      return true;
+    }
+    mark_lost(ps, gc, i); // event_calculate_xs could not locate it: the next secondary, if any
+  }
+#endif
 }
 
 // Rare boundary conditions, out of line so that the crossing kernel does not carry them.  They take
@@ -713,7 +754,7 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
       }
     }
   }
-  return ev_revive(ps, i);
+  return ev_revive(ps, gc, i);
 }
 
 // the replica of the tally VALUE arrays this block adds into (see k_score)
@@ -839,7 +880,7 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
   ps.material_last[i] = C_NONE;
   if (SCORE && record)
     score_after_collision(ps, i, n_coord, gc, ridx, score_values(gc));
-  return ev_revive(ps, i);
+  return ev_revive(ps, gc, i);
 }
 
 // The particle columns a list kernel receives are the GLOBAL ones (EvArgs::ps.is_local == 0; the tail
@@ -2181,6 +2222,11 @@ struct Engine {
   int n_collision_tallies = 0;       // tallies scored before the collision (collision estimator)
   int n_after_collision_tallies = 0; // ... after it, from the collision records (analog estimator)
   double* d_lost_rec = nullptr;      // state of the first lost particles of the generation (mark_lost)
+  double* d_sec_site = nullptr;      // secondary-neutron pool (GenCtx::sec_*), allocated when the model can create them
+  int32_t* d_sec_next = nullptr;
+  int32_t* d_sec_head = nullptr;
+  int32_t* d_sec_count = nullptr;
+  int32_t sec_cap = 0;
   int64_t n_lost_last = 0;           // lost particles of the last generation
   double* d_an_d = nullptr;          // collision records, AN_ND / AN_NI columns of `cap` entries
   int32_t* d_an_i = nullptr;
@@ -2781,6 +2827,51 @@ static int upload_model(const omcgpu_model* m)
   return 0;
 }
 
+// inelastic_scatter creates yield - 1 secondary neutrons when a product's yield is an integer >= 2,
+// e.g. (n,2n) (src/physics.cpp:1158-1162): can a yield function of the model take such a value on
+// an interval?  (a constant, or a flat piece / flat extrapolation of a tabulated function)
+static bool model_creates_secondaries(const omcgpu_model* m)
+{
+  if (!m->run_CE)
+    return false;
+  for (int r = 0; r < m->n_reactions; ++r) {
+    if (!m->rx_inelastic[r] || m->rx_prod_ofs[r + 1] <= m->rx_prod_ofs[r])
+      continue;
+    const int fn = m->prod_yield_fn[m->rx_prod_ofs[r]];
+    if (fn < 0 || fn >= m->n_functions)
+      continue;
+    const double* d = m->fn_data + m->fn_ofs[fn];
+    const int n = m->fn_ofs[fn + 1] - m->fn_ofs[fn];
+    auto integral = [](double y) { return y >= 2.0 && std::floor(y) == y; };
+    if (m->fn_type[fn] == OMCGPU_FN_POLYNOMIAL) {
+      bool constant = true;
+      for (int k = 1; k < n; ++k)
+        constant = constant && d[k] == 0.0;
+      if (n >= 1 && (!constant || integral(d[0])))
+        return true; // (a non-constant polynomial may cross an integer: keep the pool)
+    } else {
+      const int np = n / 2;
+      const double* y = d + np;
+      for (int k = 0; k < np; ++k)
+        if (integral(y[k]))
+          return true;
+    }
+  }
+  return false;
+}
+
+} // namespace omc (the C entry point below is used by check_supported)
+extern "C" int omcgpu_needs_extended_build(const omcgpu_model* m)
+{
+  if (!m)
+    return 0;
+  for (int l = 0; l < m->n_lattices; ++l)
+    if (m->lat_type && m->lat_type[l] != OMCGPU_LATTICE_RECT)
+      return 1;
+  return omc::model_creates_secondaries(m) ? 1 : 0;
+}
+namespace omc {
+
 static int check_supported(const omcgpu_model* m)
 {
   if (m->n_coord_levels > OMCGPU_MAX_COORD)
@@ -2798,12 +2889,10 @@ static int check_supported(const omcgpu_model* m)
   if (!m->run_CE && has_density_multipliers(m))
     return fail(OMCGPU_E_UNSUPPORTED, "cell density multipliers (src/cell.cpp:104-120) in a multigroup model are not "
                                       "supported on the device (continuous-energy models: resolved at omcgpu_init)%s");
-#if !OMC_HEX_LATTICES
-  for (int l = 0; l < m->n_lattices; ++l)
-    if (m->lat_type[l] != OMCGPU_LATTICE_RECT)
-      return fail(OMCGPU_E_UNSUPPORTED, "hexagonal lattices (src/lattice.cpp:458-1009) are compiled into libomcgpu_hex.so "
-                                        "(-DOMC_HEX_LATTICES=1), not into this build: load that library%s");
-#endif
+  if (omcgpu_needs_extended_build(m) && !OMC_EXTENDED)
+    return fail(OMCGPU_E_UNSUPPORTED, "hexagonal lattices (src/lattice.cpp:458-1009) and secondary neutrons of integer "
+                                      "yields (src/physics.cpp:1158-1162) are compiled into libomcgpu_ext.so "
+                                      "(-DOMC_EXTENDED=1), not into this build: load that library%s");
   for (int t = 0; t < m->n_tallies; ++t) {
     if (m->tally_n_filters[t] > OMCGPU_MAX_FILTERS || m->tally_n_scores[t] > OMCGPU_MAX_SCORES)
       return fail(OMCGPU_E_UNSUPPORTED, "tally has too many filters or scores%s");
@@ -2821,38 +2910,6 @@ static int check_supported(const omcgpu_model* m)
     for (int p = 0; p < m->n_products; ++p)
       if (m->prod_elaw[p] < 0 || m->prod_elaw[p] > OMCGPU_ELAW_WATT)
         return fail(OMCGPU_E_UNSUPPORTED, "secondary energy law not supported on the device%s");
-    // inelastic_scatter creates yield - 1 secondary neutrons when a product's yield is an integer
-    // >= 2, e.g. (n,2n) (src/physics.cpp:1158-1162); the device keeps no secondary bank, so a
-    // yield function with a flat piece at such a value is refused instead of silently
-    // transporting one neutron of unchanged weight
-    for (int r = 0; r < m->n_reactions; ++r) {
-      if (!m->rx_inelastic[r] || m->rx_prod_ofs[r + 1] <= m->rx_prod_ofs[r])
-        continue;
-      const int fn = m->prod_yield_fn[m->rx_prod_ofs[r]];
-      if (fn < 0 || fn >= m->n_functions)
-        return fail(OMCGPU_E_DATA, "reaction product without a yield function%s");
-      const double* d = m->fn_data + m->fn_ofs[fn];
-      const int n = m->fn_ofs[fn + 1] - m->fn_ofs[fn];
-      auto creates_secondaries = [](double y) { return y >= 2.0 && std::floor(y) == y; };
-      bool bad = false;
-      if (m->fn_type[fn] == OMCGPU_FN_POLYNOMIAL) {
-        bool constant = true;
-        for (int k = 1; k < n; ++k)
-          constant = constant && d[k] == 0.0;
-        bad = n >= 1 && constant && creates_secondaries(d[0]);
-      } else {
-        const int np = n / 2;
-        const double* y = d + np;
-        bad = np == 1 && creates_secondaries(y[0]);
-        for (int k = 0; k + 1 < np; ++k)
-          bad = bad || (y[k] == y[k + 1] && creates_secondaries(y[k]));
-        bad = bad || (np >= 1 && (creates_secondaries(y[0]) || creates_secondaries(y[np - 1]))); // flat extrapolation
-      }
-      if (bad)
-        return fail(OMCGPU_E_UNSUPPORTED,
-          "a scattering reaction has an integer neutron yield >= 2 (secondary neutrons, src/physics.cpp:1158): "
-          "not supported on the device%s");
-    }
   }
   return 0;
 }
@@ -2889,6 +2946,11 @@ static EvArgs make_args(const omcgpu_gen_in* in)
   a.gc.an_cap = G.cap;
   a.gc.lost_rec = G.d_lost_rec;
   a.gc.lost_cap = OMCGPU_MAX_LOST_RECORDS;
+  a.gc.sec_site = G.d_sec_site;
+  a.gc.sec_next = G.d_sec_next;
+  a.gc.sec_head = G.d_sec_head;
+  a.gc.sec_count = G.d_sec_count;
+  a.gc.sec_cap = G.sec_cap;
   a.fl = G.fl[0];
   a.fl_buf = 0;
   a.first_event = NEXT_NONE;
@@ -3476,6 +3538,8 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
   std::memset(out, 0, sizeof(*out));
   CUDA_OK(cudaMemsetAsync(G.d_counts, 0, N_COUNTS * sizeof(int32_t), G.stream));
   CUDA_OK(cudaMemsetAsync(G.d_counters, 0, N_COUNTERS * sizeof(unsigned long long), G.stream));
+  if (G.d_sec_count)
+    CUDA_OK(cudaMemsetAsync(G.d_sec_count, 0, 2 * sizeof(int32_t), G.stream));
   CUDA_OK(cudaEventRecord(G.ev0, G.stream));
   EvArgs a = make_args(in);
   SweepStats st;
@@ -3508,12 +3572,22 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
   for (int k = 0; k < 4; ++k)
     out->global_tally[k] = tot[k];
   out->total_weight = tot[4];
-  out->n_events = (int64_t)tot[5];
+  out->n_events = (int64_t)tot[5]; // (+ the events of particles that went on as a secondary, below)
   G.n_fis = std::min<int64_t>(G.h_counts[4], G.fis_cap);
   out->n_fission = G.n_fis;
   out->n_lost = G.h_counts[5];
   G.n_lost_last = out->n_lost;
   out->n_bank_full = G.h_counts[7];
+  if (G.d_sec_count) { // a full secondary pool is an error, not a silent loss of neutrons
+    int32_t sc[2] = {0, 0};
+#if OMC_CUDA
+    CUDA_OK(cudaMemcpy(sc, G.d_sec_count, sizeof(sc), cudaMemcpyDeviceToHost));
+#else
+    std::memcpy(sc, G.d_sec_count, sizeof(sc));
+#endif
+    if (sc[1] > 0)
+      return fail(OMCGPU_E_OUT_OF_BOUNDS, "the secondary-neutron pool is full (set OMCGPU_SECONDARY_POOL to a larger number of sites)%s");
+  }
   drain_score_times(st, st.score_issued); // the stream sync above covers every scoring launch
   out->ms_surface = st.ms_kernel[0];
   out->ms_collide = st.ms_kernel[1];
@@ -3528,6 +3602,7 @@ static int run_generation(const omcgpu_gen_in* in, omcgpu_gen_out* out)
   out->n_red = (int64_t)G.h_counters[CNT_RED];
   out->n_items_surface = st.n_cross;
   out->n_items_collide = st.n_coll;
+  out->n_events += (int64_t)G.h_counters[0];
   out->n_xs_lookups = n_xs + (int64_t)G.h_counters[1];
   out->n_collisions = n_coll + (int64_t)G.h_counters[2];
   out->n_crossings = n_cross + (int64_t)G.h_counters[3];
@@ -3976,6 +4051,18 @@ static int init_impl(const omcgpu_model* model, int device, int64_t max_particle
   }
   rc = rc ? rc : dev_alloc(&G.d_tally, (size_t)G.tally_stride * G.tally_replicas);
   rc = rc ? rc : dev_alloc(&G.d_lost_rec, (size_t)OMCGPU_MAX_LOST_RECORDS * OMCGPU_LOST_RECORD);
+  G.d_sec_site = nullptr;
+  G.d_sec_next = G.d_sec_head = G.d_sec_count = nullptr;
+  G.sec_cap = 0;
+  if (model_creates_secondaries(model)) {
+    G.sec_cap = (int32_t)std::min<int64_t>(std::max<int64_t>(1 << 16, cap / 2), 1 << 30);
+    if (const char* t = std::getenv("OMCGPU_SECONDARY_POOL"))
+      G.sec_cap = std::max(1, std::atoi(t));
+    rc = rc ? rc : dev_alloc(&G.d_sec_site, (size_t)G.sec_cap * SEC_ND);
+    rc = rc ? rc : dev_alloc(&G.d_sec_next, (size_t)G.sec_cap);
+    rc = rc ? rc : dev_alloc(&G.d_sec_head, (size_t)cap);
+    rc = rc ? rc : dev_alloc(&G.d_sec_count, 2);
+  }
   G.d_an_d = nullptr;
   G.d_an_i = nullptr;
   if (G.n_after_collision_tallies > 0) { // collision records for the tallies scored after a collision
@@ -4510,6 +4597,8 @@ int omcgpu_collide(int64_t n, const int32_t* material, const double* E, const do
   const EvArgs ev = make_args(&in);
   a.ps = G.ps;
   a.gc = ev.gc;
+  a.gc.sec_site = nullptr; // the probe reports the colliding neutron only
+  a.gc.an_d = nullptr;
   a.fb = G.fis;
   a.n = n;
   a.wgt = wgt;

@@ -933,6 +933,7 @@ struct Api {
   int (*host_register)(void*, int64_t) = nullptr;
   int (*host_unregister)(void*) = nullptr;
   int64_t (*lost_particles)(double*, int64_t) = nullptr;
+  int (*needs_extended_build)(const omcgpu_model*) = nullptr;
 } api;
 bool g_ready = false;
 std::vector<double> g_values;
@@ -945,7 +946,7 @@ void bind(Fn& fn, const char* name)
     fatal_error(fmt::format("OPENMC_GPU: {} lacks the symbol {}", "libomcgpu", name));
 }
 
-bool g_hex_lattices = false; // the model has hexagonal lattices: the build that carries their code
+bool g_extended = false; // the model needs libomcgpu_ext.so (omcgpu_needs_extended_build)
 
 void load_library()
 {
@@ -958,9 +959,9 @@ void load_library()
     Dl_info info;
     if (dladdr(reinterpret_cast<void*>(&load_library), &info) && info.dli_fname) {
       path = info.dli_fname;
-      path = path.substr(0, path.find_last_of('/') + 1) + (g_hex_lattices ? "libomcgpu_hex.so" : "libomcgpu.so");
+      path = path.substr(0, path.find_last_of('/') + 1) + (g_extended ? "libomcgpu_ext.so" : "libomcgpu.so");
     } else {
-      path = g_hex_lattices ? "libomcgpu_hex.so" : "libomcgpu.so";
+      path = g_extended ? "libomcgpu_ext.so" : "libomcgpu.so";
     }
   }
   api.handle = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
@@ -974,6 +975,7 @@ void load_library()
   bind(api.host_register, "omcgpu_host_register");
   bind(api.host_unregister, "omcgpu_host_unregister");
   bind(api.lost_particles, "omcgpu_lost_particles");
+  bind(api.needs_extended_build, "omcgpu_needs_extended_build");
 }
 
 void check(int rc, const char* what)
@@ -995,15 +997,20 @@ bool enabled()
 
 void simulation_init()
 {
-  for (const auto& lat : model::lattices) // which build of the device library: see load_library
-    if (dynamic_cast<const HexLattice*>(lat.get()))
-      g_hex_lattices = true;
   load_library();
   const omcgpu_model* m;
   try {
     m = flatten_model();
   } catch (const std::runtime_error& e) {
     fatal_error(e.what());
+  }
+  // which build of the device library (include/omcgpu.h, omcgpu_needs_extended_build): the default
+  // one answers; a model with hexagonal lattices or secondary neutrons gets libomcgpu_ext.so
+  if (!std::getenv("OMCGPU_LIB") && api.needs_extended_build(m)) {
+    dlclose(api.handle);
+    api = Api {};
+    g_extended = true;
+    load_library();
   }
   int device = 0;
   if (const char* env = std::getenv("OPENMC_GPU_DEVICE"))

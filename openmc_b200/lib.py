@@ -27,9 +27,9 @@ from . import _abi as abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.environ.get("OMCGPU_LIB") or os.path.join(_HERE, "csrc", "libomcgpu.so")
-# the same sources with the hexagonal-lattice dispatch compiled in (csrc/build.py): Engine.init loads
-# it instead of the default build for models with hexagonal lattices
-HEX_LIB = os.path.join(_HERE, "csrc", "libomcgpu_hex.so")
+# the same sources with the rarely needed features compiled in (csrc/build.py: hexagonal lattices,
+# secondary neutrons): Engine.init loads it for the models omcgpu_needs_extended_build names
+EXT_LIB = os.path.join(_HERE, "csrc", "libomcgpu_ext.so")
 
 DEFAULT_SEED = 1            # include/openmc/random_lcg.h:17
 DEFAULT_STRIDE = 152917     # include/openmc/random_lcg.h:18
@@ -76,13 +76,15 @@ class Engine:
     def init(self, model: abi.ModelHandle, device: int = 0, max_particles: int = 100000):
         self.model = model
         self.max_particles = int(max_particles)
-        # the build that carries the hexagonal-lattice code, for the models that need it
-        hexagonal = int(model["n_lattices"]) > 0 and bool(np.any(np.asarray(model["lat_type"])[:int(model["n_lattices"])] != 0))
+        # the build that carries the rarely needed features, for the models that need them
         want = self._default_path
-        if hexagonal and os.path.basename(self._default_path) == "libomcgpu.so":
-            want = os.path.join(os.path.dirname(self._default_path), "libomcgpu_hex.so")
-            if not os.path.exists(want):
-                raise OmcGpuError(f"{want} not found: build it with `python -m openmc_b200.csrc.build`")
+        if os.path.basename(self._default_path) == "libomcgpu.so":
+            if self.path != self._default_path:
+                self._load(self._default_path)
+            if self.lib.omcgpu_needs_extended_build(model.byref()):
+                want = os.path.join(os.path.dirname(self._default_path), "libomcgpu_ext.so")
+                if not os.path.exists(want):
+                    raise OmcGpuError(f"{want} not found: build it with `python -m openmc_b200.csrc.build`")
         if want != self.path:
             self._load(want)
         self._check(self.lib.omcgpu_init(model.byref(), C.c_int(device), C.c_int64(max_particles)))

@@ -114,7 +114,7 @@ def _params(name, Z, A, rng):
 
 
 def synthetic_nuclide(name, Z, A, n_grid=100000, fissionable=False, inelastic=False,
-                      delayed=False, temperature=294.0) -> Nuclide:
+                      delayed=False, temperature=294.0, n2n=False) -> Nuclide:
     """Seeded synthetic nuclide: sigma(E) = smooth 1/v + sum of Lorentzian resonances."""
     rng = np.random.default_rng(1000 + Z * 1000 + A)
     awr = A * 0.99
@@ -185,6 +185,17 @@ def synthetic_nuclide(name, Z, A, n_grid=100000, fissionable=False, inelastic=Fa
         rx.append(Reaction(51, thr, xs, q, True,
                            [Product(0, Function1D("poly", [1.0]), abi.OMCGPU_ELAW_LEVEL,
                                     ((awr + 1.0) / awr * abs(q), mass_ratio))]))
+    if n2n:
+        # (n,2n): integer yield 2 -> one secondary neutron per reaction (src/physics.cpp:1158-1162),
+        # Maxwellian secondaries restricted to E_out <= E - U
+        e_thr = 2.0e6 * (1.0 + 1.0 / awr)
+        thr = int(np.searchsorted(energy, e_thr))
+        e = energy[thr:]
+        xs = 0.9 * (1.0 - np.exp(-(e - energy[thr]) / 1.5e6))
+        theta = Function1D("tab", ([E_LOW, E_HIGH], [0.35e6, 0.35e6]))
+        rx.append(Reaction(16, thr, xs, -1.9e6, False,
+                           [Product(0, Function1D("poly", [2.0]), abi.OMCGPU_ELAW_MAXWELL,
+                                    (1.9e6, 0.0), (theta, None))]))
     rx.append(Reaction(102, 0, capture, 5.0e6, False, []))
     rx.sort(key=lambda r: r.mt)   # HDF5 group-name order: reaction_002, _018, _051, _102
     return Nuclide(name, Z, A, awr, temperature * K_BOLTZMANN, energy, rx, total_nu)

@@ -221,6 +221,7 @@ struct Particle {
   int n_progeny {0};
   int64_t n_event {0};
   int n_collision {0};
+  std::vector<omcgpu_site> secondary_bank; // Particle::create_secondary, src/particle.cpp:75-93
   bool fission {false};
   // what the analog estimator reads after a collision (src/tallies/tally_scoring.cpp:1116-1330, 1622-1990)
   bool event_scatter {false};  // p.event() == TallyEvent::SCATTER
@@ -1737,7 +1738,24 @@ void ce_inelastic_scatter(int i_nuclide, int rx, Particle& p)
   p.u() = rotate_angle(p.u(), mu, nullptr, p.current_seed());
   double yield = eval_function(M->prod_yield_fn[prod], E_in);
   if (std::floor(yield) == yield && yield > 0) {
-    // integral yields would create secondaries: the synthetic libraries use 1
+    // an integral yield creates exactly yield - 1 secondary neutrons (:1158-1162)
+    for (int i = 0; i < static_cast<int>(std::round(yield)) - 1; ++i) {
+      if (p.E < M->energy_cutoff) // create_secondary, src/particle.cpp:78-82
+        continue;
+      omcgpu_site site;
+      std::memset(&site, 0, sizeof(site));
+      site.r[0] = p.r().x;
+      site.r[1] = p.r().y;
+      site.r[2] = p.r().z;
+      site.u[0] = p.u().x;
+      site.u[1] = p.u().y;
+      site.u[2] = p.u().z;
+      site.E = p.E;
+      site.wgt = p.wgt;
+      site.time = p.time;
+      site.surf_id = SURFACE_NONE;
+      p.secondary_bank.push_back(site);
+    }
   } else {
     p.wgt *= yield;
   }
@@ -2498,11 +2516,17 @@ void event_collide(Particle& p)
 }
 
 void event_revive(Particle& p)
-{
+{ // Particle::event_revive_from_secondary, src/particle.cpp:417-473
   ++p.n_event;
   RS.n_events++;
   if (p.n_event == M->max_particle_events)
     p.wgt = 0.0;
+  if (!p.alive() && !p.secondary_bank.empty()) {
+    const omcgpu_site site = p.secondary_bank.back();
+    p.secondary_bank.pop_back();
+    from_source(p, &site); // the random-number streams, the id and the k accumulators carry on
+    p.n_event = 0;
+  }
 }
 
 void event_death(Particle& p)

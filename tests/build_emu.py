@@ -23,7 +23,7 @@ def build(force=False):
     deps.append(os.path.join(ROOT, "include", "omcgpu.h"))
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) < os.path.getmtime(LIB) for d in deps):
         return LIB
-    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DOMC_EMU", "-DOMC_HEX_LATTICES=1", "-ffp-contract=off",
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DOMC_EMU", "-DOMC_EXTENDED=1", "-ffp-contract=off",
            "-fno-fast-math", "-x", "c++", os.path.join(CSRC, "engine.cu"), "-o", LIB]
     subprocess.check_call(cmd)
     return LIB

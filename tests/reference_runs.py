@@ -34,6 +34,7 @@ RUNS = {
     "hex_bundle_x3d": (1000, 6, 2),        # orientation x, two axial levels
     "pincell_ce_density": (1000, 8, 3),    # cell densities (density multipliers) on the fuel rings and the moderator
     "assembly_ce_density": (1000, 6, 2),   # one density per INSTANCE of the fuel cell (distribcell offsets)
+    "pincell_ce_n2n": (1000, 8, 3),        # (n,2n) reactions: secondary neutrons from integer yields
 }
 _CACHE = {}
 
@@ -81,6 +82,10 @@ def build(name):
                          and any(n == "U235" for n, _ in c.fill.components))
         n_inst = 17 * 17 - 25
         fuel_cell.density = list(10.0 + 0.4 * np.cos(0.37 * np.arange(n_inst)))
+        ce = True
+    elif name == "pincell_ce_n2n":
+        library = nuclide.synthetic_library(nuclide.PINCELL_NUCLIDES, 3000, n2n=True)
+        m, lib, box, of = examples.pincell_ce(n_grid=3000, mesh_dim=6, energy_bins=12, tallies=True, library=library)
         ce = True
     elif name == "hex_bundle_y":
         m, lib, box, of = examples.hex_bundle("y")

@@ -99,10 +99,12 @@ def test_host_bank_is_authoritative_between_generations(emu_lib):
     eng.finalize()
 
 
-def test_integer_yield_secondaries_are_refused(emu_lib):
+def test_integer_yield_secondaries_need_the_extended_build(emu_lib):
     """an inelastic product whose yield is an integer >= 2 makes the reference bank yield - 1
-    secondary neutrons (src/physics.cpp:1158-1162); the device has no secondary bank and must
-    refuse the model instead of transporting one neutron of unchanged weight"""
+    secondary neutrons (src/physics.cpp:1158-1162).  The device transports them in the extended
+    build (libomcgpu_ext.so; the host-compiled engine of this tier is that build):
+    omcgpu_needs_extended_build names such a model, a non-integer yield only scales the weight"""
+    import ctypes as C
     model, box, of, _ = cases.build_ce()
     rx = int(np.flatnonzero(np.asarray(model["rx_inelastic"]))[0])
     fn = int(model["prod_yield_fn"][int(model["rx_prod_ofs"][rx])])
@@ -111,11 +113,13 @@ def test_integer_yield_secondaries_are_refused(emu_lib):
     keep = float(model["fn_data"][o0])
     eng = lib.Engine(emu_lib)
     try:
+        assert eng.lib.omcgpu_needs_extended_build(model.byref()) == 0
         model["fn_data"][o0] = 2.0
-        with pytest.raises(lib.OmcGpuError) as e:
-            eng.init(model, 0, 100)
-        assert _code(e) == abi.OMCGPU_E_UNSUPPORTED and "yield" in str(e.value)
-        model["fn_data"][o0] = 1.5          # a non-integer yield only scales the weight: accepted
+        assert eng.lib.omcgpu_needs_extended_build(model.byref()) == 1
+        eng.init(model, 0, 100)             # the extended build takes it
+        eng.finalize()
+        model["fn_data"][o0] = 1.5          # a non-integer yield only scales the weight
+        assert eng.lib.omcgpu_needs_extended_build(model.byref()) == 0
         eng.init(model, 0, 100)
         eng.finalize()
     finally:

@@ -186,3 +186,38 @@ def test_density_multipliers_of_a_multigroup_model_are_refused(emu_lib):
 def test_cell_density_multipliers_on_gpu(gpu_engine, name, monkeypatch):
     monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", "2048")
     _check_generation(gpu_engine, lambda: _analog_case(name), 20000, None, exact_bank=False)
+
+
+@pytest.mark.parametrize("sweep", ["1", "2"])
+@pytest.mark.parametrize("threshold", ["0", "100000"])
+def test_secondary_neutrons_from_integer_yields(emu_lib, threshold, sweep, monkeypatch):
+    """(n,2n) in every nuclide of the pin cell: inelastic_scatter creates yield - 1 secondary
+    neutrons (src/physics.cpp:1158-1162), event_revive_from_secondary transports them after the
+    particle's death (src/particle.cpp:417-473) -- pool of sites + one list per particle on the
+    device; the oracle equals the reference's binary bit for bit on this model"""
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)
+    monkeypatch.setenv("OMCGPU_SWEEP", sweep)
+    _check_generation(lib.Engine(emu_lib), lambda: _analog_case("pincell_ce_n2n"), 1500, 1e-11)
+
+
+def test_secondaries_change_the_answer_and_a_full_pool_is_an_error(emu_lib, monkeypatch):
+    """the same generation with the pool squeezed to 2 sites fails loudly (nothing is dropped
+    silently); and the (n,2n) reactions do happen in this model: hundreds of extra events"""
+    import reference_runs as rr
+    m, libx, model, box, of, ce = rr.build("pincell_ce_n2n")
+    o = Oracle(model)
+    n = 1500
+    src = o.sample_initial_source(n, box, of)
+    eng = lib.Engine(emu_lib)
+    monkeypatch.setenv("OMCGPU_SECONDARY_POOL", "2")
+    eng.init(model, 0, n)
+    gi = eng.gen_in(n, 0, 0, 1.0, False)
+    with pytest.raises(lib.OmcGpuError, match="secondary-neutron pool is full"):
+        eng.transport_generation(gi, src)
+    eng.finalize()
+
+
+@pytest.mark.gpu
+def test_secondary_neutrons_on_gpu(gpu_engine, monkeypatch):
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", "2048")
+    _check_generation(gpu_engine, lambda: _analog_case("pincell_ce_n2n"), 20000, None, exact_bank=False)

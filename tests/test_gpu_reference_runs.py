@@ -28,6 +28,7 @@ MG = ["pincell_mg", "c5g7_core", "surface_zoo", "rotated_fills", "periodic_box",
       "hex_bundle_y", "hex_bundle_x3d"]                           # hexagonal lattices
 CE = ["pincell_ce", "pincell_ce_temperatures", "assembly_ce", "pwr_core_ce", "pincell_ce_analog", "pincell_ce_analog_survival",
       "pincell_ce_density", "assembly_ce_density",                # cell density multipliers
+      "pincell_ce_n2n",                                           # secondary neutrons from (n,2n)
       # multigroup, but a last-ulp difference of CUDA's log() flips a history within five generations
       # (curved reflective boundary + rotated re-entry): the first four generations agree to 1e-6
       "rotational_wedge"]
