@@ -500,8 +500,9 @@ int64_t omcgpu_lost_particles(double* records, int64_t capacity);
 
 /* The device library comes in two builds of the same sources (openmc_b200/csrc/build.py):
  * libomcgpu.so, and libomcgpu_ext.so with the rarely needed features compiled in -- hexagonal
- * lattices (src/lattice.cpp:458-1009) and secondary neutrons of reactions with an integer yield
- * (src/physics.cpp:1158-1162, src/particle.cpp:417-473).  Compiled into every kernel, their
+ * lattices (src/lattice.cpp:458-1009), axis cones and general quadrics, white and rotational
+ * periodic boundaries, analog-estimator tallies, and secondary neutrons of reactions with an
+ * integer yield (src/physics.cpp:1158-1162, src/particle.cpp:417-473).  Compiled into every kernel, their
  * dispatch costs 2-4 % even on models that use neither (profiles/r68-r70, r75), so the caller
  * asks, before omcgpu_init, which build the model needs: 1 = libomcgpu_ext.so.  omcgpu_init of
  * the other build refuses such a model by name.  Pure host code: no device is needed. */

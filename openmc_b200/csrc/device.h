@@ -11,6 +11,26 @@
 #include <cstddef>
 #include <cstring>
 
+// ---- what the extended build (libomcgpu_ext.so, -DOMC_EXTENDED=1) carries and the default build does not:
+// omcgpu_needs_extended_build (engine.cu) names the models that need it, omcgpu_init of the default build
+// refuses them (every one of these features costs the event kernels registers / spills / instruction
+// cache even when no particle ever takes the branch: profiles/r58, r66, r68-r70, r75)
+#ifndef OMC_EXTENDED
+#define OMC_EXTENDED 0 /* 1: libomcgpu_ext.so, the build with the rarely needed features compiled in */
+#endif
+#ifndef OMC_HEX_LATTICES
+#define OMC_HEX_LATTICES OMC_EXTENDED
+#endif
+#ifndef OMC_SECONDARIES
+#define OMC_SECONDARIES OMC_EXTENDED /* secondary neutrons of integer yields: create_secondary / ev_revive */
+#endif
+#ifndef OMC_RARE_SURFACES
+#define OMC_RARE_SURFACES OMC_EXTENDED /* axis cones, general quadrics; white and rotational periodic boundaries */
+#endif
+#ifndef OMC_AFTER_COLLISION_TALLIES
+#define OMC_AFTER_COLLISION_TALLIES OMC_EXTENDED /* analog estimator: collision records */
+#endif
+
 namespace omc {
 
 #if OMC_CUDA
@@ -275,6 +295,7 @@ OMC_HD double surf_evaluate(int s, V3 r)
     const double x = r.x - c0, y = r.y - c1, z = r.z - c2;
     return x * x + y * y + z * z - c3 * c3;
   }
+#if OMC_RARE_SURFACES
   case OMCGPU_SURF_XCONE: { // axis_aligned_cone_evaluate, src/surface.cpp:688-696
     const double r1 = r.x - c0, r2 = r.y - c1, r3 = r.z - c2;
     return r2 * r2 + r3 * r3 - c3 * r1 * r1;
@@ -283,14 +304,16 @@ OMC_HD double surf_evaluate(int s, V3 r)
     const double r1 = r.y - c1, r2 = r.x - c0, r3 = r.z - c2;
     return r2 * r2 + r3 * r3 - c3 * r1 * r1;
   }
-#ifndef OMC_NO_QUADRIC /* measurement build */
   case OMCGPU_SURF_QUADRIC:
     return general_quadric_evaluate(c, r);
-#endif
   default: { // z-cone
     const double r1 = r.z - c2, r2 = r.x - c0, r3 = r.y - c1;
     return r2 * r2 + r3 * r3 - c3 * r1 * r1;
   }
+#else
+  default: // (cones and quadrics: extended build; omcgpu_init refuses them here)
+    return 0.0;
+#endif
   }
 }
 
@@ -314,16 +337,19 @@ OMC_HD V3 surf_normal(int s, V3 r)
     return v3(2.0 * (r.x - gld(c)), 2.0 * (r.y - gld(c + 1)), 0.0);
   case OMCGPU_SURF_SPHERE:
     return v3(2.0 * (r.x - gld(c)), 2.0 * (r.y - gld(c + 1)), 2.0 * (r.z - gld(c + 2)));
+#if OMC_RARE_SURFACES
   case OMCGPU_SURF_XCONE: // axis_aligned_cone_normal, src/surface.cpp:747-756
     return v3(-2.0 * gld(c + 3) * (r.x - gld(c)), 2.0 * (r.y - gld(c + 1)), 2.0 * (r.z - gld(c + 2)));
   case OMCGPU_SURF_YCONE:
     return v3(2.0 * (r.x - gld(c)), -2.0 * gld(c + 3) * (r.y - gld(c + 1)), 2.0 * (r.z - gld(c + 2)));
-#ifndef OMC_NO_QUADRIC /* measurement build */
   case OMCGPU_SURF_QUADRIC:
     return general_quadric_normal(c, r);
-#endif
   default:
     return v3(2.0 * (r.x - gld(c)), 2.0 * (r.y - gld(c + 1)), -2.0 * gld(c + 3) * (r.z - gld(c + 2)));
+#else
+  default:
+    return v3(0., 0., 1.);
+#endif
   }
 }
 
@@ -436,16 +462,19 @@ OMC_HD double surf_distance(int s, V3 r, V3 u, bool coincident)
     const double cc = x * x + y * y + z * z - c3 * c3;
     return quadric_distance<false>(1.0, k, cc, coincident);
   }
+#if OMC_RARE_SURFACES
   case OMCGPU_SURF_XCONE:
     return cone_distance(r.x - c0, r.y - c1, r.z - c2, u.x, u.y, u.z, c3, coincident);
   case OMCGPU_SURF_YCONE:
     return cone_distance(r.y - c1, r.x - c0, r.z - c2, u.y, u.x, u.z, c3, coincident);
-#ifndef OMC_NO_QUADRIC /* measurement build */
   case OMCGPU_SURF_QUADRIC:
     return general_quadric_distance(c, r, u, coincident);
-#endif
   default:
     return cone_distance(r.z - c2, r.x - c0, r.y - c1, u.z, u.x, u.y, c3, coincident);
+#else
+  default:
+    return INFTY;
+#endif
   }
 }
 
@@ -554,15 +583,7 @@ struct LatIdx {
 // hexagonal lattices or secondary neutrons): the dispatch in the lattice functions cost every event kernel 2-4 % in
 // registers and spills even for models without a lattice (profiles/r68-r69), so the default
 // build does not carry it and omcgpu_init refuses such models there, naming the other build.
-#ifndef OMC_EXTENDED
-#define OMC_EXTENDED 0 /* 1: libomcgpu_ext.so, the build with the rarely needed features compiled in */
-#endif
-#ifndef OMC_HEX_LATTICES
-#define OMC_HEX_LATTICES OMC_EXTENDED
-#endif
-#ifndef OMC_SECONDARIES
-#define OMC_SECONDARIES OMC_EXTENDED /* secondary neutrons of integer yields: create_secondary / ev_revive */
-#endif
+
 OMC_HD bool lat_is_hex(int l)
 {
 #if OMC_HEX_LATTICES
@@ -2079,7 +2100,12 @@ OMC_HD int64_t an_index(const Collider& p, const GenCtx& gc)
 }
 OMC_HD bool an_on(const GenCtx& gc) // records are written only while tallies are active
 {
+#if OMC_AFTER_COLLISION_TALLIES
   return gc.an_d != nullptr && gc.tallies_active;
+#else
+  (void)gc;
+  return false;
+#endif
 }
 OMC_HD void an_put(const GenCtx& gc, int64_t idx, int k, double v)
 {

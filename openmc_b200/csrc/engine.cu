@@ -698,11 +698,13 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
           LV(ry, 0) += gld(t + 1);
           LV(rz, 0) += gld(t + 2);
         } else {
+#if OMC_RARE_SURFACES
           const PosDir o = rotate_periodic(get_r(ps, i, 0), get_u(ps, i, 0), s, axis);
           LV(rx, 0) = o.r.x;
           LV(ry, 0) = o.r.y;
           LV(rz, 0) = o.r.z;
           set_u(ps, i, 0, o.u);
+#endif
         }
         const int partner = gld(DM.surf_periodic + s) + 1;
         // translational: same side of the partner; rotational: the other side (both normals of a
@@ -716,11 +718,14 @@ OMC_D bool ev_surface(const PState& ps, const GenCtx& gc, int64_t i)
       if (n_coord != 1) {
         mark_lost(ps, gc, i);
       } else {
+#if OMC_RARE_SURFACES
         if (bc == OMCGPU_BC_WHITE) {
           const DirSeed o = white_reflect(get_r(ps, i, 0), get_u(ps, i, 0), ps.seed[i], s);
           ps.seed[i] = o.seed;
           set_u(ps, i, 0, o.u);
-        } else {
+        } else
+#endif
+        {
           const V3 r = get_r(ps, i, 0);
           V3 u = get_u(ps, i, 0);
           V3 n = surf_normal(s, r); // Position::reflect, include/openmc/position.h:207-213
@@ -2867,8 +2872,18 @@ extern "C" int omcgpu_needs_extended_build(const omcgpu_model* m)
     return 0;
   for (int l = 0; l < m->n_lattices; ++l)
     if (m->lat_type && m->lat_type[l] != OMCGPU_LATTICE_RECT)
-      return 1;
-  return omc::model_creates_secondaries(m) ? 1 : 0;
+      return 1; // hexagonal lattices
+  for (int s = 0; s < m->n_surfaces; ++s) {
+    if (m->surf_type[s] >= OMCGPU_SURF_XCONE)
+      return 1; // axis cones, general quadrics
+    if (m->surf_bc[s] == OMCGPU_BC_WHITE || (m->surf_bc[s] == OMCGPU_BC_PERIODIC && m->surf_periodic_axis[s] >= 0))
+      return 1; // white and rotational periodic boundaries
+  }
+  for (int t = 0; t < m->n_tallies; ++t)
+    if (m->tally_estimator[t] == OMCGPU_ESTIMATOR_ANALOG ||
+        (m->tally_estimator[t] == OMCGPU_ESTIMATOR_COLLISION && !m->run_CE && m->survival_biasing))
+      return 1; // tallies scored after the collision from the collision records
+  return omc::model_creates_secondaries(m) ? 1 : 0; // secondary neutrons of integer yields
 }
 namespace omc {
 
@@ -2890,9 +2905,10 @@ static int check_supported(const omcgpu_model* m)
     return fail(OMCGPU_E_UNSUPPORTED, "cell density multipliers (src/cell.cpp:104-120) in a multigroup model are not "
                                       "supported on the device (continuous-energy models: resolved at omcgpu_init)%s");
   if (omcgpu_needs_extended_build(m) && !OMC_EXTENDED)
-    return fail(OMCGPU_E_UNSUPPORTED, "hexagonal lattices (src/lattice.cpp:458-1009) and secondary neutrons of integer "
-                                      "yields (src/physics.cpp:1158-1162) are compiled into libomcgpu_ext.so "
-                                      "(-DOMC_EXTENDED=1), not into this build: load that library%s");
+    return fail(OMCGPU_E_UNSUPPORTED, "hexagonal lattices, axis cones, general quadrics, white / rotational periodic "
+                                      "boundaries, analog-estimator tallies and secondary neutrons of integer yields are "
+                                      "compiled into libomcgpu_ext.so (-DOMC_EXTENDED=1), not into this build: load that "
+                                      "library (omcgpu_needs_extended_build)%s");
   for (int t = 0; t < m->n_tallies; ++t) {
     if (m->tally_n_filters[t] > OMCGPU_MAX_FILTERS || m->tally_n_scores[t] > OMCGPU_MAX_SCORES)
       return fail(OMCGPU_E_UNSUPPORTED, "tally has too many filters or scores%s");
