@@ -41,3 +41,23 @@ def test_no_cpu_fallback():
     eng = lib.Engine()
     with pytest.raises(lib.OmcGpuError, match="no CUDA device"):
         eng.init(model, 0, 1000)
+
+
+def test_which_models_need_the_extended_build():
+    """omcgpu_needs_extended_build (pure host code of the PRODUCT library, no device needed): the
+    models with hexagonal lattices, axis cones / general quadrics, white / rotational periodic
+    boundaries, analog-estimator tallies or secondary neutrons of integer yields are the ones the
+    loaders hand to libomcgpu_ext.so; everything else -- BASELINE.json's five configurations
+    among them -- runs on the default build, whose kernels carry none of that code"""
+    import ctypes as C
+    import reference_runs as rr
+    from openmc_b200 import lib as omclib
+    L = C.CDLL(omclib.DEFAULT_LIB)
+    extended = {"surface_zoo", "white_pincell", "quadric_pin", "rotational_wedge", "pincell_ce_analog",
+                "pincell_ce_analog_survival", "pincell_mg_analog", "pincell_mg_analog_survival", "hex_bundle_y",
+                "hex_bundle_x3d", "pincell_ce_n2n"}
+    for name in rr.RUNS:
+        if name in ("pwr_core_ce", "assembly_ce_density"):      # (slow to build; nothing new in them)
+            continue
+        m, libx, model, box, of, ce = rr.build(name)
+        assert bool(L.omcgpu_needs_extended_build(model.byref())) == (name in extended), name
