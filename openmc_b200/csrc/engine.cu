@@ -393,9 +393,20 @@ OMC_D void ev_xs(const PState& ps, int64_t i, int batch_min = OMC_XS_BATCH_MIN, 
     const int a = mg_angle_index(m, get_u(ps, i, n_coord - 1));
     const int ba = mg_ba(m, t, a);
     const int g = ps.g[i];
-    ps.xs_total[i] = ld(DM.mg_total + ba * G + g) * 1.0;
-    ps.xs_absorption[i] = ld(DM.mg_absorption + ba * G + g) * 1.0;
-    ps.xs_nu_fission[i] = ld(DM.mgm_fissionable + m) ? ld(DM.mg_nu_fission + ba * G + g) * 1.0 : 0.;
+    // Cell::density_mult of the particle's cell instance (src/mgxs.cpp:620-625; extended build: continuous-
+    // energy models fold it into their device materials at omcgpu_init and never come here)
+    double mult = 1.0;
+#if OMC_EXTENDED
+    if (DM.cell_density_mult != nullptr) {
+      const int c = LV(cell, n_coord - 1);
+      const int d0 = ld(DM.cell_density_ofs + c), nd = ld(DM.cell_density_ofs + c + 1) - d0;
+      if (nd > 0)
+        mult = ld(DM.cell_density_mult + d0 + (nd > 1 ? ps.cell_instance[i] : 0));
+    }
+#endif
+    ps.xs_total[i] = ld(DM.mg_total + ba * G + g) * mult;
+    ps.xs_absorption[i] = ld(DM.mg_absorption + ba * G + g) * mult;
+    ps.xs_nu_fission[i] = ld(DM.mgm_fissionable + m) ? ld(DM.mg_nu_fission + ba * G + g) * mult : 0.;
   }
 }
 
@@ -2478,7 +2489,10 @@ static int upload_model(const omcgpu_model* m)
   h.mat_base = nullptr;
   G.mat_mult.clear();
   G.temps_expanded = h.run_CE && m->n_nuclide_temps > 0;
-  h.cell_density_ofs = nullptr; // host-side input only: folded into the device materials below
+  // continuous energy: host-side input only, folded into the device materials below; multigroup: the
+  // lookup of the extended build reads them (uploaded after the geometry block)
+  const bool mg_density = !h.run_CE && has_density_multipliers(m);
+  h.cell_density_ofs = nullptr;
   h.cell_density_mult = nullptr;
   if (h.run_CE && (m->n_nuclide_temps > 0 || has_density_multipliers(m))) {
     expand_temperatures(m, X);
@@ -2610,6 +2624,12 @@ static int upload_model(const omcgpu_model* m)
 #if OMC_CUDA
     CUDA_OK(cudaMemcpyToSymbol(c_geo_blob, &G.geo_blob, sizeof(char*)));
 #endif
+  }
+  if (mg_density) {
+    h.cell_density_ofs = m->cell_density_ofs;
+    h.cell_density_mult = m->cell_density_mult;
+    UP(cell_density_ofs, nc + 1);
+    UP(cell_density_mult, m->cell_density_ofs[nc]);
   }
   const int n_mn = nm ? h.mat_nuc_ofs[nm] : 0;
   if (h.mat_base)
@@ -2883,6 +2903,8 @@ extern "C" int omcgpu_needs_extended_build(const omcgpu_model* m)
     if (m->tally_estimator[t] == OMCGPU_ESTIMATOR_ANALOG ||
         (m->tally_estimator[t] == OMCGPU_ESTIMATOR_COLLISION && !m->run_CE && m->survival_biasing))
       return 1; // tallies scored after the collision from the collision records
+  if (!m->run_CE && omc::has_density_multipliers(m))
+    return 1; // cell density multipliers of a multigroup model (continuous energy: resolved at omcgpu_init)
   return omc::model_creates_secondaries(m) ? 1 : 0; // secondary neutrons of integer yields
 }
 namespace omc {
@@ -2901,12 +2923,9 @@ static int check_supported(const omcgpu_model* m)
           m->surf_periodic_axis[s] < -1 || m->surf_periodic_axis[s] > 2))
       return fail(OMCGPU_E_UNSUPPORTED, "periodic boundary: only between two planes%s");
   }
-  if (!m->run_CE && has_density_multipliers(m))
-    return fail(OMCGPU_E_UNSUPPORTED, "cell density multipliers (src/cell.cpp:104-120) in a multigroup model are not "
-                                      "supported on the device (continuous-energy models: resolved at omcgpu_init)%s");
   if (omcgpu_needs_extended_build(m) && !OMC_EXTENDED)
     return fail(OMCGPU_E_UNSUPPORTED, "hexagonal lattices, axis cones, general quadrics, white / rotational periodic "
-                                      "boundaries, analog-estimator tallies and secondary neutrons of integer yields are "
+                                      "boundaries, analog-estimator tallies, multigroup density multipliers and secondary neutrons are "
                                       "compiled into libomcgpu_ext.so (-DOMC_EXTENDED=1), not into this build: load that "
                                       "library (omcgpu_needs_extended_build)%s");
   for (int t = 0; t < m->n_tallies; ++t) {

@@ -820,6 +820,22 @@ def build_mg_model(model: Model, lib: MGXSLibrary) -> abi.ModelHandle:
     v.update(model.flatten_geometry())
     v.update(build_mg_fields(model, lib))
     v.update(model.flatten_tallies(lib.G, lib.group_edges))
+    # cell densities -> multipliers (finalize_cell_densities, src/geometry_aux.cpp:197-211; a macroscopic
+    # material's density_gpcc_ is its one atom density with awr = 1, src/material.cpp:458-466)
+    from .model import MASS_NEUTRON, N_AVOGADRO
+    dofs = [0]; dmult = []
+    for c in model.cells:
+        if getattr(c, "density", None) is None:
+            dmult.append(1.0)
+        else:
+            if c.fill_type != "material" or c.fill is None:
+                raise ValueError(f"cell {c.id}: a density needs a (non-void) material")
+            rho_m = 1.0 if c.fill.density is None else float(c.fill.density)
+            gpcc = 0.0
+            gpcc += rho_m * 1.0 * MASS_NEUTRON / N_AVOGADRO
+            dmult += [float(r) / gpcc for r in np.atleast_1d(np.asarray(c.density, float))]
+        dofs.append(len(dmult))
+    v.update(cell_density_ofs=np.array(dofs, np.int32), cell_density_mult=np.array(dmult or [1.0]))
     # unused CE fields
     v.update(n_nuclides=0, n_log_bins=0, log_spacing=1.0, n_reactions=0, n_products=0, n_functions=0)
     return abi.ModelHandle(v)

@@ -1175,9 +1175,9 @@ void mg_calculate_xs(Particle& p)
   }
   int G = M->mg_n_groups;
   int ba = mg_ba(m, p.mg_t, p.mg_a);
-  p.xs_total = M->mg_total[ba * G + p.g] * 1.0;
-  p.xs_absorption = M->mg_absorption[ba * G + p.g] * 1.0;
-  p.xs_nu_fission = M->mgm_fissionable[m] ? M->mg_nu_fission[ba * G + p.g] * 1.0 : 0.;
+  p.xs_total = M->mg_total[ba * G + p.g] * p.density_mult; // src/mgxs.cpp:620-625
+  p.xs_absorption = M->mg_absorption[ba * G + p.g] * p.density_mult;
+  p.xs_nu_fission = M->mgm_fissionable[m] ? M->mg_nu_fission[ba * G + p.g] * p.density_mult : 0.;
 }
 
 void mg_sample_fission_energy(int m, int gin, int& dg, int& gout, uint64_t* seed, int t, int a)

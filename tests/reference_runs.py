@@ -35,6 +35,7 @@ RUNS = {
     "pincell_ce_density": (1000, 8, 3),    # cell densities (density multipliers) on the fuel rings and the moderator
     "assembly_ce_density": (1000, 6, 2),   # one density per INSTANCE of the fuel cell (distribcell offsets)
     "pincell_ce_n2n": (1000, 8, 3),        # (n,2n) reactions: secondary neutrons from integer yields
+    "c5g7_core_density": (1000, 6, 2),     # multigroup: one density per INSTANCE of the UO2 pins' fuel cell
 }
 _CACHE = {}
 
@@ -87,6 +88,15 @@ def build(name):
         library = nuclide.synthetic_library(nuclide.PINCELL_NUCLIDES, 3000, n2n=True)
         m, lib, box, of = examples.pincell_ce(n_grid=3000, mesh_dim=6, energy_bins=12, tallies=True, library=library)
         ce = True
+    elif name == "c5g7_core_density":
+        m, lib, box, of = examples.c5g7_core(mesh_dim=17)
+        m.settings["material_cell_offsets"] = 1
+        model0 = mgxs.build_mg_model(m, lib)          # (for the number of instances of the cell)
+        fuel = m.cells[0]
+        n_inst = int(m._n_instances[0])
+        fuel.density = list(1.6749 * (1.0 + 0.15 * np.cos(0.11 * np.arange(n_inst))))
+        m.cells[1].density = 1.5                       # the water around those pins: one value
+        ce = False
     elif name == "hex_bundle_y":
         m, lib, box, of = examples.hex_bundle("y")
         ce = False

@@ -55,7 +55,7 @@ def test_which_models_need_the_extended_build():
     L = C.CDLL(omclib.DEFAULT_LIB)
     extended = {"surface_zoo", "white_pincell", "quadric_pin", "rotational_wedge", "pincell_ce_analog",
                 "pincell_ce_analog_survival", "pincell_mg_analog", "pincell_mg_analog_survival", "hex_bundle_y",
-                "hex_bundle_x3d", "pincell_ce_n2n"}
+                "hex_bundle_x3d", "pincell_ce_n2n", "c5g7_core_density"}
     for name in rr.RUNS:
         if name in ("pwr_core_ce", "assembly_ce_density"):      # (slow to build; nothing new in them)
             continue

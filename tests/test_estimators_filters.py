@@ -169,20 +169,20 @@ def test_cell_density_multipliers(emu_lib, name, threshold, monkeypatch):
     _check_generation(lib.Engine(emu_lib), lambda: _analog_case(name), 1500, 1e-11)
 
 
-def test_density_multipliers_of_a_multigroup_model_are_refused(emu_lib):
-    import reference_runs as rr
-    m, libx, model, box, of, ce = rr.build("pincell_mg")
-    model["cell_density_mult"][0] = 0.9          # (in place: the handle points at this array)
+@pytest.mark.parametrize("threshold", ["0", "100000"])
+def test_cell_density_multipliers_multigroup(emu_lib, threshold, monkeypatch):
+    """Mgxs::calculate_xs scales total / absorption / nu-fission by the multiplier of the cell
+    instance (src/mgxs.cpp:620-625): read at the lookup by the extended build (one density per
+    instance of the UO2 pins' fuel cell of the C5G7-style core; the oracle equals the reference's
+    binary bit for bit on this model)"""
+    monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", threshold)
+    model = _check_generation(lib.Engine(emu_lib), lambda: _analog_case("c5g7_core_density"), 1500, 1e-11)
     eng = lib.Engine(emu_lib)
-    try:
-        with pytest.raises(lib.OmcGpuError, match="density multipliers"):
-            eng.init(model, 0, 100)
-    finally:
-        model["cell_density_mult"][0] = 1.0
+    assert eng.lib.omcgpu_needs_extended_build(model.byref()) == 1
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["pincell_ce_density", "assembly_ce_density"])
+@pytest.mark.parametrize("name", ["pincell_ce_density", "assembly_ce_density", "c5g7_core_density"])
 def test_cell_density_multipliers_on_gpu(gpu_engine, name, monkeypatch):
     monkeypatch.setenv("OMCGPU_TAIL_THRESHOLD", "2048")
     _check_generation(gpu_engine, lambda: _analog_case(name), 20000, None, exact_bank=False)

@@ -25,7 +25,8 @@ pytestmark = pytest.mark.gpu
 
 MG = ["pincell_mg", "c5g7_core", "surface_zoo", "rotated_fills", "periodic_box", "white_pincell", "quadric_pin",
       "pincell_mg_analog", "pincell_mg_analog_survival",          # analog-estimator tallies
-      "hex_bundle_y", "hex_bundle_x3d"]                           # hexagonal lattices
+      "hex_bundle_y", "hex_bundle_x3d",                           # hexagonal lattices
+      "c5g7_core_density"]                                        # cell density multipliers, multigroup
 CE = ["pincell_ce", "pincell_ce_temperatures", "assembly_ce", "pwr_core_ce", "pincell_ce_analog", "pincell_ce_analog_survival",
       "pincell_ce_density", "assembly_ce_density",                # cell density multipliers
       "pincell_ce_n2n",                                           # secondary neutrons from (n,2n)
