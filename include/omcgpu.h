@@ -112,6 +112,8 @@ extern "C" {
 #define OMCGPU_FILTER_UNIVERSE  4
 #define OMCGPU_FILTER_DISTRIBCELL 5 /* filter_idata = { cell index }; bins = instances of that cell
                                      (src/tallies/filter_distribcell.cpp:40-63) */
+#define OMCGPU_FILTER_ENERGYOUT 6 /* EnergyoutFilter (src/tallies/filter_energy.cpp:100-125): the energy / group AFTER the
+                                     collision; analog tallies only; filter_ddata = bin edges as for ENERGY */
 /* LatticeType + HexLattice::Orientation, include/openmc/lattice.h */
 #define OMCGPU_LATTICE_RECT  0
 #define OMCGPU_LATTICE_HEX_Y 1

@@ -2959,7 +2959,7 @@ OMC_HD int distribcell_bin(const PState& ps, int64_t i, int n_coord, int cell)
 // point, MeshFilter::get_all_bins src/tallies/filter_mesh.cpp:61-66; sc.g is then the
 // pre-collision group, EnergyFilter::get_all_bins src/tallies/filter_energy.cpp:62-67)
 OMC_HD bool tally_prepare(const PState& ps, int64_t i, int n_coord, int t, double E_last,
-  const ScoreCtx& sc, TallyEval& te, const V3* r_point = nullptr)
+  const ScoreCtx& sc, TallyEval& te, const V3* r_point = nullptr, double E_post = 0.0, int g_post = 0)
 {
   const int G = DM.mg_n_groups;
   te.nf = ld(DM.tally_n_filters + t);
@@ -2991,6 +2991,20 @@ OMC_HD bool tally_prepare(const PState& ps, int64_t i, int n_coord, int t, doubl
         const double* e = DM.filter_ddata + o;
         if (E_last >= ld(e) && E_last <= ld(e + nbin)) {
           te.bins[k][0] = (int)lower_bound_index(e, (int64_t)nbin + 1, E_last);
+          te.nb[k] = 1;
+        }
+      }
+      break;
+    }
+    case OMCGPU_FILTER_ENERGYOUT: { // EnergyoutFilter::get_all_bins, src/tallies/filter_energy.cpp:100-112:
+      const int nbin = ld(DM.filter_n_bins + f); // the energy / group the particle LEFT the collision with
+      if (!DM.run_CE && ld(DM.filter_matches_groups + f)) {
+        te.bins[k][0] = G - g_post - 1;
+        te.nb[k] = 1;
+      } else {
+        const double* e = DM.filter_ddata + o;
+        if (E_post >= ld(e) && E_post <= ld(e + nbin)) {
+          te.bins[k][0] = (int)lower_bound_index(e, (int64_t)nbin + 1, E_post);
           te.nb[k] = 1;
         }
       }
@@ -3282,7 +3296,7 @@ OMC_OOL void score_after_collision(const PState& ps, int64_t i, int n_coord, con
       continue;
     TallyEval te;
     sc.g = g_last; // the energy filter matches the group the particle collided in
-    if (!tally_prepare(ps, i, n_coord, t, E_last, sc, te, &r))
+    if (!tally_prepare(ps, i, n_coord, t, E_last, sc, te, &r, d[AN_E_POST * cap], n[AN_G_POST * cap]))
       continue;
     if (ld(DM.tally_estimator + t) == OMCGPU_ESTIMATOR_ANALOG) {
       tally_emit_with(te, t, 0, 1.0, an, values);

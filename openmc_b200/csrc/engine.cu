@@ -874,6 +874,7 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
   if (record) {
     an_puti(gc, ridx, AN_ALIVE, p.wgt != 0.0 ? 1 : 0);
     an_puti(gc, ridx, AN_G_POST, p.g);
+    an_put(gc, ridx, AN_E_POST, p.E);
   }
   const int n_coord = ps.n_coord[i];
   { // directions of all levels follow level 0, through the rotations of rotated fills
@@ -2935,9 +2936,19 @@ static int check_supported(const omcgpu_model* m)
         m->tally_estimator[t] != OMCGPU_ESTIMATOR_ANALOG)
       return fail(OMCGPU_E_UNSUPPORTED, "unknown tally estimator%s");
     int n_mesh = 0;
-    for (int k = 0; k < m->tally_n_filters[t]; ++k)
-      if (m->filter_type[m->tally_filters[t * OMCGPU_MAX_FILTERS + k]] == OMCGPU_FILTER_MESH)
+    for (int k = 0; k < m->tally_n_filters[t]; ++k) {
+      const int ft = m->filter_type[m->tally_filters[t * OMCGPU_MAX_FILTERS + k]];
+      if (ft == OMCGPU_FILTER_MESH)
         ++n_mesh;
+      if (ft == OMCGPU_FILTER_ENERGYOUT) {
+        if (m->tally_estimator[t] != OMCGPU_ESTIMATOR_ANALOG)
+          return fail(OMCGPU_E_UNSUPPORTED, "an energyout filter needs the analog estimator%s");
+        for (int sidx = 0; sidx < m->tally_n_scores[t]; ++sidx)
+          if (m->tally_scores[t * OMCGPU_MAX_SCORES + sidx] == OMCGPU_SCORE_NU_FISSION)
+            return fail(OMCGPU_E_UNSUPPORTED, "nu-fission with an energyout filter (score_fission_eout, "
+                                              "src/tallies/tally_scoring.cpp:383-470) is not supported on the device%s");
+      }
+    }
     if (n_mesh > 1)
       return fail(OMCGPU_E_UNSUPPORTED, "more than one mesh filter per tally%s");
   }

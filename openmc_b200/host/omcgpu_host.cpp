@@ -808,8 +808,9 @@ void flatten_tallies(Flat& F)
       usable[i] = f->type() == FilterType::MESH && !p->translated_ &&
                   dynamic_cast<const RegularMesh*>(model::meshes[p->mesh_].get()) != nullptr;
     } else if (auto p = dynamic_cast<const EnergyFilter*>(f)) {
-      ftype[i] = OMCGPU_FILTER_ENERGY;
-      usable[i] = f->type() == FilterType::ENERGY;
+      // EnergyoutFilter derives from EnergyFilter: same bins, matched on the post-collision energy
+      ftype[i] = f->type() == FilterType::ENERGY_OUT ? OMCGPU_FILTER_ENERGYOUT : OMCGPU_FILTER_ENERGY;
+      usable[i] = f->type() == FilterType::ENERGY || f->type() == FilterType::ENERGY_OUT;
       fmg[i] = p->matches_transport_groups_ ? 1 : 0;
       for (double e : p->bins_) {
         fd.push_back(e);

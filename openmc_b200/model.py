@@ -164,7 +164,7 @@ class Mesh:
 @dataclass
 class Filter:
     id: int
-    type: str                          # 'mesh' 'energy' 'cell' 'material' 'universe' 'distribcell'
+    type: str                          # 'mesh' 'energy' 'energyout' 'cell' 'material' 'universe' 'distribcell'
     bins: object                       # mesh id | energy edges | list of ids | [cell id]
 
 
@@ -757,8 +757,8 @@ class Model:
                 ftype[i] = abi.OMCGPU_FILTER_MESH
                 fmesh[i] = mesh_index[f.bins]
                 fnb[i] = int(np.prod(self.meshes[fmesh[i]].dimension))
-            elif f.type == "energy":
-                ftype[i] = abi.OMCGPU_FILTER_ENERGY
+            elif f.type in ("energy", "energyout"):
+                ftype[i] = abi.OMCGPU_FILTER_ENERGY if f.type == "energy" else abi.OMCGPU_FILTER_ENERGYOUT
                 edges = [float(e) for e in f.bins]
                 fnb[i] = len(edges) - 1
                 fd += edges; fi += [0] * len(edges)
@@ -818,7 +818,7 @@ class Model:
             if f.type == "mesh":
                 m = [m for m in self.meshes if m.id == f.bins][0]
                 nb *= int(np.prod(m.dimension))
-            elif f.type == "energy":
+            elif f.type in ("energy", "energyout"):
                 nb *= len(f.bins) - 1
             elif f.type == "distribcell":
                 nb *= int(self._n_instances[self._c_index[f.bins[0]]])

@@ -1985,6 +1985,17 @@ void filter_get_all_bins(int f, Particle& p, Match& match, bool tracklength = tr
     }
     break;
   }
+  case OMCGPU_FILTER_ENERGYOUT: { // EnergyoutFilter::get_all_bins, src/tallies/filter_energy.cpp:100-125
+    int nb = M->filter_n_bins[f];
+    if (!M->run_CE && M->filter_matches_groups[f]) {
+      match.bins.push_back(M->mg_n_groups - p.g - 1);
+      match.weights.push_back(1.0);
+    } else if (p.E >= ddata[0] && p.E <= ddata[nb]) {
+      match.bins.push_back(lower_bound_index(ddata, ddata + nb + 1, p.E));
+      match.weights.push_back(1.0);
+    }
+    break;
+  }
   case OMCGPU_FILTER_CELL:
     for (int i = 0; i < p.n_coord; i++) {
       int b = idata[p.coord[i].cell];

@@ -199,7 +199,7 @@ def tallies_elements(m) -> list:
     for f in m.filters:
         if f.type == "mesh":
             bins = str(int(f.bins))
-        elif f.type == "energy":
+        elif f.type in ("energy", "energyout"):
             bins = _fmt(f.bins)
         else:
             bins = " ".join(str(int(b)) for b in f.bins)

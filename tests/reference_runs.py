@@ -65,6 +65,11 @@ def build(name):
         m.tallies.append(Tally(nt + 1, [nf + 1, energy_f.id], six, estimator="analog"))
         m.tallies.append(Tally(nt + 2, [mesh_f.id], ["flux", "nu-fission", "scatter"], estimator="analog"))
         m.tallies.append(Tally(nt + 3, [nf + 1], six, estimator="collision"))
+        # a scattering matrix: incoming x outgoing energy (EnergyoutFilter: the energy after the collision)
+        eo = [1.0e-5, 0.625, 1.0e3, 1.0e5, 20.0e6] if ce else sorted(lib.group_edges)
+        m.filters.append(Filter(nf + 2, "energy", eo))
+        m.filters.append(Filter(nf + 3, "energyout", eo))
+        m.tallies.append(Tally(nt + 4, [nf + 2, nf + 3], ["scatter"], estimator="analog"))
         if name.endswith("_survival"):
             m.settings["survival_biasing"] = 1
     elif name == "pincell_ce_density":
