@@ -223,6 +223,6 @@ struct GenCtx {
 constexpr int SEC_ND = 9;
 enum { AN_RX, AN_RY, AN_RZ, AN_E_LAST, AN_WGT_LAST, AN_WGT_BANK, AN_MICRO_T, AN_MICRO_A, AN_MICRO_F, AN_MICRO_NF,
   AN_XS_T, AN_XS_A, AN_XS_F, AN_XS_NF, AN_E_POST, AN_ND };
-enum { AN_SCATTER, AN_FISSION, AN_ALIVE, AN_G_LAST, AN_G_POST, AN_MATERIAL, AN_MG_BA, AN_NI };
+enum { AN_SCATTER, AN_FISSION, AN_ALIVE, AN_G_LAST, AN_G_POST, AN_MATERIAL, AN_MG_BA, AN_FIS_BASE, AN_NI };
 
 } // namespace omc

@@ -2172,6 +2172,7 @@ OMC_HD void collision_mg(Collider& p, int ba, const GenCtx& gc, const Bank& fb)
       }
       if (an_on(gc) && k > 0) { // p.fission(), p.wgt_bank() = sites stored / weight, src/physics_mg.cpp:223-233
         an_puti(gc, an_index(p, gc), AN_FISSION, 1);
+        an_puti(gc, an_index(p, gc), AN_FIS_BASE, base); // p.nu_bank(): the k sites from this slot on
         an_put(gc, an_index(p, gc), AN_WGT_BANK, (double)k);
       }
     }
@@ -2317,6 +2318,7 @@ OMC_HD void collision_ce(Collider& p, const GenCtx& gc, const Bank& fb, bool& no
       }
       if (an_on(gc) && k > 0) { // p.fission(), p.wgt_bank() = sites stored / weight, src/physics.cpp:268-281
         an_puti(gc, an_index(p, gc), AN_FISSION, 1);
+        an_puti(gc, an_index(p, gc), AN_FIS_BASE, base); // p.nu_bank(): the k sites from this slot on
         an_put(gc, an_index(p, gc), AN_WGT_BANK, (double)k);
       }
     }
@@ -3102,9 +3104,14 @@ struct AnalogScore {
   double micro_t, micro_a, micro_f, micro_nf; // of the nuclide collided with (CE)
   double mg_fis_over_abs, mg_nufis_over_abs;  // table values at (angle, temperature, p_g) (MG)
   bool scatter, fission;                      // p.event() == SCATTER, p.fission()
+  bool eout;                                  // the tally has an EnergyoutFilter: nu-fission goes site by site
   OMC_D double operator()(int score, bool& skip) const
   {
     skip = false;
+    if (eout && score == OMCGPU_SCORE_NU_FISSION) { // score_fission_eout (score_after_collision), or nothing
+      skip = true;
+      return 0.0;
+    }
     const bool sb = DM.survival_biasing != 0;
     if (DM.run_CE) {
       const double wgt_absorb = sb ? wgt_last * micro_a / micro_t : 0.0;
@@ -3252,7 +3259,7 @@ OMC_OOL void score_collision(const PState& ps, int64_t i, int n_coord, V3 r, dou
 // score_analog_tally_ce / _mg (src/tallies/tally_scoring.cpp:2314-2414) and, for the case above,
 // score_collision_tally, from the record the collision left for particle idx
 OMC_OOL void score_after_collision(const PState& ps, int64_t i, int n_coord, const GenCtx& gc, int64_t idx,
-  double* values)
+  double* values, const double* bank_E)
 {
   const double* d = gc.an_d + idx;
   const int32_t* n = gc.an_i + idx;
@@ -3283,6 +3290,7 @@ OMC_OOL void score_after_collision(const PState& ps, int64_t i, int n_coord, con
   an.micro_nf = d[AN_MICRO_NF * cap];
   an.scatter = n[AN_SCATTER * cap] != 0;
   an.fission = n[AN_FISSION * cap] != 0;
+  an.eout = false;
   an.mg_fis_over_abs = an.mg_nufis_over_abs = 0.0;
   if (!DM.run_CE) {
     const int G = DM.mg_n_groups;
@@ -3299,7 +3307,54 @@ OMC_OOL void score_after_collision(const PState& ps, int64_t i, int n_coord, con
     if (!tally_prepare(ps, i, n_coord, t, E_last, sc, te, &r, d[AN_E_POST * cap], n[AN_G_POST * cap]))
       continue;
     if (ld(DM.tally_estimator + t) == OMCGPU_ESTIMATOR_ANALOG) {
+      int eo_pos = -1; // tally.energyout_filter_
+      for (int k = 0; k < te.nf; ++k)
+        if (ld(DM.filter_type + ld(DM.tally_filters + OMCGPU_MAX_FILTERS * t + k)) == OMCGPU_FILTER_ENERGYOUT)
+          eo_pos = k;
+      an.eout = eo_pos >= 0;
       tally_emit_with(te, t, 0, 1.0, an, values);
+      // score_fission_eout, src/tallies/tally_scoring.cpp:383-470: nu-fission of a tally with an
+      // EnergyoutFilter, once per fission site banked in this collision (the wgt_bank sites of the
+      // fission bank from AN_FIS_BASE on), into the outgoing-energy bin of that site
+      if (eo_pos >= 0 && (DM.survival_biasing || an.fission) && an.fission && !(DM.run_CE && sc.xs_fission == 0)) {
+        const int ns = ld(DM.tally_n_scores + t);
+        const int fe = ld(DM.tally_filters + OMCGPU_MAX_FILTERS * t + eo_pos);
+        const double* eb = DM.filter_ddata + ld(DM.filter_data_ofs + fe);
+        const int neb = ld(DM.filter_n_bins + fe);
+        const int base = n[AN_FIS_BASE * cap], n_bank = (int)an.wgt_bank;
+        double* results = values + ld(DM.tally_result_ofs + t);
+        for (int s = 0; s < ns; ++s) {
+          if (ld(DM.tally_scores + OMCGPU_MAX_SCORES * t + s) != OMCGPU_SCORE_NU_FISSION)
+            continue;
+          for (int b = 0; b < n_bank; ++b) {
+            const double E_site = bank_E[base + b];
+            int bin_out;
+            if (!DM.run_CE && ld(DM.filter_matches_groups + fe)) {
+              bin_out = neb - (int)E_site - 1;
+            } else {
+              const double E_out = DM.run_CE ? E_site : ld(DM.mg_energy_bin_avg + (int)E_site);
+              if (E_out < ld(eb) || E_out > ld(eb + neb))
+                continue;
+              bin_out = (int)lower_bound_index(eb, (int64_t)neb + 1, E_out);
+            }
+            // the other filters' matches as tally_emit_with walks them
+            int n0 = te.nf > 0 ? (eo_pos == 0 ? 1 : te.nb[0]) : 1, n1 = te.nf > 1 ? (eo_pos == 1 ? 1 : te.nb[1]) : 1,
+                n2 = te.nf > 2 ? (eo_pos == 2 ? 1 : te.nb[2]) : 1;
+            for (int a = 0; a < n0; ++a)
+              for (int bb = 0; bb < n1; ++bb)
+                for (int c = 0; c < n2; ++c) {
+                  int64_t index = 0;
+                  if (te.nf > 0)
+                    index += (int64_t)(eo_pos == 0 ? bin_out : te.bins[0][a]) * te.stride[0];
+                  if (te.nf > 1)
+                    index += (int64_t)(eo_pos == 1 ? bin_out : te.bins[1][bb]) * te.stride[1];
+                  if (te.nf > 2)
+                    index += (int64_t)(eo_pos == 2 ? bin_out : te.bins[2][c]) * te.stride[2];
+                  tally_add(results + index * ns + s, gc.keff * 1.0, false); // keff * site weight (1 / weight)
+                }
+          }
+        }
+      }
     } else {
       sc.g = p_g;
       tally_emit(te, t, 0, 1.0, sc, values);

@@ -896,7 +896,7 @@ OMC_D bool ev_collide(const PState& ps, const GenCtx& gc, const Bank& fb, int64_
   ps.k_abs[i] = p.k_abs;
   ps.material_last[i] = C_NONE;
   if (SCORE && record)
-    score_after_collision(ps, i, n_coord, gc, ridx, score_values(gc));
+    score_after_collision(ps, i, n_coord, gc, ridx, score_values(gc), fb.E);
   return ev_revive(ps, gc, i);
 }
 
@@ -1097,7 +1097,7 @@ OMC_D void body_after_collision_score(int64_t tid, const EvArgs& a)
   if (tid >= *a.q_in.count)
     return;
   const int32_t i = list_item(a.q_in, tid);
-  score_after_collision(a.ps, i, a.ps.n_coord[i], a.gc, a.ps.id_shift + i, score_values(a.gc));
+  score_after_collision(a.ps, i, a.ps.n_coord[i], a.gc, a.ps.id_shift + i, score_values(a.gc), a.fb.E);
 }
 OMC_KERNEL(k_after_collision_score, EvArgs, body_after_collision_score)
 #define LAUNCH_AFTER_COLLISION_SCORE(n_ub, stream, args) \
@@ -2943,10 +2943,6 @@ static int check_supported(const omcgpu_model* m)
       if (ft == OMCGPU_FILTER_ENERGYOUT) {
         if (m->tally_estimator[t] != OMCGPU_ESTIMATOR_ANALOG)
           return fail(OMCGPU_E_UNSUPPORTED, "an energyout filter needs the analog estimator%s");
-        for (int sidx = 0; sidx < m->tally_n_scores[t]; ++sidx)
-          if (m->tally_scores[t * OMCGPU_MAX_SCORES + sidx] == OMCGPU_SCORE_NU_FISSION)
-            return fail(OMCGPU_E_UNSUPPORTED, "nu-fission with an energyout filter (score_fission_eout, "
-                                              "src/tallies/tally_scoring.cpp:383-470) is not supported on the device%s");
       }
     }
     if (n_mesh > 1)

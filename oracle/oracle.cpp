@@ -222,6 +222,7 @@ struct Particle {
   int64_t n_event {0};
   int n_collision {0};
   std::vector<omcgpu_site> secondary_bank; // Particle::create_secondary, src/particle.cpp:75-93
+  std::vector<omcgpu_site> nu_bank;        // the fission sites banked in THIS collision (p.nu_bank(), score_fission_eout)
   bool fission {false};
   // what the analog estimator reads after a collision (src/tallies/tally_scoring.cpp:1116-1330, 1622-1990)
   bool event_scatter {false};  // p.event() == TallyEvent::SCATTER
@@ -1320,6 +1321,7 @@ void mg_create_fission_sites(Particle& p)
     nu++;
   if (nu == 0)
     return;
+  p.nu_bank.clear();
   p.fission = true;
   int n_sites_stored;
   for (n_sites_stored = 0; n_sites_stored < nu; n_sites_stored++) {
@@ -1353,6 +1355,7 @@ void mg_create_fission_sites(Particle& p)
       p.n_progeny--;
       break;
     }
+    p.nu_bank.push_back(site);
     p.delayed_group = dg + 1;
   }
   if (n_sites_stored == 0) {
@@ -1642,6 +1645,7 @@ void ce_create_fission_sites(Particle& p, int i_nuclide, int rx, const MicroXS& 
     ++nu;
   if (nu == 0)
     return;
+  p.nu_bank.clear();
   p.fission = true;
   int n_sites_stored;
   for (n_sites_stored = 0; n_sites_stored < nu; n_sites_stored++) {
@@ -1662,6 +1666,7 @@ void ce_create_fission_sites(Particle& p, int i_nuclide, int rx, const MicroXS& 
       p.n_progeny--;
       break;
     }
+    p.nu_bank.push_back(site);
   }
   if (n_sites_stored == 0) {
     p.fission = false;
@@ -2104,6 +2109,11 @@ void score_tallies(Particle& p, double flux, int estimator)
     int ns = M->tally_n_scores[t];
     const int32_t* scores = M->tally_scores + OMCGPU_MAX_SCORES * t;
     double* results = RS.tally_values.data() + M->tally_result_ofs[t];
+    int eo_pos = -1; // tally.energyout_filter_
+    for (int i = 0; i < nf; ++i)
+      if (M->filter_type[filt[i]] == OMCGPU_FILTER_ENERGYOUT)
+        eo_pos = i;
+    const bool skip_all_eout = false;
     int ibin[OMCGPU_MAX_FILTERS] = {0, 0, 0};
     while (true) {
       int64_t index = 0;
@@ -2268,6 +2278,39 @@ void score_tallies(Particle& p, double flux, int estimator)
               (m >= 0 && M->mgm_fissionable[m]) ? flux * M->mg_nu_fission[ba * G + p_g] : flux * 0.;
             break;
           }
+        }
+        // score_fission_eout, :383-470: nu-fission of a tally with an EnergyoutFilter is scored once per
+        // fission site banked in this collision, into the outgoing-energy bin of THAT site
+        if (analog && scores[s] == OMCGPU_SCORE_NU_FISSION && eo_pos >= 0 && !skip_all_eout &&
+            (M->survival_biasing || p.fission)) {
+          if (!(M->run_CE ? p.xs_fission == 0 : false)) { // (CE: `if (p.macro_xs().fission == 0) continue;` comes first)
+            const int fe = filt[eo_pos];
+            const double* eb = M->filter_ddata + M->filter_data_ofs[fe];
+            const int neb = M->filter_n_bins[fe];
+            const int n_bank = p.fission ? (int)p.nu_bank.size() : 0; // p.n_bank(): reset after every collision
+            for (int b = 0; b < n_bank; ++b) {
+              const omcgpu_site& site = p.nu_bank[b];
+              const double sc_site = RS.keff * site.wgt;
+              int bin_out;
+              if (!M->run_CE && M->filter_matches_groups[fe]) {
+                bin_out = neb - static_cast<int>(site.E) - 1;
+              } else {
+                const double E_out = M->run_CE ? site.E : M->mg_energy_bin_avg[static_cast<int>(site.E)];
+                if (E_out < eb[0] || E_out > eb[neb])
+                  continue;
+                bin_out = lower_bound_index(eb, eb + neb + 1, E_out);
+              }
+              int64_t idx2 = 0;
+              double w2 = 1.;
+              for (int i = 0; i < nf; ++i) {
+                const Match& mt = matches[filt[i]];
+                idx2 += (int64_t)(i == eo_pos ? bin_out : mt.bins[ibin[i]]) * strides[i];
+                w2 *= mt.weights[ibin[i]];
+              }
+              results[idx2 * ns + s] += sc_site * w2;
+            }
+          }
+          continue;
         }
         if (!skip)
           results[index * ns + s] += score * weight;

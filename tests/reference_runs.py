@@ -69,7 +69,7 @@ def build(name):
         eo = [1.0e-5, 0.625, 1.0e3, 1.0e5, 20.0e6] if ce else sorted(lib.group_edges)
         m.filters.append(Filter(nf + 2, "energy", eo))
         m.filters.append(Filter(nf + 3, "energyout", eo))
-        m.tallies.append(Tally(nt + 4, [nf + 2, nf + 3], ["scatter"], estimator="analog"))
+        m.tallies.append(Tally(nt + 4, [nf + 2, nf + 3], ["scatter", "nu-fission"], estimator="analog"))
         if name.endswith("_survival"):
             m.settings["survival_biasing"] = 1
     elif name == "pincell_ce_density":
