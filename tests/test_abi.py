@@ -3,6 +3,8 @@ include/omcgpu.h declares, and refuses to run without a CUDA device."""
 import ctypes as C
 import re
 
+import numpy as np
+
 import pytest
 
 from openmc_b200 import _abi as abi
@@ -61,3 +63,23 @@ def test_which_models_need_the_extended_build():
             continue
         m, libx, model, box, of, ce = rr.build(name)
         assert bool(L.omcgpu_needs_extended_build(model.byref())) == (name in extended), name
+
+
+def test_descriptions_flattened_before_a_field_existed_keep_their_meaning():
+    """tests/golden/*.npz were flattened before lat_type, cell_density_*, surf_periodic_axis and
+    tally_estimator joined omcgpu_model: ModelHandle fills in what their absence meant
+    (rectangular lattices, no density multipliers, translational periodicity, tracklength
+    tallies) with arrays of the model's own sizes -- not one zero the library would read past"""
+    m, libx, model, box, of, ce = __import__("reference_runs").build("c5g7_core")
+    values = {k: model[k] for k, *_ in abi.STRUCTS["omcgpu_model"]}
+    for k in ("lat_type", "cell_density_ofs", "cell_density_mult", "surf_periodic_axis", "tally_estimator"):
+        values.pop(k)
+    old = abi.ModelHandle(values)
+    nl, nc, ns, nt = (int(model[k]) for k in ("n_lattices", "n_cells", "n_surfaces", "n_tallies"))
+    assert old["lat_type"].size == nl and not old["lat_type"].any()
+    assert np.array_equal(old["cell_density_ofs"], np.arange(nc + 1)) and np.all(old["cell_density_mult"] == 1.0)
+    assert old["surf_periodic_axis"].size == ns and np.all(old["surf_periodic_axis"] == -1)
+    assert old["tally_estimator"].size == nt and np.all(old["tally_estimator"] == abi.OMCGPU_ESTIMATOR_TRACKLENGTH)
+    import ctypes as C
+    from openmc_b200 import lib as omclib
+    assert C.CDLL(omclib.DEFAULT_LIB).omcgpu_needs_extended_build(old.byref()) == 0
