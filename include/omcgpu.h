@@ -511,6 +511,14 @@ int64_t omcgpu_lost_particles(double* records, int64_t capacity);
 int omcgpu_needs_extended_build(const omcgpu_model* model);
 int omcgpu_get_fission_bank(omcgpu_site* fission_bank, int64_t capacity, int64_t* n);
 
+/* Mesh::count_sites (src/mesh.cpp:941-997) over the fission bank the last generation left ON THE
+ * DEVICE: the weight of the sites in every bin of a regular mesh (n_dim axes: shape, lower_left,
+ * width), *sites_outside = 1 if some site lies outside it.  shannon_entropy (src/eigenvalue.cpp:579-607)
+ * reads simulation::fission_bank, which stays on the device in the drop-in: the glue gets the
+ * counts here and finishes the sum as the reference does.  Valid until the next generation starts. */
+int omcgpu_count_fission_sites(int32_t n_dim, const int32_t* shape, const double* lower_left, const double* width,
+  double* counts, int64_t n_bins, int32_t* sites_outside);
+
 /* Uniform-comb resampling of the (sorted, device-resident) fission bank into
  * the device-resident source bank -- the sampling half of synchronize_bank()
  * (src/eigenvalue.cpp:152-178).  `start`/`total` are this rank's offset in and

@@ -1891,6 +1891,34 @@ OMC_D void body_reduce(int64_t tid, const ReduceArgs& a)
 }
 OMC_KERNEL(k_reduce, ReduceArgs, body_reduce)
 
+// ---- Mesh::count_sites over a bank (Shannon entropy), src/mesh.cpp:941-997 -----------------------
+struct CountArgs {
+  Bank bank;
+  int64_t n;
+  int32_t nd, shape[3];
+  double ll[3], w[3];
+  double* counts;
+  int32_t* outside;
+};
+OMC_D void body_count_sites(int64_t tid, const CountArgs& a)
+{
+  if (tid >= a.n)
+    return;
+  const double r[3] = {a.bank.x[tid], a.bank.y[tid], a.bank.z[tid]};
+  int bin = 0, cells = 1;
+  for (int k = 0; k < a.nd; ++k) { // StructuredMesh::get_bin :874-929
+    const int idx = mesh_index(r[k], a.ll[k], a.w[k]);
+    if (idx < 1 || idx > a.shape[k]) {
+      *a.outside = 1;
+      return;
+    }
+    bin += (idx - 1) * cells;
+    cells *= a.shape[k];
+  }
+  atomic_add_f64(a.counts + bin, a.bank.wgt[tid]);
+}
+OMC_KERNEL(k_count_sites, CountArgs, body_count_sites)
+
 // ---- fold the replicas of the tally VALUE arrays into replica 0 --------------------
 struct FoldArgs {
   double* v;
@@ -3743,6 +3771,61 @@ int omcgpu_sweep_kind(void)
   if (!G.ready)
     return -1;
   return G.sweep_mode == 2 ? 2 : (G.fuse_xs ? 1 : 0);
+}
+
+int omcgpu_count_fission_sites(int32_t n_dim, const int32_t* shape, const double* lower_left, const double* width,
+  double* counts, int64_t n_bins, int32_t* sites_outside)
+{
+  if (!G.ready)
+    return fail(OMCGPU_E_UNASSIGNED, "omcgpu_init has not been called%s");
+  if (n_dim < 1 || n_dim > 3 || !shape || !lower_left || !width || !counts || !sites_outside)
+    return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_count_fission_sites: bad arguments%s");
+  int64_t bins = 1;
+  for (int k = 0; k < n_dim; ++k)
+    bins *= shape[k];
+  if (bins != n_bins || bins < 1)
+    return fail(OMCGPU_E_INVALID_ARGUMENT, "omcgpu_count_fission_sites: n_bins does not match the mesh shape%s");
+  CountArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.bank = G.fis;
+  a.n = G.n_fis;
+  a.nd = n_dim;
+  for (int k = 0; k < n_dim; ++k) {
+    a.shape[k] = shape[k];
+    a.ll[k] = lower_left[k];
+    a.w[k] = width[k];
+  }
+  double* d_counts = nullptr;
+  int32_t* d_out = nullptr;
+#if OMC_CUDA
+  if (cudaMalloc((void**)&d_counts, bins * sizeof(double)) != cudaSuccess ||
+      cudaMalloc((void**)&d_out, sizeof(int32_t)) != cudaSuccess) {
+    cudaFree(d_counts);
+    return fail(OMCGPU_E_ALLOCATE, "omcgpu_count_fission_sites: cudaMalloc failed%s");
+  }
+  cudaMemsetAsync(d_counts, 0, bins * sizeof(double), G.stream);
+  cudaMemsetAsync(d_out, 0, sizeof(int32_t), G.stream);
+#else
+  d_counts = counts;
+  std::memset(counts, 0, bins * sizeof(double));
+  *sites_outside = 0;
+  d_out = sites_outside;
+#endif
+  a.counts = d_counts;
+  a.outside = d_out;
+  OMC_LAUNCH(k_count_sites, a.n, G.stream, a);
+#if OMC_CUDA
+  cudaError_t e = cudaMemcpyAsync(counts, d_counts, bins * sizeof(double), cudaMemcpyDeviceToHost, G.stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(sites_outside, d_out, sizeof(int32_t), cudaMemcpyDeviceToHost, G.stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(G.stream);
+  cudaFree(d_counts);
+  cudaFree(d_out);
+  if (e != cudaSuccess)
+    return fail(OMCGPU_E_CUDA, "omcgpu_count_fission_sites: %s", cudaGetErrorString(e));
+#endif
+  return 0;
 }
 
 int64_t omcgpu_lost_particles(double* records, int64_t capacity)

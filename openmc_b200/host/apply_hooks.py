@@ -1,4 +1,4 @@
-"""Make the four edits of INTEGRATION.md to COPIES of the reference's src/simulation.cpp and
+"""Make the five edits of INTEGRATION.md to COPIES of the reference's src/simulation.cpp and
 src/finalize.cpp (the reference tree itself is read-only and is never modified; the copies go to
 a build directory that is not under version control).
 
@@ -39,6 +39,9 @@ def main(src, out):
     # finalize_generation: the device has sorted and combed the bank
     s = edit(s, "sort_fission_bank();", 0, ["if (!gpu::bank_synchronized())", "  sort_fission_bank();"], p)
     s = edit(s, "synchronize_bank();", 0, ["if (!gpu::bank_synchronized())", "  synchronize_bank();"], p)
+    # ... and the fission bank stayed there: its Shannon entropy comes from the device's site counts
+    s = edit(s, "shannon_entropy();", 0,
+             ["{", "  if (gpu::bank_synchronized())", "    gpu::shannon_entropy();", "  else", "    shannon_entropy();", "}"], p)
     s = edit(s, '#include "openmc/simulation.h"', 0, ['#include "openmc/simulation.h"', INCLUDE.rstrip("\n")], p)
     open(os.path.join(out, "simulation.cpp"), "w").write(s)
 

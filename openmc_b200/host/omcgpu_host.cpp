@@ -935,6 +935,7 @@ struct Api {
   int (*host_unregister)(void*) = nullptr;
   int64_t (*lost_particles)(double*, int64_t) = nullptr;
   int (*needs_extended_build)(const omcgpu_model*) = nullptr;
+  int (*count_fission_sites)(int32_t, const int32_t*, const double*, const double*, double*, int64_t, int32_t*) = nullptr;
 } api;
 bool g_ready = false;
 std::vector<double> g_values;
@@ -977,6 +978,7 @@ void load_library()
   bind(api.host_unregister, "omcgpu_host_unregister");
   bind(api.lost_particles, "omcgpu_lost_particles");
   bind(api.needs_extended_build, "omcgpu_needs_extended_build");
+  bind(api.count_fission_sites, "omcgpu_count_fission_sites");
 }
 
 void check(int rc, const char* what)
@@ -1112,6 +1114,42 @@ void transport_generation()
 bool bank_synchronized()
 {
   return enabled() && g_ready;
+}
+
+// shannon_entropy, src/eigenvalue.cpp:579-607: the reference counts the sites of
+// simulation::fission_bank on the entropy mesh (Mesh::count_sites, src/mesh.cpp:941-997); in the
+// drop-in that bank never leaves the device, so the device counts (unit weights: the sums are exact
+// whatever the order) and the rest is the reference's own arithmetic
+void shannon_entropy()
+{
+  const RegularMesh* mesh = simulation::entropy_mesh;
+  const int nd = mesh->n_dimension_;
+  int32_t shape[3] = {1, 1, 1};
+  double ll[3] = {0, 0, 0}, w[3] = {1, 1, 1};
+  int64_t n_bins = 1;
+  for (int k = 0; k < nd; ++k) {
+    shape[k] = mesh->shape_[k];
+    ll[k] = mesh->lower_left_[k];
+    w[k] = mesh->width_[k];
+    n_bins *= shape[k];
+  }
+  std::vector<double> p(n_bins, 0.0);
+  int32_t sites_outside = 0;
+  check(api.count_fission_sites(nd, shape, ll, w, p.data(), n_bins, &sites_outside), "omcgpu_count_fission_sites");
+  if (sites_outside && mpi::master)
+    warning("Fission source site(s) outside of entropy box.");
+  if (mpi::master) {
+    double total = 0.0; // xt::sum(p)
+    for (double x : p)
+      total += x;
+    double H = 0.0;
+    for (double x : p) {
+      const double p_i = x / total;
+      if (p_i > 0.0)
+        H -= p_i * std::log2(p_i);
+    }
+    simulation::entropy.push_back(H);
+  }
 }
 
 void simulation_finalize()

@@ -31,6 +31,8 @@ void simulation_init();
 void transport_generation();
 //! true: sort_fission_bank() / synchronize_bank() of this generation were done on the device
 bool bank_synchronized();
+// shannon_entropy (src/eigenvalue.cpp:579-607) over the fission bank that stayed on the device
+void shannon_entropy();
 void simulation_finalize();
 
 } // namespace gpu

@@ -101,6 +101,20 @@ class Engine:
             self._check(-n)
         return rec[:n]
 
+    def count_fission_sites(self, shape, lower_left, width):
+        """Mesh::count_sites over the device fission bank of the last generation (Shannon entropy):
+        -> (weights per mesh bin, sites_outside)"""
+        shape = np.ascontiguousarray(shape, np.int32)
+        ll = np.ascontiguousarray(lower_left, np.float64)
+        w = np.ascontiguousarray(width, np.float64)
+        counts = np.zeros(int(np.prod(shape)))
+        outside = C.c_int32(0)
+        self._check(self.lib.omcgpu_count_fission_sites(
+            C.c_int32(shape.size), shape.ctypes.data_as(C.c_void_p), ll.ctypes.data_as(C.c_void_p),
+            w.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), C.c_int64(counts.size),
+            C.byref(outside)))
+        return counts, bool(outside.value)
+
     def set_option(self, name: str, value: int):
         self._check(self.lib.omcgpu_set_option(name.encode(), C.c_int64(value)))
 

@@ -185,6 +185,11 @@ def settings_elements(m, particles, batches, inactive, box, only_fissionable, ru
         out.append(f"  <temperature_default>{float(st['temperature_default'])!r}</temperature_default>")
     if st.get("material_cell_offsets") is False:
         out.append("  <material_cell_offsets>false</material_cell_offsets>")
+    if st.get("entropy_mesh") is not None:      # (dimension, lower_left, upper_right): Shannon entropy
+        dim, ll, ur = st["entropy_mesh"]
+        out += ['  <mesh id="9001">', f"    <dimension>{' '.join(str(int(d)) for d in dim)}</dimension>",
+                f"    <lower_left>{_fmt(ll)}</lower_left>", f"    <upper_right>{_fmt(ur)}</upper_right>", "  </mesh>",
+                "  <entropy_mesh>9001</entropy_mesh>"]
     for k, v in (extra or {}).items():
         out.append(f"  <{k}>{v}</{k}>")
     return out

@@ -154,6 +154,32 @@ def test_lost_particles_are_reported_like_the_reference(dropin):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def test_shannon_entropy_of_the_device_fission_bank(dropin):
+    """an <entropy_mesh>: the reference computes the Shannon entropy of simulation::fission_bank every
+    generation (src/eigenvalue.cpp:579-607) and prints it beside k; in the drop-in that bank stays
+    on the device, which counts its sites on the mesh (omcgpu_count_fission_sites) -- the lines of
+    every generation (k AND entropy) must be the reference's, character for character"""
+    import re
+    m, lib, model, box, of, ce = rr.build("c5g7_core")
+    import copy
+    m2 = copy.deepcopy(m)
+    m2.settings["entropy_mesh"] = ((6, 6), (box[0], box[1]), (box[3], box[4]))
+    d = tempfile.mkdtemp(prefix="omc_dropin_")
+    try:
+        rr.write_inputs(d, m2, lib, box, of, ce, 600, 5, 2)
+        gpu = _run(d, dropin)
+        assert gpu.returncode == 0, gpu.stdout[-1500:] + gpu.stderr[-1500:]
+        ref = _run(d, dropin, gpu=False)
+        assert ref.returncode == 0
+        lines = lambda out: [ln for ln in out.splitlines() if re.match(r"^\s+\d+/\d+\s", ln)]
+        a, b = lines(gpu.stdout), lines(ref.stdout)
+        assert len(a) == 5 and a == b
+        assert all(len(ln.split()) >= 3 for ln in a)          # Bat./Gen., k, entropy
+        assert 0.0 < float(a[0].split()[2]) < np.log2(36) + 1e-9
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def test_event_timers_are_fed_by_the_device(dropin):
     """print_runtime (src/output.cpp:439-446) lists the event timers of an event-based run: in the
     drop-in they carry the device's per-kernel times"""

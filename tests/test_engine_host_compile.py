@@ -211,3 +211,39 @@ def test_lost_particles_are_counted_and_recorded(emu_lib):
     np.testing.assert_allclose(np.linalg.norm(rec[:, 4:7], axis=1), 1.0, rtol=1e-12)
     assert rec[:3].shape == eng.lost_particles(3).shape
     eng.finalize()
+
+
+def test_fission_sites_counted_on_a_mesh(emu_lib):
+    """Mesh::count_sites (src/mesh.cpp:941-997) over the device fission bank, what shannon_entropy
+    (src/eigenvalue.cpp:579-607) is computed from in the drop-in: equal to counting the sites the
+    host reads back, sites outside the mesh flagged"""
+    model, box, of = cases.build("mg_temperature_multi")
+    o = Oracle(model)
+    n = 3000
+    src = o.sample_initial_source(n, box, of)
+    eng = lib.Engine(emu_lib)
+    eng.init(model, 0, n)
+    gi = eng.gen_in(n, 0, 0, 1.0, False)
+    out = eng.run_generation(gi) if False else None
+    fb, out = eng.transport_generation(gi, src)
+    r = fb["r"]
+    lo, hi = r.min(axis=0) - 1e-9, r.max(axis=0) + 1e-9
+    for shape in ((4, 3, 2), (5, 5)):
+        nd = len(shape)
+        width = (hi[:nd] - lo[:nd]) / np.array(shape)
+        counts, outside = eng.count_fission_sites(shape, lo[:nd], width)
+        idx = np.ceil((r[:, :nd] - lo[:nd]) / width).astype(int)
+        want = np.zeros(shape[::-1]).reshape(-1)
+        flat = np.zeros(len(r), int)
+        cells = 1
+        for k in range(nd):
+            flat += (idx[:, k] - 1) * cells
+            cells *= shape[k]
+        np.add.at(want, flat, fb["wgt"])
+        assert not outside and np.array_equal(counts, want) and counts.sum() == out.n_fission
+    # half the box: the sites beyond it are reported, the others still counted
+    width = (hi - lo) / np.array((4, 3, 2))
+    width[0] /= 2
+    counts, outside = eng.count_fission_sites((4, 3, 2), lo, width)
+    assert outside and 0 < counts.sum() < out.n_fission
+    eng.finalize()

@@ -145,6 +145,27 @@ def test_second_scoring_kernel_equals_the_first(gpu_engine, monkeypatch):
         np.testing.assert_allclose(b, a, rtol=1e-10, atol=1e-12 * a.max())
 
 
+def test_fission_sites_counted_on_a_mesh_on_gpu(gpu_engine):
+    """omcgpu_count_fission_sites (Mesh::count_sites for the Shannon entropy of the drop-in): the
+    device's counts equal counting the fission bank the host reads back"""
+    model, box, of = cases.build("mg_temperature_multi")
+    n = 20000
+    src = Oracle(model).sample_initial_source(n, box, of)
+    gpu_engine.init(model, 0, n)
+    gi = gpu_engine.gen_in(n, 0, 0, 1.0, False)
+    fb, out = gpu_engine.transport_generation(gi, src)
+    r = fb["r"]
+    lo, hi = r.min(axis=0) - 1e-9, r.max(axis=0) + 1e-9
+    shape = (7, 5, 3)
+    width = (hi - lo) / np.array(shape)
+    counts, outside = gpu_engine.count_fission_sites(shape, lo, width)
+    idx = np.ceil((r - lo) / width).astype(int) - 1
+    want = np.zeros(int(np.prod(shape)))
+    np.add.at(want, idx[:, 0] + shape[0] * (idx[:, 1] + shape[1] * idx[:, 2]), fb["wgt"])
+    assert not outside and np.array_equal(counts, want) and counts.sum() == out.n_fission
+    gpu_engine.finalize()
+
+
 def test_device_collision_equals_reference_vectors_on_gpu(gpu_engine):
     """collision_ce ON THE DEVICE (omcgpu_collide) against tests/golden/refcoll_ce.npz, the
     vectors the reference's collision() wrote.  Integer results (seed = the number of random
