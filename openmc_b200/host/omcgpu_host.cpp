@@ -170,6 +170,20 @@ void flatten_settings(Flat& F)
     unsupported("a run mode other than eigenvalue");
   if (settings::ufs_on || settings::weight_windows_on || settings::ifp_on)
     unsupported("uniform fission site weighting / weight windows / IFP");
+  // what the reference does per particle on the HOST while it transports it, and the device path does
+  // not do: refused by name rather than silently left out
+  if (settings::surf_source_write || settings::surf_source_read)
+    unsupported("surface source files (surf_source_write / surf_source_read)");
+  if (settings::collision_track)
+    unsupported("the collision track file");
+  if (settings::write_all_tracks || !settings::track_identifiers.empty() || settings::trace_batch > 0)
+    unsupported("particle tracks / particle tracing");
+  if (settings::check_overlaps)
+    unsupported("the cell overlap check");
+  if (settings::res_scat_on)
+    unsupported("resonance upscattering (res_scat)");
+  if (settings::time_cutoff[0] < INFTY)
+    unsupported("a neutron time cutoff");
   if (model::n_coord_levels > OMCGPU_MAX_COORD)
     unsupported("geometry nested deeper than OMCGPU_MAX_COORD levels");
 }

@@ -154,6 +154,23 @@ def test_lost_particles_are_reported_like_the_reference(dropin):
         shutil.rmtree(d, ignore_errors=True)
 
 
+@pytest.mark.parametrize("setting, word", [("track", "tracks"), ("surf_source_write", "surface source")])
+def test_host_side_per_particle_features_are_refused(dropin, setting, word):
+    """what the reference does on the host while it transports a particle (surface source banking,
+    particle tracks, the overlap check ...) the device path does not do: the run stops naming the feature
+    instead of leaving it out silently"""
+    m, lib, model, box, of, ce = rr.build("pincell_mg")
+    d = tempfile.mkdtemp(prefix="omc_dropin_")
+    try:
+        value = "1 1 1" if setting == "track" else "<surface_ids>1</surface_ids><max_particles>100</max_particles>"
+        rr.write_inputs(d, m, lib, box, of, ce, 200, 3, 1, extra={setting: value})
+        res = _run(d, dropin)
+        text = " ".join((res.stdout + res.stderr).split())
+        assert res.returncode != 0 and "not supported by the device path" in text and word in text, text[-1500:]
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def test_shannon_entropy_of_the_device_fission_bank(dropin):
     """an <entropy_mesh>: the reference computes the Shannon entropy of simulation::fission_bank every
     generation (src/eigenvalue.cpp:579-607) and prints it beside k; in the drop-in that bank stays
