@@ -950,6 +950,7 @@ struct Api {
   int64_t (*lost_particles)(double*, int64_t) = nullptr;
   int (*needs_extended_build)(const omcgpu_model*) = nullptr;
   int (*count_fission_sites)(int32_t, const int32_t*, const double*, const double*, double*, int64_t, int32_t*) = nullptr;
+  int (*update)(const omcgpu_model*, uint32_t) = nullptr;
 } api;
 bool g_ready = false;
 std::vector<double> g_values;
@@ -993,6 +994,7 @@ void load_library()
   bind(api.lost_particles, "omcgpu_lost_particles");
   bind(api.needs_extended_build, "omcgpu_needs_extended_build");
   bind(api.count_fission_sites, "omcgpu_count_fission_sites");
+  bind(api.update, "omcgpu_update");
 }
 
 void check(int rc, const char* what)
@@ -1039,6 +1041,50 @@ void simulation_init()
   g_ready = true;
 }
 
+// openmc_cell_set_temperature / openmc_material_set_density(ies) / openmc_cell_set_density
+// (include/openmc/capi.h) change the HOST model between batches -- the whole point of openmc.lib in
+// coupled calculations.  Before every generation the mutable arrays are rebuilt from model:: exactly
+// as the flattener built them (a few thousand doubles) and compared with what the device has:
+// changed temperatures / atom densities go over with omcgpu_update, anything that would change an
+// array's shape or a density multiplier (folded into the device materials at omcgpu_init) stops the
+// run by name.  No silent stale data.
+static void refresh_mutable_properties()
+{
+  Flat& F = *g_flat;
+  std::vector<double> ckt, dens, cden;
+  for (const auto& cp : model::cells) {
+    const Cell& c = *cp;
+    if (c.type_ == Fill::MATERIAL)
+      for (double x : c.sqrtkT_)
+        ckt.push_back(x);
+    for (double d : c.density_mult_)
+      cden.push_back(d);
+  }
+  for (const auto& mp : model::materials)
+    for (size_t k = 0; k < mp->nuclide_.size(); ++k)
+      dens.push_back(mp->atom_density_(k));
+  auto differs = [&](const char* name, const double* have, const std::vector<double>& now) {
+    if ((int64_t)now.size() != F.length[name])
+      fatal_error(fmt::format("OPENMC_GPU: the number of entries of {} changed after initialisation ({} -> {}): "
+                              "not supported by the device path", name, F.length[name], now.size()));
+    return std::memcmp(have, now.data(), now.size() * sizeof(double)) != 0;
+  };
+  if (differs("cell_density_mult", F.m.cell_density_mult, cden))
+    fatal_error("OPENMC_GPU: cell densities changed after initialisation: not supported by the device path "
+                "(they are folded into the device materials at omcgpu_init)");
+  uint32_t what = 0;
+  if (differs("cell_sqrtkT", F.m.cell_sqrtkT, ckt)) {
+    std::memcpy(const_cast<double*>(F.m.cell_sqrtkT), ckt.data(), ckt.size() * sizeof(double));
+    what |= OMCGPU_UPDATE_CELL_TEMPERATURES;
+  }
+  if (differs("mat_atom_density", F.m.mat_atom_density, dens)) {
+    std::memcpy(const_cast<double*>(F.m.mat_atom_density), dens.data(), dens.size() * sizeof(double));
+    what |= OMCGPU_UPDATE_MATERIAL_DENSITIES;
+  }
+  if (what)
+    check(api.update(&F.m, what), "omcgpu_update");
+}
+
 // Particle::mark_as_lost (src/particle.cpp:762-785) for the particles the device lost in this
 // generation: the warning per particle (the device keeps the state of the first
 // OMCGPU_MAX_LOST_RECORDS), the count, and the reference's abort rule.  No particle restart files:
@@ -1074,6 +1120,7 @@ void transport_generation()
 {
   if (!g_ready)
     fatal_error("OPENMC_GPU: transport_generation before simulation_init");
+  refresh_mutable_properties();
   omcgpu_gen_in in {};
   in.n_particles = simulation::work_per_rank;
   in.id_offset = simulation::work_index[mpi::rank];

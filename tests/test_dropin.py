@@ -171,6 +171,35 @@ def test_host_side_per_particle_features_are_refused(dropin, setting, word):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def test_properties_changed_through_the_c_api_reach_the_device(dropin):
+    """a coupled calculation on the reference's C API (tests/coupled_worker.py): after two batches the
+    fuel density is lowered and a cell heated through openmc_material_set_density /
+    openmc_cell_set_temperature.  The glue compares the mutable arrays with what the device holds
+    before every generation and sends the changes over (omcgpu_update): k-combined after every
+    batch equals the reference library's doing the same -- and differs from an undisturbed run"""
+    d = _inputs("pincell_ce")
+    try:
+        def run(gpu, change=True, worker="coupled_worker.py"):
+            env = dict(os.environ)
+            env.pop("OPENMC_GPU", None)
+            env.pop("COUPLED_NO_CHANGE", None)
+            if not change:
+                env["COUPLED_NO_CHANGE"] = "1"
+            if gpu:
+                env.update(OPENMC_GPU="1", OMCGPU_LIB=dropin)
+            res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", worker), GPU_LIB], cwd=d,
+                                 capture_output=True, text=True, env=env, timeout=1200)
+            assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+            line = [ln for ln in res.stdout.splitlines() if ln.startswith("KEFF")][0]
+            return [float(x) for x in line.split()[1:]]
+        k_gpu, k_ref, k_plain = run(True), run(False), run(True, change=False)
+        assert len(k_gpu) == rr.RUNS["pincell_ce"][1]
+        np.testing.assert_allclose(k_gpu, k_ref, rtol=1e-12)          # (sums in another order: last ulp)
+        assert k_gpu[:2] == k_plain[:2] and abs(k_gpu[-1] - k_plain[-1]) > 1e-4   # the change is felt
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def test_shannon_entropy_of_the_device_fission_bank(dropin):
     """an <entropy_mesh>: the reference computes the Shannon entropy of simulation::fission_bank every
     generation (src/eigenvalue.cpp:579-607) and prints it beside k; in the drop-in that bank stays
