@@ -1038,6 +1038,7 @@ void simulation_init()
   // the banks were allocated by allocate_banks() just above the hook: page-lock them so that the
   // per-generation copies are DMA transfers straight from / into them
   api.host_register(simulation::source_bank.data(), simulation::source_bank.size() * sizeof(SourceSite));
+  g_signature = structure_signature();
   g_ready = true;
 }
 
@@ -1048,8 +1049,50 @@ void simulation_init()
 // changed temperatures / atom densities go over with omcgpu_update, anything that would change an
 // array's shape or a density multiplier (folded into the device materials at omcgpu_init) stops the
 // run by name.  No silent stale data.
+// what omcgpu_init turned into device tables and omcgpu_update cannot change: cell fills / materials,
+// the tallies with their filters, scores and estimators.  openmc.lib can change all of them between
+// batches (openmc_cell_set_fill, openmc_extend_tallies, openmc_tally_set_scores ...); the device
+// would go on with the old ones, so a changed signature stops the run by name.
+static uint64_t structure_signature()
+{
+  uint64_t h = 1469598103934665603ull; // FNV-1a
+  auto mix = [&](int64_t v) {
+    for (int k = 0; k < 8; ++k) {
+      h ^= (uint64_t)(v >> (8 * k)) & 0xff;
+      h *= 1099511628211ull;
+    }
+  };
+  mix(model::cells.size());
+  for (const auto& cp : model::cells) {
+    mix((int64_t)cp->type_);
+    mix(cp->fill_);
+    mix(cp->material_.size());
+    for (int32_t m : cp->material_)
+      mix(m);
+  }
+  mix(model::tally_filters.size());
+  for (const auto& f : model::tally_filters)
+    mix(f->n_bins());
+  mix(model::tallies.size());
+  for (const auto& tp : model::tallies) {
+    mix((int64_t)tp->estimator_);
+    mix(tp->n_filter_bins_);
+    for (auto f : tp->filters())
+      mix(f);
+    for (int sc : tp->scores_)
+      mix(sc);
+    for (int nu : tp->nuclides_)
+      mix(nu);
+  }
+  return h;
+}
+static uint64_t g_signature = 0;
+
 static void refresh_mutable_properties()
 {
+  if (structure_signature() != g_signature)
+    fatal_error("OPENMC_GPU: cell fills / materials or the tallies (filters, scores, estimators) changed after "
+                "initialisation: not supported by the device path (it holds the tables omcgpu_init built)");
   Flat& F = *g_flat;
   std::vector<double> ckt, dens, cden;
   for (const auto& cp : model::cells) {
