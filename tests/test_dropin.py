@@ -88,6 +88,32 @@ def test_dropin_binary_equals_the_reference_binary(dropin, name):
                                    atol=1e-14 * ref["tally_sum_sq"].max())
 
 
+def test_several_generations_per_batch(dropin):
+    """<generations_per_batch>: the seeds of a generation come from total_gen + overall_generation()
+    (src/simulation.cpp:613-616, src/eigenvalue.cpp:152-178) and the tallies of a batch accumulate
+    over its generations -- the drop-in's statepoint equals the reference binary's"""
+    from oracle import omh5
+    m, lib, model, box, of, ce = rr.build("pincell_mg")
+    d = tempfile.mkdtemp(prefix="omc_dropin_")
+    try:
+        rr.write_inputs(d, m, lib, box, of, ce, 400, 4, 1, gen_per_batch=3)
+        out = {}
+        for gpu in (True, False):
+            res = _run(d, dropin, gpu=gpu)
+            assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+            sp = sorted(f for f in os.listdir(d) if f.startswith("statepoint"))[-1]
+            out[gpu] = rr.digest({"statepoint": omh5.File(os.path.join(d, sp))})
+        a, b = out[True], out[False]
+        assert a["k_generation"].size == 12 and np.array_equal(a["k_generation"], b["k_generation"])
+        assert np.array_equal(a["k_combined"], b["k_combined"])
+        for k in ("bank_r", "bank_E"):
+            assert np.array_equal(a[k], b[k]), k
+        np.testing.assert_allclose(a["tally_sum"], b["tally_sum"], rtol=1e-11, atol=1e-14 * b["tally_sum"].max())
+        np.testing.assert_allclose(a["tally_sum_sq"], b["tally_sum_sq"], rtol=1e-11, atol=1e-14 * b["tally_sum_sq"].max())
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def test_switch_off_is_the_reference(dropin):
     d = _inputs("pincell_mg")
     try:
