@@ -114,6 +114,33 @@ def test_several_generations_per_batch(dropin):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def test_restart_from_a_statepoint(dropin):
+    """`openmc -r statepoint.3.h5`: the reference reloads k, the tallies and the source bank and goes on
+    with batch 4 (load_state_point, src/state_point.cpp); the drop-in continues from the same state
+    -- seeds from simulation::total_gen, host source bank uploaded -- and ends where the
+    uninterrupted reference run ends"""
+    from oracle import omh5
+    m, lib, model, box, of, ce = rr.build("pincell_mg")
+    d = tempfile.mkdtemp(prefix="omc_dropin_")
+    try:
+        rr.write_inputs(d, m, lib, box, of, ce, 400, 5, 2,
+                        extra={"state_point": "<batches>3 5</batches>", "sourcepoint": "<batches>3 5</batches>"})
+        assert _run(d, dropin, gpu=False).returncode == 0           # (removes no statepoint it needs: none yet)
+        full = rr.digest({"statepoint": omh5.File(os.path.join(d, "statepoint.5.h5"))})
+        os.remove(os.path.join(d, "statepoint.5.h5"))
+        env = dict(os.environ, OPENMC_GPU="1", OMCGPU_LIB=dropin)
+        res = subprocess.run([GPU_BINARY, "-s", "1", "-r", "statepoint.3.h5"], cwd=d, capture_output=True, text=True,
+                             env=env, timeout=1200)
+        assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+        got = rr.digest({"statepoint": omh5.File(os.path.join(d, "statepoint.5.h5"))})
+        assert np.array_equal(got["k_generation"], full["k_generation"])
+        assert np.array_equal(got["bank_E"], full["bank_E"]) and np.array_equal(got["bank_r"], full["bank_r"])
+        np.testing.assert_allclose(got["k_combined"], full["k_combined"], rtol=1e-12)
+        np.testing.assert_allclose(got["tally_sum"], full["tally_sum"], rtol=1e-11, atol=1e-14 * full["tally_sum"].max())
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def test_switch_off_is_the_reference(dropin):
     d = _inputs("pincell_mg")
     try:
